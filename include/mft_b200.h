@@ -1,0 +1,183 @@
+/*
+ * mft_b200.h -- C ABI of libmft_b200.so: the B200 (sm_100a) implementation of MeshfreeTrixi.jl's
+ * semidiscrete right-hand side `rhs!` and the pieces around it.
+ *
+ * This is the drop-in boundary.  The reference's reserved plug-in point is the empty engine type
+ * `RBFFDEngineCUDA` (src/solvers/rbfsolver.jl:60-61, selected with
+ * `PointCloudSolver(basis; engine = RBFFDEngineCUDA())`, src/solvers/pointcloudsolver/types.jl:71-74).
+ * Julia methods specialised on that engine `ccall` the functions below (see INTEGRATION.md for the glue).
+ * All file:line citations are relative to the reference repository root.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MFT_E* code on failure; mft_last_error() returns a
+ *     thread-local message.  No exceptions cross the boundary.
+ *   - the caller owns every host array; the library copies during set_* calls and never keeps host pointers
+ *     (exception: MFT_MEM_HOST calls read/write the caller's arrays synchronously during the call).
+ *   - indices arrive exactly as Julia stores them: 1-based Int64.
+ *   - state arrays are SoA: `V` separate `double*` of length n_local+n_halo, i.e. StructArrays.components(u)
+ *     (allocate_nested_array, src/solvers/pointcloudsolver/rbfsolver.jl:111-116).
+ *   - a ctx is bound to one device, is not thread-safe and not re-entrant; calls are synchronous.
+ *   - there is no CPU fallback: without a usable CUDA device mft_ctx_create fails with MFT_ENODEVICE.
+ */
+#ifndef MFT_B200_H
+#define MFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mft_ctx mft_ctx;
+
+/* error codes */
+#define MFT_OK 0
+#define MFT_EINVAL (-1)   /* bad argument / call order */
+#define MFT_ECUDA (-2)    /* CUDA runtime error */
+#define MFT_ENODEVICE (-3)
+#define MFT_ENOTSUP (-4)  /* combination not implemented (e.g. residual viscosity for advection) */
+#define MFT_ENCCL (-5)
+
+/* equations: Trixi CompressibleEulerEquations2D(gamma) / LinearScalarAdvectionEquation2D(a1,a2);
+ * flux call site src/solvers/pointcloudsolver/rbfsolver.jl:259 */
+#define MFT_EQ_EULER2D 0      /* params: gamma            ; nvars = 4 */
+#define MFT_EQ_ADVECTION2D 1  /* params: a1, a2           ; nvars = 1 */
+
+/* operator slots: cache.rbf_differentiation_matrices[1:2] (rbfsolver.jl:139,162) */
+#define MFT_OP_DX 0
+#define MFT_OP_DY 1
+
+/* boundary kinds: functors of src/equations/PointCloudBCs.jl */
+#define MFT_BC_DIRICHLET 0   /* :49-63   du_b = 0, u_b = g(x,t) (value table)            */
+#define MFT_BC_SLIP_WALL 1   /* :87-106  du_b = (du1,0,0,du4), u_b = slip-projected        */
+#define MFT_BC_DO_NOTHING 2  /* :108-115                                                     */
+
+/* source kinds: callable structs of src/sources/hyperviscosity.jl */
+#define MFT_SRC_HV_FLYER 0    /* :52-64    du += -gamma * H u          params: gamma                    + matrix */
+#define MFT_SRC_HV_TOMINEC 1  /* :121-134  du += -gamma * (L'L) u      params: gamma                    + matrix */
+#define MFT_SRC_UPWIND 2      /* :351-380  params: c_uw, dx_avg                                                  */
+#define MFT_SRC_RESIDUAL 3    /* :382-409  params: c_rv, c_uw, dx_avg, polydeg                                   */
+
+#define MFT_MEM_HOST 0
+#define MFT_MEM_DEVICE 1
+
+/* options (mft_set_option) */
+#define MFT_OPT_EXACT_ORDER 0      /* 1 (default): sums in the reference's order with separate mul/add ->
+                                      bit-identical to the CSC SpMV of SparseArrays; 0: single sweep with FMAs */
+#define MFT_OPT_MEAN_DIVISOR_VN 1  /* 1 (default): ode_mean divides by V*N (recursive_length, src/auxiliary/mpi.jl:42) */
+#define MFT_OPT_MAX_LEXICOGRAPHIC 2/* 1 (default): maximum(::StructArray{SVector}) = lexicographic max (mpi.jl:71-81) */
+#define MFT_OPT_DIAGNOSTICS 3      /* 1: keep eps_uw/eps_rv/eps/eps_c/residual for mft_get_field (default 0)     */
+#define MFT_OPT_CUDA_GRAPH 4       /* 1 (default): replay mft_ssprk_step through a captured CUDA graph             */
+
+/* fields (mft_get_field): caches of create_tominec_rv_cache, hyperviscosity.jl:202-244 */
+#define MFT_FIELD_EPS 0        /* N doubles   */
+#define MFT_FIELD_EPS_UW 1     /* N doubles   */
+#define MFT_FIELD_EPS_RV 2     /* N doubles   */
+#define MFT_FIELD_EPS_C 3      /* N doubles (0,1,2) */
+#define MFT_FIELD_RESIDUAL 4   /* V*N doubles, SoA */
+#define MFT_FIELD_APPROX_DU 5  /* V*N doubles, SoA */
+#define MFT_FIELD_NORMS 6      /* V doubles: n_inf_norms of update_residual_visc! */
+
+#define MFT_SSPRK33 0
+
+const char *mft_last_error(void);
+int mft_version(void);
+int mft_device_count(void);
+
+/* ---- lifetime -------------------------------------------------------------------------------------
+ * replaces Trixi.create_cache for the CUDA engine (reference: rbfsolver.jl:130-165; parallel: parallel_rbfsolver.jl:17-54).
+ * n_local owned points followed by n_halo halo points (layout of ParallelPointCloudDomain,
+ * src/domains/PointCloudDomain/ParallelPointCloud.jl:144); n_halo = 0 on one GPU. */
+int mft_ctx_create(mft_ctx **out, int device, int64_t n_local, int64_t n_halo, int nvars, int ndims, int k);
+int mft_ctx_destroy(mft_ctx *ctx);
+
+int mft_set_equation(mft_ctx *ctx, int kind, const double *params, int nparams);
+int mft_set_option(mft_ctx *ctx, int option, double value);
+
+/* device ordering: device row d holds caller point perm1[d] (1-based).  Owned points must stay in front of
+ * halo points.  Optional; default identity.  mft_sfc_order() below produces a Hilbert ordering. */
+int mft_set_permutation(mft_ctx *ctx, const int64_t *perm1);
+/* reference summation rank of every caller point (default: its own index).  A multi-GPU caller passes global
+ * point ids so that per-row sums run in ascending GLOBAL column order like the serial CSC SpMV. */
+int mft_set_order_keys(mft_ctx *ctx, const int64_t *keys);
+
+/* operators as Julia SparseMatrixCSC{Float64,Int64} fields (colptr n+1, rowval nnz, nzval nnz; 1-based), n = n_local+n_halo.
+ * Dx and Dy must share one sparsity pattern (they do: compute_flux_operator, compute_operators.jl:443-452). */
+int mft_set_operator_csc(mft_ctx *ctx, int slot, const int64_t *colptr, const int64_t *rowval, const double *nzval);
+/* same operators as neighbour/weight tables: nbr1 (n_local x k, row-major, 1-based), wx, wy (n_local x k) */
+int mft_set_operator_ell(mft_ctx *ctx, const int64_t *nbr1, const double *wx, const double *wy);
+
+/* boundary groups, call order = NamedTuple order of `boundary_conditions` (calc_boundary_flux!, rbfsolver.jl:277-286).
+ * idx1: 1-based point indices (BoundaryData.idx), normals: nb x 2 row-major, values: Dirichlet table SoA values[v*nb+j] or NULL */
+int mft_add_boundary(mft_ctx *ctx, int kind, int64_t nb, const int64_t *idx1, const double *normals, const double *values);
+int mft_update_boundary_values(mft_ctx *ctx, int group, const double *values);
+
+/* sources, call order = order of SourceTerms(...) (calc_sources!, rbfsolver.jl:388-395).  HV kinds take their
+ * matrix (CSC as above); others pass NULLs. */
+int mft_add_source(mft_ctx *ctx, int kind, const double *params, int nparams, const int64_t *colptr,
+                   const int64_t *rowval, const double *nzval);
+
+/* builds the device layouts; called implicitly by the first compute call */
+int mft_finalize(mft_ctx *ctx);
+
+/* ---- the hot path -----------------------------------------------------------------------------------
+ * Trixi.rhs!(du,u,t,domain,...) rbfsolver.jl:397-428.  u is IN/OUT (strong BCs overwrite boundary points).
+ * MFT_MEM_HOST: u_soa/du_soa are host arrays (H2D of u, D2H of u and du inside the call).
+ * MFT_MEM_DEVICE: pointers are ignored; operates on the resident state (see mft_upload_state). */
+int mft_rhs(mft_ctx *ctx, double t, double *const *u_soa, double *const *du_soa, int mem);
+/* calc_fluxes! rbfsolver.jl:247-265: du += -Dx F(u) - Dy G(u)  (host arrays; du is accumulated into) */
+int mft_calc_fluxes(mft_ctx *ctx, double *const *u_soa, double *const *du_soa);
+/* source functor call source(du,u,t,...) for source number `index` (0-based, order of mft_add_source) */
+int mft_apply_source(mft_ctx *ctx, int index, double t, double *const *u_soa, double *const *du_soa);
+/* calc_boundary_flux! rbfsolver.jl:277-318 on host arrays (one pass) */
+int mft_boundary_pass(mft_ctx *ctx, double t, double *const *u_soa, double *const *du_soa);
+
+/* ---- resident state + time loop ---------------------------------------------------------------------- */
+int mft_upload_state(mft_ctx *ctx, const double *const *u_soa);
+int mft_download_state(mft_ctx *ctx, double *const *u_soa);
+int mft_download_du(mft_ctx *ctx, double *const *du_soa);
+/* HistoryCallback affect: modify_cache!(::SourceResidualViscosityTominec) history.jl:91-129 on the resident u.
+ * Weights from time_deriv_weights! (:131-152) are computed by the library ... */
+int mft_history_push(mft_ctx *ctx, double t, int64_t success_iter, int approx_order);
+/* ... or supplied by the caller (n weights, most recent first), so the Julia side can keep its own solve */
+int mft_history_push_weights(mft_ctx *ctx, double t, int64_t success_iter, int n, const double *weights);
+/* one SSPRK step on the resident state, FSAL structure (k=f(u_n) carried between steps), 3 rhs! per step */
+int mft_ssprk_step(mft_ctx *ctx, int scheme, double t, double dt);
+int mft_get_field(mft_ctx *ctx, int field, double *out);
+int mft_synchronize(mft_ctx *ctx);
+/* number of kernels launched by this ctx since creation (bench.py `gpu_launches`) */
+int64_t mft_launch_count(mft_ctx *ctx);
+/* CUDA-event time (ms) of kernel class `which` accumulated since the last reset; which<0 resets all. */
+int mft_kernel_time_ms(mft_ctx *ctx, int which, double *ms, int64_t *launches);
+#define MFT_K_PASS_A 0
+#define MFT_K_PASS_B 1
+#define MFT_K_REDUCE 2
+#define MFT_K_STAGE 3
+#define MFT_K_BC 4
+#define MFT_K_OTHER 5
+int mft_set_kernel_timing(mft_ctx *ctx, int enable);
+
+/* pinned host memory helpers for MFT_MEM_HOST callers */
+int mft_host_alloc(void **out, int64_t bytes);
+int mft_host_free(void *p);
+int mft_host_register(void *p, int64_t bytes);
+int mft_host_unregister(void *p);
+
+/* ---- setup helpers (host code, no GPU needed) ---------------------------------------------------------
+ * Hilbert space-filling-curve order of a 2-D cloud: perm1_out[d] = 1-based index of the d-th point along the curve. */
+int mft_sfc_order(int64_t n, const double *x, const double *y, int64_t *perm1_out);
+
+/* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------------------------------------
+ * replaces MPICache + perform_halo_update! (src/domains/PointCloudDomain/ParallelPointCloud.jl:6-71,
+ * src/auxiliary/mpi.jl:217-265) and the Allreduces of ode_mean/ode_maximum (mpi.jl:40-81). */
+int mft_nccl_unique_id(void *id128);  /* rank 0 creates, the host program broadcasts the 128 bytes */
+int mft_comm_init(mft_ctx *ctx, int nranks, int rank, const void *id128);
+/* halo plan: for each peer p (rank id peers[p]) send owned points send_idx1[send_off[p]..send_off[p+1]) (1-based,
+ * caller numbering) and receive recv_count[p] points into the halo tail, in peer order */
+int mft_set_halo(mft_ctx *ctx, int npeers, const int *peers, const int64_t *send_off, const int64_t *send_idx1,
+                 const int64_t *recv_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFT_B200_H */

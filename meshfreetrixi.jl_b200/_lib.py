@@ -1,0 +1,133 @@
+"""ctypes binding of libmft_b200.so (the C ABI declared in include/mft_b200.h).
+
+The library is the product; there is no Python/NumPy/CPU fallback.  If the shared object is missing or a call fails
+the error is raised, never papered over.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmft_b200.so")
+
+# constants of include/mft_b200.h
+EQ_EULER2D, EQ_ADVECTION2D = 0, 1
+OP_DX, OP_DY = 0, 1
+BC_DIRICHLET, BC_SLIP_WALL, BC_DO_NOTHING = 0, 1, 2
+SRC_HV_FLYER, SRC_HV_TOMINEC, SRC_UPWIND, SRC_RESIDUAL = 0, 1, 2, 3
+MEM_HOST, MEM_DEVICE = 0, 1
+OPT_EXACT_ORDER, OPT_MEAN_DIVISOR_VN, OPT_MAX_LEXICOGRAPHIC, OPT_DIAGNOSTICS, OPT_CUDA_GRAPH = 0, 1, 2, 3, 4
+FIELD_EPS, FIELD_EPS_UW, FIELD_EPS_RV, FIELD_EPS_C, FIELD_RESIDUAL, FIELD_APPROX_DU, FIELD_NORMS = range(7)
+SSPRK33 = 0
+K_PASS_A, K_PASS_B, K_REDUCE, K_STAGE, K_BC, K_OTHER = range(6)
+
+EXPORTS = [
+    "mft_last_error", "mft_version", "mft_device_count", "mft_ctx_create", "mft_ctx_destroy", "mft_set_equation",
+    "mft_set_option", "mft_set_permutation", "mft_set_order_keys", "mft_set_operator_csc", "mft_set_operator_ell",
+    "mft_add_boundary", "mft_update_boundary_values", "mft_add_source", "mft_finalize", "mft_rhs", "mft_calc_fluxes",
+    "mft_apply_source", "mft_boundary_pass", "mft_upload_state", "mft_download_state", "mft_download_du",
+    "mft_history_push", "mft_history_push_weights", "mft_ssprk_step", "mft_get_field", "mft_synchronize",
+    "mft_launch_count", "mft_kernel_time_ms", "mft_set_kernel_timing", "mft_host_alloc", "mft_host_free",
+    "mft_host_register", "mft_host_unregister", "mft_sfc_order", "mft_nccl_unique_id", "mft_comm_init", "mft_set_halo",
+]
+
+_lib = None
+
+
+class MftError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libmft_b200.so; raises if it has not been built (see build.py / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MftError(f"{LIB_PATH} not found: build it with `python meshfreetrixi.jl_b200/build.py` "
+                       "(needs nvcc).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.mft_last_error.restype = C.c_char_p
+    lib.mft_launch_count.restype = C.c_int64
+    lib.mft_launch_count.argtypes = [C.c_void_p]
+    vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
+    sigs = {
+        "mft_ctx_create": [C.POINTER(vp), i32, i64, i64, i32, i32, i32],
+        "mft_ctx_destroy": [vp],
+        "mft_set_equation": [vp, i32, vp, i32],
+        "mft_set_option": [vp, i32, dbl],
+        "mft_set_permutation": [vp, vp],
+        "mft_set_order_keys": [vp, vp],
+        "mft_set_operator_csc": [vp, i32, vp, vp, vp],
+        "mft_set_operator_ell": [vp, vp, vp, vp],
+        "mft_add_boundary": [vp, i32, i64, vp, vp, vp],
+        "mft_update_boundary_values": [vp, i32, vp],
+        "mft_add_source": [vp, i32, vp, i32, vp, vp, vp],
+        "mft_finalize": [vp],
+        "mft_rhs": [vp, dbl, vp, vp, i32],
+        "mft_calc_fluxes": [vp, vp, vp],
+        "mft_apply_source": [vp, i32, dbl, vp, vp],
+        "mft_boundary_pass": [vp, dbl, vp, vp],
+        "mft_upload_state": [vp, vp],
+        "mft_download_state": [vp, vp],
+        "mft_download_du": [vp, vp],
+        "mft_history_push": [vp, dbl, i64, i32],
+        "mft_history_push_weights": [vp, dbl, i64, i32, vp],
+        "mft_ssprk_step": [vp, i32, dbl, dbl],
+        "mft_get_field": [vp, i32, vp],
+        "mft_synchronize": [vp],
+        "mft_kernel_time_ms": [vp, i32, C.POINTER(dbl), C.POINTER(i64)],
+        "mft_set_kernel_timing": [vp, i32],
+        "mft_host_alloc": [C.POINTER(vp), i64],
+        "mft_host_free": [vp],
+        "mft_host_register": [vp, i64],
+        "mft_host_unregister": [vp],
+        "mft_sfc_order": [i64, vp, vp, vp],
+        "mft_nccl_unique_id": [vp],
+        "mft_comm_init": [vp, i32, i32, vp],
+        "mft_set_halo": [vp, i32, vp, vp, vp, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise MftError(f"libmft_b200 error {rc}: {load().mft_last_error().decode()}")
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def soa_ptrs(arr: np.ndarray):
+    """(V,N) C-contiguous float64 -> array of V row pointers (= StructArrays.components(u))."""
+    assert arr.dtype == np.float64 and arr.flags.c_contiguous and arr.ndim == 2
+    V = arr.shape[0]
+    ptrs = (C.c_void_p * V)(*[arr.ctypes.data + v * arr.strides[0] for v in range(V)])
+    return ptrs
+
+
+def sfc_order(points: np.ndarray) -> np.ndarray:
+    """Hilbert ordering (host helper in the library): returns perm (0-based), device row d <- point perm[d]."""
+    x = np.ascontiguousarray(points[:, 0], dtype=np.float64)
+    y = np.ascontiguousarray(points[:, 1], dtype=np.float64)
+    out = np.empty(len(x), dtype=np.int64)
+    check(load().mft_sfc_order(len(x), ptr(x), ptr(y), ptr(out)))
+    return out - 1
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array backed by cudaHostAlloc memory (never freed explicitly; process-lifetime buffers)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    check(load().mft_host_alloc(C.byref(p), n))
+    buf = (C.c_char * n).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)

@@ -1,0 +1,418 @@
+"""Host-side mirror of the reference's Trixi-style interface for the `rhs!` path.
+
+Same names, argument meaning and call order as MeshfreeTrixi.jl so that tests read like the reference's own
+(test/divergence_test.jl, test/upwind_viscosity_test.jl, test/history_test.jl):
+
+    basis  = PointCloudBasis(Point2D(), 3, approximation_type=RBF(PolyharmonicSpline(3)))
+    solver = PointCloudSolver(basis, engine=RBFFDEngineCUDA())
+    domain = PointCloudDomain(solver, "data/cyl_0_05", dict(inlet=1, outlet=2, bottom=3, top=4, cyl=5))
+    semi   = SemidiscretizationHyperbolic(domain, equations, ic, solver, boundary_conditions=..., source_terms=...)
+    ode    = semidiscretize(semi, (0.0, 0.5));  rhs_(du, ode.u0, semi, t)
+
+Everything numerical on the path is executed by libmft_b200.so through its C ABI (see _lib.py); this module only
+marshals arrays.  State arrays are (V, N) float64 C-contiguous = the V component vectors of the reference's
+StructArray (allocate_nested_array, src/solvers/pointcloudsolver/rbfsolver.jl:111-116).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib as L
+from . import cloud as cloudmod
+from . import setup_ops
+
+
+# ---- basis / solver / engine (src/solvers/rbfsolver.jl:8-71, src/solvers/pointcloudsolver/types.jl:71-86) ----
+class Point2D:
+    ndims = 2
+
+
+@dataclass
+class PolyharmonicSpline:
+    Nrbf: int = 3
+
+
+@dataclass
+class RBF:
+    rbf_type: PolyharmonicSpline = field(default_factory=PolyharmonicSpline)
+
+
+@dataclass
+class RefPointData:
+    elem: object
+    approx_type: RBF
+    N: int
+    nv: int
+
+
+def PointCloudBasis(element_type, polydeg, approximation_type=None, nv=None):
+    """types.jl:83-86 -> RefPointData (geometry_primatives.jl:189-201).  `nv` overrides the stencil width
+    (RefPointData is a plain struct in the reference; the stencil sweep of BASELINE.json overrides it)."""
+    approximation_type = approximation_type or RBF()
+    return RefPointData(element_type, approximation_type, polydeg, nv or setup_ops.num_neighbors(polydeg, 2))
+
+
+@dataclass
+class RBFFDEngineCUDA:
+    """The reference's reserved, method-less plug-in point (src/solvers/rbfsolver.jl:60-61), given a body."""
+    device: int = 0
+    reorder: str | None = "hilbert"   # space-filling-curve device ordering
+    exact_order: bool = True           # reference summation order, separate mul/add (bit-identical sums)
+    diagnostics: bool = False          # keep eps/eps_uw/eps_rv/residual on device for inspection
+    mean_divisor_vn: bool = True       # ode_mean divides by V*N (recursive_length)
+    max_lexicographic: bool = True     # maximum(::StructArray{SVector}) is a lexicographic max
+
+
+@dataclass
+class RBFSolver:
+    basis: RefPointData
+    engine: object
+
+
+def PointCloudSolver(basis, engine=None):
+    return RBFSolver(basis, engine or RBFFDEngineCUDA())
+
+
+# ---- domain (geometry_primatives.jl:297-364, SerialPointCloud.jl:12-54) ------------------------------------------
+@dataclass
+class PointData:
+    points: np.ndarray
+    neighbors: np.ndarray  # (N,nv) 0-based, self first
+    num_points: int
+    num_neighbors: int
+    dx_min: float
+    dx_avg: float
+
+
+@dataclass
+class BoundaryData:
+    idx: np.ndarray      # 0-based
+    normals: np.ndarray  # (n,2)
+
+
+class PointCloudDomain:
+    def __init__(self, solver, source, boundary_names):
+        """source: Medusa case name (file-based ctor, types.jl:133-145) or a cloud.Cloud; boundary_names maps a
+        name to the 1-based boundary group number, as in the reference tests."""
+        cl = cloudmod.read_medusa_file(source) if isinstance(source, str) else source
+        nv = solver.basis.nv
+        nb, dx_min, dx_avg = setup_ops.knn(cl.points, nv)
+        self.pd = PointData(np.ascontiguousarray(cl.points, dtype=np.float64), nb, cl.points.shape[0], nv, dx_min, dx_avg)
+        self.boundary_tags = {name: BoundaryData(np.asarray(cl.boundary_idxs[g - 1], dtype=np.int64),
+                                                 np.asarray(cl.boundary_normals[g - 1], dtype=np.float64))
+                              for name, g in boundary_names.items()}
+        self.cloud = cl
+
+
+# ---- equations (Trixi, third party) ------------------------------------------------------------------------------
+@dataclass
+class CompressibleEulerEquations2D:
+    gamma: float
+    nvars = 4
+    kind = L.EQ_EULER2D
+
+    def params(self):
+        return [self.gamma]
+
+
+@dataclass
+class LinearScalarAdvectionEquation2D:
+    a1: float
+    a2: float
+    nvars = 1
+    kind = L.EQ_ADVECTION2D
+
+    def params(self):
+        return [self.a1, self.a2]
+
+
+# ---- boundary conditions (src/equations/PointCloudBCs.jl) ------------------------------------------------------
+@dataclass
+class BoundaryConditionDirichlet:
+    boundary_value_function: object   # f(x (n,2), t, equations) -> (V,n)
+    time_dependent: bool = False
+    kind = L.BC_DIRICHLET
+
+
+class _SlipWall:
+    kind = L.BC_SLIP_WALL
+
+
+boundary_condition_slip_wall = _SlipWall()
+
+
+class BoundaryConditionDoNothing:
+    kind = L.BC_DO_NOTHING
+
+
+# ---- sources (src/sources/hyperviscosity.jl, generic_sources.jl) --------------------------------------------------
+class _Source:
+    index = None   # position in SourceTerms once attached to a semidiscretization
+    semi = None
+
+    def __call__(self, du, u, t, semi=None):
+        """source(du,u,t,domain,equations,solver,cache): du is accumulated into."""
+        semi = semi or self.semi
+        L.check(L.load().mft_apply_source(semi.ctx, self.index, float(t), L.soa_ptrs(u), L.soa_ptrs(du)))
+
+    @property
+    def cache(self):
+        return _SourceCacheView(self)
+
+
+class _SourceCacheView:
+    def __init__(self, src):
+        self._s = src
+
+    def _scalar(self, fld):
+        semi = self._s.semi
+        out = np.empty(semi.n)
+        L.check(L.load().mft_get_field(semi.ctx, fld, L.ptr(out)))
+        return out
+
+    eps = property(lambda self: self._scalar(L.FIELD_EPS))
+    eps_uw = property(lambda self: self._scalar(L.FIELD_EPS_UW))
+    eps_rv = property(lambda self: self._scalar(L.FIELD_EPS_RV))
+    eps_c = property(lambda self: self._scalar(L.FIELD_EPS_C))
+
+    def _vec(self, fld):
+        semi = self._s.semi
+        out = np.empty((semi.V, semi.n))
+        L.check(L.load().mft_get_field(semi.ctx, fld, L.ptr(out)))
+        return out
+
+    residual = property(lambda self: self._vec(L.FIELD_RESIDUAL))
+    approx_du = property(lambda self: self._vec(L.FIELD_APPROX_DU))
+
+    @property
+    def norms(self):
+        out = np.empty(self._s.semi.V)
+        L.check(L.load().mft_get_field(self._s.semi.ctx, L.FIELD_NORMS, L.ptr(out)))
+        return out
+
+
+class SourceHyperviscosityFlyer(_Source):
+    """hyperviscosity.jl:14-64: H = sum_d d^{2k}/dx_d^{2k}, gamma = c*dx_min^{2k}."""
+    kind = L.SRC_HV_FLYER
+
+    def __init__(self, solver, equations, domain, k=2, c=1.0):
+        p, N = solver.basis.approx_type.rbf_type.Nrbf, solver.basis.N
+        ops = setup_ops.compute_flux_operator(domain.pd.points, domain.pd.neighbors, p, N, 2 * k)
+        self.hv_differentiation_matrix = (ops[0] + ops[1]).tocsc()
+        self.gamma = c * domain.pd.dx_min ** (2 * k)
+        self.c = c
+
+
+class SourceHyperviscosityTominec(_Source):
+    """hyperviscosity.jl:80-134: H = L'L with L = dxx + dyy, gamma = c*dx_min^4.5."""
+    kind = L.SRC_HV_TOMINEC
+
+    def __init__(self, solver, equations, domain, c=1.0):
+        p, N = solver.basis.approx_type.rbf_type.Nrbf, solver.basis.N
+        ops = setup_ops.compute_flux_operator(domain.pd.points, domain.pd.neighbors, p, N, 2)
+        lap = (ops[0] + ops[1]).tocsc()
+        self.hv_differentiation_matrix = (lap.T @ lap).tocsc()
+        self.gamma = c * domain.pd.dx_min ** 4.5
+        self.c = c
+
+
+class SourceUpwindViscosityTominec(_Source):
+    """hyperviscosity.jl:148-167, apply :351-380."""
+    kind = L.SRC_UPWIND
+
+    def __init__(self, solver, equations, domain, c=1.0, c_uw=1.0, polydeg=4):
+        self.c_rv, self.c_uw, self.polydeg, self.dx_avg = c, c_uw, polydeg, domain.pd.dx_avg
+
+
+class SourceResidualViscosityTominec(_Source):
+    """hyperviscosity.jl:181-200, apply :382-409."""
+    kind = L.SRC_RESIDUAL
+
+    def __init__(self, solver, equations, domain, c_rv=1.0, c_uw=1.0, polydeg=4):
+        self.c_rv, self.c_uw, self.polydeg, self.dx_avg = c_rv, c_uw, polydeg, domain.pd.dx_avg
+
+
+class SourceTerms:
+    """generic_sources.jl:7-18: iteration order = keyword order."""
+
+    def __init__(self, **kwargs):
+        self.sources = dict(kwargs)
+
+    def values(self):
+        return list(self.sources.values())
+
+    def __len__(self):
+        return len(self.sources)
+
+    def __getattr__(self, name):
+        try:
+            return self.__dict__["sources"][name]
+        except KeyError:
+            raise AttributeError(name)
+
+
+# ---- semidiscretization (Trixi.SemidiscretizationHyperbolic + create_cache, rbfsolver.jl:130-185) -----------------
+@dataclass
+class Cache:
+    pd: PointData
+    rbf_differentiation_matrices: list
+
+
+class SemidiscretizationHyperbolic:
+    def __init__(self, domain, equations, initial_condition, solver, boundary_conditions=None, source_terms=None,
+                 operators=None):
+        if not isinstance(solver.engine, RBFFDEngineCUDA):
+            raise TypeError("this package implements the RBFFDEngineCUDA engine only (no CPU engine, no fallback)")
+        self.domain, self.equations, self.initial_condition, self.solver = domain, equations, initial_condition, solver
+        self.boundary_conditions = dict(boundary_conditions or {})
+        self.source_terms = source_terms or SourceTerms()
+        eng = solver.engine
+        pd = domain.pd
+        self.n, self.V = pd.num_points, equations.nvars
+        p, N = solver.basis.approx_type.rbf_type.Nrbf, solver.basis.N
+        ops = operators or setup_ops.compute_flux_operator(pd.points, pd.neighbors, p, N)
+        self.cache = Cache(pd, ops)
+        lib = L.load()
+        ctx = C.c_void_p()
+        L.check(lib.mft_ctx_create(C.byref(ctx), eng.device, self.n, 0, self.V, 2, pd.num_neighbors))
+        self.ctx = ctx
+        prm = np.asarray(equations.params(), dtype=np.float64)
+        L.check(lib.mft_set_equation(ctx, equations.kind, L.ptr(prm), len(prm)))
+        L.check(lib.mft_set_option(ctx, L.OPT_EXACT_ORDER, float(eng.exact_order)))
+        L.check(lib.mft_set_option(ctx, L.OPT_DIAGNOSTICS, float(eng.diagnostics)))
+        L.check(lib.mft_set_option(ctx, L.OPT_MEAN_DIVISOR_VN, float(eng.mean_divisor_vn)))
+        L.check(lib.mft_set_option(ctx, L.OPT_MAX_LEXICOGRAPHIC, float(eng.max_lexicographic)))
+        if eng.reorder == "hilbert":
+            self.perm = L.sfc_order(pd.points)
+            perm1 = np.ascontiguousarray(self.perm + 1)
+            L.check(lib.mft_set_permutation(ctx, L.ptr(perm1)))
+        else:
+            self.perm = None
+        for slot, A in ((L.OP_DX, ops[0]), (L.OP_DY, ops[1])):
+            cp, rv, nz = setup_ops.julia_csc(A)
+            L.check(lib.mft_set_operator_csc(ctx, slot, L.ptr(cp), L.ptr(rv), L.ptr(nz)))
+        self._bc_groups = []
+        for name, bc in self.boundary_conditions.items():
+            tag = domain.boundary_tags[name]   # KeyError for unknown names, like rbfsolver.jl:300
+            idx1 = np.ascontiguousarray(tag.idx + 1, dtype=np.int64)
+            nrm = np.ascontiguousarray(tag.normals, dtype=np.float64)
+            vals = None
+            if bc.kind == L.BC_DIRICHLET:
+                vals = np.ascontiguousarray(bc.boundary_value_function(pd.points[tag.idx], 0.0, equations), dtype=np.float64)
+                assert vals.shape == (self.V, len(tag.idx))
+            L.check(lib.mft_add_boundary(ctx, bc.kind, len(idx1), L.ptr(idx1), L.ptr(nrm), L.ptr(vals)))
+            self._bc_groups.append((name, bc, tag))
+        for i, src in enumerate(self.source_terms.values()):
+            src.index, src.semi = i, self
+            if src.kind in (L.SRC_HV_FLYER, L.SRC_HV_TOMINEC):
+                prm = np.asarray([src.gamma], dtype=np.float64)
+                cp, rv, nz = setup_ops.julia_csc(src.hv_differentiation_matrix)
+                L.check(lib.mft_add_source(ctx, src.kind, L.ptr(prm), 1, L.ptr(cp), L.ptr(rv), L.ptr(nz)))
+            elif src.kind == L.SRC_UPWIND:
+                prm = np.asarray([src.c_uw, src.dx_avg], dtype=np.float64)
+                L.check(lib.mft_add_source(ctx, src.kind, L.ptr(prm), 2, None, None, None))
+            else:
+                prm = np.asarray([src.c_rv, src.c_uw, src.dx_avg, float(src.polydeg)], dtype=np.float64)
+                L.check(lib.mft_add_source(ctx, src.kind, L.ptr(prm), 4, None, None, None))
+        L.check(lib.mft_finalize(ctx))
+
+    def refresh_boundary_values(self, t):
+        lib = L.load()
+        for g, (name, bc, tag) in enumerate(self._bc_groups):
+            if bc.kind == L.BC_DIRICHLET and bc.time_dependent:
+                vals = np.ascontiguousarray(bc.boundary_value_function(self.domain.pd.points[tag.idx], t, self.equations))
+                L.check(lib.mft_update_boundary_values(self.ctx, g, L.ptr(vals)))
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            L.load().mft_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class ODEProblem:
+    u0: np.ndarray
+    tspan: tuple
+    p: SemidiscretizationHyperbolic
+
+
+def compute_coefficients(t, semi):
+    """rbfsolver.jl:174-185: u[i] = initial_condition(points[i], t, equations)"""
+    u = np.ascontiguousarray(semi.initial_condition(semi.domain.pd.points, t, semi.equations), dtype=np.float64)
+    assert u.shape == (semi.V, semi.n)
+    return u
+
+
+def semidiscretize(semi, tspan):
+    return ODEProblem(compute_coefficients(tspan[0], semi), tuple(tspan), semi)
+
+
+def rhs_(du, u, semi, t):
+    """Trixi.rhs!(du_ode, u_ode, semi, t) -> Trixi.rhs!(du,u,t,domain,...) rbfsolver.jl:397-428.  u is IN/OUT."""
+    semi.refresh_boundary_values(t)
+    L.check(L.load().mft_rhs(semi.ctx, float(t), L.soa_ptrs(u), L.soa_ptrs(du), L.MEM_HOST))
+
+
+def calc_fluxes_(du, u, semi):
+    """calc_fluxes!(du,u,domain,...,engine::RBFFDEngineCUDA,...)  (reference CPU method: rbfsolver.jl:247-265)"""
+    L.check(L.load().mft_calc_fluxes(semi.ctx, L.soa_ptrs(u), L.soa_ptrs(du)))
+
+
+def calc_boundary_flux_(du, u, semi, t):
+    semi.refresh_boundary_values(t)
+    L.check(L.load().mft_boundary_pass(semi.ctx, float(t), L.soa_ptrs(u), L.soa_ptrs(du)))
+
+
+# ---- callbacks + time integration (history.jl:15-129; SSPRK: SURVEY.md appendix B.5) -------------------------------
+@dataclass
+class HistoryCallback:
+    approx_order: int = 4
+
+
+class SSPRK33:
+    scheme = L.SSPRK33
+    stages = 3
+
+
+@dataclass
+class Solution:
+    u: np.ndarray
+    t: float
+    nsteps: int
+    nrhs: int
+
+
+def solve(ode, alg, dt, callback=None, nsteps=None):
+    """Fixed-step SSP integration with the state resident on the device (FSAL structure, callbacks after
+    every step); mirrors solve(ode, SSPRK..; dt, adaptive=false, callback=CallbackSet(...))."""
+    semi = ode.p
+    lib = L.load()
+    t0, t1 = ode.tspan
+    if nsteps is None:
+        nsteps = int(round((t1 - t0) / dt))
+    cbs = [] if callback is None else (list(callback) if isinstance(callback, (list, tuple)) else [callback])
+    hist = [c for c in cbs if isinstance(c, HistoryCallback)]
+    u0 = np.ascontiguousarray(ode.u0, dtype=np.float64)
+    L.check(lib.mft_upload_state(semi.ctx, L.soa_ptrs(u0)))
+    t = float(t0)
+    for h in hist:   # initialize! (history.jl:51-54)
+        L.check(lib.mft_history_push(semi.ctx, t, 0, h.approx_order))
+    nrhs = 1 if nsteps > 0 else 0
+    for it in range(nsteps):
+        L.check(lib.mft_ssprk_step(semi.ctx, alg.scheme, t, float(dt)))
+        t = t + dt
+        nrhs += alg.stages
+        for h in hist:
+            L.check(lib.mft_history_push(semi.ctx, t, it + 1, h.approx_order))
+    u = np.empty_like(u0)
+    L.check(lib.mft_download_state(semi.ctx, L.soa_ptrs(u)))
+    return Solution(u, t, nsteps, nrhs)

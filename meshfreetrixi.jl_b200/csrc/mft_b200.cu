@@ -1,0 +1,1443 @@
+// mft_b200.cu -- C ABI (include/mft_b200.h) + host orchestration of the sm_100a rhs! path.
+// There is no CPU fallback anywhere in this file: every compute entry point needs a CUDA device.
+#include "../../include/mft_b200.h"
+#include "mft_kernels.cuh"
+#include "mft_nccl.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace mft;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(x)                                                                                               \
+    do {                                                                                                    \
+        cudaError_t e_ = (x);                                                                               \
+        if (e_ != cudaSuccess) return fail(MFT_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+    } while (0)
+#define CHECK(x)             \
+    do {                     \
+        int r_ = (x);        \
+        if (r_ != 0) return r_; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------
+// host-side sparse helpers (setup time)
+// ------------------------------------------------------------------------------------------------------
+struct HostCsc {
+    bool set = false;
+    std::vector<int64_t> colptr, rowval;  // 0-based internally
+    std::vector<double> nz;
+};
+
+struct Csr2 {  // rows with paired weights, entries of a row in summation order
+    int64_t nrows = 0;
+    std::vector<int64_t> ptr;
+    std::vector<int32_t> col;
+    std::vector<double> wx, wy;
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    int64_t n = 0;
+    int alloc(int64_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) return 0;
+        cudaError_t e = cudaMalloc(&p, sizeof(T) * (size_t)count);
+        if (e != cudaSuccess) return fail(MFT_ECUDA, "cudaMalloc(%lld bytes): %s", (long long)(sizeof(T) * count), cudaGetErrorString(e));
+        return 0;
+    }
+    int upload(const std::vector<T> &h)
+    {
+        CHECK(alloc((int64_t)h.size()));
+        if (!h.empty()) CU(cudaMemcpy(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct DevEll {
+    DevBuf<int> idx, off;
+    DevBuf<double> wx, wy;
+    int nslices = 0;
+    int64_t ncols_total = 0;  // sum of slice widths
+    int64_t nnz = 0;
+    Ell2 view2() const { return Ell2{idx.p, wx.p, wy.p, off.p}; }
+    Ell1 view1() const { return Ell1{idx.p, wx.p, off.p}; }
+    void release()
+    {
+        idx.release();
+        off.release();
+        wx.release();
+        wy.release();
+    }
+};
+
+struct BcGroup {
+    int kind;
+    int64_t nb;
+    DevBuf<int> idx;
+    DevBuf<double> normals, values;
+};
+
+struct Source {
+    int kind;
+    double gamma = 0, c_rv = 1, c_uw = 1, dx_avg = 0;
+    int polydeg = 4;
+    HostCsc hv_host;
+    DevEll hv;
+};
+
+struct KTimer {
+    std::vector<cudaEvent_t> ev;  // pairs
+    std::vector<int> cls;
+};
+
+struct mft_ctx {
+    int device = 0;
+    int64_t n_local = 0, n_halo = 0, n_tot = 0;
+    int V = 0, ndims = 2, k = 0;
+    int eq = -1;
+    double eqp[2] = {0, 0};
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+    // options
+    int exact = 1, mean_div_vn = 1, max_lex = 1, diagnostics = 0;
+    // ordering
+    bool have_perm = false;
+    std::vector<int32_t> perm, iperm;  // device->caller, caller->device (0-based)
+    std::vector<int64_t> keys;         // caller index -> summation rank
+    DevBuf<int> d_perm;
+    // operators
+    HostCsc host_ops[2];
+    Csr2 host_ell;  // from mft_set_operator_ell
+    bool have_ell_input = false;
+    DevEll fwd, tra;
+    // bcs, sources
+    std::vector<BcGroup *> bcs;
+    std::vector<Source *> srcs;
+    bool finalized = false;
+    // device state (AoS)
+    DevBuf<double> u, du, uprev, g, approx_du, stage_soa;
+    std::vector<DevBuf<double>> hist;
+    std::vector<double> time_history, time_weights;
+    int hist_head = 0, nslots = 0;
+    int64_t success_iter = 0;
+    // diagnostics
+    DevBuf<double> eps, eps_uw, eps_rv, eps_c, residual;
+    // reductions
+    DevBuf<double> partial, stats;  // stats: sum[V], mean[V], norms[V]
+    int red_blocks = 0;
+    bool have_fsal = false;
+    int64_t launches = 0;
+    // per-class timing
+    bool timing = false;
+    KTimer kt;
+    // multi-GPU
+    NcclApi *nccl = nullptr;
+    void *comm = nullptr;
+    int nranks = 1, rank = 0;
+    int64_t n_global = 0;
+    std::vector<int> peers;
+    std::vector<int64_t> send_off, recv_off;  // prefix offsets (points)
+    DevBuf<int> send_rows;
+    DevBuf<double> send_buf;
+    DevBuf<double> gather_buf;  // nranks * 2V doubles
+    int64_t n_send = 0;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// misc
+// ------------------------------------------------------------------------------------------------------
+extern "C" const char *mft_last_error(void) { return g_err.c_str(); }
+extern "C" int mft_version(void) { return 100; }
+extern "C" int mft_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+struct ScopedTimer {
+    mft_ctx *c;
+    bool on;
+    ScopedTimer(mft_ctx *ctx, int cls) : c(ctx), on(ctx->timing)
+    {
+        if (on) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            c->kt.ev.push_back(a);
+            c->kt.ev.push_back(b);
+            c->kt.cls.push_back(cls);
+            cudaEventRecord(a, c->stream);
+        }
+    }
+    ~ScopedTimer()
+    {
+        if (on) cudaEventRecord(c->kt.ev.back(), c->stream);
+    }
+};
+
+#define LAUNCH_CHECK()                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = cudaGetLastError();                                                        \
+        if (e_ != cudaSuccess) return fail(MFT_ECUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------------
+extern "C" int mft_ctx_create(mft_ctx **out, int device, int64_t n_local, int64_t n_halo, int nvars, int ndims, int k)
+{
+    if (!out) return fail(MFT_EINVAL, "mft_ctx_create: out is NULL");
+    *out = nullptr;
+    if (n_local <= 0 || n_halo < 0) return fail(MFT_EINVAL, "mft_ctx_create: bad sizes n_local=%lld n_halo=%lld", (long long)n_local, (long long)n_halo);
+    if (n_local + n_halo > 2000000000LL) return fail(MFT_EINVAL, "mft_ctx_create: more than 2^31 points per device is not supported");
+    if (nvars != 1 && nvars != 4) return fail(MFT_ENOTSUP, "mft_ctx_create: nvars must be 1 (advection) or 4 (Euler 2-D), got %d", nvars);
+    if (ndims != 2) return fail(MFT_ENOTSUP, "mft_ctx_create: only 2-D point clouds are supported, got ndims=%d", ndims);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MFT_ENODEVICE, "mft_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= ndev) return fail(MFT_EINVAL, "mft_ctx_create: device %d out of range [0,%d)", device, ndev);
+    CU(cudaSetDevice(device));
+    mft_ctx *c = new mft_ctx();
+    c->device = device;
+    c->n_local = n_local;
+    c->n_halo = n_halo;
+    c->n_tot = n_local + n_halo;
+    c->V = nvars;
+    c->ndims = ndims;
+    c->k = k;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_c, cudaEventDisableTiming));
+    const int64_t len = c->n_tot * nvars;
+    CHECK(c->u.alloc(len));
+    CHECK(c->du.alloc(len));
+    CHECK(c->stage_soa.alloc(len));
+    CU(cudaMemset(c->u.p, 0, sizeof(double) * len));
+    CU(cudaMemset(c->du.p, 0, sizeof(double) * len));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->red_blocks = prop.multiProcessorCount * 4;
+    CHECK(c->partial.alloc((int64_t)c->red_blocks * nvars));
+    CHECK(c->stats.alloc(3 * nvars));
+    CU(cudaMemset(c->stats.p, 0, sizeof(double) * 3 * nvars));
+    *out = c;
+    return MFT_OK;
+}
+
+extern "C" int mft_ctx_destroy(mft_ctx *c)
+{
+    if (!c) return MFT_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->comm && c->nccl) c->nccl->commDestroy(c->comm);
+    for (auto *b : c->bcs) {
+        b->idx.release();
+        b->normals.release();
+        b->values.release();
+        delete b;
+    }
+    for (auto *s : c->srcs) {
+        s->hv.release();
+        delete s;
+    }
+    c->fwd.release();
+    c->tra.release();
+    for (auto &h : c->hist) h.release();
+    DevBuf<double> *bufs[] = {&c->u, &c->du, &c->uprev, &c->g, &c->approx_du, &c->stage_soa, &c->eps, &c->eps_uw,
+                              &c->eps_rv, &c->eps_c, &c->residual, &c->partial, &c->stats, &c->send_buf, &c->gather_buf};
+    for (auto *b : bufs) b->release();
+    c->d_perm.release();
+    c->send_rows.release();
+    for (auto ev : c->kt.ev) cudaEventDestroy(ev);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->ev_c) cudaEventDestroy(c->ev_c);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    delete c;
+    return MFT_OK;
+}
+
+#define NEED_CTX(c)                                               \
+    do {                                                          \
+        if (!(c)) return fail(MFT_EINVAL, "%s: ctx is NULL", __func__); \
+        CU(cudaSetDevice((c)->device));                           \
+    } while (0)
+
+extern "C" int mft_set_equation(mft_ctx *c, int kind, const double *params, int nparams)
+{
+    NEED_CTX(c);
+    if (kind == MFT_EQ_EULER2D) {
+        if (c->V != 4) return fail(MFT_EINVAL, "mft_set_equation: Euler 2-D needs nvars=4");
+        if (nparams < 1 || !params) return fail(MFT_EINVAL, "mft_set_equation: Euler 2-D needs gamma");
+        c->eqp[0] = params[0];
+    } else if (kind == MFT_EQ_ADVECTION2D) {
+        if (c->V != 1) return fail(MFT_EINVAL, "mft_set_equation: advection needs nvars=1");
+        if (nparams < 2 || !params) return fail(MFT_EINVAL, "mft_set_equation: advection needs a1, a2");
+        c->eqp[0] = params[0];
+        c->eqp[1] = params[1];
+    } else {
+        return fail(MFT_ENOTSUP, "mft_set_equation: unknown equation kind %d", kind);
+    }
+    c->eq = kind;
+    return MFT_OK;
+}
+
+extern "C" int mft_set_option(mft_ctx *c, int option, double value)
+{
+    NEED_CTX(c);
+    switch (option) {
+    case MFT_OPT_EXACT_ORDER: c->exact = value != 0; break;
+    case MFT_OPT_MEAN_DIVISOR_VN: c->mean_div_vn = value != 0; break;
+    case MFT_OPT_MAX_LEXICOGRAPHIC: c->max_lex = value != 0; break;
+    case MFT_OPT_DIAGNOSTICS: c->diagnostics = value != 0; break;
+    case MFT_OPT_CUDA_GRAPH: break;  // reserved
+    default: return fail(MFT_EINVAL, "mft_set_option: unknown option %d", option);
+    }
+    return MFT_OK;
+}
+
+extern "C" int mft_set_permutation(mft_ctx *c, const int64_t *perm1)
+{
+    NEED_CTX(c);
+    if (c->finalized) return fail(MFT_EINVAL, "mft_set_permutation: must be called before the first compute call");
+    if (!perm1) return fail(MFT_EINVAL, "mft_set_permutation: perm is NULL");
+    const int64_t n = c->n_tot;
+    std::vector<int32_t> perm(n), iperm(n, -1);
+    for (int64_t d = 0; d < n; ++d) {
+        const int64_t p = perm1[d] - 1;
+        if (p < 0 || p >= n) return fail(MFT_EINVAL, "mft_set_permutation: entry %lld out of range", (long long)perm1[d]);
+        if (iperm[p] != -1) return fail(MFT_EINVAL, "mft_set_permutation: duplicate entry %lld", (long long)perm1[d]);
+        if ((d < c->n_local) != (p < c->n_local)) return fail(MFT_EINVAL, "mft_set_permutation: owned and halo points must not mix");
+        perm[d] = (int32_t)p;
+        iperm[p] = (int32_t)d;
+    }
+    c->perm.swap(perm);
+    c->iperm.swap(iperm);
+    c->have_perm = true;
+    return MFT_OK;
+}
+
+extern "C" int mft_set_order_keys(mft_ctx *c, const int64_t *keys)
+{
+    NEED_CTX(c);
+    if (c->finalized) return fail(MFT_EINVAL, "mft_set_order_keys: must be called before the first compute call");
+    if (!keys) return fail(MFT_EINVAL, "mft_set_order_keys: keys is NULL");
+    c->keys.assign(keys, keys + c->n_tot);
+    return MFT_OK;
+}
+
+static int copy_csc(mft_ctx *c, HostCsc &dst, const int64_t *colptr, const int64_t *rowval, const double *nzval, const char *who)
+{
+    if (!colptr || !rowval || !nzval) return fail(MFT_EINVAL, "%s: NULL CSC array", who);
+    const int64_t n = c->n_tot;
+    if (colptr[0] != 1) return fail(MFT_EINVAL, "%s: colptr[0] must be 1 (Julia 1-based), got %lld", who, (long long)colptr[0]);
+    const int64_t nnz = colptr[n] - 1;
+    if (nnz < 0) return fail(MFT_EINVAL, "%s: negative nnz", who);
+    dst.colptr.resize(n + 1);
+    for (int64_t i = 0; i <= n; ++i) {
+        dst.colptr[i] = colptr[i] - 1;
+        if (i > 0 && dst.colptr[i] < dst.colptr[i - 1]) return fail(MFT_EINVAL, "%s: colptr not monotone at %lld", who, (long long)i);
+    }
+    dst.rowval.resize(nnz);
+    for (int64_t p = 0; p < nnz; ++p) {
+        const int64_t r = rowval[p] - 1;
+        if (r < 0 || r >= n) return fail(MFT_EINVAL, "%s: rowval[%lld]=%lld out of range", who, (long long)p, (long long)rowval[p]);
+        dst.rowval[p] = r;
+    }
+    dst.nz.assign(nzval, nzval + nnz);
+    dst.set = true;
+    return MFT_OK;
+}
+
+extern "C" int mft_set_operator_csc(mft_ctx *c, int slot, const int64_t *colptr, const int64_t *rowval, const double *nzval)
+{
+    NEED_CTX(c);
+    if (c->finalized) return fail(MFT_EINVAL, "mft_set_operator_csc: operators are immutable after the first compute call");
+    if (slot != MFT_OP_DX && slot != MFT_OP_DY) return fail(MFT_EINVAL, "mft_set_operator_csc: slot must be MFT_OP_DX or MFT_OP_DY");
+    return copy_csc(c, c->host_ops[slot], colptr, rowval, nzval, "mft_set_operator_csc");
+}
+
+extern "C" int mft_set_operator_ell(mft_ctx *c, const int64_t *nbr1, const double *wx, const double *wy)
+{
+    NEED_CTX(c);
+    if (c->finalized) return fail(MFT_EINVAL, "mft_set_operator_ell: operators are immutable after the first compute call");
+    if (!nbr1 || !wx || !wy) return fail(MFT_EINVAL, "mft_set_operator_ell: NULL array");
+    if (c->k <= 0) return fail(MFT_EINVAL, "mft_set_operator_ell: ctx was created with k=%d", c->k);
+    Csr2 &A = c->host_ell;
+    const int64_t n = c->n_local, k = c->k;
+    A.nrows = n;
+    A.ptr.resize(n + 1);
+    A.col.resize(n * k);
+    A.wx.assign(wx, wx + n * k);
+    A.wy.assign(wy, wy + n * k);
+    for (int64_t i = 0; i <= n; ++i) A.ptr[i] = i * k;
+    for (int64_t p = 0; p < n * k; ++p) {
+        const int64_t j = nbr1[p] - 1;
+        if (j < 0 || j >= c->n_tot) return fail(MFT_EINVAL, "mft_set_operator_ell: neighbour %lld out of range", (long long)nbr1[p]);
+        A.col[p] = (int32_t)j;
+    }
+    c->have_ell_input = true;
+    return MFT_OK;
+}
+
+extern "C" int mft_add_boundary(mft_ctx *c, int kind, int64_t nb, const int64_t *idx1, const double *normals, const double *values)
+{
+    NEED_CTX(c);
+    if (c->finalized) return fail(MFT_EINVAL, "mft_add_boundary: must be called before the first compute call");
+    if (kind < 0 || kind > 2) return fail(MFT_EINVAL, "mft_add_boundary: unknown kind %d", kind);
+    if (nb < 0 || (nb > 0 && !idx1)) return fail(MFT_EINVAL, "mft_add_boundary: bad index list");
+    if (kind == MFT_BC_DIRICHLET && nb > 0 && !values) return fail(MFT_EINVAL, "mft_add_boundary: Dirichlet group needs a value table");
+    if (kind == MFT_BC_SLIP_WALL && c->V != 4) return fail(MFT_ENOTSUP, "mft_add_boundary: slip wall is defined for Euler 2-D only");
+    if (kind == MFT_BC_SLIP_WALL && nb > 0 && !normals) return fail(MFT_EINVAL, "mft_add_boundary: slip wall needs normals");
+    BcGroup *g = new BcGroup();
+    g->kind = kind;
+    g->nb = nb;
+    std::vector<int> idx(nb);
+    for (int64_t j = 0; j < nb; ++j) {
+        const int64_t p = idx1[j] - 1;
+        if (p < 0 || p >= c->n_tot) {
+            delete g;
+            return fail(MFT_EINVAL, "mft_add_boundary: index %lld out of range", (long long)idx1[j]);
+        }
+        idx[j] = (int)p;  // caller numbering for now; remapped in finalize
+    }
+    int r = g->idx.upload(idx);
+    if (r == 0 && normals && nb > 0) r = g->normals.upload(std::vector<double>(normals, normals + 2 * nb));
+    if (r == 0 && values && nb > 0) {
+        std::vector<double> aos((size_t)nb * c->V);
+        for (int64_t j = 0; j < nb; ++j)
+            for (int v = 0; v < c->V; ++v) aos[j * c->V + v] = values[(int64_t)v * nb + j];
+        r = g->values.upload(aos);
+    }
+    if (r != 0) {
+        delete g;
+        return r;
+    }
+    // keep caller-numbered indices on the host for the finalize remap
+    c->bcs.push_back(g);
+    return MFT_OK;
+}
+
+extern "C" int mft_update_boundary_values(mft_ctx *c, int group, const double *values)
+{
+    NEED_CTX(c);
+    if (group < 0 || group >= (int)c->bcs.size()) return fail(MFT_EINVAL, "mft_update_boundary_values: group %d out of range", group);
+    BcGroup *g = c->bcs[group];
+    if (g->kind != MFT_BC_DIRICHLET) return fail(MFT_EINVAL, "mft_update_boundary_values: group %d is not Dirichlet", group);
+    if (!values) return fail(MFT_EINVAL, "mft_update_boundary_values: values is NULL");
+    std::vector<double> aos((size_t)g->nb * c->V);
+    for (int64_t j = 0; j < g->nb; ++j)
+        for (int v = 0; v < c->V; ++v) aos[j * c->V + v] = values[(int64_t)v * g->nb + j];
+    if (g->nb > 0) CU(cudaMemcpyAsync(g->values.p, aos.data(), sizeof(double) * aos.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return MFT_OK;
+}
+
+extern "C" int mft_add_source(mft_ctx *c, int kind, const double *params, int nparams, const int64_t *colptr,
+                              const int64_t *rowval, const double *nzval)
+{
+    NEED_CTX(c);
+    if (c->finalized) return fail(MFT_EINVAL, "mft_add_source: must be called before the first compute call");
+    Source *s = new Source();
+    s->kind = kind;
+    int r = MFT_OK;
+    if (kind == MFT_SRC_HV_FLYER || kind == MFT_SRC_HV_TOMINEC) {
+        if (nparams < 1 || !params) r = fail(MFT_EINVAL, "mft_add_source: hyperviscosity needs gamma");
+        else {
+            s->gamma = params[0];
+            r = copy_csc(c, s->hv_host, colptr, rowval, nzval, "mft_add_source");
+        }
+    } else if (kind == MFT_SRC_UPWIND) {
+        if (c->eq != MFT_EQ_EULER2D) r = fail(MFT_ENOTSUP, "mft_add_source: upwind viscosity is defined for Euler 2-D only (hyperviscosity.jl:246-247); call mft_set_equation first");
+        else if (nparams < 2 || !params) r = fail(MFT_EINVAL, "mft_add_source: upwind viscosity needs c_uw, dx_avg");
+        else {
+            s->c_uw = params[0];
+            s->dx_avg = params[1];
+        }
+    } else if (kind == MFT_SRC_RESIDUAL) {
+        if (c->eq != MFT_EQ_EULER2D) r = fail(MFT_ENOTSUP, "mft_add_source: residual viscosity is defined for Euler 2-D only (hyperviscosity.jl:289-291); call mft_set_equation first");
+        else if (nparams < 4 || !params) r = fail(MFT_EINVAL, "mft_add_source: residual viscosity needs c_rv, c_uw, dx_avg, polydeg");
+        else {
+            s->c_rv = params[0];
+            s->c_uw = params[1];
+            s->dx_avg = params[2];
+            s->polydeg = (int)params[3];
+            if (s->polydeg < 0 || s->polydeg > 7) r = fail(MFT_EINVAL, "mft_add_source: polydeg must be in [0,7]");
+            for (auto *o : c->srcs)
+                if (o->kind == MFT_SRC_RESIDUAL) r = fail(MFT_ENOTSUP, "mft_add_source: only one residual-viscosity source per ctx");
+        }
+    } else {
+        r = fail(MFT_EINVAL, "mft_add_source: unknown kind %d", kind);
+    }
+    if (r != 0) {
+        delete s;
+        return r;
+    }
+    c->srcs.push_back(s);
+    return MFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// finalize: build device layouts
+// ------------------------------------------------------------------------------------------------------
+static void sort_rows_by_key(Csr2 &A, const std::vector<int64_t> &keys, bool paired)
+{
+    if (keys.empty()) return;
+    std::vector<int64_t> ord;
+    std::vector<int32_t> tc;
+    std::vector<double> tx, ty;
+    for (int64_t r = 0; r < A.nrows; ++r) {
+        const int64_t b = A.ptr[r], e = A.ptr[r + 1], len = e - b;
+        bool sorted = true;
+        for (int64_t p = b + 1; p < e; ++p)
+            if (keys[A.col[p - 1]] > keys[A.col[p]]) {
+                sorted = false;
+                break;
+            }
+        if (sorted) continue;
+        ord.resize(len);
+        std::iota(ord.begin(), ord.end(), (int64_t)0);
+        std::stable_sort(ord.begin(), ord.end(), [&](int64_t a, int64_t c2) { return keys[A.col[b + a]] < keys[A.col[b + c2]]; });
+        tc.resize(len);
+        tx.resize(len);
+        if (paired) ty.resize(len);
+        for (int64_t q = 0; q < len; ++q) {
+            tc[q] = A.col[b + ord[q]];
+            tx[q] = A.wx[b + ord[q]];
+            if (paired) ty[q] = A.wy[b + ord[q]];
+        }
+        for (int64_t q = 0; q < len; ++q) {
+            A.col[b + q] = tc[q];
+            A.wx[b + q] = tx[q];
+            if (paired) A.wy[b + q] = ty[q];
+        }
+    }
+}
+
+// rows of A^T from rows of A (entries of each output row in ascending source-row order)
+static void transpose_rows(const Csr2 &A, int64_t ncols, bool paired, Csr2 &T)
+{
+    T.nrows = ncols;
+    T.ptr.assign(ncols + 1, 0);
+    for (int64_t p = 0; p < (int64_t)A.col.size(); ++p) T.ptr[A.col[p] + 1]++;
+    for (int64_t i = 0; i < ncols; ++i) T.ptr[i + 1] += T.ptr[i];
+    T.col.resize(A.col.size());
+    T.wx.resize(A.col.size());
+    if (paired) T.wy.resize(A.col.size());
+    std::vector<int64_t> fill(T.ptr.begin(), T.ptr.end() - 1);
+    for (int64_t r = 0; r < A.nrows; ++r)
+        for (int64_t p = A.ptr[r]; p < A.ptr[r + 1]; ++p) {
+            const int64_t q = fill[A.col[p]]++;
+            T.col[q] = (int32_t)r;
+            T.wx[q] = A.wx[p];
+            if (paired) T.wy[q] = A.wy[p];
+        }
+}
+
+// CSC columns -> "rows of the transpose" directly (column i of D = row i of D'), ascending row index
+static void csc_to_colrows(const HostCsc &X, const HostCsc *Y, int64_t n, Csr2 &T)
+{
+    T.nrows = n;
+    T.ptr.assign(X.colptr.begin(), X.colptr.end());
+    T.col.resize(X.rowval.size());
+    for (size_t p = 0; p < X.rowval.size(); ++p) T.col[p] = (int32_t)X.rowval[p];
+    T.wx = X.nz;
+    if (Y) T.wy = Y->nz;
+}
+
+// build sliced ELL for device rows [0, nrows_dev): device row d <- caller row perm[d]; columns remapped by iperm
+static int build_ell(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, bool paired, DevEll &out)
+{
+    const int64_t nsl = (nrows_dev + kSlice - 1) / kSlice;
+    std::vector<int> off(nsl + 1, 0);
+    auto caller_row = [&](int64_t d) -> int64_t { return c->have_perm ? c->perm[d] : d; };
+    int64_t nnz = 0;
+    for (int64_t s = 0; s < nsl; ++s) {
+        int64_t w = 0;
+        for (int64_t d = s * kSlice; d < std::min(nrows_dev, (s + 1) * kSlice); ++d) {
+            const int64_t r = caller_row(d);
+            const int64_t len = A.ptr[r + 1] - A.ptr[r];
+            w = std::max(w, len);
+            nnz += len;
+        }
+        const int64_t tot = (int64_t)off[s] + w;
+        if (tot > 0x7fffffffLL / kSlice * 16) return fail(MFT_EINVAL, "operator too large for 32-bit slice offsets");
+        off[s + 1] = (int)tot;
+    }
+    const int64_t ncols = off[nsl];
+    std::vector<int> idx((size_t)ncols * kSlice, -1);
+    std::vector<double> wx((size_t)ncols * kSlice, 0.0), wy;
+    if (paired) wy.assign((size_t)ncols * kSlice, 0.0);
+    for (int64_t s = 0; s < nsl; ++s)
+        for (int64_t d = s * kSlice; d < std::min(nrows_dev, (s + 1) * kSlice); ++d) {
+            const int64_t r = caller_row(d);
+            const int lane = (int)(d - s * kSlice);
+            int64_t cpos = off[s];
+            for (int64_t p = A.ptr[r]; p < A.ptr[r + 1]; ++p, ++cpos) {
+                const int64_t j = A.col[p];
+                const size_t at = (size_t)cpos * kSlice + lane;
+                idx[at] = c->have_perm ? c->iperm[j] : (int)j;
+                wx[at] = A.wx[p];
+                if (paired) wy[at] = A.wy[p];
+            }
+        }
+    out.nslices = (int)nsl;
+    out.ncols_total = ncols;
+    out.nnz = nnz;
+    CHECK(out.idx.upload(idx));
+    CHECK(out.off.upload(off));
+    CHECK(out.wx.upload(wx));
+    if (paired) CHECK(out.wy.upload(wy));
+    return MFT_OK;
+}
+
+static bool has_visc(const mft_ctx *c)
+{
+    for (auto *s : c->srcs)
+        if (s->kind == MFT_SRC_UPWIND || s->kind == MFT_SRC_RESIDUAL) return true;
+    return false;
+}
+static Source *residual_source(const mft_ctx *c)
+{
+    for (auto *s : c->srcs)
+        if (s->kind == MFT_SRC_RESIDUAL) return s;
+    return nullptr;
+}
+
+extern "C" int mft_finalize(mft_ctx *c)
+{
+    NEED_CTX(c);
+    if (c->finalized) return MFT_OK;
+    if (c->eq < 0) return fail(MFT_EINVAL, "mft_finalize: mft_set_equation was not called");
+    const int64_t n = c->n_tot;
+    Csr2 F, T;
+    if (c->have_ell_input) {
+        F = c->host_ell;
+        // complete F with empty halo rows so that the transpose sees n_tot columns
+        sort_rows_by_key(F, c->keys, true);
+        // default summation order for the ELL input is ascending caller column index
+        if (c->keys.empty()) {
+            std::vector<int64_t> ident(n);
+            std::iota(ident.begin(), ident.end(), (int64_t)0);
+            sort_rows_by_key(F, ident, true);
+        }
+        transpose_rows(F, n, true, T);
+        sort_rows_by_key(T, c->keys, true);
+    } else {
+        if (!c->host_ops[0].set || !c->host_ops[1].set) return fail(MFT_EINVAL, "mft_finalize: Dx and Dy operators were not both set");
+        const HostCsc &X = c->host_ops[0], &Y = c->host_ops[1];
+        if (X.colptr != Y.colptr || X.rowval != Y.rowval)
+            return fail(MFT_ENOTSUP, "mft_finalize: Dx and Dy must share one sparsity pattern (compute_flux_operator builds them from the same neighbour lists)");
+        csc_to_colrows(X, &Y, n, T);  // rows of D' (ascending caller row index inside each)
+        transpose_rows(T, n, true, F);  // rows of D, ascending caller column index
+        sort_rows_by_key(F, c->keys, true);
+        sort_rows_by_key(T, c->keys, true);
+    }
+    // drop halo rows of the forward operator: only owned rows are computed here
+    if (c->have_perm) CHECK(c->d_perm.upload(std::vector<int>(c->perm.begin(), c->perm.end())));
+    CHECK(build_ell(c, F, c->n_local, true, c->fwd));
+    if (has_visc(c)) {
+        CHECK(build_ell(c, T, c->n_local, true, c->tra));
+        CHECK(c->g.alloc(n * 2 * c->V));
+        CU(cudaMemset(c->g.p, 0, sizeof(double) * n * 2 * c->V));
+    }
+    for (auto *s : c->srcs) {
+        if (s->kind == MFT_SRC_HV_FLYER || s->kind == MFT_SRC_HV_TOMINEC) {
+            Csr2 HT, H;
+            csc_to_colrows(s->hv_host, nullptr, n, HT);
+            transpose_rows(HT, n, false, H);
+            sort_rows_by_key(H, c->keys, false);
+            CHECK(build_ell(c, H, c->n_local, false, s->hv));
+            s->hv_host = HostCsc();
+        }
+        if (s->kind == MFT_SRC_RESIDUAL) {
+            c->nslots = s->polydeg + 1;
+            c->hist.resize(c->nslots);
+            for (auto &h : c->hist) {
+                CHECK(h.alloc(n * c->V));
+                CU(cudaMemset(h.p, 0, sizeof(double) * n * c->V));
+            }
+            c->time_history.assign(c->nslots, 0.0);
+            c->time_weights.assign(c->nslots, 0.0);
+            CHECK(c->approx_du.alloc(n * c->V));
+            CU(cudaMemset(c->approx_du.p, 0, sizeof(double) * n * c->V));
+        }
+    }
+    if (c->diagnostics && has_visc(c)) {
+        CHECK(c->eps.alloc(n));
+        CHECK(c->eps_uw.alloc(n));
+        CHECK(c->eps_rv.alloc(n));
+        CHECK(c->eps_c.alloc(n));
+        CHECK(c->residual.alloc(n * c->V));
+        CU(cudaMemset(c->eps.p, 0, sizeof(double) * n));
+        CU(cudaMemset(c->eps_uw.p, 0, sizeof(double) * n));
+        CU(cudaMemset(c->eps_rv.p, 0, sizeof(double) * n));
+        CU(cudaMemset(c->eps_c.p, 0, sizeof(double) * n));
+        CU(cudaMemset(c->residual.p, 0, sizeof(double) * n * c->V));
+    }
+    // boundary indices: caller numbering -> device rows
+    if (c->have_perm) {
+        for (auto *g : c->bcs) {
+            if (g->nb == 0) continue;
+            std::vector<int> idx(g->nb);
+            CU(cudaMemcpy(idx.data(), g->idx.p, sizeof(int) * g->nb, cudaMemcpyDeviceToHost));
+            for (auto &i : idx) i = c->iperm[i];
+            CU(cudaMemcpy(g->idx.p, idx.data(), sizeof(int) * g->nb, cudaMemcpyHostToDevice));
+        }
+    }
+    CHECK(c->uprev.alloc(n * c->V));
+    // free host staging
+    c->host_ops[0] = HostCsc();
+    c->host_ops[1] = HostCsc();
+    c->host_ell = Csr2();
+    c->finalized = true;
+    return MFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// state transfer
+// ------------------------------------------------------------------------------------------------------
+static int upload_soa(mft_ctx *c, const double *const *soa, double *dst_aos)
+{
+    const int64_t n = c->n_tot;
+    for (int v = 0; v < c->V; ++v) {
+        if (!soa || !soa[v]) return fail(MFT_EINVAL, "state component %d is NULL", v);
+        CU(cudaMemcpyAsync(c->stage_soa.p + (int64_t)v * n, soa[v], sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    ScopedTimer t(c, MFT_K_OTHER);
+    if (c->V == 4)
+        k_pack<4><<<grid_for(n, 256), 256, 0, c->stream>>>(c->stage_soa.p, n, c->d_perm.p, reinterpret_cast<Vec<4> *>(dst_aos), n);
+    else
+        k_pack<1><<<grid_for(n, 256), 256, 0, c->stream>>>(c->stage_soa.p, n, c->d_perm.p, reinterpret_cast<Vec<1> *>(dst_aos), n);
+    c->launches++;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}
+
+static int download_soa(mft_ctx *c, const double *src_aos, double *const *soa)
+{
+    const int64_t n = c->n_tot;
+    {
+        ScopedTimer t(c, MFT_K_OTHER);
+        if (c->V == 4)
+            k_unpack<4><<<grid_for(n, 256), 256, 0, c->stream>>>(reinterpret_cast<const Vec<4> *>(src_aos), c->d_perm.p, c->stage_soa.p, n, n);
+        else
+            k_unpack<1><<<grid_for(n, 256), 256, 0, c->stream>>>(reinterpret_cast<const Vec<1> *>(src_aos), c->d_perm.p, c->stage_soa.p, n, n);
+        c->launches++;
+        LAUNCH_CHECK();
+    }
+    for (int v = 0; v < c->V; ++v) {
+        if (!soa || !soa[v]) return fail(MFT_EINVAL, "state component %d is NULL", v);
+        CU(cudaMemcpyAsync(soa[v], c->stage_soa.p + (int64_t)v * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return MFT_OK;
+}
+
+extern "C" int mft_upload_state(mft_ctx *c, const double *const *u_soa)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    CHECK(upload_soa(c, u_soa, c->u.p));
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_fsal = false;
+    return MFT_OK;
+}
+extern "C" int mft_download_state(mft_ctx *c, double *const *u_soa)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    CHECK(download_soa(c, c->u.p, u_soa));
+    CU(cudaStreamSynchronize(c->stream));
+    return MFT_OK;
+}
+extern "C" int mft_download_du(mft_ctx *c, double *const *du_soa)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    CHECK(download_soa(c, c->du.p, du_soa));
+    CU(cudaStreamSynchronize(c->stream));
+    return MFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// halo exchange (NCCL send/recv straight from/to device buffers; receive lands in the halo tail)
+// ------------------------------------------------------------------------------------------------------
+template <int W>
+static int halo_exchange(mft_ctx *c, double *field /* AoS, W doubles per point */)
+{
+    if (c->nranks <= 1 || (c->n_send == 0 && c->n_halo == 0)) return MFT_OK;
+    if (!c->comm) return fail(MFT_EINVAL, "halo exchange requested but mft_comm_init was not called");
+    if (c->n_send > 0) {
+        ScopedTimer t(c, MFT_K_OTHER);
+        k_halo_pack<W><<<grid_for(c->n_send, 256), 256, 0, c->stream>>>(reinterpret_cast<const Vec<W> *>(field), c->send_rows.p,
+                                                                     reinterpret_cast<Vec<W> *>(c->send_buf.p), c->n_send);
+        c->launches++;
+        LAUNCH_CHECK();
+    }
+    NcclApi *N = c->nccl;
+    if (N->groupStart() != 0) return fail(MFT_ENCCL, "ncclGroupStart failed");
+    for (size_t p = 0; p < c->peers.size(); ++p) {
+        const int64_t ns = c->send_off[p + 1] - c->send_off[p];
+        const int64_t nr = c->recv_off[p + 1] - c->recv_off[p];
+        if (ns > 0 && N->send(c->send_buf.p + c->send_off[p] * W, (size_t)ns * W, NCCL_DOUBLE, c->peers[p], c->comm, c->stream) != 0)
+            return fail(MFT_ENCCL, "ncclSend failed: %s", N->lastError(c->comm));
+        if (nr > 0 && N->recv(field + (c->n_local + c->recv_off[p]) * W, (size_t)nr * W, NCCL_DOUBLE, c->peers[p], c->comm, c->stream) != 0)
+            return fail(MFT_ENCCL, "ncclRecv failed: %s", N->lastError(c->comm));
+    }
+    if (N->groupEnd() != 0) return fail(MFT_ENCCL, "ncclGroupEnd failed: %s", N->lastError(c->comm));
+    return MFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// kernels launch helpers
+// ------------------------------------------------------------------------------------------------------
+static int launch_boundary(mft_ctx *c, bool write_du)
+{
+    for (auto *g : c->bcs) {
+        if (g->nb == 0 || g->kind == MFT_BC_DO_NOTHING) continue;
+        ScopedTimer t(c, MFT_K_BC);
+        BcArgs a{g->kind, g->nb, g->idx.p, g->normals.p, g->values.p, c->u.p, write_du ? c->du.p : nullptr};
+        if (c->V == 4)
+            k_boundary<4><<<grid_for(g->nb, 128), 128, 0, c->stream>>>(a);
+        else
+            k_boundary<1><<<grid_for(g->nb, 128), 128, 0, c->stream>>>(a);
+        c->launches++;
+        LAUNCH_CHECK();
+    }
+    return MFT_OK;
+}
+
+template <int V, int EQ>
+static int launch_pass_a_t(mft_ctx *c, const PassAArgs &a, bool do_flux, int visc)
+{
+    const int grid = grid_for(a.n_rows, 128);
+#define PA(EX, DF, VI) k_pass_a<V, EQ, EX, DF, VI><<<grid, 128, 0, c->stream>>>(a)
+    if constexpr (V == 4) {
+        if (c->exact) {
+            if (do_flux && visc == VISC_NONE) PA(true, true, VISC_NONE);
+            else if (do_flux && visc == VISC_UPWIND) PA(true, true, VISC_UPWIND);
+            else if (do_flux && visc == VISC_RESIDUAL) PA(true, true, VISC_RESIDUAL);
+            else if (!do_flux && visc == VISC_UPWIND) PA(true, false, VISC_UPWIND);
+            else if (!do_flux && visc == VISC_RESIDUAL) PA(true, false, VISC_RESIDUAL);
+            else return fail(MFT_EINVAL, "pass A: nothing to do");
+        } else {
+            if (do_flux && visc == VISC_NONE) PA(false, true, VISC_NONE);
+            else if (do_flux && visc == VISC_UPWIND) PA(false, true, VISC_UPWIND);
+            else if (do_flux && visc == VISC_RESIDUAL) PA(false, true, VISC_RESIDUAL);
+            else if (!do_flux && visc == VISC_UPWIND) PA(false, false, VISC_UPWIND);
+            else if (!do_flux && visc == VISC_RESIDUAL) PA(false, false, VISC_RESIDUAL);
+            else return fail(MFT_EINVAL, "pass A: nothing to do");
+        }
+    } else {
+        if (!do_flux || visc != VISC_NONE) return fail(MFT_ENOTSUP, "viscosity sources need Euler 2-D");
+        if (c->exact) PA(true, true, VISC_NONE);
+        else PA(false, true, VISC_NONE);
+    }
+#undef PA
+    c->launches++;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}
+
+static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bool accumulate)
+{
+    ScopedTimer t(c, MFT_K_PASS_A);
+    PassAArgs a{};
+    a.op = c->fwd.view2();
+    a.u = c->u.p;
+    a.du = c->du.p;
+    a.g = c->g.p;
+    a.approx_du = c->approx_du.p;
+    a.norms = c->stats.p + 2 * c->V;
+    a.n_rows = c->n_local;
+    a.eqp0 = c->eqp[0];
+    a.eqp1 = c->eqp[1];
+    a.c_uw = s ? s->c_uw : 0.0;
+    a.c_rv = s ? s->c_rv : 0.0;
+    a.dx_avg = s ? s->dx_avg : 0.0;
+    a.success_iter_zero = c->success_iter == 0;
+    a.accumulate = accumulate ? 1 : 0;
+    if (c->diagnostics && visc != VISC_NONE) {
+        a.eps = c->eps.p;
+        a.eps_uw = c->eps_uw.p;
+        a.eps_rv = c->eps_rv.p;
+        a.eps_c = c->eps_c.p;
+        a.residual = c->residual.p;
+    }
+    if (c->V == 4) return launch_pass_a_t<4, EQ_EULER2D>(c, a, do_flux, visc);
+    return launch_pass_a_t<1, EQ_ADVECTION2D>(c, a, do_flux, visc);
+}
+
+static int launch_pass_b(mft_ctx *c)
+{
+    ScopedTimer t(c, MFT_K_PASS_B);
+    PassBArgs a{c->tra.view2(), c->g.p, c->du.p, c->n_local};
+    const int grid = grid_for(a.n_rows, 128);
+    if (c->exact) k_pass_b<4, true><<<grid, 128, 0, c->stream>>>(a);
+    else k_pass_b<4, false><<<grid, 128, 0, c->stream>>>(a);
+    c->launches++;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}
+
+static int launch_spmv(mft_ctx *c, const Source *s)
+{
+    ScopedTimer t(c, MFT_K_OTHER);
+    SpmvArgs a{s->hv.view1(), c->u.p, c->du.p, c->n_local, -s->gamma};
+    const int grid = grid_for(a.n_rows, 128);
+    if (c->V == 4) {
+        if (c->exact) k_spmv_accum<4, true><<<grid, 128, 0, c->stream>>>(a);
+        else k_spmv_accum<4, false><<<grid, 128, 0, c->stream>>>(a);
+    } else {
+        if (c->exact) k_spmv_accum<1, true><<<grid, 128, 0, c->stream>>>(a);
+        else k_spmv_accum<1, false><<<grid, 128, 0, c->stream>>>(a);
+    }
+    c->launches++;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}
+
+// ode_mean + ode_maximum of |u - mean| on the post-BC state (hyperviscosity.jl:305-311)
+static int launch_norms(mft_ctx *c)
+{
+    ScopedTimer t(c, MFT_K_REDUCE);
+    const int V = 4;
+    const int64_t n = c->n_local;
+    const Vec<4> *u = reinterpret_cast<const Vec<4> *>(c->u.p);
+    double *sum = c->stats.p, *mean = c->stats.p + V, *norms = c->stats.p + 2 * V;
+    k_reduce_sum<4><<<c->red_blocks, 256, 0, c->stream>>>(u, n, c->partial.p);
+    c->launches++;
+    LAUNCH_CHECK();
+    const double n_global = (double)n;
+    const double divisor = c->mean_div_vn ? (double)V * n_global : n_global;
+    k_finish_mean<4><<<1, 32, 0, c->stream>>>(c->partial.p, c->red_blocks, divisor, sum);
+    c->launches++;
+    LAUNCH_CHECK();
+    if (c->max_lex) {
+        k_reduce_maxdev<4, true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, mean, c->partial.p);
+        k_finish_norms<4, true><<<1, 32, 0, c->stream>>>(c->partial.p, c->red_blocks, norms, 1);
+    } else {
+        k_reduce_maxdev<4, false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, mean, c->partial.p);
+        k_finish_norms<4, false><<<1, 32, 0, c->stream>>>(c->partial.p, c->red_blocks, norms, 1);
+    }
+    c->launches += 2;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}
+
+static int launch_norms_multi(mft_ctx *c);
+
+// one source functor call on the resident state
+static int apply_source_dev(mft_ctx *c, Source *s)
+{
+    if (s->kind == MFT_SRC_HV_FLYER || s->kind == MFT_SRC_HV_TOMINEC) return launch_spmv(c, s);
+    const int visc = s->kind == MFT_SRC_UPWIND ? VISC_UPWIND : VISC_RESIDUAL;
+    if (visc == VISC_RESIDUAL) CHECK(c->nranks > 1 ? launch_norms_multi(c) : launch_norms(c));
+    CHECK(launch_pass_a(c, false, visc, s, false));
+    CHECK(halo_exchange<8>(c, c->g.p));
+    return launch_pass_b(c);
+}
+
+// Trixi.rhs! on the resident state: du <- rhs(u), u gets the strong BCs
+static int rhs_device(mft_ctx *c, double t)
+{
+    (void)t;  // Dirichlet tables are refreshed by the caller (mft_update_boundary_values) when time-dependent
+    // update_halos! (parallel_rbfsolver.jl:98-101) happens before the BC pass in the reference; BC points are owned
+    // points, and halo copies of boundary points must carry the BC-imposed value the owner computes, so the
+    // exchange runs after the owner applied its BCs.
+    CHECK(launch_boundary(c, false));  // pass 1: du is formed from 0 below, only u needs writing
+    CHECK(halo_exchange<4 /*V set below*/>(c, c->u.p));
+    size_t first = 0;
+    if (!c->srcs.empty() && (c->srcs[0]->kind == MFT_SRC_UPWIND || c->srcs[0]->kind == MFT_SRC_RESIDUAL)) {
+        Source *s = c->srcs[0];
+        const int visc = s->kind == MFT_SRC_UPWIND ? VISC_UPWIND : VISC_RESIDUAL;
+        if (visc == VISC_RESIDUAL) CHECK(c->nranks > 1 ? launch_norms_multi(c) : launch_norms(c));
+        CHECK(launch_pass_a(c, true, visc, s, false));  // flux divergence + D u + eps + g in one sweep
+        CHECK(halo_exchange<8>(c, c->g.p));
+        CHECK(launch_pass_b(c));
+        first = 1;
+    } else {
+        CHECK(launch_pass_a(c, true, VISC_NONE, nullptr, false));
+    }
+    for (size_t i = first; i < c->srcs.size(); ++i) CHECK(apply_source_dev(c, c->srcs[i]));
+    CHECK(launch_boundary(c, true));  // pass 2
+    return MFT_OK;
+}
+
+extern "C" int mft_rhs(mft_ctx *c, double t, double *const *u_soa, double *const *du_soa, int mem)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    if (c->V == 1 && c->nranks > 1) return fail(MFT_ENOTSUP, "multi-rank advection is not implemented");
+    if (mem == MFT_MEM_HOST) {
+        CHECK(upload_soa(c, u_soa, c->u.p));
+        c->have_fsal = false;
+    } else if (mem != MFT_MEM_DEVICE) {
+        return fail(MFT_EINVAL, "mft_rhs: mem must be MFT_MEM_HOST or MFT_MEM_DEVICE");
+    }
+    CHECK(rhs_device(c, t));
+    if (mem == MFT_MEM_HOST) {
+        CHECK(download_soa(c, c->u.p, u_soa));
+        CU(cudaStreamSynchronize(c->stream));  // stage_soa is reused by the next download
+        CHECK(download_soa(c, c->du.p, du_soa));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return MFT_OK;
+}
+
+extern "C" int mft_calc_fluxes(mft_ctx *c, double *const *u_soa, double *const *du_soa)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    CHECK(upload_soa(c, u_soa, c->u.p));
+    CHECK(upload_soa(c, du_soa, c->du.p));
+    c->have_fsal = false;
+    CHECK(launch_pass_a(c, true, VISC_NONE, nullptr, true));
+    CHECK(download_soa(c, c->du.p, du_soa));
+    CU(cudaStreamSynchronize(c->stream));
+    return MFT_OK;
+}
+
+extern "C" int mft_apply_source(mft_ctx *c, int index, double t, double *const *u_soa, double *const *du_soa)
+{
+    (void)t;
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    if (index < 0 || index >= (int)c->srcs.size()) return fail(MFT_EINVAL, "mft_apply_source: index %d out of range", index);
+    CHECK(upload_soa(c, u_soa, c->u.p));
+    CHECK(upload_soa(c, du_soa, c->du.p));
+    c->have_fsal = false;
+    CHECK(apply_source_dev(c, c->srcs[index]));
+    CHECK(download_soa(c, c->du.p, du_soa));
+    CU(cudaStreamSynchronize(c->stream));
+    return MFT_OK;
+}
+
+extern "C" int mft_boundary_pass(mft_ctx *c, double t, double *const *u_soa, double *const *du_soa)
+{
+    (void)t;
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    CHECK(upload_soa(c, u_soa, c->u.p));
+    CHECK(upload_soa(c, du_soa, c->du.p));
+    c->have_fsal = false;
+    CHECK(launch_boundary(c, true));
+    CHECK(download_soa(c, c->u.p, u_soa));
+    CU(cudaStreamSynchronize(c->stream));
+    CHECK(download_soa(c, c->du.p, du_soa));
+    CU(cudaStreamSynchronize(c->stream));
+    return MFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// history + time stepping
+// ------------------------------------------------------------------------------------------------------
+// time_deriv_weights! history.jl:131-152: w = scale * (A' \ b'), LU with partial pivoting
+static void time_deriv_weights(int m, const double *t, double *w)
+{
+    double maxabs = 0.0;
+    for (int i = 0; i < m; ++i) maxabs = std::fmax(maxabs, std::fabs(t[i]));
+    const double scale = 1.0 / maxabs;
+    double ts[8], M[64], b[8];
+    for (int i = 0; i < m; ++i) ts[i] = t[i] * scale;
+    for (int k = 0; k < m; ++k) {
+        for (int i = 0; i < m; ++i) M[k * m + i] = std::pow(ts[i], (double)k);
+        b[k] = (double)k * std::pow(ts[0], (double)(k - 1));
+    }
+    for (int col = 0; col < m; ++col) {
+        int piv = col;
+        double best = std::fabs(M[col * m + col]);
+        for (int r = col + 1; r < m; ++r)
+            if (std::fabs(M[r * m + col]) > best) {
+                best = std::fabs(M[r * m + col]);
+                piv = r;
+            }
+        if (piv != col) {
+            for (int j = 0; j < m; ++j) std::swap(M[col * m + j], M[piv * m + j]);
+            std::swap(b[col], b[piv]);
+        }
+        for (int r = col + 1; r < m; ++r) {
+            const double l = M[r * m + col] / M[col * m + col];
+            M[r * m + col] = l;
+            for (int j = col + 1; j < m; ++j) M[r * m + j] = M[r * m + j] - l * M[col * m + j];
+            b[r] = b[r] - l * b[col];
+        }
+    }
+    for (int r = m - 1; r >= 0; --r) {
+        double s = b[r];
+        for (int j = r + 1; j < m; ++j) s = s - M[r * m + j] * b[j];
+        b[r] = s / M[r * m + r];
+    }
+    for (int i = 0; i < m; ++i) w[i] = scale * b[i];
+}
+
+static int history_push_common(mft_ctx *c, double t, int64_t success_iter, bool given, int nterms,
+                               const double *weights_or_null, int approx_order)
+{
+    if (c->nslots == 0) return MFT_OK;  // modify_cache! fallback: no-op without a residual-viscosity source (history.jl:87-89)
+    c->success_iter = success_iter;
+    // shift_soln_history! history.jl:105-111 as a ring buffer: slot 0 = most recent
+    c->hist_head = (c->hist_head + c->nslots - 1) % c->nslots;
+    for (int s = c->nslots - 1; s >= 1; --s) c->time_history[s] = c->time_history[s - 1];
+    c->time_history[0] = t;
+    const int64_t len = c->n_tot * c->V;
+    CU(cudaMemcpyAsync(c->hist[c->hist_head].p, c->u.p, sizeof(double) * len, cudaMemcpyDeviceToDevice, c->stream));
+    // update_approx_du! history.jl:113-129
+    ApproxDuArgs a{};
+    a.out = c->approx_du.p;
+    a.len = len;
+    a.nterms = 0;
+    if (success_iter > 0) {
+        int ntp = nterms;
+        if (!given) {
+            ntp = (int)std::min<int64_t>(success_iter + 1, (int64_t)approx_order + 1);
+            if (ntp > c->nslots) return fail(MFT_EINVAL, "mft_history_push: approx_order+1 = %d exceeds polydeg+1 = %d history slots", approx_order + 1, c->nslots);
+            time_deriv_weights(ntp, c->time_history.data(), c->time_weights.data());
+        } else {
+            if (ntp > c->nslots || ntp > 8) return fail(MFT_EINVAL, "mft_history_push_weights: %d weights exceed %d history slots", ntp, c->nslots);
+            for (int i = 0; i < ntp; ++i) c->time_weights[i] = weights_or_null[i];
+        }
+        a.nterms = ntp;
+        for (int s = 0; s < ntp; ++s) {
+            a.hist[s] = c->hist[(c->hist_head + s) % c->nslots].p;
+            a.w[s] = c->time_weights[s];
+        }
+    }
+    {
+        ScopedTimer tm(c, MFT_K_OTHER);
+        k_approx_du<<<c->red_blocks * 2, 256, 0, c->stream>>>(a);
+        c->launches++;
+        LAUNCH_CHECK();
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return MFT_OK;
+}
+
+extern "C" int mft_history_push(mft_ctx *c, double t, int64_t success_iter, int approx_order)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    if (approx_order < 0 || approx_order > 7) return fail(MFT_EINVAL, "mft_history_push: approx_order must be in [0,7]");
+    return history_push_common(c, t, success_iter, false, 0, nullptr, approx_order);
+}
+
+extern "C" int mft_history_push_weights(mft_ctx *c, double t, int64_t success_iter, int n, const double *weights)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    if (n < 0 || (n > 0 && !weights)) return fail(MFT_EINVAL, "mft_history_push_weights: bad weights");
+    return history_push_common(c, t, success_iter, true, n, weights, 0);
+}
+
+static int launch_stage(mft_ctx *c, int stage, double dt)
+{
+    ScopedTimer tm(c, MFT_K_STAGE);
+    const int64_t len = c->n_local * c->V;
+    k_ssprk33_stage<<<c->red_blocks * 2, 256, 0, c->stream>>>(stage, dt, c->uprev.p, c->du.p, c->u.p, len);
+    c->launches++;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}
+
+extern "C" int mft_ssprk_step(mft_ctx *c, int scheme, double t, double dt)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    if (scheme != MFT_SSPRK33) return fail(MFT_ENOTSUP, "mft_ssprk_step: only MFT_SSPRK33 is implemented");
+    if (!c->have_fsal) CHECK(rhs_device(c, t));  // k = f(u_n): first step only (FSAL afterwards)
+    CHECK(launch_stage(c, 1, dt));
+    CHECK(rhs_device(c, t + dt));
+    CHECK(launch_stage(c, 2, dt));
+    CHECK(rhs_device(c, t + dt / 2));
+    CHECK(launch_stage(c, 3, dt));
+    CHECK(rhs_device(c, t + dt));
+    c->have_fsal = true;
+    return MFT_OK;  // asynchronous: mft_synchronize / downloads wait
+}
+
+extern "C" int mft_synchronize(mft_ctx *c)
+{
+    NEED_CTX(c);
+    CU(cudaStreamSynchronize(c->stream));
+    return MFT_OK;
+}
+
+extern "C" int64_t mft_launch_count(mft_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int mft_set_kernel_timing(mft_ctx *c, int enable)
+{
+    NEED_CTX(c);
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto ev : c->kt.ev) cudaEventDestroy(ev);
+    c->kt.ev.clear();
+    c->kt.cls.clear();
+    c->timing = enable != 0;
+    return MFT_OK;
+}
+
+extern "C" int mft_kernel_time_ms(mft_ctx *c, int which, double *ms, int64_t *launches)
+{
+    NEED_CTX(c);
+    CU(cudaStreamSynchronize(c->stream));
+    if (which < 0) return mft_set_kernel_timing(c, c->timing);
+    double tot = 0.0;
+    int64_t cnt = 0;
+    for (size_t i = 0; i < c->kt.cls.size(); ++i) {
+        if (c->kt.cls[i] != which) continue;
+        float e = 0.f;
+        CU(cudaEventElapsedTime(&e, c->kt.ev[2 * i], c->kt.ev[2 * i + 1]));
+        tot += e;
+        cnt++;
+    }
+    if (ms) *ms = tot;
+    if (launches) *launches = cnt;
+    return MFT_OK;
+}
+
+extern "C" int mft_get_field(mft_ctx *c, int field, double *out)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    if (!out) return fail(MFT_EINVAL, "mft_get_field: out is NULL");
+    const int64_t n = c->n_tot;
+    CU(cudaStreamSynchronize(c->stream));
+    auto scalar = [&](DevBuf<double> &b) -> int {
+        if (!b.p) return fail(MFT_EINVAL, "mft_get_field: field not available (enable MFT_OPT_DIAGNOSTICS before the first compute call)");
+        k_unpack_scalar<<<grid_for(n, 256), 256, 0, c->stream>>>(b.p, c->d_perm.p, c->stage_soa.p, n);
+        c->launches++;
+        LAUNCH_CHECK();
+        CU(cudaMemcpyAsync(out, c->stage_soa.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return MFT_OK;
+    };
+    auto vecfield = [&](DevBuf<double> &b) -> int {
+        if (!b.p) return fail(MFT_EINVAL, "mft_get_field: field not available");
+        std::vector<double *> ptrs(c->V);
+        for (int v = 0; v < c->V; ++v) ptrs[v] = out + (int64_t)v * n;
+        CHECK(download_soa(c, b.p, ptrs.data()));
+        CU(cudaStreamSynchronize(c->stream));
+        return MFT_OK;
+    };
+    switch (field) {
+    case MFT_FIELD_EPS: return scalar(c->eps);
+    case MFT_FIELD_EPS_UW: return scalar(c->eps_uw);
+    case MFT_FIELD_EPS_RV: return scalar(c->eps_rv);
+    case MFT_FIELD_EPS_C: return scalar(c->eps_c);
+    case MFT_FIELD_RESIDUAL: return vecfield(c->residual);
+    case MFT_FIELD_APPROX_DU: return vecfield(c->approx_du);
+    case MFT_FIELD_NORMS:
+        CU(cudaMemcpy(out, c->stats.p + 2 * c->V, sizeof(double) * c->V, cudaMemcpyDeviceToHost));
+        return MFT_OK;
+    default: return fail(MFT_EINVAL, "mft_get_field: unknown field %d", field);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// pinned host memory helpers
+// ------------------------------------------------------------------------------------------------------
+extern "C" int mft_host_alloc(void **out, int64_t bytes)
+{
+    if (!out || bytes <= 0) return fail(MFT_EINVAL, "mft_host_alloc: bad arguments");
+    CU(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return MFT_OK;
+}
+extern "C" int mft_host_free(void *p)
+{
+    if (p) CU(cudaFreeHost(p));
+    return MFT_OK;
+}
+extern "C" int mft_host_register(void *p, int64_t bytes)
+{
+    if (!p || bytes <= 0) return fail(MFT_EINVAL, "mft_host_register: bad arguments");
+    CU(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault));
+    return MFT_OK;
+}
+extern "C" int mft_host_unregister(void *p)
+{
+    if (p) CU(cudaHostUnregister(p));
+    return MFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Hilbert space-filling-curve ordering (setup helper, host only)
+// ------------------------------------------------------------------------------------------------------
+static inline uint64_t hilbert_d(uint32_t x, uint32_t y, int bits)
+{
+    uint64_t d = 0;
+    for (uint32_t s = 1u << (bits - 1); s > 0; s >>= 1) {
+        const uint32_t rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+        d += (uint64_t)s * s * ((3u * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) {
+                x = (1u << bits) - 1u - x;
+                y = (1u << bits) - 1u - y;
+            }
+            const uint32_t tmp = x;
+            x = y;
+            y = tmp;
+        }
+    }
+    return d;
+}
+
+extern "C" int mft_sfc_order(int64_t n, const double *x, const double *y, int64_t *perm1_out)
+{
+    if (n <= 0 || !x || !y || !perm1_out) return fail(MFT_EINVAL, "mft_sfc_order: bad arguments");
+    double xmin = x[0], xmax = x[0], ymin = y[0], ymax = y[0];
+    for (int64_t i = 1; i < n; ++i) {
+        xmin = std::min(xmin, x[i]);
+        xmax = std::max(xmax, x[i]);
+        ymin = std::min(ymin, y[i]);
+        ymax = std::max(ymax, y[i]);
+    }
+    const int bits = 20;
+    const double ext = std::max(std::max(xmax - xmin, ymax - ymin), 1e-300);
+    const double scale = ((double)((1u << bits) - 1u)) / ext;
+    std::vector<std::pair<uint64_t, int64_t>> keyed((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const uint32_t qx = (uint32_t)((x[i] - xmin) * scale), qy = (uint32_t)((y[i] - ymin) * scale);
+        keyed[i] = {hilbert_d(qx, qy, bits), i};
+    }
+    std::sort(keyed.begin(), keyed.end());
+    for (int64_t d = 0; d < n; ++d) perm1_out[d] = keyed[d].second + 1;
+    return MFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// multi-GPU: NCCL (loaded at run time so single-GPU users do not need libnccl)
+// ------------------------------------------------------------------------------------------------------
+extern "C" int mft_nccl_unique_id(void *id128)
+{
+    if (!id128) return fail(MFT_EINVAL, "mft_nccl_unique_id: NULL");
+    NcclApi *N = nccl_api();
+    if (!N) return fail(MFT_ENCCL, "NCCL could not be loaded: %s", nccl_load_error());
+    if (N->getUniqueId(id128) != 0) return fail(MFT_ENCCL, "ncclGetUniqueId failed");
+    return MFT_OK;
+}
+
+extern "C" int mft_comm_init(mft_ctx *c, int nranks, int rank, const void *id128)
+{
+    NEED_CTX(c);
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id128) return fail(MFT_EINVAL, "mft_comm_init: bad arguments");
+    NcclApi *N = nccl_api();
+    if (!N) return fail(MFT_ENCCL, "NCCL could not be loaded: %s", nccl_load_error());
+    c->nccl = N;
+    if (N->commInitRank(&c->comm, nranks, id128, rank) != 0) return fail(MFT_ENCCL, "ncclCommInitRank failed");
+    c->nranks = nranks;
+    c->rank = rank;
+    CHECK(c->gather_buf.alloc((int64_t)nranks * c->V + 2 * c->V));
+    // global point count (ndofs of the parallel domain, parallel_rbfsolver.jl:10-13) = sum of the owned counts
+    double nl = (double)c->n_local, ng = 0.0;
+    CU(cudaMemcpy(c->gather_buf.p, &nl, sizeof(double), cudaMemcpyHostToDevice));
+    if (N->allReduce(c->gather_buf.p, c->gather_buf.p + 1, 1, NCCL_DOUBLE, NCCL_SUM, c->comm, c->stream) != 0)
+        return fail(MFT_ENCCL, "ncclAllReduce failed: %s", N->lastError(c->comm));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(&ng, c->gather_buf.p + 1, sizeof(double), cudaMemcpyDeviceToHost));
+    c->n_global = (int64_t)(ng + 0.5);
+    return MFT_OK;
+}
+
+extern "C" int mft_set_halo(mft_ctx *c, int npeers, const int *peers, const int64_t *send_off, const int64_t *send_idx1,
+                            const int64_t *recv_count)
+{
+    NEED_CTX(c);
+    if (npeers < 0 || (npeers > 0 && (!peers || !send_off || !recv_count))) return fail(MFT_EINVAL, "mft_set_halo: bad arguments");
+    c->peers.assign(peers, peers + npeers);
+    c->send_off.assign(send_off, send_off + npeers + 1);
+    c->recv_off.assign(npeers + 1, 0);
+    for (int p = 0; p < npeers; ++p) c->recv_off[p + 1] = c->recv_off[p] + recv_count[p];
+    if (c->recv_off[npeers] != c->n_halo) return fail(MFT_EINVAL, "mft_set_halo: receive counts sum to %lld, n_halo is %lld", (long long)c->recv_off[npeers], (long long)c->n_halo);
+    c->n_send = npeers > 0 ? c->send_off[npeers] : 0;
+    std::vector<int> rows((size_t)c->n_send);
+    for (int64_t i = 0; i < c->n_send; ++i) {
+        const int64_t p = send_idx1[i] - 1;
+        if (p < 0 || p >= c->n_local) return fail(MFT_EINVAL, "mft_set_halo: send index %lld is not an owned point", (long long)send_idx1[i]);
+        rows[i] = c->have_perm ? c->iperm[p] : (int)p;
+    }
+    CHECK(c->send_rows.upload(rows));
+    CHECK(c->send_buf.alloc(std::max<int64_t>(1, c->n_send) * 2 * c->V));
+    return MFT_OK;
+}
+
+// global ode_mean / ode_maximum across ranks (MPI.Allreduce in src/auxiliary/mpi.jl:45-46,76): all-gather the
+// per-rank partial results and combine them in rank order on every rank (deterministic, identical everywhere)
+static int launch_norms_multi(mft_ctx *c)
+{
+    ScopedTimer t(c, MFT_K_REDUCE);
+    const int V = 4;
+    NcclApi *N = c->nccl;
+    if (!c->comm) return fail(MFT_EINVAL, "multi-rank norms need mft_comm_init");
+    const int64_t n = c->n_local;
+    const Vec<4> *u = reinterpret_cast<const Vec<4> *>(c->u.p);
+    double *sum = c->stats.p, *mean = c->stats.p + V, *norms = c->stats.p + 2 * V;
+    double *mine = c->gather_buf.p + (int64_t)c->nranks * V;  // 2V doubles of scratch behind the gather area
+    k_reduce_sum<4><<<c->red_blocks, 256, 0, c->stream>>>(u, n, c->partial.p);
+    k_finish_mean<4><<<1, 32, 0, c->stream>>>(c->partial.p, c->red_blocks, 1.0, mine);  // mine[0..V) = local sum
+    c->launches += 2;
+    LAUNCH_CHECK();
+    if (N->allGather(mine, c->gather_buf.p, V, NCCL_DOUBLE, c->comm, c->stream) != 0)
+        return fail(MFT_ENCCL, "ncclAllGather failed: %s", N->lastError(c->comm));
+    const double ng = (double)c->n_global;
+    const double divisor = c->mean_div_vn ? (double)V * ng : ng;
+    k_finish_mean<4><<<1, 32, 0, c->stream>>>(c->gather_buf.p, c->nranks, divisor, sum);
+    c->launches++;
+    LAUNCH_CHECK();
+    if (c->max_lex) {
+        k_reduce_maxdev<4, true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, mean, c->partial.p);
+        k_finish_norms<4, true><<<1, 32, 0, c->stream>>>(c->partial.p, c->red_blocks, mine, 0);
+    } else {
+        k_reduce_maxdev<4, false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, mean, c->partial.p);
+        k_finish_norms<4, false><<<1, 32, 0, c->stream>>>(c->partial.p, c->red_blocks, mine, 0);
+    }
+    c->launches += 2;
+    LAUNCH_CHECK();
+    if (N->allGather(mine, c->gather_buf.p, V, NCCL_DOUBLE, c->comm, c->stream) != 0)
+        return fail(MFT_ENCCL, "ncclAllGather failed: %s", N->lastError(c->comm));
+    if (c->max_lex) k_finish_norms<4, true><<<1, 32, 0, c->stream>>>(c->gather_buf.p, c->nranks, norms, 1);
+    else k_finish_norms<4, false><<<1, 32, 0, c->stream>>>(c->gather_buf.p, c->nranks, norms, 1);
+    c->launches++;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}

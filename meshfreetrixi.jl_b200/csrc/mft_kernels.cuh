@@ -1,0 +1,684 @@
+// mft_kernels.cuh -- hand-written sm_100a kernels of the rhs! hot path (FP64, HBM-bound sparse stencil work).
+//
+// Compiled with -fmad=false: a fused multiply-add appears ONLY where the code says fma(), which is exactly
+// where the reference's `@muladd` scope (Trixi flux/cons2prim, history.jl) forms one.  SparseArrays' mul!
+// (the Dx/Dy applications) is outside @muladd -> separate multiply and add in EXACT mode.
+//
+// Data layout in HBM
+//   state (u, du, uprev, approx_du, history slots) : AoS, one Vec<V> (V doubles, 8V-byte aligned) per point
+//   g = eps .* (Dx u, Dy u)                        : AoS, one Vec<2V> per point (x-part then y-part)
+//   operators                                      : sliced ELL, slice = 32 consecutive device rows (one warp);
+//        entry (slice s, column c, lane l) lives at ((off[s] + c) * 32 + l) in idx[] / wx[] / wy[];
+//        idx < 0 marks padding.  Within a row the entries are stored in the reference's summation order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mft {
+
+constexpr int kSlice = 32;
+constexpr double kEps = 2.220446049250313e-16;  // Base.eps()
+
+template <int V>
+struct alignas(8 * V) Vec {
+    double a[V];
+};
+
+struct Ell2 {
+    const int *idx;
+    const double *wx;
+    const double *wy;
+    const int *off;  // nslices + 1 column offsets
+};
+struct Ell1 {
+    const int *idx;
+    const double *w;
+    const int *off;
+};
+
+// ---- 256-bit / 64-bit read-only loads and stores ------------------------------------------------------
+__device__ __forceinline__ Vec<4> ld_ro(const Vec<4> *p)
+{
+    Vec<4> v;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v.a[0]), "=d"(v.a[1]), "=d"(v.a[2]), "=d"(v.a[3])
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ Vec<1> ld_ro(const Vec<1> *p)
+{
+    Vec<1> v;
+    v.a[0] = __ldg(&p->a[0]);
+    return v;
+}
+__device__ __forceinline__ Vec<8> ld_ro(const Vec<8> *p)
+{
+    Vec<8> v;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v.a[0]), "=d"(v.a[1]), "=d"(v.a[2]), "=d"(v.a[3])
+                 : "l"(p));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4+32];"
+                 : "=d"(v.a[4]), "=d"(v.a[5]), "=d"(v.a[6]), "=d"(v.a[7])
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ Vec<2> ld_ro(const Vec<2> *p)
+{
+    Vec<2> v;
+    const double2 t = __ldg(reinterpret_cast<const double2 *>(p));
+    v.a[0] = t.x;
+    v.a[1] = t.y;
+    return v;
+}
+__device__ __forceinline__ void st_vec(Vec<4> *p, const Vec<4> &v)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.a[0]), "d"(v.a[1]), "d"(v.a[2]), "d"(v.a[3])
+                 : "memory");
+}
+__device__ __forceinline__ void st_vec(Vec<8> *p, const Vec<8> &v)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.a[0]), "d"(v.a[1]), "d"(v.a[2]), "d"(v.a[3])
+                 : "memory");
+    asm volatile("st.global.v4.f64 [%0+32], {%1,%2,%3,%4};" ::"l"(p), "d"(v.a[4]), "d"(v.a[5]), "d"(v.a[6]),
+                 "d"(v.a[7])
+                 : "memory");
+}
+__device__ __forceinline__ void st_vec(Vec<1> *p, const Vec<1> &v) { p->a[0] = v.a[0]; }
+__device__ __forceinline__ void st_vec(Vec<2> *p, const Vec<2> &v)
+{
+    *reinterpret_cast<double2 *>(p) = make_double2(v.a[0], v.a[1]);
+}
+
+// Julia max(::Float64, ::Float64): NaN-propagating
+__device__ __forceinline__ double jl_max(double a, double b)
+{
+    if (a != a) return a;
+    if (b != b) return b;
+    return a > b ? a : b;
+}
+
+// ---- physics (Trixi flux / cons2prim, third-party; inside @muladd) ---------------
+constexpr int EQ_EULER2D = 0;
+constexpr int EQ_ADVECTION2D = 1;
+
+__device__ __forceinline__ void euler_prim(double gamma, const Vec<4> &u, double &v1, double &v2, double &p)
+{
+    v1 = u.a[1] / u.a[0];
+    v2 = u.a[2] / u.a[0];
+    const double s = fma(u.a[1], v1, u.a[2] * v2);
+    const double e = fma(-0.5, s, u.a[3]);
+    p = (gamma - 1.0) * e;
+}
+
+template <int EQ, int V>
+struct Physics;
+
+template <>
+struct Physics<EQ_EULER2D, 4> {
+    double gamma;
+    double v1, v2, p;
+    __device__ __forceinline__ void prepare(const Vec<4> &u) { euler_prim(gamma, u, v1, v2, p); }
+    __device__ __forceinline__ Vec<4> flux_x(const Vec<4> &u) const
+    {
+        Vec<4> f;
+        f.a[0] = u.a[1];
+        f.a[1] = fma(u.a[1], v1, p);
+        f.a[2] = u.a[1] * v2;
+        f.a[3] = (u.a[3] + p) * v1;
+        return f;
+    }
+    __device__ __forceinline__ Vec<4> flux_y(const Vec<4> &u) const
+    {
+        Vec<4> f;
+        f.a[0] = u.a[2];
+        f.a[1] = u.a[2] * v1;
+        f.a[2] = fma(u.a[2], v2, p);
+        f.a[3] = (u.a[3] + p) * v2;
+        return f;
+    }
+};
+
+template <>
+struct Physics<EQ_ADVECTION2D, 1> {
+    double a1, a2;
+    __device__ __forceinline__ void prepare(const Vec<1> &) {}
+    __device__ __forceinline__ Vec<1> flux_x(const Vec<1> &u) const { return Vec<1>{{a1 * u.a[0]}}; }
+    __device__ __forceinline__ Vec<1> flux_y(const Vec<1> &u) const { return Vec<1>{{a2 * u.a[0]}}; }
+};
+
+// ---- pass A: fused flux evaluation + Dx/Dy stencil apply (+ D u, viscosity limiter, g = eps .* D u) --------
+// replaces calc_fluxes! (rbfsolver.jl:247-265) and the forward half of the viscosity sources
+// (hyperviscosity.jl:246-349, 364-373 / 393-402).  One thread per row; a warp owns one ELL slice, so the
+// index / weight streams are read as fully coalesced 128-B / 256-B requests and each neighbour state is one
+// 32-byte sector fetched with a single 256-bit load.
+struct PassAArgs {
+    Ell2 op;
+    const void *u;
+    void *du;
+    void *g;
+    const void *approx_du;
+    const double *norms;  // V doubles on device (n_inf_norms), residual mode
+    int64_t n_rows;
+    double eqp0, eqp1;
+    double c_uw, c_rv, dx_avg;
+    int success_iter_zero;
+    int accumulate;  // 1: start from the du in memory (calc_fluxes! semantics); 0: start from 0 (after reset_du!)
+    // diagnostics (nullable)
+    double *eps_uw, *eps_rv, *eps, *eps_c;
+    void *residual;
+};
+
+constexpr int VISC_NONE = 0;
+constexpr int VISC_UPWIND = 1;
+constexpr int VISC_RESIDUAL = 2;
+
+template <int V, int EQ, bool EXACT, bool DO_FLUX, int VISC>
+__global__ void __launch_bounds__(128) k_pass_a(const PassAArgs A)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= A.n_rows) return;
+    const int64_t slice = row >> 5;
+    const int lane = (int)(row & 31);
+    const int off = A.op.off[slice];
+    const int width = A.op.off[slice + 1] - off;
+    const int64_t base = (int64_t)off * kSlice + lane;
+    const int *__restrict__ ip = A.op.idx + base;
+    const double *__restrict__ wxp = A.op.wx + base;
+    const double *__restrict__ wyp = A.op.wy + base;
+    const Vec<V> *__restrict__ u = reinterpret_cast<const Vec<V> *>(A.u);
+
+    Physics<EQ, V> ph;
+    if constexpr (EQ == EQ_EULER2D) {
+        ph.gamma = A.eqp0;
+    } else {
+        ph.a1 = A.eqp0;
+        ph.a2 = A.eqp1;
+    }
+
+    Vec<V> acc, gx, gy;
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc.a[v] = gx.a[v] = gy.a[v] = 0.0;
+    if (DO_FLUX && A.accumulate) acc = reinterpret_cast<const Vec<V> *>(A.du)[row];
+
+    if constexpr (EXACT) {
+        // reference order: all Dx terms in ascending column order, then all Dy terms, separate mul and add
+        // (SparseArrays mul!).  alpha = -1 is folded into the flux first: w * (-F).
+#pragma unroll 4
+        for (int c = 0; c < width; ++c) {
+            const int j = ip[(int64_t)c * kSlice];
+            if (j < 0) continue;
+            const double wx = wxp[(int64_t)c * kSlice];
+            const Vec<V> uj = ld_ro(u + j);
+            if constexpr (DO_FLUX) {
+                ph.prepare(uj);
+                const Vec<V> f = ph.flux_x(uj);
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc.a[v] = acc.a[v] + wx * (-f.a[v]);
+            }
+            if constexpr (VISC != VISC_NONE) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) gx.a[v] = gx.a[v] + wx * uj.a[v];
+            }
+        }
+#pragma unroll 4
+        for (int c = 0; c < width; ++c) {
+            const int j = ip[(int64_t)c * kSlice];
+            if (j < 0) continue;
+            const double wy = wyp[(int64_t)c * kSlice];
+            const Vec<V> uj = ld_ro(u + j);
+            if constexpr (DO_FLUX) {
+                ph.prepare(uj);
+                const Vec<V> f = ph.flux_y(uj);
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc.a[v] = acc.a[v] + wy * (-f.a[v]);
+            }
+            if constexpr (VISC != VISC_NONE) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) gy.a[v] = gy.a[v] + wy * uj.a[v];
+            }
+        }
+    } else {
+        // single sweep, FMA accumulation (not the reference's rounding sequence; agrees to ~1e-13 normwise)
+#pragma unroll 4
+        for (int c = 0; c < width; ++c) {
+            const int j = ip[(int64_t)c * kSlice];
+            if (j < 0) continue;
+            const double wx = wxp[(int64_t)c * kSlice];
+            const double wy = wyp[(int64_t)c * kSlice];
+            const Vec<V> uj = ld_ro(u + j);
+            if constexpr (DO_FLUX) {
+                ph.prepare(uj);
+                const Vec<V> f = ph.flux_x(uj);
+                const Vec<V> h = ph.flux_y(uj);
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc.a[v] = fma(-wy, h.a[v], fma(-wx, f.a[v], acc.a[v]));
+            }
+            if constexpr (VISC != VISC_NONE) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    gx.a[v] = fma(wx, uj.a[v], gx.a[v]);
+                    gy.a[v] = fma(wy, uj.a[v], gy.a[v]);
+                }
+            }
+        }
+    }
+
+    if constexpr (DO_FLUX) st_vec(reinterpret_cast<Vec<V> *>(A.du) + row, acc);
+
+    if constexpr (VISC != VISC_NONE) {
+        static_assert(VISC == VISC_NONE || (EQ == EQ_EULER2D && V == 4), "viscosity sources are Euler-2D only");
+        // update_upwind_visc!  hyperviscosity.jl:246-285
+        const Vec<V> ui = ld_ro(u + row);
+        double v1, v2, p;
+        euler_prim(A.eqp0, ui, v1, v2, p);
+        const double speed = sqrt(v1 * v1 + v2 * v2);
+        double sound;
+        if (p < 0.0 || ui.a[0] < 0.0) {
+            sound = 0.0;
+        } else {
+            sound = sqrt(A.eqp0 * p / ui.a[0]);
+        }
+        const double e_uw = A.c_uw * 0.5 * A.dx_avg * (speed + sound);
+        double e = e_uw, e_rv = 0.0, e_c = 1.0;
+        if constexpr (VISC == VISC_RESIDUAL) {
+            // update_residual_visc! :289-329 (pointwise part) and update_visc! :331-349
+            Vec<V> dui;
+            if constexpr (DO_FLUX) {
+                dui = acc;
+            } else {
+                dui = reinterpret_cast<const Vec<V> *>(A.du)[row];
+            }
+            const Vec<V> ad = ld_ro(reinterpret_cast<const Vec<V> *>(A.approx_du) + row);
+            Vec<V> res;
+#pragma unroll
+            for (int v = 0; v < V; ++v) res.a[v] = fabs(ad.a[v] - dui.a[v]);
+            double mx = res.a[0] / A.norms[0];
+#pragma unroll
+            for (int v = 1; v < V; ++v) mx = jl_max(mx, res.a[v] / A.norms[v]);
+            e_rv = 0.5 * A.c_rv * (A.dx_avg * A.dx_avg) * mx;
+            if (isnan(e_rv) || isinf(e_rv) || A.success_iter_zero) {
+                if (isnan(e_uw) || isinf(e_uw)) {
+                    e = kEps;
+                    e_c = 2.0;
+                } else {
+                    e = e_uw;
+                    e_c = 1.0;
+                }
+            } else {
+                e = e_rv < e_uw ? e_rv : e_uw;
+                e_c = e_rv < e_uw ? 0.0 : 1.0;
+            }
+            if (A.residual) st_vec(reinterpret_cast<Vec<V> *>(A.residual) + row, res);
+        }
+        if (A.eps) {
+            A.eps[row] = e;
+            A.eps_uw[row] = e_uw;
+            A.eps_rv[row] = e_rv;
+            A.eps_c[row] = e_c;
+        }
+        Vec<2 * V> gout;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            gout.a[v] = e * gx.a[v];
+            gout.a[V + v] = e * gy.a[v];
+        }
+        st_vec(reinterpret_cast<Vec<2 * V> *>(A.g) + row, gout);
+    }
+}
+
+// ---- pass B: du -= Dx' gX + Dy' gY over the transposed sliced-ELL operator --------------------------------
+// adjoint mul! (call sites hyperviscosity.jl:376-377, 405-406):
+//   tmp = sum_j A[j,i] * x[j] (ascending j), then C[i] += tmp * (-1); x-direction first, then y.
+struct PassBArgs {
+    Ell2 opT;
+    const void *g;
+    void *du;
+    int64_t n_rows;
+};
+
+template <int V, bool EXACT>
+__global__ void __launch_bounds__(128) k_pass_b(const PassBArgs A)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= A.n_rows) return;
+    const int64_t slice = row >> 5;
+    const int lane = (int)(row & 31);
+    const int off = A.opT.off[slice];
+    const int width = A.opT.off[slice + 1] - off;
+    const int64_t base = (int64_t)off * kSlice + lane;
+    const int *__restrict__ ip = A.opT.idx + base;
+    const double *__restrict__ wxp = A.opT.wx + base;
+    const double *__restrict__ wyp = A.opT.wy + base;
+    const Vec<2 * V> *__restrict__ g = reinterpret_cast<const Vec<2 * V> *>(A.g);
+
+    Vec<V> tx, ty;
+#pragma unroll
+    for (int v = 0; v < V; ++v) tx.a[v] = ty.a[v] = 0.0;
+#pragma unroll 4
+    for (int c = 0; c < width; ++c) {
+        const int j = ip[(int64_t)c * kSlice];
+        if (j < 0) continue;
+        const double wx = wxp[(int64_t)c * kSlice];
+        const double wy = wyp[(int64_t)c * kSlice];
+        const Vec<2 * V> gj = ld_ro(g + j);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            if constexpr (EXACT) {
+                tx.a[v] = tx.a[v] + wx * gj.a[v];
+                ty.a[v] = ty.a[v] + wy * gj.a[V + v];
+            } else {
+                tx.a[v] = fma(wx, gj.a[v], tx.a[v]);
+                ty.a[v] = fma(wy, gj.a[V + v], ty.a[v]);
+            }
+        }
+    }
+    Vec<V> *dup = reinterpret_cast<Vec<V> *>(A.du) + row;
+    Vec<V> d = *dup;
+#pragma unroll
+    for (int v = 0; v < V; ++v) d.a[v] = (d.a[v] + tx.a[v] * -1.0) + ty.a[v] * -1.0;
+    st_vec(dup, d);
+}
+
+// ---- generic single-matrix source: du += alpha * H u  (hyperviscosity, hyperviscosity.jl:52-64,121-134) ----
+struct SpmvArgs {
+    Ell1 op;
+    const void *x;
+    void *y;
+    int64_t n_rows;
+    double alpha;
+};
+
+template <int V, bool EXACT>
+__global__ void __launch_bounds__(128) k_spmv_accum(const SpmvArgs A)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= A.n_rows) return;
+    const int64_t slice = row >> 5;
+    const int lane = (int)(row & 31);
+    const int off = A.op.off[slice];
+    const int width = A.op.off[slice + 1] - off;
+    const int64_t base = (int64_t)off * kSlice + lane;
+    const int *__restrict__ ip = A.op.idx + base;
+    const double *__restrict__ wp = A.op.w + base;
+    const Vec<V> *__restrict__ x = reinterpret_cast<const Vec<V> *>(A.x);
+    Vec<V> *yp = reinterpret_cast<Vec<V> *>(A.y) + row;
+    Vec<V> acc = *yp;
+#pragma unroll 4
+    for (int c = 0; c < width; ++c) {
+        const int j = ip[(int64_t)c * kSlice];
+        if (j < 0) continue;
+        const double w = wp[(int64_t)c * kSlice];
+        const Vec<V> xj = ld_ro(x + j);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            if constexpr (EXACT) {
+                acc.a[v] = acc.a[v] + w * (xj.a[v] * A.alpha);
+            } else {
+                acc.a[v] = fma(w, xj.a[v] * A.alpha, acc.a[v]);
+            }
+        }
+    }
+    st_vec(yp, acc);
+}
+
+// ---- strong boundary conditions (calc_single_boundary_flux!, rbfsolver.jl:288-318) -------------------------
+struct BcArgs {
+    int kind;
+    int64_t nb;
+    const int *idx;         // device rows
+    const double *normals;  // nb x 2
+    const double *values;   // nb x V (AoS)
+    void *u;
+    void *du;  // nullable: skip du writes (du not formed yet)
+};
+
+template <int V>
+__global__ void k_boundary(const BcArgs A)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A.nb) return;
+    const int b = A.idx[j];
+    Vec<V> *u = reinterpret_cast<Vec<V> *>(A.u) + b;
+    Vec<V> *du = A.du ? reinterpret_cast<Vec<V> *>(A.du) + b : nullptr;
+    if (A.kind == 0) {  // Dirichlet  PointCloudBCs.jl:49-63
+        Vec<V> val;
+#pragma unroll
+        for (int v = 0; v < V; ++v) val.a[v] = A.values[j * V + v];
+        *u = val;
+        if (du) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) du->a[v] = 0.0;
+        }
+    } else if (A.kind == 1) {  // slip wall  PointCloudBCs.jl:15-21, 87-106
+        if constexpr (V == 4) {
+            const double nx0 = A.normals[2 * j], ny0 = A.normals[2 * j + 1];
+            const double nrm = sqrt(nx0 * nx0 + ny0 * ny0);
+            const double nx = nx0 / nrm, ny = ny0 / nrm;
+            const double m1 = u->a[1], m2 = u->a[2];
+            const double vdotn = m1 * nx + m2 * ny;
+            u->a[1] = m1 - vdotn * nx;
+            u->a[2] = m2 - vdotn * ny;
+            if (du) {
+                du->a[1] = 0.0;
+                du->a[2] = 0.0;
+            }
+        }
+    }
+}
+
+// ---- reductions for update_residual_visc! (ode_mean / ode_maximum, src/auxiliary/mpi.jl:40-81) --------------
+// two-level and deterministic: every block writes one partial, a single-block kernel finishes.
+template <int V>
+__global__ void __launch_bounds__(256) k_reduce_sum(const Vec<V> *__restrict__ u, int64_t n, double *partial)
+{
+    double s[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) s[v] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Vec<V> x = ld_ro(u + i);
+#pragma unroll
+        for (int v = 0; v < V; ++v) s[v] += x.a[v];
+    }
+    __shared__ double sh[8][V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        for (int o = 16; o > 0; o >>= 1) s[v] += __shfl_down_sync(0xffffffffu, s[v], o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0)
+        for (int v = 0; v < V; ++v) sh[w][v] = s[v];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int v = 0; v < V; ++v) {
+            double t = 0.0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sh[k][v];
+            partial[(int64_t)blockIdx.x * V + v] = t;
+        }
+    }
+}
+
+// stats[0..V) = sum, then mean = sum / divisor in stats[V..2V)
+template <int V>
+__global__ void k_finish_mean(const double *partial, int nblocks, double divisor, double *stats)
+{
+    if (threadIdx.x < V) {
+        double t = 0.0;
+        for (int b = 0; b < nblocks; ++b) t += partial[(int64_t)b * V + threadIdx.x];
+        stats[threadIdx.x] = t;
+        stats[V + threadIdx.x] = t / divisor;
+    }
+}
+
+template <int V>
+__device__ __forceinline__ bool lex_less(const double *a, const double *b)
+{
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        if (a[v] < b[v]) return true;
+        if (a[v] > b[v]) return false;
+    }
+    return false;
+}
+
+// LEX: maximum over SVector elements compares lexicographically (Base isless on vectors);
+// otherwise per-component NaN-propagating max.
+template <int V, bool LEX>
+__global__ void __launch_bounds__(256) k_reduce_maxdev(const Vec<V> *__restrict__ u, int64_t n, const double *mean,
+                                                     double *partial)
+{
+    double m[V], best[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        m[v] = mean[v];
+        best[v] = -1.0;  // |.| >= 0, so -1 is below every candidate
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Vec<V> x = ld_ro(u + i);
+        double c[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) c[v] = fabs(x.a[v] - m[v]);
+        if constexpr (LEX) {
+            if (lex_less<V>(best, c)) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) best[v] = c[v];
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) best[v] = jl_max(best[v], c[v]);
+        }
+    }
+    auto combine = [&](double *a, const double *b) {
+        if constexpr (LEX) {
+            if (lex_less<V>(a, b)) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) a[v] = b[v];
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) a[v] = jl_max(a[v], b[v]);
+        }
+    };
+    for (int o = 16; o > 0; o >>= 1) {
+        double other[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) other[v] = __shfl_down_sync(0xffffffffu, best[v], o);
+        combine(best, other);
+    }
+    __shared__ double sh[8][V];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0)
+        for (int v = 0; v < V; ++v) sh[w][v] = best[v];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) combine(best, sh[k]);
+        for (int v = 0; v < V; ++v) partial[(int64_t)blockIdx.x * V + v] = best[v];
+    }
+}
+
+// norms = max over partials; 0 -> eps()  (hyperviscosity.jl:310-311)
+template <int V, bool LEX>
+__global__ void k_finish_norms(const double *partial, int nblocks, double *norms, int replace_zero)
+{
+    if (threadIdx.x == 0) {
+        double best[V];
+        for (int v = 0; v < V; ++v) best[v] = partial[v];
+        for (int b = 1; b < nblocks; ++b) {
+            const double *c = partial + (int64_t)b * V;
+            if constexpr (LEX) {
+                if (lex_less<V>(best, c))
+                    for (int v = 0; v < V; ++v) best[v] = c[v];
+            } else {
+                for (int v = 0; v < V; ++v) best[v] = jl_max(best[v], c[v]);
+            }
+        }
+        for (int v = 0; v < V; ++v) {
+            if (replace_zero && best[v] == 0.0) best[v] = kEps;
+            norms[v] = best[v];
+        }
+    }
+}
+
+// ---- SSPRK33 stage update (stage formulas: DESIGN.md "time loop") --------------------
+// stage 1 also snapshots uprev = u.  Flat over all doubles of the owned points.
+__global__ void __launch_bounds__(256) k_ssprk33_stage(int stage, double dt, double *__restrict__ uprev,
+                                                     const double *__restrict__ k, double *__restrict__ u,
+                                                     int64_t len)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const double dt2 = 2.0 * dt;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        if (stage == 1) {
+            const double up = u[i];
+            uprev[i] = up;
+            u[i] = fma(dt, k[i], up);
+        } else if (stage == 2) {
+            u[i] = fma(dt, k[i], fma(3.0, uprev[i], u[i])) / 4.0;
+        } else {
+            u[i] = fma(dt2, k[i], fma(2.0, u[i], uprev[i])) / 3.0;
+        }
+    }
+}
+
+// ---- time-history residual: approx_du = sum_s w[s] * hist[s]  (update_approx_du!, history.jl:113-129) --------
+struct ApproxDuArgs {
+    const double *hist[8];
+    double w[8];
+    int nterms;
+    double *out;
+    int64_t len;
+};
+__global__ void __launch_bounds__(256) k_approx_du(const ApproxDuArgs A)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.len; i += stride) {
+        double acc = 0.0;
+        for (int s = 0; s < A.nterms; ++s) acc = fma(A.w[s], A.hist[s][i], acc);
+        A.out[i] = acc;
+    }
+}
+
+// ---- SoA (caller order) <-> AoS (device order) -------------------------------------------------------------
+template <int V>
+__global__ void k_pack(const double *__restrict__ soa, int64_t ld, const int *__restrict__ perm, Vec<V> *out, int64_t n)
+{
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    const int64_t src = perm ? perm[d] : d;
+    Vec<V> v;
+#pragma unroll
+    for (int k = 0; k < V; ++k) v.a[k] = soa[(int64_t)k * ld + src];
+    out[d] = v;
+}
+template <int V>
+__global__ void k_unpack(const Vec<V> *__restrict__ in, const int *__restrict__ perm, double *soa, int64_t ld, int64_t n)
+{
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    const int64_t dst = perm ? perm[d] : d;
+    const Vec<V> v = in[d];
+#pragma unroll
+    for (int k = 0; k < V; ++k) soa[(int64_t)k * ld + dst] = v.a[k];
+}
+__global__ void k_unpack_scalar(const double *__restrict__ in, const int *__restrict__ perm, double *out, int64_t n)
+{
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    out[perm ? perm[d] : d] = in[d];
+}
+
+// halo send-buffer gather (perform_halo_update! pack loop, src/auxiliary/mpi.jl:234-236)
+template <int W>
+__global__ void k_halo_pack(const Vec<W> *__restrict__ src, const int *__restrict__ send_rows, Vec<W> *buf, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    buf[i] = src[send_rows[i]];
+}
+
+__global__ void k_fill_zero(double *p, int64_t len)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) p[i] = 0.0;
+}
+
+}  // namespace mft

@@ -1,0 +1,126 @@
+"""Setup-time operator generation (NOT on the timed path; north_star: "kNN search and stencil-weight generation
+remain setup-time code").  Batched numpy implementation of what the reference does point by point:
+
+  PointData ctor        src/domains/PointCloudDomain/geometry_primatives.jl:322-339  (kNN, dx_min, dx_avg)
+  compute_flux_operator src/solvers/pointcloudsolver/compute_operators.jl:409-453 (1st derivatives), :549-594 (k-th)
+
+In the drop-in deployment the Julia side keeps generating operators with its own code and hands the CSC arrays to
+`mft_set_operator_csc`; this module exists so that the Python host mirror, the tests and bench.py can build the
+same operators without the reference.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import scipy.sparse as sp
+from scipy.spatial import cKDTree
+
+
+def num_neighbors(N: int, dim: int = 2) -> int:
+    """NV = max(2*binomial(N+d,d), [10,15,20][d])   geometry_primatives.jl:197-198"""
+    return max(2 * math.comb(N + dim, dim), [10, 15, 20][dim - 1])
+
+
+def knn(points: np.ndarray, nv: int, workers: int = -1):
+    """Exact kNN sorted by distance, self first (NearestNeighbors.knn(tree, pts, nv, true)).
+    Returns neighbors (N,nv) int64 0-based, dx_min, dx_avg (from the nearest-neighbour distance)."""
+    tree = cKDTree(points)
+    d, idx = tree.query(points, k=nv, workers=workers)
+    return idx.astype(np.int64), float(d[:, 1].min()), float(d[:, 1].mean())
+
+
+def monomial_exponents(N: int):
+    return [(a, d - a) for d in range(N + 1) for a in range(d, -1, -1)]
+
+
+def _phs_axis_derivative(x, r2, p: int, k: int):
+    """k-th derivative of (x^2+y^2)^(p/2) with respect to x, written through f(s)=s^q, q=p/2, s=r^2."""
+    q = p / 2.0
+
+    def fd(m):  # m-th derivative of s^q
+        c = 1.0
+        for i in range(m):
+            c *= q - i
+        return c * np.power(r2, q - m)
+
+    if k == 0:
+        return np.power(r2, q)
+    if k == 1:
+        return 2.0 * x * fd(1)
+    if k == 2:
+        return 2.0 * fd(1) + 4.0 * x * x * fd(2)
+    if k == 3:
+        return 12.0 * x * fd(2) + 8.0 * x ** 3 * fd(3)
+    if k == 4:
+        return 12.0 * fd(2) + 48.0 * x * x * fd(3) + 16.0 * x ** 4 * fd(4)
+    raise NotImplementedError("derivative order %d" % k)
+
+
+def rbf_fd_weights(points: np.ndarray, neighbors: np.ndarray, p: int, N: int, k: int | None = None,
+                   chunk: int = 16384):
+    """Per-point weights Dx_loc, Dy_loc (N,nv): shift_stencil / [R P; P' 0] \\ rhs / rescale, batched.
+    k=None: first derivatives; k: pure k-th derivatives d^k/dx^k, d^k/dy^k (as the reference builds them)."""
+    npts, nv = neighbors.shape
+    exps = monomial_exponents(N)
+    npoly = len(exps)
+    kk = 1 if k is None else k
+    m = nv + npoly
+    eps = np.finfo(np.float64).eps
+    wx = np.empty((npts, nv))
+    wy = np.empty((npts, nv))
+    pr_x = np.array([math.factorial(kk) if (a, b) == (kk, 0) else 0.0 for (a, b) in exps])
+    pr_y = np.array([math.factorial(kk) if (a, b) == (0, kk) else 0.0 for (a, b) in exps])
+    ea = np.array([e[0] for e in exps], dtype=np.float64)
+    eb = np.array([e[1] for e in exps], dtype=np.float64)
+    for s0 in range(0, npts, chunk):
+        s1 = min(npts, s0 + chunk)
+        B = s1 - s0
+        X = points[neighbors[s0:s1]]                      # (B,nv,2)
+        Xs = X - X[:, :1, :]
+        sc = 1.0 / np.abs(Xs).max(axis=1)                 # (B,2) per-axis scaling, compute_operators.jl:239-242
+        Xs = Xs * sc[:, None, :]
+        dx = Xs[:, :, None, 0] - Xs[:, None, :, 0]
+        dy = Xs[:, :, None, 1] - Xs[:, None, :, 1]
+        M = np.zeros((B, m, m))
+        M[:, :nv, :nv] = np.power(dx * dx + dy * dy, p / 2.0)
+        P = np.power(Xs[:, :, None, 0], ea[None, None, :]) * np.power(Xs[:, :, None, 1], eb[None, None, :])
+        M[:, :nv, nv:] = P
+        M[:, nv:, :nv] = np.transpose(P, (0, 2, 1))
+        # rhs at mirrored stencil x_c - x_j with the centre at (eps,eps)   compute_operators.jl:248-263
+        mx = -Xs[:, :, 0].copy()
+        my = -Xs[:, :, 1].copy()
+        mx[:, 0] = eps
+        my[:, 0] = eps
+        r2 = mx * mx + my * my
+        rhs = np.zeros((B, m, 2))
+        rhs[:, :nv, 0] = _phs_axis_derivative(mx, r2, p, kk)
+        rhs[:, :nv, 1] = _phs_axis_derivative(my, r2, p, kk)
+        rhs[:, nv:, 0] = pr_x
+        rhs[:, nv:, 1] = pr_y
+        W = np.linalg.solve(M, rhs)
+        wx[s0:s1] = (sc[:, 0] ** kk)[:, None] * W[:, :nv, 0]
+        wy[s0:s1] = (sc[:, 1] ** kk)[:, None] * W[:, :nv, 1]
+    return wx, wy
+
+
+def assemble_csc(neighbors: np.ndarray, w: np.ndarray, ncols: int | None = None):
+    """sparse(vec(rows), vec(cols), vec(vals)) -> CSC with explicit zeros kept (compute_operators.jl:443-452)."""
+    npts, nv = neighbors.shape
+    rows = np.repeat(np.arange(npts, dtype=np.int64), nv)
+    A = sp.coo_matrix((w.reshape(-1), (rows, neighbors.reshape(-1))), shape=(npts, ncols or npts)).tocsc()
+    A.sort_indices()
+    return A
+
+
+def compute_flux_operator(points, neighbors, p: int, N: int, k: int | None = None):
+    wx, wy = rbf_fd_weights(points, neighbors, p, N, k)
+    return [assemble_csc(neighbors, wx), assemble_csc(neighbors, wy)]
+
+
+def julia_csc(A):
+    """(colptr, rowval, nzval) exactly as Julia's SparseMatrixCSC{Float64,Int64} holds them (1-based)."""
+    A = sp.csc_matrix(A)
+    A.sort_indices()
+    return (np.ascontiguousarray(A.indptr, dtype=np.int64) + 1, np.ascontiguousarray(A.indices, dtype=np.int64) + 1,
+            np.ascontiguousarray(A.data, dtype=np.float64))

@@ -1,0 +1,325 @@
+"""GPU parity: the CUDA path (libmft_b200.so through its C ABI, driven by the host mirror of the reference API)
+against the CPU oracle on the same inputs.  Tolerances (BASELINE.json north_star): 1e-12 normwise per rhs!,
+1e-9 after N steps; in exact-order mode the Dx/Dy sums are required to be BIT-IDENTICAL to the oracle."""
+import numpy as np
+import pytest
+
+import cases
+from cases import orc
+
+pytestmark = pytest.mark.gpu
+
+RHS_TOL = 1e-12
+STEP_TOL = 1e-9
+
+
+def _mft():
+    import mft_b200
+
+    return mft_b200
+
+
+@pytest.fixture(scope="module")
+def fx():
+    m = _mft()
+    s = cases.fixture_setup(p=3, N=3)
+    s["ops"] = m.setup_ops.compute_flux_operator(s["points"], s["nb"], 3, 3)
+    return s
+
+
+def _semi(fx, sources=None, bcs=cases.DIVERGENCE_TEST_BCS, ic=cases.ic_gradient, time_dependent=False, **engine_kw):
+    """the product side, built exactly like test/divergence_test.jl builds the reference side"""
+    m = _mft()
+    basis = m.PointCloudBasis(m.Point2D(), fx["N"], approximation_type=m.RBF(m.PolyharmonicSpline(fx["p"])), nv=fx["nv"])
+    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(**engine_kw))
+    domain = m.PointCloudDomain(solver, cases.FIXTURE, cases.BOUNDARY_NAMES)
+    assert np.array_equal(domain.pd.neighbors, fx["nb"])      # kNN indices bit-exact vs the oracle's
+    equations = m.CompressibleEulerEquations2D(cases.GAMMA)
+    kinds = dict(dirichlet=lambda: m.BoundaryConditionDirichlet(ic, time_dependent=time_dependent),
+                 slip=lambda: m.boundary_condition_slip_wall, nothing=lambda: m.BoundaryConditionDoNothing())
+    bc = {name: kinds[k]() for name, k in bcs.items()}
+    srcs = m.SourceTerms(**(sources(m, solver, equations, domain) if sources else {}))
+    semi = m.SemidiscretizationHyperbolic(domain, equations, ic, solver, boundary_conditions=bc, source_terms=srcs,
+                                          operators=fx["ops"])
+    return m, semi
+
+
+def _oracle(fx, sources=(), bcs=cases.DIVERGENCE_TEST_BCS, ic=cases.ic_gradient):
+    return orc.OracleProblem(fx["points"], 4, orc.EQ_EULER2D, [cases.GAMMA], fx["ops"][0], fx["ops"][1],
+                             cases.oracle_bcs(fx, bcs, ic), sources)
+
+
+@pytest.mark.parametrize("ic", [cases.ic_gradient, cases.ic_oscillatory, cases.ic_smooth_euler])
+def test_calc_fluxes_bit_exact(fx, ic):
+    """test/divergence_test.jl: calc_fluxes!(du0,u0); exact-order mode must reproduce the CSC SpMV sums bit for bit"""
+    m, semi = _semi(fx)
+    u0 = ic(fx["points"], 0.0)
+    du_ref = np.zeros_like(u0)
+    _oracle(fx).calc_fluxes(u0, du_ref)
+    du = np.zeros_like(u0)
+    m.calc_fluxes_(du, u0, semi)
+    assert cases.relerr(du, du_ref) <= RHS_TOL
+    assert np.array_equal(du, du_ref), f"not bit-identical: max abs diff {np.abs(du - du_ref).max():.3e}"
+    # accumulate semantics (du += ...)
+    du2 = np.full_like(u0, 0.25)
+    du2_ref = du2.copy()
+    _oracle(fx).calc_fluxes(u0, du2_ref)
+    m.calc_fluxes_(du2, u0, semi)
+    assert np.array_equal(du2, du2_ref)
+    semi.close()
+
+
+def test_calc_fluxes_fma_mode_within_tolerance(fx):
+    m, semi = _semi(fx, exact_order=False)
+    u0 = cases.ic_smooth_euler(fx["points"], 0.0)
+    du_ref = np.zeros_like(u0)
+    _oracle(fx).calc_fluxes(u0, du_ref)
+    du = np.zeros_like(u0)
+    m.calc_fluxes_(du, u0, semi)
+    assert cases.relerr(du, du_ref) <= RHS_TOL
+    semi.close()
+
+
+def test_no_reorder_equals_hilbert(fx):
+    u0 = cases.ic_smooth_euler(fx["points"], 0.0)
+    out = []
+    for reorder in (None, "hilbert"):
+        m, semi = _semi(fx, reorder=reorder)
+        du = np.zeros_like(u0)
+        m.calc_fluxes_(du, u0, semi)
+        out.append(du)
+        semi.close()
+    assert np.array_equal(out[0], out[1])
+
+
+def test_upwind_viscosity_source(fx):
+    """test/upwind_viscosity_test.jl:69-78 through the CUDA path, checked against the oracle and the identity"""
+    mk = lambda m, solver, eq, dom: dict(rv=m.SourceUpwindViscosityTominec(solver, eq, dom))
+    m, semi = _semi(fx, sources=mk, diagnostics=True)
+    src_o = orc.source_upwind(fx["dx_avg"])
+    P = _oracle(fx, [src_o])
+    u0 = cases.ic_gradient(fx["points"], 0.0)
+    du_ref = np.zeros_like(u0)
+    P.apply_source(0, u0, du_ref)
+    du = np.zeros_like(u0)
+    semi.source_terms.rv(du, u0, 0.0)
+    assert cases.relerr(du, du_ref) <= RHS_TOL
+    assert np.array_equal(du, du_ref)
+    eps = semi.source_terms.rv.cache.eps
+    assert np.array_equal(eps, src_o.arrays["eps"])
+    Dx, Dy = fx["ops"]
+    du1 = np.stack([-(Dx.T @ (eps * (Dx @ u0[v]))) - (Dy.T @ (eps * (Dy @ u0[v]))) for v in range(4)])
+    np.testing.assert_allclose(du, du1, rtol=1e-9, atol=1e-9)
+    semi.close()
+
+
+def test_hyperviscosity_sources(fx):
+    fx5 = cases.fixture_setup(p=5, N=3)
+    m = _mft()
+    fx5["ops"] = m.setup_ops.compute_flux_operator(fx5["points"], fx5["nb"], 5, 3)
+    mk = lambda m, solver, eq, dom: dict(hv=m.SourceHyperviscosityFlyer(solver, eq, dom, k=2, c=1.0),
+                                         hv2=m.SourceHyperviscosityTominec(solver, eq, dom, c=1.0))
+    m, semi = _semi(fx5, sources=mk, ic=cases.ic_oscillatory)
+    srcs = semi.source_terms
+    o1 = orc.OracleSource(kind=orc.SRC_HV_FLYER, hv=orc.JuliaCSC(srcs.hv.hv_differentiation_matrix), gamma=srcs.hv.gamma)
+    o2 = orc.OracleSource(kind=orc.SRC_HV_TOMINEC, hv=orc.JuliaCSC(srcs.hv2.hv_differentiation_matrix), gamma=srcs.hv2.gamma)
+    P = _oracle(fx5, [o1, o2], ic=cases.ic_oscillatory)
+    u0 = cases.ic_oscillatory(fx5["points"], 0.0)
+    for i, s in enumerate((srcs.hv, srcs.hv2)):
+        du_ref = np.full_like(u0, 0.5)
+        P.apply_source(i, u0, du_ref)
+        du = np.full_like(u0, 0.5)
+        s(du, u0, 0.0)
+        assert cases.relerr(du, du_ref) <= RHS_TOL
+        assert np.array_equal(du, du_ref)
+    semi.close()
+
+
+def test_boundary_pass(fx):
+    m, semi = _semi(fx, ic=cases.ic_smooth_euler, time_dependent=True)
+    P = _oracle(fx, ic=cases.ic_smooth_euler)
+    u = cases.ic_smooth_euler(fx["points"], 0.0) * 1.03
+    du = np.full_like(u, 0.7)
+    u_ref, du_ref = u.copy(), du.copy()
+    P.boundary_pass(u_ref, du_ref, 0.4)
+    m.calc_boundary_flux_(du, u, semi, 0.4)
+    assert np.array_equal(u, u_ref) and np.array_equal(du, du_ref)
+    semi.close()
+
+
+SOURCE_SETS = {
+    "none": (lambda m, s, e, d: {}, lambda fx: []),
+    "upwind": (lambda m, s, e, d: dict(rv=m.SourceUpwindViscosityTominec(s, e, d)),
+               lambda fx: [orc.source_upwind(fx["dx_avg"])]),
+    "residual": (lambda m, s, e, d: dict(rv=m.SourceResidualViscosityTominec(s, e, d, polydeg=3)),
+                 lambda fx: [orc.source_residual(fx["dx_avg"], polydeg=3)]),
+}
+
+
+@pytest.mark.parametrize("which", ["none", "upwind", "residual"])
+def test_full_rhs(fx, which):
+    """whole rhs! (BC pass, fluxes, source, BC pass); u in/out"""
+    mk, mko = SOURCE_SETS[which]
+    m, semi = _semi(fx, sources=mk, ic=cases.ic_smooth_euler, diagnostics=True)
+    P = _oracle(fx, mko(fx), ic=cases.ic_smooth_euler)
+    u = cases.ic_smooth_euler(fx["points"], 0.0) * 1.01
+    u_ref = u.copy()
+    du_ref = P.rhs(u_ref, 0.0)
+    du = np.empty_like(u)
+    m.rhs_(du, u, semi, 0.0)
+    assert np.array_equal(u, u_ref)
+    err = cases.relerr(du, du_ref)
+    assert err <= RHS_TOL, err
+    if which != "residual":
+        assert np.array_equal(du, du_ref)
+    semi.close()
+
+
+def test_hv_then_upwind_order_of_sources(fx):
+    """SourceTerms(hv=..., rv=...) as in test/upwind_viscosity_test.jl:52 -- sources see the du left by earlier ones"""
+    mk = lambda m, s, e, d: dict(hv=m.SourceHyperviscosityTominec(s, e, d, c=1.0),
+                                 rv=m.SourceResidualViscosityTominec(s, e, d, polydeg=3))
+    m, semi = _semi(fx, sources=mk, ic=cases.ic_smooth_euler)
+    hv = semi.source_terms.hv
+    o_hv = orc.OracleSource(kind=orc.SRC_HV_TOMINEC, hv=orc.JuliaCSC(hv.hv_differentiation_matrix), gamma=hv.gamma)
+    P = _oracle(fx, [o_hv, orc.source_residual(fx["dx_avg"], polydeg=3)], ic=cases.ic_smooth_euler)
+    u = cases.ic_smooth_euler(fx["points"], 0.0)
+    u_ref = u.copy()
+    du_ref = P.rhs(u_ref, 0.0)
+    du = np.empty_like(u)
+    m.rhs_(du, u, semi, 0.0)
+    assert cases.relerr(du, du_ref) <= RHS_TOL
+    semi.close()
+
+
+def test_residual_viscosity_with_history_and_time_integration(fx):
+    """config-2 shape on the fixture: Euler + residual viscosity + HistoryCallback + SSPRK33, 30 steps"""
+    mk, mko = SOURCE_SETS["residual"]
+    m, semi = _semi(fx, sources=mk, ic=cases.ic_smooth_euler, diagnostics=True)
+    src_o = mko(fx)[0]
+    P = _oracle(fx, [src_o], ic=cases.ic_smooth_euler)
+    u0 = cases.ic_smooth_euler(fx["points"], 0.0)
+    dt = 0.1 * fx["dx_min"] / 3.0
+    nsteps = 30
+    u_ref, t_ref = P.solve_ssprk33(u0, 0.0, dt, nsteps, approx_order=3)
+    ode = m.semidiscretize(semi, (0.0, nsteps * dt))
+    assert np.array_equal(ode.u0, u0)
+    sol = m.solve(ode, m.SSPRK33(), dt=dt, callback=m.HistoryCallback(approx_order=3), nsteps=nsteps)
+    assert abs(sol.t - t_ref) < 1e-15
+    err = cases.relerr(sol.u, u_ref)
+    assert err <= STEP_TOL, err
+    # the limiter really was active (eps_rv < eps_uw somewhere) so the residual path is exercised
+    c = semi.source_terms.rv.cache
+    assert (c.eps_c == 0).any() and (c.eps_c == 1).any()
+    np.testing.assert_allclose(c.approx_du, src_o.arrays["approx_du"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(c.norms, P.residual_norms(0, u_ref, np.zeros_like(u_ref)), rtol=1e-12)
+    semi.close()
+
+
+def test_residual_norm_conventions(fx):
+    """documented switches: ode_mean divisor V*N vs N, lexicographic vs per-component maximum"""
+    mk, _ = SOURCE_SETS["residual"]
+    for vn, lex in [(True, True), (False, False), (True, False), (False, True)]:
+        m, semi = _semi(fx, sources=mk, ic=cases.ic_smooth_euler, diagnostics=True, mean_divisor_vn=vn,
+                        max_lexicographic=lex)
+        P = _oracle(fx, [orc.source_residual(fx["dx_avg"], polydeg=3, mean_divisor_vn=vn, max_lexicographic=lex)],
+                    ic=cases.ic_smooth_euler)
+        u = cases.ic_smooth_euler(fx["points"], 0.0)
+        u_ref = u.copy()
+        du_ref = P.rhs(u_ref, 0.0)
+        du = np.empty_like(u)
+        m.rhs_(du, u, semi, 0.0)
+        np.testing.assert_allclose(semi.source_terms.rv.cache.norms, P.residual_norms(0, u_ref, du_ref), rtol=1e-13)
+        assert cases.relerr(du, du_ref) <= RHS_TOL
+        semi.close()
+
+
+def test_advection_config1(fx):
+    """BASELINE config 1: 2-D linear advection on the fixture cloud, PHS 5 / degree 3, hyperviscosity, SSPRK33"""
+    m = _mft()
+    fx5 = cases.fixture_setup(p=5, N=3)
+    ops = m.setup_ops.compute_flux_operator(fx5["points"], fx5["nb"], 5, 3)
+    basis = m.PointCloudBasis(m.Point2D(), 3, approximation_type=m.RBF(m.PolyharmonicSpline(5)))
+    solver = m.PointCloudSolver(basis)
+    domain = m.PointCloudDomain(solver, cases.FIXTURE, cases.BOUNDARY_NAMES)
+    eq = m.LinearScalarAdvectionEquation2D(1.0, 0.5)
+    ic = cases.ic_bump_advection
+    bc = dict(inlet=m.BoundaryConditionDirichlet(ic), outlet=m.BoundaryConditionDoNothing(),
+              top=m.BoundaryConditionDoNothing(), bottom=m.BoundaryConditionDoNothing(), cyl=m.BoundaryConditionDoNothing())
+    srcs = m.SourceTerms(hv=m.SourceHyperviscosityFlyer(solver, eq, domain, k=2, c=1.0),
+                         hv2=m.SourceHyperviscosityTominec(solver, eq, domain, c=1.0))
+    semi = m.SemidiscretizationHyperbolic(domain, eq, ic, solver, boundary_conditions=bc, source_terms=srcs, operators=ops)
+    o1 = orc.OracleSource(kind=orc.SRC_HV_FLYER, hv=orc.JuliaCSC(srcs.hv.hv_differentiation_matrix), gamma=srcs.hv.gamma)
+    o2 = orc.OracleSource(kind=orc.SRC_HV_TOMINEC, hv=orc.JuliaCSC(srcs.hv2.hv_differentiation_matrix), gamma=srcs.hv2.gamma)
+    obc = [orc.OracleBC(orc.BC_DIRICHLET, fx5["bidx"][0], fx5["bnrm"][0], value_fn=lambda x, t: ic(x, t))]
+    obc += [orc.OracleBC(orc.BC_DO_NOTHING, fx5["bidx"][g], fx5["bnrm"][g]) for g in (1, 3, 2, 4)]
+    P = orc.OracleProblem(fx5["points"], 1, orc.EQ_ADVECTION2D, [1.0, 0.5], ops[0], ops[1], obc, [o1, o2])
+    u = ic(fx5["points"], 0.0)
+    u_ref = u.copy()
+    du_ref = P.rhs(u_ref, 0.0)
+    du = np.empty_like(u)
+    m.rhs_(du, u, semi, 0.0)
+    assert np.array_equal(du, du_ref) and np.array_equal(u, u_ref)
+    dt = 0.1 * fx5["dx_min"]
+    u_end, _ = P.solve_ssprk33(ic(fx5["points"], 0.0), 0.0, dt, 100)
+    sol = m.solve(m.semidiscretize(semi, (0.0, 100 * dt)), m.SSPRK33(), dt=dt, nsteps=100)
+    err = cases.relerr(sol.u, u_end)
+    assert err <= STEP_TOL, err
+    semi.close()
+
+
+def test_synthetic_cloud_medium(fx):
+    """jittered-lattice cloud (the generator of BASELINE configs 2-4) at a size the oracle finishes in seconds"""
+    m = _mft()
+    cl = m.cloud.jittered_lattice(96, 80, 10.0, 10.0 * 80 / 96, seed=0)
+    basis = m.PointCloudBasis(m.Point2D(), 3, approximation_type=m.RBF(m.PolyharmonicSpline(3)))
+    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(diagnostics=True))
+    names = dict(left=1, right=2, bottom=3, top=4)
+    domain = m.PointCloudDomain(solver, cl, names)
+    eq = m.CompressibleEulerEquations2D(cases.GAMMA)
+    ic = lambda x, t, e=None: m.cloud.isentropic_vortex(x, cases.GAMMA, center=(5.0, 4.0))
+    bc = {k: m.BoundaryConditionDirichlet(ic) for k in names}
+    srcs = m.SourceTerms(rv=m.SourceResidualViscosityTominec(solver, eq, domain, c_rv=1.0, c_uw=1.0, polydeg=3))
+    semi = m.SemidiscretizationHyperbolic(domain, eq, ic, solver, boundary_conditions=bc, source_terms=srcs)
+    ops = semi.cache.rbf_differentiation_matrices
+    pd = domain.pd
+    nb_o, dxmin_o, dxavg_o = orc.point_data(pd.points, pd.num_neighbors)
+    assert np.array_equal(nb_o, pd.neighbors) and dxmin_o == pd.dx_min and dxavg_o == pd.dx_avg
+    obc = [orc.OracleBC(orc.BC_DIRICHLET, domain.boundary_tags[k].idx, domain.boundary_tags[k].normals,
+                        value_fn=lambda x, t: ic(x, t)) for k in names]
+    src_o = orc.source_residual(pd.dx_avg, polydeg=3)
+    P = orc.OracleProblem(pd.points, 4, orc.EQ_EULER2D, [cases.GAMMA], ops[0], ops[1], obc, [src_o])
+    u0 = ic(pd.points, 0.0)
+    dt = 0.1 * pd.dx_min / 8.0
+    u_ref, _ = P.solve_ssprk33(u0, 0.0, dt, 12, approx_order=3)
+    sol = m.solve(m.semidiscretize(semi, (0.0, 12 * dt)), m.SSPRK33(), dt=dt, callback=m.HistoryCallback(3), nsteps=12)
+    err = cases.relerr(sol.u, u_ref)
+    assert err <= STEP_TOL, err
+    # single rhs on the evolved state
+    u = sol.u.copy()
+    ur = sol.u.copy()
+    du_ref = P.rhs(ur, 12 * dt)
+    du = np.empty_like(u)
+    m.rhs_(du, u, semi, 12 * dt)
+    assert cases.relerr(du, du_ref) <= RHS_TOL
+    semi.close()
+
+
+def test_error_paths():
+    import ctypes as C
+    m = _mft()
+    lib = m._lib.load()
+    ctx = C.c_void_p()
+    assert lib.mft_ctx_create(C.byref(ctx), 0, 10, 0, 3, 2, 5) == -4     # nvars 3 unsupported
+    assert lib.mft_ctx_create(C.byref(ctx), 0, 0, 0, 4, 2, 5) == -1
+    assert lib.mft_ctx_create(C.byref(ctx), 0, 10, 0, 1, 2, 5) == 0
+    prm = np.array([1.0, 0.5])
+    assert lib.mft_set_equation(ctx, m._lib.EQ_ADVECTION2D, m._lib.ptr(prm), 2) == 0
+    # residual viscosity is Euler-only in the reference (hyperviscosity.jl:289-291)
+    p4 = np.array([1.0, 1.0, 0.1, 3.0])
+    assert lib.mft_add_source(ctx, m._lib.SRC_RESIDUAL, m._lib.ptr(p4), 4, None, None, None) == -4
+    assert b"Euler" in lib.mft_last_error()
+    # compute without operators -> EINVAL, never a silent fallback
+    u = np.zeros((1, 10))
+    assert lib.mft_rhs(ctx, 0.0, m._lib.soa_ptrs(u), m._lib.soa_ptrs(u.copy()), 0) == -1
+    assert lib.mft_ctx_destroy(ctx) == 0
