@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- point-stage updates/sec of the Euler RBF-FD rhs! hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (libmft_b200.so)
+    python bench.py --impl reference ...                      # the reference's CPU path (C port in oracle/), host cores
+
+Workload at N=1: BASELINE.json configs[1] -- 2-D compressible Euler (isentropic vortex) with residual viscosity on a
+1,048,576-point jittered-lattice cloud (+ boundary ring), PHS r^3 + degree-3 polynomials, k = 20, HistoryCallback(3),
+SSPRK33 with fixed dt.  A "step" is one SSPRK33 time step: 3 rhs! evaluations + 3 stage updates + the history
+callback, i.e. 3 point-stage updates per point.  Synthetic data; setup (cloud, kNN, weights, layouts) is untimed.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "point-stage updates/sec of Euler RBF-FD rhs!"
+UNIT = "point-stage updates/s"
+GAMMA = 1.4
+K_STENCIL = 20
+STAGES = 3
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(nx, ny, seed, m, need_oracle_ops=False):
+    """config 2 of SURVEY.md 8d: jittered lattice on [0,10]^2 + boundary ring, Dirichlet(vortex at t=0) on all sides"""
+    t0 = time.time()
+    cl = m.cloud.jittered_lattice(nx, ny, 10.0, 10.0 * ny / nx, seed=seed)
+    basis = m.PointCloudBasis(m.Point2D(), 3, approximation_type=m.RBF(m.PolyharmonicSpline(3)))
+    return cl, basis, time.time() - t0
+
+
+def vortex_ic(m, center):
+    return lambda x, t, eq=None: m.cloud.isentropic_vortex(x, GAMMA, center=center)
+
+
+def run_ours(args):
+    import mft_b200 as m
+
+    lib = m.load()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if world > 1:
+        return run_ours_multi(args, m, rank, world, local_rank)
+
+    nx = ny = args.n_side
+    cl, basis, _ = build_workload(nx, ny, 0, m)
+    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=0, exact_order=not args.fma))
+    names = dict(left=1, right=2, bottom=3, top=4)
+    t_setup = time.time()
+    domain = m.PointCloudDomain(solver, cl, names)
+    eq = m.CompressibleEulerEquations2D(GAMMA)
+    ic = vortex_ic(m, (5.0, 5.0 * ny / nx))
+    bc = {k: m.BoundaryConditionDirichlet(ic) for k in names}
+    srcs = m.SourceTerms(rv=m.SourceResidualViscosityTominec(solver, eq, domain, c_rv=1.0, c_uw=1.0, polydeg=3))
+    semi = m.SemidiscretizationHyperbolic(domain, eq, ic, solver, boundary_conditions=bc, source_terms=srcs)
+    t_setup = time.time() - t_setup
+    N = semi.n
+    pd = domain.pd
+    dt = 0.1 * pd.dx_min / 8.0   # CFL 0.1*dx_min/(|v|+c), |v|+c ~ 7.4 for the vortex base state
+    ode = m.semidiscretize(semi, (0.0, 1.0))
+    u0 = ode.u0
+    ctx = semi.ctx
+    L = m._lib
+
+    def steps(n, t, it0):
+        for i in range(n):
+            L.check(lib.mft_ssprk_step(ctx, L.SSPRK33, t, dt))
+            t += dt
+            L.check(lib.mft_history_push(ctx, t, it0 + i + 1, 3))
+        return t
+
+    # ---- device-resident timed region -----------------------------------------------------------------
+    L.check(lib.mft_upload_state(ctx, L.soa_ptrs(u0)))
+    L.check(lib.mft_history_push(ctx, 0.0, 0, 3))
+    t = steps(args.warmup, 0.0, 0)
+    L.check(lib.mft_synchronize(ctx))
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = lib.mft_launch_count(ctx)
+    L.check(lib.mft_timer_start(ctx))
+    t = steps(args.steps, t, args.warmup)
+    ms = C.c_double()
+    L.check(lib.mft_timer_stop(ctx, C.byref(ms)))
+    launches = lib.mft_launch_count(ctx) - launches0
+    clocks = sampler.stop()
+    total_ms = ms.value
+    ms_per_step = total_ms / args.steps
+    value = N * STAGES * args.steps / (total_ms * 1e-3)
+
+    # sanity: the state is still finite after the timed steps
+    u_end = np.empty_like(u0)
+    L.check(lib.mft_download_state(ctx, L.soa_ptrs(u_end)))
+    if not np.isfinite(u_end).all():
+        raise SystemExit("bench: non-finite state after the timed region")
+
+    # ---- per-kernel CUDA-event pass (same steps, events around every launch on the ctx stream) -----------
+    L.check(lib.mft_set_kernel_timing(ctx, 1))
+    t = steps(args.steps, t, args.warmup + args.steps)
+    ktime = {}
+    for name, cls in (("pass_a", L.K_PASS_A), ("pass_b", L.K_PASS_B), ("reduce", L.K_REDUCE), ("stage", L.K_STAGE),
+                      ("bc", L.K_BC), ("other", L.K_OTHER)):
+        kms, kn = C.c_double(), C.c_int64()
+        L.check(lib.mft_kernel_time_ms(ctx, cls, C.byref(kms), C.byref(kn)))
+        ktime[name] = (kms.value, kn.value)
+    L.check(lib.mft_set_kernel_timing(ctx, 0))
+    peak, peak_src = measured_peak()
+    V, k = 4, K_STENCIL
+    bytes_a = N * (20 * k + 8 * V + 8 * V + 8 * V + 16 * V)      # idx+wx+wy, u gather, approx_du, du, g
+    bytes_b = N * (20 * k + 16 * V + 16 * V)                     # idxT+wxT+wyT, g gather, du read+write
+    a_ms, a_n = ktime["pass_a"]
+    b_ms, b_n = ktime["pass_b"]
+    dom, dom_bytes, dom_ms, dom_n = ("k_pass_a", bytes_a, a_ms, a_n) if a_ms >= b_ms else ("k_pass_b", bytes_b, b_ms, b_n)
+    achieved = dom_bytes / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9
+    step_bytes = N * STAGES * (40 * k + 288 + 128)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes,
+                "avg_launch_ms": round(dom_ms / max(dom_n, 1), 4),
+                "whole_step": {"algorithmic_GBps": round(step_bytes / (ms_per_step * 1e-3) / 1e9, 1),
+                               "frac": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                               "bytes_per_point_stage": 40 * k + 288 + 128},
+                "kernel_ms_per_step": {kk: round(v[0] / args.steps, 4) for kk, v in ktime.items()}}
+
+    # ---- end-to-end through the reference-facing call: mft_rhs with HOST buffers (pinned) -------------------
+    u_h = L.pinned_empty((4, N))
+    du_h = L.pinned_empty((4, N))
+    u_h[:] = u_end
+    up, dup = L.soa_ptrs(u_h), L.soa_ptrs(du_h)
+    for _ in range(3):
+        L.check(lib.mft_rhs(ctx, t, up, dup, L.MEM_HOST))
+    e2e_calls = max(3, min(3 * args.steps, 30))
+    t0 = time.perf_counter()
+    for _ in range(e2e_calls):
+        L.check(lib.mft_rhs(ctx, t, up, dup, L.MEM_HOST))
+    e2e_s = time.perf_counter() - t0
+    e2e_value = N * e2e_calls / e2e_s
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": STAGES * 32 * N, "d2h_bytes_per_step": STAGES * 64 * N,
+           "call": "mft_rhs(MFT_MEM_HOST): u H2D, rhs!, u and du D2H, pinned host arrays", "calls_timed": e2e_calls}
+
+    # ---- CPU baseline: the oracle's C port of the reference structure, bounded sample, rank 0, 1 thread -----------
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_baseline(semi, domain, u_end, m, budget_s=args.cpu_seconds)
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": f"BASELINE configs[1]: 2D Euler isentropic vortex + residual viscosity, {N}-point "
+                                  f"jittered cloud ({nx}x{ny} + ring), PHS3 deg3 k=20, SSPRK33 + HistoryCallback(3)",
+                      "points": N, "k": k, "stages_per_step": STAGES,
+                      "summation": "fma single-sweep" if args.fma else "reference order (bit-exact sums)",
+                      "l2": "inputs larger than L2 (operators 2 x %.0f MB streamed every stage)" % (N * 20 * k / 1e6),
+                      "setup_s": round(t_setup, 1)},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(out))
+    semi.close()
+
+
+# DRAM bytes per launch from the committed ncu --set full capture (profiles/); None until captured
+TRAFFIC = {}
+try:
+    TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+except Exception:
+    pass
+
+
+def cpu_baseline(semi, domain, u, m, budget_s=15.0):
+    """Times the reference's CPU execution structure (oracle/mft_oracle.c: CSC/Int64 operators, one SpMV per variable
+    per direction, serial loops -- the reference's hot loops are single-threaded) on this box's host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mft_oracle as orc
+
+    pd = domain.pd
+    ops = semi.cache.rbf_differentiation_matrices
+    obc = []
+    for name, bc, tag in semi._bc_groups:
+        vals = np.ascontiguousarray(bc.boundary_value_function(pd.points[tag.idx], 0.0, None))
+        obc.append(orc.OracleBC(orc.BC_DIRICHLET, tag.idx, tag.normals, values=vals))
+    src = orc.source_residual(pd.dx_avg, polydeg=3)
+    src.success_iter = 5
+    P = orc.OracleProblem(pd.points, 4, orc.EQ_EULER2D, [GAMMA], ops[0], ops[1], obc, [src])
+    uu = np.ascontiguousarray(u.copy())
+    t0 = time.perf_counter()
+    P.rhs_repeat(uu, 1)
+    one = time.perf_counter() - t0
+    reps = int(max(2, min(200, budget_s / max(one, 1e-3))))
+    t0 = time.perf_counter()
+    P.rhs_repeat(uu, reps)
+    dt = time.perf_counter() - t0
+    return {"value": pd.num_points * reps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{reps} rhs! evaluations (Euler + residual viscosity) on the full {pd.num_points}-point cloud, "
+                      "C port of the reference's serial CSC-SpMV structure (oracle/mft_oracle.c), 1 thread"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path.  The reference is pure Julia and Julia is not in this image,
+    so the oracle's C port of its execution structure is timed (kind = "port"), single-threaded like the reference."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import mft_b200 as m
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mft_oracle as orc
+
+    nx = ny = args.ref_n_side
+    cl, basis, _ = build_workload(nx, ny, 0, m)
+    nb, dx_min, dx_avg = m.setup_ops.knn(cl.points, K_STENCIL)
+    ops = m.setup_ops.compute_flux_operator(cl.points, nb, 3, 3)
+    ic = vortex_ic(m, (5.0, 5.0 * ny / nx))
+    obc = [orc.OracleBC(orc.BC_DIRICHLET, cl.boundary_idxs[g], cl.boundary_normals[g],
+                        values=np.ascontiguousarray(ic(cl.points[cl.boundary_idxs[g]], 0.0))) for g in range(4)]
+    src = orc.source_residual(dx_avg, polydeg=3)
+    src.success_iter = 5
+    P = orc.OracleProblem(cl.points, 4, orc.EQ_EULER2D, [GAMMA], ops[0], ops[1], obc, [src])
+    N = cl.points.shape[0]
+    u = np.ascontiguousarray(ic(cl.points, 0.0))
+    lib = orc.lib()
+    dt = 0.1 * dx_min / 8.0
+    n_el = u.size
+
+    def step():
+        # one SSPRK33 step of the CPU path: 3 rhs! + 3 stage updates
+        nonlocal u
+        uprev = u.copy()
+        k = P.rhs(u, 0.0)
+        for s in (1, 2, 3):
+            lib.orc_ssprk33_stage(C.c_int64(n_el), s, C.c_double(dt), C.c_void_p(uprev.ctypes.data),
+                                  C.c_void_p(k.ctypes.data), C.c_void_p(u.ctypes.data))
+            if s < 3:
+                k = P.rhs(u, 0.0)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    value = N * STAGES * args.steps / el
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "BASELINE configs[1]: 2D Euler isentropic vortex + residual viscosity, jittered cloud, "
+                                  f"PHS3 deg3 k=20, SSPRK33; CPU arm runs a bounded {N}-point sample ({nx}x{ny} + ring) "
+                                  "of the same generator", "points": N, "k": K_STENCIL, "stages_per_step": STAGES},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": f"{args.steps} SSPRK33 steps (3 rhs! each) on a {N}-point cloud; C port of "
+                                      "the reference's serial structure (Julia is not installed; the reference's hot "
+                                      "loops are single-threaded)"},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def run_ours_multi(args, m, rank, world, local_rank):
+    raise SystemExit("multi-GPU bench not wired yet")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-side", type=int, default=1024, help="lattice side; 1024 -> the 1M-point cloud of configs[1]")
+    ap.add_argument("--ref-n-side", type=int, default=512, help="lattice side of the bounded sample the CPU arm runs")
+    ap.add_argument("--fma", action="store_true", help="single-sweep FMA summation instead of the reference order")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

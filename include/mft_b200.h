@@ -157,6 +157,10 @@ int mft_kernel_time_ms(mft_ctx *ctx, int which, double *ms, int64_t *launches);
 #define MFT_K_OTHER 5
 int mft_set_kernel_timing(mft_ctx *ctx, int enable);
 
+/* CUDA-event stopwatch on the ctx's own stream (the stream every kernel of this ctx is launched on) */
+int mft_timer_start(mft_ctx *ctx);
+int mft_timer_stop(mft_ctx *ctx, double *elapsed_ms); /* records, synchronises, returns the elapsed device time */
+
 /* pinned host memory helpers for MFT_MEM_HOST callers */
 int mft_host_alloc(void **out, int64_t bytes);
 int mft_host_free(void *p);

@@ -30,7 +30,7 @@ EXPORTS = [
     "mft_add_boundary", "mft_update_boundary_values", "mft_add_source", "mft_finalize", "mft_rhs", "mft_calc_fluxes",
     "mft_apply_source", "mft_boundary_pass", "mft_upload_state", "mft_download_state", "mft_download_du",
     "mft_history_push", "mft_history_push_weights", "mft_ssprk_step", "mft_get_field", "mft_synchronize",
-    "mft_launch_count", "mft_kernel_time_ms", "mft_set_kernel_timing", "mft_host_alloc", "mft_host_free",
+    "mft_launch_count", "mft_timer_start", "mft_timer_stop", "mft_kernel_time_ms", "mft_set_kernel_timing", "mft_host_alloc", "mft_host_free",
     "mft_host_register", "mft_host_unregister", "mft_sfc_order", "mft_nccl_unique_id", "mft_comm_init", "mft_set_halo",
 ]
 
@@ -81,6 +81,8 @@ def load():
         "mft_synchronize": [vp],
         "mft_kernel_time_ms": [vp, i32, C.POINTER(dbl), C.POINTER(i64)],
         "mft_set_kernel_timing": [vp, i32],
+        "mft_timer_start": [vp],
+        "mft_timer_stop": [vp, C.POINTER(dbl)],
         "mft_host_alloc": [C.POINTER(vp), i64],
         "mft_host_free": [vp],
         "mft_host_register": [vp, i64],

@@ -127,6 +127,7 @@ struct mft_ctx {
     double eqp[2] = {0, 0};
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     // options
     int exact = 1, mean_div_vn = 1, max_lex = 1, diagnostics = 0;
     // ordering
@@ -249,6 +250,8 @@ extern "C" int mft_ctx_create(mft_ctx **out, int device, int64_t n_local, int64_
     CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_c, cudaEventDisableTiming));
+    CU(cudaEventCreate(&c->ev_t0));
+    CU(cudaEventCreate(&c->ev_t1));
     const int64_t len = c->n_tot * nvars;
     CHECK(c->u.alloc(len));
     CHECK(c->du.alloc(len));
@@ -293,6 +296,8 @@ extern "C" int mft_ctx_destroy(mft_ctx *c)
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->ev_c) cudaEventDestroy(c->ev_c);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     delete c;
@@ -1201,6 +1206,25 @@ extern "C" int mft_synchronize(mft_ctx *c)
 {
     NEED_CTX(c);
     CU(cudaStreamSynchronize(c->stream));
+    return MFT_OK;
+}
+
+extern "C" int mft_timer_start(mft_ctx *c)
+{
+    NEED_CTX(c);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventRecord(c->ev_t0, c->stream));
+    return MFT_OK;
+}
+
+extern "C" int mft_timer_stop(mft_ctx *c, double *elapsed_ms)
+{
+    NEED_CTX(c);
+    CU(cudaEventRecord(c->ev_t1, c->stream));
+    CU(cudaEventSynchronize(c->ev_t1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+    if (elapsed_ms) *elapsed_ms = (double)ms;
     return MFT_OK;
 }
 

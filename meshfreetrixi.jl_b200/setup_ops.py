@@ -11,6 +11,8 @@ same operators without the reference.
 from __future__ import annotations
 
 import math
+import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import scipy.sparse as sp
@@ -58,7 +60,7 @@ def _phs_axis_derivative(x, r2, p: int, k: int):
 
 
 def rbf_fd_weights(points: np.ndarray, neighbors: np.ndarray, p: int, N: int, k: int | None = None,
-                   chunk: int = 16384):
+                   chunk: int = 4096, workers: int | None = None):
     """Per-point weights Dx_loc, Dy_loc (N,nv): shift_stencil / [R P; P' 0] \\ rhs / rescale, batched.
     k=None: first derivatives; k: pure k-th derivatives d^k/dx^k, d^k/dy^k (as the reference builds them)."""
     npts, nv = neighbors.shape
@@ -73,7 +75,7 @@ def rbf_fd_weights(points: np.ndarray, neighbors: np.ndarray, p: int, N: int, k:
     pr_y = np.array([math.factorial(kk) if (a, b) == (0, kk) else 0.0 for (a, b) in exps])
     ea = np.array([e[0] for e in exps], dtype=np.float64)
     eb = np.array([e[1] for e in exps], dtype=np.float64)
-    for s0 in range(0, npts, chunk):
+    def work(s0):
         s1 = min(npts, s0 + chunk)
         B = s1 - s0
         X = points[neighbors[s0:s1]]                      # (B,nv,2)
@@ -101,6 +103,15 @@ def rbf_fd_weights(points: np.ndarray, neighbors: np.ndarray, p: int, N: int, k:
         W = np.linalg.solve(M, rhs)
         wx[s0:s1] = (sc[:, 0] ** kk)[:, None] * W[:, :nv, 0]
         wy[s0:s1] = (sc[:, 1] ** kk)[:, None] * W[:, :nv, 1]
+
+    starts = list(range(0, npts, chunk))
+    nthreads = min(len(starts), workers or os.cpu_count() or 1)
+    if nthreads > 1:
+        with ThreadPoolExecutor(nthreads) as ex:   # numpy releases the GIL inside solve / power
+            list(ex.map(work, starts))
+    else:
+        for s0 in starts:
+            work(s0)
     return wx, wy
 
 
