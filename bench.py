@@ -116,7 +116,8 @@ def run_ours(args):
 
     nx = ny = args.n_side
     cl, basis, _ = build_workload(nx, ny, 0, m)
-    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=0, exact_order=not args.fma))
+    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=0, exact_order=not args.fma,
+                                                                stage_weights=bool(args.stage_weights)))
     names = dict(left=1, right=2, bottom=3, top=4)
     t_setup = time.time()
     domain = m.PointCloudDomain(solver, cl, names)
@@ -336,6 +337,7 @@ def main():
     ap.add_argument("--n-side", type=int, default=1024, help="lattice side; 1024 -> the 1M-point cloud of configs[1]")
     ap.add_argument("--ref-n-side", type=int, default=512, help="lattice side of the bounded sample the CPU arm runs")
     ap.add_argument("--fma", action="store_true", help="single-sweep FMA summation instead of the reference order")
+    ap.add_argument("--stage-weights", type=int, default=1, help="1: whole operator slices staged in smem; 0: indices only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()

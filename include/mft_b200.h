@@ -67,7 +67,12 @@ typedef struct mft_ctx mft_ctx;
 #define MFT_OPT_MEAN_DIVISOR_VN 1  /* 1 (default): ode_mean divides by V*N (recursive_length, src/auxiliary/mpi.jl:42) */
 #define MFT_OPT_MAX_LEXICOGRAPHIC 2/* 1 (default): maximum(::StructArray{SVector}) = lexicographic max (mpi.jl:71-81) */
 #define MFT_OPT_DIAGNOSTICS 3      /* 1: keep eps_uw/eps_rv/eps/eps_c/residual for mft_get_field (default 0)     */
-#define MFT_OPT_CUDA_GRAPH 4       /* 1 (default): replay mft_ssprk_step through a captured CUDA graph             */
+#define MFT_OPT_CUDA_GRAPH 4       /* reserved                                                                         */
+#define MFT_OPT_STAGE_WEIGHTS 5    /* 1 (default): a warp bulk-copies its whole operator slice (indices + weights) into
+                                      shared memory; 0: indices only, weights by coalesced loads + L2 bulk prefetch      */
+#define MFT_OPT_REFINE_ORDER 7     /* 1 (default 0): within blocks of 256 device rows, order rows by D' row length
+                                      (near-uniform transposed-ELL slices); the caller-visible numbering is unaffected */
+#define MFT_OPT_PREFETCH_DISTANCE 6/* slices ahead for the L2 prefetch of the weight blocks (STAGE_WEIGHTS = 0)        */
 
 /* fields (mft_get_field): caches of create_tominec_rv_cache, hyperviscosity.jl:202-244 */
 #define MFT_FIELD_EPS 0        /* N doubles   */

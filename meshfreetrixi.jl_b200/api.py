@@ -64,6 +64,8 @@ class RBFFDEngineCUDA:
     diagnostics: bool = False          # keep eps/eps_uw/eps_rv/residual on device for inspection
     mean_divisor_vn: bool = True       # ode_mean divides by V*N (recursive_length)
     max_lexicographic: bool = True     # maximum(::StructArray{SVector}) is a lexicographic max
+    stage_weights: bool = True         # bulk-copy whole operator slices to shared memory (else indices only)
+    refine_order: bool = False         # order rows inside 256-row blocks by D' row length (less padding, worse gather locality)
 
 
 @dataclass
@@ -285,6 +287,8 @@ class SemidiscretizationHyperbolic:
         L.check(lib.mft_set_option(ctx, L.OPT_DIAGNOSTICS, float(eng.diagnostics)))
         L.check(lib.mft_set_option(ctx, L.OPT_MEAN_DIVISOR_VN, float(eng.mean_divisor_vn)))
         L.check(lib.mft_set_option(ctx, L.OPT_MAX_LEXICOGRAPHIC, float(eng.max_lexicographic)))
+        L.check(lib.mft_set_option(ctx, L.OPT_STAGE_WEIGHTS, float(eng.stage_weights)))
+        L.check(lib.mft_set_option(ctx, L.OPT_REFINE_ORDER, float(eng.refine_order)))
         if eng.reorder == "hilbert":
             self.perm = L.sfc_order(pd.points)
             perm1 = np.ascontiguousarray(self.perm + 1)

@@ -83,19 +83,18 @@ struct DevBuf {
 };
 
 struct DevEll {
-    DevBuf<int> idx, off;
-    DevBuf<double> wx, wy;
+    DevBuf<unsigned char> blob;
+    DevBuf<int> off;
     int nslices = 0;
+    int colb = 0;             // bytes per column: kColBytes2 (paired) or kColBytes1
+    int maxw = 0;             // widest slice
     int64_t ncols_total = 0;  // sum of slice widths
     int64_t nnz = 0;
-    Ell2 view2() const { return Ell2{idx.p, wx.p, wy.p, off.p}; }
-    Ell1 view1() const { return Ell1{idx.p, wx.p, off.p}; }
+    EllBlob view() const { return EllBlob{blob.p, off.p}; }
     void release()
     {
-        idx.release();
+        blob.release();
         off.release();
-        wx.release();
-        wy.release();
     }
 };
 
@@ -129,7 +128,8 @@ struct mft_ctx {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     // options
-    int exact = 1, mean_div_vn = 1, max_lex = 1, diagnostics = 0;
+    int exact = 1, mean_div_vn = 1, max_lex = 1, diagnostics = 0, stage_w = 1, pf_dist = 0, refine_order = 0;
+    std::vector<const void *> smem_configured;
     // ordering
     bool have_perm = false;
     std::vector<int32_t> perm, iperm;  // device->caller, caller->device (0-based)
@@ -154,6 +154,13 @@ struct mft_ctx {
     DevBuf<double> eps, eps_uw, eps_rv, eps_c, residual;
     // reductions
     DevBuf<double> partial, stats;  // stats: sum[V], mean[V], norms[V]
+    DevBuf<unsigned int> ticket;
+    // merged boundary table (all groups, one launch) when no point is in two groups
+    bool bc_merged = false;
+    int64_t bc_total = 0;
+    std::vector<int64_t> bc_group_off;
+    DevBuf<int> bc_kind, bc_idx;
+    DevBuf<double> bc_normals, bc_values;
     int red_blocks = 0;
     bool have_fsal = false;
     int64_t launches = 0;
@@ -263,6 +270,9 @@ extern "C" int mft_ctx_create(mft_ctx **out, int device, int64_t n_local, int64_
     c->red_blocks = prop.multiProcessorCount * 4;
     CHECK(c->partial.alloc((int64_t)c->red_blocks * nvars));
     CHECK(c->stats.alloc(3 * nvars));
+    CHECK(c->ticket.alloc(4));
+    CU(cudaMemset(c->ticket.p, 0, 4 * sizeof(unsigned int)));
+    c->pf_dist = prop.multiProcessorCount * 16;
     CU(cudaMemset(c->stats.p, 0, sizeof(double) * 3 * nvars));
     *out = c;
     return MFT_OK;
@@ -292,6 +302,11 @@ extern "C" int mft_ctx_destroy(mft_ctx *c)
     for (auto *b : bufs) b->release();
     c->d_perm.release();
     c->send_rows.release();
+    c->ticket.release();
+    c->bc_kind.release();
+    c->bc_idx.release();
+    c->bc_normals.release();
+    c->bc_values.release();
     for (auto ev : c->kt.ev) cudaEventDestroy(ev);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -338,6 +353,9 @@ extern "C" int mft_set_option(mft_ctx *c, int option, double value)
     case MFT_OPT_MAX_LEXICOGRAPHIC: c->max_lex = value != 0; break;
     case MFT_OPT_DIAGNOSTICS: c->diagnostics = value != 0; break;
     case MFT_OPT_CUDA_GRAPH: break;  // reserved
+    case MFT_OPT_STAGE_WEIGHTS: c->stage_w = value != 0; break;
+    case MFT_OPT_PREFETCH_DISTANCE: c->pf_dist = (int)value; break;
+    case MFT_OPT_REFINE_ORDER: c->refine_order = value != 0; break;
     default: return fail(MFT_EINVAL, "mft_set_option: unknown option %d", option);
     }
     return MFT_OK;
@@ -476,6 +494,9 @@ extern "C" int mft_update_boundary_values(mft_ctx *c, int group, const double *v
     for (int64_t j = 0; j < g->nb; ++j)
         for (int v = 0; v < c->V; ++v) aos[j * c->V + v] = values[(int64_t)v * g->nb + j];
     if (g->nb > 0) CU(cudaMemcpyAsync(g->values.p, aos.data(), sizeof(double) * aos.size(), cudaMemcpyHostToDevice, c->stream));
+    if (g->nb > 0 && c->bc_merged && c->bc_group_off[group] >= 0)
+        CU(cudaMemcpyAsync(c->bc_values.p + c->bc_group_off[group] * c->V, aos.data(), sizeof(double) * aos.size(),
+                           cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return MFT_OK;
 }
@@ -612,14 +633,25 @@ static int build_ell(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, bool paired, 
         off[s + 1] = (int)tot;
     }
     const int64_t ncols = off[nsl];
-    std::vector<int> idx((size_t)ncols * kSlice, -1);
-    std::vector<double> wx((size_t)ncols * kSlice, 0.0), wy;
-    if (paired) wy.assign((size_t)ncols * kSlice, 0.0);
-    for (int64_t s = 0; s < nsl; ++s)
+    const int colb = paired ? kColBytes2 : kColBytes1;
+    std::vector<unsigned char> blob((size_t)ncols * colb + 128, 0);
+    int maxw = 0;
+    for (int64_t s = 0; s < nsl; ++s) {
+        const int w = off[s + 1] - off[s];
+        maxw = std::max(maxw, w);
+        unsigned char *b = blob.data() + (size_t)off[s] * colb;
+        int *idx = reinterpret_cast<int *>(b);
+        double *wx = reinterpret_cast<double *>(b + (size_t)w * kSlice * 4);
+        double *wy = reinterpret_cast<double *>(b + (size_t)w * kSlice * 12);
+        // padding: (row itself, weight 0) -> contributes an exact zero; dead lanes of the last slice point at row 0
+        for (int q = 0; q < w * kSlice; ++q) {
+            const int64_t d = s * kSlice + (q % kSlice);
+            idx[q] = d < nrows_dev ? (int)d : 0;
+        }
         for (int64_t d = s * kSlice; d < std::min(nrows_dev, (s + 1) * kSlice); ++d) {
             const int64_t r = caller_row(d);
             const int lane = (int)(d - s * kSlice);
-            int64_t cpos = off[s];
+            int cpos = 0;
             for (int64_t p = A.ptr[r]; p < A.ptr[r + 1]; ++p, ++cpos) {
                 const int64_t j = A.col[p];
                 const size_t at = (size_t)cpos * kSlice + lane;
@@ -628,13 +660,14 @@ static int build_ell(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, bool paired, 
                 if (paired) wy[at] = A.wy[p];
             }
         }
+    }
     out.nslices = (int)nsl;
+    out.colb = colb;
+    out.maxw = maxw;
     out.ncols_total = ncols;
     out.nnz = nnz;
-    CHECK(out.idx.upload(idx));
+    CHECK(out.blob.upload(blob));
     CHECK(out.off.upload(off));
-    CHECK(out.wx.upload(wx));
-    if (paired) CHECK(out.wy.upload(wy));
     return MFT_OK;
 }
 
@@ -644,13 +677,6 @@ static bool has_visc(const mft_ctx *c)
         if (s->kind == MFT_SRC_UPWIND || s->kind == MFT_SRC_RESIDUAL) return true;
     return false;
 }
-static Source *residual_source(const mft_ctx *c)
-{
-    for (auto *s : c->srcs)
-        if (s->kind == MFT_SRC_RESIDUAL) return s;
-    return nullptr;
-}
-
 extern "C" int mft_finalize(mft_ctx *c)
 {
     NEED_CTX(c);
@@ -679,6 +705,23 @@ extern "C" int mft_finalize(mft_ctx *c)
         transpose_rows(T, n, true, F);  // rows of D, ascending caller column index
         sort_rows_by_key(F, c->keys, true);
         sort_rows_by_key(T, c->keys, true);
+    }
+    // Within blocks of 256 device rows, order the rows by the length of their D' row: slices of the transposed
+    // sliced-ELL operator then have near-uniform width (little padding).  Locality is untouched (same block).
+    if (has_visc(c) && c->refine_order) {
+        const int64_t nl = c->n_local;
+        if (!c->have_perm) {
+            c->perm.resize(n);
+            std::iota(c->perm.begin(), c->perm.end(), 0);
+            c->iperm = c->perm;
+            c->have_perm = true;
+        }
+        auto len = [&](int32_t pt) { return T.ptr[pt + 1] - T.ptr[pt]; };
+        for (int64_t b0 = 0; b0 < nl; b0 += 256) {
+            const int64_t b1 = std::min(nl, b0 + 256);
+            std::stable_sort(c->perm.begin() + b0, c->perm.begin() + b1, [&](int32_t x, int32_t y) { return len(x) > len(y); });
+        }
+        for (int64_t d = 0; d < n; ++d) c->iperm[c->perm[d]] = (int32_t)d;
     }
     // drop halo rows of the forward operator: only owned rows are computed here
     if (c->have_perm) CHECK(c->d_perm.upload(std::vector<int>(c->perm.begin(), c->perm.end())));
@@ -730,6 +773,36 @@ extern "C" int mft_finalize(mft_ctx *c)
             CU(cudaMemcpy(idx.data(), g->idx.p, sizeof(int) * g->nb, cudaMemcpyDeviceToHost));
             for (auto &i : idx) i = c->iperm[i];
             CU(cudaMemcpy(g->idx.p, idx.data(), sizeof(int) * g->nb, cudaMemcpyHostToDevice));
+        }
+    }
+    // one merged table for all groups when no point is in two groups (then the group order cannot matter)
+    {
+        std::vector<int> kind, idx;
+        std::vector<double> nrm, val;
+        c->bc_group_off.assign(c->bcs.size(), -1);
+        for (size_t gi = 0; gi < c->bcs.size(); ++gi) {
+            BcGroup *g = c->bcs[gi];
+            if (g->nb == 0 || g->kind == MFT_BC_DO_NOTHING) continue;
+            c->bc_group_off[gi] = (int64_t)idx.size();
+            std::vector<int> gidx(g->nb);
+            CU(cudaMemcpy(gidx.data(), g->idx.p, sizeof(int) * g->nb, cudaMemcpyDeviceToHost));
+            std::vector<double> gn(2 * g->nb, 0.0), gv((size_t)g->nb * c->V, 0.0);
+            if (g->normals.p) CU(cudaMemcpy(gn.data(), g->normals.p, sizeof(double) * 2 * g->nb, cudaMemcpyDeviceToHost));
+            if (g->values.p) CU(cudaMemcpy(gv.data(), g->values.p, sizeof(double) * g->nb * c->V, cudaMemcpyDeviceToHost));
+            idx.insert(idx.end(), gidx.begin(), gidx.end());
+            kind.insert(kind.end(), (size_t)g->nb, g->kind);
+            nrm.insert(nrm.end(), gn.begin(), gn.end());
+            val.insert(val.end(), gv.begin(), gv.end());
+        }
+        std::vector<int> sorted(idx);
+        std::sort(sorted.begin(), sorted.end());
+        c->bc_merged = std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end();
+        if (c->bc_merged) {
+            c->bc_total = (int64_t)idx.size();
+            CHECK(c->bc_kind.upload(kind));
+            CHECK(c->bc_idx.upload(idx));
+            CHECK(c->bc_normals.upload(nrm));
+            CHECK(c->bc_values.upload(val));
         }
     }
     CHECK(c->uprev.alloc(n * c->V));
@@ -840,6 +913,18 @@ static int halo_exchange(mft_ctx *c, double *field /* AoS, W doubles per point *
 // ------------------------------------------------------------------------------------------------------
 static int launch_boundary(mft_ctx *c, bool write_du)
 {
+    if (c->bc_merged) {
+        if (c->bc_total == 0) return MFT_OK;
+        ScopedTimer t(c, MFT_K_BC);
+        BcMergedArgs a{c->bc_total, c->bc_kind.p, c->bc_idx.p, c->bc_normals.p, c->bc_values.p, c->u.p, write_du ? c->du.p : nullptr};
+        if (c->V == 4)
+            k_boundary_merged<4><<<grid_for(a.nb, 128), 128, 0, c->stream>>>(a);
+        else
+            k_boundary_merged<1><<<grid_for(a.nb, 128), 128, 0, c->stream>>>(a);
+        c->launches++;
+        LAUNCH_CHECK();
+        return MFT_OK;
+    }
     for (auto *g : c->bcs) {
         if (g->nb == 0 || g->kind == MFT_BC_DO_NOTHING) continue;
         ScopedTimer t(c, MFT_K_BC);
@@ -854,11 +939,43 @@ static int launch_boundary(mft_ctx *c, bool write_du)
     return MFT_OK;
 }
 
+// dynamic shared memory above 48 KB needs an opt-in per kernel
+template <typename K>
+static int ensure_smem(mft_ctx *c, K kernel, int bytes)
+{
+    const void *key = reinterpret_cast<const void *>(kernel);
+    if (std::find(c->smem_configured.begin(), c->smem_configured.end(), key) != c->smem_configured.end()) return MFT_OK;
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    c->smem_configured.push_back(key);
+    (void)bytes;
+    return MFT_OK;
+}
+
+static inline int warp_buf_bytes(const DevEll &e, bool stage_w)
+{
+    const int per_col = stage_w ? e.colb : kSlice * 4;
+    return ((std::max(e.maxw, 1) * per_col + 127) / 128) * 128;
+}
+
+template <int V, int EQ, bool EX, bool DF, int VI>
+static int launch_pass_a_k(mft_ctx *c, const PassAArgs &a, int grid, int smem)
+{
+    if (c->stage_w) {
+        CHECK(ensure_smem(c, k_pass_a<V, EQ, EX, DF, VI, true>, smem));
+        k_pass_a<V, EQ, EX, DF, VI, true><<<grid, 128, smem, c->stream>>>(a);
+    } else {
+        CHECK(ensure_smem(c, k_pass_a<V, EQ, EX, DF, VI, false>, smem));
+        k_pass_a<V, EQ, EX, DF, VI, false><<<grid, 128, smem, c->stream>>>(a);
+    }
+    return MFT_OK;
+}
+
 template <int V, int EQ>
 static int launch_pass_a_t(mft_ctx *c, const PassAArgs &a, bool do_flux, int visc)
 {
-    const int grid = grid_for(a.n_rows, 128);
-#define PA(EX, DF, VI) k_pass_a<V, EQ, EX, DF, VI><<<grid, 128, 0, c->stream>>>(a)
+    const int grid = (int)((a.n_slices + 3) / 4);
+    const int smem = 4 * a.buf_bytes;
+#define PA(EX, DF, VI) CHECK((launch_pass_a_k<V, EQ, EX, DF, VI>(c, a, grid, smem)))
     if constexpr (V == 4) {
         if (c->exact) {
             if (do_flux && visc == VISC_NONE) PA(true, true, VISC_NONE);
@@ -890,7 +1007,10 @@ static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bo
 {
     ScopedTimer t(c, MFT_K_PASS_A);
     PassAArgs a{};
-    a.op = c->fwd.view2();
+    a.op = c->fwd.view();
+    a.n_slices = c->fwd.nslices;
+    a.buf_bytes = warp_buf_bytes(c->fwd, c->stage_w);
+    a.pf_dist = c->pf_dist;
     a.u = c->u.p;
     a.du = c->du.p;
     a.g = c->g.p;
@@ -918,10 +1038,20 @@ static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bo
 static int launch_pass_b(mft_ctx *c)
 {
     ScopedTimer t(c, MFT_K_PASS_B);
-    PassBArgs a{c->tra.view2(), c->g.p, c->du.p, c->n_local};
-    const int grid = grid_for(a.n_rows, 128);
-    if (c->exact) k_pass_b<4, true><<<grid, 128, 0, c->stream>>>(a);
-    else k_pass_b<4, false><<<grid, 128, 0, c->stream>>>(a);
+    PassBArgs a{c->tra.view(), c->g.p, c->du.p, c->n_local, c->tra.nslices, warp_buf_bytes(c->tra, c->stage_w), c->pf_dist};
+    const int grid = (int)((a.n_slices + 3) / 4);
+    const int smem = 4 * a.buf_bytes;
+#define PB(EX, ST)                                                   \
+    do {                                                             \
+        CHECK(ensure_smem(c, k_pass_b<4, EX, ST>, smem));            \
+        k_pass_b<4, EX, ST><<<grid, 128, smem, c->stream>>>(a);      \
+    } while (0)
+    if (c->exact) {
+        if (c->stage_w) PB(true, true); else PB(true, false);
+    } else {
+        if (c->stage_w) PB(false, true); else PB(false, false);
+    }
+#undef PB
     c->launches++;
     LAUNCH_CHECK();
     return MFT_OK;
@@ -930,21 +1060,30 @@ static int launch_pass_b(mft_ctx *c)
 static int launch_spmv(mft_ctx *c, const Source *s)
 {
     ScopedTimer t(c, MFT_K_OTHER);
-    SpmvArgs a{s->hv.view1(), c->u.p, c->du.p, c->n_local, -s->gamma};
-    const int grid = grid_for(a.n_rows, 128);
+    SpmvArgs a{s->hv.view(), c->u.p, c->du.p, c->n_local, s->hv.nslices, warp_buf_bytes(s->hv, c->stage_w), c->pf_dist, -s->gamma};
+    const int grid = (int)((a.n_slices + 3) / 4);
+    const int smem = 4 * a.buf_bytes;
+    if (smem > 200 * 1024) return fail(MFT_ENOTSUP, "hyperviscosity operator rows too long (%d) for the shared-memory staging", s->hv.maxw);
+#define SP(VV, EX, ST)                                                 \
+    do {                                                               \
+        CHECK(ensure_smem(c, k_spmv_accum<VV, EX, ST>, smem));         \
+        k_spmv_accum<VV, EX, ST><<<grid, 128, smem, c->stream>>>(a);   \
+    } while (0)
     if (c->V == 4) {
-        if (c->exact) k_spmv_accum<4, true><<<grid, 128, 0, c->stream>>>(a);
-        else k_spmv_accum<4, false><<<grid, 128, 0, c->stream>>>(a);
+        if (c->exact) { if (c->stage_w) SP(4, true, true); else SP(4, true, false); }
+        else { if (c->stage_w) SP(4, false, true); else SP(4, false, false); }
     } else {
-        if (c->exact) k_spmv_accum<1, true><<<grid, 128, 0, c->stream>>>(a);
-        else k_spmv_accum<1, false><<<grid, 128, 0, c->stream>>>(a);
+        if (c->exact) { if (c->stage_w) SP(1, true, true); else SP(1, true, false); }
+        else { if (c->stage_w) SP(1, false, true); else SP(1, false, false); }
     }
+#undef SP
     c->launches++;
     LAUNCH_CHECK();
     return MFT_OK;
 }
 
-// ode_mean + ode_maximum of |u - mean| on the post-BC state (hyperviscosity.jl:305-311)
+// ode_mean + ode_maximum of |u - mean| on the post-BC state (hyperviscosity.jl:305-311): two launches,
+// each finishing its own cross-block reduction (last-block ticket)
 static int launch_norms(mft_ctx *c)
 {
     ScopedTimer t(c, MFT_K_REDUCE);
@@ -952,21 +1091,10 @@ static int launch_norms(mft_ctx *c)
     const int64_t n = c->n_local;
     const Vec<4> *u = reinterpret_cast<const Vec<4> *>(c->u.p);
     double *sum = c->stats.p, *mean = c->stats.p + V, *norms = c->stats.p + 2 * V;
-    k_reduce_sum<4><<<c->red_blocks, 256, 0, c->stream>>>(u, n, c->partial.p);
-    c->launches++;
-    LAUNCH_CHECK();
-    const double n_global = (double)n;
-    const double divisor = c->mean_div_vn ? (double)V * n_global : n_global;
-    k_finish_mean<4><<<1, 32, 0, c->stream>>>(c->partial.p, c->red_blocks, divisor, sum);
-    c->launches++;
-    LAUNCH_CHECK();
-    if (c->max_lex) {
-        k_reduce_maxdev<4, true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, mean, c->partial.p);
-        k_finish_norms<4, true><<<1, 32, 0, c->stream>>>(c->partial.p, c->red_blocks, norms, 1);
-    } else {
-        k_reduce_maxdev<4, false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, mean, c->partial.p);
-        k_finish_norms<4, false><<<1, 32, 0, c->stream>>>(c->partial.p, c->red_blocks, norms, 1);
-    }
+    const double divisor = c->mean_div_vn ? (double)V * (double)n : (double)n;
+    k_sum_mean<4><<<c->red_blocks, 256, 0, c->stream>>>(u, n, c->partial.p, c->ticket.p, divisor, sum);
+    if (c->max_lex) k_maxdev_norms<4, true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, mean, c->partial.p, c->ticket.p + 1, norms);
+    else k_maxdev_norms<4, false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, mean, c->partial.p, c->ticket.p + 1, norms);
     c->launches += 2;
     LAUNCH_CHECK();
     return MFT_OK;
@@ -1156,8 +1284,7 @@ static int history_push_common(mft_ctx *c, double t, int64_t success_iter, bool 
         c->launches++;
         LAUNCH_CHECK();
     }
-    CU(cudaStreamSynchronize(c->stream));
-    return MFT_OK;
+    return MFT_OK;  // asynchronous (stream order); downloads / mft_synchronize wait
 }
 
 extern "C" int mft_history_push(mft_ctx *c, double t, int64_t success_iter, int approx_order)

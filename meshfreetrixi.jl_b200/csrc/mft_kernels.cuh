@@ -9,7 +9,8 @@
 //   g = eps .* (Dx u, Dy u)                        : AoS, one Vec<2V> per point (x-part then y-part)
 //   operators                                      : sliced ELL, slice = 32 consecutive device rows (one warp);
 //        entry (slice s, column c, lane l) lives at ((off[s] + c) * 32 + l) in idx[] / wx[] / wy[];
-//        idx < 0 marks padding.  Within a row the entries are stored in the reference's summation order.
+//        padding entries point at the row itself with weight 0 (adds an exact 0, keeps the loops branch-free).
+//        Within a row the entries are stored in the reference's summation order.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,25 +25,100 @@ struct alignas(8 * V) Vec {
     double a[V];
 };
 
-struct Ell2 {
-    const int *idx;
-    const double *wx;
-    const double *wy;
+// One operator = one array of per-slice blobs.  Slice s (32 rows, width w = off[s+1]-off[s] columns) occupies
+// COLB*w bytes at base + off[s]*COLB:   [ idx : w x 32 x int32 ][ wx : w x 32 x double ][ wy : w x 32 x double ]
+// (single-weight operators have no wy block).  A blob is contiguous and 128-byte aligned, so a warp brings it
+// (or its index block) into shared memory with ONE bulk-async copy (cp.async.bulk, the 1-D TMA path) and the
+// entries of lane l sit at stride 32 -> conflict-free shared-memory reads.
+struct EllBlob {
+    const unsigned char *base;
     const int *off;  // nslices + 1 column offsets
 };
-struct Ell1 {
-    const int *idx;
-    const double *w;
-    const int *off;
+constexpr int kColBytes2 = kSlice * (4 + 8 + 8);  // 640: paired (Dx,Dy) operator
+constexpr int kColBytes1 = kSlice * (4 + 8);      // 384: single-weight operator
+
+// ---- mbarrier + bulk-async copy (TMA 1-D) -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// Per-warp staging of one slice.  STAGE_W: the whole blob goes to shared memory; otherwise only the index block
+// does (the address-dependency chain idx -> gather then never waits on DRAM), the weight blocks are read with
+// coalesced loads and the weight blocks of the slice `pf_dist` ahead are pulled into L2 by a bulk prefetch.
+struct SliceView {
+    const int *ip;       // + c*32 : column c, this lane
+    const double *wxp;   // + c*32
+    const double *wyp;   // + c*32 (paired only)
+    int width;
 };
+template <int COLB, bool STAGE_W>
+__device__ __forceinline__ SliceView stage_slice(const EllBlob &op, int64_t slice, int64_t n_slices, unsigned char *buf,
+                                                 uint64_t *bar, int lane, int pf_dist)
+{
+    const int off = op.off[slice];
+    const int width = op.off[slice + 1] - off;
+    const unsigned char *src = op.base + (size_t)off * COLB;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    if (lane == 0 && width > 0) {
+        const uint32_t bytes = (uint32_t)width * (STAGE_W ? COLB : kSlice * 4);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(buf, src, bytes, bar);
+        if (!STAGE_W) {
+            const int64_t s2 = slice + pf_dist;
+            if (s2 < n_slices) {
+                const int off2 = op.off[s2];
+                const int w2 = op.off[s2 + 1] - off2;
+                if (w2 > 0) bulk_prefetch_l2(op.base + (size_t)off2 * COLB + (size_t)w2 * kSlice * 4, (uint32_t)w2 * (COLB - kSlice * 4));
+            }
+            if (slice < pf_dist) bulk_prefetch_l2(src + (size_t)width * kSlice * 4, (uint32_t)width * (COLB - kSlice * 4));
+        }
+    }
+    SliceView v;
+    v.width = width;
+    v.ip = reinterpret_cast<const int *>(buf) + lane;
+    const unsigned char *wbase = STAGE_W ? buf : src;
+    v.wxp = reinterpret_cast<const double *>(wbase + (size_t)width * kSlice * 4) + lane;
+    v.wyp = reinterpret_cast<const double *>(wbase + (size_t)width * kSlice * 12) + lane;
+    return v;
+}
 
 // ---- 256-bit / 64-bit read-only loads and stores ------------------------------------------------------
 __device__ __forceinline__ Vec<4> ld_ro(const Vec<4> *p)
 {
     Vec<4> v;
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(v.a[0]), "=d"(v.a[1]), "=d"(v.a[2]), "=d"(v.a[3])
-                 : "l"(p));
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+        : "=d"(v.a[0]), "=d"(v.a[1]), "=d"(v.a[2]), "=d"(v.a[3])
+        : "l"(p));
     return v;
 }
 __device__ __forceinline__ Vec<1> ld_ro(const Vec<1> *p)
@@ -54,12 +130,12 @@ __device__ __forceinline__ Vec<1> ld_ro(const Vec<1> *p)
 __device__ __forceinline__ Vec<8> ld_ro(const Vec<8> *p)
 {
     Vec<8> v;
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(v.a[0]), "=d"(v.a[1]), "=d"(v.a[2]), "=d"(v.a[3])
-                 : "l"(p));
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4+32];"
-                 : "=d"(v.a[4]), "=d"(v.a[5]), "=d"(v.a[6]), "=d"(v.a[7])
-                 : "l"(p));
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+        : "=d"(v.a[0]), "=d"(v.a[1]), "=d"(v.a[2]), "=d"(v.a[3])
+        : "l"(p));
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4+32];"
+        : "=d"(v.a[4]), "=d"(v.a[5]), "=d"(v.a[6]), "=d"(v.a[7])
+        : "l"(p));
     return v;
 }
 __device__ __forceinline__ Vec<2> ld_ro(const Vec<2> *p)
@@ -152,7 +228,10 @@ struct Physics<EQ_ADVECTION2D, 1> {
 // index / weight streams are read as fully coalesced 128-B / 256-B requests and each neighbour state is one
 // 32-byte sector fetched with a single 256-bit load.
 struct PassAArgs {
-    Ell2 op;
+    EllBlob op;
+    int64_t n_slices;
+    int buf_bytes;  // shared-memory bytes per warp
+    int pf_dist;    // L2 prefetch distance in slices
     const void *u;
     void *du;
     void *g;
@@ -172,19 +251,22 @@ constexpr int VISC_NONE = 0;
 constexpr int VISC_UPWIND = 1;
 constexpr int VISC_RESIDUAL = 2;
 
-template <int V, int EQ, bool EXACT, bool DO_FLUX, int VISC>
+template <int V, int EQ, bool EXACT, bool DO_FLUX, int VISC, bool STAGE_W>
 __global__ void __launch_bounds__(128) k_pass_a(const PassAArgs A)
 {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= A.n_rows) return;
-    const int64_t slice = row >> 5;
-    const int lane = (int)(row & 31);
-    const int off = A.op.off[slice];
-    const int width = A.op.off[slice + 1] - off;
-    const int64_t base = (int64_t)off * kSlice + lane;
-    const int *__restrict__ ip = A.op.idx + base;
-    const double *__restrict__ wxp = A.op.wx + base;
-    const double *__restrict__ wyp = A.op.wy + base;
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ uint64_t bars[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t slice = (int64_t)blockIdx.x * 4 + warp;
+    if (slice >= A.n_slices) return;  // warps are independent: per-warp barriers only
+    const int64_t row = slice * kSlice + lane;
+    const bool live = row < A.n_rows;
+    const SliceView sv = stage_slice<kColBytes2, STAGE_W>(A.op, slice, A.n_slices, smem_dyn + (size_t)warp * A.buf_bytes,
+                                                         &bars[warp], lane, A.pf_dist);
+    const int width = sv.width;
+    const int *ip = sv.ip;
+    const double *wxp = sv.wxp;
+    const double *wyp = sv.wyp;
     const Vec<V> *__restrict__ u = reinterpret_cast<const Vec<V> *>(A.u);
 
     Physics<EQ, V> ph;
@@ -198,77 +280,120 @@ __global__ void __launch_bounds__(128) k_pass_a(const PassAArgs A)
     Vec<V> acc, gx, gy;
 #pragma unroll
     for (int v = 0; v < V; ++v) acc.a[v] = gx.a[v] = gy.a[v] = 0.0;
-    if (DO_FLUX && A.accumulate) acc = reinterpret_cast<const Vec<V> *>(A.du)[row];
+    if (DO_FLUX && A.accumulate && live) acc = reinterpret_cast<const Vec<V> *>(A.du)[row];
+    // own-row operands of the viscosity limiter: issued before the wait so they overlap the bulk copy
+    Vec<V> ui, ad;
+#pragma unroll
+    for (int v = 0; v < V; ++v) ui.a[v] = ad.a[v] = 0.0;
+    if constexpr (VISC != VISC_NONE) {
+        if (live) {
+            ui = ld_ro(u + row);
+            if constexpr (VISC == VISC_RESIDUAL) ad = ld_ro(reinterpret_cast<const Vec<V> *>(A.approx_du) + row);
+        }
+    }
+    if (width > 0) mbar_wait(&bars[warp], 0);
 
+    // Every loop below runs in batches of kBatch columns: all index / weight / neighbour-state loads of a batch
+    // are issued before any arithmetic, so a thread keeps kBatch independent gathers in flight (the FP64 division
+    // in the flux has a slow-path branch that otherwise stops the compiler from overlapping iterations).
+    // Columns past `width` are clamped to the last column with weight 0 (adds an exact zero).
+    constexpr int kBatch = 5;
     if constexpr (EXACT) {
         // reference order: all Dx terms in ascending column order, then all Dy terms, separate mul and add
         // (SparseArrays mul!).  alpha = -1 is folded into the flux first: w * (-F).
-#pragma unroll 4
-        for (int c = 0; c < width; ++c) {
-            const int j = ip[(int64_t)c * kSlice];
-            if (j < 0) continue;
-            const double wx = wxp[(int64_t)c * kSlice];
-            const Vec<V> uj = ld_ro(u + j);
-            if constexpr (DO_FLUX) {
-                ph.prepare(uj);
-                const Vec<V> f = ph.flux_x(uj);
+        for (int c0 = 0; c0 < width; c0 += kBatch) {
+            Vec<V> uj[kBatch];
+            double w[kBatch];
 #pragma unroll
-                for (int v = 0; v < V; ++v) acc.a[v] = acc.a[v] + wx * (-f.a[v]);
+            for (int b = 0; b < kBatch; ++b) {
+                const bool ok = c0 + b < width;
+                const int cc = ok ? c0 + b : width - 1;
+                const int j = ip[cc * kSlice];
+                const double wv = wxp[cc * kSlice];
+                w[b] = ok ? wv : 0.0;
+                uj[b] = ld_ro(u + j);
             }
-            if constexpr (VISC != VISC_NONE) {
 #pragma unroll
-                for (int v = 0; v < V; ++v) gx.a[v] = gx.a[v] + wx * uj.a[v];
+            for (int b = 0; b < kBatch; ++b) {
+                if constexpr (DO_FLUX) {
+                    ph.prepare(uj[b]);
+                    const Vec<V> f = ph.flux_x(uj[b]);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) acc.a[v] = acc.a[v] + w[b] * (-f.a[v]);
+                }
+                if constexpr (VISC != VISC_NONE) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) gx.a[v] = gx.a[v] + w[b] * uj[b].a[v];
+                }
             }
         }
-#pragma unroll 4
-        for (int c = 0; c < width; ++c) {
-            const int j = ip[(int64_t)c * kSlice];
-            if (j < 0) continue;
-            const double wy = wyp[(int64_t)c * kSlice];
-            const Vec<V> uj = ld_ro(u + j);
-            if constexpr (DO_FLUX) {
-                ph.prepare(uj);
-                const Vec<V> f = ph.flux_y(uj);
+        for (int c0 = 0; c0 < width; c0 += kBatch) {
+            Vec<V> uj[kBatch];
+            double w[kBatch];
 #pragma unroll
-                for (int v = 0; v < V; ++v) acc.a[v] = acc.a[v] + wy * (-f.a[v]);
+            for (int b = 0; b < kBatch; ++b) {
+                const bool ok = c0 + b < width;
+                const int cc = ok ? c0 + b : width - 1;
+                const int j = ip[cc * kSlice];
+                const double wv = wyp[cc * kSlice];
+                w[b] = ok ? wv : 0.0;
+                uj[b] = ld_ro(u + j);
             }
-            if constexpr (VISC != VISC_NONE) {
 #pragma unroll
-                for (int v = 0; v < V; ++v) gy.a[v] = gy.a[v] + wy * uj.a[v];
+            for (int b = 0; b < kBatch; ++b) {
+                if constexpr (DO_FLUX) {
+                    ph.prepare(uj[b]);
+                    const Vec<V> f = ph.flux_y(uj[b]);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) acc.a[v] = acc.a[v] + w[b] * (-f.a[v]);
+                }
+                if constexpr (VISC != VISC_NONE) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) gy.a[v] = gy.a[v] + w[b] * uj[b].a[v];
+                }
             }
         }
     } else {
         // single sweep, FMA accumulation (not the reference's rounding sequence; agrees to ~1e-13 normwise)
-#pragma unroll 4
-        for (int c = 0; c < width; ++c) {
-            const int j = ip[(int64_t)c * kSlice];
-            if (j < 0) continue;
-            const double wx = wxp[(int64_t)c * kSlice];
-            const double wy = wyp[(int64_t)c * kSlice];
-            const Vec<V> uj = ld_ro(u + j);
-            if constexpr (DO_FLUX) {
-                ph.prepare(uj);
-                const Vec<V> f = ph.flux_x(uj);
-                const Vec<V> h = ph.flux_y(uj);
+        for (int c0 = 0; c0 < width; c0 += kBatch) {
+            Vec<V> uj[kBatch];
+            double wa[kBatch], wb[kBatch];
 #pragma unroll
-                for (int v = 0; v < V; ++v) acc.a[v] = fma(-wy, h.a[v], fma(-wx, f.a[v], acc.a[v]));
+            for (int b = 0; b < kBatch; ++b) {
+                const bool ok = c0 + b < width;
+                const int cc = ok ? c0 + b : width - 1;
+                const int j = ip[cc * kSlice];
+                const double w1 = wxp[cc * kSlice], w2 = wyp[cc * kSlice];
+                wa[b] = ok ? w1 : 0.0;
+                wb[b] = ok ? w2 : 0.0;
+                uj[b] = ld_ro(u + j);
             }
-            if constexpr (VISC != VISC_NONE) {
 #pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    gx.a[v] = fma(wx, uj.a[v], gx.a[v]);
-                    gy.a[v] = fma(wy, uj.a[v], gy.a[v]);
+            for (int b = 0; b < kBatch; ++b) {
+                if constexpr (DO_FLUX) {
+                    ph.prepare(uj[b]);
+                    const Vec<V> f = ph.flux_x(uj[b]);
+                    const Vec<V> h = ph.flux_y(uj[b]);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) acc.a[v] = fma(-wb[b], h.a[v], fma(-wa[b], f.a[v], acc.a[v]));
+                }
+                if constexpr (VISC != VISC_NONE) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        gx.a[v] = fma(wa[b], uj[b].a[v], gx.a[v]);
+                        gy.a[v] = fma(wb[b], uj[b].a[v], gy.a[v]);
+                    }
                 }
             }
         }
     }
 
+    if (!live) return;
     if constexpr (DO_FLUX) st_vec(reinterpret_cast<Vec<V> *>(A.du) + row, acc);
 
     if constexpr (VISC != VISC_NONE) {
         static_assert(VISC == VISC_NONE || (EQ == EQ_EULER2D && V == 4), "viscosity sources are Euler-2D only");
         // update_upwind_visc!  hyperviscosity.jl:246-285
-        const Vec<V> ui = ld_ro(u + row);
         double v1, v2, p;
         euler_prim(A.eqp0, ui, v1, v2, p);
         const double speed = sqrt(v1 * v1 + v2 * v2);
@@ -288,7 +413,6 @@ __global__ void __launch_bounds__(128) k_pass_a(const PassAArgs A)
             } else {
                 dui = reinterpret_cast<const Vec<V> *>(A.du)[row];
             }
-            const Vec<V> ad = ld_ro(reinterpret_cast<const Vec<V> *>(A.approx_du) + row);
             Vec<V> res;
 #pragma unroll
             for (int v = 0; v < V; ++v) res.a[v] = fabs(ad.a[v] - dui.a[v]);
@@ -330,95 +454,135 @@ __global__ void __launch_bounds__(128) k_pass_a(const PassAArgs A)
 // adjoint mul! (call sites hyperviscosity.jl:376-377, 405-406):
 //   tmp = sum_j A[j,i] * x[j] (ascending j), then C[i] += tmp * (-1); x-direction first, then y.
 struct PassBArgs {
-    Ell2 opT;
+    EllBlob opT;
     const void *g;
     void *du;
     int64_t n_rows;
+    int64_t n_slices;
+    int buf_bytes;
+    int pf_dist;
 };
 
-template <int V, bool EXACT>
+template <int V, bool EXACT, bool STAGE_W>
 __global__ void __launch_bounds__(128) k_pass_b(const PassBArgs A)
 {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= A.n_rows) return;
-    const int64_t slice = row >> 5;
-    const int lane = (int)(row & 31);
-    const int off = A.opT.off[slice];
-    const int width = A.opT.off[slice + 1] - off;
-    const int64_t base = (int64_t)off * kSlice + lane;
-    const int *__restrict__ ip = A.opT.idx + base;
-    const double *__restrict__ wxp = A.opT.wx + base;
-    const double *__restrict__ wyp = A.opT.wy + base;
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ uint64_t bars[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t slice = (int64_t)blockIdx.x * 4 + warp;
+    if (slice >= A.n_slices) return;
+    const int64_t row = slice * kSlice + lane;
+    const bool live = row < A.n_rows;
+    const SliceView sv = stage_slice<kColBytes2, STAGE_W>(A.opT, slice, A.n_slices, smem_dyn + (size_t)warp * A.buf_bytes,
+                                                         &bars[warp], lane, A.pf_dist);
+    const int width = sv.width;
+    const int *ip = sv.ip;
+    const double *wxp = sv.wxp;
+    const double *wyp = sv.wyp;
     const Vec<2 * V> *__restrict__ g = reinterpret_cast<const Vec<2 * V> *>(A.g);
 
     Vec<V> tx, ty;
 #pragma unroll
     for (int v = 0; v < V; ++v) tx.a[v] = ty.a[v] = 0.0;
-#pragma unroll 4
-    for (int c = 0; c < width; ++c) {
-        const int j = ip[(int64_t)c * kSlice];
-        if (j < 0) continue;
-        const double wx = wxp[(int64_t)c * kSlice];
-        const double wy = wyp[(int64_t)c * kSlice];
-        const Vec<2 * V> gj = ld_ro(g + j);
+    Vec<V> d;
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            if constexpr (EXACT) {
-                tx.a[v] = tx.a[v] + wx * gj.a[v];
-                ty.a[v] = ty.a[v] + wy * gj.a[V + v];
-            } else {
-                tx.a[v] = fma(wx, gj.a[v], tx.a[v]);
-                ty.a[v] = fma(wy, gj.a[V + v], ty.a[v]);
+    for (int v = 0; v < V; ++v) d.a[v] = 0.0;
+    if (live) d = reinterpret_cast<const Vec<V> *>(A.du)[row];
+    if (width > 0) mbar_wait(&bars[warp], 0);
+    constexpr int kBatch = 4;
+    for (int c0 = 0; c0 < width; c0 += kBatch) {
+        Vec<2 * V> gj[kBatch];
+        double wa[kBatch], wb[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const bool ok = c0 + b < width;
+            const int cc = ok ? c0 + b : width - 1;
+            const int j = ip[cc * kSlice];
+            const double w1 = wxp[cc * kSlice], w2 = wyp[cc * kSlice];
+            wa[b] = ok ? w1 : 0.0;
+            wb[b] = ok ? w2 : 0.0;
+            gj[b] = ld_ro(g + j);
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                if constexpr (EXACT) {
+                    tx.a[v] = tx.a[v] + wa[b] * gj[b].a[v];
+                    ty.a[v] = ty.a[v] + wb[b] * gj[b].a[V + v];
+                } else {
+                    tx.a[v] = fma(wa[b], gj[b].a[v], tx.a[v]);
+                    ty.a[v] = fma(wb[b], gj[b].a[V + v], ty.a[v]);
+                }
             }
         }
     }
-    Vec<V> *dup = reinterpret_cast<Vec<V> *>(A.du) + row;
-    Vec<V> d = *dup;
+    if (!live) return;
 #pragma unroll
     for (int v = 0; v < V; ++v) d.a[v] = (d.a[v] + tx.a[v] * -1.0) + ty.a[v] * -1.0;
-    st_vec(dup, d);
+    st_vec(reinterpret_cast<Vec<V> *>(A.du) + row, d);
 }
 
 // ---- generic single-matrix source: du += alpha * H u  (hyperviscosity, hyperviscosity.jl:52-64,121-134) ----
 struct SpmvArgs {
-    Ell1 op;
+    EllBlob op;
     const void *x;
     void *y;
     int64_t n_rows;
+    int64_t n_slices;
+    int buf_bytes;
+    int pf_dist;
     double alpha;
 };
 
-template <int V, bool EXACT>
+template <int V, bool EXACT, bool STAGE_W>
 __global__ void __launch_bounds__(128) k_spmv_accum(const SpmvArgs A)
 {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= A.n_rows) return;
-    const int64_t slice = row >> 5;
-    const int lane = (int)(row & 31);
-    const int off = A.op.off[slice];
-    const int width = A.op.off[slice + 1] - off;
-    const int64_t base = (int64_t)off * kSlice + lane;
-    const int *__restrict__ ip = A.op.idx + base;
-    const double *__restrict__ wp = A.op.w + base;
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ uint64_t bars[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t slice = (int64_t)blockIdx.x * 4 + warp;
+    if (slice >= A.n_slices) return;
+    const int64_t row = slice * kSlice + lane;
+    const bool live = row < A.n_rows;
+    const SliceView sv = stage_slice<kColBytes1, STAGE_W>(A.op, slice, A.n_slices, smem_dyn + (size_t)warp * A.buf_bytes,
+                                                         &bars[warp], lane, A.pf_dist);
+    const int width = sv.width;
+    const int *ip = sv.ip;
+    const double *wp = sv.wxp;
     const Vec<V> *__restrict__ x = reinterpret_cast<const Vec<V> *>(A.x);
     Vec<V> *yp = reinterpret_cast<Vec<V> *>(A.y) + row;
-    Vec<V> acc = *yp;
-#pragma unroll 4
-    for (int c = 0; c < width; ++c) {
-        const int j = ip[(int64_t)c * kSlice];
-        if (j < 0) continue;
-        const double w = wp[(int64_t)c * kSlice];
-        const Vec<V> xj = ld_ro(x + j);
+    Vec<V> acc;
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            if constexpr (EXACT) {
-                acc.a[v] = acc.a[v] + w * (xj.a[v] * A.alpha);
-            } else {
-                acc.a[v] = fma(w, xj.a[v] * A.alpha, acc.a[v]);
+    for (int v = 0; v < V; ++v) acc.a[v] = 0.0;
+    if (live) acc = *yp;
+    if (width > 0) mbar_wait(&bars[warp], 0);
+    constexpr int kBatch = 6;
+    for (int c0 = 0; c0 < width; c0 += kBatch) {
+        Vec<V> xj[kBatch];
+        double w[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const bool ok = c0 + b < width;
+            const int cc = ok ? c0 + b : width - 1;
+            const int j = ip[cc * kSlice];
+            const double wv = wp[cc * kSlice];
+            w[b] = ok ? wv : 0.0;
+            xj[b] = ld_ro(x + j);
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                if constexpr (EXACT) {
+                    acc.a[v] = acc.a[v] + w[b] * (xj[b].a[v] * A.alpha);
+                } else {
+                    acc.a[v] = fma(w[b], xj[b].a[v] * A.alpha, acc.a[v]);
+                }
             }
         }
     }
-    st_vec(yp, acc);
+    if (live) st_vec(yp, acc);
 }
 
 // ---- strong boundary conditions (calc_single_boundary_flux!, rbfsolver.jl:288-318) -------------------------
@@ -594,6 +758,176 @@ __global__ void k_finish_norms(const double *partial, int nblocks, double *norms
         for (int v = 0; v < V; ++v) {
             if (replace_zero && best[v] == 0.0) best[v] = kEps;
             norms[v] = best[v];
+        }
+    }
+}
+
+// Single-launch variants for one GPU: every block writes its partial, the last block to finish (atomic ticket)
+// combines the partials in a fixed order -> deterministic for a fixed grid size.
+template <int V>
+__global__ void __launch_bounds__(256) k_sum_mean(const Vec<V> *__restrict__ u, int64_t n, double *partial,
+                                                unsigned int *ticket, double divisor, double *stats)
+{
+    double s[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) s[v] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Vec<V> x = ld_ro(u + i);
+#pragma unroll
+        for (int v = 0; v < V; ++v) s[v] += x.a[v];
+    }
+    __shared__ double sh[8][V];
+    __shared__ bool is_last;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        for (int o = 16; o > 0; o >>= 1) s[v] += __shfl_down_sync(0xffffffffu, s[v], o);
+    if (l == 0)
+        for (int v = 0; v < V; ++v) sh[w][v] = s[v];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int v = 0; v < V; ++v) {
+            double t = 0.0;
+            for (int k = 0; k < 8; ++k) t += sh[k][v];
+            partial[(int64_t)blockIdx.x * V + v] = t;
+        }
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int v = 0; v < V; ++v) s[v] = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+        for (int v = 0; v < V; ++v) s[v] += __ldcg(&partial[(int64_t)b * V + v]);
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        for (int o = 16; o > 0; o >>= 1) s[v] += __shfl_down_sync(0xffffffffu, s[v], o);
+    __syncthreads();
+    if (l == 0)
+        for (int v = 0; v < V; ++v) sh[w][v] = s[v];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int v = 0; v < V; ++v) {
+            double t = 0.0;
+            for (int k = 0; k < 8; ++k) t += sh[k][v];
+            stats[v] = t;
+            stats[V + v] = t / divisor;
+        }
+        *ticket = 0;
+    }
+}
+
+template <int V, bool LEX>
+__global__ void __launch_bounds__(256) k_maxdev_norms(const Vec<V> *__restrict__ u, int64_t n, const double *mean,
+                                                    double *partial, unsigned int *ticket, double *norms)
+{
+    double m[V], best[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        m[v] = mean[v];
+        best[v] = -1.0;
+    }
+    auto combine = [&](double *a, const double *b) {
+        if constexpr (LEX) {
+            if (lex_less<V>(a, b)) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) a[v] = b[v];
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) a[v] = jl_max(a[v], b[v]);
+        }
+    };
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Vec<V> x = ld_ro(u + i);
+        double c[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) c[v] = fabs(x.a[v] - m[v]);
+        combine(best, c);
+    }
+    __shared__ double sh[8][V];
+    __shared__ bool is_last;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    auto block_reduce = [&]() {
+        for (int o = 16; o > 0; o >>= 1) {
+            double other[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) other[v] = __shfl_down_sync(0xffffffffu, best[v], o);
+            combine(best, other);
+        }
+        if (l == 0)
+            for (int v = 0; v < V; ++v) sh[w][v] = best[v];
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int k = 1; k < 8; ++k) combine(best, sh[k]);
+    };
+    block_reduce();
+    if (threadIdx.x == 0) {
+        for (int v = 0; v < V; ++v) partial[(int64_t)blockIdx.x * V + v] = best[v];
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int v = 0; v < V; ++v) best[v] = -1.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+        double c[V];
+        for (int v = 0; v < V; ++v) c[v] = __ldcg(&partial[(int64_t)b * V + v]);
+        combine(best, c);
+    }
+    __syncthreads();
+    block_reduce();
+    if (threadIdx.x == 0) {
+        for (int v = 0; v < V; ++v) norms[v] = best[v] == 0.0 ? kEps : best[v];
+        *ticket = 0;
+    }
+}
+
+// all boundary groups in one launch (used when no point belongs to two groups, so the group order cannot matter)
+struct BcMergedArgs {
+    int64_t nb;
+    const int *kind;
+    const int *idx;
+    const double *normals;
+    const double *values;
+    void *u;
+    void *du;
+};
+template <int V>
+__global__ void k_boundary_merged(const BcMergedArgs A)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A.nb) return;
+    const int kind = A.kind[j];
+    const int b = A.idx[j];
+    Vec<V> *u = reinterpret_cast<Vec<V> *>(A.u) + b;
+    Vec<V> *du = A.du ? reinterpret_cast<Vec<V> *>(A.du) + b : nullptr;
+    if (kind == 0) {
+        Vec<V> val;
+#pragma unroll
+        for (int v = 0; v < V; ++v) val.a[v] = A.values[j * V + v];
+        *u = val;
+        if (du) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) du->a[v] = 0.0;
+        }
+    } else if (kind == 1) {
+        if constexpr (V == 4) {
+            const double nx0 = A.normals[2 * j], ny0 = A.normals[2 * j + 1];
+            const double nrm = sqrt(nx0 * nx0 + ny0 * ny0);
+            const double nx = nx0 / nrm, ny = ny0 / nrm;
+            const double m1 = u->a[1], m2 = u->a[2];
+            const double vdotn = m1 * nx + m2 * ny;
+            u->a[1] = m1 - vdotn * nx;
+            u->a[2] = m2 - vdotn * ny;
+            if (du) {
+                du->a[1] = 0.0;
+                du->a[2] = 0.0;
+            }
         }
     }
 }
