@@ -31,6 +31,7 @@ UNIT = "point-stage updates/s"
 GAMMA = 1.4
 K_STENCIL = 20
 STAGES = 3
+CLOUD_ORDER = "hilbert"
 
 
 def measured_peak():
@@ -93,6 +94,8 @@ def build_workload(nx, ny, seed, m, need_oracle_ops=False):
     """config 2 of SURVEY.md 8d: jittered lattice on [0,10]^2 + boundary ring, Dirichlet(vortex at t=0) on all sides"""
     t0 = time.time()
     cl = m.cloud.jittered_lattice(nx, ny, 10.0, 10.0 * ny / nx, seed=seed)
+    if CLOUD_ORDER == "hilbert":   # emit the synthetic cloud along a Hilbert curve (point numbering is arbitrary)
+        cl = m.cloud.reorder(cl, m._lib.sfc_order(cl.points))
     basis = m.PointCloudBasis(m.Point2D(), 3, approximation_type=m.RBF(m.PolyharmonicSpline(3)))
     return cl, basis, time.time() - t0
 
@@ -117,7 +120,7 @@ def run_ours(args):
     nx = ny = args.n_side
     cl, basis, _ = build_workload(nx, ny, 0, m)
     solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=0, exact_order=not args.fma,
-                                                                stage_weights=bool(args.stage_weights)))
+                                                                stage_weights=int(args.stage_weights)))
     names = dict(left=1, right=2, bottom=3, top=4)
     t_setup = time.time()
     domain = m.PointCloudDomain(solver, cl, names)
@@ -340,7 +343,11 @@ def main():
     ap.add_argument("--stage-weights", type=int, default=1, help="1: whole operator slices staged in smem; 0: indices only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cloud-order", default="hilbert", choices=["hilbert", "lattice"],
+                    help="numbering of the synthetic cloud's points")
     args = ap.parse_args()
+    global CLOUD_ORDER
+    CLOUD_ORDER = args.cloud_order
     if args.impl == "reference":
         run_reference(args)
     else:

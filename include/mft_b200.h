@@ -68,8 +68,9 @@ typedef struct mft_ctx mft_ctx;
 #define MFT_OPT_MAX_LEXICOGRAPHIC 2/* 1 (default): maximum(::StructArray{SVector}) = lexicographic max (mpi.jl:71-81) */
 #define MFT_OPT_DIAGNOSTICS 3      /* 1: keep eps_uw/eps_rv/eps/eps_c/residual for mft_get_field (default 0)     */
 #define MFT_OPT_CUDA_GRAPH 4       /* reserved                                                                         */
-#define MFT_OPT_STAGE_WEIGHTS 5    /* 1 (default): a warp bulk-copies its whole operator slice (indices + weights) into
-                                      shared memory; 0: indices only, weights by coalesced loads + L2 bulk prefetch      */
+#define MFT_OPT_STAGE_WEIGHTS 5    /* bit 0 (forward operator, pass A) / bit 1 (transposed operator, pass B): 1 = a warp bulk-copies
+                                      its whole operator slice (indices + weights) into shared memory, 0 = indices only, weights
+                                      by coalesced loads + L2 bulk prefetch.  Default 1 (measured best: pass A staged, pass B not) */
 #define MFT_OPT_REFINE_ORDER 7     /* 1 (default 0): within blocks of 256 device rows, order rows by D' row length
                                       (near-uniform transposed-ELL slices); the caller-visible numbering is unaffected */
 #define MFT_OPT_PREFETCH_DISTANCE 6/* slices ahead for the L2 prefetch of the weight blocks (STAGE_WEIGHTS = 0)        */

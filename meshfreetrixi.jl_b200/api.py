@@ -64,7 +64,7 @@ class RBFFDEngineCUDA:
     diagnostics: bool = False          # keep eps/eps_uw/eps_rv/residual on device for inspection
     mean_divisor_vn: bool = True       # ode_mean divides by V*N (recursive_length)
     max_lexicographic: bool = True     # maximum(::StructArray{SVector}) is a lexicographic max
-    stage_weights: bool = True         # bulk-copy whole operator slices to shared memory (else indices only)
+    stage_weights: int = 1             # bit0: pass A, bit1: pass B -- bulk-copy whole operator slices to smem
     refine_order: bool = False         # order rows inside 256-row blocks by D' row length (less padding, worse gather locality)
 
 

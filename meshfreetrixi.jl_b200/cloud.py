@@ -88,6 +88,18 @@ def jittered_lattice(nx: int, ny: int, lx: float, ly: float, seed: int = 0, jitt
     return Cloud(pts, idxs, nrm, np.arange(n0), (x0, y0, lx, ly))
 
 
+def reorder(cloud: Cloud, perm: np.ndarray) -> Cloud:
+    """Renumber the points: new point d is old point perm[d] (e.g. a Hilbert order from mft_sfc_order).  The numbering
+    of a scattered cloud is arbitrary; a space-filling-curve numbering makes "ascending neighbour index" -- the
+    order in which the reference's CSC SpMV sums a row -- spatially coherent, which is what the gather hardware likes."""
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm), dtype=perm.dtype)
+    idxs = [inv[b] for b in cloud.boundary_idxs]
+    interior = inv[cloud.interior_idx] if cloud.interior_idx is not None else None
+    return Cloud(np.ascontiguousarray(cloud.points[perm]), idxs, [n.copy() for n in cloud.boundary_normals], interior,
+                 cloud.extent)
+
+
 # ---- initial conditions (return conservative variables, shape (4,N)) -----------------------------------
 def prim2cons(rho, v1, v2, p, gamma):
     return np.stack([rho, rho * v1, rho * v2, p / (gamma - 1.0) + 0.5 * rho * (v1 * v1 + v2 * v2)])

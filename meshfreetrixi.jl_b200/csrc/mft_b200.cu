@@ -128,7 +128,7 @@ struct mft_ctx {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     // options
-    int exact = 1, mean_div_vn = 1, max_lex = 1, diagnostics = 0, stage_w = 1, pf_dist = 0, refine_order = 0;
+    int exact = 1, mean_div_vn = 1, max_lex = 1, diagnostics = 0, stage_w = 1, stage_w_b = 0, pf_dist = 0, refine_order = 0;
     std::vector<const void *> smem_configured;
     // ordering
     bool have_perm = false;
@@ -164,6 +164,15 @@ struct mft_ctx {
     int red_blocks = 0;
     bool have_fsal = false;
     int64_t launches = 0;
+    // captured SSPRK steps (CUDA graphs), keyed by the launch parameters that are baked into kernel arguments
+    struct StepGraph {
+        double dt;
+        int si_zero, with_first_rhs, uses;
+        int64_t nlaunch;
+        cudaGraphExec_t exec;
+    };
+    std::vector<StepGraph> graphs;
+    int use_graphs = 1;
     // per-class timing
     bool timing = false;
     KTimer kt;
@@ -260,11 +269,15 @@ extern "C" int mft_ctx_create(mft_ctx **out, int device, int64_t n_local, int64_
     CU(cudaEventCreate(&c->ev_t0));
     CU(cudaEventCreate(&c->ev_t1));
     const int64_t len = c->n_tot * nvars;
-    CHECK(c->u.alloc(len));
+    CHECK(c->u.alloc(len + nvars));  // + the dummy record gathered by padding entries
     CHECK(c->du.alloc(len));
     CHECK(c->stage_soa.alloc(len));
-    CU(cudaMemset(c->u.p, 0, sizeof(double) * len));
+    CU(cudaMemset(c->u.p, 0, sizeof(double) * (len + nvars)));
     CU(cudaMemset(c->du.p, 0, sizeof(double) * len));
+    if (nvars == 4) {  // a finite Euler state so that the flux of the dummy record is finite (its weight is 0)
+        const double dummy[4] = {1.0, 0.0, 0.0, 1.0};
+        CU(cudaMemcpy(c->u.p + len, dummy, sizeof dummy, cudaMemcpyHostToDevice));
+    }
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->red_blocks = prop.multiProcessorCount * 4;
@@ -307,6 +320,8 @@ extern "C" int mft_ctx_destroy(mft_ctx *c)
     c->bc_idx.release();
     c->bc_normals.release();
     c->bc_values.release();
+    for (auto &g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto ev : c->kt.ev) cudaEventDestroy(ev);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -352,8 +367,8 @@ extern "C" int mft_set_option(mft_ctx *c, int option, double value)
     case MFT_OPT_MEAN_DIVISOR_VN: c->mean_div_vn = value != 0; break;
     case MFT_OPT_MAX_LEXICOGRAPHIC: c->max_lex = value != 0; break;
     case MFT_OPT_DIAGNOSTICS: c->diagnostics = value != 0; break;
-    case MFT_OPT_CUDA_GRAPH: break;  // reserved
-    case MFT_OPT_STAGE_WEIGHTS: c->stage_w = value != 0; break;
+    case MFT_OPT_CUDA_GRAPH: c->use_graphs = value != 0; break;
+    case MFT_OPT_STAGE_WEIGHTS: c->stage_w = ((int)value & 1) != 0; c->stage_w_b = ((int)value & 2) != 0; break;
     case MFT_OPT_PREFETCH_DISTANCE: c->pf_dist = (int)value; break;
     case MFT_OPT_REFINE_ORDER: c->refine_order = value != 0; break;
     default: return fail(MFT_EINVAL, "mft_set_option: unknown option %d", option);
@@ -643,11 +658,8 @@ static int build_ell(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, bool paired, 
         int *idx = reinterpret_cast<int *>(b);
         double *wx = reinterpret_cast<double *>(b + (size_t)w * kSlice * 4);
         double *wy = reinterpret_cast<double *>(b + (size_t)w * kSlice * 12);
-        // padding: (row itself, weight 0) -> contributes an exact zero; dead lanes of the last slice point at row 0
-        for (int q = 0; q < w * kSlice; ++q) {
-            const int64_t d = s * kSlice + (q % kSlice);
-            idx[q] = d < nrows_dev ? (int)d : 0;
-        }
+        // padding: the dummy record (index n_tot) with weight 0 -> adds an exact zero, one shared sector per request
+        for (int q = 0; q < w * kSlice; ++q) idx[q] = (int)c->n_tot;
         for (int64_t d = s * kSlice; d < std::min(nrows_dev, (s + 1) * kSlice); ++d) {
             const int64_t r = caller_row(d);
             const int lane = (int)(d - s * kSlice);
@@ -728,8 +740,8 @@ extern "C" int mft_finalize(mft_ctx *c)
     CHECK(build_ell(c, F, c->n_local, true, c->fwd));
     if (has_visc(c)) {
         CHECK(build_ell(c, T, c->n_local, true, c->tra));
-        CHECK(c->g.alloc(n * 2 * c->V));
-        CU(cudaMemset(c->g.p, 0, sizeof(double) * n * 2 * c->V));
+        CHECK(c->g.alloc((n + 1) * 2 * c->V));  // + zero dummy record
+        CU(cudaMemset(c->g.p, 0, sizeof(double) * (n + 1) * 2 * c->V));
     }
     for (auto *s : c->srcs) {
         if (s->kind == MFT_SRC_HV_FLYER || s->kind == MFT_SRC_HV_TOMINEC) {
@@ -1011,6 +1023,7 @@ static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bo
     a.n_slices = c->fwd.nslices;
     a.buf_bytes = warp_buf_bytes(c->fwd, c->stage_w);
     a.pf_dist = c->pf_dist;
+    a.dummy = (int)c->n_tot;
     a.u = c->u.p;
     a.du = c->du.p;
     a.g = c->g.p;
@@ -1038,7 +1051,7 @@ static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bo
 static int launch_pass_b(mft_ctx *c)
 {
     ScopedTimer t(c, MFT_K_PASS_B);
-    PassBArgs a{c->tra.view(), c->g.p, c->du.p, c->n_local, c->tra.nslices, warp_buf_bytes(c->tra, c->stage_w), c->pf_dist};
+    PassBArgs a{c->tra.view(), c->g.p, c->du.p, c->n_local, c->tra.nslices, warp_buf_bytes(c->tra, c->stage_w_b), c->pf_dist, (int)c->n_tot};
     const int grid = (int)((a.n_slices + 3) / 4);
     const int smem = 4 * a.buf_bytes;
 #define PB(EX, ST)                                                   \
@@ -1047,9 +1060,9 @@ static int launch_pass_b(mft_ctx *c)
         k_pass_b<4, EX, ST><<<grid, 128, smem, c->stream>>>(a);      \
     } while (0)
     if (c->exact) {
-        if (c->stage_w) PB(true, true); else PB(true, false);
+        if (c->stage_w_b) PB(true, true); else PB(true, false);
     } else {
-        if (c->stage_w) PB(false, true); else PB(false, false);
+        if (c->stage_w_b) PB(false, true); else PB(false, false);
     }
 #undef PB
     c->launches++;
@@ -1060,7 +1073,7 @@ static int launch_pass_b(mft_ctx *c)
 static int launch_spmv(mft_ctx *c, const Source *s)
 {
     ScopedTimer t(c, MFT_K_OTHER);
-    SpmvArgs a{s->hv.view(), c->u.p, c->du.p, c->n_local, s->hv.nslices, warp_buf_bytes(s->hv, c->stage_w), c->pf_dist, -s->gamma};
+    SpmvArgs a{s->hv.view(), c->u.p, c->du.p, c->n_local, s->hv.nslices, warp_buf_bytes(s->hv, c->stage_w), c->pf_dist, (int)c->n_tot, -s->gamma};
     const int grid = (int)((a.n_slices + 3) / 4);
     const int smem = 4 * a.buf_bytes;
     if (smem > 200 * 1024) return fail(MFT_ENOTSUP, "hyperviscosity operator rows too long (%d) for the shared-memory staging", s->hv.maxw);
@@ -1313,19 +1326,58 @@ static int launch_stage(mft_ctx *c, int stage, double dt)
     return MFT_OK;
 }
 
-extern "C" int mft_ssprk_step(mft_ctx *c, int scheme, double t, double dt)
+static int ssprk33_step_launches(mft_ctx *c, double t, double dt, bool first_rhs)
 {
-    NEED_CTX(c);
-    CHECK(mft_finalize(c));
-    if (scheme != MFT_SSPRK33) return fail(MFT_ENOTSUP, "mft_ssprk_step: only MFT_SSPRK33 is implemented");
-    if (!c->have_fsal) CHECK(rhs_device(c, t));  // k = f(u_n): first step only (FSAL afterwards)
+    if (first_rhs) CHECK(rhs_device(c, t));  // k = f(u_n): first step only (FSAL afterwards)
     CHECK(launch_stage(c, 1, dt));
     CHECK(rhs_device(c, t + dt));
     CHECK(launch_stage(c, 2, dt));
     CHECK(rhs_device(c, t + dt / 2));
     CHECK(launch_stage(c, 3, dt));
     CHECK(rhs_device(c, t + dt));
+    return MFT_OK;
+}
+
+extern "C" int mft_ssprk_step(mft_ctx *c, int scheme, double t, double dt)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    if (scheme != MFT_SSPRK33) return fail(MFT_ENOTSUP, "mft_ssprk_step: only MFT_SSPRK33 is implemented");
+    const bool first = !c->have_fsal;
     c->have_fsal = true;
+    // The step is a fixed sequence of ~35 launches: replay it as one CUDA graph (the kernel arguments that vary
+    // between steps -- dt and the success_iter==0 flag -- are part of the cache key; t only selects Dirichlet tables,
+    // which the caller refreshes).  Eager path: per-kernel timing on, multi-rank (NCCL calls), or first use of a key.
+    const bool graph_ok = c->use_graphs && !c->timing && c->nranks == 1;
+    if (!graph_ok) return ssprk33_step_launches(c, t, dt, first);
+    const int si_zero = c->success_iter == 0;
+    mft_ctx::StepGraph *g = nullptr;
+    for (auto &e : c->graphs)
+        if (e.dt == dt && e.si_zero == si_zero && e.with_first_rhs == (int)first) g = &e;
+    if (!g) {
+        c->graphs.push_back(mft_ctx::StepGraph{dt, si_zero, (int)first, 0, 0, nullptr});
+        g = &c->graphs.back();
+    }
+    g->uses++;
+    if (g->uses == 1) return ssprk33_step_launches(c, t, dt, first);  // warm (also sets per-kernel smem attributes)
+    if (!g->exec) {
+        const int64_t l0 = c->launches;
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = ssprk33_step_launches(c, t, dt, first);
+        const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        if (rc != MFT_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (ce != cudaSuccess) return fail(MFT_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+        g->nlaunch = c->launches - l0;
+        c->launches = l0;
+        CU(cudaGraphInstantiate(&g->exec, graph, 0));
+        CU(cudaGraphDestroy(graph));
+    }
+    CU(cudaGraphLaunch(g->exec, c->stream));
+    c->launches += g->nlaunch;
     return MFT_OK;  // asynchronous: mft_synchronize / downloads wait
 }
 

@@ -9,7 +9,8 @@
 //   g = eps .* (Dx u, Dy u)                        : AoS, one Vec<2V> per point (x-part then y-part)
 //   operators                                      : sliced ELL, slice = 32 consecutive device rows (one warp);
 //        entry (slice s, column c, lane l) lives at ((off[s] + c) * 32 + l) in idx[] / wx[] / wy[];
-//        padding entries point at the row itself with weight 0 (adds an exact 0, keeps the loops branch-free).
+//        padding entries point at a dummy record one past the last point (a finite state / zeros) with weight 0:
+//        they add an exact 0, keep the loops branch-free, and all padded lanes of a request hit ONE sector.
 //        Within a row the entries are stored in the reference's summation order.
 #pragma once
 #include <cuda_runtime.h>
@@ -232,6 +233,7 @@ struct PassAArgs {
     int64_t n_slices;
     int buf_bytes;  // shared-memory bytes per warp
     int pf_dist;    // L2 prefetch distance in slices
+    int dummy;      // index of the dummy record (one past the last point): padding / batch tails gather it
     const void *u;
     void *du;
     void *g;
@@ -252,7 +254,7 @@ constexpr int VISC_UPWIND = 1;
 constexpr int VISC_RESIDUAL = 2;
 
 template <int V, int EQ, bool EXACT, bool DO_FLUX, int VISC, bool STAGE_W>
-__global__ void __launch_bounds__(128) k_pass_a(const PassAArgs A)
+__global__ void __launch_bounds__(128, 4) k_pass_a(const PassAArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ uint64_t bars[4];
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(128) k_pass_a(const PassAArgs A)
             for (int b = 0; b < kBatch; ++b) {
                 const bool ok = c0 + b < width;
                 const int cc = ok ? c0 + b : width - 1;
-                const int j = ip[cc * kSlice];
+                const int j = ok ? ip[cc * kSlice] : A.dummy;
                 const double wv = wxp[cc * kSlice];
                 w[b] = ok ? wv : 0.0;
                 uj[b] = ld_ro(u + j);
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(128) k_pass_a(const PassAArgs A)
             for (int b = 0; b < kBatch; ++b) {
                 const bool ok = c0 + b < width;
                 const int cc = ok ? c0 + b : width - 1;
-                const int j = ip[cc * kSlice];
+                const int j = ok ? ip[cc * kSlice] : A.dummy;
                 const double wv = wyp[cc * kSlice];
                 w[b] = ok ? wv : 0.0;
                 uj[b] = ld_ro(u + j);
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(128) k_pass_a(const PassAArgs A)
             for (int b = 0; b < kBatch; ++b) {
                 const bool ok = c0 + b < width;
                 const int cc = ok ? c0 + b : width - 1;
-                const int j = ip[cc * kSlice];
+                const int j = ok ? ip[cc * kSlice] : A.dummy;
                 const double w1 = wxp[cc * kSlice], w2 = wyp[cc * kSlice];
                 wa[b] = ok ? w1 : 0.0;
                 wb[b] = ok ? w2 : 0.0;
@@ -461,10 +463,11 @@ struct PassBArgs {
     int64_t n_slices;
     int buf_bytes;
     int pf_dist;
+    int dummy;
 };
 
 template <int V, bool EXACT, bool STAGE_W>
-__global__ void __launch_bounds__(128) k_pass_b(const PassBArgs A)
+__global__ void __launch_bounds__(128, 4) k_pass_b(const PassBArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ uint64_t bars[4];
@@ -497,7 +500,7 @@ __global__ void __launch_bounds__(128) k_pass_b(const PassBArgs A)
         for (int b = 0; b < kBatch; ++b) {
             const bool ok = c0 + b < width;
             const int cc = ok ? c0 + b : width - 1;
-            const int j = ip[cc * kSlice];
+            const int j = ok ? ip[cc * kSlice] : A.dummy;
             const double w1 = wxp[cc * kSlice], w2 = wyp[cc * kSlice];
             wa[b] = ok ? w1 : 0.0;
             wb[b] = ok ? w2 : 0.0;
@@ -532,11 +535,12 @@ struct SpmvArgs {
     int64_t n_slices;
     int buf_bytes;
     int pf_dist;
+    int dummy;
     double alpha;
 };
 
 template <int V, bool EXACT, bool STAGE_W>
-__global__ void __launch_bounds__(128) k_spmv_accum(const SpmvArgs A)
+__global__ void __launch_bounds__(128, 4) k_spmv_accum(const SpmvArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ uint64_t bars[4];
@@ -565,7 +569,7 @@ __global__ void __launch_bounds__(128) k_spmv_accum(const SpmvArgs A)
         for (int b = 0; b < kBatch; ++b) {
             const bool ok = c0 + b < width;
             const int cc = ok ? c0 + b : width - 1;
-            const int j = ip[cc * kSlice];
+            const int j = ok ? ip[cc * kSlice] : A.dummy;
             const double wv = wp[cc * kSlice];
             w[b] = ok ? wv : 0.0;
             xj[b] = ld_ro(x + j);
