@@ -109,6 +109,24 @@ class PointCloudDomain:
         self.cloud = cl
 
 
+class ParallelPointCloudDomain(PointCloudDomain):
+    """One rank's part of the cloud: [owned points ; halo points] (layout of the reference's
+    ParallelPointCloudDomain, src/domains/PointCloudDomain/ParallelPointCloud.jl:85-162), but cut along a
+    space-filling curve and with full global stencils for the owned rows (see partition.py)."""
+
+    def __init__(self, solver, source, boundary_names, comm):
+        from . import partition
+
+        cl = cloudmod.read_medusa_file(source) if isinstance(source, str) else source
+        basis = solver.basis
+        part = partition.build_rank_partition(cl.points, cl.boundary_idxs, cl.boundary_normals, comm.rank, comm.nranks,
+                                              basis.approx_type.rbf_type.Nrbf, basis.N, basis.nv, comm.allgather)
+        self.partition, self.comm, self.cloud = part, comm, cl
+        self.pd = PointData(part.points, part.neighbors_owned, part.n_local + part.n_halo, basis.nv, part.dx_min, part.dx_avg)
+        self.boundary_tags = {name: BoundaryData(part.boundary_idxs[g - 1], part.boundary_normals[g - 1])
+                              for name, g in boundary_names.items()}
+
+
 # ---- equations (Trixi, third party) ------------------------------------------------------------------------------
 @dataclass
 class CompressibleEulerEquations2D:
@@ -275,11 +293,21 @@ class SemidiscretizationHyperbolic:
         pd = domain.pd
         self.n, self.V = pd.num_points, equations.nvars
         p, N = solver.basis.approx_type.rbf_type.Nrbf, solver.basis.N
-        ops = operators or setup_ops.compute_flux_operator(pd.points, pd.neighbors, p, N)
+        part = getattr(domain, "partition", None)
+        self.partition = part
+        if part is not None:
+            ops = part.ops
+            for src in self.source_terms.values():
+                if src.kind in (L.SRC_HV_FLYER, L.SRC_HV_TOMINEC):
+                    raise NotImplementedError("hyperviscosity sources are not partitioned yet (multi-GPU supports the "
+                                              "flux divergence and the upwind / residual viscosity sources)")
+        else:
+            ops = operators or setup_ops.compute_flux_operator(pd.points, pd.neighbors, p, N)
         self.cache = Cache(pd, ops)
         lib = L.load()
         ctx = C.c_void_p()
-        L.check(lib.mft_ctx_create(C.byref(ctx), eng.device, self.n, 0, self.V, 2, pd.num_neighbors))
+        n_local = part.n_local if part is not None else self.n
+        L.check(lib.mft_ctx_create(C.byref(ctx), eng.device, n_local, self.n - n_local, self.V, 2, pd.num_neighbors))
         self.ctx = ctx
         prm = np.asarray(equations.params(), dtype=np.float64)
         L.check(lib.mft_set_equation(ctx, equations.kind, L.ptr(prm), len(prm)))
@@ -289,7 +317,12 @@ class SemidiscretizationHyperbolic:
         L.check(lib.mft_set_option(ctx, L.OPT_MAX_LEXICOGRAPHIC, float(eng.max_lexicographic)))
         L.check(lib.mft_set_option(ctx, L.OPT_STAGE_WEIGHTS, float(eng.stage_weights)))
         L.check(lib.mft_set_option(ctx, L.OPT_REFINE_ORDER, float(eng.refine_order)))
-        if eng.reorder == "hilbert":
+        if part is not None:
+            # local numbering is already [owned along the curve ; halo]; sums must run in ascending GLOBAL column order
+            self.perm = None
+            keys = np.ascontiguousarray(part.local_gid, dtype=np.int64)
+            L.check(lib.mft_set_order_keys(ctx, L.ptr(keys)))
+        elif eng.reorder == "hilbert":
             self.perm = L.sfc_order(pd.points)
             perm1 = np.ascontiguousarray(self.perm + 1)
             L.check(lib.mft_set_permutation(ctx, L.ptr(perm1)))
@@ -322,6 +355,21 @@ class SemidiscretizationHyperbolic:
                 prm = np.asarray([src.c_rv, src.c_uw, src.dx_avg, float(src.polydeg)], dtype=np.float64)
                 L.check(lib.mft_add_source(ctx, src.kind, L.ptr(prm), 4, None, None, None))
         L.check(lib.mft_finalize(ctx))
+        if part is not None and part.nranks > 1:
+            comm = domain.comm
+            uid = C.create_string_buffer(128)
+            if comm.rank == 0:
+                L.check(lib.mft_nccl_unique_id(uid))
+            raw = comm.broadcast_bytes(bytes(uid.raw), src=0)
+            uid = C.create_string_buffer(raw, 128)
+            L.check(lib.mft_comm_init(ctx, comm.nranks, comm.rank, uid))
+            peers = (C.c_int * max(1, len(part.peers)))(*part.peers)
+            send_off = np.zeros(len(part.peers) + 1, dtype=np.int64)
+            for i, sidx in enumerate(part.send_idx):
+                send_off[i + 1] = send_off[i] + len(sidx)
+            send_idx1 = np.ascontiguousarray(np.concatenate(part.send_idx) + 1 if part.send_idx else np.zeros(0), dtype=np.int64)
+            recv = np.ascontiguousarray(part.recv_count, dtype=np.int64)
+            L.check(lib.mft_set_halo(ctx, len(part.peers), peers, L.ptr(send_off), L.ptr(send_idx1), L.ptr(recv)))
 
     def refresh_boundary_values(self, t):
         lib = L.load()

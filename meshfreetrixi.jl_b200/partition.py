@@ -1,0 +1,192 @@
+"""Space-filling-curve partition of a point cloud and the halo plan for multi-GPU `rhs!` (setup-time host code).
+
+Replaces the reference's rank-0 slab partitioner + MPI scatter (src/domains/PointCloudDomain/partition_domain.jl:81-178,
+277-318, scatter_pointcloud.jl) and its local layout [owned points ; halo points] (ParallelPointCloud.jl:144).
+
+Differences by design (SURVEY.md section 7 hard part 5, section 8e): the parity target is the SERIAL reference on the global cloud,
+so every owned row keeps its full global stencil (weights are computed from the global neighbourhood) and two halo
+sets are exchanged per `rhs!`: the state `u` before the forward pass and `g = eps .* D u` before the transposed
+pass.  One halo set H_r = F_r + R_r serves both:
+    F_r  columns of owned rows outside the rank            (needed for u)
+    R_r  foreign rows whose stencils contain owned points   (their g enters D' rows of owned points)
+Each rank builds only its own part: kNN / weights for its owned + halo rows, in parallel on all ranks.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+from scipy.spatial import cKDTree
+
+from . import _lib as L
+from . import setup_ops
+
+
+@dataclass
+class RankPartition:
+    rank: int
+    nranks: int
+    n_global: int
+    owned_gid: np.ndarray          # (n_local,) global point ids, in curve order
+    halo_gid: np.ndarray           # (n_halo,) grouped by owner rank
+    halo_owner: np.ndarray         # (n_halo,)
+    points: np.ndarray             # (n_local+n_halo, 2) local numbering [owned ; halo]
+    neighbors_owned: np.ndarray    # (n_local, k) GLOBAL ids (kNN of the owned points, distance-sorted, self first)
+    ops: list                      # [Dx, Dy] local scipy CSC (n_tot x n_tot), halo rows restricted to local columns
+    dx_min: float
+    dx_avg: float
+    peers: list = field(default_factory=list)
+    send_idx: list = field(default_factory=list)   # per peer: local owned indices (0-based) to send
+    recv_count: list = field(default_factory=list)
+    boundary_idxs: list = field(default_factory=list)    # per group: LOCAL owned indices
+    boundary_normals: list = field(default_factory=list)
+
+    @property
+    def n_local(self):
+        return len(self.owned_gid)
+
+    @property
+    def n_halo(self):
+        return len(self.halo_gid)
+
+    @property
+    def local_gid(self):
+        return np.concatenate([self.owned_gid, self.halo_gid])
+
+
+def curve_offsets(n: int, nranks: int) -> np.ndarray:
+    """contiguous equal ranges of curve positions"""
+    return np.array([(n * r) // nranks for r in range(nranks + 1)], dtype=np.int64)
+
+
+def build_rank_partition(points: np.ndarray, boundary_idxs, boundary_normals, rank: int, nranks: int, p: int, N: int,
+                         nv: int, allgather, perm_g: np.ndarray | None = None) -> RankPartition:
+    """`allgather(obj) -> list of obj from every rank` is the only communication primitive needed
+    (torch.distributed.all_gather_object in production, a trivial stub for nranks == 1)."""
+    n = points.shape[0]
+    if perm_g is None:
+        perm_g = L.sfc_order(points)
+    pos = np.empty(n, dtype=np.int64)
+    pos[perm_g] = np.arange(n, dtype=np.int64)
+    offs = curve_offsets(n, nranks)
+    owned = perm_g[offs[rank]:offs[rank + 1]]
+    is_owned = np.zeros(n, dtype=bool)
+    is_owned[owned] = True
+
+    # kNN against the cloud restricted to a padded bounding box of the partition (exact as long as the padding
+    # exceeds the stencil radius; the padding is 12 mean spacings)
+    lo, hi = points[owned].min(axis=0), points[owned].max(axis=0)
+    area = np.prod(np.maximum(points.max(axis=0) - points.min(axis=0), 1e-300))
+    h_est = np.sqrt(area / n)
+    pad = 12.0 * h_est * max(1.0, np.sqrt(nv / 20.0))
+    box = np.nonzero(np.all((points >= lo - pad) & (points <= hi + pad), axis=1))[0]
+    tree = cKDTree(points[box])
+
+    def knn(ids):
+        return setup_ops.knn_query(tree, points[ids], nv, index_map=box)
+
+    nb_owned, d_owned = knn(owned)
+    F = np.setdiff1d(np.unique(nb_owned), owned)
+    ring1_nb, _ = knn(F) if len(F) else (np.zeros((0, nv), dtype=np.int64), None)
+    ring2 = np.setdiff1d(np.setdiff1d(np.unique(ring1_nb), owned), F)
+    cand = np.concatenate([F, ring2])
+    if len(cand):
+        cand_nb = np.concatenate([ring1_nb, knn(ring2)[0]]) if len(ring2) else ring1_nb
+        touches = is_owned[cand_nb].any(axis=1)
+    else:
+        cand_nb = np.zeros((0, nv), dtype=np.int64)
+        touches = np.zeros(0, dtype=bool)
+    in_F = np.zeros(len(cand), dtype=bool)
+    in_F[:len(F)] = True
+    keep = in_F | touches
+    halo = cand[keep]
+    halo_nb = cand_nb[keep]
+    owner = np.searchsorted(offs, pos[halo], side="right") - 1
+    order = np.lexsort((pos[halo], owner))
+    halo, halo_nb, owner = halo[order], halo_nb[order], owner[order]
+
+    n_local, n_halo = len(owned), len(halo)
+    n_tot = n_local + n_halo
+    g2l = {}
+    local_gid = np.concatenate([owned, halo])
+    lut = np.full(n, -1, dtype=np.int64)
+    lut[local_gid] = np.arange(n_tot)
+
+    # weights: owned rows (full stencils) + halo rows (entries kept only where the column is local)
+    rows_nb = np.concatenate([nb_owned, halo_nb]) if n_halo else nb_owned
+    wx, wy = setup_ops.rbf_fd_weights(points, rows_nb, p, N)
+    col_local = lut[rows_nb]
+    valid = col_local >= 0
+    assert valid[:n_local].all(), "an owned row references a point outside owned+halo"
+    r_idx = np.repeat(np.arange(n_tot, dtype=np.int64), nv).reshape(n_tot, nv)
+    ops = []
+    for w in (wx, wy):
+        A = sp.coo_matrix((w[valid], (r_idx[valid], col_local[valid])), shape=(n_tot, n_tot)).tocsc()
+        A.sort_indices()
+        ops.append(A)
+
+    # global spacing constants (PointData: dx_min / dx_avg over ALL points, geometry_primatives.jl:333-334)
+    stats = allgather((float(d_owned[:, 1].sum()), float(d_owned[:, 1].min()), n_local))
+    dx_avg = sum(s[0] for s in stats) / sum(s[2] for s in stats)
+    dx_min = min(s[1] for s in stats)
+
+    # halo plan: everyone publishes what it needs from whom
+    needs = {int(q): halo[owner == q] for q in np.unique(owner)}
+    all_needs = allgather(needs)
+    peers = sorted(set(needs.keys()) | {q for q in range(nranks) if rank in all_needs[q]})
+    send_idx, recv_count = [], []
+    for q in peers:
+        want = all_needs[q].get(rank, np.zeros(0, dtype=np.int64))   # global ids q wants from me, in q's halo order
+        li = lut[want]
+        assert (li >= 0).all() and (li < n_local).all()
+        send_idx.append(li.astype(np.int64))
+        recv_count.append(int((owner == q).sum()))
+
+    bidx, bnrm = [], []
+    for gi, gn in zip(boundary_idxs, boundary_normals):
+        sel = is_owned[gi]
+        bidx.append(lut[gi[sel]].astype(np.int64))
+        bnrm.append(np.asarray(gn)[sel])
+
+    return RankPartition(rank, nranks, n, owned, halo, owner, np.ascontiguousarray(points[local_gid]), nb_owned, ops,
+                         dx_min, dx_avg, peers, send_idx, recv_count, bidx, bnrm)
+
+
+# ---- communicators used at setup time (and to bootstrap NCCL) ------------------------------------------------------
+class LocalComm:
+    """single rank"""
+    rank, nranks = 0, 1
+
+    def allgather(self, obj):
+        return [obj]
+
+    def broadcast_bytes(self, b, src=0):
+        return b
+
+    def barrier(self):
+        pass
+
+
+class TorchComm:
+    """torch.distributed process group (nccl on GPUs, gloo in the CPU tests): setup-time plumbing only; the halo
+    exchange of the hot path is done by the library itself with NCCL send/recv on its own stream."""
+
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.rank, self.nranks = dist.get_rank(), dist.get_world_size()
+
+    def allgather(self, obj):
+        out = [None] * self.nranks
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def broadcast_bytes(self, b, src=0):
+        box = [b]
+        self.dist.broadcast_object_list(box, src=src)
+        return box[0]
+
+    def barrier(self):
+        self.dist.barrier()

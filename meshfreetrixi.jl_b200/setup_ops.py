@@ -28,8 +28,33 @@ def knn(points: np.ndarray, nv: int, workers: int = -1):
     """Exact kNN sorted by distance, self first (NearestNeighbors.knn(tree, pts, nv, true)).
     Returns neighbors (N,nv) int64 0-based, dx_min, dx_avg (from the nearest-neighbour distance)."""
     tree = cKDTree(points)
-    d, idx = tree.query(points, k=nv, workers=workers)
-    return idx.astype(np.int64), float(d[:, 1].min()), float(d[:, 1].mean())
+    idx, d = knn_query(tree, points, nv, workers=workers)
+    return idx, float(d[:, 1].min()), float(d[:, 1].mean())
+
+
+TIE_MARGIN = 4
+
+
+def knn_query(tree, queries, nv, workers=-1, index_map=None):
+    """nv nearest neighbours with exact distance ties resolved by ascending point index -- also ties that straddle
+    the k-th place (a few extra candidates are fetched, ordered canonically, then cut to nv)."""
+    kq = min(nv + TIE_MARGIN, tree.n)
+    d, idx = tree.query(queries, k=kq, workers=workers)
+    idx = idx.astype(np.int64)
+    if index_map is not None:
+        idx = index_map[idx]
+    idx, d = canonical_ties(idx, d)
+    return np.ascontiguousarray(idx[:, :nv]), np.ascontiguousarray(d[:, :nv])
+
+
+def canonical_ties(idx: np.ndarray, d: np.ndarray):
+    """Order equidistant neighbours by ascending point index.  NearestNeighbors.jl leaves the order of exact distance
+    ties implementation-defined; fixing it makes the neighbour tables -- and therefore the
+    operator weights -- independent of which tree / which rank produced them."""
+    o = np.argsort(idx, axis=1, kind="stable")
+    idx, d = np.take_along_axis(idx, o, 1), np.take_along_axis(d, o, 1)
+    o = np.argsort(d, axis=1, kind="stable")
+    return np.take_along_axis(idx, o, 1), np.take_along_axis(d, o, 1)
 
 
 def monomial_exponents(N: int):

@@ -83,9 +83,16 @@ def point_data(points: np.ndarray, nv: int):
     """PointData ctor, geometry_primatives.jl:322-339: knn(tree, pts, nv, sorted=true) + dx_min/dx_avg
     from the 2-NN distances.  Returns neighbors (N,nv) int64 0-based (self first), dx_min, dx_avg."""
     tree = cKDTree(points)
-    _, idx = tree.query(points, k=nv)
+    d, idx = tree.query(points, k=min(nv + 4, len(points)))
+    # exact distance ties: NearestNeighbors.jl's order is implementation-defined (SURVEY appendix B.6); canonicalise by
+    # ascending index (index sort, then a stable distance sort; 4 extra candidates cover ties across the k-th place)
+    idx = idx.astype(np.int64)
+    o = np.argsort(idx, axis=1, kind="stable")
+    idx, d = np.take_along_axis(idx, o, 1), np.take_along_axis(d, o, 1)
+    o = np.argsort(d, axis=1, kind="stable")
+    idx = np.ascontiguousarray(np.take_along_axis(idx, o, 1)[:, :nv])
     d2, _ = tree.query(points, k=2)
-    return idx.astype(np.int64), float(d2[:, 1].min()), float(d2[:, 1].mean())
+    return idx, float(d2[:, 1].min()), float(d2[:, 1].mean())
 
 
 def _monomial_exponents(N: int):

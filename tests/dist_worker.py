@@ -1,0 +1,172 @@
+"""Worker launched by torch.distributed.run from tests/test_multi_rank.py.
+
+--mode cpu : gloo, no GPU.  Builds the rank's partition with the production planner (partition.py) and runs the
+             multi-rank rhs! ALGORITHM (halo exchange of u, forward pass on owned rows, halo exchange of g,
+             transposed pass) in numpy/scipy on the local operators; compares the owned rows with the serial oracle on the
+             global cloud.  This pins the partition / halo plan / algorithm that the CUDA path implements.
+--mode gpu : nccl, one GPU per rank.  Runs the real library (NCCL halo exchange inside libmft_b200.so) and compares rhs!
+             and a few SSPRK33 steps with the serial oracle.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GAMMA = 1.4
+
+
+def euler_flux(u):
+    rho, m1, m2, E = u
+    v1, v2 = m1 / rho, m2 / rho
+    p = (GAMMA - 1) * (E - 0.5 * (m1 * v1 + m2 * v2))
+    return np.stack([m1, m1 * v1 + p, m1 * v2, (E + p) * v1]), np.stack([m2, m2 * v1, m2 * v2 + p, (E + p) * v2]), (v1, v2, p)
+
+
+def exchange(dist, part, field):
+    """field: (W, n_tot); fills the halo tail from the owners (the plan of partition.py, object collectives on gloo)"""
+    n_local = part.n_local
+    out = {int(q): np.ascontiguousarray(field[:, idx]) for q, idx in zip(part.peers, part.send_idx)}
+    boxes = [None] * part.nranks
+    dist.all_gather_object(boxes, out)
+    off = n_local
+    for q, cnt in zip(part.peers, part.recv_count):
+        if cnt:
+            field[:, off:off + cnt] = boxes[q][part.rank]
+        off += cnt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="cpu")
+    ap.add_argument("--out", default="")
+    ap.add_argument("--source", default="upwind")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+
+    import mft_b200 as m
+    import mft_oracle as orc
+    from mft_b200 import partition
+
+    rank = int(os.environ["RANK"])
+    if args.mode == "gpu":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group("nccl")
+    else:
+        dist.init_process_group("gloo")
+    comm = partition.TorchComm()
+
+    cl = m.cloud.jittered_lattice(72, 60, 10.0, 10.0 * 60 / 72, seed=4)
+    names = dict(left=1, right=2, bottom=3, top=4)
+    ic = lambda x, t, e=None: m.cloud.isentropic_vortex(x, GAMMA, center=(5.0, 4.0))
+    basis = m.PointCloudBasis(m.Point2D(), 3, approximation_type=m.RBF(m.PolyharmonicSpline(3)))
+
+    # ---- serial oracle on the global cloud (every rank computes it; it is small) -------------------------------
+    nb, dx_min, dx_avg = orc.point_data(cl.points, basis.nv)
+    ops = m.setup_ops.compute_flux_operator(cl.points, nb, 3, 3)
+    obc = [orc.OracleBC(orc.BC_DIRICHLET, cl.boundary_idxs[g], cl.boundary_normals[g], value_fn=lambda x, t: ic(x, t))
+           for g in range(4)]
+    src_o = orc.source_upwind(dx_avg) if args.source == "upwind" else orc.source_residual(dx_avg, polydeg=3)
+    P = orc.OracleProblem(cl.points, 4, orc.EQ_EULER2D, [GAMMA], ops[0], ops[1], obc, [src_o])
+    u0 = ic(cl.points, 0.0) * (1.0 + 0.01 * np.sin(cl.points[:, 0]))
+    u_ser = u0.copy()
+    du_ser = P.rhs(u_ser, 0.0)
+
+    results = {}
+    if args.mode == "cpu":
+        part = partition.build_rank_partition(cl.points, cl.boundary_idxs, cl.boundary_normals, comm.rank, comm.nranks,
+                                              3, 3, basis.nv, comm.allgather)
+        gid = part.local_gid
+        nl = part.n_local
+        # the local operator rows of owned points are the global rows, bit for bit
+        Dxg = ops[0].tocsr()
+        Dxl = part.ops[0].tocsr()
+        for i in range(0, nl, 37):
+            gl, ll = Dxg[gid[i]], Dxl[i]
+            assert np.array_equal(np.sort(gid[ll.indices]), np.sort(gl.indices))
+            o1, o2 = np.argsort(gid[ll.indices]), np.argsort(gl.indices)
+            assert np.array_equal(ll.data[o1], gl.data[o2])
+        assert abs(part.dx_avg - dx_avg) < 1e-15 and part.dx_min == dx_min
+        # ownership is a partition of the cloud
+        owned_all = comm.allgather(part.owned_gid)
+        allg = np.concatenate(owned_all)
+        assert len(allg) == len(cl.points) and len(np.unique(allg)) == len(allg)
+        # ---- the multi-rank algorithm on the local data ------------------------------------------------------------
+        u = np.ascontiguousarray(u0[:, gid])
+        u[:, nl:] = np.nan                                  # halo values must come from the exchange
+        for g in range(4):                                  # BC pass 1 on owned boundary points
+            bi = part.boundary_idxs[g]
+            u[:, bi] = ic(part.points[bi], 0.0)
+        exchange(dist, part, u)
+        assert np.array_equal(u, u_ser[:, gid])             # halo copies carry the owner's BC-imposed values
+        F, G, (v1, v2, p) = euler_flux(u)
+        Dx, Dy = part.ops[0].tocsr(), part.ops[1].tocsr()
+        du = np.stack([-(Dx[:nl] @ F[v]) - (Dy[:nl] @ G[v]) for v in range(4)])
+        eps = 0.5 * part.dx_avg * (np.hypot(v1, v2) + np.sqrt(GAMMA * p / u[0]))[:nl]
+        g8 = np.zeros((8, len(gid)))
+        for v in range(4):
+            g8[v, :nl] = eps * (Dx[:nl] @ u[v])
+            g8[4 + v, :nl] = eps * (Dy[:nl] @ u[v])
+        g8[:, nl:] = np.nan
+        exchange(dist, part, g8)
+        for v in range(4):
+            du[v] -= (Dx.T @ g8[v])[:nl] + (Dy.T @ g8[4 + v])[:nl]
+        for g in range(4):
+            du[:, part.boundary_idxs[g]] = 0.0
+        ref = du_ser[:, part.owned_gid]
+        err = max(np.abs(du[v] - ref[v]).max() / np.abs(du_ser[v]).max() for v in range(4))
+        results = dict(rank=rank, n_local=nl, n_halo=part.n_halo, err=float(err))
+        assert args.source == "upwind"
+        assert err < 1e-12, err
+    else:
+        solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=int(os.environ.get("LOCAL_RANK", rank)),
+                                                                    diagnostics=True))
+        domain = m.ParallelPointCloudDomain(solver, cl, names, comm)
+        part = domain.partition
+        eq = m.CompressibleEulerEquations2D(GAMMA)
+        bc = {k: m.BoundaryConditionDirichlet(ic) for k in names}
+        if args.source == "upwind":
+            srcs = m.SourceTerms(rv=m.SourceUpwindViscosityTominec(solver, eq, domain))
+        else:
+            srcs = m.SourceTerms(rv=m.SourceResidualViscosityTominec(solver, eq, domain, polydeg=3))
+        semi = m.SemidiscretizationHyperbolic(domain, eq, ic, solver, boundary_conditions=bc, source_terms=srcs)
+        gid = part.local_gid
+        nl = part.n_local
+        u = np.ascontiguousarray(u0[:, gid])
+        u[:, nl:] = 0.0
+        du = np.zeros_like(u)
+        m.rhs_(du, u, semi, 0.0)
+        ref = du_ser[:, part.owned_gid]
+        err = max(np.abs(du[v, :nl] - ref[v]).max() / np.abs(du_ser[v]).max() for v in range(4))
+        assert np.array_equal(u[:, :nl], u_ser[:, part.owned_gid])
+        assert np.array_equal(u[:, nl:], u_ser[:, part.halo_gid]), "halo state after rhs! must be the owners' values"
+        assert (du[:, nl:] == 0).all()                       # reset_halos! parallel_rbfsolver.jl:74-91
+        # time integration: 10 SSPRK33 steps with the history callback, against the serial oracle
+        dt = 0.1 * dx_min / 8.0
+        u_ref, _ = P.solve_ssprk33(u0, 0.0, dt, 10, approx_order=3)
+        ode = m.ODEProblem(np.ascontiguousarray(u0[:, gid]), (0.0, 10 * dt), semi)
+        sol = m.solve(ode, m.SSPRK33(), dt=dt, callback=m.HistoryCallback(3), nsteps=10)
+        err2 = max(np.abs(sol.u[v, :nl] - u_ref[v, part.owned_gid]).max() / np.abs(u_ref[v]).max() for v in range(4))
+        results = dict(rank=rank, n_local=nl, n_halo=part.n_halo, err=float(err), err_steps=float(err2))
+        assert err < 1e-12, err
+        assert err2 < 1e-9, err2
+        semi.close()
+    allres = comm.allgather(results)
+    if rank == 0:
+        print("MULTI_RANK_OK", allres)
+        if args.out:
+            import json
+
+            json.dump(allres, open(args.out, "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

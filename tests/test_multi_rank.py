@@ -1,0 +1,61 @@
+"""N>1 path.  CPU: world_size-2 gloo run of the production partition planner + the multi-rank rhs! algorithm
+(tests/dist_worker.py --mode cpu).  GPU (needs >= 2 devices): the real library with NCCL halo exchange against the
+serial oracle."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+import cases
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _launch(nproc, mode, source, tmp_path, timeout=600):
+    out = os.path.join(tmp_path, f"res_{mode}_{source}.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(cases.ROOT, "tests", "dist_worker.py"), "--mode", mode, "--source", source, "--out", out]
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "MULTI_RANK_OK" in res.stdout
+    return json.load(open(out))
+
+
+def test_partition_and_algorithm_world2_gloo(tmp_path):
+    res = _launch(2, "cpu", "upwind", str(tmp_path))
+    assert len(res) == 2 and sum(r["n_local"] for r in res) == 72 * 60 + 2 * (72 + 60)
+    assert all(r["n_halo"] > 0 and r["err"] < 1e-12 for r in res)
+
+
+def test_partition_world3_gloo(tmp_path):
+    res = _launch(3, "cpu", "upwind", str(tmp_path))
+    assert len(res) == 3 and all(r["err"] < 1e-12 for r in res)
+
+
+def _ngpu():
+    try:
+        import mft_b200
+
+        return mft_b200._lib.load().mft_device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("source", ["upwind", "residual"])
+def test_two_gpus_match_serial_oracle(tmp_path, source):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    res = _launch(2, "gpu", source, str(tmp_path))
+    assert all(r["err"] < 1e-12 and r["err_steps"] < 1e-9 for r in res)
