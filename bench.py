@@ -104,39 +104,63 @@ def vortex_ic(m, center):
     return lambda x, t, eq=None: m.cloud.isentropic_vortex(x, GAMMA, center=center)
 
 
+GRID_FOR_GPUS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}   # lattice multiples: fixed points per GPU (weak scaling)
+
+
 def run_ours(args):
     import mft_b200 as m
 
     lib = m.load()
+    L = m._lib
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
-    if world > 1:
-        return run_ours_multi(args, m, rank, world, local_rank)
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    multi = world > 1
+    dist = None
+    if multi:
+        import torch
+        import torch.distributed as dist
 
-    nx = ny = args.n_side
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+        from mft_b200 import partition
+        comm = partition.TorchComm()
+    gx, gy = GRID_FOR_GPUS.get(world, (world, 1))
+    nx, ny = args.n_side * gx, args.n_side * gy
     cl, basis, _ = build_workload(nx, ny, 0, m)
-    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=0, exact_order=not args.fma,
-                                                                stage_weights=int(args.stage_weights)))
+    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=local_rank, exact_order=not args.fma,
+                                                                stage_weights=int(args.stage_weights),
+                                                                cuda_graph=int(args.graph)))
     names = dict(left=1, right=2, bottom=3, top=4)
     t_setup = time.time()
-    domain = m.PointCloudDomain(solver, cl, names)
+    domain = m.ParallelPointCloudDomain(solver, cl, names, comm) if multi else m.PointCloudDomain(solver, cl, names)
     eq = m.CompressibleEulerEquations2D(GAMMA)
     ic = vortex_ic(m, (5.0, 5.0 * ny / nx))
     bc = {k: m.BoundaryConditionDirichlet(ic) for k in names}
     srcs = m.SourceTerms(rv=m.SourceResidualViscosityTominec(solver, eq, domain, c_rv=1.0, c_uw=1.0, polydeg=3))
     semi = m.SemidiscretizationHyperbolic(domain, eq, ic, solver, boundary_conditions=bc, source_terms=srcs)
     t_setup = time.time() - t_setup
-    N = semi.n
+    N = cl.points.shape[0]                                    # global points
+    n_own = domain.partition.n_local if multi else N          # rows this rank computes
     pd = domain.pd
     dt = 0.1 * pd.dx_min / 8.0   # CFL 0.1*dx_min/(|v|+c), |v|+c ~ 7.4 for the vortex base state
     ode = m.semidiscretize(semi, (0.0, 1.0))
     u0 = ode.u0
     ctx = semi.ctx
-    L = m._lib
+
+    def barrier():
+        if multi:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if not multi:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def steps(n, t, it0):
         for i in range(n):
@@ -145,28 +169,31 @@ def run_ours(args):
             L.check(lib.mft_history_push(ctx, t, it0 + i + 1, 3))
         return t
 
-    # ---- device-resident timed region -----------------------------------------------------------------
+    # ---- device-resident timed region: barrier + sync on both sides, CUDA events on the ctx stream, max over ranks ----
     L.check(lib.mft_upload_state(ctx, L.soa_ptrs(u0)))
     L.check(lib.mft_history_push(ctx, 0.0, 0, 3))
     t = steps(args.warmup, 0.0, 0)
     L.check(lib.mft_synchronize(ctx))
-    sampler = ClockSampler(0)
-    sampler.start()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     launches0 = lib.mft_launch_count(ctx)
     L.check(lib.mft_timer_start(ctx))
     t = steps(args.steps, t, args.warmup)
     ms = C.c_double()
     L.check(lib.mft_timer_stop(ctx, C.byref(ms)))
+    barrier()
     launches = lib.mft_launch_count(ctx) - launches0
-    clocks = sampler.stop()
-    total_ms = ms.value
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = max_over_ranks(ms.value)
     ms_per_step = total_ms / args.steps
     value = N * STAGES * args.steps / (total_ms * 1e-3)
 
     # sanity: the state is still finite after the timed steps
     u_end = np.empty_like(u0)
     L.check(lib.mft_download_state(ctx, L.soa_ptrs(u_end)))
-    if not np.isfinite(u_end).all():
+    if not np.isfinite(u_end[:, :n_own]).all():
         raise SystemExit("bench: non-finite state after the timed region")
 
     # ---- per-kernel CUDA-event pass (same steps, events around every launch on the ctx stream) -----------
@@ -181,55 +208,65 @@ def run_ours(args):
     L.check(lib.mft_set_kernel_timing(ctx, 0))
     peak, peak_src = measured_peak()
     V, k = 4, K_STENCIL
-    bytes_a = N * (20 * k + 8 * V + 8 * V + 8 * V + 16 * V)      # idx+wx+wy, u gather, approx_du, du, g
-    bytes_b = N * (20 * k + 16 * V + 16 * V)                     # idxT+wxT+wyT, g gather, du read+write
+    bytes_a = n_own * (20 * k + 8 * V + 8 * V + 8 * V + 16 * V)  # idx+wx+wy, u gather, approx_du, du, g
+    bytes_b = n_own * (20 * k + 16 * V + 16 * V)                 # idxT+wxT+wyT, g gather, du read+write
     a_ms, a_n = ktime["pass_a"]
     b_ms, b_n = ktime["pass_b"]
     dom, dom_bytes, dom_ms, dom_n = ("k_pass_a", bytes_a, a_ms, a_n) if a_ms >= b_ms else ("k_pass_b", bytes_b, b_ms, b_n)
     achieved = dom_bytes / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9
     step_bytes = N * STAGES * (40 * k + 288 + 128)
+    agg_peak = peak * world
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes,
                 "avg_launch_ms": round(dom_ms / max(dom_n, 1), 4),
                 "whole_step": {"algorithmic_GBps": round(step_bytes / (ms_per_step * 1e-3) / 1e9, 1),
-                               "frac": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                               "frac_of_n_gpu_peak": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / agg_peak, 4),
                                "bytes_per_point_stage": 40 * k + 288 + 128},
-                "kernel_ms_per_step": {kk: round(v[0] / args.steps, 4) for kk, v in ktime.items()}}
+                "kernel_ms_per_step": {kk: round(v[0] / args.steps, 4) for kk, v in ktime.items()},
+                "note": "per-kernel times: rank 0, CUDA events around every launch (eager replay of the same steps)"}
 
     # ---- end-to-end through the reference-facing call: mft_rhs with HOST buffers (pinned) -------------------
-    u_h = L.pinned_empty((4, N))
-    du_h = L.pinned_empty((4, N))
+    n_arr = u0.shape[1]
+    u_h = L.pinned_empty((4, n_arr))
+    du_h = L.pinned_empty((4, n_arr))
     u_h[:] = u_end
     up, dup = L.soa_ptrs(u_h), L.soa_ptrs(du_h)
     for _ in range(3):
         L.check(lib.mft_rhs(ctx, t, up, dup, L.MEM_HOST))
     e2e_calls = max(3, min(3 * args.steps, 30))
+    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_calls):
         L.check(lib.mft_rhs(ctx, t, up, dup, L.MEM_HOST))
-    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = N * e2e_calls / e2e_s
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": STAGES * 32 * N, "d2h_bytes_per_step": STAGES * 64 * N,
            "call": "mft_rhs(MFT_MEM_HOST): u H2D, rhs!, u and du D2H, pinned host arrays", "calls_timed": e2e_calls}
 
-    # ---- CPU baseline: the oracle's C port of the reference structure, bounded sample, rank 0, 1 thread -----------
+    # ---- CPU baseline: the oracle's C port of the reference structure, bounded sample, rank 0, N=1 only -----------
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not multi:
         cpu = cpu_baseline(semi, domain, u_end, m, budget_s=args.cpu_seconds)
 
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic",
-           "config": {"workload": f"BASELINE configs[1]: 2D Euler isentropic vortex + residual viscosity, {N}-point "
-                                  f"jittered cloud ({nx}x{ny} + ring), PHS3 deg3 k=20, SSPRK33 + HistoryCallback(3)",
-                      "points": N, "k": k, "stages_per_step": STAGES,
-                      "summation": "fma single-sweep" if args.fma else "reference order (bit-exact sums)",
-                      "l2": "inputs larger than L2 (operators 2 x %.0f MB streamed every stage)" % (N * 20 * k / 1e6),
-                      "setup_s": round(t_setup, 1)},
-           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(out))
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": f"BASELINE configs[1]: 2D Euler isentropic vortex + residual viscosity, {N}-point "
+                                      f"jittered cloud ({nx}x{ny} + ring), PHS3 deg3 k=20, SSPRK33 + HistoryCallback(3)",
+                          "points": N, "points_per_gpu": N // world, "k": k, "stages_per_step": STAGES,
+                          "summation": "fma single-sweep" if args.fma else "reference order (bit-exact sums)",
+                          "partition": "single GPU" if not multi else f"Hilbert-curve ranges over {world} ranks, NCCL halo exchange (u, g) + all-gather norms per stage",
+                          "l2": "inputs larger than L2 (operators 2 x %.0f MB per GPU streamed every stage)" % (n_own * 20 * k / 1e6),
+                          "setup_s": round(t_setup, 1)},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(out))
     semi.close()
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # DRAM bytes per launch from the committed ncu --set full capture (profiles/); None until captured
@@ -327,10 +364,6 @@ def run_reference(args):
     print(json.dumps(out))
 
 
-def run_ours_multi(args, m, rank, world, local_rank):
-    raise SystemExit("multi-GPU bench not wired yet")
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -341,6 +374,7 @@ def main():
     ap.add_argument("--ref-n-side", type=int, default=512, help="lattice side of the bounded sample the CPU arm runs")
     ap.add_argument("--fma", action="store_true", help="single-sweep FMA summation instead of the reference order")
     ap.add_argument("--stage-weights", type=int, default=1, help="1: whole operator slices staged in smem; 0: indices only")
+    ap.add_argument("--graph", type=int, default=1, help="0 eager, 1 CUDA-graph replay on one GPU, 2 also multi-rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--cloud-order", default="hilbert", choices=["hilbert", "lattice"],

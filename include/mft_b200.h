@@ -67,7 +67,8 @@ typedef struct mft_ctx mft_ctx;
 #define MFT_OPT_MEAN_DIVISOR_VN 1  /* 1 (default): ode_mean divides by V*N (recursive_length, src/auxiliary/mpi.jl:42) */
 #define MFT_OPT_MAX_LEXICOGRAPHIC 2/* 1 (default): maximum(::StructArray{SVector}) = lexicographic max (mpi.jl:71-81) */
 #define MFT_OPT_DIAGNOSTICS 3      /* 1: keep eps_uw/eps_rv/eps/eps_c/residual for mft_get_field (default 0)     */
-#define MFT_OPT_CUDA_GRAPH 4       /* reserved                                                                         */
+#define MFT_OPT_CUDA_GRAPH 4       /* 1 (default): mft_ssprk_step replays a captured CUDA graph on one GPU; 2: also multi-rank
+                                      (NCCL calls captured into the graph); 0: always eager launches                      */
 #define MFT_OPT_STAGE_WEIGHTS 5    /* bit 0 (forward operator, pass A) / bit 1 (transposed operator, pass B): 1 = a warp bulk-copies
                                       its whole operator slice (indices + weights) into shared memory, 0 = indices only, weights
                                       by coalesced loads + L2 bulk prefetch.  Default 1 (measured best: pass A staged, pass B not) */

@@ -65,6 +65,7 @@ class RBFFDEngineCUDA:
     mean_divisor_vn: bool = True       # ode_mean divides by V*N (recursive_length)
     max_lexicographic: bool = True     # maximum(::StructArray{SVector}) is a lexicographic max
     stage_weights: int = 1             # bit0: pass A, bit1: pass B -- bulk-copy whole operator slices to smem
+    cuda_graph: int = 1                # 1: graph replay of SSPRK steps on one GPU; 2: also multi-rank; 0: eager
     refine_order: bool = False         # order rows inside 256-row blocks by D' row length (less padding, worse gather locality)
 
 
@@ -317,6 +318,7 @@ class SemidiscretizationHyperbolic:
         L.check(lib.mft_set_option(ctx, L.OPT_MAX_LEXICOGRAPHIC, float(eng.max_lexicographic)))
         L.check(lib.mft_set_option(ctx, L.OPT_STAGE_WEIGHTS, float(eng.stage_weights)))
         L.check(lib.mft_set_option(ctx, L.OPT_REFINE_ORDER, float(eng.refine_order)))
+        L.check(lib.mft_set_option(ctx, L.OPT_CUDA_GRAPH, float(eng.cuda_graph)))
         if part is not None:
             # local numbering is already [owned along the curve ; halo]; sums must run in ascending GLOBAL column order
             self.perm = None

@@ -367,7 +367,7 @@ extern "C" int mft_set_option(mft_ctx *c, int option, double value)
     case MFT_OPT_MEAN_DIVISOR_VN: c->mean_div_vn = value != 0; break;
     case MFT_OPT_MAX_LEXICOGRAPHIC: c->max_lex = value != 0; break;
     case MFT_OPT_DIAGNOSTICS: c->diagnostics = value != 0; break;
-    case MFT_OPT_CUDA_GRAPH: c->use_graphs = value != 0; break;
+    case MFT_OPT_CUDA_GRAPH: c->use_graphs = (int)value; break;
     case MFT_OPT_STAGE_WEIGHTS: c->stage_w = ((int)value & 1) != 0; c->stage_w_b = ((int)value & 2) != 0; break;
     case MFT_OPT_PREFETCH_DISTANCE: c->pf_dist = (int)value; break;
     case MFT_OPT_REFINE_ORDER: c->refine_order = value != 0; break;
@@ -1029,6 +1029,14 @@ static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bo
     a.g = c->g.p;
     a.approx_du = c->approx_du.p;
     a.norms = c->stats.p + 2 * c->V;
+    a.norm_parts = 0;
+    a.norm_lex = c->max_lex;
+    a.norms_out = nullptr;
+    if (c->nranks > 1 && visc == VISC_RESIDUAL) {
+        a.norms = c->gather_buf.p + (int64_t)c->nranks * c->V;
+        a.norm_parts = c->nranks;
+        a.norms_out = c->stats.p + 2 * c->V;
+    }
     a.n_rows = c->n_local;
     a.eqp0 = c->eqp[0];
     a.eqp1 = c->eqp[1];
@@ -1106,8 +1114,10 @@ static int launch_norms(mft_ctx *c)
     double *sum = c->stats.p, *mean = c->stats.p + V, *norms = c->stats.p + 2 * V;
     const double divisor = c->mean_div_vn ? (double)V * (double)n : (double)n;
     k_sum_mean<4><<<c->red_blocks, 256, 0, c->stream>>>(u, n, c->partial.p, c->ticket.p, divisor, sum);
-    if (c->max_lex) k_maxdev_norms<4, true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, mean, c->partial.p, c->ticket.p + 1, norms);
-    else k_maxdev_norms<4, false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, mean, c->partial.p, c->ticket.p + 1, norms);
+    if (c->max_lex)
+        k_maxdev_norms<4, true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, sum, 1, divisor, c->partial.p, c->ticket.p + 1, norms, 1, mean);
+    else
+        k_maxdev_norms<4, false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, sum, 1, divisor, c->partial.p, c->ticket.p + 1, norms, 1, mean);
     c->launches += 2;
     LAUNCH_CHECK();
     return MFT_OK;
@@ -1348,7 +1358,7 @@ extern "C" int mft_ssprk_step(mft_ctx *c, int scheme, double t, double dt)
     // The step is a fixed sequence of ~35 launches: replay it as one CUDA graph (the kernel arguments that vary
     // between steps -- dt and the success_iter==0 flag -- are part of the cache key; t only selects Dirichlet tables,
     // which the caller refreshes).  Eager path: per-kernel timing on, multi-rank (NCCL calls), or first use of a key.
-    const bool graph_ok = c->use_graphs && !c->timing && c->nranks == 1;
+    const bool graph_ok = c->use_graphs && !c->timing && (c->nranks == 1 || c->use_graphs >= 2);
     if (!graph_ok) return ssprk33_step_launches(c, t, dt, first);
     const int si_zero = c->success_iter == 0;
     mft_ctx::StepGraph *g = nullptr;
@@ -1570,7 +1580,7 @@ extern "C" int mft_comm_init(mft_ctx *c, int nranks, int rank, const void *id128
     if (N->commInitRank(&c->comm, nranks, id128, rank) != 0) return fail(MFT_ENCCL, "ncclCommInitRank failed");
     c->nranks = nranks;
     c->rank = rank;
-    CHECK(c->gather_buf.alloc((int64_t)nranks * c->V + 2 * c->V));
+    CHECK(c->gather_buf.alloc((int64_t)2 * nranks * c->V + 4 * c->V));
     // global point count (ndofs of the parallel domain, parallel_rbfsolver.jl:10-13) = sum of the owned counts
     double nl = (double)c->n_local, ng = 0.0;
     CU(cudaMemcpy(c->gather_buf.p, &nl, sizeof(double), cudaMemcpyHostToDevice));
@@ -1604,8 +1614,10 @@ extern "C" int mft_set_halo(mft_ctx *c, int npeers, const int *peers, const int6
     return MFT_OK;
 }
 
-// global ode_mean / ode_maximum across ranks (MPI.Allreduce in src/auxiliary/mpi.jl:45-46,76): all-gather the
-// per-rank partial results and combine them in rank order on every rank (deterministic, identical everywhere)
+// global ode_mean / ode_maximum across ranks (MPI.Allreduce in src/auxiliary/mpi.jl:45-46,76): every rank reduces its
+// owned points, the per-rank results are all-gathered, and the CONSUMER kernel combines them in rank order
+// (k_maxdev_norms forms the mean from the gathered sums, pass A forms the norms from the gathered candidates):
+// two kernels + two tiny all-gathers per stage.
 static int launch_norms_multi(mft_ctx *c)
 {
     ScopedTimer t(c, MFT_K_REDUCE);
@@ -1614,33 +1626,24 @@ static int launch_norms_multi(mft_ctx *c)
     if (!c->comm) return fail(MFT_EINVAL, "multi-rank norms need mft_comm_init");
     const int64_t n = c->n_local;
     const Vec<4> *u = reinterpret_cast<const Vec<4> *>(c->u.p);
-    double *sum = c->stats.p, *mean = c->stats.p + V, *norms = c->stats.p + 2 * V;
-    double *mine = c->gather_buf.p + (int64_t)c->nranks * V;  // 2V doubles of scratch behind the gather area
-    k_reduce_sum<4><<<c->red_blocks, 256, 0, c->stream>>>(u, n, c->partial.p);
-    k_finish_mean<4><<<1, 32, 0, c->stream>>>(c->partial.p, c->red_blocks, 1.0, mine);  // mine[0..V) = local sum
-    c->launches += 2;
+    double *gsum = c->gather_buf.p;                              // nranks x V
+    double *gmax = c->gather_buf.p + (int64_t)c->nranks * V;     // nranks x V
+    double *mine = c->gather_buf.p + (int64_t)2 * c->nranks * V; // 2V scratch (sum | mean, unused)
+    double *mine2 = mine + 2 * V;                                // V scratch
+    k_sum_mean<4><<<c->red_blocks, 256, 0, c->stream>>>(u, n, c->partial.p, c->ticket.p, 1.0, mine);
+    c->launches++;
     LAUNCH_CHECK();
-    if (N->allGather(mine, c->gather_buf.p, V, NCCL_DOUBLE, c->comm, c->stream) != 0)
+    if (N->allGather(mine, gsum, V, NCCL_DOUBLE, c->comm, c->stream) != 0)
         return fail(MFT_ENCCL, "ncclAllGather failed: %s", N->lastError(c->comm));
     const double ng = (double)c->n_global;
     const double divisor = c->mean_div_vn ? (double)V * ng : ng;
-    k_finish_mean<4><<<1, 32, 0, c->stream>>>(c->gather_buf.p, c->nranks, divisor, sum);
+    if (c->max_lex)
+        k_maxdev_norms<4, true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, gsum, c->nranks, divisor, c->partial.p, c->ticket.p + 1, mine2, 0, c->stats.p + V);
+    else
+        k_maxdev_norms<4, false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, gsum, c->nranks, divisor, c->partial.p, c->ticket.p + 1, mine2, 0, c->stats.p + V);
     c->launches++;
     LAUNCH_CHECK();
-    if (c->max_lex) {
-        k_reduce_maxdev<4, true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, mean, c->partial.p);
-        k_finish_norms<4, true><<<1, 32, 0, c->stream>>>(c->partial.p, c->red_blocks, mine, 0);
-    } else {
-        k_reduce_maxdev<4, false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, mean, c->partial.p);
-        k_finish_norms<4, false><<<1, 32, 0, c->stream>>>(c->partial.p, c->red_blocks, mine, 0);
-    }
-    c->launches += 2;
-    LAUNCH_CHECK();
-    if (N->allGather(mine, c->gather_buf.p, V, NCCL_DOUBLE, c->comm, c->stream) != 0)
+    if (N->allGather(mine2, gmax, V, NCCL_DOUBLE, c->comm, c->stream) != 0)
         return fail(MFT_ENCCL, "ncclAllGather failed: %s", N->lastError(c->comm));
-    if (c->max_lex) k_finish_norms<4, true><<<1, 32, 0, c->stream>>>(c->gather_buf.p, c->nranks, norms, 1);
-    else k_finish_norms<4, false><<<1, 32, 0, c->stream>>>(c->gather_buf.p, c->nranks, norms, 1);
-    c->launches++;
-    LAUNCH_CHECK();
     return MFT_OK;
 }

@@ -223,6 +223,17 @@ struct Physics<EQ_ADVECTION2D, 1> {
     __device__ __forceinline__ Vec<1> flux_y(const Vec<1> &u) const { return Vec<1>{{a2 * u.a[0]}}; }
 };
 
+template <int V>
+__device__ __forceinline__ bool lex_less(const double *a, const double *b)
+{
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        if (a[v] < b[v]) return true;
+        if (a[v] > b[v]) return false;
+    }
+    return false;
+}
+
 // ---- pass A: fused flux evaluation + Dx/Dy stencil apply (+ D u, viscosity limiter, g = eps .* D u) --------
 // replaces calc_fluxes! (rbfsolver.jl:247-265) and the forward half of the viscosity sources
 // (hyperviscosity.jl:246-349, 364-373 / 393-402).  One thread per row; a warp owns one ELL slice, so the
@@ -238,7 +249,10 @@ struct PassAArgs {
     void *du;
     void *g;
     const void *approx_du;
-    const double *norms;  // V doubles on device (n_inf_norms), residual mode
+    const double *norms;  // residual mode: norm_parts x V candidates (one per rank) to be combined, or the final V norms
+    int norm_parts;       // 0: norms[] is final; >0: combine norm_parts candidates (lexicographic or per component)
+    int norm_lex;
+    double *norms_out;    // nullable: row 0 publishes the combined norms (diagnostics)
     int64_t n_rows;
     double eqp0, eqp1;
     double c_uw, c_rv, dx_avg;
@@ -418,9 +432,38 @@ __global__ void __launch_bounds__(128, 4) k_pass_a(const PassAArgs A)
             Vec<V> res;
 #pragma unroll
             for (int v = 0; v < V; ++v) res.a[v] = fabs(ad.a[v] - dui.a[v]);
-            double mx = res.a[0] / A.norms[0];
+            double nrm[V];
+            if (A.norm_parts > 0) {
+                // global ode_maximum: combine the per-rank candidates in rank order (MPI.Allreduce(MAX), mpi.jl:76)
 #pragma unroll
-            for (int v = 1; v < V; ++v) mx = jl_max(mx, res.a[v] / A.norms[v]);
+                for (int v = 0; v < V; ++v) nrm[v] = A.norms[v];
+                for (int r = 1; r < A.norm_parts; ++r) {
+                    double c[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) c[v] = A.norms[r * V + v];
+                    if (A.norm_lex) {
+                        if (lex_less<V>(nrm, c)) {
+#pragma unroll
+                            for (int v = 0; v < V; ++v) nrm[v] = c[v];
+                        }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) nrm[v] = jl_max(nrm[v], c[v]);
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < V; ++v) nrm[v] = nrm[v] == 0.0 ? kEps : nrm[v];
+                if (A.norms_out && row == 0) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) A.norms_out[v] = nrm[v];
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) nrm[v] = A.norms[v];
+            }
+            double mx = res.a[0] / nrm[0];
+#pragma unroll
+            for (int v = 1; v < V; ++v) mx = jl_max(mx, res.a[v] / nrm[v]);
             e_rv = 0.5 * A.c_rv * (A.dx_avg * A.dx_avg) * mx;
             if (isnan(e_rv) || isinf(e_rv) || A.success_iter_zero) {
                 if (isnan(e_uw) || isinf(e_uw)) {
@@ -677,17 +720,6 @@ __global__ void k_finish_mean(const double *partial, int nblocks, double divisor
     }
 }
 
-template <int V>
-__device__ __forceinline__ bool lex_less(const double *a, const double *b)
-{
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        if (a[v] < b[v]) return true;
-        if (a[v] > b[v]) return false;
-    }
-    return false;
-}
-
 // LEX: maximum over SVector elements compares lexicographically (Base isless on vectors);
 // otherwise per-component NaN-propagating max.
 template <int V, bool LEX>
@@ -824,14 +856,22 @@ __global__ void __launch_bounds__(256) k_sum_mean(const Vec<V> *__restrict__ u, 
 }
 
 template <int V, bool LEX>
-__global__ void __launch_bounds__(256) k_maxdev_norms(const Vec<V> *__restrict__ u, int64_t n, const double *mean,
-                                                    double *partial, unsigned int *ticket, double *norms)
+__global__ void __launch_bounds__(256) k_maxdev_norms(const Vec<V> *__restrict__ u, int64_t n, const double *sums,
+                                                    int nparts, double divisor, double *partial, unsigned int *ticket,
+                                                    double *norms, int replace_zero, double *mean_out)
 {
+    // mean = (sum of the per-rank sums, in rank order) / divisor  -- ode_mean, src/auxiliary/mpi.jl:40-52
     double m[V], best[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        m[v] = mean[v];
+        double t = sums[v];
+        for (int r = 1; r < nparts; ++r) t += sums[r * V + v];
+        m[v] = t / divisor;
         best[v] = -1.0;
+    }
+    if (mean_out && blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) mean_out[v] = m[v];
     }
     auto combine = [&](double *a, const double *b) {
         if constexpr (LEX) {
@@ -886,7 +926,7 @@ __global__ void __launch_bounds__(256) k_maxdev_norms(const Vec<V> *__restrict__
     __syncthreads();
     block_reduce();
     if (threadIdx.x == 0) {
-        for (int v = 0; v < V; ++v) norms[v] = best[v] == 0.0 ? kEps : best[v];
+        for (int v = 0; v < V; ++v) norms[v] = (replace_zero && best[v] == 0.0) ? kEps : best[v];
         *ticket = 0;
     }
 }
