@@ -132,7 +132,8 @@ def run_ours(args):
     cl, basis, _ = build_workload(nx, ny, 0, m)
     solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=local_rank, exact_order=not args.fma,
                                                                 stage_weights=int(args.stage_weights),
-                                                                cuda_graph=int(args.graph)))
+                                                                cuda_graph=int(args.graph),
+                                                                single_sweep_exact=bool(args.single_sweep)))
     names = dict(left=1, right=2, bottom=3, top=4)
     t_setup = time.time()
     domain = m.ParallelPointCloudDomain(solver, cl, names, comm) if multi else m.PointCloudDomain(solver, cl, names)
@@ -375,6 +376,7 @@ def main():
     ap.add_argument("--fma", action="store_true", help="single-sweep FMA summation instead of the reference order")
     ap.add_argument("--stage-weights", type=int, default=1, help="1: whole operator slices staged in smem; 0: indices only")
     ap.add_argument("--graph", type=int, default=1, help="0 eager, 1 CUDA-graph replay on one GPU, 2 also multi-rank")
+    ap.add_argument("--single-sweep", type=int, default=0, help="k=20 single-sweep exact pass A (register-parked y-products)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--cloud-order", default="hilbert", choices=["hilbert", "lattice"],

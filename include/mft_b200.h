@@ -74,6 +74,9 @@ typedef struct mft_ctx mft_ctx;
                                       by coalesced loads + L2 bulk prefetch.  Default 1 (measured best: pass A staged, pass B not) */
 #define MFT_OPT_REFINE_ORDER 7     /* 1 (default 0): within blocks of 256 device rows, order rows by D' row length
                                       (near-uniform transposed-ELL slices); the caller-visible numbering is unaffected */
+#define MFT_OPT_SINGLE_SWEEP_EXACT 8/* 1: for the default 20-wide stencil use the single-sweep exact kernel (y-products parked in registers:
+                                      one gather + one flux per neighbour, but 255 registers -> 8 warps/SM; measured 20 % slower);
+                                      0 (default): the two-sweep exact kernel.  Same results bit for bit.                       */
 #define MFT_OPT_PREFETCH_DISTANCE 6/* slices ahead for the L2 prefetch of the weight blocks (STAGE_WEIGHTS = 0)        */
 
 /* fields (mft_get_field): caches of create_tominec_rv_cache, hyperviscosity.jl:202-244 */

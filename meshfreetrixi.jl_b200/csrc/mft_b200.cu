@@ -128,7 +128,7 @@ struct mft_ctx {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     // options
-    int exact = 1, mean_div_vn = 1, max_lex = 1, diagnostics = 0, stage_w = 1, stage_w_b = 0, pf_dist = 0, refine_order = 0;
+    int exact = 1, mean_div_vn = 1, max_lex = 1, diagnostics = 0, stage_w = 1, stage_w_b = 0, pf_dist = 0, refine_order = 0, kfix_ok = 0;
     std::vector<const void *> smem_configured;
     // ordering
     bool have_perm = false;
@@ -371,6 +371,7 @@ extern "C" int mft_set_option(mft_ctx *c, int option, double value)
     case MFT_OPT_STAGE_WEIGHTS: c->stage_w = ((int)value & 1) != 0; c->stage_w_b = ((int)value & 2) != 0; break;
     case MFT_OPT_PREFETCH_DISTANCE: c->pf_dist = (int)value; break;
     case MFT_OPT_REFINE_ORDER: c->refine_order = value != 0; break;
+    case MFT_OPT_SINGLE_SWEEP_EXACT: c->kfix_ok = value != 0; break;
     default: return fail(MFT_EINVAL, "mft_set_option: unknown option %d", option);
     }
     return MFT_OK;
@@ -972,6 +973,14 @@ static inline int warp_buf_bytes(const DevEll &e, bool stage_w)
 template <int V, int EQ, bool EX, bool DF, int VI>
 static int launch_pass_a_k(mft_ctx *c, const PassAArgs &a, int grid, int smem)
 {
+    if constexpr (V == 4 && EX && DF) {
+        // uniform 20-wide forward operator (degree-3 default stencil): single-sweep exact kernel
+        if (c->kfix_ok && c->fwd.maxw == 20 && c->fwd.ncols_total == (int64_t)20 * c->fwd.nslices && c->stage_w) {
+            CHECK(ensure_smem(c, k_pass_a<V, EQ, EX, DF, VI, true, 20>, smem));
+            k_pass_a<V, EQ, EX, DF, VI, true, 20><<<grid, 128, smem, c->stream>>>(a);
+            return MFT_OK;
+        }
+    }
     if (c->stage_w) {
         CHECK(ensure_smem(c, k_pass_a<V, EQ, EX, DF, VI, true>, smem));
         k_pass_a<V, EQ, EX, DF, VI, true><<<grid, 128, smem, c->stream>>>(a);

@@ -267,8 +267,12 @@ constexpr int VISC_NONE = 0;
 constexpr int VISC_UPWIND = 1;
 constexpr int VISC_RESIDUAL = 2;
 
-template <int V, int EQ, bool EXACT, bool DO_FLUX, int VISC, bool STAGE_W>
-__global__ void __launch_bounds__(128, 4) k_pass_a(const PassAArgs A)
+// KFIX > 0: every slice is exactly KFIX columns wide (the forward operator of a kNN cloud) and the kernel is the
+// single-sweep exact variant: the x-chain runs in the sweep while the y-products w_y * (-G) are parked in registers
+// (fully unrolled), then the y-chain is appended in order.  Same rounding sequence as the two-sweep form, but each
+// neighbour state is gathered once and its flux evaluated once.
+template <int V, int EQ, bool EXACT, bool DO_FLUX, int VISC, bool STAGE_W, int KFIX = 0>
+__global__ void __launch_bounds__(128, (KFIX > 0 ? 2 : 4)) k_pass_a(const PassAArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ uint64_t bars[4];
@@ -313,8 +317,46 @@ __global__ void __launch_bounds__(128, 4) k_pass_a(const PassAArgs A)
     // are issued before any arithmetic, so a thread keeps kBatch independent gathers in flight (the FP64 division
     // in the flux has a slow-path branch that otherwise stops the compiler from overlapping iterations).
     // Columns past `width` are clamped to the last column with weight 0 (adds an exact zero).
-    constexpr int kBatch = 5;
-    if constexpr (EXACT) {
+    constexpr int kBatch = KFIX > 0 ? 4 : 5;
+    if constexpr (EXACT && KFIX > 0 && DO_FLUX) {
+        static_assert(KFIX % 4 == 0, "KFIX must be a multiple of the batch size");
+        double yp[KFIX][V];
+#pragma unroll
+        for (int c0 = 0; c0 < KFIX; c0 += kBatch) {
+            Vec<V> uj[kBatch];
+            double wa[kBatch], wb[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const int j = ip[(c0 + b) * kSlice];
+                wa[b] = wxp[(c0 + b) * kSlice];
+                wb[b] = wyp[(c0 + b) * kSlice];
+                uj[b] = ld_ro(u + j);
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                ph.prepare(uj[b]);
+                const Vec<V> f = ph.flux_x(uj[b]);
+                const Vec<V> h = ph.flux_y(uj[b]);
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    acc.a[v] = acc.a[v] + wa[b] * (-f.a[v]);
+                    yp[c0 + b][v] = wb[b] * (-h.a[v]);
+                }
+                if constexpr (VISC != VISC_NONE) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        gx.a[v] = gx.a[v] + wa[b] * uj[b].a[v];
+                        gy.a[v] = gy.a[v] + wb[b] * uj[b].a[v];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < KFIX; ++c) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc.a[v] = acc.a[v] + yp[c][v];
+        }
+    } else if constexpr (EXACT) {
         // reference order: all Dx terms in ascending column order, then all Dy terms, separate mul and add
         // (SparseArrays mul!).  alpha = -1 is folded into the flux first: w * (-F).
         for (int c0 = 0; c0 < width; c0 += kBatch) {
