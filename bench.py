@@ -133,7 +133,8 @@ def run_ours(args):
     solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=local_rank, exact_order=not args.fma,
                                                                 stage_weights=int(args.stage_weights),
                                                                 cuda_graph=int(args.graph),
-                                                                single_sweep_exact=bool(args.single_sweep)))
+                                                                single_sweep_exact=bool(args.single_sweep),
+                                                                exchange=args.exchange))
     names = dict(left=1, right=2, bottom=3, top=4)
     t_setup = time.time()
     domain = m.ParallelPointCloudDomain(solver, cl, names, comm) if multi else m.PointCloudDomain(solver, cl, names)
@@ -259,7 +260,7 @@ def run_ours(args):
                                       f"jittered cloud ({nx}x{ny} + ring), PHS3 deg3 k=20, SSPRK33 + HistoryCallback(3)",
                           "points": N, "points_per_gpu": N // world, "k": k, "stages_per_step": STAGES,
                           "summation": "fma single-sweep" if args.fma else "reference order (bit-exact sums)",
-                          "partition": "single GPU" if not multi else f"Hilbert-curve ranges over {world} ranks, NCCL halo exchange (u, g) + all-gather norms per stage",
+                          "partition": "single GPU" if not multi else f"Hilbert-curve ranges over {world} ranks, halo exchange (u, g) + global norms per stage via {'NVLink peer-memory puts (CUDA IPC), graph-replayed' if args.exchange == 'p2p' else 'NCCL send/recv + all-gather'}",
                           "l2": "inputs larger than L2 (operators 2 x %.0f MB per GPU streamed every stage)" % (n_own * 20 * k / 1e6),
                           "setup_s": round(t_setup, 1)},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
@@ -377,6 +378,7 @@ def main():
     ap.add_argument("--stage-weights", type=int, default=1, help="1: whole operator slices staged in smem; 0: indices only")
     ap.add_argument("--graph", type=int, default=1, help="0 eager, 1 CUDA-graph replay on one GPU, 2 also multi-rank")
     ap.add_argument("--single-sweep", type=int, default=0, help="k=20 single-sweep exact pass A (register-parked y-products)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo exchange mechanism")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--cloud-order", default="hilbert", choices=["hilbert", "lattice"],

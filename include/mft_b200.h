@@ -191,6 +191,17 @@ int mft_comm_init(mft_ctx *ctx, int nranks, int rank, const void *id128);
 int mft_set_halo(mft_ctx *ctx, int npeers, const int *peers, const int64_t *send_off, const int64_t *send_idx1,
                  const int64_t *recv_count);
 
+/* Peer-memory exchange over NVLink (alternative to the NCCL path, same results): ranks map each other's state
+ * arrays with CUDA IPC and write halo blocks / partial norms straight into the peer's memory, flagged by epoch counters.
+ * Kernel-only, hence a whole multi-GPU SSPRK step replays as one CUDA graph.
+ *   1. every rank: mft_p2p_handles(ctx, buf192)            -> 3 x 64-byte IPC handles {u, g, flag window}
+ *   2. host program all-gathers the handles (and, per peer, the row in the PEER's array where this rank's block starts:
+ *      n_local(peer) + the peer's receive offset for this rank)
+ *   3. every rank: mft_p2p_connect(ctx, nranks, rank, all_handles, peer_dst_row [one per peer of mft_set_halo], n_global) */
+int mft_p2p_handles(mft_ctx *ctx, void *out3x64);
+int mft_p2p_connect(mft_ctx *ctx, int nranks, int rank, const void *all_handles, const int64_t *peer_dst_row,
+                    int64_t n_global);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,7 +32,7 @@ EXPORTS = [
     "mft_apply_source", "mft_boundary_pass", "mft_upload_state", "mft_download_state", "mft_download_du",
     "mft_history_push", "mft_history_push_weights", "mft_ssprk_step", "mft_get_field", "mft_synchronize",
     "mft_launch_count", "mft_timer_start", "mft_timer_stop", "mft_kernel_time_ms", "mft_set_kernel_timing", "mft_host_alloc", "mft_host_free",
-    "mft_host_register", "mft_host_unregister", "mft_sfc_order", "mft_nccl_unique_id", "mft_comm_init", "mft_set_halo",
+    "mft_host_register", "mft_host_unregister", "mft_sfc_order", "mft_nccl_unique_id", "mft_comm_init", "mft_set_halo", "mft_p2p_handles", "mft_p2p_connect",
 ]
 
 _lib = None
@@ -92,6 +92,8 @@ def load():
         "mft_nccl_unique_id": [vp],
         "mft_comm_init": [vp, i32, i32, vp],
         "mft_set_halo": [vp, i32, vp, vp, vp, vp],
+        "mft_p2p_handles": [vp, vp],
+        "mft_p2p_connect": [vp, i32, i32, vp, vp, i64],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)

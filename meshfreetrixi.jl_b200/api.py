@@ -66,6 +66,7 @@ class RBFFDEngineCUDA:
     max_lexicographic: bool = True     # maximum(::StructArray{SVector}) is a lexicographic max
     stage_weights: int = 1             # bit0: pass A, bit1: pass B -- bulk-copy whole operator slices to smem
     cuda_graph: int = 1                # 1: graph replay of SSPRK steps on one GPU; 2: also multi-rank; 0: eager
+    exchange: str = "p2p"              # multi-GPU halo exchange: "p2p" (CUDA-IPC peer memory over NVLink) or "nccl"
     single_sweep_exact: bool = False   # k=20: exact-order pass A in one sweep (y-products parked in registers)
     refine_order: bool = False         # order rows inside 256-row blocks by D' row length (less padding, worse gather locality)
 
@@ -361,12 +362,13 @@ class SemidiscretizationHyperbolic:
         L.check(lib.mft_finalize(ctx))
         if part is not None and part.nranks > 1:
             comm = domain.comm
-            uid = C.create_string_buffer(128)
-            if comm.rank == 0:
-                L.check(lib.mft_nccl_unique_id(uid))
-            raw = comm.broadcast_bytes(bytes(uid.raw), src=0)
-            uid = C.create_string_buffer(raw, 128)
-            L.check(lib.mft_comm_init(ctx, comm.nranks, comm.rank, uid))
+            if eng.exchange == "nccl":
+                uid = C.create_string_buffer(128)
+                if comm.rank == 0:
+                    L.check(lib.mft_nccl_unique_id(uid))
+                raw = comm.broadcast_bytes(bytes(uid.raw), src=0)
+                uid = C.create_string_buffer(raw, 128)
+                L.check(lib.mft_comm_init(ctx, comm.nranks, comm.rank, uid))
             peers = (C.c_int * max(1, len(part.peers)))(*part.peers)
             send_off = np.zeros(len(part.peers) + 1, dtype=np.int64)
             for i, sidx in enumerate(part.send_idx):
@@ -374,6 +376,22 @@ class SemidiscretizationHyperbolic:
             send_idx1 = np.ascontiguousarray(np.concatenate(part.send_idx) + 1 if part.send_idx else np.zeros(0), dtype=np.int64)
             recv = np.ascontiguousarray(part.recv_count, dtype=np.int64)
             L.check(lib.mft_set_halo(ctx, len(part.peers), peers, L.ptr(send_off), L.ptr(send_idx1), L.ptr(recv)))
+            if eng.exchange == "p2p":
+                # map the peers' state arrays (CUDA IPC) and tell every sender where its block starts in my halo tail
+                hbuf = C.create_string_buffer(192)
+                L.check(lib.mft_p2p_handles(ctx, hbuf))
+                all_h = comm.allgather(bytes(hbuf.raw))
+                my_rows, off = {}, part.n_local
+                for q, cnt in zip(part.peers, part.recv_count):
+                    my_rows[int(q)] = int(off)
+                    off += cnt
+                all_rows = comm.allgather(my_rows)
+                dst_row = np.ascontiguousarray([all_rows[q].get(comm.rank, 0) for q in part.peers], dtype=np.int64)
+                blob = C.create_string_buffer(b"".join(all_h), 192 * comm.nranks)
+                L.check(lib.mft_p2p_connect(ctx, comm.nranks, comm.rank, blob, L.ptr(dst_row), part.n_global))
+                comm.barrier()
+            elif eng.exchange != "nccl":
+                raise ValueError("RBFFDEngineCUDA.exchange must be 'p2p' or 'nccl'")
 
     def refresh_boundary_values(self, t):
         lib = L.load()

@@ -187,6 +187,13 @@ struct mft_ctx {
     DevBuf<double> send_buf;
     DevBuf<double> gather_buf;  // nranks * 2V doubles
     int64_t n_send = 0;
+    // peer-memory exchange (CUDA IPC over NVLink)
+    bool p2p = false;
+    P2PPeers peers_dev{};
+    DevBuf<unsigned char> p2p_window, p2p_local;
+    DevBuf<int> send_peer;
+    DevBuf<long long> send_dst;
+    std::vector<void *> ipc_opened;
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -313,6 +320,11 @@ extern "C" int mft_ctx_destroy(mft_ctx *c)
     DevBuf<double> *bufs[] = {&c->u, &c->du, &c->uprev, &c->g, &c->approx_du, &c->stage_soa, &c->eps, &c->eps_uw,
                               &c->eps_rv, &c->eps_c, &c->residual, &c->partial, &c->stats, &c->send_buf, &c->gather_buf};
     for (auto *b : bufs) b->release();
+    for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
+    c->p2p_window.release();
+    c->p2p_local.release();
+    c->send_peer.release();
+    c->send_dst.release();
     c->d_perm.release();
     c->send_rows.release();
     c->ticket.release();
@@ -833,15 +845,18 @@ extern "C" int mft_finalize(mft_ctx *c)
 static int upload_soa(mft_ctx *c, const double *const *soa, double *dst_aos)
 {
     const int64_t n = c->n_tot;
+    // Multi-rank: only the owned rows are taken from the caller.  The halo tail belongs to the exchange -- with
+    // peer-memory puts a neighbour may already have written the next halo block while this upload is still queued.
+    const int64_t n_up = c->nranks > 1 ? c->n_local : n;
     for (int v = 0; v < c->V; ++v) {
         if (!soa || !soa[v]) return fail(MFT_EINVAL, "state component %d is NULL", v);
         CU(cudaMemcpyAsync(c->stage_soa.p + (int64_t)v * n, soa[v], sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     }
     ScopedTimer t(c, MFT_K_OTHER);
     if (c->V == 4)
-        k_pack<4><<<grid_for(n, 256), 256, 0, c->stream>>>(c->stage_soa.p, n, c->d_perm.p, reinterpret_cast<Vec<4> *>(dst_aos), n);
+        k_pack<4><<<grid_for(n_up, 256), 256, 0, c->stream>>>(c->stage_soa.p, n, c->d_perm.p, reinterpret_cast<Vec<4> *>(dst_aos), n_up);
     else
-        k_pack<1><<<grid_for(n, 256), 256, 0, c->stream>>>(c->stage_soa.p, n, c->d_perm.p, reinterpret_cast<Vec<1> *>(dst_aos), n);
+        k_pack<1><<<grid_for(n_up, 256), 256, 0, c->stream>>>(c->stage_soa.p, n, c->d_perm.p, reinterpret_cast<Vec<1> *>(dst_aos), n_up);
     c->launches++;
     LAUNCH_CHECK();
     return MFT_OK;
@@ -899,6 +914,18 @@ template <int W>
 static int halo_exchange(mft_ctx *c, double *field /* AoS, W doubles per point */)
 {
     if (c->nranks <= 1 || (c->n_send == 0 && c->n_halo == 0)) return MFT_OK;
+    if (c->p2p) {
+        const int F = W == 8 ? 1 : 0;
+        ScopedTimer t(c, MFT_K_OTHER);
+        P2PLocal *L = reinterpret_cast<P2PLocal *>(c->p2p_local.p);
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(128, (c->n_send + 255) / 256));
+        k_p2p_put<W><<<grid, 256, 0, c->stream>>>(c->peers_dev, L, F, reinterpret_cast<const Vec<W> *>(field), c->send_rows.p,
+                                                 c->send_peer.p, c->send_dst.p, c->n_send);
+        k_p2p_wait<<<1, 32, 0, c->stream>>>(c->peers_dev, L, F);
+        c->launches += 2;
+        LAUNCH_CHECK();
+        return MFT_OK;
+    }
     if (!c->comm) return fail(MFT_EINVAL, "halo exchange requested but mft_comm_init was not called");
     if (c->n_send > 0) {
         ScopedTimer t(c, MFT_K_OTHER);
@@ -1367,7 +1394,7 @@ extern "C" int mft_ssprk_step(mft_ctx *c, int scheme, double t, double dt)
     // The step is a fixed sequence of ~35 launches: replay it as one CUDA graph (the kernel arguments that vary
     // between steps -- dt and the success_iter==0 flag -- are part of the cache key; t only selects Dirichlet tables,
     // which the caller refreshes).  Eager path: per-kernel timing on, multi-rank (NCCL calls), or first use of a key.
-    const bool graph_ok = c->use_graphs && !c->timing && (c->nranks == 1 || c->use_graphs >= 2);
+    const bool graph_ok = c->use_graphs && !c->timing && (c->nranks == 1 || c->p2p || c->use_graphs >= 2);
     if (!graph_ok) return ssprk33_step_launches(c, t, dt, first);
     const int si_zero = c->success_iter == 0;
     mft_ctx::StepGraph *g = nullptr;
@@ -1404,6 +1431,11 @@ extern "C" int mft_synchronize(mft_ctx *c)
 {
     NEED_CTX(c);
     CU(cudaStreamSynchronize(c->stream));
+    if (c->p2p) {
+        P2PLocal h;
+        CU(cudaMemcpy(&h, c->p2p_local.p, sizeof h, cudaMemcpyDeviceToHost));
+        if (h.error) return fail(MFT_ENCCL, "peer-memory exchange timed out waiting for a peer flag (a rank fell out of step)");
+    }
     return MFT_OK;
 }
 
@@ -1632,6 +1664,21 @@ static int launch_norms_multi(mft_ctx *c)
     ScopedTimer t(c, MFT_K_REDUCE);
     const int V = 4;
     NcclApi *N = c->nccl;
+    if (c->p2p) {
+        const int64_t n = c->n_local;
+        const Vec<4> *u = reinterpret_cast<const Vec<4> *>(c->u.p);
+        P2PLocal *L = reinterpret_cast<P2PLocal *>(c->p2p_local.p);
+        const double ng = (double)c->n_global;
+        const double divisor = c->mean_div_vn ? (double)V * ng : ng;
+        double *gmax = c->gather_buf.p + (int64_t)c->nranks * V;
+        k_p2p_sum<<<c->red_blocks, 256, 0, c->stream>>>(u, n, c->partial.p, c->peers_dev, L);
+        if (c->max_lex) k_p2p_maxdev<true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, divisor, c->partial.p, c->peers_dev, L, c->stats.p + V);
+        else k_p2p_maxdev<false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, divisor, c->partial.p, c->peers_dev, L, c->stats.p + V);
+        k_p2p_collect_max<<<1, 32, 0, c->stream>>>(c->peers_dev, L, gmax);
+        c->launches += 3;
+        LAUNCH_CHECK();
+        return MFT_OK;
+    }
     if (!c->comm) return fail(MFT_EINVAL, "multi-rank norms need mft_comm_init");
     const int64_t n = c->n_local;
     const Vec<4> *u = reinterpret_cast<const Vec<4> *>(c->u.p);
@@ -1654,5 +1701,86 @@ static int launch_norms_multi(mft_ctx *c)
     LAUNCH_CHECK();
     if (N->allGather(mine2, gmax, V, NCCL_DOUBLE, c->comm, c->stream) != 0)
         return fail(MFT_ENCCL, "ncclAllGather failed: %s", N->lastError(c->comm));
+    return MFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// peer-memory exchange setup: CUDA IPC handles of {u, g, window} travel through the host program (all-gather)
+// ------------------------------------------------------------------------------------------------------
+extern "C" int mft_p2p_handles(mft_ctx *c, void *out3x64)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    if (!out3x64) return fail(MFT_EINVAL, "mft_p2p_handles: NULL");
+    if (c->V != 4) return fail(MFT_ENOTSUP, "peer-memory exchange is implemented for Euler 2-D");
+    if (!c->p2p_window.p) {
+        CHECK(c->p2p_window.alloc((int64_t)sizeof(P2PWindow)));
+        CHECK(c->p2p_local.alloc((int64_t)sizeof(P2PLocal)));
+        CU(cudaMemset(c->p2p_window.p, 0, sizeof(P2PWindow)));
+        CU(cudaMemset(c->p2p_local.p, 0, sizeof(P2PLocal)));
+        if (!c->g.p) {  // no viscosity source: still give peers something valid to map
+            CHECK(c->g.alloc((c->n_tot + 1) * 2 * c->V));
+            CU(cudaMemset(c->g.p, 0, sizeof(double) * (c->n_tot + 1) * 2 * c->V));
+        }
+    }
+    cudaIpcMemHandle_t h[3];
+    CU(cudaIpcGetMemHandle(&h[0], c->u.p));
+    CU(cudaIpcGetMemHandle(&h[1], c->g.p));
+    CU(cudaIpcGetMemHandle(&h[2], c->p2p_window.p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(out3x64, h, sizeof h);
+    return MFT_OK;
+}
+
+extern "C" int mft_p2p_connect(mft_ctx *c, int nranks, int rank, const void *all_handles, const int64_t *peer_dst_row,
+                               int64_t n_global)
+{
+    NEED_CTX(c);
+    if (nranks < 2 || nranks > kMaxRanks || rank < 0 || rank >= nranks || !all_handles)
+        return fail(MFT_EINVAL, "mft_p2p_connect: bad arguments (2..%d ranks)", kMaxRanks);
+    if (!c->p2p_window.p) return fail(MFT_EINVAL, "mft_p2p_connect: call mft_p2p_handles first");
+    if (c->peers.empty() && c->n_halo > 0) return fail(MFT_EINVAL, "mft_p2p_connect: call mft_set_halo first");
+    const cudaIpcMemHandle_t *H = reinterpret_cast<const cudaIpcMemHandle_t *>(all_handles);
+    P2PPeers &P = c->peers_dev;
+    memset(&P, 0, sizeof P);
+    P.nranks = nranks;
+    P.rank = rank;
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            P.field[0][r] = c->u.p;
+            P.field[1][r] = c->g.p;
+            P.win[r] = reinterpret_cast<P2PWindow *>(c->p2p_window.p);
+            continue;
+        }
+        void *q[3];
+        for (int k = 0; k < 3; ++k) {
+            cudaError_t e = cudaIpcOpenMemHandle(&q[k], H[r * 3 + k], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return fail(MFT_ECUDA, "cudaIpcOpenMemHandle(rank %d): %s (peer access over NVLink/PCIe is required)", r, cudaGetErrorString(e));
+            c->ipc_opened.push_back(q[k]);
+        }
+        P.field[0][r] = q[0];
+        P.field[1][r] = q[1];
+        P.win[r] = reinterpret_cast<P2PWindow *>(q[2]);
+    }
+    // destinations / sources and the per-entry routing table
+    std::vector<int> speer((size_t)c->n_send);
+    std::vector<long long> sdst((size_t)c->n_send);
+    for (size_t p = 0; p < c->peers.size(); ++p) {
+        const int64_t ns = c->send_off[p + 1] - c->send_off[p];
+        const int64_t nr = c->recv_off[p + 1] - c->recv_off[p];
+        if (ns > 0) P.dst[P.ndst++] = c->peers[p];
+        if (nr > 0) P.src[P.nsrc++] = c->peers[p];
+        for (int64_t i = 0; i < ns; ++i) {
+            speer[c->send_off[p] + i] = c->peers[p];
+            sdst[c->send_off[p] + i] = (long long)(peer_dst_row[p] + i);
+        }
+    }
+    CHECK(c->send_peer.upload(speer));
+    CHECK(c->send_dst.upload(sdst));
+    c->nranks = nranks;
+    c->rank = rank;
+    c->n_global = n_global;
+    if (!c->gather_buf.p) CHECK(c->gather_buf.alloc((int64_t)2 * nranks * c->V + 4 * c->V));
+    c->p2p = true;
     return MFT_OK;
 }

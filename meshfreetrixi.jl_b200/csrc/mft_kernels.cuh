@@ -1095,6 +1095,277 @@ __global__ void k_halo_pack(const Vec<W> *__restrict__ src, const int *__restric
     buf[i] = src[send_rows[i]];
 }
 
+// =====================================================================================================================
+// Peer-memory (NVLink) exchange: one process per GPU, peers' buffers mapped with CUDA IPC.  A sender writes its halo
+// block straight into the receiver's halo tail and then raises an epoch flag in the receiver's window; the per-rank
+// partial norms travel the same way.  Only kernels are involved, so a whole multi-GPU SSPRK step is graph-capturable,
+// and the latency is one NVLink write instead of an NCCL launch.  Flow control: a rank re-uses a peer's halo tail only
+// after that peer has signalled (credit flag) that it consumed the previous epoch.
+// =====================================================================================================================
+constexpr int kMaxRanks = 16;
+constexpr unsigned long long kSpinLimit = 1ull << 31;  // ~ seconds: then give up and raise the error flag
+
+struct P2PWindow {                                 // lives in every rank's memory; peers write into it
+    unsigned long long data_flag[2][kMaxRanks];    // [field][src rank]: epoch whose halo block has fully arrived
+    unsigned long long credit[2][kMaxRanks];       // [field][dst rank]: epoch of `field` that dst has consumed
+    unsigned long long sum_flag[2][kMaxRanks];     // [parity][rank]
+    unsigned long long max_flag[2][kMaxRanks];
+    double sums[2][kMaxRanks][4];
+    double maxs[2][kMaxRanks][4];
+};
+
+struct P2PLocal {                                  // local counters (never written remotely)
+    unsigned long long epoch[2];                   // halo epochs of field 0 (u) and 1 (g)
+    unsigned long long epoch_n;                    // norms epoch
+    unsigned int ticket[4];
+    int error;
+};
+
+struct P2PPeers {
+    P2PWindow *win[kMaxRanks];   // windows of all ranks (own included)
+    void *field[2][kMaxRanks];   // peers' u and g arrays
+    int nranks, rank;
+    int ndst, nsrc;              // ranks I send to / receive from
+    int dst[kMaxRanks], src[kMaxRanks];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long want, int *error)
+{
+    unsigned long long n = 0;
+    while (ld_acquire_sys(flag) < want) {
+        if (++n > kSpinLimit) {
+            *error = 1;
+            return false;
+        }
+        __nanosleep(64);
+    }
+    return true;
+}
+
+// put: every send entry goes straight into the destination rank's halo tail.  F = field id (0: u, 1: g).
+template <int W>
+__global__ void __launch_bounds__(256) k_p2p_put(P2PPeers P, P2PLocal *L, int F, const Vec<W> *__restrict__ src_field,
+                                               const int *__restrict__ send_rows, const int *__restrict__ send_peer,
+                                               const long long *__restrict__ send_dst, int64_t n_send)
+{
+    __shared__ bool is_last;
+    const unsigned long long e = L->epoch[F] + 1;
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            // credits: everything stream-ordered before this kernel has consumed the halos of both fields' last epochs
+            for (int f = 0; f < 2; ++f) {
+                const unsigned long long ef = L->epoch[f];
+                for (int i = 0; i < P.nsrc; ++i) st_release_sys(&P.win[P.src[i]]->credit[f][P.rank], ef);
+            }
+        }
+        // wait until every destination has consumed epoch e-1 of this field
+        for (int i = 0; i < P.ndst; ++i) spin_until(&P.win[P.rank]->credit[F][P.dst[i]], e - 1, &L->error);
+    }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_send; i += (int64_t)gridDim.x * blockDim.x) {
+        const Vec<W> v = src_field[send_rows[i]];
+        Vec<W> *dst = reinterpret_cast<Vec<W> *>(P.field[F][send_peer[i]]) + send_dst[i];
+        st_vec(dst, v);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&L->ticket[F], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence_system();
+        for (int i = 0; i < P.ndst; ++i) st_release_sys(&P.win[P.dst[i]]->data_flag[F][P.rank], e);
+        L->epoch[F] = e;
+        L->ticket[F] = 0;
+    }
+}
+
+// wait until the halo blocks of the current epoch of field F have arrived from every source rank
+__global__ void k_p2p_wait(P2PPeers P, P2PLocal *L, int F)
+{
+    if (threadIdx.x < P.nsrc) spin_until(&P.win[P.rank]->data_flag[F][P.src[threadIdx.x]], L->epoch[F], &L->error);
+}
+
+// publish V doubles (this rank's partial sum or max-deviation candidate) into every rank's window
+__device__ __forceinline__ void p2p_publish(const P2PPeers &P, int which, int par, unsigned long long en, const double *val)
+{
+    for (int r = 0; r < P.nranks; ++r) {
+        P2PWindow *w = P.win[r];
+        double *dst = which == 0 ? w->sums[par][P.rank] : w->maxs[par][P.rank];
+        for (int v = 0; v < 4; ++v) dst[v] = val[v];
+    }
+    __threadfence_system();
+    for (int r = 0; r < P.nranks; ++r) {
+        P2PWindow *w = P.win[r];
+        st_release_sys(which == 0 ? &w->sum_flag[par][P.rank] : &w->max_flag[par][P.rank], en);
+    }
+}
+__device__ __forceinline__ void p2p_wait_all(const P2PPeers &P, P2PLocal *L, int which, int par, unsigned long long en)
+{
+    const P2PWindow *w = P.win[P.rank];
+    for (int r = 0; r < P.nranks; ++r) spin_until(which == 0 ? &w->sum_flag[par][r] : &w->max_flag[par][r], en, &L->error);
+}
+
+// local sum of the owned points -> published to all ranks (epoch en = epoch_n + 1)
+__global__ void __launch_bounds__(256) k_p2p_sum(const Vec<4> *__restrict__ u, int64_t n, double *partial, P2PPeers P, P2PLocal *L)
+{
+    constexpr int V = 4;
+    double s[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) s[v] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Vec<V> x = ld_ro(u + i);
+#pragma unroll
+        for (int v = 0; v < V; ++v) s[v] += x.a[v];
+    }
+    __shared__ double sh[8][V];
+    __shared__ bool is_last;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        for (int o = 16; o > 0; o >>= 1) s[v] += __shfl_down_sync(0xffffffffu, s[v], o);
+    if (l == 0)
+        for (int v = 0; v < V; ++v) sh[w][v] = s[v];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int v = 0; v < V; ++v) {
+            double t = 0.0;
+            for (int k = 0; k < 8; ++k) t += sh[k][v];
+            partial[(int64_t)blockIdx.x * V + v] = t;
+        }
+        __threadfence();
+        is_last = atomicAdd(&L->ticket[2], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int v = 0; v < V; ++v) s[v] = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+        for (int v = 0; v < V; ++v) s[v] += __ldcg(&partial[(int64_t)b * V + v]);
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        for (int o = 16; o > 0; o >>= 1) s[v] += __shfl_down_sync(0xffffffffu, s[v], o);
+    __syncthreads();
+    if (l == 0)
+        for (int v = 0; v < V; ++v) sh[w][v] = s[v];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot[V];
+        for (int v = 0; v < V; ++v) {
+            double t = 0.0;
+            for (int k = 0; k < 8; ++k) t += sh[k][v];
+            tot[v] = t;
+        }
+        const unsigned long long en = L->epoch_n + 1;
+        p2p_publish(P, 0, (int)(en & 1), en, tot);
+        L->ticket[2] = 0;
+    }
+}
+
+// max deviation from the GLOBAL mean (sums of all ranks, combined in rank order) -> candidates published to all ranks
+template <bool LEX>
+__global__ void __launch_bounds__(256) k_p2p_maxdev(const Vec<4> *__restrict__ u, int64_t n, double divisor, double *partial,
+                                                  P2PPeers P, P2PLocal *L, double *mean_out)
+{
+    constexpr int V = 4;
+    const unsigned long long en = L->epoch_n + 1;
+    const int par = (int)(en & 1);
+    if (threadIdx.x == 0) p2p_wait_all(P, L, 0, par, en);
+    __syncthreads();
+    double m[V], best[V];
+    const P2PWindow *win = P.win[P.rank];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        double t = __ldcv(&win->sums[par][0][v]);
+        for (int r = 1; r < P.nranks; ++r) t += __ldcv(&win->sums[par][r][v]);
+        m[v] = t / divisor;
+        best[v] = -1.0;
+    }
+    if (mean_out && blockIdx.x == 0 && threadIdx.x == 0)
+        for (int v = 0; v < V; ++v) mean_out[v] = m[v];
+    auto combine = [&](double *a, const double *b) {
+        if constexpr (LEX) {
+            if (lex_less<V>(a, b)) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) a[v] = b[v];
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) a[v] = jl_max(a[v], b[v]);
+        }
+    };
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Vec<V> x = ld_ro(u + i);
+        double c[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) c[v] = fabs(x.a[v] - m[v]);
+        combine(best, c);
+    }
+    __shared__ double sh[8][V];
+    __shared__ bool is_last;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    auto block_reduce = [&]() {
+        for (int o = 16; o > 0; o >>= 1) {
+            double other[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) other[v] = __shfl_down_sync(0xffffffffu, best[v], o);
+            combine(best, other);
+        }
+        if (l == 0)
+            for (int v = 0; v < V; ++v) sh[w][v] = best[v];
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int k = 1; k < 8; ++k) combine(best, sh[k]);
+    };
+    block_reduce();
+    if (threadIdx.x == 0) {
+        for (int v = 0; v < V; ++v) partial[(int64_t)blockIdx.x * V + v] = best[v];
+        __threadfence();
+        is_last = atomicAdd(&L->ticket[3], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int v = 0; v < V; ++v) best[v] = -1.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+        double c[V];
+        for (int v = 0; v < V; ++v) c[v] = __ldcg(&partial[(int64_t)b * V + v]);
+        combine(best, c);
+    }
+    __syncthreads();
+    block_reduce();
+    if (threadIdx.x == 0) {
+        p2p_publish(P, 1, par, en, best);
+        L->epoch_n = en;
+        L->ticket[3] = 0;
+    }
+}
+
+// one thread waits for the max-deviation candidates of all ranks and copies them to a local, L1-cacheable buffer that
+// pass A then reads like the NCCL-gathered one
+__global__ void k_p2p_collect_max(P2PPeers P, P2PLocal *L, double *out /* nranks x 4 */)
+{
+    if (threadIdx.x == 0) {
+        const unsigned long long en = L->epoch_n;
+        const int par = (int)(en & 1);
+        p2p_wait_all(P, L, 1, par, en);
+        const P2PWindow *win = P.win[P.rank];
+        for (int r = 0; r < P.nranks; ++r)
+            for (int v = 0; v < 4; ++v) out[r * 4 + v] = __ldcv(&win->maxs[par][r][v]);
+    }
+}
+
 __global__ void k_fill_zero(double *p, int64_t len)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;

@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--mode", default="cpu")
     ap.add_argument("--out", default="")
     ap.add_argument("--source", default="upwind")
+    ap.add_argument("--exchange", default="p2p")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -126,7 +127,7 @@ def main():
         assert err < 1e-12, err
     else:
         solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=int(os.environ.get("LOCAL_RANK", rank)),
-                                                                    diagnostics=True))
+                                                                    diagnostics=True, exchange=args.exchange))
         domain = m.ParallelPointCloudDomain(solver, cl, names, comm)
         part = domain.partition
         eq = m.CompressibleEulerEquations2D(GAMMA)
