@@ -910,21 +910,35 @@ extern "C" int mft_download_du(mft_ctx *c, double *const *du_soa)
 // ------------------------------------------------------------------------------------------------------
 // halo exchange (NCCL send/recv straight from/to device buffers; receive lands in the halo tail)
 // ------------------------------------------------------------------------------------------------------
+// peer-memory exchange, split so that independent work can be queued between the put and the wait
+template <int W>
+static int p2p_put(mft_ctx *c, double *field)
+{
+    ScopedTimer t(c, MFT_K_OTHER);
+    P2PLocal *L = reinterpret_cast<P2PLocal *>(c->p2p_local.p);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(128, (c->n_send + 255) / 256));
+    k_p2p_put<W><<<grid, 256, 0, c->stream>>>(c->peers_dev, L, W == 8 ? 1 : 0, reinterpret_cast<const Vec<W> *>(field),
+                                             c->send_rows.p, c->send_peer.p, c->send_dst.p, c->n_send);
+    c->launches++;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}
+static int p2p_wait(mft_ctx *c, int F)
+{
+    ScopedTimer t(c, MFT_K_OTHER);
+    k_p2p_wait<<<1, 32, 0, c->stream>>>(c->peers_dev, reinterpret_cast<P2PLocal *>(c->p2p_local.p), F);
+    c->launches++;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}
+
 template <int W>
 static int halo_exchange(mft_ctx *c, double *field /* AoS, W doubles per point */)
 {
     if (c->nranks <= 1 || (c->n_send == 0 && c->n_halo == 0)) return MFT_OK;
     if (c->p2p) {
-        const int F = W == 8 ? 1 : 0;
-        ScopedTimer t(c, MFT_K_OTHER);
-        P2PLocal *L = reinterpret_cast<P2PLocal *>(c->p2p_local.p);
-        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(128, (c->n_send + 255) / 256));
-        k_p2p_put<W><<<grid, 256, 0, c->stream>>>(c->peers_dev, L, F, reinterpret_cast<const Vec<W> *>(field), c->send_rows.p,
-                                                 c->send_peer.p, c->send_dst.p, c->n_send);
-        k_p2p_wait<<<1, 32, 0, c->stream>>>(c->peers_dev, L, F);
-        c->launches += 2;
-        LAUNCH_CHECK();
-        return MFT_OK;
+        CHECK(p2p_put<W>(c, field));
+        return p2p_wait(c, W == 8 ? 1 : 0);
     }
     if (!c->comm) return fail(MFT_EINVAL, "halo exchange requested but mft_comm_init was not called");
     if (c->n_send > 0) {
@@ -1160,6 +1174,7 @@ static int launch_norms(mft_ctx *c)
 }
 
 static int launch_norms_multi(mft_ctx *c);
+static int p2p_norms_part(mft_ctx *c, int part);
 
 // one source functor call on the resident state
 static int apply_source_dev(mft_ctx *c, Source *s)
@@ -1180,12 +1195,24 @@ static int rhs_device(mft_ctx *c, double t)
     // points, and halo copies of boundary points must carry the BC-imposed value the owner computes, so the
     // exchange runs after the owner applied its BCs.
     CHECK(launch_boundary(c, false));  // pass 1: du is formed from 0 below, only u needs writing
-    CHECK(halo_exchange<4 /*V set below*/>(c, c->u.p));
+    const bool fused_visc = !c->srcs.empty() && (c->srcs[0]->kind == MFT_SRC_UPWIND || c->srcs[0]->kind == MFT_SRC_RESIDUAL);
+    const bool p2p_rv = c->p2p && c->nranks > 1 && fused_visc && c->srcs[0]->kind == MFT_SRC_RESIDUAL;
+    if (p2p_rv) {
+        // the norms only need OWNED points, so their two flag round-trips are interleaved with the halo put / wait:
+        // sums fly while the halo block is being written, candidates fly while we wait for the neighbours' halo
+        CHECK(p2p_norms_part(c, 0));
+        CHECK(p2p_put<4>(c, c->u.p));
+        CHECK(p2p_norms_part(c, 1));
+        CHECK(p2p_wait(c, 0));
+        CHECK(p2p_norms_part(c, 2));
+    } else {
+        CHECK(halo_exchange<4 /*V set below*/>(c, c->u.p));
+    }
     size_t first = 0;
-    if (!c->srcs.empty() && (c->srcs[0]->kind == MFT_SRC_UPWIND || c->srcs[0]->kind == MFT_SRC_RESIDUAL)) {
+    if (fused_visc) {
         Source *s = c->srcs[0];
         const int visc = s->kind == MFT_SRC_UPWIND ? VISC_UPWIND : VISC_RESIDUAL;
-        if (visc == VISC_RESIDUAL) CHECK(c->nranks > 1 ? launch_norms_multi(c) : launch_norms(c));
+        if (visc == VISC_RESIDUAL && !p2p_rv) CHECK(c->nranks > 1 ? launch_norms_multi(c) : launch_norms(c));
         CHECK(launch_pass_a(c, true, visc, s, false));  // flux divergence + D u + eps + g in one sweep
         CHECK(halo_exchange<8>(c, c->g.p));
         CHECK(launch_pass_b(c));
@@ -1655,6 +1682,30 @@ extern "C" int mft_set_halo(mft_ctx *c, int npeers, const int *peers, const int6
     return MFT_OK;
 }
 
+// peer-memory norms in three separately launchable parts: 0 = local sum + publish, 1 = wait sums, max deviation from the
+// global mean + publish, 2 = wait candidates and stage them for pass A
+static int p2p_norms_part(mft_ctx *c, int part)
+{
+    ScopedTimer t(c, MFT_K_REDUCE);
+    const int V = 4;
+    const int64_t n = c->n_local;
+    const Vec<4> *u = reinterpret_cast<const Vec<4> *>(c->u.p);
+    P2PLocal *L = reinterpret_cast<P2PLocal *>(c->p2p_local.p);
+    if (part == 0) {
+        k_p2p_sum<<<c->red_blocks, 256, 0, c->stream>>>(u, n, c->partial.p, c->peers_dev, L);
+    } else if (part == 1) {
+        const double ng = (double)c->n_global;
+        const double divisor = c->mean_div_vn ? (double)V * ng : ng;
+        if (c->max_lex) k_p2p_maxdev<true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, divisor, c->partial.p, c->peers_dev, L, c->stats.p + V);
+        else k_p2p_maxdev<false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, divisor, c->partial.p, c->peers_dev, L, c->stats.p + V);
+    } else {
+        k_p2p_collect_max<<<1, 32, 0, c->stream>>>(c->peers_dev, L, c->gather_buf.p + (int64_t)c->nranks * V);
+    }
+    c->launches++;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}
+
 // global ode_mean / ode_maximum across ranks (MPI.Allreduce in src/auxiliary/mpi.jl:45-46,76): every rank reduces its
 // owned points, the per-rank results are all-gathered, and the CONSUMER kernel combines them in rank order
 // (k_maxdev_norms forms the mean from the gathered sums, pass A forms the norms from the gathered candidates):
@@ -1665,19 +1716,9 @@ static int launch_norms_multi(mft_ctx *c)
     const int V = 4;
     NcclApi *N = c->nccl;
     if (c->p2p) {
-        const int64_t n = c->n_local;
-        const Vec<4> *u = reinterpret_cast<const Vec<4> *>(c->u.p);
-        P2PLocal *L = reinterpret_cast<P2PLocal *>(c->p2p_local.p);
-        const double ng = (double)c->n_global;
-        const double divisor = c->mean_div_vn ? (double)V * ng : ng;
-        double *gmax = c->gather_buf.p + (int64_t)c->nranks * V;
-        k_p2p_sum<<<c->red_blocks, 256, 0, c->stream>>>(u, n, c->partial.p, c->peers_dev, L);
-        if (c->max_lex) k_p2p_maxdev<true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, divisor, c->partial.p, c->peers_dev, L, c->stats.p + V);
-        else k_p2p_maxdev<false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, divisor, c->partial.p, c->peers_dev, L, c->stats.p + V);
-        k_p2p_collect_max<<<1, 32, 0, c->stream>>>(c->peers_dev, L, gmax);
-        c->launches += 3;
-        LAUNCH_CHECK();
-        return MFT_OK;
+        CHECK(p2p_norms_part(c, 0));
+        CHECK(p2p_norms_part(c, 1));
+        return p2p_norms_part(c, 2);
     }
     if (!c->comm) return fail(MFT_EINVAL, "multi-rank norms need mft_comm_init");
     const int64_t n = c->n_local;

@@ -1147,7 +1147,7 @@ __device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsig
             *error = 1;
             return false;
         }
-        __nanosleep(64);
+        __nanosleep(20);
     }
     return true;
 }
@@ -1177,9 +1177,13 @@ __global__ void __launch_bounds__(256) k_p2p_put(P2PPeers P, P2PLocal *L, int F,
         Vec<W> *dst = reinterpret_cast<Vec<W> *>(P.field[F][send_peer[i]]) + send_dst[i];
         st_vec(dst, v);
     }
-    __threadfence_system();
+    // fences are cumulative: the block barrier makes every thread's remote stores visible to thread 0, whose
+    // system-scope fence then orders them before the ticket (and, in the last block, before the flags)
     __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(&L->ticket[F], 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        is_last = atomicAdd(&L->ticket[F], 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (is_last && threadIdx.x == 0) {
         __threadfence_system();

@@ -61,3 +61,12 @@ def test_two_gpus_match_serial_oracle(tmp_path, source, exchange):
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     res = _launch(2, "gpu", source, str(tmp_path), timeout=240, exchange=exchange)
     assert all(r["err"] < 1e-12 and r["err_steps"] < 1e-9 for r in res)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nproc", [4, 8])
+def test_many_gpus_p2p_match_serial_oracle(tmp_path, nproc):
+    if _ngpu() < nproc:
+        pytest.skip(f"needs {nproc} GPUs (run under gpurun --gpus {nproc})")
+    res = _launch(nproc, "gpu", "residual", str(tmp_path), timeout=300, exchange="p2p")
+    assert len(res) == nproc and all(r["err"] < 1e-12 and r["err_steps"] < 1e-9 for r in res)
