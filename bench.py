@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -65,6 +65,10 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
+
+    def mark(self):
+        """samples before this point are warm-up; keep the last one (GPU already under load) and everything after"""
+        self.first = max(0, len(self.rows) - 1)
 
     def stop(self):
         if not self.proc:
@@ -77,7 +81,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[getattr(self, 'first', 0):]:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -174,12 +178,14 @@ def run_ours(args):
     # ---- device-resident timed region: barrier + sync on both sides, CUDA events on the ctx stream, max over ranks ----
     L.check(lib.mft_upload_state(ctx, L.soa_ptrs(u0)))
     L.check(lib.mft_history_push(ctx, 0.0, 0, 3))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()   # nvidia-smi needs ~100 ms to deliver its first sample: start before the warm-up steps
     t = steps(args.warmup, 0.0, 0)
     L.check(lib.mft_synchronize(ctx))
     barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     launches0 = lib.mft_launch_count(ctx)
     L.check(lib.mft_timer_start(ctx))
     t = steps(args.steps, t, args.warmup)
@@ -369,8 +375,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-side", type=int, default=1024, help="lattice side; 1024 -> the 1M-point cloud of configs[1]")
     ap.add_argument("--ref-n-side", type=int, default=512, help="lattice side of the bounded sample the CPU arm runs")

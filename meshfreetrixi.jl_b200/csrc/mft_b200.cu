@@ -1011,9 +1011,17 @@ static inline int warp_buf_bytes(const DevEll &e, bool stage_w)
     return ((std::max(e.maxw, 1) * per_col + 127) / 128) * 128;
 }
 
+// Whole-slice staging keeps 4 CTAs/SM only while a warp's blob is <= ~14 KB (k <= 22); wider stencils stage the index
+// block only (measured: stencil sweep in profiles/), which keeps occupancy and the L1 carve-out.
+static inline bool stage_whole_slice(const mft_ctx *c, const DevEll &e, bool want)
+{
+    return want && e.maxw * e.colb <= 14 * 1024;
+}
+
 template <int V, int EQ, bool EX, bool DF, int VI>
 static int launch_pass_a_k(mft_ctx *c, const PassAArgs &a, int grid, int smem)
 {
+    const bool stage_w = stage_whole_slice(c, c->fwd, c->stage_w);
     if constexpr (V == 4 && EX && DF) {
         // uniform 20-wide forward operator (degree-3 default stencil): single-sweep exact kernel
         if (c->kfix_ok && c->fwd.maxw == 20 && c->fwd.ncols_total == (int64_t)20 * c->fwd.nslices && c->stage_w) {
@@ -1022,7 +1030,7 @@ static int launch_pass_a_k(mft_ctx *c, const PassAArgs &a, int grid, int smem)
             return MFT_OK;
         }
     }
-    if (c->stage_w) {
+    if (stage_w) {
         CHECK(ensure_smem(c, k_pass_a<V, EQ, EX, DF, VI, true>, smem));
         k_pass_a<V, EQ, EX, DF, VI, true><<<grid, 128, smem, c->stream>>>(a);
     } else {
@@ -1071,7 +1079,7 @@ static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bo
     PassAArgs a{};
     a.op = c->fwd.view();
     a.n_slices = c->fwd.nslices;
-    a.buf_bytes = warp_buf_bytes(c->fwd, c->stage_w);
+    a.buf_bytes = warp_buf_bytes(c->fwd, stage_whole_slice(c, c->fwd, c->stage_w));
     a.pf_dist = c->pf_dist;
     a.dummy = (int)c->n_tot;
     a.u = c->u.p;
@@ -1109,7 +1117,8 @@ static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bo
 static int launch_pass_b(mft_ctx *c)
 {
     ScopedTimer t(c, MFT_K_PASS_B);
-    PassBArgs a{c->tra.view(), c->g.p, c->du.p, c->n_local, c->tra.nslices, warp_buf_bytes(c->tra, c->stage_w_b), c->pf_dist, (int)c->n_tot};
+    const bool stage_b = stage_whole_slice(c, c->tra, c->stage_w_b);
+    PassBArgs a{c->tra.view(), c->g.p, c->du.p, c->n_local, c->tra.nslices, warp_buf_bytes(c->tra, stage_b), c->pf_dist, (int)c->n_tot};
     const int grid = (int)((a.n_slices + 3) / 4);
     const int smem = 4 * a.buf_bytes;
 #define PB(EX, ST)                                                   \
@@ -1118,9 +1127,9 @@ static int launch_pass_b(mft_ctx *c)
         k_pass_b<4, EX, ST><<<grid, 128, smem, c->stream>>>(a);      \
     } while (0)
     if (c->exact) {
-        if (c->stage_w_b) PB(true, true); else PB(true, false);
+        if (stage_b) PB(true, true); else PB(true, false);
     } else {
-        if (c->stage_w_b) PB(false, true); else PB(false, false);
+        if (stage_b) PB(false, true); else PB(false, false);
     }
 #undef PB
     c->launches++;
@@ -1131,7 +1140,8 @@ static int launch_pass_b(mft_ctx *c)
 static int launch_spmv(mft_ctx *c, const Source *s)
 {
     ScopedTimer t(c, MFT_K_OTHER);
-    SpmvArgs a{s->hv.view(), c->u.p, c->du.p, c->n_local, s->hv.nslices, warp_buf_bytes(s->hv, c->stage_w), c->pf_dist, (int)c->n_tot, -s->gamma};
+    const bool stage_s = stage_whole_slice(c, s->hv, c->stage_w);
+    SpmvArgs a{s->hv.view(), c->u.p, c->du.p, c->n_local, s->hv.nslices, warp_buf_bytes(s->hv, stage_s), c->pf_dist, (int)c->n_tot, -s->gamma};
     const int grid = (int)((a.n_slices + 3) / 4);
     const int smem = 4 * a.buf_bytes;
     if (smem > 200 * 1024) return fail(MFT_ENOTSUP, "hyperviscosity operator rows too long (%d) for the shared-memory staging", s->hv.maxw);
@@ -1141,11 +1151,11 @@ static int launch_spmv(mft_ctx *c, const Source *s)
         k_spmv_accum<VV, EX, ST><<<grid, 128, smem, c->stream>>>(a);   \
     } while (0)
     if (c->V == 4) {
-        if (c->exact) { if (c->stage_w) SP(4, true, true); else SP(4, true, false); }
-        else { if (c->stage_w) SP(4, false, true); else SP(4, false, false); }
+        if (c->exact) { if (stage_s) SP(4, true, true); else SP(4, true, false); }
+        else { if (stage_s) SP(4, false, true); else SP(4, false, false); }
     } else {
-        if (c->exact) { if (c->stage_w) SP(1, true, true); else SP(1, true, false); }
-        else { if (c->stage_w) SP(1, false, true); else SP(1, false, false); }
+        if (c->exact) { if (stage_s) SP(1, true, true); else SP(1, true, false); }
+        else { if (stage_s) SP(1, false, true); else SP(1, false, false); }
     }
 #undef SP
     c->launches++;

@@ -323,3 +323,50 @@ def test_error_paths():
     u = np.zeros((1, 10))
     assert lib.mft_rhs(ctx, 0.0, m._lib.soa_ptrs(u), m._lib.soa_ptrs(u.copy()), 0) == -1
     assert lib.mft_ctx_destroy(ctx) == 0
+
+
+def test_ell_operator_input_equals_csc_input(fx):
+    """mft_set_operator_ell (neighbour / weight tables) and mft_set_operator_csc (Julia CSC fields) build the same device
+    operator: identical rhs! bit for bit (Euler + upwind viscosity exercises D and D')."""
+    import ctypes as C
+
+    m = _mft()
+    L = m._lib
+    lib = m.load()
+    mk = lambda m_, s, e, d: dict(rv=m_.SourceUpwindViscosityTominec(s, e, d))
+    m, semi = _semi(fx, sources=mk, ic=cases.ic_smooth_euler)
+    u = cases.ic_smooth_euler(fx["points"], 0.0) * 1.01
+    du_csc = np.empty_like(u)
+    m.rhs_(du_csc, u.copy(), semi, 0.0)
+    # same problem through the ELL entry point
+    nb = fx["nb"]
+    n, k = nb.shape
+    Dx, Dy = (A.tocsr() for A in fx["ops"])
+    wx = np.empty((n, k))
+    wy = np.empty((n, k))
+    for i in range(n):
+        lx = dict(zip(Dx.indices[Dx.indptr[i]:Dx.indptr[i + 1]], Dx.data[Dx.indptr[i]:Dx.indptr[i + 1]]))
+        ly = dict(zip(Dy.indices[Dy.indptr[i]:Dy.indptr[i + 1]], Dy.data[Dy.indptr[i]:Dy.indptr[i + 1]]))
+        wx[i] = [lx[j] for j in nb[i]]
+        wy[i] = [ly[j] for j in nb[i]]
+    ctx = C.c_void_p()
+    L.check(lib.mft_ctx_create(C.byref(ctx), 0, n, 0, 4, 2, k))
+    g = np.array([cases.GAMMA])
+    L.check(lib.mft_set_equation(ctx, L.EQ_EULER2D, L.ptr(g), 1))
+    nbr1 = np.ascontiguousarray(nb + 1)
+    L.check(lib.mft_set_operator_ell(ctx, L.ptr(nbr1), L.ptr(wx), L.ptr(wy)))
+    for name, bc, tag in semi._bc_groups:
+        idx1 = np.ascontiguousarray(tag.idx + 1)
+        nrm = np.ascontiguousarray(tag.normals)
+        vals = None
+        if bc.kind == L.BC_DIRICHLET:
+            vals = np.ascontiguousarray(cases.ic_smooth_euler(fx["points"][tag.idx], 0.0))
+        L.check(lib.mft_add_boundary(ctx, bc.kind, len(idx1), L.ptr(idx1), L.ptr(nrm), L.ptr(vals)))
+    prm = np.array([1.0, fx["dx_avg"]])
+    L.check(lib.mft_add_source(ctx, L.SRC_UPWIND, L.ptr(prm), 2, None, None, None))
+    uu = u.copy()
+    du_ell = np.empty_like(u)
+    L.check(lib.mft_rhs(ctx, 0.0, L.soa_ptrs(uu), L.soa_ptrs(du_ell), L.MEM_HOST))
+    L.check(lib.mft_ctx_destroy(ctx))
+    assert np.array_equal(du_ell, du_csc)
+    semi.close()
