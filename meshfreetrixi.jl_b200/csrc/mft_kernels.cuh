@@ -166,6 +166,14 @@ __device__ __forceinline__ void st_vec(Vec<2> *p, const Vec<2> &v)
     *reinterpret_cast<double2 *>(p) = make_double2(v.a[0], v.a[1]);
 }
 
+// read-once operator data (weights read straight from global memory): do not allocate in L1, leave it to the gathers
+__device__ __forceinline__ double ld_stream(const double *p)
+{
+    double v;
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 // Julia max(::Float64, ::Float64): NaN-propagating
 __device__ __forceinline__ double jl_max(double a, double b)
 {
@@ -586,7 +594,14 @@ __global__ void __launch_bounds__(128, 4) k_pass_b(const PassBArgs A)
             const bool ok = c0 + b < width;
             const int cc = ok ? c0 + b : width - 1;
             const int j = ok ? ip[cc * kSlice] : A.dummy;
-            const double w1 = wxp[cc * kSlice], w2 = wyp[cc * kSlice];
+            double w1, w2;
+            if constexpr (STAGE_W) {
+                w1 = wxp[cc * kSlice];
+                w2 = wyp[cc * kSlice];
+            } else {
+                w1 = ld_stream(wxp + cc * kSlice);
+                w2 = ld_stream(wyp + cc * kSlice);
+            }
             wa[b] = ok ? w1 : 0.0;
             wb[b] = ok ? w2 : 0.0;
             gj[b] = ld_ro(g + j);
