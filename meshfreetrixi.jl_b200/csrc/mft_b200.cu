@@ -1704,12 +1704,14 @@ static int p2p_norms_part(mft_ctx *c, int part)
     if (part == 0) {
         k_p2p_sum<<<c->red_blocks, 256, 0, c->stream>>>(u, n, c->partial.p, c->peers_dev, L);
     } else if (part == 1) {
+        k_p2p_wait_norms<<<1, 32, 0, c->stream>>>(c->peers_dev, L, 0, nullptr);
+        c->launches++;
         const double ng = (double)c->n_global;
         const double divisor = c->mean_div_vn ? (double)V * ng : ng;
         if (c->max_lex) k_p2p_maxdev<true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, divisor, c->partial.p, c->peers_dev, L, c->stats.p + V);
         else k_p2p_maxdev<false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, divisor, c->partial.p, c->peers_dev, L, c->stats.p + V);
     } else {
-        k_p2p_collect_max<<<1, 32, 0, c->stream>>>(c->peers_dev, L, c->gather_buf.p + (int64_t)c->nranks * V);
+        k_p2p_wait_norms<<<1, 32, 0, c->stream>>>(c->peers_dev, L, 1, c->gather_buf.p + (int64_t)c->nranks * V);
     }
     c->launches++;
     LAUNCH_CHECK();

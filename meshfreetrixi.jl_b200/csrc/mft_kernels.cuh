@@ -1297,10 +1297,10 @@ __global__ void __launch_bounds__(256) k_p2p_maxdev(const Vec<4> *__restrict__ u
                                                   P2PPeers P, P2PLocal *L, double *mean_out)
 {
     constexpr int V = 4;
+    // the sums of all ranks have arrived: k_p2p_wait_norms<<<>>> runs right before this kernel (one polling thread
+    // per flag instead of a system-scope acquire in every block)
     const unsigned long long en = L->epoch_n + 1;
     const int par = (int)(en & 1);
-    if (threadIdx.x == 0) p2p_wait_all(P, L, 0, par, en);
-    __syncthreads();
     double m[V], best[V];
     const P2PWindow *win = P.win[P.rank];
 #pragma unroll
@@ -1371,16 +1371,17 @@ __global__ void __launch_bounds__(256) k_p2p_maxdev(const Vec<4> *__restrict__ u
     }
 }
 
-// one thread waits for the max-deviation candidates of all ranks and copies them to a local, L1-cacheable buffer that
-// pass A then reads like the NCCL-gathered one
-__global__ void k_p2p_collect_max(P2PPeers P, P2PLocal *L, double *out /* nranks x 4 */)
+// one polling thread per rank flag: which = 0 waits for the partial sums of norms epoch epoch_n+1,
+// which = 1 waits for the max-deviation candidates of epoch epoch_n and stages them in a local buffer for pass A
+__global__ void k_p2p_wait_norms(P2PPeers P, P2PLocal *L, int which, double *out /* nranks x 4, which == 1 */)
 {
-    if (threadIdx.x == 0) {
-        const unsigned long long en = L->epoch_n;
-        const int par = (int)(en & 1);
-        p2p_wait_all(P, L, 1, par, en);
-        const P2PWindow *win = P.win[P.rank];
-        for (int r = 0; r < P.nranks; ++r)
+    const unsigned long long en = which == 0 ? L->epoch_n + 1 : L->epoch_n;
+    const int par = (int)(en & 1);
+    const P2PWindow *win = P.win[P.rank];
+    const int r = threadIdx.x;
+    if (r < P.nranks) {
+        spin_until(which == 0 ? &win->sum_flag[par][r] : &win->max_flag[par][r], en, &L->error);
+        if (which == 1)
             for (int v = 0; v < 4; ++v) out[r * 4 + v] = __ldcv(&win->maxs[par][r][v]);
     }
 }
