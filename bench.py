@@ -250,8 +250,11 @@ def run_ours(args):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = N * e2e_calls / e2e_s
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": STAGES * 32 * N, "d2h_bytes_per_step": STAGES * 64 * N,
-           "call": "mft_rhs(MFT_MEM_HOST): u H2D, rhs!, u and du D2H, pinned host arrays", "calls_timed": e2e_calls}
+    n_touched = sum(len(domain.boundary_tags[k].idx) for k in names) + (u0.shape[1] - n_own if multi else 0)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": STAGES * 32 * N,
+           "d2h_bytes_per_step": STAGES * 32 * (N + n_touched * world),
+           "call": "mft_rhs(MFT_MEM_HOST): u H2D, rhs!, du D2H + the rows of u that rhs! changes (boundary points, halo), "
+                   "pinned host arrays", "calls_timed": e2e_calls}
 
     # ---- CPU baseline: the oracle's C port of the reference structure, bounded sample, rank 0, N=1 only -----------
     cpu = None

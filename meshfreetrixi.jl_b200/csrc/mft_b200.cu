@@ -156,6 +156,12 @@ struct mft_ctx {
     DevBuf<double> partial, stats;  // stats: sum[V], mean[V], norms[V]
     DevBuf<unsigned int> ticket;
     // merged boundary table (all groups, one launch) when no point is in two groups
+    // rows of u that rhs! can change (boundary points, halo tail): the only part of u a host caller gets back
+    std::vector<int64_t> touched_caller;
+    DevBuf<int> touched_dev;
+    DevBuf<double> touched_buf;
+    double *touched_host = nullptr;
+    std::vector<std::vector<int64_t>> bc_caller_rows;
     bool bc_merged = false;
     int64_t bc_total = 0;
     std::vector<int64_t> bc_group_off;
@@ -320,6 +326,9 @@ extern "C" int mft_ctx_destroy(mft_ctx *c)
     DevBuf<double> *bufs[] = {&c->u, &c->du, &c->uprev, &c->g, &c->approx_du, &c->stage_soa, &c->eps, &c->eps_uw,
                               &c->eps_rv, &c->eps_c, &c->residual, &c->partial, &c->stats, &c->send_buf, &c->gather_buf};
     for (auto *b : bufs) b->release();
+    if (c->touched_host) cudaFreeHost(c->touched_host);
+    c->touched_dev.release();
+    c->touched_buf.release();
     for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
     c->p2p_window.release();
     c->p2p_local.release();
@@ -508,6 +517,9 @@ extern "C" int mft_add_boundary(mft_ctx *c, int kind, int64_t nb, const int64_t 
     }
     // keep caller-numbered indices on the host for the finalize remap
     c->bcs.push_back(g);
+    c->bc_caller_rows.emplace_back();
+    if (kind != MFT_BC_DO_NOTHING)
+        for (int64_t j = 0; j < nb; ++j) c->bc_caller_rows.back().push_back(idx1[j] - 1);
     return MFT_OK;
 }
 
@@ -829,6 +841,19 @@ extern "C" int mft_finalize(mft_ctx *c)
             CHECK(c->bc_normals.upload(nrm));
             CHECK(c->bc_values.upload(val));
         }
+    }
+    {
+        std::vector<int64_t> rows;
+        for (auto &v : c->bc_caller_rows) rows.insert(rows.end(), v.begin(), v.end());
+        for (int64_t h = c->n_local; h < n; ++h) rows.push_back(h);
+        std::sort(rows.begin(), rows.end());
+        rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+        c->touched_caller = rows;
+        std::vector<int> dev(rows.size());
+        for (size_t i = 0; i < rows.size(); ++i) dev[i] = c->have_perm ? c->iperm[rows[i]] : (int)rows[i];
+        CHECK(c->touched_dev.upload(dev));
+        CHECK(c->touched_buf.alloc(std::max<int64_t>(1, (int64_t)rows.size()) * c->V));
+        CU(cudaHostAlloc((void **)&c->touched_host, sizeof(double) * std::max<size_t>(1, rows.size()) * c->V, cudaHostAllocDefault));
     }
     CHECK(c->uprev.alloc(n * c->V));
     // free host staging
@@ -1248,9 +1273,26 @@ extern "C" int mft_rhs(mft_ctx *c, double t, double *const *u_soa, double *const
     }
     CHECK(rhs_device(c, t));
     if (mem == MFT_MEM_HOST) {
-        CHECK(download_soa(c, c->u.p, u_soa));
-        CU(cudaStreamSynchronize(c->stream));  // stage_soa is reused by the next download
+        // rhs! changes u only at boundary points (strong BCs) and in the halo tail: bring back just those rows
+        const int64_t m = (int64_t)c->touched_caller.size();
+        if (m > 0) {
+            ScopedTimer tm(c, MFT_K_OTHER);
+            if (c->V == 4)
+                k_gather_rows<4><<<grid_for(m, 256), 256, 0, c->stream>>>(reinterpret_cast<const Vec<4> *>(c->u.p), c->touched_dev.p, c->touched_buf.p, m);
+            else
+                k_gather_rows<1><<<grid_for(m, 256), 256, 0, c->stream>>>(reinterpret_cast<const Vec<1> *>(c->u.p), c->touched_dev.p, c->touched_buf.p, m);
+            c->launches++;
+            LAUNCH_CHECK();
+            CU(cudaMemcpyAsync(c->touched_host, c->touched_buf.p, sizeof(double) * m * c->V, cudaMemcpyDeviceToHost, c->stream));
+        }
         CHECK(download_soa(c, c->du.p, du_soa));
+        CU(cudaStreamSynchronize(c->stream));
+        for (int v = 0; v < c->V; ++v) {
+            double *dst = u_soa[v];
+            const double *src = c->touched_host + (int64_t)v * m;
+            for (int64_t i = 0; i < m; ++i) dst[c->touched_caller[i]] = src[i];
+        }
+        return MFT_OK;
     }
     CU(cudaStreamSynchronize(c->stream));
     return MFT_OK;

@@ -1094,6 +1094,16 @@ __global__ void k_unpack(const Vec<V> *__restrict__ in, const int *__restrict__ 
 #pragma unroll
     for (int k = 0; k < V; ++k) soa[(int64_t)k * ld + dst] = v.a[k];
 }
+// compact gather of a few rows (boundary + halo points) into an SoA buffer: buf[v*m + i] = field[rows[i]].a[v]
+template <int V>
+__global__ void k_gather_rows(const Vec<V> *__restrict__ field, const int *__restrict__ rows, double *buf, int64_t m)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const Vec<V> v = field[rows[i]];
+#pragma unroll
+    for (int k = 0; k < V; ++k) buf[(int64_t)k * m + i] = v.a[k];
+}
 __global__ void k_unpack_scalar(const double *__restrict__ in, const int *__restrict__ perm, double *out, int64_t n)
 {
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
