@@ -138,7 +138,7 @@ def run_ours(args):
                                                                 stage_weights=int(args.stage_weights),
                                                                 cuda_graph=int(args.graph),
                                                                 single_sweep_exact=bool(args.single_sweep),
-                                                                exchange=args.exchange))
+                                                                exchange=args.exchange, pair_rows=int(args.pair_rows)))
     names = dict(left=1, right=2, bottom=3, top=4)
     t_setup = time.time()
     domain = m.ParallelPointCloudDomain(solver, cl, names, comm) if multi else m.PointCloudDomain(solver, cl, names)
@@ -384,9 +384,10 @@ def main():
     ap.add_argument("--n-side", type=int, default=1024, help="lattice side; 1024 -> the 1M-point cloud of configs[1]")
     ap.add_argument("--ref-n-side", type=int, default=512, help="lattice side of the bounded sample the CPU arm runs")
     ap.add_argument("--fma", action="store_true", help="single-sweep FMA summation instead of the reference order")
-    ap.add_argument("--stage-weights", type=int, default=1, help="1: whole operator slices staged in smem; 0: indices only")
+    ap.add_argument("--stage-weights", type=int, default=5, help="bit0: pass A slices staged in smem, bit1: pass B, bit2: one weight buffer refilled between the x and y sweeps")
     ap.add_argument("--graph", type=int, default=1, help="0 eager, 1 CUDA-graph replay on one GPU, 2 also multi-rank")
     ap.add_argument("--single-sweep", type=int, default=0, help="k=20 single-sweep exact pass A (register-parked y-products)")
+    ap.add_argument("--pair-rows", type=int, default=1, help="row-pair (union stencil) operator layout (bit0: pass B, bit1: pass A)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo exchange mechanism")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

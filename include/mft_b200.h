@@ -71,12 +71,17 @@ typedef struct mft_ctx mft_ctx;
                                       (NCCL calls captured into the graph); 0: always eager launches                      */
 #define MFT_OPT_STAGE_WEIGHTS 5    /* bit 0 (forward operator, pass A) / bit 1 (transposed operator, pass B): 1 = a warp bulk-copies
                                       its whole operator slice (indices + weights) into shared memory, 0 = indices only, weights
-                                      by coalesced loads + L2 bulk prefetch.  Default 1 (measured best: pass A staged, pass B not) */
+                                      by coalesced loads + L2 bulk prefetch.  bit 2: exact-order pass A keeps ONE weight buffer and refills it with wy
+                                      after the x sweep (smaller footprint -> larger L1).  Default 5 (measured best). */
 #define MFT_OPT_REFINE_ORDER 7     /* 1 (default 0): within blocks of 256 device rows, order rows by D' row length
                                       (near-uniform transposed-ELL slices); the caller-visible numbering is unaffected */
 #define MFT_OPT_SINGLE_SWEEP_EXACT 8/* 1: for the default 20-wide stencil use the single-sweep exact kernel (y-products parked in registers:
                                       one gather + one flux per neighbour, but 255 registers -> 8 warps/SM; measured 20 % slower);
                                       0 (default): the two-sweep exact kernel.  Same results bit for bit.                       */
+#define MFT_OPT_PAIR_ROWS 9        /* bit 0: transposed operator (pass B), bit 1: forward operator (pass A, measured slower: FP64/latency-bound); default 1.
+                                      An operator is stored per PAIR of consecutive rows (union of the two
+                                      D' rows, zero weight where a row lacks an entry): each shared neighbour record is gathered once
+                                      for both rows.  Same sums bit for bit.  0: one row per thread.                        */
 #define MFT_OPT_PREFETCH_DISTANCE 6/* slices ahead for the L2 prefetch of the weight blocks (STAGE_WEIGHTS = 0)        */
 
 /* fields (mft_get_field): caches of create_tominec_rv_cache, hyperviscosity.jl:202-244 */

@@ -21,6 +21,7 @@ SRC_HV_FLYER, SRC_HV_TOMINEC, SRC_UPWIND, SRC_RESIDUAL = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 OPT_EXACT_ORDER, OPT_MEAN_DIVISOR_VN, OPT_MAX_LEXICOGRAPHIC, OPT_DIAGNOSTICS, OPT_CUDA_GRAPH = 0, 1, 2, 3, 4
 OPT_STAGE_WEIGHTS, OPT_PREFETCH_DISTANCE, OPT_REFINE_ORDER, OPT_SINGLE_SWEEP_EXACT = 5, 6, 7, 8
+OPT_PAIR_ROWS = 9
 FIELD_EPS, FIELD_EPS_UW, FIELD_EPS_RV, FIELD_EPS_C, FIELD_RESIDUAL, FIELD_APPROX_DU, FIELD_NORMS = range(7)
 SSPRK33 = 0
 K_PASS_A, K_PASS_B, K_REDUCE, K_STAGE, K_BC, K_OTHER = range(6)

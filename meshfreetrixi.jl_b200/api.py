@@ -64,9 +64,10 @@ class RBFFDEngineCUDA:
     diagnostics: bool = False          # keep eps/eps_uw/eps_rv/residual on device for inspection
     mean_divisor_vn: bool = True       # ode_mean divides by V*N (recursive_length)
     max_lexicographic: bool = True     # maximum(::StructArray{SVector}) is a lexicographic max
-    stage_weights: int = 1             # bit0: pass A, bit1: pass B -- bulk-copy whole operator slices to smem
+    stage_weights: int = 5             # bit0: pass A, bit1: pass B -- bulk-copy whole operator slices to smem
     cuda_graph: int = 1                # 1: graph replay of SSPRK steps on one GPU; 2: also multi-rank; 0: eager
     exchange: str = "p2p"              # multi-GPU halo exchange: "p2p" (CUDA-IPC peer memory over NVLink) or "nccl"
+    pair_rows: int = 1                 # row-pair (union stencil) layout: bit0 transposed operator (pass B), bit1 forward (pass A)
     single_sweep_exact: bool = False   # k=20: exact-order pass A in one sweep (y-products parked in registers)
     refine_order: bool = False         # order rows inside 256-row blocks by D' row length (less padding, worse gather locality)
 
@@ -322,6 +323,7 @@ class SemidiscretizationHyperbolic:
         L.check(lib.mft_set_option(ctx, L.OPT_REFINE_ORDER, float(eng.refine_order)))
         L.check(lib.mft_set_option(ctx, L.OPT_CUDA_GRAPH, float(eng.cuda_graph)))
         L.check(lib.mft_set_option(ctx, L.OPT_SINGLE_SWEEP_EXACT, float(eng.single_sweep_exact)))
+        L.check(lib.mft_set_option(ctx, L.OPT_PAIR_ROWS, float(eng.pair_rows)))
         if part is not None:
             # local numbering is already [owned along the curve ; halo]; sums must run in ascending GLOBAL column order
             self.perm = None

@@ -139,7 +139,9 @@ struct mft_ctx {
     HostCsc host_ops[2];
     Csr2 host_ell;  // from mft_set_operator_ell
     bool have_ell_input = false;
-    DevEll fwd, tra;
+    DevEll fwd, fwd_pair, tra, tra_pair;
+    int pair_rows = 1;
+    int two_phase = 1;
     // bcs, sources
     std::vector<BcGroup *> bcs;
     std::vector<Source *> srcs;
@@ -322,6 +324,8 @@ extern "C" int mft_ctx_destroy(mft_ctx *c)
     }
     c->fwd.release();
     c->tra.release();
+    c->tra_pair.release();
+    c->fwd_pair.release();
     for (auto &h : c->hist) h.release();
     DevBuf<double> *bufs[] = {&c->u, &c->du, &c->uprev, &c->g, &c->approx_du, &c->stage_soa, &c->eps, &c->eps_uw,
                               &c->eps_rv, &c->eps_c, &c->residual, &c->partial, &c->stats, &c->send_buf, &c->gather_buf};
@@ -389,10 +393,11 @@ extern "C" int mft_set_option(mft_ctx *c, int option, double value)
     case MFT_OPT_MAX_LEXICOGRAPHIC: c->max_lex = value != 0; break;
     case MFT_OPT_DIAGNOSTICS: c->diagnostics = value != 0; break;
     case MFT_OPT_CUDA_GRAPH: c->use_graphs = (int)value; break;
-    case MFT_OPT_STAGE_WEIGHTS: c->stage_w = ((int)value & 1) != 0; c->stage_w_b = ((int)value & 2) != 0; break;
+    case MFT_OPT_STAGE_WEIGHTS: c->stage_w = ((int)value & 1) != 0; c->stage_w_b = ((int)value & 2) != 0; c->two_phase = ((int)value & 4) != 0; break;
     case MFT_OPT_PREFETCH_DISTANCE: c->pf_dist = (int)value; break;
     case MFT_OPT_REFINE_ORDER: c->refine_order = value != 0; break;
     case MFT_OPT_SINGLE_SWEEP_EXACT: c->kfix_ok = value != 0; break;
+    case MFT_OPT_PAIR_ROWS: c->pair_rows = (int)value; break;
     default: return fail(MFT_EINVAL, "mft_set_option: unknown option %d", option);
     }
     return MFT_OK;
@@ -708,6 +713,76 @@ static int build_ell(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, bool paired, 
     return MFT_OK;
 }
 
+// pair-slice blobs: device rows (2l, 2l+1) share one lane; the lane walks the union of the two rows' entries in the
+// reference order (ascending key), with a zero weight where a row lacks the entry
+static int build_ell_pairs(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, DevEll &out)
+{
+    const int64_t rows_per_slice = 2 * kSlice;
+    const int64_t nsl = (nrows_dev + rows_per_slice - 1) / rows_per_slice;
+    auto caller_row = [&](int64_t d) -> int64_t { return c->have_perm ? c->perm[d] : d; };
+    auto key = [&](int32_t col) -> int64_t { return c->keys.empty() ? (int64_t)col : c->keys[col]; };
+    struct Ent { int32_t col; double w[4]; };
+    std::vector<std::vector<Ent>> lists((size_t)nsl * kSlice);
+    std::vector<int> off(nsl + 1, 0);
+    int maxw = 0;
+    int64_t nnz = 0;
+    for (int64_t s = 0; s < nsl; ++s) {
+        int w = 0;
+        for (int l = 0; l < kSlice; ++l) {
+            const int64_t dA = s * rows_per_slice + 2 * l, dB = dA + 1;
+            std::vector<Ent> &U = lists[s * kSlice + l];
+            int64_t pa = 0, ea = 0, pb = 0, eb = 0;
+            if (dA < nrows_dev) { const int64_t r = caller_row(dA); pa = A.ptr[r]; ea = A.ptr[r + 1]; }
+            if (dB < nrows_dev) { const int64_t r = caller_row(dB); pb = A.ptr[r]; eb = A.ptr[r + 1]; }
+            nnz += (ea - pa) + (eb - pb);
+            while (pa < ea || pb < eb) {
+                Ent e{};
+                const bool takeA = pa < ea && (pb >= eb || key(A.col[pa]) <= key(A.col[pb]));
+                const bool takeB = pb < eb && (pa >= ea || key(A.col[pb]) <= key(A.col[pa]));
+                if (takeA && takeB && A.col[pa] != A.col[pb]) {
+                    // equal keys on different columns cannot happen for a permutation of keys; fall back to A first
+                    e.col = A.col[pa]; e.w[0] = A.wx[pa]; e.w[1] = A.wy[pa]; ++pa;
+                } else if (takeA && takeB) {
+                    e.col = A.col[pa]; e.w[0] = A.wx[pa]; e.w[1] = A.wy[pa]; e.w[2] = A.wx[pb]; e.w[3] = A.wy[pb]; ++pa; ++pb;
+                } else if (takeA) {
+                    e.col = A.col[pa]; e.w[0] = A.wx[pa]; e.w[1] = A.wy[pa]; ++pa;
+                } else {
+                    e.col = A.col[pb]; e.w[2] = A.wx[pb]; e.w[3] = A.wy[pb]; ++pb;
+                }
+                U.push_back(e);
+            }
+            w = std::max(w, (int)U.size());
+        }
+        maxw = std::max(maxw, w);
+        off[s + 1] = off[s] + w;
+    }
+    const int64_t ncols = off[nsl];
+    std::vector<unsigned char> blob((size_t)ncols * kColBytesPair + 128, 0);
+    for (int64_t s = 0; s < nsl; ++s) {
+        const int w = off[s + 1] - off[s];
+        unsigned char *b = blob.data() + (size_t)off[s] * kColBytesPair;
+        int *idx = reinterpret_cast<int *>(b);
+        double *wq = reinterpret_cast<double *>(b + (size_t)w * kSlice * 4);
+        for (int q = 0; q < w * kSlice; ++q) idx[q] = (int)c->n_tot;
+        for (int l = 0; l < kSlice; ++l) {
+            const std::vector<Ent> &U = lists[s * kSlice + l];
+            for (size_t cpos = 0; cpos < U.size(); ++cpos) {
+                const size_t at = cpos * kSlice + l;
+                idx[at] = c->have_perm ? c->iperm[U[cpos].col] : (int)U[cpos].col;
+                for (int q = 0; q < 4; ++q) wq[(size_t)q * w * kSlice + at] = U[cpos].w[q];
+            }
+        }
+    }
+    out.nslices = (int)nsl;
+    out.colb = kColBytesPair;
+    out.maxw = maxw;
+    out.ncols_total = ncols;
+    out.nnz = nnz;
+    CHECK(out.blob.upload(blob));
+    CHECK(out.off.upload(off));
+    return MFT_OK;
+}
+
 static bool has_visc(const mft_ctx *c)
 {
     for (auto *s : c->srcs)
@@ -763,8 +838,10 @@ extern "C" int mft_finalize(mft_ctx *c)
     // drop halo rows of the forward operator: only owned rows are computed here
     if (c->have_perm) CHECK(c->d_perm.upload(std::vector<int>(c->perm.begin(), c->perm.end())));
     CHECK(build_ell(c, F, c->n_local, true, c->fwd));
+    if ((c->pair_rows & 2) && c->V == 4) CHECK(build_ell_pairs(c, F, c->n_local, c->fwd_pair));
     if (has_visc(c)) {
-        CHECK(build_ell(c, T, c->n_local, true, c->tra));
+        if ((c->pair_rows & 1) && c->V == 4) CHECK(build_ell_pairs(c, T, c->n_local, c->tra_pair));
+        else CHECK(build_ell(c, T, c->n_local, true, c->tra));
         CHECK(c->g.alloc((n + 1) * 2 * c->V));  // + zero dummy record
         CU(cudaMemset(c->g.p, 0, sizeof(double) * (n + 1) * 2 * c->V));
     }
@@ -1102,9 +1179,12 @@ static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bo
 {
     ScopedTimer t(c, MFT_K_PASS_A);
     PassAArgs a{};
+    const bool use_pair = do_flux && c->V == 4 && c->fwd_pair.blob.p != nullptr;
     a.op = c->fwd.view();
     a.n_slices = c->fwd.nslices;
     a.buf_bytes = warp_buf_bytes(c->fwd, stage_whole_slice(c, c->fwd, c->stage_w));
+    a.two_phase = c->two_phase && c->exact && stage_whole_slice(c, c->fwd, c->stage_w);
+    if (a.two_phase) a.buf_bytes = ((std::max(c->fwd.maxw, 1) * kSlice * 12 + 127) / 128) * 128;
     a.pf_dist = c->pf_dist;
     a.dummy = (int)c->n_tot;
     a.u = c->u.p;
@@ -1135,6 +1215,32 @@ static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bo
         a.eps_c = c->eps_c.p;
         a.residual = c->residual.p;
     }
+    if (use_pair) {
+        const DevEll &e = c->fwd_pair;
+        a.op = e.view();
+        a.n_slices = e.nslices;
+        a.buf_bytes = ((std::max(e.maxw, 1) * kSlice * 4 + 127) / 128) * 128;
+        const int grid = (int)((a.n_slices + 3) / 4);
+        const int smem = 4 * a.buf_bytes;
+#define PAP(EX, VI)                                                                      \
+    do {                                                                                 \
+        CHECK(ensure_smem(c, k_pass_a_pair<4, EQ_EULER2D, EX, VI>, smem));               \
+        k_pass_a_pair<4, EQ_EULER2D, EX, VI><<<grid, 128, smem, c->stream>>>(a);         \
+    } while (0)
+        if (c->exact) {
+            if (visc == VISC_NONE) PAP(true, VISC_NONE);
+            else if (visc == VISC_UPWIND) PAP(true, VISC_UPWIND);
+            else PAP(true, VISC_RESIDUAL);
+        } else {
+            if (visc == VISC_NONE) PAP(false, VISC_NONE);
+            else if (visc == VISC_UPWIND) PAP(false, VISC_UPWIND);
+            else PAP(false, VISC_RESIDUAL);
+        }
+#undef PAP
+        c->launches++;
+        LAUNCH_CHECK();
+        return MFT_OK;
+    }
     if (c->V == 4) return launch_pass_a_t<4, EQ_EULER2D>(c, a, do_flux, visc);
     return launch_pass_a_t<1, EQ_ADVECTION2D>(c, a, do_flux, visc);
 }
@@ -1142,6 +1248,22 @@ static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bo
 static int launch_pass_b(mft_ctx *c)
 {
     ScopedTimer t(c, MFT_K_PASS_B);
+    if (c->tra_pair.blob.p) {
+        const DevEll &e = c->tra_pair;
+        PassBPairArgs a{e.view(), c->g.p, c->du.p, c->n_local, e.nslices, ((std::max(e.maxw, 1) * kSlice * 4 + 127) / 128) * 128, (int)c->n_tot};
+        const int grid = (int)((a.n_slices + 3) / 4);
+        const int smem = 4 * a.buf_bytes;
+        if (c->exact) {
+            CHECK(ensure_smem(c, k_pass_b_pair<4, true>, smem));
+            k_pass_b_pair<4, true><<<grid, 128, smem, c->stream>>>(a);
+        } else {
+            CHECK(ensure_smem(c, k_pass_b_pair<4, false>, smem));
+            k_pass_b_pair<4, false><<<grid, 128, smem, c->stream>>>(a);
+        }
+        c->launches++;
+        LAUNCH_CHECK();
+        return MFT_OK;
+    }
     const bool stage_b = stage_whole_slice(c, c->tra, c->stage_w_b);
     PassBArgs a{c->tra.view(), c->g.p, c->du.p, c->n_local, c->tra.nslices, warp_buf_bytes(c->tra, stage_b), c->pf_dist, (int)c->n_tot};
     const int grid = (int)((a.n_slices + 3) / 4);

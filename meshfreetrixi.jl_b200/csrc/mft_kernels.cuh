@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace mft {
 
@@ -37,6 +38,7 @@ struct EllBlob {
 };
 constexpr int kColBytes2 = kSlice * (4 + 8 + 8);  // 640: paired (Dx,Dy) operator
 constexpr int kColBytes1 = kSlice * (4 + 8);      // 384: single-weight operator
+constexpr int kColBytesPair = kSlice * (4 + 4 * 8);  // 1152: row-pair operator (idx + wxA, wyA, wxB, wyB)
 
 // ---- mbarrier + bulk-async copy (TMA 1-D) -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,7 +85,7 @@ struct SliceView {
 };
 template <int COLB, bool STAGE_W>
 __device__ __forceinline__ SliceView stage_slice(const EllBlob &op, int64_t slice, int64_t n_slices, unsigned char *buf,
-                                                 uint64_t *bar, int lane, int pf_dist)
+                                                 uint64_t *bar, int lane, int pf_dist, bool two_phase = false)
 {
     const int off = op.off[slice];
     const int width = op.off[slice + 1] - off;
@@ -91,9 +93,11 @@ __device__ __forceinline__ SliceView stage_slice(const EllBlob &op, int64_t slic
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
     if (lane == 0 && width > 0) {
-        const uint32_t bytes = (uint32_t)width * (STAGE_W ? COLB : kSlice * 4);
+        // two_phase (paired operators, exact order): stage [idx | wx] now, wy replaces wx after the first sweep
+        const uint32_t bytes = (uint32_t)width * (STAGE_W ? (two_phase ? kSlice * 12 : COLB) : kSlice * 4);
         mbar_expect_tx(bar, bytes);
         bulk_g2s(buf, src, bytes, bar);
+        if (STAGE_W && two_phase) bulk_prefetch_l2(src + (size_t)width * kSlice * 12, (uint32_t)width * kSlice * 8);
         if (!STAGE_W) {
             const int64_t s2 = slice + pf_dist;
             if (s2 < n_slices) {
@@ -109,7 +113,7 @@ __device__ __forceinline__ SliceView stage_slice(const EllBlob &op, int64_t slic
     v.ip = reinterpret_cast<const int *>(buf) + lane;
     const unsigned char *wbase = STAGE_W ? buf : src;
     v.wxp = reinterpret_cast<const double *>(wbase + (size_t)width * kSlice * 4) + lane;
-    v.wyp = reinterpret_cast<const double *>(wbase + (size_t)width * kSlice * 12) + lane;
+    v.wyp = reinterpret_cast<const double *>(wbase + (size_t)width * kSlice * ((STAGE_W && two_phase) ? 4 : 12)) + lane;
     return v;
 }
 
@@ -252,6 +256,7 @@ struct PassAArgs {
     int64_t n_slices;
     int buf_bytes;  // shared-memory bytes per warp
     int pf_dist;    // L2 prefetch distance in slices
+    int two_phase;  // exact order + staged weights: one weight buffer, refilled with wy after the x sweep
     int dummy;      // index of the dummy record (one past the last point): padding / batch tails gather it
     const void *u;
     void *du;
@@ -275,6 +280,102 @@ constexpr int VISC_NONE = 0;
 constexpr int VISC_UPWIND = 1;
 constexpr int VISC_RESIDUAL = 2;
 
+// per-row epilogue of pass A: store du, evaluate the viscosity limiter (update_upwind_visc!, update_residual_visc!,
+// update_visc!, hyperviscosity.jl:246-349) and store g = eps .* (Dx u, Dy u)
+template <int V, int EQ, bool DO_FLUX, int VISC>
+__device__ __forceinline__ void pass_a_epilogue(const PassAArgs &A, int64_t row, const Vec<V> &acc, const Vec<V> &gx,
+                                                const Vec<V> &gy, const Vec<V> &ui, const Vec<V> &ad)
+{
+    if constexpr (DO_FLUX) st_vec(reinterpret_cast<Vec<V> *>(A.du) + row, acc);
+
+    if constexpr (VISC != VISC_NONE) {
+        static_assert(VISC == VISC_NONE || (EQ == EQ_EULER2D && V == 4), "viscosity sources are Euler-2D only");
+        // update_upwind_visc!  hyperviscosity.jl:246-285
+        double v1, v2, p;
+        euler_prim(A.eqp0, ui, v1, v2, p);
+        const double speed = sqrt(v1 * v1 + v2 * v2);
+        double sound;
+        if (p < 0.0 || ui.a[0] < 0.0) {
+            sound = 0.0;
+        } else {
+            sound = sqrt(A.eqp0 * p / ui.a[0]);
+        }
+        const double e_uw = A.c_uw * 0.5 * A.dx_avg * (speed + sound);
+        double e = e_uw, e_rv = 0.0, e_c = 1.0;
+        if constexpr (VISC == VISC_RESIDUAL) {
+            // update_residual_visc! :289-329 (pointwise part) and update_visc! :331-349
+            Vec<V> dui;
+            if constexpr (DO_FLUX) {
+                dui = acc;
+            } else {
+                dui = reinterpret_cast<const Vec<V> *>(A.du)[row];
+            }
+            Vec<V> res;
+#pragma unroll
+            for (int v = 0; v < V; ++v) res.a[v] = fabs(ad.a[v] - dui.a[v]);
+            double nrm[V];
+            if (A.norm_parts > 0) {
+                // global ode_maximum: combine the per-rank candidates in rank order (MPI.Allreduce(MAX), mpi.jl:76)
+#pragma unroll
+                for (int v = 0; v < V; ++v) nrm[v] = A.norms[v];
+                for (int r = 1; r < A.norm_parts; ++r) {
+                    double c[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) c[v] = A.norms[r * V + v];
+                    if (A.norm_lex) {
+                        if (lex_less<V>(nrm, c)) {
+#pragma unroll
+                            for (int v = 0; v < V; ++v) nrm[v] = c[v];
+                        }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) nrm[v] = jl_max(nrm[v], c[v]);
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < V; ++v) nrm[v] = nrm[v] == 0.0 ? kEps : nrm[v];
+                if (A.norms_out && row == 0) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) A.norms_out[v] = nrm[v];
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) nrm[v] = A.norms[v];
+            }
+            double mx = res.a[0] / nrm[0];
+#pragma unroll
+            for (int v = 1; v < V; ++v) mx = jl_max(mx, res.a[v] / nrm[v]);
+            e_rv = 0.5 * A.c_rv * (A.dx_avg * A.dx_avg) * mx;
+            if (isnan(e_rv) || isinf(e_rv) || A.success_iter_zero) {
+                if (isnan(e_uw) || isinf(e_uw)) {
+                    e = kEps;
+                    e_c = 2.0;
+                } else {
+                    e = e_uw;
+                    e_c = 1.0;
+                }
+            } else {
+                e = e_rv < e_uw ? e_rv : e_uw;
+                e_c = e_rv < e_uw ? 0.0 : 1.0;
+            }
+            if (A.residual) st_vec(reinterpret_cast<Vec<V> *>(A.residual) + row, res);
+        }
+        if (A.eps) {
+            A.eps[row] = e;
+            A.eps_uw[row] = e_uw;
+            A.eps_rv[row] = e_rv;
+            A.eps_c[row] = e_c;
+        }
+        Vec<2 * V> gout;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            gout.a[v] = e * gx.a[v];
+            gout.a[V + v] = e * gy.a[v];
+        }
+        st_vec(reinterpret_cast<Vec<2 * V> *>(A.g) + row, gout);
+    }
+}
+
 // KFIX > 0: every slice is exactly KFIX columns wide (the forward operator of a kNN cloud) and the kernel is the
 // single-sweep exact variant: the x-chain runs in the sweep while the y-products w_y * (-G) are parked in registers
 // (fully unrolled), then the y-chain is appended in order.  Same rounding sequence as the two-sweep form, but each
@@ -289,8 +390,9 @@ __global__ void __launch_bounds__(128, (KFIX > 0 ? 2 : 4)) k_pass_a(const PassAA
     if (slice >= A.n_slices) return;  // warps are independent: per-warp barriers only
     const int64_t row = slice * kSlice + lane;
     const bool live = row < A.n_rows;
+    const bool two_phase = EXACT && STAGE_W && KFIX == 0 && A.two_phase;
     const SliceView sv = stage_slice<kColBytes2, STAGE_W>(A.op, slice, A.n_slices, smem_dyn + (size_t)warp * A.buf_bytes,
-                                                         &bars[warp], lane, A.pf_dist);
+                                                         &bars[warp], lane, A.pf_dist, two_phase);
     const int width = sv.width;
     const int *ip = sv.ip;
     const double *wxp = sv.wxp;
@@ -393,6 +495,18 @@ __global__ void __launch_bounds__(128, (KFIX > 0 ? 2 : 4)) k_pass_a(const PassAA
                 }
             }
         }
+        if (two_phase && width > 0) {
+            // every lane is done with wx: refill the weight buffer with wy (already pulled into L2 by the prefetch)
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const unsigned char *src = A.op.base + (size_t)A.op.off[slice] * kColBytes2;
+                mbar_expect_tx(&bars[warp], (uint32_t)width * kSlice * 8);
+                bulk_g2s(smem_dyn + (size_t)warp * A.buf_bytes + (size_t)width * kSlice * 4, src + (size_t)width * kSlice * 12,
+                         (uint32_t)width * kSlice * 8, &bars[warp]);
+            }
+            mbar_wait(&bars[warp], 1);
+        }
         for (int c0 = 0; c0 < width; c0 += kBatch) {
             Vec<V> uj[kBatch];
             double w[kBatch];
@@ -455,94 +569,145 @@ __global__ void __launch_bounds__(128, (KFIX > 0 ? 2 : 4)) k_pass_a(const PassAA
     }
 
     if (!live) return;
-    if constexpr (DO_FLUX) st_vec(reinterpret_cast<Vec<V> *>(A.du) + row, acc);
+    pass_a_epilogue<V, EQ, DO_FLUX, VISC>(A, row, acc, gx, gy, ui, ad);
+}
 
+// ---- pass A over ROW PAIRS (same idea as k_pass_b_pair): one thread owns rows (2l, 2l+1) and walks the union of the
+// two stencils, so a neighbour state shared by both rows is gathered -- and its flux evaluated -- once per sweep.
+// Exact order: sweep 1 = all Dx terms in ascending column order, sweep 2 = all Dy terms; zero weights add exact zeros.
+template <int V, int EQ, bool EXACT, int VISC>
+__global__ void __launch_bounds__(128, 3) k_pass_a_pair(const PassAArgs A)
+{
+    static_assert(V == 4 && EQ == EQ_EULER2D, "pair kernel is instantiated for Euler 2-D");
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ uint64_t bars[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t slice = (int64_t)blockIdx.x * 4 + warp;
+    if (slice >= A.n_slices) return;
+    const int64_t rowA = slice * (2 * kSlice) + 2 * lane, rowB = rowA + 1;
+    const bool liveA = rowA < A.n_rows, liveB = rowB < A.n_rows;
+    const int off = A.op.off[slice];
+    const int width = A.op.off[slice + 1] - off;
+    const unsigned char *src = A.op.base + (size_t)off * kColBytesPair;
+    unsigned char *buf = smem_dyn + (size_t)warp * A.buf_bytes;
+    if (lane == 0) mbar_init(&bars[warp], 1);
+    __syncwarp();
+    if (lane == 0 && width > 0) {
+        mbar_expect_tx(&bars[warp], (uint32_t)width * kSlice * 4);
+        bulk_g2s(buf, src, (uint32_t)width * kSlice * 4, &bars[warp]);
+    }
+    const int *ip = reinterpret_cast<const int *>(buf) + lane;
+    const double *wbase = reinterpret_cast<const double *>(src + (size_t)width * kSlice * 4) + lane;
+    const size_t wstride = (size_t)width * kSlice;
+    const Vec<V> *__restrict__ u = reinterpret_cast<const Vec<V> *>(A.u);
+    Physics<EQ, V> ph;
+    ph.gamma = A.eqp0;
+
+    Vec<V> accA, accB, gxA, gxB, gyA, gyB, uiA, uiB, adA, adB;
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        accA.a[v] = accB.a[v] = gxA.a[v] = gxB.a[v] = gyA.a[v] = gyB.a[v] = uiA.a[v] = uiB.a[v] = adA.a[v] = adB.a[v] = 0.0;
+    if (A.accumulate) {
+        if (liveA) accA = reinterpret_cast<const Vec<V> *>(A.du)[rowA];
+        if (liveB) accB = reinterpret_cast<const Vec<V> *>(A.du)[rowB];
+    }
     if constexpr (VISC != VISC_NONE) {
-        static_assert(VISC == VISC_NONE || (EQ == EQ_EULER2D && V == 4), "viscosity sources are Euler-2D only");
-        // update_upwind_visc!  hyperviscosity.jl:246-285
-        double v1, v2, p;
-        euler_prim(A.eqp0, ui, v1, v2, p);
-        const double speed = sqrt(v1 * v1 + v2 * v2);
-        double sound;
-        if (p < 0.0 || ui.a[0] < 0.0) {
-            sound = 0.0;
-        } else {
-            sound = sqrt(A.eqp0 * p / ui.a[0]);
-        }
-        const double e_uw = A.c_uw * 0.5 * A.dx_avg * (speed + sound);
-        double e = e_uw, e_rv = 0.0, e_c = 1.0;
+        if (liveA) uiA = ld_ro(u + rowA);
+        if (liveB) uiB = ld_ro(u + rowB);
         if constexpr (VISC == VISC_RESIDUAL) {
-            // update_residual_visc! :289-329 (pointwise part) and update_visc! :331-349
-            Vec<V> dui;
-            if constexpr (DO_FLUX) {
-                dui = acc;
-            } else {
-                dui = reinterpret_cast<const Vec<V> *>(A.du)[row];
-            }
-            Vec<V> res;
+            if (liveA) adA = ld_ro(reinterpret_cast<const Vec<V> *>(A.approx_du) + rowA);
+            if (liveB) adB = ld_ro(reinterpret_cast<const Vec<V> *>(A.approx_du) + rowB);
+        }
+    }
+    if (width > 0) mbar_wait(&bars[warp], 0);
+
+    constexpr int kBatch = 4;
+    if constexpr (EXACT) {
+        auto sweep = [&](auto dir_tag) {
+            constexpr int DIR = decltype(dir_tag)::value;
+            const double *wA = wbase + (size_t)DIR * wstride;        // wxA | wyA
+            const double *wB = wbase + (size_t)(2 + DIR) * wstride;  // wxB | wyB
+            for (int c0 = 0; c0 < width; c0 += kBatch) {
+                Vec<V> uj[kBatch];
+                double wa[kBatch], wb[kBatch];
 #pragma unroll
-            for (int v = 0; v < V; ++v) res.a[v] = fabs(ad.a[v] - dui.a[v]);
-            double nrm[V];
-            if (A.norm_parts > 0) {
-                // global ode_maximum: combine the per-rank candidates in rank order (MPI.Allreduce(MAX), mpi.jl:76)
+                for (int b = 0; b < kBatch; ++b) {
+                    const bool ok = c0 + b < width;
+                    const int cc = ok ? c0 + b : width - 1;
+                    const int j = ok ? ip[cc * kSlice] : A.dummy;
+                    const double w1 = ld_stream(wA + (size_t)cc * kSlice), w2 = ld_stream(wB + (size_t)cc * kSlice);
+                    wa[b] = ok ? w1 : 0.0;
+                    wb[b] = ok ? w2 : 0.0;
+                    uj[b] = ld_ro(u + j);
+                }
 #pragma unroll
-                for (int v = 0; v < V; ++v) nrm[v] = A.norms[v];
-                for (int r = 1; r < A.norm_parts; ++r) {
-                    double c[V];
+                for (int b = 0; b < kBatch; ++b) {
+                    ph.prepare(uj[b]);
+                    Vec<V> f;
+                    if constexpr (DIR == 0) f = ph.flux_x(uj[b]);
+                    else f = ph.flux_y(uj[b]);
 #pragma unroll
-                    for (int v = 0; v < V; ++v) c[v] = A.norms[r * V + v];
-                    if (A.norm_lex) {
-                        if (lex_less<V>(nrm, c)) {
+                    for (int v = 0; v < V; ++v) {
+                        accA.a[v] = accA.a[v] + wa[b] * (-f.a[v]);
+                        accB.a[v] = accB.a[v] + wb[b] * (-f.a[v]);
+                    }
+                    if constexpr (VISC != VISC_NONE) {
 #pragma unroll
-                            for (int v = 0; v < V; ++v) nrm[v] = c[v];
+                        for (int v = 0; v < V; ++v) {
+                            if constexpr (DIR == 0) {
+                                gxA.a[v] = gxA.a[v] + wa[b] * uj[b].a[v];
+                                gxB.a[v] = gxB.a[v] + wb[b] * uj[b].a[v];
+                            } else {
+                                gyA.a[v] = gyA.a[v] + wa[b] * uj[b].a[v];
+                                gyB.a[v] = gyB.a[v] + wb[b] * uj[b].a[v];
+                            }
                         }
-                    } else {
-#pragma unroll
-                        for (int v = 0; v < V; ++v) nrm[v] = jl_max(nrm[v], c[v]);
                     }
                 }
-#pragma unroll
-                for (int v = 0; v < V; ++v) nrm[v] = nrm[v] == 0.0 ? kEps : nrm[v];
-                if (A.norms_out && row == 0) {
-#pragma unroll
-                    for (int v = 0; v < V; ++v) A.norms_out[v] = nrm[v];
-                }
-            } else {
-#pragma unroll
-                for (int v = 0; v < V; ++v) nrm[v] = A.norms[v];
             }
-            double mx = res.a[0] / nrm[0];
+        };
+        sweep(std::integral_constant<int, 0>{});
+        sweep(std::integral_constant<int, 1>{});
+    } else {
+        for (int c0 = 0; c0 < width; c0 += kBatch) {
+            Vec<V> uj[kBatch];
+            double w[kBatch][4];
 #pragma unroll
-            for (int v = 1; v < V; ++v) mx = jl_max(mx, res.a[v] / nrm[v]);
-            e_rv = 0.5 * A.c_rv * (A.dx_avg * A.dx_avg) * mx;
-            if (isnan(e_rv) || isinf(e_rv) || A.success_iter_zero) {
-                if (isnan(e_uw) || isinf(e_uw)) {
-                    e = kEps;
-                    e_c = 2.0;
-                } else {
-                    e = e_uw;
-                    e_c = 1.0;
+            for (int b = 0; b < kBatch; ++b) {
+                const bool ok = c0 + b < width;
+                const int cc = ok ? c0 + b : width - 1;
+                const int j = ok ? ip[cc * kSlice] : A.dummy;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double wv = ld_stream(wbase + q * wstride + (size_t)cc * kSlice);
+                    w[b][q] = ok ? wv : 0.0;
                 }
-            } else {
-                e = e_rv < e_uw ? e_rv : e_uw;
-                e_c = e_rv < e_uw ? 0.0 : 1.0;
+                uj[b] = ld_ro(u + j);
             }
-            if (A.residual) st_vec(reinterpret_cast<Vec<V> *>(A.residual) + row, res);
-        }
-        if (A.eps) {
-            A.eps[row] = e;
-            A.eps_uw[row] = e_uw;
-            A.eps_rv[row] = e_rv;
-            A.eps_c[row] = e_c;
-        }
-        Vec<2 * V> gout;
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            gout.a[v] = e * gx.a[v];
-            gout.a[V + v] = e * gy.a[v];
+            for (int b = 0; b < kBatch; ++b) {
+                ph.prepare(uj[b]);
+                const Vec<V> f = ph.flux_x(uj[b]);
+                const Vec<V> h = ph.flux_y(uj[b]);
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    accA.a[v] = fma(-w[b][1], h.a[v], fma(-w[b][0], f.a[v], accA.a[v]));
+                    accB.a[v] = fma(-w[b][3], h.a[v], fma(-w[b][2], f.a[v], accB.a[v]));
+                }
+                if constexpr (VISC != VISC_NONE) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        gxA.a[v] = fma(w[b][0], uj[b].a[v], gxA.a[v]);
+                        gyA.a[v] = fma(w[b][1], uj[b].a[v], gyA.a[v]);
+                        gxB.a[v] = fma(w[b][2], uj[b].a[v], gxB.a[v]);
+                        gyB.a[v] = fma(w[b][3], uj[b].a[v], gyB.a[v]);
+                    }
+                }
+            }
         }
-        st_vec(reinterpret_cast<Vec<2 * V> *>(A.g) + row, gout);
     }
+    if (liveA) pass_a_epilogue<V, EQ, true, VISC>(A, rowA, accA, gxA, gyA, uiA, adA);
+    if (liveB) pass_a_epilogue<V, EQ, true, VISC>(A, rowB, accB, gxB, gyB, uiB, adB);
 }
 
 // ---- pass B: du -= Dx' gX + Dy' gY over the transposed sliced-ELL operator --------------------------------
@@ -624,6 +789,99 @@ __global__ void __launch_bounds__(128, 4) k_pass_b(const PassBArgs A)
 #pragma unroll
     for (int v = 0; v < V; ++v) d.a[v] = (d.a[v] + tx.a[v] * -1.0) + ty.a[v] * -1.0;
     st_vec(reinterpret_cast<Vec<V> *>(A.du) + row, d);
+}
+
+// ---- pass B over ROW PAIRS: one thread owns two consecutive rows and walks the UNION of their D' rows ----------------
+// The gather is the bottleneck (about one 32-byte sector per cycle per SM, almost no sharing between the lanes of a
+// request), and two rows that are neighbours along the curve share ~15 of 20 entries: walking the union (~25 entries,
+// a zero weight where a row does not have the entry) fetches every shared g record once for both rows -> ~1/3 fewer
+// gathered sectors.  Entries stay in the reference's order and a zero weight adds an exact zero, so the sums are
+// unchanged bit for bit (for finite g).  Blob per pair-slice (32 lanes x 2 rows):
+//   [ idx : w x 32 int32 ][ wxA ][ wyA ][ wxB ][ wyB ]   (each weight block w x 32 doubles)
+
+struct PassBPairArgs {
+    EllBlob opT;       // pair-slice blobs
+    const void *g;
+    void *du;
+    int64_t n_rows;
+    int64_t n_slices;  // pair-slices
+    int buf_bytes;     // per-warp shared memory for the index block
+    int dummy;
+};
+
+template <int V, bool EXACT>
+__global__ void __launch_bounds__(128, 3) k_pass_b_pair(const PassBPairArgs A)
+{
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ uint64_t bars[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t slice = (int64_t)blockIdx.x * 4 + warp;
+    if (slice >= A.n_slices) return;
+    const int64_t rowA = slice * (2 * kSlice) + 2 * lane, rowB = rowA + 1;
+    const bool liveA = rowA < A.n_rows, liveB = rowB < A.n_rows;
+    const int off = A.opT.off[slice];
+    const int width = A.opT.off[slice + 1] - off;
+    const unsigned char *src = A.opT.base + (size_t)off * kColBytesPair;
+    unsigned char *buf = smem_dyn + (size_t)warp * A.buf_bytes;
+    if (lane == 0) mbar_init(&bars[warp], 1);
+    __syncwarp();
+    if (lane == 0 && width > 0) {
+        mbar_expect_tx(&bars[warp], (uint32_t)width * kSlice * 4);
+        bulk_g2s(buf, src, (uint32_t)width * kSlice * 4, &bars[warp]);
+    }
+    const int *ip = reinterpret_cast<const int *>(buf) + lane;
+    const double *wbase = reinterpret_cast<const double *>(src + (size_t)width * kSlice * 4) + lane;
+    const size_t wstride = (size_t)width * kSlice;  // doubles per weight block
+    const Vec<2 * V> *__restrict__ g = reinterpret_cast<const Vec<2 * V> *>(A.g);
+
+    Vec<V> txA, tyA, txB, tyB, dA, dB;
+#pragma unroll
+    for (int v = 0; v < V; ++v) txA.a[v] = tyA.a[v] = txB.a[v] = tyB.a[v] = dA.a[v] = dB.a[v] = 0.0;
+    if (liveA) dA = reinterpret_cast<const Vec<V> *>(A.du)[rowA];
+    if (liveB) dB = reinterpret_cast<const Vec<V> *>(A.du)[rowB];
+    if (width > 0) mbar_wait(&bars[warp], 0);
+
+    constexpr int kBatch = 4;
+    for (int c0 = 0; c0 < width; c0 += kBatch) {
+        Vec<2 * V> gj[kBatch];
+        double w[kBatch][4];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const bool ok = c0 + b < width;
+            const int cc = ok ? c0 + b : width - 1;
+            const int j = ok ? ip[cc * kSlice] : A.dummy;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double wv = ld_stream(wbase + q * wstride + (size_t)cc * kSlice);
+                w[b][q] = ok ? wv : 0.0;
+            }
+            gj[b] = ld_ro(g + j);
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                if constexpr (EXACT) {
+                    txA.a[v] = txA.a[v] + w[b][0] * gj[b].a[v];
+                    tyA.a[v] = tyA.a[v] + w[b][1] * gj[b].a[V + v];
+                    txB.a[v] = txB.a[v] + w[b][2] * gj[b].a[v];
+                    tyB.a[v] = tyB.a[v] + w[b][3] * gj[b].a[V + v];
+                } else {
+                    txA.a[v] = fma(w[b][0], gj[b].a[v], txA.a[v]);
+                    tyA.a[v] = fma(w[b][1], gj[b].a[V + v], tyA.a[v]);
+                    txB.a[v] = fma(w[b][2], gj[b].a[v], txB.a[v]);
+                    tyB.a[v] = fma(w[b][3], gj[b].a[V + v], tyB.a[v]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        dA.a[v] = (dA.a[v] + txA.a[v] * -1.0) + tyA.a[v] * -1.0;
+        dB.a[v] = (dB.a[v] + txB.a[v] * -1.0) + tyB.a[v] * -1.0;
+    }
+    if (liveA) st_vec(reinterpret_cast<Vec<V> *>(A.du) + rowA, dA);
+    if (liveB) st_vec(reinterpret_cast<Vec<V> *>(A.du) + rowB, dB);
 }
 
 // ---- generic single-matrix source: du += alpha * H u  (hyperviscosity, hyperviscosity.jl:52-64,121-134) ----
