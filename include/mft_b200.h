@@ -158,6 +158,12 @@ int mft_history_push(mft_ctx *ctx, double t, int64_t success_iter, int approx_or
 int mft_history_push_weights(mft_ctx *ctx, double t, int64_t success_iter, int n, const double *weights);
 /* one SSPRK step on the resident state, FSAL structure (k=f(u_n) carried between steps), 3 rhs! per step */
 int mft_ssprk_step(mft_ctx *ctx, int scheme, double t, double dt);
+/* one SSPRK43 step (4 stages + FSAL rhs!) with OrdinaryDiffEq's embedded error estimate; the integrator the reference names
+ * (rbfsolver_test.jl:104-107).  Returns the local sum_i (err_i / (abstol + max(|u_n,i|,|u_n+1,i|) reltol))^2 and the number
+ * of local entries; the caller sums both over ranks, EEst = sqrt(sumsq/count) (ode_norm, src/auxiliary/mpi.jl:15-19), runs its
+ * step-size controller and then calls mft_step_commit(ctx, accept).  A rejected step restores u_n and f(u_n). */
+int mft_ssprk43_step(mft_ctx *ctx, double t, double dt, double abstol, double reltol, double *sumsq_out, int64_t *count_out);
+int mft_step_commit(mft_ctx *ctx, int accept);
 int mft_get_field(mft_ctx *ctx, int field, double *out);
 int mft_synchronize(mft_ctx *ctx);
 /* number of kernels launched by this ctx since creation (bench.py `gpu_launches`) */

@@ -31,7 +31,7 @@ EXPORTS = [
     "mft_set_option", "mft_set_permutation", "mft_set_order_keys", "mft_set_operator_csc", "mft_set_operator_ell",
     "mft_add_boundary", "mft_update_boundary_values", "mft_add_source", "mft_finalize", "mft_rhs", "mft_calc_fluxes",
     "mft_apply_source", "mft_boundary_pass", "mft_upload_state", "mft_download_state", "mft_download_du",
-    "mft_history_push", "mft_history_push_weights", "mft_ssprk_step", "mft_get_field", "mft_synchronize",
+    "mft_history_push", "mft_history_push_weights", "mft_ssprk_step", "mft_ssprk43_step", "mft_step_commit", "mft_get_field", "mft_synchronize",
     "mft_launch_count", "mft_timer_start", "mft_timer_stop", "mft_kernel_time_ms", "mft_set_kernel_timing", "mft_host_alloc", "mft_host_free",
     "mft_host_register", "mft_host_unregister", "mft_sfc_order", "mft_nccl_unique_id", "mft_comm_init", "mft_set_halo", "mft_p2p_handles", "mft_p2p_connect",
 ]
@@ -79,6 +79,8 @@ def load():
         "mft_history_push": [vp, dbl, i64, i32],
         "mft_history_push_weights": [vp, dbl, i64, i32, vp],
         "mft_ssprk_step": [vp, i32, dbl, dbl],
+        "mft_ssprk43_step": [vp, dbl, dbl, dbl, dbl, C.POINTER(dbl), C.POINTER(i64)],
+        "mft_step_commit": [vp, i32],
         "mft_get_field": [vp, i32, vp],
         "mft_synchronize": [vp],
         "mft_kernel_time_ms": [vp, i32, C.POINTER(dbl), C.POINTER(i64)],

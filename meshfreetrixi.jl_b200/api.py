@@ -459,6 +459,36 @@ class SSPRK33:
     stages = 3
 
 
+class SSPRK43:
+    """adaptive; the error estimate comes from the library, the step-size controller runs on the host"""
+    stages = 4
+
+
+class PIController:
+    """OrdinaryDiffEq's default PI controller for an order-3 method (third party, unpinned): beta1 = 7/(10k),
+    beta2 = 2/(5k), gamma = 0.9, qmin = 0.2, qmax = 10, qsteady in [1, 1.2], qoldinit = 1e-4.  In the Julia deployment
+    OrdinaryDiffEq keeps its own controller; this one drives the Python host loop."""
+
+    def __init__(self, order=3, gamma=0.9, qmin=0.2, qmax=10.0, qsteady_min=1.0, qsteady_max=1.2, qoldinit=1e-4):
+        self.beta1, self.beta2 = 7.0 / (10.0 * order), 2.0 / (5.0 * order)
+        self.gamma, self.qmin, self.qmax = gamma, qmin, qmax
+        self.qsteady_min, self.qsteady_max, self.qoldinit = qsteady_min, qsteady_max, qoldinit
+        self.qold = qoldinit
+
+    def propose(self, dt, eest):
+        if eest == 0.0:
+            q, q11 = 1.0 / self.qmax, 0.0
+        else:
+            q11 = eest ** self.beta1
+            q = max(1.0 / self.qmax, min(1.0 / self.qmin, q11 / self.qold ** self.beta2 / self.gamma))
+        if eest <= 1.0:
+            if self.qsteady_min <= q <= self.qsteady_max:
+                q = 1.0
+            self.qold = max(eest, self.qoldinit)
+            return True, dt / q
+        return False, dt / min(1.0 / self.qmin, q11 / self.gamma)
+
+
 @dataclass
 class Solution:
     u: np.ndarray
@@ -467,9 +497,51 @@ class Solution:
     nrhs: int
 
 
-def solve(ode, alg, dt, callback=None, nsteps=None):
+def solve_adaptive(ode, alg, dt, abstol=1e-8, reltol=1e-8, callback=None, max_steps=100000, allreduce=None):
+    """solve(ode, SSPRK43(); abstol, reltol, callback=...) (rbfsolver_test.jl:104-107): adaptive steps, FSAL, callbacks
+    after every ACCEPTED step.  `allreduce(sumsq, count) -> (sumsq, count)` combines ranks in multi-GPU runs."""
+    semi = ode.p
+    lib = L.load()
+    t0, t1 = ode.tspan
+    cbs = [] if callback is None else (list(callback) if isinstance(callback, (list, tuple)) else [callback])
+    hist = [c for c in cbs if isinstance(c, HistoryCallback)]
+    u0 = np.ascontiguousarray(ode.u0, dtype=np.float64)
+    L.check(lib.mft_upload_state(semi.ctx, L.soa_ptrs(u0)))
+    t, dt = float(t0), float(dt)
+    for h in hist:
+        L.check(lib.mft_history_push(semi.ctx, t, 0, h.approx_order))
+    ctrl = PIController()
+    accepted, log, nrhs = 0, [], 1
+    ss, cnt = C.c_double(), C.c_int64()
+    for _ in range(max_steps):
+        if t >= t1 - 1e-14 * max(1.0, abs(t1)):
+            break
+        dt = min(dt, t1 - t)
+        L.check(lib.mft_ssprk43_step(semi.ctx, t, dt, abstol, reltol, C.byref(ss), C.byref(cnt)))
+        sumsq, count = (ss.value, cnt.value) if allreduce is None else allreduce(ss.value, cnt.value)
+        eest = float(np.sqrt(sumsq / count))
+        accept, dt_next = ctrl.propose(dt, eest)
+        L.check(lib.mft_step_commit(semi.ctx, int(accept)))
+        log.append((t, dt, eest, accept))
+        nrhs += alg.stages
+        if accept:
+            t += dt
+            accepted += 1
+            for h in hist:
+                L.check(lib.mft_history_push(semi.ctx, t, accepted, h.approx_order))
+        dt = dt_next
+    u = np.empty_like(u0)
+    L.check(lib.mft_download_state(semi.ctx, L.soa_ptrs(u)))
+    sol = Solution(u, t, accepted, nrhs)
+    sol.log = log
+    return sol
+
+
+def solve(ode, alg, dt, callback=None, nsteps=None, **kw):
     """Fixed-step SSP integration with the state resident on the device (FSAL structure, callbacks after
-    every step); mirrors solve(ode, SSPRK..; dt, adaptive=false, callback=CallbackSet(...))."""
+    every step); mirrors solve(ode, SSPRK..; dt, adaptive=false, callback=CallbackSet(...)).  SSPRK43 -> adaptive."""
+    if isinstance(alg, SSPRK43):
+        return solve_adaptive(ode, alg, dt, callback=callback, **kw)
     semi = ode.p
     lib = L.load()
     t0, t1 = ode.tspan

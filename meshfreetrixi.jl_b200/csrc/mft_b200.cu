@@ -148,6 +148,8 @@ struct mft_ctx {
     bool finalized = false;
     // device state (AoS)
     DevBuf<double> u, du, uprev, g, approx_du, stage_soa;
+    DevBuf<double> utilde, kfsal, u_save;  // SSPRK43: error vector, f(u_n) kept for a rejected step, u_n incl. halo
+    bool step_pending = false;
     std::vector<DevBuf<double>> hist;
     std::vector<double> time_history, time_weights;
     int hist_head = 0, nslots = 0;
@@ -297,11 +299,11 @@ extern "C" int mft_ctx_create(mft_ctx **out, int device, int64_t n_local, int64_
     CU(cudaGetDeviceProperties(&prop, device));
     c->red_blocks = prop.multiProcessorCount * 4;
     CHECK(c->partial.alloc((int64_t)c->red_blocks * nvars));
-    CHECK(c->stats.alloc(3 * nvars));
+    CHECK(c->stats.alloc(3 * nvars + 4));  // sum | mean | norms | SSPRK43 error sum
     CHECK(c->ticket.alloc(4));
     CU(cudaMemset(c->ticket.p, 0, 4 * sizeof(unsigned int)));
     c->pf_dist = prop.multiProcessorCount * 16;
-    CU(cudaMemset(c->stats.p, 0, sizeof(double) * 3 * nvars));
+    CU(cudaMemset(c->stats.p, 0, sizeof(double) * (3 * nvars + 4)));
     *out = c;
     return MFT_OK;
 }
@@ -327,7 +329,7 @@ extern "C" int mft_ctx_destroy(mft_ctx *c)
     c->tra_pair.release();
     c->fwd_pair.release();
     for (auto &h : c->hist) h.release();
-    DevBuf<double> *bufs[] = {&c->u, &c->du, &c->uprev, &c->g, &c->approx_du, &c->stage_soa, &c->eps, &c->eps_uw,
+    DevBuf<double> *bufs[] = {&c->utilde, &c->kfsal, &c->u_save, &c->u, &c->du, &c->uprev, &c->g, &c->approx_du, &c->stage_soa, &c->eps, &c->eps_uw,
                               &c->eps_rv, &c->eps_c, &c->residual, &c->partial, &c->stats, &c->send_buf, &c->gather_buf};
     for (auto *b : bufs) b->release();
     if (c->touched_host) cudaFreeHost(c->touched_host);
@@ -1626,6 +1628,75 @@ extern "C" int mft_ssprk_step(mft_ctx *c, int scheme, double t, double dt)
     CU(cudaGraphLaunch(g->exec, c->stream));
     c->launches += g->nlaunch;
     return MFT_OK;  // asynchronous: mft_synchronize / downloads wait
+}
+
+// ---- SSPRK43 with embedded error estimate (the integrator the reference names: rbfsolver_test.jl:104-107) ------------
+// The library does the four stages and returns the LOCAL sum of squared scaled errors and the local entry count; the
+// caller combines ranks (sum both), forms EEst = sqrt(sumsq/count) (ode_norm, src/auxiliary/mpi.jl:15-19) and runs its
+// own step-size controller (OrdinaryDiffEq's stays in charge in the Julia deployment), then commits or rolls back
+// with mft_step_commit.
+extern "C" int mft_ssprk43_step(mft_ctx *c, double t, double dt, double abstol, double reltol, double *sumsq_out,
+                                int64_t *count_out)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    if (c->step_pending) return fail(MFT_EINVAL, "mft_ssprk43_step: previous step was neither committed nor rejected (mft_step_commit)");
+    const int64_t len = c->n_local * c->V, len_tot = c->n_tot * c->V;
+    if (!c->utilde.p) {
+        CHECK(c->utilde.alloc(len_tot));
+        CHECK(c->kfsal.alloc(len_tot));
+        CHECK(c->u_save.alloc(len_tot + c->V));
+        CU(cudaMemsetAsync(c->utilde.p, 0, sizeof(double) * len_tot, c->stream));
+    }
+    if (!c->have_fsal) CHECK(rhs_device(c, t));  // k = f(u_n, t)
+    c->have_fsal = true;
+    // keep f(u_n) and u_n (rhs! also rewrites boundary / halo entries of u) for a possible rejection
+    CU(cudaMemcpyAsync(c->kfsal.p, c->du.p, sizeof(double) * len_tot, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->u_save.p, c->u.p, sizeof(double) * len_tot, cudaMemcpyDeviceToDevice, c->stream));
+    const int grid = c->red_blocks * 2;
+    auto stage = [&](int st) -> int {
+        ScopedTimer tm(c, MFT_K_STAGE);
+        k_ssprk43_stage<<<grid, 256, 0, c->stream>>>(st, dt, c->uprev.p, c->du.p, c->u.p, c->utilde.p, len);
+        c->launches++;
+        LAUNCH_CHECK();
+        return MFT_OK;
+    };
+    CHECK(stage(1));
+    CHECK(rhs_device(c, t + dt / 2));
+    CHECK(stage(2));
+    CHECK(rhs_device(c, t + dt));
+    CHECK(stage(3));
+    CHECK(rhs_device(c, t + dt / 2));
+    CHECK(stage(4));
+    {
+        ScopedTimer tm(c, MFT_K_REDUCE);
+        k_error_sumsq<<<c->red_blocks, 256, 0, c->stream>>>(c->utilde.p, c->uprev.p, c->u.p, len, abstol, reltol, c->partial.p,
+                                                         c->ticket.p + 2, c->stats.p + 3 * c->V);
+        c->launches++;
+        LAUNCH_CHECK();
+    }
+    CHECK(rhs_device(c, t + dt));  // FSAL: k = f(u_{n+1}, t+dt)
+    double ss = 0.0;
+    CU(cudaMemcpyAsync(&ss, c->stats.p + 3 * c->V, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (sumsq_out) *sumsq_out = ss;
+    if (count_out) *count_out = len;
+    c->step_pending = true;
+    return MFT_OK;
+}
+
+// accept != 0: keep u_{n+1} and its f; accept == 0: restore u_n and f(u_n) (a rejected step leaves no trace)
+extern "C" int mft_step_commit(mft_ctx *c, int accept)
+{
+    NEED_CTX(c);
+    if (!c->step_pending) return fail(MFT_EINVAL, "mft_step_commit: no step pending");
+    if (!accept) {
+        const int64_t len_tot = c->n_tot * c->V;
+        CU(cudaMemcpyAsync(c->u.p, c->u_save.p, sizeof(double) * len_tot, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->du.p, c->kfsal.p, sizeof(double) * len_tot, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->step_pending = false;
+    return MFT_OK;
 }
 
 extern "C" int mft_synchronize(mft_ctx *c)

@@ -1312,6 +1312,76 @@ __global__ void __launch_bounds__(256) k_ssprk33_stage(int stage, double dt, dou
     }
 }
 
+// ---- SSPRK43 stage updates + embedded error estimate (OrdinaryDiffEq low-storage SSPRK43; DESIGN.md "time loop") --------
+// stage 1 also snapshots uprev; stage 3 forms utilde = (uprev + 2 u3)/3 and u = (2 uprev + u3)/3; stage 4 turns utilde into
+// the error vector 0.5*(utilde - u).
+__global__ void __launch_bounds__(256) k_ssprk43_stage(int stage, double dt, double *__restrict__ uprev,
+                                                     const double *__restrict__ k, double *__restrict__ u,
+                                                     double *__restrict__ utilde, int64_t len)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const double h = dt / 2.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        if (stage == 1) {
+            const double up = u[i];
+            uprev[i] = up;
+            u[i] = fma(h, k[i], up);
+        } else if (stage == 2) {
+            u[i] = fma(h, k[i], u[i]);
+        } else if (stage == 3) {
+            const double u3 = fma(h, k[i], u[i]);
+            const double up = uprev[i];
+            utilde[i] = fma(2.0, u3, up) / 3.0;
+            u[i] = fma(2.0, up, u3) / 3.0;
+        } else {
+            const double un = fma(h, k[i], u[i]);
+            u[i] = un;
+            utilde[i] = 0.5 * (utilde[i] - un);
+        }
+    }
+}
+
+// sum_i (utilde_i / (abstol + max(|uprev_i|,|u_i|) reltol))^2 over the owned entries; deterministic (last block finishes)
+__global__ void __launch_bounds__(256) k_error_sumsq(const double *__restrict__ utilde, const double *__restrict__ uprev,
+                                                   const double *__restrict__ u, int64_t len, double abstol, double reltol,
+                                                   double *partial, unsigned int *ticket, double *out)
+{
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = fabs(uprev[i]), b = fabs(u[i]);
+        const double r = utilde[i] / (abstol + (a > b ? a : b) * reltol);
+        s += r * r;
+    }
+    __shared__ double sh[8];
+    __shared__ bool is_last;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (l == 0) sh[w] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += sh[k];
+        partial[blockIdx.x] = t;
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    s = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += __ldcg(&partial[b]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if (l == 0) sh[w] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += sh[k];
+        *out = t;
+        *ticket = 0;
+    }
+}
+
 // ---- time-history residual: approx_du = sum_s w[s] * hist[s]  (update_approx_du!, history.jl:113-129) --------
 struct ApproxDuArgs {
     const double *hist[8];

@@ -490,6 +490,49 @@ void orc_ssprk33_stage(int64_t len, int stage, double dt, const double *uprev, c
 }
 
 /* ------------------------------------------------------------------------------------------
+ * SSPRK43 (OrdinaryDiffEq low-storage form, third party / unpinned; the integrator the
+ * reference names: rbfsolver_test.jl:104-107).  With h = dt/2 and k = f(u):
+ *   stage 1: u = fma(h, k, uprev)                 then k = f(u, t+h)
+ *   stage 2: u = fma(h, k, u)                     then k = f(u, t+dt)
+ *   stage 3: u = fma(h, k, u); utilde = fma(2,u,uprev)/3; u = fma(2,uprev,u)/3      then k = f(u, t+h)
+ *   stage 4: u = fma(h, k, u); utilde = 0.5*(utilde - u)                            then k = f(u, t+dt)  (FSAL)
+ * Error estimate: EEst = sqrt( sum_i (utilde_i / (abstol + max(|uprev_i|,|u_i|)*reltol))^2 / len )   (calculate_residuals
+ * + ODE_DEFAULT_NORM / ode_norm, src/auxiliary/mpi.jl:15-19: RMS over all scalars).
+ * ---------------------------------------------------------------------------------------- */
+void orc_ssprk43_stage(int64_t len, int stage, double dt, const double *uprev, const double *k, double *u, double *utilde)
+{
+    const double h = dt / 2.0;
+    if (stage == 1) {
+        for (int64_t i = 0; i < len; ++i) u[i] = fma(h, k[i], uprev[i]);
+    } else if (stage == 2) {
+        for (int64_t i = 0; i < len; ++i) u[i] = fma(h, k[i], u[i]);
+    } else if (stage == 3) {
+        for (int64_t i = 0; i < len; ++i) {
+            const double u3 = fma(h, k[i], u[i]);
+            utilde[i] = fma(2.0, u3, uprev[i]) / 3.0;
+            u[i] = fma(2.0, uprev[i], u3) / 3.0;
+        }
+    } else {
+        for (int64_t i = 0; i < len; ++i) {
+            const double un = fma(h, k[i], u[i]);
+            u[i] = un;
+            utilde[i] = 0.5 * (utilde[i] - un);
+        }
+    }
+}
+
+double orc_error_sumsq(int64_t len, const double *utilde, const double *uprev, const double *u, double abstol, double reltol)
+{
+    double s = 0.0;
+    for (int64_t i = 0; i < len; ++i) {
+        const double a = fabs(uprev[i]), b = fabs(u[i]);
+        const double r = utilde[i] / (abstol + (a > b ? a : b) * reltol);
+        s += r * r;
+    }
+    return s;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Timed loop for the CPU baseline (bench.py cpu_baseline / --impl reference): `reps` rhs!
  * evaluations on the same state, exactly the reference's serial execution structure.
  * ---------------------------------------------------------------------------------------- */

@@ -411,6 +411,84 @@ class OracleProblem:
         return u, t
 
 
+class PIController:
+    """OrdinaryDiffEq's default PI step-size controller (third party, unpinned) for an order-3 method:
+    beta1 = 7/(10k), beta2 = 2/(5k), gamma = 0.9, qmin = 0.2, qmax = 10, qsteady in [1, 1.2], qoldinit = 1e-4.
+    Used on BOTH sides of the SSPRK43 parity tests; in the drop-in deployment the controller stays inside OrdinaryDiffEq
+    and the library only supplies the error estimate."""
+
+    def __init__(self, order=3, gamma=0.9, qmin=0.2, qmax=10.0, qsteady_min=1.0, qsteady_max=1.2, qoldinit=1e-4):
+        self.beta1, self.beta2 = 7.0 / (10.0 * order), 2.0 / (5.0 * order)
+        self.gamma, self.qmin, self.qmax = gamma, qmin, qmax
+        self.qsteady_min, self.qsteady_max, self.qoldinit = qsteady_min, qsteady_max, qoldinit
+        self.qold = qoldinit
+
+    def propose(self, dt, eest):
+        """returns (accept, dt_next)"""
+        if eest == 0.0:
+            q, q11 = 1.0 / self.qmax, 0.0
+        else:
+            q11 = eest ** self.beta1
+            q = q11 / self.qold ** self.beta2
+            q = max(1.0 / self.qmax, min(1.0 / self.qmin, q / self.gamma))
+        if eest <= 1.0:                                   # step_accept_controller!
+            if self.qsteady_min <= q <= self.qsteady_max:
+                q = 1.0
+            self.qold = max(eest, self.qoldinit)
+            return True, dt / q
+        return False, dt / min(1.0 / self.qmin, q11 / self.gamma)   # step_reject_controller!
+
+
+def _ssprk43_step(P, u, k, t, dt, abstol, reltol):
+    """one SSPRK43 step from (u, k=f(u,t)); returns (u_new, k_new=f(u_new,t+dt), EEst).  u, k are not modified."""
+    L = lib()
+    L.orc_error_sumsq.restype = C.c_double
+    uprev = u
+    un = u.copy()
+    ut = np.zeros_like(u)
+    n_el = u.size
+    args = lambda st, kk: (C.c_int64(n_el), st, C.c_double(dt), C.c_void_p(_ptr(uprev)), C.c_void_p(_ptr(kk)),
+                           C.c_void_p(_ptr(un)), C.c_void_p(_ptr(ut)))
+    L.orc_ssprk43_stage(*args(1, k))
+    kk = P.rhs(un, t + dt / 2)
+    L.orc_ssprk43_stage(*args(2, kk))
+    kk = P.rhs(un, t + dt)
+    L.orc_ssprk43_stage(*args(3, kk))
+    kk = P.rhs(un, t + dt / 2)
+    L.orc_ssprk43_stage(*args(4, kk))
+    ss = L.orc_error_sumsq(C.c_int64(n_el), C.c_void_p(_ptr(ut)), C.c_void_p(_ptr(uprev)), C.c_void_p(_ptr(un)),
+                           C.c_double(abstol), C.c_double(reltol))
+    eest = math.sqrt(ss / n_el)
+    kk = P.rhs(un, t + dt)
+    return un, kk, eest
+
+
+def solve_ssprk43(P, u0, t0, t1, dt0, abstol=1e-8, reltol=1e-8, approx_order=None, max_steps=10000):
+    """Adaptive SSPRK43 with FSAL, HistoryCallback after every ACCEPTED step (rbfsolver_test.jl:104-107)."""
+    u = np.ascontiguousarray(u0, dtype=np.float64).copy()
+    t, dt = float(t0), float(dt0)
+    ctrl = PIController()
+    success_iter = 0
+    if approx_order is not None:
+        P.history_callback(u, t, 0, approx_order)
+    k = P.rhs(u, t)
+    log = []
+    for _ in range(max_steps):
+        if t >= t1 - 1e-14 * max(1.0, abs(t1)):
+            break
+        dt = min(dt, t1 - t)
+        un, kn, eest = _ssprk43_step(P, u, k, t, dt, abstol, reltol)
+        accept, dt_next = ctrl.propose(dt, eest)
+        log.append((t, dt, eest, accept))
+        if accept:
+            u, k, t = un, kn, t + dt
+            success_iter += 1
+            if approx_order is not None:
+                P.history_callback(u, t, success_iter, approx_order)
+        dt = dt_next
+    return u, t, log
+
+
 def time_deriv_weights(t):
     t = np.ascontiguousarray(t, dtype=np.float64)
     w = np.zeros_like(t)

@@ -370,3 +370,48 @@ def test_ell_operator_input_equals_csc_input(fx):
     L.check(lib.mft_ctx_destroy(ctx))
     assert np.array_equal(du_ell, du_csc)
     semi.close()
+
+
+def test_ssprk43_step_and_adaptive_run(fx):
+    """SSPRK43 (the integrator the reference names, rbfsolver_test.jl:104-107): one step (state + embedded error estimate)
+    and an adaptive run with accepted AND rejected steps, residual viscosity + history callback, against the oracle"""
+    mk, mko = SOURCE_SETS["residual"]
+    m, semi = _semi(fx, sources=mk, ic=cases.ic_smooth_euler)
+    P = _oracle(fx, mko(fx), ic=cases.ic_smooth_euler)
+    u0 = cases.ic_smooth_euler(fx["points"], 0.0)
+    # single step
+    k = P.rhs(u0.copy(), 0.0)
+    ub = u0.copy()
+    P.boundary_pass(ub, np.zeros_like(ub), 0.0)
+    un, kn, eest_ref = orc._ssprk43_step(P, ub, k, 0.0, 1e-3, 1e-6, 1e-6)
+    import ctypes as C
+    lib, L = m.load(), m._lib
+    L.check(lib.mft_upload_state(semi.ctx, L.soa_ptrs(u0)))
+    ss, cnt = C.c_double(), C.c_int64()
+    L.check(lib.mft_ssprk43_step(semi.ctx, 0.0, 1e-3, 1e-6, 1e-6, C.byref(ss), C.byref(cnt)))
+    assert cnt.value == u0.size
+    eest = np.sqrt(ss.value / cnt.value)
+    assert abs(eest - eest_ref) <= 1e-10 * eest_ref
+    L.check(lib.mft_step_commit(semi.ctx, 1))
+    u1 = np.empty_like(u0)
+    L.check(lib.mft_download_state(semi.ctx, L.soa_ptrs(u1)))
+    assert cases.relerr(u1, un) <= 1e-12
+    # a rejected step leaves no trace
+    L.check(lib.mft_ssprk43_step(semi.ctx, 1e-3, 5e-2, 1e-6, 1e-6, C.byref(ss), C.byref(cnt)))
+    L.check(lib.mft_step_commit(semi.ctx, 0))
+    u2 = np.empty_like(u0)
+    L.check(lib.mft_download_state(semi.ctx, L.soa_ptrs(u2)))
+    assert np.array_equal(u2, u1)
+    semi.close()
+    # adaptive run (same controller on both sides)
+    m, semi = _semi(fx, sources=mk, ic=cases.ic_smooth_euler)
+    P = _oracle(fx, mko(fx), ic=cases.ic_smooth_euler)
+    u_ref, t_ref, log_ref = orc.solve_ssprk43(P, u0, 0.0, 0.004, 1e-3, abstol=1e-6, reltol=1e-6, approx_order=3)
+    sol = m.solve(m.semidiscretize(semi, (0.0, 0.004)), m.SSPRK43(), dt=1e-3, abstol=1e-6, reltol=1e-6,
+                  callback=m.HistoryCallback(approx_order=3))
+    assert [a[3] for a in sol.log] == [a[3] for a in log_ref], "accept/reject sequence differs"
+    assert any(not a[3] for a in sol.log) and sum(a[3] for a in sol.log) >= 5
+    np.testing.assert_allclose([a[1] for a in sol.log], [a[1] for a in log_ref], rtol=1e-9)
+    assert abs(sol.t - t_ref) < 1e-15
+    assert cases.relerr(sol.u, u_ref) <= STEP_TOL
+    semi.close()

@@ -194,3 +194,22 @@ def test_pairwise_sum_matches_fsum():
     a = rng.standard_normal(100003)
     import math
     assert abs(orc.sum_pairwise(a) - math.fsum(a)) < 1e-10
+
+
+def test_ssprk43_error_estimate_is_third_order(fx):
+    """known answer for the SSPRK43 restatement (OrdinaryDiffEq is unpinned): the embedded estimate of a 3rd-order pair
+    scales as dt^3 on a smooth, BC-consistent state, and a state with rhs == 0 gives EEst == 0"""
+    bcs = dict(inlet="dirichlet", outlet="dirichlet", top="dirichlet", bottom="dirichlet", cyl="dirichlet")
+    P = _problem(fx, bcs=bcs, ic=cases.ic_smooth_euler)
+    u0 = cases.ic_smooth_euler(fx["points"], 0.0)
+    k = P.rhs(u0.copy(), 0.0)
+    e = [orc._ssprk43_step(P, u0.copy(), k, 0.0, dt, 1e-8, 1e-8)[2] for dt in (4e-3, 2e-3, 1e-3)]
+    assert 7.5 < e[0] / e[1] < 8.5 and 7.5 < e[1] / e[2] < 8.5
+    uc = np.ascontiguousarray(np.tile(np.array([[1.0], [0.3], [-0.2], [2.5]]), (1, u0.shape[1])))
+    Pc = orc.OracleProblem(fx["points"], 4, orc.EQ_EULER2D, [cases.GAMMA], fx["ops"][0], fx["ops"][1], [], [])
+    kc = Pc.rhs(uc.copy(), 0.0)
+    un, kn, ee = orc._ssprk43_step(Pc, uc.copy(), kc, 0.0, 1e-2, 1e-8, 1e-8)
+    assert ee < 1e-3 and np.abs(un - uc).max() < 1e-10     # constants are annihilated up to roundoff of D*1
+    # adaptive run: the controller accepts/rejects and ends exactly at t1
+    u, t, log = orc.solve_ssprk43(P, u0, 0.0, 0.03, 1e-3, abstol=1e-6, reltol=1e-6)
+    assert abs(t - 0.03) < 1e-15 and len(log) >= 5 and np.isfinite(u).all()
