@@ -993,128 +993,8 @@ __global__ void k_boundary(const BcArgs A)
 }
 
 // ---- reductions for update_residual_visc! (ode_mean / ode_maximum, src/auxiliary/mpi.jl:40-81) --------------
-// two-level and deterministic: every block writes one partial, a single-block kernel finishes.
-template <int V>
-__global__ void __launch_bounds__(256) k_reduce_sum(const Vec<V> *__restrict__ u, int64_t n, double *partial)
-{
-    double s[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) s[v] = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const Vec<V> x = ld_ro(u + i);
-#pragma unroll
-        for (int v = 0; v < V; ++v) s[v] += x.a[v];
-    }
-    __shared__ double sh[8][V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        for (int o = 16; o > 0; o >>= 1) s[v] += __shfl_down_sync(0xffffffffu, s[v], o);
-    }
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0)
-        for (int v = 0; v < V; ++v) sh[w][v] = s[v];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int v = 0; v < V; ++v) {
-            double t = 0.0;
-            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sh[k][v];
-            partial[(int64_t)blockIdx.x * V + v] = t;
-        }
-    }
-}
-
-// stats[0..V) = sum, then mean = sum / divisor in stats[V..2V)
-template <int V>
-__global__ void k_finish_mean(const double *partial, int nblocks, double divisor, double *stats)
-{
-    if (threadIdx.x < V) {
-        double t = 0.0;
-        for (int b = 0; b < nblocks; ++b) t += partial[(int64_t)b * V + threadIdx.x];
-        stats[threadIdx.x] = t;
-        stats[V + threadIdx.x] = t / divisor;
-    }
-}
-
-// LEX: maximum over SVector elements compares lexicographically (Base isless on vectors);
-// otherwise per-component NaN-propagating max.
-template <int V, bool LEX>
-__global__ void __launch_bounds__(256) k_reduce_maxdev(const Vec<V> *__restrict__ u, int64_t n, const double *mean,
-                                                     double *partial)
-{
-    double m[V], best[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        m[v] = mean[v];
-        best[v] = -1.0;  // |.| >= 0, so -1 is below every candidate
-    }
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const Vec<V> x = ld_ro(u + i);
-        double c[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) c[v] = fabs(x.a[v] - m[v]);
-        if constexpr (LEX) {
-            if (lex_less<V>(best, c)) {
-#pragma unroll
-                for (int v = 0; v < V; ++v) best[v] = c[v];
-            }
-        } else {
-#pragma unroll
-            for (int v = 0; v < V; ++v) best[v] = jl_max(best[v], c[v]);
-        }
-    }
-    auto combine = [&](double *a, const double *b) {
-        if constexpr (LEX) {
-            if (lex_less<V>(a, b)) {
-#pragma unroll
-                for (int v = 0; v < V; ++v) a[v] = b[v];
-            }
-        } else {
-#pragma unroll
-            for (int v = 0; v < V; ++v) a[v] = jl_max(a[v], b[v]);
-        }
-    };
-    for (int o = 16; o > 0; o >>= 1) {
-        double other[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) other[v] = __shfl_down_sync(0xffffffffu, best[v], o);
-        combine(best, other);
-    }
-    __shared__ double sh[8][V];
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0)
-        for (int v = 0; v < V; ++v) sh[w][v] = best[v];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) combine(best, sh[k]);
-        for (int v = 0; v < V; ++v) partial[(int64_t)blockIdx.x * V + v] = best[v];
-    }
-}
-
-// norms = max over partials; 0 -> eps()  (hyperviscosity.jl:310-311)
-template <int V, bool LEX>
-__global__ void k_finish_norms(const double *partial, int nblocks, double *norms, int replace_zero)
-{
-    if (threadIdx.x == 0) {
-        double best[V];
-        for (int v = 0; v < V; ++v) best[v] = partial[v];
-        for (int b = 1; b < nblocks; ++b) {
-            const double *c = partial + (int64_t)b * V;
-            if constexpr (LEX) {
-                if (lex_less<V>(best, c))
-                    for (int v = 0; v < V; ++v) best[v] = c[v];
-            } else {
-                for (int v = 0; v < V; ++v) best[v] = jl_max(best[v], c[v]);
-            }
-        }
-        for (int v = 0; v < V; ++v) {
-            if (replace_zero && best[v] == 0.0) best[v] = kEps;
-            norms[v] = best[v];
-        }
-    }
-}
-
-// Single-launch variants for one GPU: every block writes its partial, the last block to finish (atomic ticket)
-// combines the partials in a fixed order -> deterministic for a fixed grid size.
+// Single launch each: every block writes its partial, the last block to finish (atomic ticket) combines the partials
+// in a fixed order -> deterministic for a fixed grid size.
 template <int V>
 __global__ void __launch_bounds__(256) k_sum_mean(const Vec<V> *__restrict__ u, int64_t n, double *partial,
                                                 unsigned int *ticket, double divisor, double *stats)
@@ -1566,12 +1446,6 @@ __device__ __forceinline__ void p2p_publish(const P2PPeers &P, int which, int pa
         st_release_sys(which == 0 ? &w->sum_flag[par][P.rank] : &w->max_flag[par][P.rank], en);
     }
 }
-__device__ __forceinline__ void p2p_wait_all(const P2PPeers &P, P2PLocal *L, int which, int par, unsigned long long en)
-{
-    const P2PWindow *w = P.win[P.rank];
-    for (int r = 0; r < P.nranks; ++r) spin_until(which == 0 ? &w->sum_flag[par][r] : &w->max_flag[par][r], en, &L->error);
-}
-
 // local sum of the owned points -> published to all ranks (epoch en = epoch_n + 1)
 __global__ void __launch_bounds__(256) k_p2p_sum(const Vec<4> *__restrict__ u, int64_t n, double *partial, P2PPeers P, P2PLocal *L)
 {
@@ -1722,12 +1596,6 @@ __global__ void k_p2p_wait_norms(P2PPeers P, P2PLocal *L, int which, double *out
         if (which == 1)
             for (int v = 0; v < 4; ++v) out[r * 4 + v] = __ldcv(&win->maxs[par][r][v]);
     }
-}
-
-__global__ void k_fill_zero(double *p, int64_t len)
-{
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) p[i] = 0.0;
 }
 
 }  // namespace mft
