@@ -72,7 +72,9 @@ typedef struct mft_ctx mft_ctx;
 #define MFT_OPT_STAGE_WEIGHTS 5    /* bit 0 (forward operator, pass A) / bit 1 (transposed operator, pass B): 1 = a warp bulk-copies
                                       its whole operator slice (indices + weights) into shared memory, 0 = indices only, weights
                                       by coalesced loads + L2 bulk prefetch.  bit 2: exact-order pass A keeps ONE weight buffer and refills it with wy
-                                      after the x sweep (smaller footprint -> larger L1).  Default 5 (measured best). */
+                                      after the x sweep (smaller footprint -> larger L1).  Union-tile kernels: bit 0 / bit 1 stage the compact weight
+                                      blocks of one direction (two sweeps) unless that leaves too few blocks per SM; bit 3 forces it.
+                                      Default 5 (measured best). */
 #define MFT_OPT_REFINE_ORDER 7     /* 1 (default 0): within blocks of 256 device rows, order rows by D' row length
                                       (near-uniform transposed-ELL slices); the caller-visible numbering is unaffected */
 #define MFT_OPT_SINGLE_SWEEP_EXACT 8/* 1: for the default 20-wide stencil use the single-sweep exact kernel (y-products parked in registers:
@@ -82,6 +84,14 @@ typedef struct mft_ctx mft_ctx;
                                       An operator is stored per PAIR of consecutive rows (union of the two
                                       D' rows, zero weight where a row lacks an entry): each shared neighbour record is gathered once
                                       for both rows.  Same sums bit for bit.  0: one row per thread.                        */
+#define MFT_OPT_TILE 10            /* bit 0: pass A, bit 1: pass B run over "union tiles" (Euler 2-D): a block of 128 rows loads the
+                                      union of its stencils into shared memory once and rows read it with 16-bit local offsets
+                                      (mft_tile_kernels.cuh); bit 2: the slots of a tile are bank-coloured (fewer LDS conflicts);
+                                      bit 3: every record is kept twice under different bank assignments and each read picks the
+                                      copy that avoids a conflict.  Same sums bit for bit.  Default 15.                     */
+#define MFT_OPT_TILE_ROWS 11       /* rows per thread of the union-tile kernels, decimal digits: units = pass A, tens = pass B, each 1, 2
+                                      or 4 (e.g. 42 = pass B 4 rows, pass A 2 rows).  A thread walks the union of its rows' stencils
+                                      (16-bit word = slot | row mask << 12, weights compact per row).  Same sums bit for bit.   */
 #define MFT_OPT_PREFETCH_DISTANCE 6/* slices ahead for the L2 prefetch of the weight blocks (STAGE_WEIGHTS = 0)        */
 
 /* fields (mft_get_field): caches of create_tominec_rv_cache, hyperviscosity.jl:202-244 */
@@ -191,6 +201,13 @@ int mft_host_unregister(void *p);
 /* ---- setup helpers (host code, no GPU needed) ---------------------------------------------------------
  * Hilbert space-filling-curve order of a 2-D cloud: perm1_out[d] = 1-based index of the d-th point along the curve. */
 int mft_sfc_order(int64_t n, const double *x, const double *y, int64_t *perm1_out);
+
+/* Host-only self test of the union-tile operator format (MFT_OPT_TILE): lays out a random ragged banded operator for
+ * n points (k entries per row, R = 1, 2 or 4 rows per thread, layout bit 0 = bank colouring, bit 1 = two record copies,
+ * optional row permutation + order keys),
+ * replays the kernels' walk on the CPU and compares it bit for bit with plain row sums.  Returns 0 when identical.
+ * stats4 (nullable): mean LDS.128 bank-conflict degree, union steps per row, union entries per row, slots per tile. */
+int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int with_perm, unsigned seed, double *stats4);
 
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------------------------------------
  * replaces MPICache + perform_halo_update! (src/domains/PointCloudDomain/ParallelPointCloud.jl:6-71,

@@ -2,6 +2,7 @@
 // There is no CPU fallback anywhere in this file: every compute entry point needs a CUDA device.
 #include "../../include/mft_b200.h"
 #include "mft_kernels.cuh"
+#include "mft_tile_kernels.cuh"
 #include "mft_nccl.h"
 
 #include <algorithm>
@@ -98,6 +99,26 @@ struct DevEll {
     }
 };
 
+// union tiles with R rows per thread (mask-compressed weights), see mft_tile_kernels.cuh
+struct DevTileR {
+    DevBuf<unsigned char> blob;
+    DevBuf<long long> boff;
+    DevBuf<int> wl, uoff, ulist;
+    DevBuf<unsigned short> uslot;
+    int R = 0, nslices = 0, ntiles = 0, maxW = 0, maxL = 0, sstride = 0, ncopy = 1;
+    int64_t nnz = 0, nunion = 0, nsteps = 0;
+    bool ready() const { return blob.p != nullptr; }
+    void release()
+    {
+        blob.release();
+        boff.release();
+        wl.release();
+        uoff.release();
+        ulist.release();
+        uslot.release();
+    }
+};
+
 struct BcGroup {
     int kind;
     int64_t nb;
@@ -140,6 +161,10 @@ struct mft_ctx {
     Csr2 host_ell;  // from mft_set_operator_ell
     bool have_ell_input = false;
     DevEll fwd, fwd_pair, tra, tra_pair;
+    DevTileR fwd_tiler, tra_tiler;
+    int tile_rows_a = 1, tile_rows_b = 1;  // MFT_OPT_TILE_ROWS: rows per thread of the union-tile kernels (1, 2 or 4)
+    int stage_force = 0;
+    int tile = 15;  // MFT_OPT_TILE: bit 0 pass A, bit 1 pass B (Euler 2-D only), bit 2 bank-coloured slots, bit 3 two copies
     int pair_rows = 1;
     int two_phase = 1;
     // bcs, sources
@@ -328,6 +353,8 @@ extern "C" int mft_ctx_destroy(mft_ctx *c)
     c->tra.release();
     c->tra_pair.release();
     c->fwd_pair.release();
+    c->fwd_tiler.release();
+    c->tra_tiler.release();
     for (auto &h : c->hist) h.release();
     DevBuf<double> *bufs[] = {&c->utilde, &c->kfsal, &c->u_save, &c->u, &c->du, &c->uprev, &c->g, &c->approx_du, &c->stage_soa, &c->eps, &c->eps_uw,
                               &c->eps_rv, &c->eps_c, &c->residual, &c->partial, &c->stats, &c->send_buf, &c->gather_buf};
@@ -395,11 +422,19 @@ extern "C" int mft_set_option(mft_ctx *c, int option, double value)
     case MFT_OPT_MAX_LEXICOGRAPHIC: c->max_lex = value != 0; break;
     case MFT_OPT_DIAGNOSTICS: c->diagnostics = value != 0; break;
     case MFT_OPT_CUDA_GRAPH: c->use_graphs = (int)value; break;
-    case MFT_OPT_STAGE_WEIGHTS: c->stage_w = ((int)value & 1) != 0; c->stage_w_b = ((int)value & 2) != 0; c->two_phase = ((int)value & 4) != 0; break;
+    case MFT_OPT_STAGE_WEIGHTS: c->stage_w = ((int)value & 1) != 0; c->stage_w_b = ((int)value & 2) != 0; c->two_phase = ((int)value & 4) != 0; c->stage_force = ((int)value & 8) != 0; break;
     case MFT_OPT_PREFETCH_DISTANCE: c->pf_dist = (int)value; break;
     case MFT_OPT_REFINE_ORDER: c->refine_order = value != 0; break;
     case MFT_OPT_SINGLE_SWEEP_EXACT: c->kfix_ok = value != 0; break;
     case MFT_OPT_PAIR_ROWS: c->pair_rows = (int)value; break;
+    case MFT_OPT_TILE: c->tile = (int)value; break;
+    case MFT_OPT_TILE_ROWS: {
+        const int a = (int)value % 10, b = ((int)value / 10) % 10;
+        if ((a != 1 && a != 2 && a != 4) || (b != 1 && b != 2 && b != 4)) return fail(MFT_EINVAL, "MFT_OPT_TILE_ROWS: digits must be 1, 2 or 4");
+        c->tile_rows_a = a;
+        c->tile_rows_b = b;
+        break;
+    }
     default: return fail(MFT_EINVAL, "mft_set_option: unknown option %d", option);
     }
     return MFT_OK;
@@ -785,6 +820,438 @@ static int build_ell_pairs(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, DevEll 
     return MFT_OK;
 }
 
+// Union tiles (mft_tile_kernels.cuh).  Tile = kTileWarps slices; slice = 32 lanes x R rows: lane l of slice s owns device
+// rows (s*32 + l)*R + r and walks the union of their entries in summation order; step word = slot | row mask << 12; the
+// weights stay compact per row.  The tile's union list is sorted by device index (coalesced loads) and ends with the dummy
+// record; uslot[] gives each entry its shared-memory slot.  With `colour` the slots are chosen so that points requested
+// together by the 8 lanes of an LDS.128 phase fall into different 16-byte bank groups (slot mod 8) where possible:
+// greedy weighted colouring of the co-request graph + two refinement sweeps.
+struct HostTileR {
+    int R = 0, nslices = 0, ntiles = 0, maxW = 0, maxL = 0, sstride = 0, ncopy = 1;
+    int64_t nnz = 0, nsteps = 0;
+    std::vector<unsigned char> blob;
+    std::vector<long long> boff;
+    std::vector<int> wl, uoff, ulist;
+    std::vector<unsigned short> uslot;
+};
+
+static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, int R, bool colour, bool two_copies, HostTileR &out)
+{
+    if (R > 2) two_copies = false;  // the copy-select bit (14) is a row-mask bit for R = 4
+    uint64_t lcg = 0x9e3779b97f4a7c15ULL;
+    std::vector<int> slot1;
+    const int64_t rows_per_slice = (int64_t)kSlice * R, rows_per_tile = rows_per_slice * kTileWarps;
+    const int64_t nsl = (nrows_dev + rows_per_slice - 1) / rows_per_slice;
+    const int64_t ntl = (nrows_dev + rows_per_tile - 1) / rows_per_tile;
+    auto caller_row = [&](int64_t d) -> int64_t { return c->have_perm ? c->perm[d] : d; };
+    auto dev_col = [&](int64_t j) -> int { return c->have_perm ? c->iperm[j] : (int)j; };
+    auto key = [&](int32_t col) -> int64_t { return c->keys.empty() ? (int64_t)col : c->keys[col]; };
+    constexpr int NB = 8;  // 16-byte bank groups seen by one LDS.128 phase (8 lanes)
+    std::vector<long long> &boff = out.boff;
+    std::vector<int> &wl = out.wl, &uoff = out.uoff, &ulist = out.ulist;
+    std::vector<unsigned short> &uslot = out.uslot;
+    std::vector<unsigned char> &blob = out.blob;
+    boff.assign(nsl, 0);
+    wl.assign(2 * nsl, 0);
+    uoff.assign(ntl + 1, 0);
+    ulist.clear();
+    uslot.clear();
+    blob.clear();
+    std::vector<int> cols;
+    std::vector<int> node_of((size_t)c->n_tot + 1, -1);
+    blob.reserve((size_t)nrows_dev * 20 * 18);
+    struct Step { int node; unsigned mask; };
+    std::vector<std::vector<Step>> lanes((size_t)kTileWarps * kSlice);
+    std::vector<unsigned short> adj;   // nu x nu co-request counts
+    std::vector<int> slot, order, bank, deg, grp, nb_ptr, nb_idx, nb_w;
+    int max_slot = 0, maxW = 0, maxL = 0;
+    int64_t nnz = 0, nsteps = 0;
+    for (int64_t t = 0; t < ntl; ++t) {
+        const int64_t d0 = t * rows_per_tile, d1 = std::min(nrows_dev, d0 + rows_per_tile);
+        cols.clear();
+        for (int64_t d = d0; d < d1; ++d) {
+            const int64_t r = caller_row(d);
+            for (int64_t p = A.ptr[r]; p < A.ptr[r + 1]; ++p) {
+                const int j = dev_col(A.col[p]);
+                if (node_of[j] < 0) {
+                    node_of[j] = 0;
+                    cols.push_back(j);
+                }
+            }
+        }
+        std::sort(cols.begin(), cols.end());
+        const int nu = (int)cols.size();
+        for (int q = 0; q < nu; ++q) node_of[cols[q]] = q;
+        // lane step lists of the tile's slices: R-way merge by summation key
+        const int64_t s0 = d0 / rows_per_slice;
+        const int ns_tile = (int)((d1 - d0 + rows_per_slice - 1) / rows_per_slice);
+        for (int si = 0; si < ns_tile; ++si)
+            for (int l = 0; l < kSlice; ++l) {
+                std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
+                U.clear();
+                int64_t pp[4], ee[4];
+                for (int r = 0; r < R; ++r) {
+                    const int64_t d = ((s0 + si) * kSlice + l) * R + r;
+                    pp[r] = ee[r] = 0;
+                    if (d < nrows_dev) {
+                        const int64_t cr = caller_row(d);
+                        pp[r] = A.ptr[cr];
+                        ee[r] = A.ptr[cr + 1];
+                        nnz += ee[r] - pp[r];
+                    }
+                }
+                for (;;) {
+                    int best = -1;
+                    for (int r = 0; r < R; ++r)
+                        if (pp[r] < ee[r] && (best < 0 || key(A.col[pp[r]]) < key(A.col[pp[best]]))) best = r;
+                    if (best < 0) break;
+                    const int32_t col = A.col[pp[best]];
+                    Step st{node_of[dev_col(col)], 0u};
+                    for (int r = 0; r < R; ++r)
+                        if (pp[r] < ee[r] && A.col[pp[r]] == col) {
+                            st.mask |= 1u << r;
+                            ++pp[r];
+                        }
+                    U.push_back(st);
+                }
+            }
+        // slots
+        slot.assign(nu, 0);
+        int nslots = nu;
+        if (!colour || nu <= NB) {
+            for (int q = 0; q < nu; ++q) slot[q] = q;
+        } else {
+            adj.assign((size_t)nu * nu, 0);
+            for (int si = 0; si < ns_tile; ++si) {
+                size_t W = 0;
+                for (int l = 0; l < kSlice; ++l) W = std::max(W, lanes[(size_t)si * kSlice + l].size());
+                for (size_t cpos = 0; cpos < W; ++cpos)
+                    for (int ph = 0; ph < kSlice / NB; ++ph) {
+                        grp.clear();
+                        for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
+                            const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
+                            if (cpos < U.size() && std::find(grp.begin(), grp.end(), U[cpos].node) == grp.end()) grp.push_back(U[cpos].node);
+                        }
+                        for (size_t x = 0; x < grp.size(); ++x)
+                            for (size_t y = 0; y < grp.size(); ++y)
+                                if (x != y) {
+                                    unsigned short &e = adj[(size_t)grp[x] * nu + grp[y]];
+                                    if (e < 0xffff) ++e;
+                                }
+                    }
+            }
+            // adjacency lists (node, weight) from the dense counts
+            deg.assign(nu, 0);
+            nb_ptr.assign(nu + 1, 0);
+            nb_idx.clear();
+            nb_w.clear();
+            for (int a = 0; a < nu; ++a) {
+                const unsigned short *row = &adj[(size_t)a * nu];
+                int sum = 0;
+                for (int b = 0; b < nu; ++b)
+                    if (row[b]) {
+                        sum += row[b];
+                        nb_idx.push_back(b);
+                        nb_w.push_back(row[b]);
+                    }
+                deg[a] = sum;
+                nb_ptr[a + 1] = (int)nb_idx.size();
+            }
+            order.resize(nu);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return deg[a] > deg[b]; });
+            bank.assign(nu, -1);
+            int fill[NB] = {0};
+            auto choose = [&](int a) {
+                long long cost[NB] = {0};
+                for (int q = nb_ptr[a]; q < nb_ptr[a + 1]; ++q)
+                    if (bank[nb_idx[q]] >= 0) cost[bank[nb_idx[q]]] += nb_w[q];
+                int bestb = 0;
+                for (int k = 1; k < NB; ++k)   // ties -> emptiest bank group (keeps the slot count low)
+                    if (cost[k] < cost[bestb] || (cost[k] == cost[bestb] && fill[k] < fill[bestb])) bestb = k;
+                return bestb;
+            };
+            for (int a : order) {
+                bank[a] = choose(a);
+                ++fill[bank[a]];
+            }
+            for (int pass = 0; pass < 2; ++pass)
+                for (int a : order) {
+                    --fill[bank[a]];
+                    bank[a] = -1;
+                    bank[a] = choose(a);
+                    ++fill[bank[a]];
+                }
+            int level[NB] = {0};
+            nslots = 0;
+            for (int q = 0; q < nu; ++q) {
+                slot[q] = level[bank[q]]++ * NB + bank[q];
+                nslots = std::max(nslots, slot[q] + 1);
+            }
+        }
+        // second copy of the tile's records under an independent (pseudo-random) bank assignment: each distinct point a
+        // phase requests may then be read from either copy ("two choices"), which the emit loop below exploits
+        if (two_copies) {
+            slot1.resize(nu);   // a random permutation of 0..nu-1: balanced bank groups, independent of copy 0
+            std::iota(slot1.begin(), slot1.end(), 0);
+            for (int q = nu - 1; q > 0; --q) {
+                lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+                std::swap(slot1[q], slot1[(int)((lcg >> 33) % (uint64_t)(q + 1))]);
+            }
+            nslots = std::max(nslots, nu);
+        }
+        if (nslots + 1 > 4095) return fail(MFT_ENOTSUP, "union tile: %d slots in one block exceed the 12-bit slot field", nslots);
+        max_slot = std::max(max_slot, nslots);  // the dummy record takes slot `nslots`
+        // emit the slices
+        for (int si = 0; si < ns_tile; ++si) {
+            const int64_t s = s0 + si;
+            int W = 0, L = 0;
+            for (int l = 0; l < kSlice; ++l) {
+                W = std::max(W, (int)lanes[(size_t)si * kSlice + l].size());
+                for (int r = 0; r < R; ++r) {
+                    const int64_t d = (s * kSlice + l) * R + r;
+                    if (d < nrows_dev) {
+                        const int64_t cr = caller_row(d);
+                        L = std::max(L, (int)(A.ptr[cr + 1] - A.ptr[cr]));
+                    }
+                }
+            }
+            maxW = std::max(maxW, W);
+            maxL = std::max(maxL, L);
+            nsteps += W;
+            const size_t word_bytes = (size_t)W * kSlice * 2, wblk = (size_t)L * kSlice * 8;
+            const size_t at0 = blob.size();
+            boff[s] = (long long)at0;
+            wl[2 * s] = W;
+            wl[2 * s + 1] = L;
+            blob.resize(at0 + word_bytes + 2 * R * wblk, 0);
+            unsigned short *word = reinterpret_cast<unsigned short *>(blob.data() + at0);
+            for (int q = 0; q < W * kSlice; ++q) word[q] = (unsigned short)nslots;  // dummy slot, empty mask
+            for (int l = 0; l < kSlice; ++l) {
+                const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
+                for (size_t cpos = 0; cpos < U.size(); ++cpos)
+                    word[cpos * kSlice + l] = (unsigned short)(slot[U[cpos].node] | (U[cpos].mask << 12));
+            }
+            if (two_copies) {
+                // per step and LDS.128 phase (8 lanes): the copy of each distinct point that minimises the largest number of
+                // distinct addresses in one bank group (exhaustive over <= 2^8 choices)
+                for (int cpos = 0; cpos < W; ++cpos)
+                    for (int ph = 0; ph < kSlice / NB; ++ph) {
+                        grp.clear();
+                        for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
+                            const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
+                            if ((size_t)cpos < U.size() && std::find(grp.begin(), grp.end(), U[cpos].node) == grp.end()) grp.push_back(U[cpos].node);
+                        }
+                        const int kk = (int)grp.size();
+                        if (kk < 2) continue;
+                        int best_bits = 0, best_max = 99;
+                        for (int bits = 0; bits < (1 << kk) && best_max > 1; ++bits) {
+                            int cnt[NB] = {0}, mx = 0;
+                            for (int q = 0; q < kk; ++q) mx = std::max(mx, ++cnt[((bits >> q) & 1 ? slot1[grp[q]] : slot[grp[q]]) % NB]);
+                            if (mx < best_max) {
+                                best_max = mx;
+                                best_bits = bits;
+                            }
+                        }
+                        for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
+                            const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
+                            if ((size_t)cpos >= U.size()) continue;
+                            const int q = (int)(std::find(grp.begin(), grp.end(), U[cpos].node) - grp.begin());
+                            if ((best_bits >> q) & 1)
+                                word[(size_t)cpos * kSlice + l] = (unsigned short)(slot1[U[cpos].node] | (U[cpos].mask << 12) | 0x4000u);
+                        }
+                    }
+            }
+            for (int l = 0; l < kSlice; ++l) {
+                for (int r = 0; r < R; ++r) {
+                    const int64_t d = (s * kSlice + l) * R + r;
+                    if (d >= nrows_dev) continue;
+                    const int64_t cr = caller_row(d);
+                    double *wx = reinterpret_cast<double *>(blob.data() + at0 + word_bytes + (size_t)r * wblk);
+                    double *wy = reinterpret_cast<double *>(blob.data() + at0 + word_bytes + (size_t)(R + r) * wblk);
+                    int pos = 0;
+                    for (int64_t p = A.ptr[cr]; p < A.ptr[cr + 1]; ++p, ++pos) {
+                        wx[(size_t)pos * kSlice + l] = A.wx[p];
+                        wy[(size_t)pos * kSlice + l] = A.wy[p];
+                    }
+                }
+            }
+        }
+        for (int q = 0; q < nu; ++q) node_of[cols[q]] = -1;
+        ulist.insert(ulist.end(), cols.begin(), cols.end());
+        for (int q = 0; q < nu; ++q) {
+            uslot.push_back((unsigned short)slot[q]);
+            uslot.push_back((unsigned short)(two_copies ? slot1[q] : slot[q]));
+        }
+        ulist.push_back((int)c->n_tot);  // the dummy record (a finite state in u, zeros in g)
+        uslot.push_back((unsigned short)nslots);
+        uslot.push_back((unsigned short)nslots);
+        if (ulist.size() > 0x7fffffffULL) return fail(MFT_EINVAL, "union lists exceed 32-bit offsets");
+        uoff[t + 1] = (int)ulist.size();
+    }
+    blob.resize(blob.size() + 128, 0);
+    out.R = R;
+    out.nslices = (int)nsl;
+    out.ntiles = (int)ntl;
+    out.maxW = maxW;
+    out.maxL = maxL;
+    out.sstride = ((max_slot + 1 + 7) / 8) * 8;
+    out.nnz = nnz;
+    out.nsteps = nsteps;
+    out.ncopy = two_copies ? 2 : 1;
+    if (ulist.empty()) {
+        ulist.push_back(0);
+        uslot.push_back(0);
+        uslot.push_back(0);
+    }
+    return MFT_OK;
+}
+
+static int build_tiler(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, int R, bool colour, bool two_copies, DevTileR &out)
+{
+    HostTileR h;
+    CHECK(build_tiler_host(c, A, nrows_dev, R, colour, two_copies, h));
+    out.ncopy = h.ncopy;
+    out.R = h.R;
+    out.nslices = h.nslices;
+    out.ntiles = h.ntiles;
+    out.maxW = h.maxW;
+    out.maxL = h.maxL;
+    out.sstride = h.sstride;
+    out.nnz = h.nnz;
+    out.nunion = (int64_t)h.ulist.size();
+    out.nsteps = h.nsteps;
+    CHECK(out.blob.upload(h.blob));
+    CHECK(out.boff.upload(h.boff));
+    CHECK(out.wl.upload(h.wl));
+    CHECK(out.uoff.upload(h.uoff));
+    CHECK(out.ulist.upload(h.ulist));
+    CHECK(out.uslot.upload(h.uslot));
+    return MFT_OK;
+}
+
+// Host-only self test of the union-tile format (no CUDA calls): a random banded operator is laid out by
+// build_tiler_host, then the kernels' walk (step words, row masks, per-row weight cursors, slot table) is replayed on
+// the CPU and compared bit for bit with the plain row sums in summation order.  Returns 0 when identical.
+extern "C" int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int with_perm, unsigned seed, double *stats4)
+{
+    if (n <= 0 || k <= 0 || k > n || (R != 1 && R != 2 && R != 4)) return fail(MFT_EINVAL, "mft_debug_tile_selftest: bad arguments");
+    mft_ctx ctx;
+    ctx.n_local = n - n / 7;  // some trailing "halo" columns without rows
+    ctx.n_halo = n - ctx.n_local;
+    ctx.n_tot = n;
+    ctx.V = 4;
+    uint64_t st = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+    auto rnd = [&]() { st = st * 6364136223846793005ULL + 1442695040888963407ULL; return (uint32_t)(st >> 33); };
+    if (with_perm) {
+        ctx.have_perm = true;
+        ctx.perm.resize(n);
+        std::iota(ctx.perm.begin(), ctx.perm.end(), 0);
+        // shuffle inside windows so that locality survives (device rows near each other stay near)
+        for (int64_t b = 0; b < ctx.n_local; b += 64)
+            for (int64_t i = std::min(ctx.n_local, b + 64) - 1; i > b; --i) std::swap(ctx.perm[i], ctx.perm[b + rnd() % (i - b + 1)]);
+        ctx.iperm.resize(n);
+        for (int64_t d = 0; d < n; ++d) ctx.iperm[ctx.perm[d]] = (int32_t)d;
+        ctx.keys.resize(n);
+        for (int64_t i = 0; i < n; ++i) ctx.keys[i] = (int64_t)(n - 1 - i) * 3;  // descending keys: order != column order
+    }
+    Csr2 A;
+    A.nrows = n;
+    A.ptr.assign(n + 1, 0);
+    for (int64_t r = 0; r < n; ++r) {
+        const int len = r < ctx.n_local ? std::max(1, k - (int)(rnd() % 4)) : 0;   // ragged rows
+        std::vector<int32_t> cs;
+        while ((int)cs.size() < len) {
+            const int64_t j = std::min<int64_t>(n - 1, std::max<int64_t>(0, r + (int64_t)(rnd() % (6 * k)) - 3 * k));
+            if (std::find(cs.begin(), cs.end(), (int32_t)j) == cs.end()) cs.push_back((int32_t)j);
+        }
+        auto keyf = [&](int32_t col) { return ctx.keys.empty() ? (int64_t)col : ctx.keys[col]; };
+        std::sort(cs.begin(), cs.end(), [&](int32_t a, int32_t b) { return keyf(a) < keyf(b); });
+        for (int32_t j : cs) {
+            A.col.push_back(j);
+            A.wx.push_back((double)(int)(rnd() % 2001 - 1000) / 64.0);
+            A.wy.push_back((double)(int)(rnd() % 2001 - 1000) / 32.0);
+        }
+        A.ptr[r + 1] = (int64_t)A.col.size();
+    }
+    HostTileR h;
+    CHECK(build_tiler_host(&ctx, A, ctx.n_local, R, (layout & 1) != 0, (layout & 2) != 0, h));
+    std::vector<double> x((size_t)n + 1);
+    for (auto &v : x) v = (double)(int)(rnd() % 4001 - 2000) / 128.0;   // indexed by DEVICE column; x[n] = dummy record
+    auto caller_row = [&](int64_t d) -> int64_t { return ctx.have_perm ? ctx.perm[d] : d; };
+    auto dev_col = [&](int64_t j) -> int64_t { return ctx.have_perm ? ctx.iperm[j] : j; };
+    int64_t bad = 0, conflicts = 0, phases = 0;
+    std::vector<double> smem((size_t)h.sstride * 2);
+    for (int t = 0; t < h.ntiles; ++t) {
+        std::fill(smem.begin(), smem.end(), std::nan(""));
+        const int u0 = h.uoff[t], nu = h.uoff[t + 1] - u0;
+        for (int q = 0; q < nu; ++q) {
+            if (h.uslot[2 * (u0 + q)] >= h.sstride || h.uslot[2 * (u0 + q) + 1] >= h.sstride) return fail(MFT_EINVAL, "selftest: slot beyond sstride");
+            if (q > 0 && q < nu - 1 && h.ulist[u0 + q] <= h.ulist[u0 + q - 1]) return fail(MFT_EINVAL, "selftest: union list not ascending");
+            smem[h.uslot[2 * (u0 + q)]] = x[h.ulist[u0 + q]];
+            if (h.ncopy == 2) smem[h.sstride + h.uslot[2 * (u0 + q) + 1]] = x[h.ulist[u0 + q]];
+        }
+        if (h.ulist[u0 + nu - 1] != n) return fail(MFT_EINVAL, "selftest: tile list does not end with the dummy record");
+        const uint32_t dword = h.uslot[2 * (u0 + nu - 1)];
+        for (int w = 0; w < kTileWarps; ++w) {
+            const int64_t s = (int64_t)t * kTileWarps + w;
+            if (s >= h.nslices) break;
+            const int W = h.wl[2 * s], L = h.wl[2 * s + 1];
+            const unsigned char *src = h.blob.data() + h.boff[s];
+            const unsigned short *word = reinterpret_cast<const unsigned short *>(src);
+            const double *wx = reinterpret_cast<const double *>(src + (size_t)W * kSlice * 2);
+            const double *wy = wx + (size_t)R * L * kSlice;
+            for (int c0 = 0; c0 < W; ++c0)
+                for (int ph = 0; ph < 4; ++ph) {   // bank-conflict degree of this LDS.128 phase
+                    int cnt[8] = {0}, seen[8], ns = 0;
+                    for (int l = ph * 8; l < ph * 8 + 8; ++l) {
+                        const int sl = word[c0 * kSlice + l] & 0x4fff;   // slot + copy bit: distinct addresses
+                        bool dup = false;
+                        for (int q = 0; q < ns; ++q) dup |= seen[q] == sl;
+                        if (!dup) { seen[ns++] = sl; ++cnt[(sl & 0xfff) % 8]; }
+                    }
+                    conflicts += *std::max_element(cnt, cnt + 8);
+                    ++phases;
+                }
+            for (int l = 0; l < kSlice; ++l) {
+                double ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0};
+                int pos[4] = {0, 0, 0, 0};
+                for (int c0 = 0; c0 < W + 3; ++c0) {   // + batch tail steps
+                    const uint32_t wd = c0 < W ? word[c0 * kSlice + l] : dword;
+                    const double xv = smem[(wd & 0xfff) + ((R <= 2 && (wd & 0x4000u)) ? (size_t)h.sstride : 0)];
+                    for (int r = 0; r < R; ++r) {
+                        const bool m = (wd >> (12 + r)) & 1u;
+                        const double w1 = m ? wx[((size_t)r * L + pos[r]) * kSlice + l] : 0.0;
+                        const double w2 = m ? wy[((size_t)r * L + pos[r]) * kSlice + l] : 0.0;
+                        pos[r] += m;
+                        ax[r] = ax[r] + w1 * xv;
+                        ay[r] = ay[r] + w2 * xv;
+                    }
+                }
+                for (int r = 0; r < R; ++r) {
+                    const int64_t d = (s * kSlice + l) * R + r;
+                    if (d >= ctx.n_local) continue;
+                    const int64_t cr = caller_row(d);
+                    double rx = 0.0, ry = 0.0;
+                    for (int64_t p = A.ptr[cr]; p < A.ptr[cr + 1]; ++p) {
+                        rx = rx + A.wx[p] * x[dev_col(A.col[p])];
+                        ry = ry + A.wy[p] * x[dev_col(A.col[p])];
+                    }
+                    if (!(rx == ax[r] && ry == ay[r]) || pos[r] != (int)(A.ptr[cr + 1] - A.ptr[cr])) ++bad;
+                }
+            }
+        }
+    }
+    if (stats4) {
+        stats4[0] = phases ? (double)conflicts / (double)phases : 0.0;   // mean LDS.128 conflict degree
+        stats4[1] = (double)h.nsteps * kSlice / (double)std::max<int64_t>(1, ctx.n_local);  // union steps per row
+        stats4[2] = (double)h.ulist.size() / (double)std::max<int64_t>(1, ctx.n_local);    // union entries per row
+        stats4[3] = (double)h.sstride;
+    }
+    if (bad) return fail(MFT_EINVAL, "mft_debug_tile_selftest: %lld rows differ", (long long)bad);
+    return MFT_OK;
+}
+
 static bool has_visc(const mft_ctx *c)
 {
     for (auto *s : c->srcs)
@@ -839,10 +1306,14 @@ extern "C" int mft_finalize(mft_ctx *c)
     }
     // drop halo rows of the forward operator: only owned rows are computed here
     if (c->have_perm) CHECK(c->d_perm.upload(std::vector<int>(c->perm.begin(), c->perm.end())));
-    CHECK(build_ell(c, F, c->n_local, true, c->fwd));
-    if ((c->pair_rows & 2) && c->V == 4) CHECK(build_ell_pairs(c, F, c->n_local, c->fwd_pair));
+    const bool tile_a = (c->tile & 1) && c->V == 4 && c->eq == MFT_EQ_EULER2D;
+    const bool tile_b = (c->tile & 2) && c->V == 4 && c->eq == MFT_EQ_EULER2D;
+    if (tile_a) CHECK(build_tiler(c, F, c->n_local, c->tile_rows_a, (c->tile & 4) != 0, (c->tile & 8) != 0, c->fwd_tiler));
+    else CHECK(build_ell(c, F, c->n_local, true, c->fwd));
+    if (!tile_a && (c->pair_rows & 2) && c->V == 4) CHECK(build_ell_pairs(c, F, c->n_local, c->fwd_pair));
     if (has_visc(c)) {
-        if ((c->pair_rows & 1) && c->V == 4) CHECK(build_ell_pairs(c, T, c->n_local, c->tra_pair));
+        if (tile_b) CHECK(build_tiler(c, T, c->n_local, c->tile_rows_b, (c->tile & 4) != 0, (c->tile & 8) != 0, c->tra_tiler));
+        else if ((c->pair_rows & 1) && c->V == 4) CHECK(build_ell_pairs(c, T, c->n_local, c->tra_pair));
         else CHECK(build_ell(c, T, c->n_local, true, c->tra));
         CHECK(c->g.alloc((n + 1) * 2 * c->V));  // + zero dummy record
         CU(cudaMemset(c->g.p, 0, sizeof(double) * (n + 1) * 2 * c->V));
@@ -1177,16 +1648,95 @@ static int launch_pass_a_t(mft_ctx *c, const PassAArgs &a, bool do_flux, int vis
     return MFT_OK;
 }
 
+// per-warp staging buffer: the step words, plus (staged weights) the R compact weight blocks of one direction
+static TileROp tiler_view(const DevTileR &e, bool stage_w)
+{
+    const int bytes = std::max(e.maxW, 1) * kSlice * 2 + (stage_w ? e.R * std::max(e.maxL, 1) * kSlice * 8 : 0);
+    return TileROp{e.blob.p, e.boff.p, e.wl.p, e.uoff.p, e.ulist.p, e.uslot.p, e.sstride, e.ncopy, ((bytes + 127) / 128) * 128};
+}
+
+// staged weights keep at least `min_blocks` blocks per SM resident; otherwise stream them
+static bool tiler_stage(const mft_ctx *c, const DevTileR &e, int narrays, bool want, int min_blocks)
+{
+    if (!want || !c->exact) return false;
+    if (c->stage_force) min_blocks = 1;
+    const TileROp t = tiler_view(e, true);
+    const int smem = narrays * e.ncopy * t.sstride * 16 + kTileWarps * t.buf_bytes + 1024;
+    return smem * min_blocks <= 224 * 1024;
+}
+
+template <int R>
+static int launch_pass_a_tiler(mft_ctx *c, const PassAArgs &a0, bool do_flux, int visc)
+{
+    PassAArgs a = a0;
+    const DevTileR &e = c->fwd_tiler;
+    const bool stage = tiler_stage(c, e, 3, c->stage_w, R == 1 ? 4 : R == 2 ? 3 : 2);
+    const TileROp t = tiler_view(e, stage);
+    a.n_slices = e.nslices;
+    const int grid = e.ntiles;
+    const int smem = 3 * e.ncopy * t.sstride * 16 + kTileWarps * t.buf_bytes;
+    if (smem > 200 * 1024) return fail(MFT_ENOTSUP, "union tile: %d bytes of shared memory per block", smem);
+#define PAR(EX, DF, VI, ST)                                                                         \
+    do {                                                                                            \
+        CHECK(ensure_smem(c, k_pass_a_tiler<R, EX, DF, VI, ST>, smem));                             \
+        k_pass_a_tiler<R, EX, DF, VI, ST><<<grid, kTileWarps * 32, smem, c->stream>>>(a, t);       \
+    } while (0)
+#define PAR2(DF, VI)                                        \
+    do {                                                    \
+        if (!c->exact) PAR(false, DF, VI, false);           \
+        else if (stage) PAR(true, DF, VI, true);            \
+        else PAR(true, DF, VI, false);                      \
+    } while (0)
+    if (do_flux && visc == VISC_NONE) PAR2(true, VISC_NONE);
+    else if (do_flux && visc == VISC_UPWIND) PAR2(true, VISC_UPWIND);
+    else if (do_flux && visc == VISC_RESIDUAL) PAR2(true, VISC_RESIDUAL);
+    else if (!do_flux && visc == VISC_UPWIND) PAR2(false, VISC_UPWIND);
+    else if (!do_flux && visc == VISC_RESIDUAL) PAR2(false, VISC_RESIDUAL);
+    else return fail(MFT_EINVAL, "pass A: nothing to do");
+#undef PAR2
+#undef PAR
+    c->launches++;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}
+
+template <int R>
+static int launch_pass_b_tiler(mft_ctx *c)
+{
+    const DevTileR &e = c->tra_tiler;
+    const bool stage = tiler_stage(c, e, 4, c->stage_w_b, R == 1 ? 4 : R == 2 ? 3 : 2);
+    const TileROp t = tiler_view(e, stage);
+    PassBTileArgs a{c->g.p, c->du.p, c->n_local, e.nslices};
+    const int smem = 4 * e.ncopy * t.sstride * 16 + kTileWarps * t.buf_bytes;
+    if (smem > 200 * 1024) return fail(MFT_ENOTSUP, "union tile: %d bytes of shared memory per block", smem);
+#define PBR(EX, ST)                                                                                  \
+    do {                                                                                             \
+        CHECK(ensure_smem(c, k_pass_b_tiler<R, EX, ST>, smem));                                      \
+        k_pass_b_tiler<R, EX, ST><<<e.ntiles, kTileWarps * 32, smem, c->stream>>>(a, t);            \
+    } while (0)
+    if (!c->exact) PBR(false, false);
+    else if (stage) PBR(true, true);
+    else PBR(true, false);
+#undef PBR
+    c->launches++;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}
+
 static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bool accumulate)
 {
     ScopedTimer t(c, MFT_K_PASS_A);
     PassAArgs a{};
-    const bool use_pair = do_flux && c->V == 4 && c->fwd_pair.blob.p != nullptr;
-    a.op = c->fwd.view();
-    a.n_slices = c->fwd.nslices;
-    a.buf_bytes = warp_buf_bytes(c->fwd, stage_whole_slice(c, c->fwd, c->stage_w));
-    a.two_phase = c->two_phase && c->exact && stage_whole_slice(c, c->fwd, c->stage_w);
-    if (a.two_phase) a.buf_bytes = ((std::max(c->fwd.maxw, 1) * kSlice * 12 + 127) / 128) * 128;
+    const bool use_tiler = c->fwd_tiler.ready();
+    const bool use_tile = use_tiler;
+    const bool use_pair = !use_tile && do_flux && c->V == 4 && c->fwd_pair.blob.p != nullptr;
+    if (!use_tile) {
+        a.op = c->fwd.view();
+        a.n_slices = c->fwd.nslices;
+        a.buf_bytes = warp_buf_bytes(c->fwd, stage_whole_slice(c, c->fwd, c->stage_w));
+        a.two_phase = c->two_phase && c->exact && stage_whole_slice(c, c->fwd, c->stage_w);
+        if (a.two_phase) a.buf_bytes = ((std::max(c->fwd.maxw, 1) * kSlice * 12 + 127) / 128) * 128;
+    }
     a.pf_dist = c->pf_dist;
     a.dummy = (int)c->n_tot;
     a.u = c->u.p;
@@ -1216,6 +1766,10 @@ static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bo
         a.eps_rv = c->eps_rv.p;
         a.eps_c = c->eps_c.p;
         a.residual = c->residual.p;
+    }
+    if (use_tiler) {
+        const int R = c->fwd_tiler.R;
+        return R == 1 ? launch_pass_a_tiler<1>(c, a, do_flux, visc) : R == 2 ? launch_pass_a_tiler<2>(c, a, do_flux, visc) : launch_pass_a_tiler<4>(c, a, do_flux, visc);
     }
     if (use_pair) {
         const DevEll &e = c->fwd_pair;
@@ -1250,6 +1804,10 @@ static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bo
 static int launch_pass_b(mft_ctx *c)
 {
     ScopedTimer t(c, MFT_K_PASS_B);
+    if (c->tra_tiler.ready()) {
+        const int R = c->tra_tiler.R;
+        return R == 1 ? launch_pass_b_tiler<1>(c) : R == 2 ? launch_pass_b_tiler<2>(c) : launch_pass_b_tiler<4>(c);
+    }
     if (c->tra_pair.blob.p) {
         const DevEll &e = c->tra_pair;
         PassBPairArgs a{e.view(), c->g.p, c->du.p, c->n_local, e.nslices, ((std::max(e.maxw, 1) * kSlice * 4 + 127) / 128) * 128, (int)c->n_tot};

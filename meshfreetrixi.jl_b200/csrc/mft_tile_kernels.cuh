@@ -1,0 +1,479 @@
+// mft_tile_kernels.cuh -- "union tile" variants of pass A / pass B for Euler 2-D (V = 4).
+//
+// The thread-per-row gathers of k_pass_a / k_pass_b go through the L1 data pipe at one wavefront per distinct 32-byte
+// sector (~20 per 32-lane request; profiles/README.md).  A block of consecutive device rows is a compact patch of the
+// cloud (Hilbert order) and the UNION of its stencils is only 1.4-1.9 points per row (tools/tile_sim.py).  So:
+//
+//   phase 1  the block loads the union ONCE with near-coalesced 256-bit loads (the union list is sorted), evaluates the
+//            two IEEE divisions v = m / rho ONCE per union point, and stores the records in shared memory as 16-byte
+//            units  A[s] = (rho, m1)  B[s] = (m2, E)  C[s] = (v1, v2)          (pass B:  A..D = gx01 gx23 gy01 gy23)
+//   phase 2  thread per R rows; every neighbour access is 3 (4) LDS.128 at a 12-bit local slot; the flux is rebuilt
+//            from (u, v1, v2) with the reference's operations, so sums are bit-identical to k_pass_a.
+//
+// Indices cost 2 bytes per entry instead of 4; the union lists add ~6 bytes per row and union point.
+#pragma once
+#include "mft_kernels.cuh"
+
+namespace mft {
+
+constexpr int kTileWarps = 4;
+
+__device__ __forceinline__ double2 lds2(const unsigned char *arr, uint32_t off)
+{
+    return *reinterpret_cast<const double2 *>(arr + off);
+}
+
+struct PassBTileArgs {
+    const void *g;
+    void *du;
+    int64_t n_rows;
+    int64_t n_slices;
+};
+
+// =====================================================================================================================
+// R rows per thread over union tiles.
+//
+// With one row per thread the kernels are bound by the shared-memory wavefront rate (ncu, profiles/r1_tile_*: l1tex
+// data pipe 71 % busy, 1076 shared wavefronts per 32 rows, 1.9-way bank conflicts on the scattered LDS.128).  Two levers:
+//  * rows that are consecutive along the curve share ~3/4 of their stencil, so a thread that owns R consecutive rows and
+//    walks the UNION of their stencils reads every shared neighbour record once for all R rows: 13.5 (R=2) / 8.3 (R=4)
+//    union steps per row instead of 20;
+//  * the slot of a union point is ours to choose: the builder colours the points of a tile with the 8 bank groups so
+//    that the points requested together by the 8 lanes of an LDS.128 phase fall into different groups (1.6-way instead
+//    of 1.9 / 2.1 / 2.5-way for R = 1 / 2 / 4).  uslot[] maps the sorted union list to the slots; the last entry of every
+//    tile's list is the dummy record (a finite state / zeros) that padding steps point at.
+// A step carries a 16-bit word  slot | mask << 12  (mask bit r: row r has this entry); the weights stay COMPACT per
+// row (no explicit zeros, HBM traffic = nnz): a row advances its own cursor when its mask bit is set.  Where a row
+// lacks the entry it adds w = 0 times a finite value, i.e. an exact zero, so the sums are unchanged bit for bit.
+//
+// Slice = 32 lanes x R rows (device rows slice*32R + lane*R + r).  Blob of a slice, 16-byte aligned:
+//   [ word : W x 32 x uint16 ][ wx_0 : L x 32 x f64 ] .. [ wx_{R-1} ][ wy_0 ] .. [ wy_{R-1} ]
+// W = longest lane union, L = longest row of the slice.  Weights are streamed from global memory (coalesced up to the
+// cursor skew between lanes); only the word block is staged in shared memory (bulk async copy).
+struct TileROp {
+    const unsigned char *base;
+    const long long *boff;  // n_slices: byte offset of the slice blob
+    const int *wl;          // n_slices x 2: W, L
+    const int *uoff;        // n_tiles + 1 offsets into ulist / uslot
+    const int *ulist;       // device indices of the tile's union, ascending; last entry of a tile = the dummy record
+    const unsigned short *uslot;  // shared-memory slots of each entry: (copy 0, copy 1)
+    int sstride;            // 16-byte units per shared array copy (> largest slot)
+    int ncopy;              // 1, or 2: every record is stored twice under different bank assignments; bit 14 of a step
+                            // word selects the copy (R <= 2), chosen by the builder to avoid bank conflicts in the phase
+    int buf_bytes;          // per-warp staging buffer (word block)
+};
+
+// STAGE_W (exact order only): the warp also stages its compact weight blocks in shared memory -- wx_0..wx_{R-1} with the
+// step words (one bulk copy), wy_* over them after the x sweep.  A row's cursor then indexes a lane-private column of
+// shared memory (bank = lane, conflict-free) instead of issuing a global load whose lanes sit at different cursors.
+template <int R, bool EXACT, bool DO_FLUX, int VISC, bool STAGE_W>
+__global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)) k_pass_a_tiler(const PassAArgs A, const TileROp T)
+{
+    static_assert(EXACT || !STAGE_W, "staged weights: exact-order (two sweep) mode only");
+    constexpr int V = 4;
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ uint64_t bars[kTileWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t slice = (int64_t)blockIdx.x * kTileWarps + warp;
+    const bool has_slice = slice < A.n_slices;
+    const int64_t row0 = (slice * kSlice + lane) * R;
+    const uint32_t arr_bytes = (uint32_t)T.sstride * 16u, nc = (uint32_t)T.ncopy;
+    unsigned char *sA = smem_dyn, *sB = smem_dyn + nc * arr_bytes, *sC = smem_dyn + 2 * nc * arr_bytes;
+    unsigned char *buf = smem_dyn + 3 * nc * arr_bytes + (size_t)warp * T.buf_bytes;
+
+    int W = 0, L = 0;
+    const unsigned char *src = nullptr;
+    if (has_slice) {
+        W = T.wl[2 * slice];
+        L = T.wl[2 * slice + 1];
+        src = T.base + T.boff[slice];
+        if (lane == 0) mbar_init(&bars[warp], 1);
+        __syncwarp();
+        if (lane == 0 && W > 0) {
+            const uint32_t wbytes = (uint32_t)L * kSlice * 8 * R;  // one direction, all R rows
+            const uint32_t bytes = (uint32_t)W * kSlice * 2 + (STAGE_W ? wbytes : 0u);
+            mbar_expect_tx(&bars[warp], bytes);
+            bulk_g2s(buf, src, bytes, &bars[warp]);
+            if (wbytes > 0) bulk_prefetch_l2(src + (size_t)W * kSlice * 2 + (STAGE_W ? wbytes : 0u), wbytes);
+        }
+    }
+    const unsigned short *ip = reinterpret_cast<const unsigned short *>(buf) + lane;
+    const double *wbase = reinterpret_cast<const double *>((STAGE_W ? buf : src) + (size_t)W * kSlice * 2) + lane;  // wx_0
+    const size_t rstride = (size_t)L * kSlice;                                                    // doubles per weight block
+    const Vec<V> *__restrict__ u = reinterpret_cast<const Vec<V> *>(A.u);
+
+    const int u0 = T.uoff[blockIdx.x];
+    const int nu = T.uoff[blockIdx.x + 1] - u0;
+    for (int t = threadIdx.x; t < nu; t += kTileWarps * 32) {
+        const int j = __ldg(T.ulist + u0 + t);
+        const unsigned int sl2 = __ldg(reinterpret_cast<const unsigned int *>(T.uslot) + u0 + t);
+        const int sl = (int)(sl2 & 0xffffu);
+        const Vec<V> x = ld_ro(u + j);
+        const double v1 = x.a[1] / x.a[0];
+        const double v2 = x.a[2] / x.a[0];
+        reinterpret_cast<double2 *>(sA)[sl] = make_double2(x.a[0], x.a[1]);
+        reinterpret_cast<double2 *>(sB)[sl] = make_double2(x.a[2], x.a[3]);
+        reinterpret_cast<double2 *>(sC)[sl] = make_double2(v1, v2);
+        if (nc == 2) {
+            const int s1 = (int)(sl2 >> 16) + T.sstride;
+            reinterpret_cast<double2 *>(sA)[s1] = make_double2(x.a[0], x.a[1]);
+            reinterpret_cast<double2 *>(sB)[s1] = make_double2(x.a[2], x.a[3]);
+            reinterpret_cast<double2 *>(sC)[s1] = make_double2(v1, v2);
+        }
+    }
+    const uint32_t dword = nu > 0 ? (uint32_t)__ldg(T.uslot + 2 * (u0 + nu - 1)) : 0u;  // dummy slot (copy 0), empty mask
+
+    Vec<V> acc[R], gx[R], gy[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[r].a[v] = gx[r].a[v] = gy[r].a[v] = 0.0;
+        if (DO_FLUX && A.accumulate && has_slice && row0 + r < A.n_rows) acc[r] = reinterpret_cast<const Vec<V> *>(A.du)[row0 + r];
+    }
+    __syncthreads();
+    if (!has_slice) return;
+    if (W > 0) mbar_wait(&bars[warp], 0);
+
+    const double gm1 = A.eqp0 - 1.0;
+    constexpr int kBatch = R <= 2 ? 4 : 2;
+    auto pressure = [&](const double2 &qa, const double2 &qb, const double2 &qc) {
+        const double s = fma(qa.y, qc.x, qb.x * qc.y);
+        const double e = fma(-0.5, s, qb.y);
+        return gm1 * e;
+    };
+    if constexpr (EXACT) {
+        auto sweep = [&](auto dir_tag) {
+            constexpr int DIR = decltype(dir_tag)::value;
+            if (STAGE_W && DIR == 1 && W > 0 && L > 0) {
+                // every lane is done with wx: the weight buffer is refilled with the wy blocks (prefetched into L2)
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    const uint32_t wbytes = (uint32_t)L * kSlice * 8 * R;
+                    mbar_expect_tx(&bars[warp], wbytes);
+                    bulk_g2s(buf + (size_t)W * kSlice * 2, src + (size_t)W * kSlice * 2 + wbytes, wbytes, &bars[warp]);
+                }
+                mbar_wait(&bars[warp], 1);
+            }
+            const double *wd = wbase + (STAGE_W ? (size_t)0 : (size_t)DIR * R * rstride);
+            int pos[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) pos[r] = 0;
+            for (int c0 = 0; c0 < W; c0 += kBatch) {
+                double2 qa[kBatch], qb[kBatch], qc[kBatch];
+                double w[kBatch][R];
+#pragma unroll
+                for (int b = 0; b < kBatch; ++b) {
+                    const bool ok = c0 + b < W;
+                    const int cc = ok ? c0 + b : W - 1;
+                    const uint32_t word = ok ? (uint32_t)ip[cc * kSlice] : dword;
+                    const uint32_t o = ((word & 0xfffu) << 4) + (R <= 2 ? ((word >> 14) & 1u) * arr_bytes : 0u);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const bool m = (word >> (12 + r)) & 1u;
+                        w[b][r] = 0.0;
+                        if (m) w[b][r] = STAGE_W ? wd[r * rstride + (size_t)pos[r] * kSlice] : ld_stream(wd + r * rstride + (size_t)pos[r] * kSlice);
+                        pos[r] += m ? 1 : 0;
+                    }
+                    qa[b] = lds2(sA, o);
+                    qb[b] = lds2(sB, o);
+                    qc[b] = lds2(sC, o);
+                }
+#pragma unroll
+                for (int b = 0; b < kBatch; ++b) {
+                    if constexpr (DO_FLUX) {
+                        const double p = pressure(qa[b], qb[b], qc[b]);
+                        double f[4];
+                        if constexpr (DIR == 0) {
+                            f[0] = qa[b].y;
+                            f[1] = fma(qa[b].y, qc[b].x, p);
+                            f[2] = qa[b].y * qc[b].y;
+                            f[3] = (qb[b].y + p) * qc[b].x;
+                        } else {
+                            f[0] = qb[b].x;
+                            f[1] = qb[b].x * qc[b].x;
+                            f[2] = fma(qb[b].x, qc[b].y, p);
+                            f[3] = (qb[b].y + p) * qc[b].y;
+                        }
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+#pragma unroll
+                            for (int v = 0; v < V; ++v) acc[r].a[v] = acc[r].a[v] + w[b][r] * (-f[v]);
+                        }
+                    }
+                    if constexpr (VISC != VISC_NONE) {
+                        const double uu[4] = {qa[b].x, qa[b].y, qb[b].x, qb[b].y};
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+#pragma unroll
+                            for (int v = 0; v < V; ++v) {
+                                if constexpr (DIR == 0) gx[r].a[v] = gx[r].a[v] + w[b][r] * uu[v];
+                                else gy[r].a[v] = gy[r].a[v] + w[b][r] * uu[v];
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        sweep(std::integral_constant<int, 0>{});
+        sweep(std::integral_constant<int, 1>{});
+    } else {
+        const double *wdx = wbase, *wdy = wbase + (size_t)R * rstride;
+        int pos[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) pos[r] = 0;
+        for (int c0 = 0; c0 < W; c0 += kBatch) {
+            double2 qa[kBatch], qb[kBatch], qc[kBatch];
+            double wa[kBatch][R], wb[kBatch][R];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const bool ok = c0 + b < W;
+                const int cc = ok ? c0 + b : W - 1;
+                const uint32_t word = ok ? (uint32_t)ip[cc * kSlice] : dword;
+                const uint32_t o = ((word & 0xfffu) << 4) + (R <= 2 ? ((word >> 14) & 1u) * arr_bytes : 0u);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const bool m = (word >> (12 + r)) & 1u;
+                    wa[b][r] = wb[b][r] = 0.0;
+                    if (m) {
+                        wa[b][r] = ld_stream(wdx + r * rstride + (size_t)pos[r] * kSlice);
+                        wb[b][r] = ld_stream(wdy + r * rstride + (size_t)pos[r] * kSlice);
+                    }
+                    pos[r] += m ? 1 : 0;
+                }
+                qa[b] = lds2(sA, o);
+                qb[b] = lds2(sB, o);
+                qc[b] = lds2(sC, o);
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const double uu[4] = {qa[b].x, qa[b].y, qb[b].x, qb[b].y};
+                if constexpr (DO_FLUX) {
+                    const double p = pressure(qa[b], qb[b], qc[b]);
+                    const double f[4] = {qa[b].y, fma(qa[b].y, qc[b].x, p), qa[b].y * qc[b].y, (qb[b].y + p) * qc[b].x};
+                    const double h[4] = {qb[b].x, qb[b].x * qc[b].x, fma(qb[b].x, qc[b].y, p), (qb[b].y + p) * qc[b].y};
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) acc[r].a[v] = fma(-wb[b][r], h[v], fma(-wa[b][r], f[v], acc[r].a[v]));
+                    }
+                }
+                if constexpr (VISC != VISC_NONE) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            gx[r].a[v] = fma(wa[b][r], uu[v], gx[r].a[v]);
+                            gy[r].a[v] = fma(wb[b][r], uu[v], gy[r].a[v]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t row = row0 + r;
+        if (row < A.n_rows) {
+            Vec<V> ui, ad;
+#pragma unroll
+            for (int v = 0; v < V; ++v) ui.a[v] = ad.a[v] = 0.0;
+            if constexpr (VISC != VISC_NONE) {
+                ui = ld_ro(u + row);
+                if constexpr (VISC == VISC_RESIDUAL) ad = ld_ro(reinterpret_cast<const Vec<V> *>(A.approx_du) + row);
+            }
+            pass_a_epilogue<V, EQ_EULER2D, DO_FLUX, VISC>(A, row, acc[r], gx[r], gy[r], ui, ad);
+        }
+    }
+}
+
+// STAGE_W: two sweeps (the x chain with wx_* over arrays A,B, then the y chain with wy_* over C,D -- the chains are
+// independent, so splitting them changes no sum), each with its weight blocks staged like pass A.
+template <int R, bool EXACT, bool STAGE_W>
+__global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)) k_pass_b_tiler(const PassBTileArgs A, const TileROp T)
+{
+    constexpr int V = 4;
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ uint64_t bars[kTileWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t slice = (int64_t)blockIdx.x * kTileWarps + warp;
+    const bool has_slice = slice < A.n_slices;
+    const int64_t row0 = (slice * kSlice + lane) * R;
+    const uint32_t arr_bytes = (uint32_t)T.sstride * 16u, nc = (uint32_t)T.ncopy;
+    unsigned char *sA = smem_dyn, *sB = smem_dyn + nc * arr_bytes, *sC = smem_dyn + 2 * nc * arr_bytes, *sD = smem_dyn + 3 * nc * arr_bytes;
+    unsigned char *buf = smem_dyn + 4 * nc * arr_bytes + (size_t)warp * T.buf_bytes;
+
+    int W = 0, L = 0;
+    const unsigned char *src = nullptr;
+    if (has_slice) {
+        W = T.wl[2 * slice];
+        L = T.wl[2 * slice + 1];
+        src = T.base + T.boff[slice];
+        if (lane == 0) mbar_init(&bars[warp], 1);
+        __syncwarp();
+        if (lane == 0 && W > 0) {
+            const uint32_t wbytes = (uint32_t)L * kSlice * 8 * R;
+            const uint32_t bytes = (uint32_t)W * kSlice * 2 + (STAGE_W ? wbytes : 0u);
+            mbar_expect_tx(&bars[warp], bytes);
+            bulk_g2s(buf, src, bytes, &bars[warp]);
+            if (wbytes > 0) {
+                if (STAGE_W) bulk_prefetch_l2(src + (size_t)W * kSlice * 2 + wbytes, wbytes);
+                else bulk_prefetch_l2(src + (size_t)W * kSlice * 2, 2 * wbytes);
+            }
+        }
+    }
+    const unsigned short *ip = reinterpret_cast<const unsigned short *>(buf) + lane;
+    const double *wdx = reinterpret_cast<const double *>((STAGE_W ? buf : src) + (size_t)W * kSlice * 2) + lane;
+    const size_t rstride = (size_t)L * kSlice;
+    const double *wdy = wdx + (STAGE_W ? (size_t)0 : (size_t)R * rstride);
+    const Vec<2 * V> *__restrict__ g = reinterpret_cast<const Vec<2 * V> *>(A.g);
+
+    const int u0 = T.uoff[blockIdx.x];
+    const int nu = T.uoff[blockIdx.x + 1] - u0;
+    for (int t = threadIdx.x; t < nu; t += kTileWarps * 32) {
+        const int j = __ldg(T.ulist + u0 + t);
+        const unsigned int sl2 = __ldg(reinterpret_cast<const unsigned int *>(T.uslot) + u0 + t);
+        const int sl = (int)(sl2 & 0xffffu);
+        const Vec<2 * V> x = ld_ro(g + j);
+        reinterpret_cast<double2 *>(sA)[sl] = make_double2(x.a[0], x.a[1]);
+        reinterpret_cast<double2 *>(sB)[sl] = make_double2(x.a[2], x.a[3]);
+        reinterpret_cast<double2 *>(sC)[sl] = make_double2(x.a[4], x.a[5]);
+        reinterpret_cast<double2 *>(sD)[sl] = make_double2(x.a[6], x.a[7]);
+        if (nc == 2) {
+            const int s1 = (int)(sl2 >> 16) + T.sstride;
+            reinterpret_cast<double2 *>(sA)[s1] = make_double2(x.a[0], x.a[1]);
+            reinterpret_cast<double2 *>(sB)[s1] = make_double2(x.a[2], x.a[3]);
+            reinterpret_cast<double2 *>(sC)[s1] = make_double2(x.a[4], x.a[5]);
+            reinterpret_cast<double2 *>(sD)[s1] = make_double2(x.a[6], x.a[7]);
+        }
+    }
+    const uint32_t dword = nu > 0 ? (uint32_t)__ldg(T.uslot + 2 * (u0 + nu - 1)) : 0u;
+    Vec<V> tx[R], ty[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) tx[r].a[v] = ty[r].a[v] = 0.0;
+    }
+    __syncthreads();
+    if (!has_slice) return;
+    if (W > 0) mbar_wait(&bars[warp], 0);
+
+    constexpr int kBatch = R <= 2 ? 4 : 2;
+    if constexpr (STAGE_W) {
+        auto sweep = [&](auto dir_tag) {
+            constexpr int DIR = decltype(dir_tag)::value;
+            if (DIR == 1 && W > 0 && L > 0) {
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    const uint32_t wbytes = (uint32_t)L * kSlice * 8 * R;
+                    mbar_expect_tx(&bars[warp], wbytes);
+                    bulk_g2s(buf + (size_t)W * kSlice * 2, src + (size_t)W * kSlice * 2 + wbytes, wbytes, &bars[warp]);
+                }
+                mbar_wait(&bars[warp], 1);
+            }
+            const unsigned char *s0 = DIR == 0 ? sA : sC, *s1 = DIR == 0 ? sB : sD;
+            int pos[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) pos[r] = 0;
+            for (int c0 = 0; c0 < W; c0 += kBatch) {
+                double2 qa[kBatch], qb[kBatch];
+                double w[kBatch][R];
+#pragma unroll
+                for (int b = 0; b < kBatch; ++b) {
+                    const bool ok = c0 + b < W;
+                    const int cc = ok ? c0 + b : W - 1;
+                    const uint32_t word = ok ? (uint32_t)ip[cc * kSlice] : dword;
+                    const uint32_t o = ((word & 0xfffu) << 4) + (R <= 2 ? ((word >> 14) & 1u) * arr_bytes : 0u);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const bool m = (word >> (12 + r)) & 1u;
+                        w[b][r] = 0.0;
+                        if (m) w[b][r] = wdx[r * rstride + (size_t)pos[r] * kSlice];
+                        pos[r] += m ? 1 : 0;
+                    }
+                    qa[b] = lds2(s0, o);
+                    qb[b] = lds2(s1, o);
+                }
+#pragma unroll
+                for (int b = 0; b < kBatch; ++b) {
+                    const double gv[4] = {qa[b].x, qa[b].y, qb[b].x, qb[b].y};
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            if constexpr (DIR == 0) {
+                                if constexpr (EXACT) tx[r].a[v] = tx[r].a[v] + w[b][r] * gv[v];
+                                else tx[r].a[v] = fma(w[b][r], gv[v], tx[r].a[v]);
+                            } else {
+                                if constexpr (EXACT) ty[r].a[v] = ty[r].a[v] + w[b][r] * gv[v];
+                                else ty[r].a[v] = fma(w[b][r], gv[v], ty[r].a[v]);
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        sweep(std::integral_constant<int, 0>{});
+        sweep(std::integral_constant<int, 1>{});
+    } else {
+        int pos[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) pos[r] = 0;
+        for (int c0 = 0; c0 < W; c0 += kBatch) {
+            double2 qa[kBatch], qb[kBatch], qc[kBatch], qd[kBatch];
+            double wa[kBatch][R], wb[kBatch][R];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const bool ok = c0 + b < W;
+                const int cc = ok ? c0 + b : W - 1;
+                const uint32_t word = ok ? (uint32_t)ip[cc * kSlice] : dword;
+                const uint32_t o = ((word & 0xfffu) << 4) + (R <= 2 ? ((word >> 14) & 1u) * arr_bytes : 0u);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const bool m = (word >> (12 + r)) & 1u;
+                    wa[b][r] = wb[b][r] = 0.0;
+                    if (m) {
+                        wa[b][r] = ld_stream(wdx + r * rstride + (size_t)pos[r] * kSlice);
+                        wb[b][r] = ld_stream(wdy + r * rstride + (size_t)pos[r] * kSlice);
+                    }
+                    pos[r] += m ? 1 : 0;
+                }
+                qa[b] = lds2(sA, o);
+                qb[b] = lds2(sB, o);
+                qc[b] = lds2(sC, o);
+                qd[b] = lds2(sD, o);
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const double gxv[4] = {qa[b].x, qa[b].y, qb[b].x, qb[b].y};
+                const double gyv[4] = {qc[b].x, qc[b].y, qd[b].x, qd[b].y};
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        if constexpr (EXACT) {
+                            tx[r].a[v] = tx[r].a[v] + wa[b][r] * gxv[v];
+                            ty[r].a[v] = ty[r].a[v] + wb[b][r] * gyv[v];
+                        } else {
+                            tx[r].a[v] = fma(wa[b][r], gxv[v], tx[r].a[v]);
+                            ty[r].a[v] = fma(wb[b][r], gyv[v], ty[r].a[v]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t row = row0 + r;
+        if (row < A.n_rows) {
+            Vec<V> d = reinterpret_cast<const Vec<V> *>(A.du)[row];
+#pragma unroll
+            for (int v = 0; v < V; ++v) d.a[v] = (d.a[v] + tx[r].a[v] * -1.0) + ty[r].a[v] * -1.0;
+            st_vec(reinterpret_cast<Vec<V> *>(A.du) + row, d);
+        }
+    }
+}
+
+}  // namespace mft

@@ -51,3 +51,28 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "mft_oracle" not in src and "oracle/" not in src, f
+
+
+import pytest
+
+
+@pytest.mark.parametrize("R", [1, 2, 4])
+@pytest.mark.parametrize("layout", [0, 1, 2, 3])   # bit 0: bank-coloured slots, bit 1: two copies of the records
+@pytest.mark.parametrize("with_perm", [0, 1])
+def test_union_tile_format_replays_bit_exact(R, layout, with_perm):
+    """Host logic of the union-tile operator layout (mft_tile_kernels.cuh): the builder's step words, row masks,
+    compact weight cursors and slot table, replayed on the CPU, reproduce the plain row sums bit for bit -- ragged rows,
+    a trailing halo, tiles that end mid-slice; colouring / two copies lower the simulated LDS.128 bank-conflict degree."""
+    m = _mft()
+    lib = m._lib.load()
+    for n, k in ((33, 3), (130, 5), (1000, 7), (4100, 20)):
+        st = (C.c_double * 4)()
+        rc = lib.mft_debug_tile_selftest(n, k, R, layout, with_perm, 1234 + n, st)
+        assert rc == 0, lib.mft_last_error()
+        assert st[3] < 4095
+        if n == 4100:
+            plain = (C.c_double * 4)()
+            assert lib.mft_debug_tile_selftest(n, k, R, 0, with_perm, 1234 + n, plain) == 0
+            assert st[0] <= plain[0] + 1e-12
+            if layout and not (R == 4 and layout == 2):   # R = 4 has no copy-select bit
+                assert st[0] < 0.95 * plain[0]

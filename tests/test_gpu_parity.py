@@ -175,6 +175,50 @@ def test_full_rhs(fx, which):
     semi.close()
 
 
+LAYOUTS = [dict(tile=0, pair_rows=0), dict(tile=0, pair_rows=1), dict(tile=0, pair_rows=3), dict(tile=3, tile_rows=11),
+           dict(tile=7, tile_rows=11), dict(tile=15, tile_rows=11), dict(tile=15, tile_rows=11, stage_weights=4),
+           dict(tile=11, tile_rows=11, stage_weights=7), dict(tile=15, tile_rows=22), dict(tile=15, tile_rows=22, stage_weights=15),
+           dict(tile=7, tile_rows=22, stage_weights=4), dict(tile=3, tile_rows=44), dict(tile=15, tile_rows=44, stage_weights=15),
+           dict(tile=15, tile_rows=42), dict(tile=13, tile_rows=12), dict(tile=14, tile_rows=41, pair_rows=0)]
+
+
+@pytest.mark.parametrize("layout", LAYOUTS, ids=lambda d: "-".join(f"{k}{v}" for k, v in d.items()))
+def test_operator_layouts_bit_identical(fx, layout):
+    """Every device layout of the operators (sliced ELL, row pairs, union tiles with 1/2/4 rows per thread) applies the
+    same sums in the same order: calc_fluxes! and the upwind-viscosity source are bit-identical to the oracle, the
+    residual-viscosity rhs! agrees to 1e-12 (its global norms are reduced in a different association)."""
+    u0 = cases.ic_smooth_euler(fx["points"], 0.0) * 1.01
+    m, semi = _semi(fx, sources=SOURCE_SETS["upwind"][0], ic=cases.ic_smooth_euler, **layout)
+    du_ref = np.full_like(u0, 0.125)
+    _oracle(fx).calc_fluxes(u0, du_ref)
+    du = np.full_like(u0, 0.125)
+    m.calc_fluxes_(du, u0, semi)
+    assert np.array_equal(du, du_ref)
+    P = _oracle(fx, SOURCE_SETS["upwind"][1](fx), ic=cases.ic_smooth_euler)
+    u, u_ref = u0.copy(), u0.copy()
+    du_ref = P.rhs(u_ref, 0.0)
+    m.rhs_(du, u, semi, 0.0)
+    assert np.array_equal(u, u_ref) and np.array_equal(du, du_ref)
+    du_s = np.zeros_like(u0)
+    du_s_ref = np.zeros_like(u0)
+    P.apply_source(0, u0, du_s_ref)
+    semi.source_terms.rv(du_s, u0, 0.0)          # the source on its own (pass A without the flux part)
+    assert np.array_equal(du_s, du_s_ref)
+    semi.close()
+    m, semi = _semi(fx, sources=SOURCE_SETS["residual"][0], ic=cases.ic_smooth_euler, **layout)
+    P = _oracle(fx, SOURCE_SETS["residual"][1](fx), ic=cases.ic_smooth_euler)
+    u, u_ref = u0.copy(), u0.copy()
+    du_ref = P.rhs(u_ref, 0.0)
+    m.rhs_(du, u, semi, 0.0)
+    assert cases.relerr(du, du_ref) <= RHS_TOL
+    semi.close()
+    m, semi = _semi(fx, exact_order=False, sources=SOURCE_SETS["upwind"][0], ic=cases.ic_smooth_euler, **layout)
+    u = u0.copy()
+    m.rhs_(du, u, semi, 0.0)
+    assert cases.relerr(du, _oracle(fx, SOURCE_SETS["upwind"][1](fx), ic=cases.ic_smooth_euler).rhs(u0.copy(), 0.0)) <= 1e-11
+    semi.close()
+
+
 def test_hv_then_upwind_order_of_sources(fx):
     """SourceTerms(hv=..., rv=...) as in test/upwind_viscosity_test.jl:52 -- sources see the du left by earlier ones"""
     mk = lambda m, s, e, d: dict(hv=m.SourceHyperviscosityTominec(s, e, d, c=1.0),
