@@ -139,7 +139,8 @@ def run_ours(args):
                                                                 cuda_graph=int(args.graph),
                                                                 single_sweep_exact=bool(args.single_sweep),
                                                                 exchange=args.exchange, pair_rows=int(args.pair_rows),
-                                                                tile=int(args.tile), tile_rows=int(args.tile_rows)))
+                                                                tile=int(args.tile), tile_rows=int(args.tile_rows),
+                                                                prefetch_distance=args.pf_dist))
     names = dict(left=1, right=2, bottom=3, top=4)
     t_setup = time.time()
     domain = m.ParallelPointCloudDomain(solver, cl, names, comm) if multi else m.PointCloudDomain(solver, cl, names)
@@ -389,6 +390,7 @@ def main():
     ap.add_argument("--graph", type=int, default=1, help="0 eager, 1 CUDA-graph replay on one GPU, 2 also multi-rank")
     ap.add_argument("--single-sweep", type=int, default=0, help="k=20 single-sweep exact pass A (register-parked y-products)")
     ap.add_argument("--tile", type=int, default=15, help="union-tile kernels (bit0: pass A, bit1: pass B, bit2: bank-coloured slots, bit3: two record copies)")
+    ap.add_argument("--pf-dist", type=int, default=None, help="slices ahead for the L2 prefetch of operator data (0: off; default: 16 per SM)")
     ap.add_argument("--tile-rows", type=int, default=11, help="rows per thread of the tile kernels: units digit pass A, tens digit pass B")
     ap.add_argument("--pair-rows", type=int, default=1, help="row-pair (union stencil) operator layout (bit0: pass B, bit1: pass A)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo exchange mechanism")

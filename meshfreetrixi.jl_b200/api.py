@@ -70,6 +70,7 @@ class RBFFDEngineCUDA:
     pair_rows: int = 1                 # row-pair (union stencil) layout: bit0 transposed operator (pass B), bit1 forward (pass A)
     tile: int = 15                     # union-tile kernels: bit0 pass A, bit1 pass B, bit2 bank-coloured slots, bit3 two record copies
     tile_rows: int = 11                # rows per thread of the union-tile kernels: units digit pass A, tens digit pass B (1, 2, 4)
+    prefetch_distance: int | None = None  # slices ahead for the L2 prefetch of operator data (None: library default, 0: off)
     single_sweep_exact: bool = False   # k=20: exact-order pass A in one sweep (y-products parked in registers)
     refine_order: bool = False         # order rows inside 256-row blocks by D' row length (less padding, worse gather locality)
 
@@ -328,6 +329,8 @@ class SemidiscretizationHyperbolic:
         L.check(lib.mft_set_option(ctx, L.OPT_PAIR_ROWS, float(eng.pair_rows)))
         L.check(lib.mft_set_option(ctx, L.OPT_TILE, float(eng.tile)))
         L.check(lib.mft_set_option(ctx, L.OPT_TILE_ROWS, float(eng.tile_rows)))
+        if eng.prefetch_distance is not None:
+            L.check(lib.mft_set_option(ctx, L.OPT_PREFETCH_DISTANCE, float(eng.prefetch_distance)))
         if part is not None:
             # local numbering is already [owned along the curve ; halo]; sums must run in ascending GLOBAL column order
             self.perm = None

@@ -327,7 +327,7 @@ extern "C" int mft_ctx_create(mft_ctx **out, int device, int64_t n_local, int64_
     CHECK(c->stats.alloc(3 * nvars + 4));  // sum | mean | norms | SSPRK43 error sum
     CHECK(c->ticket.alloc(4));
     CU(cudaMemset(c->ticket.p, 0, 4 * sizeof(unsigned int)));
-    c->pf_dist = prop.multiProcessorCount * 16;
+    c->pf_dist = prop.multiProcessorCount * 8;
     CU(cudaMemset(c->stats.p, 0, sizeof(double) * (3 * nvars + 4)));
     *out = c;
     return MFT_OK;
@@ -1649,10 +1649,10 @@ static int launch_pass_a_t(mft_ctx *c, const PassAArgs &a, bool do_flux, int vis
 }
 
 // per-warp staging buffer: the step words, plus (staged weights) the R compact weight blocks of one direction
-static TileROp tiler_view(const DevTileR &e, bool stage_w)
+static TileROp tiler_view(const DevTileR &e, bool stage_w, int pf_slices = 0)
 {
     const int bytes = std::max(e.maxW, 1) * kSlice * 2 + (stage_w ? e.R * std::max(e.maxL, 1) * kSlice * 8 : 0);
-    return TileROp{e.blob.p, e.boff.p, e.wl.p, e.uoff.p, e.ulist.p, e.uslot.p, e.sstride, e.ncopy, ((bytes + 127) / 128) * 128};
+    return TileROp{e.blob.p, e.boff.p, e.wl.p, e.uoff.p, e.ulist.p, e.uslot.p, e.sstride, e.ncopy, ((bytes + 127) / 128) * 128, pf_slices / kTileWarps};
 }
 
 // staged weights keep at least `min_blocks` blocks per SM resident; otherwise stream them
@@ -1671,21 +1671,24 @@ static int launch_pass_a_tiler(mft_ctx *c, const PassAArgs &a0, bool do_flux, in
     PassAArgs a = a0;
     const DevTileR &e = c->fwd_tiler;
     const bool stage = tiler_stage(c, e, 3, c->stage_w, R == 1 ? 4 : R == 2 ? 3 : 2);
-    const TileROp t = tiler_view(e, stage);
+    const TileROp t = tiler_view(e, stage, c->pf_dist);
     a.n_slices = e.nslices;
     const int grid = e.ntiles;
     const int smem = 3 * e.ncopy * t.sstride * 16 + kTileWarps * t.buf_bytes;
     if (smem > 200 * 1024) return fail(MFT_ENOTSUP, "union tile: %d bytes of shared memory per block", smem);
-#define PAR(EX, DF, VI, ST)                                                                         \
-    do {                                                                                            \
-        CHECK(ensure_smem(c, k_pass_a_tiler<R, EX, DF, VI, ST>, smem));                             \
-        k_pass_a_tiler<R, EX, DF, VI, ST><<<grid, kTileWarps * 32, smem, c->stream>>>(a, t);       \
+#define PAR(EX, DF, VI, ST, PI)                                                                         \
+    do {                                                                                                \
+        CHECK(ensure_smem(c, k_pass_a_tiler<R, EX, DF, VI, ST, PI>, smem));                             \
+        k_pass_a_tiler<R, EX, DF, VI, ST, PI><<<grid, kTileWarps * 32, smem, c->stream>>>(a, t);       \
     } while (0)
-#define PAR2(DF, VI)                                        \
-    do {                                                    \
-        if (!c->exact) PAR(false, DF, VI, false);           \
-        else if (stage) PAR(true, DF, VI, true);            \
-        else PAR(true, DF, VI, false);                      \
+#define PAR2(DF, VI)                                                   \
+    do {                                                               \
+        const bool pipe = (c->tile & 16) != 0;                         \
+        if (!c->exact) PAR(false, DF, VI, false, false);               \
+        else if (stage && pipe) PAR(true, DF, VI, true, true);         \
+        else if (stage) PAR(true, DF, VI, true, false);                \
+        else if (pipe) PAR(true, DF, VI, false, true);                 \
+        else PAR(true, DF, VI, false, false);                          \
     } while (0)
     if (do_flux && visc == VISC_NONE) PAR2(true, VISC_NONE);
     else if (do_flux && visc == VISC_UPWIND) PAR2(true, VISC_UPWIND);
@@ -1705,18 +1708,20 @@ static int launch_pass_b_tiler(mft_ctx *c)
 {
     const DevTileR &e = c->tra_tiler;
     const bool stage = tiler_stage(c, e, 4, c->stage_w_b, R == 1 ? 4 : R == 2 ? 3 : 2);
-    const TileROp t = tiler_view(e, stage);
+    const TileROp t = tiler_view(e, stage, c->pf_dist);
     PassBTileArgs a{c->g.p, c->du.p, c->n_local, e.nslices};
     const int smem = 4 * e.ncopy * t.sstride * 16 + kTileWarps * t.buf_bytes;
     if (smem > 200 * 1024) return fail(MFT_ENOTSUP, "union tile: %d bytes of shared memory per block", smem);
-#define PBR(EX, ST)                                                                                  \
-    do {                                                                                             \
-        CHECK(ensure_smem(c, k_pass_b_tiler<R, EX, ST>, smem));                                      \
-        k_pass_b_tiler<R, EX, ST><<<e.ntiles, kTileWarps * 32, smem, c->stream>>>(a, t);            \
+#define PBR(EX, ST, PI)                                                                                  \
+    do {                                                                                                 \
+        CHECK(ensure_smem(c, k_pass_b_tiler<R, EX, ST, PI>, smem));                                      \
+        k_pass_b_tiler<R, EX, ST, PI><<<e.ntiles, kTileWarps * 32, smem, c->stream>>>(a, t);            \
     } while (0)
-    if (!c->exact) PBR(false, false);
-    else if (stage) PBR(true, true);
-    else PBR(true, false);
+    const bool pipe = (c->tile & 16) != 0;
+    if (!c->exact) PBR(false, false, false);
+    else if (stage) PBR(true, true, false);
+    else if (pipe) PBR(true, false, true);
+    else PBR(true, false, false);
 #undef PBR
     c->launches++;
     LAUNCH_CHECK();

@@ -61,12 +61,58 @@ struct TileROp {
     int ncopy;              // 1, or 2: every record is stored twice under different bank assignments; bit 14 of a step
                             // word selects the copy (R <= 2), chosen by the builder to avoid bank conflicts in the phase
     int buf_bytes;          // per-warp staging buffer (word block)
+    int pf_tiles;           // > 0: pull the operator data of tile blockIdx.x + pf_tiles into L2 (it is first touched about one
+                            // block lifetime later, by then an L2 hit instead of a DRAM round trip on the critical path)
 };
 
 // STAGE_W (exact order only): the warp also stages its compact weight blocks in shared memory -- wx_0..wx_{R-1} with the
 // step words (one bulk copy), wy_* over them after the x sweep.  A row's cursor then indexes a lane-private column of
 // shared memory (bank = lane, conflict-free) instead of issuing a global load whose lanes sit at different cursors.
-template <int R, bool EXACT, bool DO_FLUX, int VISC, bool STAGE_W>
+// PIPE: the step words and weights of batch i+1 are fetched while batch i is being computed (one shared-memory / global
+// round trip less on the dependent chain  word -> record -> arithmetic  of every batch).
+// L2 prefetch of a later tile's operator data: the offsets are loaded at kernel entry (tile_pf_begin) and used after the
+// block barrier (tile_pf_issue), when they have long arrived -- no stall on the way.
+struct TilePf {
+    int u0, u1, W, L;
+    long long boff;
+    bool tile_ok, slice_ok;
+};
+__device__ __forceinline__ TilePf tile_pf_begin(const TileROp &T, int64_t n_slices, int warp)
+{
+    TilePf p{0, 0, 0, 0, 0, false, false};
+    if (T.pf_tiles <= 0) return p;
+    const int64_t tn = (int64_t)blockIdx.x + T.pf_tiles;
+    p.tile_ok = tn < (int64_t)gridDim.x;
+    if (p.tile_ok) {
+        p.u0 = __ldg(T.uoff + tn);
+        p.u1 = __ldg(T.uoff + tn + 1);
+        const int64_t sn = tn * kTileWarps + warp;
+        p.slice_ok = sn < n_slices;
+        if (p.slice_ok) {
+            p.boff = __ldg(T.boff + sn);
+            p.W = __ldg(T.wl + 2 * sn);
+            p.L = __ldg(T.wl + 2 * sn + 1);
+        }
+    }
+    return p;
+}
+template <int R>
+__device__ __forceinline__ void tile_pf_issue(const TileROp &T, const TilePf &p, int warp, int lane)
+{
+    if (!p.tile_ok) return;
+    if (warp == 0) {  // union list + slot table: 4 bytes per entry each, one 128-byte line per prefetch
+        for (int i = lane * 32; i < p.u1 - p.u0; i += 32 * 32) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(T.ulist + p.u0 + i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned int *>(T.uslot) + p.u0 + i));
+        }
+    }
+    if (lane == 0 && p.slice_ok) {
+        const uint32_t bytes = (uint32_t)p.W * kSlice * 2 + 2u * R * (uint32_t)p.L * kSlice * 8;
+        if (bytes > 0) bulk_prefetch_l2(T.base + p.boff, bytes);
+    }
+}
+
+template <int R, bool EXACT, bool DO_FLUX, int VISC, bool STAGE_W, bool PIPE>
 __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)) k_pass_a_tiler(const PassAArgs A, const TileROp T)
 {
     static_assert(EXACT || !STAGE_W, "staged weights: exact-order (two sweep) mode only");
@@ -97,6 +143,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
             if (wbytes > 0) bulk_prefetch_l2(src + (size_t)W * kSlice * 2 + (STAGE_W ? wbytes : 0u), wbytes);
         }
     }
+    const TilePf pf = tile_pf_begin(T, A.n_slices, warp);
     const unsigned short *ip = reinterpret_cast<const unsigned short *>(buf) + lane;
     const double *wbase = reinterpret_cast<const double *>((STAGE_W ? buf : src) + (size_t)W * kSlice * 2) + lane;  // wx_0
     const size_t rstride = (size_t)L * kSlice;                                                    // doubles per weight block
@@ -123,6 +170,16 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
     }
     const uint32_t dword = nu > 0 ? (uint32_t)__ldg(T.uslot + 2 * (u0 + nu - 1)) : 0u;  // dummy slot (copy 0), empty mask
 
+    if constexpr (VISC != VISC_NONE) {  // the epilogue's own-row operands: pull them towards the SM now
+        if (has_slice && row0 < A.n_rows) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(u + row0));
+            if constexpr (R == 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(u + row0 + 2));
+            if constexpr (VISC == VISC_RESIDUAL) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const Vec<V> *>(A.approx_du) + row0));
+                if constexpr (R == 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const Vec<V> *>(A.approx_du) + row0 + 2));
+            }
+        }
+    }
     Vec<V> acc[R], gx[R], gy[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -131,6 +188,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
         if (DO_FLUX && A.accumulate && has_slice && row0 + r < A.n_rows) acc[r] = reinterpret_cast<const Vec<V> *>(A.du)[row0 + r];
     }
     __syncthreads();
+    tile_pf_issue<R>(T, pf, warp, lane);
     if (!has_slice) return;
     if (W > 0) mbar_wait(&bars[warp], 0);
 
@@ -159,25 +217,49 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
             int pos[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) pos[r] = 0;
-            for (int c0 = 0; c0 < W; c0 += kBatch) {
-                double2 qa[kBatch], qb[kBatch], qc[kBatch];
-                double w[kBatch][R];
+            // step words + weights of the batch starting at column c0 (cursors advance in step order)
+            auto fetch = [&](int c0, uint32_t (&wordv)[kBatch], double (&wv)[kBatch][R]) {
 #pragma unroll
                 for (int b = 0; b < kBatch; ++b) {
                     const bool ok = c0 + b < W;
                     const int cc = ok ? c0 + b : W - 1;
                     const uint32_t word = ok ? (uint32_t)ip[cc * kSlice] : dword;
-                    const uint32_t o = ((word & 0xfffu) << 4) + (R <= 2 ? ((word >> 14) & 1u) * arr_bytes : 0u);
+                    wordv[b] = word;
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         const bool m = (word >> (12 + r)) & 1u;
-                        w[b][r] = 0.0;
-                        if (m) w[b][r] = STAGE_W ? wd[r * rstride + (size_t)pos[r] * kSlice] : ld_stream(wd + r * rstride + (size_t)pos[r] * kSlice);
+                        wv[b][r] = 0.0;
+                        if (m) wv[b][r] = STAGE_W ? wd[r * rstride + (size_t)pos[r] * kSlice] : ld_stream(wd + r * rstride + (size_t)pos[r] * kSlice);
                         pos[r] += m ? 1 : 0;
                     }
+                }
+            };
+            uint32_t wordn[kBatch];
+            double wn[kBatch][R];
+            if constexpr (PIPE) fetch(0, wordn, wn);
+            for (int c0 = 0; c0 < W; c0 += kBatch) {
+                double2 qa[kBatch], qb[kBatch], qc[kBatch];
+                uint32_t wordc[kBatch];
+                double w[kBatch][R];
+                if constexpr (PIPE) {
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b) {
+                        wordc[b] = wordn[b];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) w[b][r] = wn[b][r];
+                    }
+                } else {
+                    fetch(c0, wordc, w);
+                }
+#pragma unroll
+                for (int b = 0; b < kBatch; ++b) {
+                    const uint32_t o = ((wordc[b] & 0xfffu) << 4) + (R <= 2 ? ((wordc[b] >> 14) & 1u) * arr_bytes : 0u);
                     qa[b] = lds2(sA, o);
                     qb[b] = lds2(sB, o);
                     qc[b] = lds2(sC, o);
+                }
+                if constexpr (PIPE) {
+                    if (c0 + kBatch < W) fetch(c0 + kBatch, wordn, wn);
                 }
 #pragma unroll
                 for (int b = 0; b < kBatch; ++b) {
@@ -289,7 +371,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
 
 // STAGE_W: two sweeps (the x chain with wx_* over arrays A,B, then the y chain with wy_* over C,D -- the chains are
 // independent, so splitting them changes no sum), each with its weight blocks staged like pass A.
-template <int R, bool EXACT, bool STAGE_W>
+template <int R, bool EXACT, bool STAGE_W, bool PIPE>
 __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)) k_pass_b_tiler(const PassBTileArgs A, const TileROp T)
 {
     constexpr int V = 4;
@@ -322,6 +404,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
             }
         }
     }
+    const TilePf pf = tile_pf_begin(T, A.n_slices, warp);
     const unsigned short *ip = reinterpret_cast<const unsigned short *>(buf) + lane;
     const double *wdx = reinterpret_cast<const double *>((STAGE_W ? buf : src) + (size_t)W * kSlice * 2) + lane;
     const size_t rstride = (size_t)L * kSlice;
@@ -348,6 +431,10 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
         }
     }
     const uint32_t dword = nu > 0 ? (uint32_t)__ldg(T.uslot + 2 * (u0 + nu - 1)) : 0u;
+    if (has_slice && row0 < A.n_rows) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const Vec<V> *>(A.du) + row0));
+        if constexpr (R == 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const Vec<V> *>(A.du) + row0 + 2));
+    }
     Vec<V> tx[R], ty[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -355,6 +442,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
         for (int v = 0; v < V; ++v) tx[r].a[v] = ty[r].a[v] = 0.0;
     }
     __syncthreads();
+    tile_pf_issue<R>(T, pf, warp, lane);
     if (!has_slice) return;
     if (W > 0) mbar_wait(&bars[warp], 0);
 
@@ -420,29 +508,55 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
         int pos[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) pos[r] = 0;
-        for (int c0 = 0; c0 < W; c0 += kBatch) {
-            double2 qa[kBatch], qb[kBatch], qc[kBatch], qd[kBatch];
-            double wa[kBatch][R], wb[kBatch][R];
+        auto fetch = [&](int c0, uint32_t (&wordv)[kBatch], double (&wav)[kBatch][R], double (&wbv)[kBatch][R]) {
 #pragma unroll
             for (int b = 0; b < kBatch; ++b) {
                 const bool ok = c0 + b < W;
                 const int cc = ok ? c0 + b : W - 1;
                 const uint32_t word = ok ? (uint32_t)ip[cc * kSlice] : dword;
-                const uint32_t o = ((word & 0xfffu) << 4) + (R <= 2 ? ((word >> 14) & 1u) * arr_bytes : 0u);
+                wordv[b] = word;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const bool m = (word >> (12 + r)) & 1u;
-                    wa[b][r] = wb[b][r] = 0.0;
+                    wav[b][r] = wbv[b][r] = 0.0;
                     if (m) {
-                        wa[b][r] = ld_stream(wdx + r * rstride + (size_t)pos[r] * kSlice);
-                        wb[b][r] = ld_stream(wdy + r * rstride + (size_t)pos[r] * kSlice);
+                        wav[b][r] = ld_stream(wdx + r * rstride + (size_t)pos[r] * kSlice);
+                        wbv[b][r] = ld_stream(wdy + r * rstride + (size_t)pos[r] * kSlice);
                     }
                     pos[r] += m ? 1 : 0;
                 }
+            }
+        };
+        uint32_t wordn[kBatch];
+        double wan[kBatch][R], wbn[kBatch][R];
+        if constexpr (PIPE) fetch(0, wordn, wan, wbn);
+        for (int c0 = 0; c0 < W; c0 += kBatch) {
+            double2 qa[kBatch], qb[kBatch], qc[kBatch], qd[kBatch];
+            uint32_t wordc[kBatch];
+            double wa[kBatch][R], wb[kBatch][R];
+            if constexpr (PIPE) {
+#pragma unroll
+                for (int b = 0; b < kBatch; ++b) {
+                    wordc[b] = wordn[b];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        wa[b][r] = wan[b][r];
+                        wb[b][r] = wbn[b][r];
+                    }
+                }
+            } else {
+                fetch(c0, wordc, wa, wb);
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const uint32_t o = ((wordc[b] & 0xfffu) << 4) + (R <= 2 ? ((wordc[b] >> 14) & 1u) * arr_bytes : 0u);
                 qa[b] = lds2(sA, o);
                 qb[b] = lds2(sB, o);
                 qc[b] = lds2(sC, o);
                 qd[b] = lds2(sD, o);
+            }
+            if constexpr (PIPE) {
+                if (c0 + kBatch < W) fetch(c0 + kBatch, wordn, wan, wbn);
             }
 #pragma unroll
             for (int b = 0; b < kBatch; ++b) {
