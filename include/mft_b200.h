@@ -72,8 +72,8 @@ typedef struct mft_ctx mft_ctx;
 #define MFT_OPT_STAGE_WEIGHTS 5    /* bit 0 (forward operator, pass A) / bit 1 (transposed operator, pass B): 1 = a warp bulk-copies
                                       its whole operator slice (indices + weights) into shared memory, 0 = indices only, weights
                                       by coalesced loads + L2 bulk prefetch.  bit 2: exact-order pass A keeps ONE weight buffer and refills it with wy
-                                      after the x sweep (smaller footprint -> larger L1).  Union-tile kernels: bit 0 / bit 1 stage the compact weight
-                                      blocks of one direction (two sweeps) unless that leaves too few blocks per SM; bit 3 forces it.
+                                      after the x sweep (smaller footprint -> larger L1).  Union-tile kernels stream their weights (measured faster) unless bit 3 is set:
+                                      then bit 0 / bit 1 stage the compact weight blocks of one direction (two sweeps).
                                       Default 5 (measured best). */
 #define MFT_OPT_REFINE_ORDER 7     /* 1 (default 0): within blocks of 256 device rows, order rows by D' row length
                                       (near-uniform transposed-ELL slices); the caller-visible numbering is unaffected */
@@ -92,7 +92,8 @@ typedef struct mft_ctx mft_ctx;
 #define MFT_OPT_TILE_ROWS 11       /* rows per thread of the union-tile kernels, decimal digits: units = pass A, tens = pass B, each 1, 2
                                       or 4 (e.g. 42 = pass B 4 rows, pass A 2 rows).  A thread walks the union of its rows' stencils
                                       (16-bit word = slot | row mask << 12, weights compact per row).  Same sums bit for bit.   */
-#define MFT_OPT_PREFETCH_DISTANCE 6/* slices ahead for the L2 prefetch of the weight blocks (STAGE_WEIGHTS = 0)        */
+#define MFT_OPT_PREFETCH_DISTANCE 6/* slices ahead for the L2 prefetch of operator data (weight blocks; union tiles: step words, weights, union
+                                      list of the tile that many slices ahead).  Default 8 per SM; 0: off.               */
 
 /* fields (mft_get_field): caches of create_tominec_rv_cache, hyperviscosity.jl:202-244 */
 #define MFT_FIELD_EPS 0        /* N doubles   */

@@ -1658,8 +1658,10 @@ static TileROp tiler_view(const DevTileR &e, bool stage_w, int pf_slices = 0)
 // staged weights keep at least `min_blocks` blocks per SM resident; otherwise stream them
 static bool tiler_stage(const mft_ctx *c, const DevTileR &e, int narrays, bool want, int min_blocks)
 {
-    if (!want || !c->exact) return false;
-    if (c->stage_force) min_blocks = 1;
+    // measured (profiles/README.md): with the L2 prefetch of later tiles, streamed weights beat staged ones (pass A 152 vs
+    // 156 us), so the tile kernels stage only on explicit request (MFT_OPT_STAGE_WEIGHTS bit 3)
+    if (!want || !c->exact || !c->stage_force) return false;
+    min_blocks = 1;
     const TileROp t = tiler_view(e, true);
     const int smem = narrays * e.ncopy * t.sstride * 16 + kTileWarps * t.buf_bytes + 1024;
     return smem * min_blocks <= 224 * 1024;
