@@ -1678,19 +1678,16 @@ static int launch_pass_a_tiler(mft_ctx *c, const PassAArgs &a0, bool do_flux, in
     const int grid = e.ntiles;
     const int smem = 3 * e.ncopy * t.sstride * 16 + kTileWarps * t.buf_bytes;
     if (smem > 200 * 1024) return fail(MFT_ENOTSUP, "union tile: %d bytes of shared memory per block", smem);
-#define PAR(EX, DF, VI, ST, PI)                                                                         \
-    do {                                                                                                \
-        CHECK(ensure_smem(c, k_pass_a_tiler<R, EX, DF, VI, ST, PI>, smem));                             \
-        k_pass_a_tiler<R, EX, DF, VI, ST, PI><<<grid, kTileWarps * 32, smem, c->stream>>>(a, t);       \
+#define PAR(EX, DF, VI, ST)                                                                         \
+    do {                                                                                            \
+        CHECK(ensure_smem(c, k_pass_a_tiler<R, EX, DF, VI, ST>, smem));                             \
+        k_pass_a_tiler<R, EX, DF, VI, ST><<<grid, kTileWarps * 32, smem, c->stream>>>(a, t);       \
     } while (0)
-#define PAR2(DF, VI)                                                   \
-    do {                                                               \
-        const bool pipe = (c->tile & 16) != 0;                         \
-        if (!c->exact) PAR(false, DF, VI, false, false);               \
-        else if (stage && pipe) PAR(true, DF, VI, true, true);         \
-        else if (stage) PAR(true, DF, VI, true, false);                \
-        else if (pipe) PAR(true, DF, VI, false, true);                 \
-        else PAR(true, DF, VI, false, false);                          \
+#define PAR2(DF, VI)                                        \
+    do {                                                    \
+        if (!c->exact) PAR(false, DF, VI, false);           \
+        else if (stage) PAR(true, DF, VI, true);            \
+        else PAR(true, DF, VI, false);                      \
     } while (0)
     if (do_flux && visc == VISC_NONE) PAR2(true, VISC_NONE);
     else if (do_flux && visc == VISC_UPWIND) PAR2(true, VISC_UPWIND);
@@ -1714,16 +1711,14 @@ static int launch_pass_b_tiler(mft_ctx *c)
     PassBTileArgs a{c->g.p, c->du.p, c->n_local, e.nslices};
     const int smem = 4 * e.ncopy * t.sstride * 16 + kTileWarps * t.buf_bytes;
     if (smem > 200 * 1024) return fail(MFT_ENOTSUP, "union tile: %d bytes of shared memory per block", smem);
-#define PBR(EX, ST, PI)                                                                                  \
-    do {                                                                                                 \
-        CHECK(ensure_smem(c, k_pass_b_tiler<R, EX, ST, PI>, smem));                                      \
-        k_pass_b_tiler<R, EX, ST, PI><<<e.ntiles, kTileWarps * 32, smem, c->stream>>>(a, t);            \
+#define PBR(EX, ST)                                                                                  \
+    do {                                                                                             \
+        CHECK(ensure_smem(c, k_pass_b_tiler<R, EX, ST>, smem));                                      \
+        k_pass_b_tiler<R, EX, ST><<<e.ntiles, kTileWarps * 32, smem, c->stream>>>(a, t);            \
     } while (0)
-    const bool pipe = (c->tile & 16) != 0;
-    if (!c->exact) PBR(false, false, false);
-    else if (stage) PBR(true, true, false);
-    else if (pipe) PBR(true, false, true);
-    else PBR(true, false, false);
+    if (!c->exact) PBR(false, false);
+    else if (stage) PBR(true, true);
+    else PBR(true, false);
 #undef PBR
     c->launches++;
     LAUNCH_CHECK();

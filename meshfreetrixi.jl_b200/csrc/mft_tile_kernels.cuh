@@ -68,8 +68,6 @@ struct TileROp {
 // STAGE_W (exact order only): the warp also stages its compact weight blocks in shared memory -- wx_0..wx_{R-1} with the
 // step words (one bulk copy), wy_* over them after the x sweep.  A row's cursor then indexes a lane-private column of
 // shared memory (bank = lane, conflict-free) instead of issuing a global load whose lanes sit at different cursors.
-// PIPE: the step words and weights of batch i+1 are fetched while batch i is being computed (one shared-memory / global
-// round trip less on the dependent chain  word -> record -> arithmetic  of every batch).
 // L2 prefetch of a later tile's operator data: the offsets are loaded at kernel entry (tile_pf_begin) and used after the
 // block barrier (tile_pf_issue), when they have long arrived -- no stall on the way.
 struct TilePf {
@@ -112,7 +110,7 @@ __device__ __forceinline__ void tile_pf_issue(const TileROp &T, const TilePf &p,
     }
 }
 
-template <int R, bool EXACT, bool DO_FLUX, int VISC, bool STAGE_W, bool PIPE>
+template <int R, bool EXACT, bool DO_FLUX, int VISC, bool STAGE_W>
 __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)) k_pass_a_tiler(const PassAArgs A, const TileROp T)
 {
     static_assert(EXACT || !STAGE_W, "staged weights: exact-order (two sweep) mode only");
@@ -234,32 +232,17 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
                     }
                 }
             };
-            uint32_t wordn[kBatch];
-            double wn[kBatch][R];
-            if constexpr (PIPE) fetch(0, wordn, wn);
             for (int c0 = 0; c0 < W; c0 += kBatch) {
                 double2 qa[kBatch], qb[kBatch], qc[kBatch];
                 uint32_t wordc[kBatch];
                 double w[kBatch][R];
-                if constexpr (PIPE) {
-#pragma unroll
-                    for (int b = 0; b < kBatch; ++b) {
-                        wordc[b] = wordn[b];
-#pragma unroll
-                        for (int r = 0; r < R; ++r) w[b][r] = wn[b][r];
-                    }
-                } else {
-                    fetch(c0, wordc, w);
-                }
+                fetch(c0, wordc, w);
 #pragma unroll
                 for (int b = 0; b < kBatch; ++b) {
                     const uint32_t o = ((wordc[b] & 0xfffu) << 4) + (R <= 2 ? ((wordc[b] >> 14) & 1u) * arr_bytes : 0u);
                     qa[b] = lds2(sA, o);
                     qb[b] = lds2(sB, o);
                     qc[b] = lds2(sC, o);
-                }
-                if constexpr (PIPE) {
-                    if (c0 + kBatch < W) fetch(c0 + kBatch, wordn, wn);
                 }
 #pragma unroll
                 for (int b = 0; b < kBatch; ++b) {
@@ -371,7 +354,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
 
 // STAGE_W: two sweeps (the x chain with wx_* over arrays A,B, then the y chain with wy_* over C,D -- the chains are
 // independent, so splitting them changes no sum), each with its weight blocks staged like pass A.
-template <int R, bool EXACT, bool STAGE_W, bool PIPE>
+template <int R, bool EXACT, bool STAGE_W>
 __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)) k_pass_b_tiler(const PassBTileArgs A, const TileROp T)
 {
     constexpr int V = 4;
@@ -527,26 +510,11 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
                 }
             }
         };
-        uint32_t wordn[kBatch];
-        double wan[kBatch][R], wbn[kBatch][R];
-        if constexpr (PIPE) fetch(0, wordn, wan, wbn);
         for (int c0 = 0; c0 < W; c0 += kBatch) {
             double2 qa[kBatch], qb[kBatch], qc[kBatch], qd[kBatch];
             uint32_t wordc[kBatch];
             double wa[kBatch][R], wb[kBatch][R];
-            if constexpr (PIPE) {
-#pragma unroll
-                for (int b = 0; b < kBatch; ++b) {
-                    wordc[b] = wordn[b];
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        wa[b][r] = wan[b][r];
-                        wb[b][r] = wbn[b][r];
-                    }
-                }
-            } else {
-                fetch(c0, wordc, wa, wb);
-            }
+            fetch(c0, wordc, wa, wb);
 #pragma unroll
             for (int b = 0; b < kBatch; ++b) {
                 const uint32_t o = ((wordc[b] & 0xfffu) << 4) + (R <= 2 ? ((wordc[b] >> 14) & 1u) * arr_bytes : 0u);
@@ -554,9 +522,6 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
                 qb[b] = lds2(sB, o);
                 qc[b] = lds2(sC, o);
                 qd[b] = lds2(sD, o);
-            }
-            if constexpr (PIPE) {
-                if (c0 + kBatch < W) fetch(c0 + kBatch, wordn, wan, wbn);
             }
 #pragma unroll
             for (int b = 0; b < kBatch; ++b) {

@@ -180,8 +180,7 @@ LAYOUTS = [dict(tile=0, pair_rows=0), dict(tile=0, pair_rows=1), dict(tile=0, pa
            dict(tile=11, tile_rows=11, stage_weights=15), dict(tile=15, tile_rows=22), dict(tile=15, tile_rows=22, stage_weights=15),
            dict(tile=7, tile_rows=22, stage_weights=4), dict(tile=3, tile_rows=44), dict(tile=15, tile_rows=44, stage_weights=15),
            dict(tile=15, tile_rows=42), dict(tile=13, tile_rows=12), dict(tile=14, tile_rows=41, pair_rows=0),
-           dict(tile=31, tile_rows=11), dict(tile=23, tile_rows=11, stage_weights=4), dict(tile=31, tile_rows=22),
-           dict(tile=19, tile_rows=44, stage_weights=4), dict(tile=15, tile_rows=11, prefetch_distance=0),
+           dict(tile=15, tile_rows=11, prefetch_distance=0),
            dict(tile=15, tile_rows=22, prefetch_distance=8), dict(tile=15, tile_rows=11, prefetch_distance=4)]
 
 
