@@ -48,6 +48,67 @@ def lib():
     return _LIB
 
 
+_FAST = None
+
+
+def fast_lib():
+    """libmft_cpu_fast.so: CPU baseline (ii) of SURVEY.md 8(d) (fused row-parallel multi-threaded rhs!, mft_cpu_fast.c)."""
+    global _FAST
+    if _FAST is None:
+        so = os.path.join(_HERE, "libmft_cpu_fast.so")
+        src = os.path.join(_HERE, "mft_cpu_fast.c")
+        if not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "libmft_cpu_fast.so"])
+        _FAST = C.CDLL(so)
+        _FAST.fast_max_threads.restype = C.c_int
+    return _FAST
+
+
+class _FASTP(C.Structure):
+    _fields_ = [("n", C.c_int64), ("ptr", C.c_void_p), ("col", C.c_void_p), ("wx", C.c_void_p), ("wy", C.c_void_p),
+                ("tptr", C.c_void_p), ("tcol", C.c_void_p), ("twx", C.c_void_p), ("twy", C.c_void_p),
+                ("nb", C.c_int64), ("bidx", C.c_void_p), ("bval", C.c_void_p),
+                ("gamma", C.c_double), ("c_rv", C.c_double), ("c_uw", C.c_double), ("dx_avg", C.c_double),
+                ("success_iter_zero", C.c_int), ("mean_divisor_vn", C.c_int), ("max_lexicographic", C.c_int)]
+
+
+class FastCpuProblem:
+    """Euler + residual-viscosity rhs! with Dirichlet tables on the fused multi-threaded CPU kernel (AoS state)."""
+
+    def __init__(self, Dx, Dy, gamma, dx_avg, bidx, bvals, c_rv=1.0, c_uw=1.0, success_iter=5,
+                 mean_divisor_vn=True, max_lexicographic=True):
+        X = sp.csr_matrix(Dx)
+        Y = sp.csr_matrix(Dy)
+        X.sort_indices()
+        Y.sort_indices()
+        assert np.array_equal(X.indptr, Y.indptr) and np.array_equal(X.indices, Y.indices)
+        XT = sp.csr_matrix(sp.csc_matrix(Dx).T)     # rows of D' = columns of D, ascending source row
+        YT = sp.csr_matrix(sp.csc_matrix(Dy).T)
+        XT.sort_indices()
+        YT.sort_indices()
+        self.n = X.shape[0]
+        self._keep = [np.ascontiguousarray(X.indptr, dtype=np.int64), np.ascontiguousarray(X.indices, dtype=np.int32),
+                      np.ascontiguousarray(X.data), np.ascontiguousarray(Y.data),
+                      np.ascontiguousarray(XT.indptr, dtype=np.int64), np.ascontiguousarray(XT.indices, dtype=np.int32),
+                      np.ascontiguousarray(XT.data), np.ascontiguousarray(YT.data),
+                      np.ascontiguousarray(bidx, dtype=np.int32), np.ascontiguousarray(np.asarray(bvals).T.copy())]
+        k = self._keep
+        self.p = _FASTP(self.n, *[a.ctypes.data for a in k[:8]], len(k[8]), k[8].ctypes.data, k[9].ctypes.data,
+                        float(gamma), float(c_rv), float(c_uw), float(dx_avg), int(success_iter == 0),
+                        int(mean_divisor_vn), int(max_lexicographic))
+        self.g = np.zeros((self.n, 8))
+
+    def rhs(self, u_soa, approx_du_soa=None, reps=1):
+        """u_soa (4,N) in/out semantics as rhs!; returns du (4,N)"""
+        u = np.ascontiguousarray(u_soa.T.copy())
+        ad = np.zeros_like(u) if approx_du_soa is None else np.ascontiguousarray(approx_du_soa.T.copy())
+        du = np.empty_like(u)
+        fast_lib().fast_rhs_rv_repeat(C.byref(self.p), C.c_void_p(u.ctypes.data), C.c_void_p(ad.ctypes.data),
+                                      C.c_void_p(du.ctypes.data), C.c_void_p(self.g.ctypes.data), int(reps))
+        u_soa[:] = u.T
+        return np.ascontiguousarray(du.T)
+
+
 # --------------------------------------------------------------------------------------------
 # Setup side
 # --------------------------------------------------------------------------------------------

@@ -213,3 +213,30 @@ def test_ssprk43_error_estimate_is_third_order(fx):
     # adaptive run: the controller accepts/rejects and ends exactly at t1
     u, t, log = orc.solve_ssprk43(P, u0, 0.0, 0.03, 1e-3, abstol=1e-6, reltol=1e-6)
     assert abs(t - 0.03) < 1e-15 and len(log) >= 5 and np.isfinite(u).all()
+
+
+def test_best_effort_cpu_baseline_matches_the_oracle():
+    """oracle/mft_cpu_fast.c (CPU baseline (ii) of SURVEY.md 8d: fused, row-parallel, AoS) computes the same Euler +
+    residual-viscosity rhs! as the reference-structured oracle: u identical, du to 1e-12 (only the association of the
+    global mean differs) -- with 1 thread and with all host cores."""
+    import mft_b200 as m
+
+    fx = cases.fixture_setup(p=3, N=3)
+    ops = m.setup_ops.compute_flux_operator(fx["points"], fx["nb"], 3, 3)
+    ic = cases.ic_smooth_euler
+    bcs = dict(inlet="dirichlet", outlet="dirichlet", top="dirichlet", bottom="dirichlet", cyl="dirichlet")
+    for si in (0, 5):
+        src = orc.source_residual(fx["dx_avg"], polydeg=3)
+        src.success_iter = si
+        P = orc.OracleProblem(fx["points"], 4, orc.EQ_EULER2D, [cases.GAMMA], ops[0], ops[1], cases.oracle_bcs(fx, bcs, ic), [src])
+        u0 = ic(fx["points"], 0.0) * 1.01
+        u_ref = u0.copy()
+        du_ref = P.rhs(u_ref, 0.0)
+        bidx = np.concatenate(fx["bidx"])
+        F = orc.FastCpuProblem(ops[0], ops[1], cases.GAMMA, fx["dx_avg"], bidx, ic(fx["points"][bidx], 0.0), success_iter=si)
+        for threads in (1, 3, orc.fast_lib().fast_max_threads()):
+            orc.fast_lib().fast_set_threads(int(threads))
+            u = u0.copy()
+            du = F.rhs(u)
+            assert np.array_equal(u, u_ref)
+            assert cases.relerr(du, du_ref) <= 1e-12
