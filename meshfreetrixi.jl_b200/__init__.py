@@ -5,11 +5,12 @@ The directory name is not a valid Python identifier; import it through the root-
 
 Contents: csrc/ (sm_100a CUDA kernels + the C ABI of include/mft_b200.h), _lib.py (ctypes binding), api.py (host-side
 mirror of the reference's interface for the path), setup_ops.py / cloud.py (setup-time code), partition.py
-(space-filling-curve partition + halo plan for multi-GPU).
+(space-filling-curve partition + halo plan for multi-GPU), vtk.py (VTK snapshot writer + SolutionSavingCallback).
 """
-from . import _lib, cloud, setup_ops  # noqa: F401
+from . import _lib, cloud, setup_ops, vtk  # noqa: F401
 from ._lib import MftError, load  # noqa: F401
 from .api import *  # noqa: F401,F403
+from .vtk import SolutionSavingCallback, trixi2vtk  # noqa: F401
 from .api import (BoundaryConditionDirichlet, BoundaryConditionDoNothing, CompressibleEulerEquations2D,  # noqa: F401
                   HistoryCallback, LinearScalarAdvectionEquation2D, Point2D, PointCloudBasis, PointCloudDomain,
                   PointCloudSolver, PolyharmonicSpline, RBF, RBFFDEngineCUDA, SemidiscretizationHyperbolic,

@@ -504,6 +504,17 @@ class Solution:
     nrhs: int
 
 
+def _run_savers(savers, semi, t, it, finished, template):
+    """SolutionSavingCallback affect! (save_solution_vtk.jl:136-173): download the resident state only when a file is due"""
+    due = [c for c in savers if c.due(t, it, finished)]
+    if not due:
+        return
+    u = np.empty_like(template)
+    L.check(L.load().mft_download_state(semi.ctx, L.soa_ptrs(u)))
+    for c in due:
+        c(u, semi, t, it, finished)
+
+
 def solve_adaptive(ode, alg, dt, abstol=1e-8, reltol=1e-8, callback=None, max_steps=100000, allreduce=None):
     """solve(ode, SSPRK43(); abstol, reltol, callback=...) (rbfsolver_test.jl:104-107): adaptive steps, FSAL, callbacks
     after every ACCEPTED step.  `allreduce(sumsq, count) -> (sumsq, count)` combines ranks in multi-GPU runs."""
@@ -512,11 +523,13 @@ def solve_adaptive(ode, alg, dt, abstol=1e-8, reltol=1e-8, callback=None, max_st
     t0, t1 = ode.tspan
     cbs = [] if callback is None else (list(callback) if isinstance(callback, (list, tuple)) else [callback])
     hist = [c for c in cbs if isinstance(c, HistoryCallback)]
+    savers = [c for c in cbs if hasattr(c, "due")]
     u0 = np.ascontiguousarray(ode.u0, dtype=np.float64)
     L.check(lib.mft_upload_state(semi.ctx, L.soa_ptrs(u0)))
     t, dt = float(t0), float(dt)
     for h in hist:
         L.check(lib.mft_history_push(semi.ctx, t, 0, h.approx_order))
+    _run_savers(savers, semi, t, 0, False, u0)
     ctrl = PIController()
     accepted, log, nrhs = 0, [], 1
     ss, cnt = C.c_double(), C.c_int64()
@@ -536,6 +549,7 @@ def solve_adaptive(ode, alg, dt, abstol=1e-8, reltol=1e-8, callback=None, max_st
             accepted += 1
             for h in hist:
                 L.check(lib.mft_history_push(semi.ctx, t, accepted, h.approx_order))
+            _run_savers(savers, semi, t, accepted, t >= t1 - 1e-14 * max(1.0, abs(t1)), u0)
         dt = dt_next
     u = np.empty_like(u0)
     L.check(lib.mft_download_state(semi.ctx, L.soa_ptrs(u)))
@@ -556,11 +570,13 @@ def solve(ode, alg, dt, callback=None, nsteps=None, **kw):
         nsteps = int(round((t1 - t0) / dt))
     cbs = [] if callback is None else (list(callback) if isinstance(callback, (list, tuple)) else [callback])
     hist = [c for c in cbs if isinstance(c, HistoryCallback)]
+    savers = [c for c in cbs if hasattr(c, "due")]
     u0 = np.ascontiguousarray(ode.u0, dtype=np.float64)
     L.check(lib.mft_upload_state(semi.ctx, L.soa_ptrs(u0)))
     t = float(t0)
     for h in hist:   # initialize! (history.jl:51-54)
         L.check(lib.mft_history_push(semi.ctx, t, 0, h.approx_order))
+    _run_savers(savers, semi, t, 0, False, u0)   # initialize_save_cb! (save_solution_vtk.jl:123-134)
     nrhs = 1 if nsteps > 0 else 0
     for it in range(nsteps):
         L.check(lib.mft_ssprk_step(semi.ctx, alg.scheme, t, float(dt)))
@@ -568,6 +584,7 @@ def solve(ode, alg, dt, callback=None, nsteps=None, **kw):
         nrhs += alg.stages
         for h in hist:
             L.check(lib.mft_history_push(semi.ctx, t, it + 1, h.approx_order))
+        _run_savers(savers, semi, t, it + 1, it + 1 == nsteps, u0)
     u = np.empty_like(u0)
     L.check(lib.mft_download_state(semi.ctx, L.soa_ptrs(u)))
     return Solution(u, t, nsteps, nrhs)
