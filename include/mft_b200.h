@@ -203,6 +203,21 @@ int mft_host_unregister(void *p);
  * Hilbert space-filling-curve order of a 2-D cloud: perm1_out[d] = 1-based index of the d-th point along the curve. */
 int mft_sfc_order(int64_t n, const double *x, const double *y, int64_t *perm1_out);
 
+/* ---- Zhang-Shu positivity limiter (stage callback) ------------------------------------------------------
+ * replaces Trixi.limiter_zhang_shu!(u, threshold, variable, domain::PointCloudDomain{2}, ...)
+ * (src/callbacks_stage/positivity_zhang_shu_point2d.jl:22-82) and the (thresholds, variables) recursion of
+ * PositivityPreservingLimiterZhangShu (src/callbacks_stage/positivity_zhang_shu.jl:29-72).  Euler 2-D, single GPU. */
+#define MFT_VAR_DENSITY 0   /* Trixi.density  */
+#define MFT_VAR_PRESSURE 1  /* Trixi.pressure */
+/* domain.pd.neighbors flattened: n_local x k row-major, 1-based, in the kNN list order (distance-sorted, self first) */
+int mft_set_neighbors(mft_ctx *ctx, const int64_t *nbr1);
+/* limiter!(u_ode, integrator, semi, t): one pass per (threshold, variable) pair, in order.  MFT_MEM_HOST: u_soa in/out;
+ * MFT_MEM_DEVICE: acts on the resident state (u_soa ignored). */
+int mft_limiter_zhang_shu(mft_ctx *ctx, int npairs, const double *thresholds, const int *variables, double *const *u_soa,
+                          int mem);
+/* SSPRK33(stage_limiter!): mft_ssprk_step applies the limiter after every stage update.  npairs = 0 removes it. */
+int mft_set_stage_limiter(mft_ctx *ctx, int npairs, const double *thresholds, const int *variables);
+
 /* Host-only self test of the union-tile operator format (MFT_OPT_TILE): lays out a random ragged banded operator for
  * n points (k entries per row, R = 1, 2 or 4 rows per thread, layout bit 0 = bank colouring, bit 1 = two record copies,
  * optional row permutation + order keys),

@@ -16,5 +16,5 @@ from .api import (BoundaryConditionDirichlet, BoundaryConditionDoNothing, Compre
                   PointCloudSolver, PolyharmonicSpline, RBF, RBFFDEngineCUDA, SemidiscretizationHyperbolic,
                   SourceHyperviscosityFlyer, SourceHyperviscosityTominec, SourceResidualViscosityTominec,
                   SourceTerms, SourceUpwindViscosityTominec, SSPRK33, SSPRK43, PIController, ParallelPointCloudDomain,
-                  boundary_condition_slip_wall, solve_adaptive,
+                  boundary_condition_slip_wall, solve_adaptive, PositivityPreservingLimiterZhangShu, density, pressure,
                   calc_boundary_flux_, calc_fluxes_, compute_coefficients, rhs_, semidiscretize, solve)

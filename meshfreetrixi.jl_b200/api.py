@@ -342,6 +342,9 @@ class SemidiscretizationHyperbolic:
             L.check(lib.mft_set_permutation(ctx, L.ptr(perm1)))
         else:
             self.perm = None
+        if part is None and self.V == 4:   # domain.pd.neighbors for the Zhang-Shu stage limiter (list order = kNN order)
+            nbr1 = np.ascontiguousarray(pd.neighbors + 1, dtype=np.int64)
+            L.check(lib.mft_set_neighbors(ctx, L.ptr(nbr1)))
         for slot, A in ((L.OP_DX, ops[0]), (L.OP_DY, ops[1])):
             cp, rv, nz = setup_ops.julia_csc(A)
             L.check(lib.mft_set_operator_csc(ctx, slot, L.ptr(cp), L.ptr(rv), L.ptr(nz)))
@@ -462,8 +465,52 @@ class HistoryCallback:
 
 
 class SSPRK33:
+    """SSPRK33(stage_limiter!) of OrdinaryDiffEq: the optional stage limiter runs on the device after every stage update"""
     scheme = L.SSPRK33
     stages = 3
+
+    def __init__(self, stage_limiter=None):
+        self.stage_limiter = stage_limiter
+
+
+def density(u, equations=None):
+    """Trixi.density (third party): first conserved variable"""
+    return u[0]
+
+
+def pressure(u, equations):
+    """Trixi.pressure for CompressibleEulerEquations2D (third party)"""
+    return (equations.gamma - 1.0) * (u[3] - 0.5 * (u[1] * u[1] + u[2] * u[2]) / u[0])
+
+
+class PositivityPreservingLimiterZhangShu:
+    """PositivityPreservingLimiterZhangShu(; thresholds, variables) (src/callbacks_stage/positivity_zhang_shu.jl:15-48):
+    applied to the scalar `variables` (density, pressure) in their given order with the associated thresholds."""
+
+    _KINDS = {density: L.VAR_DENSITY, pressure: L.VAR_PRESSURE}
+
+    def __init__(self, thresholds, variables):
+        if len(thresholds) != len(variables):
+            raise ValueError("thresholds and variables must have the same length")
+        self.thresholds = tuple(float(x) for x in thresholds)
+        self.variables = tuple(variables)
+        try:
+            self.kinds = tuple(self._KINDS[v] for v in self.variables)
+        except KeyError:
+            raise NotImplementedError("the device limiter knows Trixi's `density` and `pressure`") from None
+
+    def _arrays(self):
+        return (np.asarray(self.thresholds, dtype=np.float64), np.asarray(self.kinds, dtype=np.int32))
+
+    def __call__(self, u, semi, t=None):
+        """limiter!(u_ode, integrator, semi, t) on a host array (in place)"""
+        thr, kinds = self._arrays()
+        L.check(L.load().mft_limiter_zhang_shu(semi.ctx, len(kinds), L.ptr(thr), L.ptr(kinds), L.soa_ptrs(u), L.MEM_HOST))
+        return u
+
+    def install(self, semi):
+        thr, kinds = self._arrays()
+        L.check(L.load().mft_set_stage_limiter(semi.ctx, len(kinds), L.ptr(thr), L.ptr(kinds)))
 
 
 class SSPRK43:
@@ -571,6 +618,13 @@ def solve(ode, alg, dt, callback=None, nsteps=None, **kw):
     cbs = [] if callback is None else (list(callback) if isinstance(callback, (list, tuple)) else [callback])
     hist = [c for c in cbs if isinstance(c, HistoryCallback)]
     savers = [c for c in cbs if hasattr(c, "due")]
+    lim = getattr(alg, "stage_limiter", None)
+    if lim is not None:
+        lim.install(semi)
+        semi._stage_limiter_installed = True
+    elif getattr(semi, "_stage_limiter_installed", False):
+        L.check(lib.mft_set_stage_limiter(semi.ctx, 0, None, None))
+        semi._stage_limiter_installed = False
     u0 = np.ascontiguousarray(ode.u0, dtype=np.float64)
     L.check(lib.mft_upload_state(semi.ctx, L.soa_ptrs(u0)))
     t = float(t0)

@@ -162,6 +162,13 @@ struct mft_ctx {
     bool have_ell_input = false;
     DevEll fwd, fwd_pair, tra, tra_pair;
     DevTileR fwd_tiler, tra_tiler;
+    // Zhang-Shu limiter: kNN table in list order, scratch, stage-limiter configuration
+    std::vector<int32_t> host_nbr;  // caller numbering, n_local x k row-major
+    DevBuf<int> zs_nbr;
+    DevBuf<double> zs_tmp;
+    DevBuf<unsigned char> zs_flag;
+    std::vector<double> stage_lim_thresholds;
+    std::vector<int> stage_lim_variables;
     int tile_rows_a = 1, tile_rows_b = 1;  // MFT_OPT_TILE_ROWS: rows per thread of the union-tile kernels (1, 2 or 4)
     int stage_force = 0;
     int tile = 15;  // MFT_OPT_TILE: bit 0 pass A, bit 1 pass B (Euler 2-D only), bit 2 bank-coloured slots, bit 3 two copies
@@ -355,6 +362,9 @@ extern "C" int mft_ctx_destroy(mft_ctx *c)
     c->fwd_pair.release();
     c->fwd_tiler.release();
     c->tra_tiler.release();
+    c->zs_nbr.release();
+    c->zs_tmp.release();
+    c->zs_flag.release();
     for (auto &h : c->hist) h.release();
     DevBuf<double> *bufs[] = {&c->utilde, &c->kfsal, &c->u_save, &c->u, &c->du, &c->uprev, &c->g, &c->approx_du, &c->stage_soa, &c->eps, &c->eps_uw,
                               &c->eps_rv, &c->eps_c, &c->residual, &c->partial, &c->stats, &c->send_buf, &c->gather_buf};
@@ -2125,6 +2135,8 @@ extern "C" int mft_history_push_weights(mft_ctx *c, double t, int64_t success_it
     return history_push_common(c, t, success_iter, true, n, weights, 0);
 }
 
+static int launch_limiter(mft_ctx *c, int npairs, const double *thresholds, const int *variables);
+
 static int launch_stage(mft_ctx *c, int stage, double dt)
 {
     ScopedTimer tm(c, MFT_K_STAGE);
@@ -2132,6 +2144,9 @@ static int launch_stage(mft_ctx *c, int stage, double dt)
     k_ssprk33_stage<<<c->red_blocks * 2, 256, 0, c->stream>>>(stage, dt, c->uprev.p, c->du.p, c->u.p, len);
     c->launches++;
     LAUNCH_CHECK();
+    // stage_limiter!(u, integrator, p, t) after every stage update (OrdinaryDiffEq SSPRK33(stage_limiter!))
+    if (!c->stage_lim_variables.empty())
+        CHECK(launch_limiter(c, (int)c->stage_lim_variables.size(), c->stage_lim_thresholds.data(), c->stage_lim_variables.data()));
     return MFT_OK;
 }
 
@@ -2190,6 +2205,94 @@ extern "C" int mft_ssprk_step(mft_ctx *c, int scheme, double t, double dt)
     return MFT_OK;  // asynchronous: mft_synchronize / downloads wait
 }
 
+// ---- Zhang-Shu positivity limiter (row f4; positivity_zhang_shu_point2d.jl:22-82, positivity_zhang_shu.jl:50-72) --------
+extern "C" int mft_set_neighbors(mft_ctx *c, const int64_t *nbr1)
+{
+    NEED_CTX(c);
+    if (!nbr1) return fail(MFT_EINVAL, "mft_set_neighbors: NULL array");
+    if (c->k <= 0) return fail(MFT_EINVAL, "mft_set_neighbors: ctx was created with k=%d", c->k);
+    const int64_t n = c->n_local, k = c->k;
+    c->host_nbr.resize((size_t)(n * k));
+    for (int64_t p = 0; p < n * k; ++p) {
+        const int64_t j = nbr1[p] - 1;
+        if (j < 0 || j >= c->n_tot) return fail(MFT_EINVAL, "mft_set_neighbors: neighbour %lld out of range", (long long)nbr1[p]);
+        c->host_nbr[(size_t)p] = (int32_t)j;
+    }
+    c->zs_nbr.release();  // rebuilt (device numbering) at the next limiter call
+    return MFT_OK;
+}
+
+static int zs_prepare(mft_ctx *c)
+{
+    if (c->V != 4 || c->eq != MFT_EQ_EULER2D) return fail(MFT_ENOTSUP, "Zhang-Shu limiter: Euler 2-D only");
+    if (c->nranks > 1) return fail(MFT_ENOTSUP, "Zhang-Shu limiter: multi-rank runs need a halo refresh per pass (not implemented)");
+    if (c->host_nbr.empty()) return fail(MFT_EINVAL, "Zhang-Shu limiter: mft_set_neighbors was not called");
+    if (c->zs_nbr.p) return MFT_OK;
+    const int64_t n = c->n_local, k = c->k;
+    std::vector<int> tab((size_t)(n * k));
+    for (int64_t d = 0; d < n; ++d) {
+        const int64_t r = c->have_perm ? c->perm[d] : d;  // device row d holds caller point r
+        for (int64_t q = 0; q < k; ++q) {
+            const int32_t j = c->host_nbr[(size_t)(r * k + q)];
+            tab[(size_t)(q * n + d)] = c->have_perm ? c->iperm[j] : j;
+        }
+    }
+    CHECK(c->zs_nbr.upload(tab));
+    CHECK(c->zs_tmp.alloc(n * c->V));
+    CHECK(c->zs_flag.alloc(n));
+    return MFT_OK;
+}
+
+// one limiter call = one pass per (threshold, variable) pair, in order, each pass on the state the previous one left
+static int launch_limiter(mft_ctx *c, int npairs, const double *thresholds, const int *variables)
+{
+    CHECK(zs_prepare(c));
+    ScopedTimer tm(c, MFT_K_OTHER);
+    const int64_t n = c->n_local;
+    for (int i = 0; i < npairs; ++i) {
+        if (variables[i] != ZS_VAR_DENSITY && variables[i] != ZS_VAR_PRESSURE) return fail(MFT_EINVAL, "Zhang-Shu limiter: unknown variable %d", variables[i]);
+        ZsArgs a{c->zs_nbr.p, c->k, n, c->u.p, c->zs_tmp.p, c->zs_flag.p, thresholds[i], c->eqp[0], variables[i]};
+        k_zs_detect<<<grid_for(n, 128), 128, 0, c->stream>>>(a);
+        k_zs_apply<<<grid_for(n, 256), 256, 0, c->stream>>>(n, c->zs_flag.p, c->zs_tmp.p, c->u.p);
+        c->launches += 2;
+        LAUNCH_CHECK();
+    }
+    return MFT_OK;
+}
+
+extern "C" int mft_limiter_zhang_shu(mft_ctx *c, int npairs, const double *thresholds, const int *variables,
+                                     double *const *u_soa, int mem)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    if (npairs < 0 || (npairs > 0 && (!thresholds || !variables))) return fail(MFT_EINVAL, "mft_limiter_zhang_shu: bad arguments");
+    if (mem == MFT_MEM_HOST) {
+        CHECK(upload_soa(c, u_soa, c->u.p));
+    } else if (mem != MFT_MEM_DEVICE) {
+        return fail(MFT_EINVAL, "mft_limiter_zhang_shu: mem must be MFT_MEM_HOST or MFT_MEM_DEVICE");
+    }
+    c->have_fsal = false;  // u changed: f(u) has to be recomputed
+    CHECK(launch_limiter(c, npairs, thresholds, variables));
+    if (mem == MFT_MEM_HOST) {
+        CHECK(download_soa(c, c->u.p, u_soa));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return MFT_OK;
+}
+
+extern "C" int mft_set_stage_limiter(mft_ctx *c, int npairs, const double *thresholds, const int *variables)
+{
+    NEED_CTX(c);
+    if (npairs < 0 || (npairs > 0 && (!thresholds || !variables))) return fail(MFT_EINVAL, "mft_set_stage_limiter: bad arguments");
+    c->stage_lim_thresholds.assign(thresholds, thresholds + npairs);
+    c->stage_lim_variables.assign(variables, variables + npairs);
+    // captured steps bake the launch sequence in: start over
+    for (auto &g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
+    return MFT_OK;
+}
+
 // ---- SSPRK43 with embedded error estimate (the integrator the reference names: rbfsolver_test.jl:104-107) ------------
 // The library does the four stages and returns the LOCAL sum of squared scaled errors and the local entry count; the
 // caller combines ranks (sum both), forms EEst = sqrt(sumsq/count) (ode_norm, src/auxiliary/mpi.jl:15-19) and runs its
@@ -2201,6 +2304,7 @@ extern "C" int mft_ssprk43_step(mft_ctx *c, double t, double dt, double abstol, 
     NEED_CTX(c);
     CHECK(mft_finalize(c));
     if (c->step_pending) return fail(MFT_EINVAL, "mft_ssprk43_step: previous step was neither committed nor rejected (mft_step_commit)");
+    if (!c->stage_lim_variables.empty()) return fail(MFT_ENOTSUP, "mft_ssprk43_step: the stage limiter is wired into mft_ssprk_step (SSPRK33) only");
     const int64_t len = c->n_local * c->V, len_tot = c->n_tot * c->V;
     if (!c->utilde.p) {
         CHECK(c->utilde.alloc(len_tot));

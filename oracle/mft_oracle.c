@@ -540,3 +540,50 @@ void orc_rhs_repeat(const orc_problem *P, double *u, double *du, int reps)
 {
     for (int r = 0; r < reps; ++r) orc_rhs(P, u, du);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Zhang-Shu positivity limiter on the point cloud:
+ * src/callbacks_stage/positivity_zhang_shu_point2d.jl:22-82 (one (threshold, variable) pair; the recursion over pairs
+ * of positivity_zhang_shu.jl:50-72 is done by the caller).  nbr: n x k row-major, 0-based, in the kNN list order.
+ * variable 0 = Trixi.density, 1 = Trixi.pressure (third party: (gamma-1)*(rho_e - 0.5*(rho_v1^2+rho_v2^2)/rho), no
+ * product that @muladd can fuse).  The blend theta*u + (1-theta)*u_mean is inside @muladd; StaticArrays maps
+ * muladd(scalar, SVector, SVector) to per-component muladd -> fma.  PARITY UNPINNED (no reference test uses it).
+ * local_u, u_mean: scratch, 4n each (SoA like u). ---------------------------------------------------------------- */
+static double zs_variable(int variable, double gamma, double rho, double m1, double m2, double E)
+{
+    if (variable == 0) return rho;
+    return (gamma - 1.0) * (E - 0.5 * (m1 * m1 + m2 * m2) / rho);
+}
+static double jl_min(double a, double b)
+{
+    if (a != a) return a;
+    if (b != b) return b;
+    return a < b ? a : b;
+}
+void orc_limiter_zhang_shu(int64_t n, int k, const int64_t *nbr, double gamma, double threshold, int variable, double *u,
+                           double *local_u, double *u_mean)
+{
+    for (int64_t i = 0; i < 4 * n; ++i) local_u[i] = u_mean[i] = 0.0; /* set_to_zero! :28-29 */
+    for (int64_t e = 0; e < n; ++e) {
+        double value_min = INFINITY; /* typemax */
+        for (int q = 0; q < k; ++q) {
+            const int64_t i = nbr[e * k + q];
+            value_min = jl_min(value_min, zs_variable(variable, gamma, u[i], u[n + i], u[2 * n + i], u[3 * n + i]));
+        }
+        if (!(value_min < threshold)) continue;
+        for (int q = 0; q < k; ++q) {
+            const int64_t i = nbr[e * k + q];
+            for (int v = 0; v < 4; ++v) u_mean[v * n + e] = u_mean[v * n + e] + u[v * n + i];
+        }
+        for (int v = 0; v < 4; ++v) u_mean[v * n + e] = u_mean[v * n + e] / (double)k;
+        const double value_mean = zs_variable(variable, gamma, u_mean[e], u_mean[n + e], u_mean[2 * n + e], u_mean[3 * n + e]);
+        const double theta = (value_mean - threshold) / (value_mean - value_min);
+        for (int v = 0; v < 4; ++v) local_u[v * n + e] = fma(theta, u[v * n + e], (1.0 - theta) * u_mean[v * n + e]);
+    }
+    for (int64_t e = 0; e < n; ++e) {
+        int nonzero = 0;
+        for (int v = 0; v < 4; ++v) nonzero |= local_u[v * n + e] != 0.0;
+        if (nonzero)
+            for (int v = 0; v < 4; ++v) u[v * n + e] = local_u[v * n + e];
+    }
+}

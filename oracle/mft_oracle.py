@@ -550,6 +550,22 @@ def solve_ssprk43(P, u0, t0, t1, dt0, abstol=1e-8, reltol=1e-8, approx_order=Non
     return u, t, log
 
 
+VAR_DENSITY, VAR_PRESSURE = 0, 1
+
+
+def limiter_zhang_shu(u, neighbors, thresholds, variables, gamma):
+    """PositivityPreservingLimiterZhangShu(thresholds, variables)(u, ...) (positivity_zhang_shu.jl:29-72 +
+    positivity_zhang_shu_point2d.jl:22-82): in place on u (4,N); neighbors (N,k) 0-based in kNN list order"""
+    u = np.ascontiguousarray(u)
+    nb = np.ascontiguousarray(neighbors, dtype=np.int64)
+    n, k = nb.shape
+    s1, s2 = np.zeros_like(u), np.zeros_like(u)
+    for thr, var in zip(thresholds, variables):
+        lib().orc_limiter_zhang_shu(C.c_int64(n), C.c_int(k), C.c_void_p(_ptr(nb)), C.c_double(gamma), C.c_double(thr),
+                                    C.c_int(var), C.c_void_p(_ptr(u)), C.c_void_p(_ptr(s1)), C.c_void_p(_ptr(s2)))
+    return u
+
+
 def time_deriv_weights(t):
     t = np.ascontiguousarray(t, dtype=np.float64)
     w = np.zeros_like(t)
