@@ -2218,6 +2218,10 @@ extern "C" int mft_set_neighbors(mft_ctx *c, const int64_t *nbr1)
         if (j < 0 || j >= c->n_tot) return fail(MFT_EINVAL, "mft_set_neighbors: neighbour %lld out of range", (long long)nbr1[p]);
         c->host_nbr[(size_t)p] = (int32_t)j;
     }
+    // captured steps may hold the old table's address: start over
+    for (auto &g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
     c->zs_nbr.release();  // rebuilt (device numbering) at the next limiter call
     return MFT_OK;
 }
