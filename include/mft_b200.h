@@ -203,6 +203,22 @@ int mft_host_unregister(void *p);
  * Hilbert space-filling-curve order of a 2-D cloud: perm1_out[d] = 1-based index of the d-th point along the curve. */
 int mft_sfc_order(int64_t n, const double *x, const double *y, int64_t *perm1_out);
 
+/* ---- setup pipeline on the device ------------------------------------------
+ * Stateless: host arrays in, host arrays out; the device is used for the search / the batched solves.
+ *
+ * mft_setup_knn replaces the KDTree + knn(kdtree, points, nv, true) calls of the PointData constructor
+ * (src/domains/PointCloudDomain/geometry_primatives.jl:322-339): nbr1_out = n x k row-major, 1-based, ascending by
+ * distance, the point itself first, exact distance ties by ascending index; dist_out (nullable) = the n x k distances
+ * (dx_min = minimum, dx_avg = mean of column 2, as the reference forms them from its 2-NN query). */
+int mft_setup_knn(int device, int64_t n, const double *x, const double *y, int k, int64_t *nbr1_out, double *dist_out);
+/* mft_setup_rbf_weights replaces the per-point loop of compute_flux_operator
+ * (src/solvers/pointcloudsolver/compute_operators.jl:409-453; deriv_order > 1: :549-594) for the polyharmonic spline
+ * basis r^phs_power + monomials up to poly_degree: wx_out / wy_out = n x k row-major weights of d^m/dx^m and d^m/dy^m
+ * (m = deriv_order, 1..4), aligned with nbr1 (= domain.pd.neighbors, 1-based).  Feed them to mft_set_operator_ell, or
+ * assemble sparse(I, J, V) on the caller's side. */
+int mft_setup_rbf_weights(int device, int64_t n, const double *x, const double *y, int k, const int64_t *nbr1, int phs_power,
+                          int poly_degree, int deriv_order, double *wx_out, double *wy_out);
+
 /* ---- Zhang-Shu positivity limiter (stage callback) ------------------------------------------------------
  * replaces Trixi.limiter_zhang_shu!(u, threshold, variable, domain::PointCloudDomain{2}, ...)
  * (src/callbacks_stage/positivity_zhang_shu_point2d.jl:22-82) and the (thresholds, variables) recursion of

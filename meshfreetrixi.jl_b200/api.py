@@ -73,6 +73,7 @@ class RBFFDEngineCUDA:
     prefetch_distance: int | None = None  # slices ahead for the L2 prefetch of operator data (None: library default, 0: off)
     single_sweep_exact: bool = False   # k=20: exact-order pass A in one sweep (y-products parked in registers)
     refine_order: bool = False         # order rows inside 256-row blocks by D' row length (less padding, worse gather locality)
+    setup: str = "host"                # "device": kNN + RBF-FD weight solves on the GPU (mft_setup_knn / mft_setup_rbf_weights)
 
 
 @dataclass
@@ -108,7 +109,7 @@ class PointCloudDomain:
         name to the 1-based boundary group number, as in the reference tests."""
         cl = cloudmod.read_medusa_file(source) if isinstance(source, str) else source
         nv = solver.basis.nv
-        nb, dx_min, dx_avg = setup_ops.knn(cl.points, nv)
+        nb, dx_min, dx_avg = setup_ops.knn_with(solver.engine, cl.points, nv)
         self.pd = PointData(np.ascontiguousarray(cl.points, dtype=np.float64), nb, cl.points.shape[0], nv, dx_min, dx_avg)
         self.boundary_tags = {name: BoundaryData(np.asarray(cl.boundary_idxs[g - 1], dtype=np.int64),
                                                  np.asarray(cl.boundary_normals[g - 1], dtype=np.float64))
@@ -227,7 +228,7 @@ class SourceHyperviscosityFlyer(_Source):
 
     def __init__(self, solver, equations, domain, k=2, c=1.0):
         p, N = solver.basis.approx_type.rbf_type.Nrbf, solver.basis.N
-        ops = setup_ops.compute_flux_operator(domain.pd.points, domain.pd.neighbors, p, N, 2 * k)
+        ops = setup_ops.flux_operator_with(solver.engine, domain.pd.points, domain.pd.neighbors, p, N, 2 * k)
         self.hv_differentiation_matrix = (ops[0] + ops[1]).tocsc()
         self.gamma = c * domain.pd.dx_min ** (2 * k)
         self.c = c
@@ -239,7 +240,7 @@ class SourceHyperviscosityTominec(_Source):
 
     def __init__(self, solver, equations, domain, c=1.0):
         p, N = solver.basis.approx_type.rbf_type.Nrbf, solver.basis.N
-        ops = setup_ops.compute_flux_operator(domain.pd.points, domain.pd.neighbors, p, N, 2)
+        ops = setup_ops.flux_operator_with(solver.engine, domain.pd.points, domain.pd.neighbors, p, N, 2)
         lap = (ops[0] + ops[1]).tocsc()
         self.hv_differentiation_matrix = (lap.T @ lap).tocsc()
         self.gamma = c * domain.pd.dx_min ** 4.5
@@ -309,7 +310,7 @@ class SemidiscretizationHyperbolic:
                     raise NotImplementedError("hyperviscosity sources are not partitioned yet (multi-GPU supports the "
                                               "flux divergence and the upwind / residual viscosity sources)")
         else:
-            ops = operators or setup_ops.compute_flux_operator(pd.points, pd.neighbors, p, N)
+            ops = operators or setup_ops.flux_operator_with(eng, pd.points, pd.neighbors, p, N)
         self.cache = Cache(pd, ops)
         lib = L.load()
         ctx = C.c_void_p()

@@ -2516,6 +2516,8 @@ static inline uint64_t hilbert_d(uint32_t x, uint32_t y, int bits)
     return d;
 }
 
+#include "mft_setup_cuda.inl"
+
 extern "C" int mft_sfc_order(int64_t n, const double *x, const double *y, int64_t *perm1_out)
 {
     if (n <= 0 || !x || !y || !perm1_out) return fail(MFT_EINVAL, "mft_sfc_order: bad arguments");

@@ -160,3 +160,53 @@ def julia_csc(A):
     A.sort_indices()
     return (np.ascontiguousarray(A.indptr, dtype=np.int64) + 1, np.ascontiguousarray(A.indices, dtype=np.int64) + 1,
             np.ascontiguousarray(A.data, dtype=np.float64))
+
+
+# ---- the same two setup steps on the device (libmft_b200.so, no CPU path) -----------
+def knn_device(points: np.ndarray, nv: int, device: int = 0):
+    """mft_setup_knn: cell-grid kNN on the GPU.  Same result contract as knn() (neighbour tables bit-identical:
+    distance-sorted, self first, exact ties by ascending index)."""
+    from . import _lib as L
+
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    n = pts.shape[0]
+    x, y = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1])
+    nbr1 = np.empty((n, nv), dtype=np.int64)
+    dist = np.empty((n, nv), dtype=np.float64)
+    L.check(L.load().mft_setup_knn(device, n, L.ptr(x), L.ptr(y), nv, L.ptr(nbr1), L.ptr(dist)))
+    nbr1 -= 1
+    return nbr1, float(dist[:, 1].min()), float(dist[:, 1].mean())
+
+
+def rbf_fd_weights_device(points: np.ndarray, neighbors: np.ndarray, p: int, N: int, k: int | None = None, device: int = 0):
+    """mft_setup_rbf_weights: one GPU thread per point builds and solves its (nv + npoly)^2 system.  Same contract as
+    rbf_fd_weights() (weights agree to rounding: different elimination order)."""
+    from . import _lib as L
+
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    n, nv = neighbors.shape
+    x, y = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1])
+    nbr1 = np.ascontiguousarray(neighbors, dtype=np.int64) + 1
+    wx = np.empty((n, nv), dtype=np.float64)
+    wy = np.empty((n, nv), dtype=np.float64)
+    L.check(L.load().mft_setup_rbf_weights(device, n, L.ptr(x), L.ptr(y), nv, L.ptr(nbr1), p, N, 1 if k is None else k,
+                                           L.ptr(wx), L.ptr(wy)))
+    return wx, wy
+
+
+def compute_flux_operator_device(points, neighbors, p: int, N: int, k: int | None = None, device: int = 0):
+    wx, wy = rbf_fd_weights_device(points, neighbors, p, N, k, device)
+    return [assemble_csc(neighbors, wx), assemble_csc(neighbors, wy)]
+
+
+def knn_with(engine, points, nv):
+    """PointData ctor for an engine: RBFFDEngineCUDA(setup="device") searches on the GPU."""
+    if getattr(engine, "setup", "host") == "device":
+        return knn_device(points, nv, engine.device)
+    return knn(points, nv)
+
+
+def flux_operator_with(engine, points, neighbors, p, N, k=None):
+    if getattr(engine, "setup", "host") == "device":
+        return compute_flux_operator_device(points, neighbors, p, N, k, engine.device)
+    return compute_flux_operator(points, neighbors, p, N, k)

@@ -1,0 +1,56 @@
+"""Host emulation of the product's sync-free device kernels (TEST INFRASTRUCTURE).  The product's per-thread device
+functions (meshfreetrixi.jl_b200/csrc/*_kernels.cuh, `MFT_HD` bodies) and their host orchestration are compiled with g++
+and driven by a host loop, so the CPU-only test tier can check kernel logic against the oracle.  The product never loads
+this library."""
+import ctypes as C
+
+import numpy as np
+
+from . import build as _build
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(_build.build())
+        _lib.emu_last_error.restype = C.c_char_p
+    return _lib
+
+
+class EmuError(RuntimeError):
+    pass
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _check(rc):
+    if rc != 0:
+        raise EmuError(lib().emu_last_error().decode())
+
+
+def setup_knn(points, k):
+    """emulated mft_setup_knn -> (neighbors 0-based (n,k), distances (n,k))"""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    n = len(pts)
+    x, y = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1])
+    nb = np.empty((n, k), np.int64)
+    d = np.empty((n, k))
+    _check(lib().emu_setup_knn(C.c_int64(n), _p(x), _p(y), C.c_int(k), _p(nb), _p(d)))
+    return nb - 1, d
+
+
+def setup_rbf_weights(points, neighbors, p, N, kk=1, scratch_bytes=0):
+    """emulated mft_setup_rbf_weights -> (wx, wy) (n,k); scratch_bytes > 0 forces small launches (chunking)"""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    n, k = neighbors.shape
+    x, y = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1])
+    nb1 = np.ascontiguousarray(neighbors, dtype=np.int64) + 1
+    wx = np.empty((n, k))
+    wy = np.empty((n, k))
+    _check(lib().emu_setup_rbf_weights(C.c_int64(n), _p(x), _p(y), C.c_int(k), _p(nb1), C.c_int(p), C.c_int(N), C.c_int(kk),
+                                       _p(wx), _p(wy), C.c_int64(scratch_bytes)))
+    return wx, wy

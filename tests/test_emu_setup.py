@@ -1,0 +1,155 @@
+"""Row f1 (device setup pipeline), CPU tier: the product's kernel thread bodies and host orchestration
+(csrc/mft_setup_kernels.cuh, csrc/mft_setup_host.inl), compiled for the host by tests/emu and checked against the oracle
+and brute force.  The GPU tier (tests/test_zz_setup_gpu.py) runs the same source as CUDA kernels through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import emu
+from cases import orc
+
+
+def brute_knn(pts, k):
+    """all-pairs reference: ascending (distance, index)"""
+    dx = pts[:, None, 0] - pts[None, :, 0]
+    dy = pts[:, None, 1] - pts[None, :, 1]
+    d = np.sqrt(dx * dx + dy * dy)
+    idx = np.broadcast_to(np.arange(len(pts)), d.shape)
+    o = np.lexsort((idx, d), axis=1)[:, :k]
+    return o, np.take_along_axis(d, o, 1)
+
+
+def adversarial_clouds():
+    rng = np.random.default_rng(5)
+    out = {}
+    gx, gy = np.meshgrid(np.arange(40.0), np.arange(25.0))
+    out["lattice"] = np.stack([gx.ravel(), gy.ravel()], 1) * 0.1          # exact distance ties everywhere
+    out["uniform"] = rng.random((3000, 2)) * [3.0, 1.0]
+    c = rng.normal(size=(2500, 2)) * 0.01
+    c[:500] += [5, 5]
+    c[500:1000] *= 100
+    out["clustered"] = c                                                    # cell occupancy from 0 to hundreds
+    out["thin"] = np.stack([rng.random(2000), rng.random(2000) * 1e-9], 1)  # extreme aspect ratio
+    out["line"] = np.stack([rng.random(500), np.zeros(500)], 1)             # zero extent in y
+    d = rng.random((1000, 2))
+    d[::7] = d[3]
+    out["duplicates"] = d                                                   # coincident points (distance 0 ties)
+    out["tiny"] = rng.random((20, 2))                                       # k == n
+    out["offset"] = rng.random((2000, 2)) * 1e-3 + [1e5, -3e4]              # far from the origin
+    out["single_cell"] = np.zeros((30, 2)) + rng.random((30, 2)) * 1e-300   # degenerate extent
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(adversarial_clouds()))
+def test_knn_bit_exact_vs_brute_force(name):
+    pts = np.ascontiguousarray(adversarial_clouds()[name])
+    for k in (1, 7, 20, 42):
+        if k > len(pts):
+            continue
+        nb, d = emu.setup_knn(pts, k)
+        rb, rd = brute_knn(pts, k)
+        assert np.array_equal(nb, rb), (name, k)
+        assert np.array_equal(d, rd), (name, k)
+
+
+def test_knn_matches_the_oracle_on_the_fixture_and_a_synthetic_cloud():
+    fx = cases.fixture_setup()
+    nb, d = emu.setup_knn(fx["points"], fx["nv"])
+    assert np.array_equal(nb, fx["nb"])
+    assert d[:, 1].min() == fx["dx_min"] and d[:, 1].mean() == fx["dx_avg"]
+    import mft_b200 as m
+
+    cl = m.cloud.jittered_lattice(256, 128, 10.0, 5.0, seed=0).points
+    nb, d = emu.setup_knn(cl, 20)
+    onb, omin, oavg = orc.point_data(cl, 20)
+    assert np.array_equal(nb, onb) and d[:, 1].min() == omin and d[:, 1].mean() == oavg
+
+
+def test_knn_argument_errors():
+    pts = np.random.default_rng(0).random((10, 2))
+    with pytest.raises(emu.EmuError, match="exceeds the number of points"):
+        emu.setup_knn(pts, 11)
+    with pytest.raises(emu.EmuError, match="outside 1"):
+        emu.setup_knn(np.random.default_rng(0).random((100, 2)), 65)
+    bad = pts.copy()
+    bad[3, 1] = np.nan
+    with pytest.raises(emu.EmuError, match="non-finite"):
+        emu.setup_knn(bad, 3)
+
+
+@pytest.mark.parametrize("p,N,k", [(3, 3, None), (5, 3, None), (5, 3, 2), (5, 3, 4), (3, 2, None), (5, 4, None), (7, 5, None)])
+def test_weights_match_oracle(p, N, k):
+    """one-thread-per-point LU (product kernel body) vs the oracle's per-point Bunch-Kaufman solve: 1e-8 of the row scale
+    (same bar as the host mirror, tests/test_setup_cpu.py); 1e-5 for 4th derivatives"""
+    s = cases.fixture_setup(p=p, N=N)
+    import mft_b200 as m
+
+    wx, wy = emu.setup_rbf_weights(s["points"], s["nb"], p, N, k or 1)
+    ref = orc.compute_flux_operator(s["points"], s["nb"], p, N, k)
+    for w, B in zip((wx, wy), ref):
+        A = m.setup_ops.assemble_csc(s["nb"], w)
+        assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+        tol = 1e-8 if (k or 1) <= 2 else 1e-5
+        assert np.abs(A.data - B.data).max() <= tol * np.abs(B.data).max()
+
+
+def test_weights_reproduce_polynomials():
+    """size-independent property: D x^a y^b is exact for a + b <= N (here at the 1e-9 level of the operator scale)"""
+    import mft_b200 as m
+
+    cl = m.cloud.jittered_lattice(64, 48, 4.0, 3.0, seed=2).points
+    nb, _ = emu.setup_knn(cl, 20)
+    wx, wy = emu.setup_rbf_weights(cl, nb, 3, 3, 1)
+    X, Y = cl[nb, 0], cl[nb, 1]
+    scale = np.abs(wx).sum(axis=1).max()
+    assert np.abs(wx.sum(axis=1)).max() <= 1e-9 * scale and np.abs(wy.sum(axis=1)).max() <= 1e-9 * scale
+    assert np.abs((wx * X).sum(axis=1) - 1.0).max() <= 1e-8 and np.abs((wy * Y).sum(axis=1) - 1.0).max() <= 1e-8
+    assert np.abs((wx * Y).sum(axis=1)).max() <= 1e-8 and np.abs((wy * X).sum(axis=1)).max() <= 1e-8
+    f = X ** 2 * Y
+    assert np.abs((wx * f).sum(axis=1) - 2 * cl[:, 0] * cl[:, 1]).max() <= 1e-7
+    # second derivatives: L (x^2 + y^2) = 4
+    wxx, wyy = emu.setup_rbf_weights(cl, nb, 5, 3, 2)
+    assert np.abs(((wxx + wyy) * (X ** 2 + Y ** 2)).sum(axis=1) - 4.0).max() <= 1e-6
+
+
+def test_weights_do_not_depend_on_the_launch_chunking():
+    s = cases.fixture_setup(p=3, N=3)
+    a = emu.setup_rbf_weights(s["points"], s["nb"], 3, 3, 1)
+    b = emu.setup_rbf_weights(s["points"], s["nb"], 3, 3, 1, scratch_bytes=1)      # 256 points per launch
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_weights_argument_and_degenerate_stencil_errors():
+    rng = np.random.default_rng(1)
+    pts = rng.random((200, 2))
+    nb, _ = emu.setup_knn(pts, 20)
+    with pytest.raises(emu.EmuError, match="derivative order"):
+        emu.setup_rbf_weights(pts, nb, 3, 3, 5)
+    with pytest.raises(emu.EmuError, match="odd"):
+        emu.setup_rbf_weights(pts, nb, 4, 3, 1)
+    with pytest.raises(emu.EmuError, match="monomials"):
+        emu.setup_rbf_weights(pts, nb[:, :8], 3, 3, 1)
+    bad = nb.copy()
+    bad[5, 3] = 200
+    with pytest.raises(emu.EmuError, match="out of range"):
+        emu.setup_rbf_weights(pts, bad, 3, 3, 1)
+    line = np.stack([rng.random(100), np.zeros(100)], 1)          # collinear stencil: the reference's `\\` would throw
+    nbl, _ = emu.setup_knn(line, 20)
+    with pytest.raises(emu.EmuError, match="singular"):
+        emu.setup_rbf_weights(line, nbl, 3, 3, 1)
+
+
+def test_product_library_refuses_setup_without_a_device():
+    import mft_b200 as m
+
+    lib = m._lib.load()
+    if lib.mft_device_count() > 0:
+        pytest.skip("GPU box: covered by tests/test_zz_setup_gpu.py")
+    pts = np.random.default_rng(0).random((50, 2))
+    with pytest.raises(m._lib.MftError, match="no CPU fallback"):
+        m.setup_ops.knn_device(pts, 5)
+    nb, _ = emu.setup_knn(pts, 20)
+    with pytest.raises(m._lib.MftError, match="no CPU fallback"):
+        m.setup_ops.rbf_fd_weights_device(pts, nb, 3, 3)
