@@ -3,6 +3,7 @@
 #include "../../include/mft_b200.h"
 #include "mft_kernels.cuh"
 #include "mft_tile_kernels.cuh"
+#include "mft_limiter_kernels.cuh"
 #include "mft_nccl.h"
 
 #include <algorithm>

@@ -1192,96 +1192,7 @@ __global__ void __launch_bounds__(256) k_ssprk33_stage(int stage, double dt, dou
     }
 }
 
-// ---- Zhang-Shu positivity limiter on the point cloud (stage callback) -----------------
-// Trixi.limiter_zhang_shu!(u, threshold, variable, domain::PointCloudDomain{2}, ...)
-// src/callbacks_stage/positivity_zhang_shu_point2d.jl:22-82.  Per point: minimum of `variable` over its kNN stencil
-// (domain.pd.neighbors: distance-sorted, self first); where that is below the threshold the point is blended towards the
-// stencil mean,  theta = (var(mean) - threshold) / (var(mean) - min),  u <- theta*u + (1-theta)*mean.  Jacobi style: all
-// reads see the state before the pass (the reference builds local_u first and copies afterwards), hence two kernels.
-// Arithmetic as the reference's: the mean adds the neighbours in list order and divides by k; the blend sits in an
-// @muladd scope and StaticArrays' muladd(scalar, SVector, SVector) maps to per-component muladd -> fma(theta, u, (1-theta)*mean);
-// Trixi's `pressure` has no fusable product.  (Third-party semantics, no reference test: parity unpinned.)
-constexpr int ZS_VAR_DENSITY = 0;
-constexpr int ZS_VAR_PRESSURE = 1;
-
-struct ZsArgs {
-    const int *nbr;  // k x n_rows, column-major ([c][row]): device index of the c-th nearest neighbour
-    int k;
-    int64_t n_rows;
-    const void *u;
-    void *tmp;            // limited states
-    unsigned char *flag;  // 1: row was limited
-    double threshold, gamma;
-    int variable;
-};
-
-__device__ __forceinline__ double zs_variable(int variable, double gamma, const Vec<4> &u)
-{
-    if (variable == ZS_VAR_DENSITY) return u.a[0];
-    return (gamma - 1.0) * (u.a[3] - 0.5 * (u.a[1] * u.a[1] + u.a[2] * u.a[2]) / u.a[0]);
-}
-// Julia min(::Float64, ::Float64): NaN-propagating
-__device__ __forceinline__ double jl_min(double a, double b)
-{
-    if (a != a) return a;
-    if (b != b) return b;
-    return a < b ? a : b;
-}
-
-__global__ void __launch_bounds__(128) k_zs_detect(const ZsArgs A)
-{
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= A.n_rows) return;
-    const Vec<4> *__restrict__ u = reinterpret_cast<const Vec<4> *>(A.u);
-    double vmin = __longlong_as_double(0x7ff0000000000000LL);  // typemax(Float64)
-    Vec<4> sum;
-#pragma unroll
-    for (int v = 0; v < 4; ++v) sum.a[v] = 0.0;
-    constexpr int kBatch = 4;
-    for (int c0 = 0; c0 < A.k; c0 += kBatch) {
-        Vec<4> uj[kBatch];
-#pragma unroll
-        for (int b = 0; b < kBatch; ++b) {
-            const int cc = c0 + b < A.k ? c0 + b : A.k - 1;
-            uj[b] = ld_ro(u + A.nbr[(int64_t)cc * A.n_rows + row]);
-        }
-#pragma unroll
-        for (int b = 0; b < kBatch; ++b) {
-            if (c0 + b < A.k) {
-                vmin = jl_min(vmin, zs_variable(A.variable, A.gamma, uj[b]));
-#pragma unroll
-                for (int v = 0; v < 4; ++v) sum.a[v] = sum.a[v] + uj[b].a[v];
-            }
-        }
-    }
-    unsigned char f = 0;
-    if (vmin < A.threshold) {
-        Vec<4> mean, lim;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) mean.a[v] = sum.a[v] / (double)A.k;
-        const double vmean = zs_variable(A.variable, A.gamma, mean);
-        const double theta = (vmean - A.threshold) / (vmean - vmin);
-        const Vec<4> ui = ld_ro(u + row);
-        bool nonzero = false;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            lim.a[v] = fma(theta, ui.a[v], (1.0 - theta) * mean.a[v]);
-            nonzero |= lim.a[v] != 0.0;  // local_u[element] != zero_el (NaN != 0 is true, as in Julia)
-        }
-        if (nonzero) {
-            st_vec(reinterpret_cast<Vec<4> *>(A.tmp) + row, lim);
-            f = 1;
-        }
-    }
-    A.flag[row] = f;
-}
-
-__global__ void __launch_bounds__(256) k_zs_apply(int64_t n_rows, const unsigned char *__restrict__ flag, const void *tmp, void *u)
-{
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n_rows) return;
-    if (flag[row]) reinterpret_cast<Vec<4> *>(u)[row] = reinterpret_cast<const Vec<4> *>(tmp)[row];
-}
+// (the Zhang-Shu positivity limiter kernels live in mft_limiter_kernels.cuh)
 
 // ---- SSPRK43 stage updates + embedded error estimate (OrdinaryDiffEq low-storage SSPRK43; DESIGN.md "time loop") --------
 // stage 1 also snapshots uprev; stage 3 forms utilde = (uprev + 2 u3)/3 and u = (2 uprev + u3)/3; stage 4 turns utilde into

@@ -54,3 +54,16 @@ def setup_rbf_weights(points, neighbors, p, N, kk=1, scratch_bytes=0):
     _check(lib().emu_setup_rbf_weights(C.c_int64(n), _p(x), _p(y), C.c_int(k), _p(nb1), C.c_int(p), C.c_int(N), C.c_int(kk),
                                        _p(wx), _p(wy), C.c_int64(scratch_bytes)))
     return wx, wy
+
+
+def limiter_zhang_shu(u, neighbors, thresholds, variables, gamma):
+    """emulated k_zs_detect / k_zs_apply passes, in place on u (4,N); neighbors (N,k) 0-based in kNN list order"""
+    assert u.dtype == np.float64 and u.flags.c_contiguous
+    nb = np.ascontiguousarray(neighbors, dtype=np.int64)
+    n, k = nb.shape
+    thr = np.asarray(thresholds, dtype=np.float64)
+    var = np.asarray(variables, dtype=np.int32)
+    rc = lib().emu_limiter_zhang_shu(C.c_int64(n), C.c_int(k), _p(nb), C.c_double(gamma), C.c_int(len(thr)), _p(thr), _p(var), _p(u))
+    if rc != 0:
+        raise EmuError("emu_limiter_zhang_shu failed")
+    return u

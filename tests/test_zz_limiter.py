@@ -59,6 +59,24 @@ def test_oracle_limiter_against_python_restatement_and_properties():
     assert np.array_equal(orc.limiter_zhang_shu(v.copy(), fx["nb"], (1e-6,), (orc.VAR_DENSITY,), cases.GAMMA), v)
 
 
+def test_emulated_device_kernels_match_oracle_bit_for_bit():
+    """the product's kernel thread bodies (csrc/mft_limiter_kernels.cuh) run on the host by tests/emu, device data layout"""
+    import emu
+
+    fx = cases.fixture_setup(p=3, N=3)
+    for thr, var in (((0.05, 0.02), (orc.VAR_DENSITY, orc.VAR_PRESSURE)), ((0.9,), (orc.VAR_DENSITY,)),
+                     ((1e-6,), (orc.VAR_PRESSURE,))):
+        u0 = _state(fx)
+        ref = orc.limiter_zhang_shu(u0.copy(), fx["nb"], thr, var, cases.GAMMA)
+        got = emu.limiter_zhang_shu(u0.copy(), fx["nb"], thr, var, cases.GAMMA)
+        assert np.array_equal(got, ref, equal_nan=True)
+    u0 = _state(fx)
+    u0[0, 40] = np.nan                                              # NaN propagates through Julia's min: stencils of 40 are limited
+    ref = orc.limiter_zhang_shu(u0.copy(), fx["nb"], (0.05,), (orc.VAR_DENSITY,), cases.GAMMA)
+    got = emu.limiter_zhang_shu(u0.copy(), fx["nb"], (0.05,), (orc.VAR_DENSITY,), cases.GAMMA)
+    assert np.array_equal(got, ref, equal_nan=True)
+
+
 @pytest.mark.gpu
 def test_device_limiter_matches_oracle():
     import mft_b200 as m
