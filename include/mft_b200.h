@@ -57,6 +57,7 @@ typedef struct mft_ctx mft_ctx;
 #define MFT_SRC_HV_TOMINEC 1  /* :121-134  du += -gamma * (L'L) u      params: gamma                    + matrix */
 #define MFT_SRC_UPWIND 2      /* :351-380  params: c_uw, dx_avg                                                  */
 #define MFT_SRC_RESIDUAL 3    /* :382-409  params: c_rv, c_uw, dx_avg, polydeg                                   */
+#define MFT_SRC_IGR 4         /* src/sources/IGR.jl:211-239  params: alpha [, maxiter = 20] ; sigma solved by CG (IterativeSolvers.cg!) */
 
 #define MFT_MEM_HOST 0
 #define MFT_MEM_DEVICE 1
@@ -103,6 +104,8 @@ typedef struct mft_ctx mft_ctx;
 #define MFT_FIELD_RESIDUAL 4   /* V*N doubles, SoA */
 #define MFT_FIELD_APPROX_DU 5  /* V*N doubles, SoA */
 #define MFT_FIELD_NORMS 6      /* V doubles: n_inf_norms of update_residual_visc! */
+#define MFT_FIELD_SIGMA 7      /* N doubles: cache.sigma of SourceIGR (IGR.jl:169-191) */
+#define MFT_FIELD_IGR_STATUS 8 /* 3 doubles: CG iterations of the last solve, final |r|, initial |r| */
 
 #define MFT_SSPRK33 0
 

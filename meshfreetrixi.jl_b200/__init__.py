@@ -15,6 +15,6 @@ from .api import (BoundaryConditionDirichlet, BoundaryConditionDoNothing, Compre
                   HistoryCallback, LinearScalarAdvectionEquation2D, Point2D, PointCloudBasis, PointCloudDomain,
                   PointCloudSolver, PolyharmonicSpline, RBF, RBFFDEngineCUDA, SemidiscretizationHyperbolic,
                   SourceHyperviscosityFlyer, SourceHyperviscosityTominec, SourceResidualViscosityTominec,
-                  SourceTerms, SourceUpwindViscosityTominec, SSPRK33, SSPRK43, PIController, ParallelPointCloudDomain,
+                  SourceTerms, SourceUpwindViscosityTominec, SourceIGR, cg_, SSPRK33, SSPRK43, PIController, ParallelPointCloudDomain,
                   boundary_condition_slip_wall, solve_adaptive, PositivityPreservingLimiterZhangShu, density, pressure,
                   calc_boundary_flux_, calc_fluxes_, compute_coefficients, rhs_, semidiscretize, solve)

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, "libmft_b200.so")
 EQ_EULER2D, EQ_ADVECTION2D = 0, 1
 OP_DX, OP_DY = 0, 1
 BC_DIRICHLET, BC_SLIP_WALL, BC_DO_NOTHING = 0, 1, 2
-SRC_HV_FLYER, SRC_HV_TOMINEC, SRC_UPWIND, SRC_RESIDUAL = 0, 1, 2, 3
+SRC_HV_FLYER, SRC_HV_TOMINEC, SRC_UPWIND, SRC_RESIDUAL, SRC_IGR = 0, 1, 2, 3, 4
 MEM_HOST, MEM_DEVICE = 0, 1
 OPT_EXACT_ORDER, OPT_MEAN_DIVISOR_VN, OPT_MAX_LEXICOGRAPHIC, OPT_DIAGNOSTICS, OPT_CUDA_GRAPH = 0, 1, 2, 3, 4
 OPT_STAGE_WEIGHTS, OPT_PREFETCH_DISTANCE, OPT_REFINE_ORDER, OPT_SINGLE_SWEEP_EXACT = 5, 6, 7, 8
@@ -25,7 +25,7 @@ OPT_PAIR_ROWS = 9
 OPT_TILE = 10
 OPT_TILE_ROWS = 11
 VAR_DENSITY, VAR_PRESSURE = 0, 1
-FIELD_EPS, FIELD_EPS_UW, FIELD_EPS_RV, FIELD_EPS_C, FIELD_RESIDUAL, FIELD_APPROX_DU, FIELD_NORMS = range(7)
+FIELD_EPS, FIELD_EPS_UW, FIELD_EPS_RV, FIELD_EPS_C, FIELD_RESIDUAL, FIELD_APPROX_DU, FIELD_NORMS, FIELD_SIGMA, FIELD_IGR_STATUS = range(9)
 SSPRK33 = 0
 K_PASS_A, K_PASS_B, K_REDUCE, K_STAGE, K_BC, K_OTHER = range(6)
 

@@ -215,6 +215,15 @@ class _SourceCacheView:
     residual = property(lambda self: self._vec(L.FIELD_RESIDUAL))
     approx_du = property(lambda self: self._vec(L.FIELD_APPROX_DU))
 
+    sigma = property(lambda self: self._scalar(L.FIELD_SIGMA))
+
+    @property
+    def igr_status(self):
+        """(CG iterations of the last solve, final |r|, initial |r|)"""
+        out = np.empty(3)
+        L.check(L.load().mft_get_field(self._s.semi.ctx, L.FIELD_IGR_STATUS, L.ptr(out)))
+        return int(out[0]), float(out[1]), float(out[2])
+
     @property
     def norms(self):
         out = np.empty(self._s.semi.V)
@@ -261,6 +270,25 @@ class SourceResidualViscosityTominec(_Source):
 
     def __init__(self, solver, equations, domain, c_rv=1.0, c_uw=1.0, polydeg=4):
         self.c_rv, self.c_uw, self.polydeg, self.dx_avg = c_rv, c_uw, polydeg, domain.pd.dx_avg
+
+
+def cg_(*args, **kw):
+    """IterativeSolvers.cg!: the linear solver SourceIGR runs on the device (the only one implemented)."""
+    raise TypeError("cg_ is a tag for SourceIGR(linear_solver=cg_); the solve runs inside libmft_b200")
+
+
+class SourceIGR(_Source):
+    """IGR.jl:14-36: information-geometric regularisation.  Per rhs!: b = alpha (tr(Du)^2 + tr((Du)^2)) from the
+    gradients of the primitive variables (:117-158), (rho^-1 - alpha (Dx rho^-1 Dx + Dy rho^-1 Dy)) sigma = b solved by
+    `maxiter` (hard-wired 20, :190) conjugate-gradient iterations from sigma = 0 (:169-191), then du[2] -= Dx sigma,
+    du[3] -= Dy sigma (:211-239).  `linear_solver`: the reference's default `cg` cannot take its three positional
+    arguments; the in-place `cg!` (here `cg_`) is what runs."""
+    kind = L.SRC_IGR
+
+    def __init__(self, solver, equations, domain, alpha=1.0, linear_solver=cg_, maxiter=20):
+        if linear_solver is not cg_:
+            raise NotImplementedError("SourceIGR: only the conjugate-gradient solver (cg_) is implemented on the device")
+        self.alpha, self.maxiter = float(alpha), int(maxiter)
 
 
 class SourceTerms:
@@ -368,6 +396,11 @@ class SemidiscretizationHyperbolic:
                 L.check(lib.mft_add_source(ctx, src.kind, L.ptr(prm), 1, L.ptr(cp), L.ptr(rv), L.ptr(nz)))
             elif src.kind == L.SRC_UPWIND:
                 prm = np.asarray([src.c_uw, src.dx_avg], dtype=np.float64)
+                L.check(lib.mft_add_source(ctx, src.kind, L.ptr(prm), 2, None, None, None))
+            elif src.kind == L.SRC_IGR:
+                if part is not None:
+                    raise NotImplementedError("SourceIGR is single-GPU")
+                prm = np.asarray([src.alpha, float(src.maxiter)], dtype=np.float64)
                 L.check(lib.mft_add_source(ctx, src.kind, L.ptr(prm), 2, None, None, None))
             else:
                 prm = np.asarray([src.c_rv, src.c_uw, src.dx_avg, float(src.polydeg)], dtype=np.float64)

@@ -4,6 +4,7 @@
 #include "mft_kernels.cuh"
 #include "mft_tile_kernels.cuh"
 #include "mft_limiter_kernels.cuh"
+#include "mft_igr_kernels.cuh"
 #include "mft_nccl.h"
 
 #include <algorithm>
@@ -133,6 +134,15 @@ struct Source {
     int polydeg = 4;
     HostCsc hv_host;
     DevEll hv;
+    // SourceIGR (IGR.jl): alpha, CG iteration cap, forward operator as plain sliced ELL, CG vectors, device-side CG scalars
+    double igr_alpha = 1.0;
+    int igr_maxiter = 20;
+    DevEll igr_op;
+    DevBuf<double> igr_vec;  // rho_inv, b, r, c (n each), x, p (n_tot + 1 each), t (2 (n_tot + 1))
+    DevBuf<double> igr_partial;
+    DevBuf<unsigned int> igr_ticket;
+    DevBuf<mft_igr::IgrScalars> igr_scalars;
+    mft_igr::IgrArgs igr_args;
 };
 
 struct KTimer {
@@ -355,6 +365,11 @@ extern "C" int mft_ctx_destroy(mft_ctx *c)
     }
     for (auto *s : c->srcs) {
         s->hv.release();
+        s->igr_op.release();
+        s->igr_vec.release();
+        s->igr_partial.release();
+        s->igr_ticket.release();
+        s->igr_scalars.release();
         delete s;
     }
     c->fwd.release();
@@ -626,6 +641,14 @@ extern "C" int mft_add_source(mft_ctx *c, int kind, const double *params, int np
             if (s->polydeg < 0 || s->polydeg > 7) r = fail(MFT_EINVAL, "mft_add_source: polydeg must be in [0,7]");
             for (auto *o : c->srcs)
                 if (o->kind == MFT_SRC_RESIDUAL) r = fail(MFT_ENOTSUP, "mft_add_source: only one residual-viscosity source per ctx");
+        }
+    } else if (kind == MFT_SRC_IGR) {
+        if (c->eq != MFT_EQ_EULER2D) r = fail(MFT_ENOTSUP, "mft_add_source: the IGR source is defined for Euler 2-D only (IGR.jl:117-119); call mft_set_equation first");
+        else if (nparams < 1 || !params) r = fail(MFT_EINVAL, "mft_add_source: IGR needs alpha [, maxiter]");
+        else {
+            s->igr_alpha = params[0];
+            s->igr_maxiter = nparams >= 2 ? (int)params[1] : 20;
+            if (s->igr_maxiter < 0 || s->igr_maxiter > 1000) r = fail(MFT_EINVAL, "mft_add_source: IGR maxiter must be in [0,1000]");
         }
     } else {
         r = fail(MFT_EINVAL, "mft_add_source: unknown kind %d", kind);
@@ -1338,6 +1361,41 @@ extern "C" int mft_finalize(mft_ctx *c)
             CHECK(build_ell(c, H, c->n_local, false, s->hv));
             s->hv_host = HostCsc();
         }
+        if (s->kind == MFT_SRC_IGR) {
+            using mft_igr::IgrArgs;
+            using mft_igr::IgrScalars;
+            CHECK(build_ell(c, F, c->n_local, true, s->igr_op));
+            const int64_t nl = c->n_local, np1 = n + 1;
+            CHECK(s->igr_vec.alloc(4 * nl + 4 * np1));
+            CU(cudaMemset(s->igr_vec.p, 0, sizeof(double) * (4 * nl + 4 * np1)));
+            const int nblocks = grid_for(nl, mft_igr::kBlock);
+            CHECK(s->igr_partial.alloc(nblocks));
+            CHECK(s->igr_ticket.alloc(1));
+            CU(cudaMemset(s->igr_ticket.p, 0, sizeof(unsigned int)));
+            IgrScalars init{};
+            init.prev_res = 1.0;
+            init.maxiter = s->igr_maxiter;
+            init.done = 1;
+            CHECK(s->igr_scalars.upload(std::vector<IgrScalars>(1, init)));
+            IgrArgs &A = s->igr_args;
+            A.blob = s->igr_op.blob.p;
+            A.off = s->igr_op.off.p;
+            A.n_rows = nl;
+            A.u = c->u.p;
+            A.du = c->du.p;
+            A.alpha = s->igr_alpha;
+            double *v = s->igr_vec.p;
+            A.rho_inv = v;
+            A.b = v + nl;
+            A.r = v + 2 * nl;
+            A.c = v + 3 * nl;
+            A.x = v + 4 * nl;
+            A.p = v + 4 * nl + np1;
+            A.t = v + 4 * nl + 2 * np1;
+            A.partial = s->igr_partial.p;
+            A.ticket = s->igr_ticket.p;
+            A.S = s->igr_scalars.p;
+        }
         if (s->kind == MFT_SRC_RESIDUAL) {
             c->nslots = s->polydeg + 1;
             c->hist.resize(c->nslots);
@@ -1906,9 +1964,32 @@ static int launch_norms(mft_ctx *c)
 static int launch_norms_multi(mft_ctx *c);
 static int p2p_norms_part(mft_ctx *c, int part);
 
+// SourceIGR functor call (IGR.jl:211-239): right-hand side + CG start, maxiter CG iterations of four launches each
+// (device-side control: converged iterations return at once), then the sigma-flux accumulation.  Fixed launch sequence.
+static int launch_igr(mft_ctx *c, Source *s)
+{
+    using namespace mft_igr;
+    if (c->nranks > 1) return fail(MFT_ENOTSUP, "the IGR source is single-GPU (its linear solve needs halo refreshes and global dot products per iteration)");
+    ScopedTimer tm(c, MFT_K_OTHER);
+    const IgrArgs &A = s->igr_args;
+    const int grid = grid_for(A.n_rows, kBlock);
+    k_igr_rhs<<<grid, kBlock, 0, c->stream>>>(A);
+    for (int it = 0; it < s->igr_maxiter; ++it) {
+        k_igr_dir<<<grid, kBlock, 0, c->stream>>>(A);
+        k_igr_grad<<<grid, kBlock, 0, c->stream>>>(A);
+        k_igr_apply<<<grid, kBlock, 0, c->stream>>>(A);
+        k_igr_update<<<grid, kBlock, 0, c->stream>>>(A);
+    }
+    k_igr_flux<<<grid, kBlock, 0, c->stream>>>(A);
+    c->launches += 2 + 4 * s->igr_maxiter;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}
+
 // one source functor call on the resident state
 static int apply_source_dev(mft_ctx *c, Source *s)
 {
+    if (s->kind == MFT_SRC_IGR) return launch_igr(c, s);
     if (s->kind == MFT_SRC_HV_FLYER || s->kind == MFT_SRC_HV_TOMINEC) return launch_spmv(c, s);
     const int visc = s->kind == MFT_SRC_UPWIND ? VISC_UPWIND : VISC_RESIDUAL;
     if (visc == VISC_RESIDUAL) CHECK(c->nranks > 1 ? launch_norms_multi(c) : launch_norms(c));
@@ -2438,15 +2519,16 @@ extern "C" int mft_get_field(mft_ctx *c, int field, double *out)
     if (!out) return fail(MFT_EINVAL, "mft_get_field: out is NULL");
     const int64_t n = c->n_tot;
     CU(cudaStreamSynchronize(c->stream));
-    auto scalar = [&](DevBuf<double> &b) -> int {
-        if (!b.p) return fail(MFT_EINVAL, "mft_get_field: field not available (enable MFT_OPT_DIAGNOSTICS before the first compute call)");
-        k_unpack_scalar<<<grid_for(n, 256), 256, 0, c->stream>>>(b.p, c->d_perm.p, c->stage_soa.p, n);
+    auto scalar_ptr = [&](const double *bp) -> int {
+        if (!bp) return fail(MFT_EINVAL, "mft_get_field: field not available (enable MFT_OPT_DIAGNOSTICS before the first compute call)");
+        k_unpack_scalar<<<grid_for(n, 256), 256, 0, c->stream>>>(bp, c->d_perm.p, c->stage_soa.p, n);
         c->launches++;
         LAUNCH_CHECK();
         CU(cudaMemcpyAsync(out, c->stage_soa.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         return MFT_OK;
     };
+    auto scalar = [&](DevBuf<double> &b) -> int { return scalar_ptr(b.p); };
     auto vecfield = [&](DevBuf<double> &b) -> int {
         if (!b.p) return fail(MFT_EINVAL, "mft_get_field: field not available");
         std::vector<double *> ptrs(c->V);
@@ -2462,6 +2544,22 @@ extern "C" int mft_get_field(mft_ctx *c, int field, double *out)
     case MFT_FIELD_EPS_C: return scalar(c->eps_c);
     case MFT_FIELD_RESIDUAL: return vecfield(c->residual);
     case MFT_FIELD_APPROX_DU: return vecfield(c->approx_du);
+    case MFT_FIELD_SIGMA:
+        for (auto *s : c->srcs)
+            if (s->kind == MFT_SRC_IGR) return scalar_ptr(s->igr_args.x);
+        return fail(MFT_EINVAL, "mft_get_field: no IGR source");
+    case MFT_FIELD_IGR_STATUS: {
+        for (auto *s : c->srcs)
+            if (s->kind == MFT_SRC_IGR) {
+                mft_igr::IgrScalars S;
+                CU(cudaMemcpy(&S, s->igr_scalars.p, sizeof S, cudaMemcpyDeviceToHost));
+                out[0] = (double)S.iter;
+                out[1] = S.res;
+                out[2] = S.res0;
+                return MFT_OK;
+            }
+        return fail(MFT_EINVAL, "mft_get_field: no IGR source");
+    }
     case MFT_FIELD_NORMS:
         CU(cudaMemcpy(out, c->stats.p + 2 * c->V, sizeof(double) * c->V, cudaMemcpyDeviceToHost));
         return MFT_OK;

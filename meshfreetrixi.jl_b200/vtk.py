@@ -175,6 +175,8 @@ def source_fields(source):
     """write2vtk! for SourceUpwindViscosityTominec / SourceResidualViscosityTominec (write2vtk.jl:328-345); the fields live
     on the device and are fetched with mft_get_field (needs the engine's diagnostics option)"""
     name = type(source).__name__
+    if name == "SourceIGR":          # write2vtk.jl:344-349
+        return {"sigma": source.cache.sigma}
     if name not in ("SourceUpwindViscosityTominec", "SourceResidualViscosityTominec"):
         return {}
     c = source.cache

@@ -40,6 +40,7 @@
 #define ORC_SRC_HV_TOMINEC 1
 #define ORC_SRC_UPWIND 2
 #define ORC_SRC_RESIDUAL 3
+#define ORC_SRC_IGR 4
 
 /* Julia SparseMatrixCSC{Float64,Int64}: colptr (n+1), rowval (nnz), both 1-based. */
 typedef struct {
@@ -72,6 +73,13 @@ typedef struct {
     int64_t *eps_c;                /* N */
     double *residual;              /* V x N SoA */
     double *approx_du;             /* V x N SoA */
+    /* SourceIGR (src/sources/IGR.jl) */
+    double igr_alpha;
+    int64_t igr_maxiter;
+    double *igr_sigma; /* N   : cache.sigma */
+    double *igr_work;  /* >= 9N : rho_inv, igr_rhs, then {flux_y (4N)} reused as {tmp1, tmp2, tmp3, r, p, c, products} */
+    int64_t igr_iters; /* out: CG iterations performed */
+    double igr_res;    /* out: final |r| */
 } orc_source;
 
 typedef struct {
@@ -353,6 +361,96 @@ static void apply_eps_dissipation(const orc_problem *P, const orc_source *S, con
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * SourceIGR, src/sources/IGR.jl (outside every @muladd scope: separate * and +).
+ * PARITY UNPINNED: no reference test exercises it, and its linear solver is third party.
+ * ---------------------------------------------------------------------------------------- */
+
+/* mul!(y, A::IGRCompositeMatrix, v)  IGR.jl:55-70 */
+static void igr_composite_mul(const orc_problem *P, const orc_source *S, const double *rho_inv, double *tmp1, double *tmp2,
+                              double *tmp3, const double *v, double *y)
+{
+    const int64_t n = P->n;
+    orc_spmv_csc(n, &P->D[0], v, tmp1);
+    orc_spmv_csc(n, &P->D[1], v, tmp2);
+    for (int64_t i = 0; i < n; ++i) tmp1[i] = rho_inv[i] * tmp1[i];
+    for (int64_t i = 0; i < n; ++i) tmp2[i] = rho_inv[i] * tmp2[i];
+    orc_spmv_csc(n, &P->D[0], tmp1, tmp3);
+    orc_spmv_csc(n, &P->D[1], tmp2, tmp1);
+    for (int64_t i = 0; i < n; ++i) y[i] = rho_inv[i] * v[i];
+    for (int64_t i = 0; i < n; ++i) y[i] = y[i] - S->igr_alpha * (tmp3[i] + tmp1[i]);
+}
+
+/* norm / dot are BLAS calls in the reference (summation order unspecified); pairwise here */
+static double igr_dot(const double *a, const double *b, double *scratch, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i) scratch[i] = a[i] * b[i];
+    return orc_sum(scratch, n);
+}
+
+/* IterativeSolvers.cg!(x, A, b; maxiter) (third party, unpinned): abstol = 0, reltol = sqrt(eps), no preconditioner,
+ * initially_zero = false.  x is zero on entry here (update_sigma! zeroes sigma first, IGR.jl:181). */
+static void igr_cg(const orc_problem *P, orc_source *S, const double *rho_inv, const double *b, double *x, double *w)
+{
+    const int64_t n = P->n;
+    double *tmp1 = w, *tmp2 = w + n, *tmp3 = w + 2 * n, *r = w + 3 * n, *p = w + 4 * n, *c = w + 5 * n, *scr = w + 6 * n;
+    for (int64_t i = 0; i < n; ++i) r[i] = b[i];
+    igr_composite_mul(P, S, rho_inv, tmp1, tmp2, tmp3, x, c);
+    for (int64_t i = 0; i < n; ++i) r[i] = r[i] - c[i];
+    for (int64_t i = 0; i < n; ++i) p[i] = 0.0;
+    double residual = sqrt(igr_dot(r, r, scr, n)), prev_residual = 1.0;
+    const double tol = fmax(1.4901161193847656e-08 * residual, 0.0);
+    int64_t it = 0;
+    while (!(residual <= tol) && it < S->igr_maxiter) {
+        const double beta = (residual * residual) / (prev_residual * prev_residual);
+        for (int64_t i = 0; i < n; ++i) p[i] = r[i] + beta * p[i];
+        igr_composite_mul(P, S, rho_inv, tmp1, tmp2, tmp3, p, c);
+        const double alpha = (residual * residual) / igr_dot(p, c, scr, n);
+        for (int64_t i = 0; i < n; ++i) x[i] = x[i] + alpha * p[i];
+        for (int64_t i = 0; i < n; ++i) r[i] = r[i] - alpha * c[i];
+        prev_residual = residual;
+        residual = sqrt(igr_dot(r, r, scr, n));
+        ++it;
+    }
+    S->igr_iters = it;
+    S->igr_res = residual;
+}
+
+static void igr_apply(const orc_problem *P, orc_source *S, const double *u, double *du)
+{
+    const int64_t n = P->n;
+    const double gamma = P->eqp[0];
+    double *rho_inv = S->igr_work, *rhs = S->igr_work + n, *w = S->igr_work + 2 * n;
+    double *u_prim = P->scratch_a, *flux_x = P->scratch_b; /* flux_y: w (4N needed -> use w..w+4N before the CG uses it) */
+    double *flux_y = w;
+    /* update_igr_rhs! :117-158 */
+    for (int64_t i = 0; i < n; ++i) {
+        double v1, v2, p;
+        euler_pressure_velocity(gamma, u[i], u[n + i], u[2 * n + i], u[3 * n + i], &v1, &v2, &p);
+        u_prim[i] = u[i];
+        u_prim[n + i] = v1;
+        u_prim[2 * n + i] = v2;
+        u_prim[3 * n + i] = p;
+    }
+    for (int v = 0; v < 4; ++v) orc_spmv_csc(n, &P->D[0], u_prim + v * n, flux_x + v * n);
+    for (int v = 0; v < 4; ++v) orc_spmv_csc(n, &P->D[1], u_prim + v * n, flux_y + v * n);
+    for (int64_t i = 0; i < n; ++i) {
+        double trace = 0.0;
+        trace = trace + flux_x[i];         /* flux_x[i][1] */
+        trace = trace + flux_y[n + i];     /* flux_y[i][2] */
+        const double fx2 = flux_x[n + i], fx3 = flux_x[2 * n + i], fy2 = flux_y[n + i], fy3 = flux_y[2 * n + i];
+        const double trace_squared = (fx2 * fx2 + (2.0 * fy2) * fx3) + fy3 * fy3;
+        rhs[i] = S->igr_alpha * (trace * trace + trace_squared);
+    }
+    /* update_sigma! :169-191 */
+    for (int64_t i = 0; i < n; ++i) S->igr_sigma[i] = 0.0;
+    for (int64_t i = 0; i < n; ++i) rho_inv[i] = 1.0 / u[i];
+    igr_cg(P, S, rho_inv, rhs, S->igr_sigma, w);
+    /* flux_igr + mul_by_accum!(D[i], -1) :225-238 (fields with a zero flux receive w * (0 * -1): no change) */
+    orc_spmv_csc_accum(n, &P->D[0], S->igr_sigma, -1.0, du + n);
+    orc_spmv_csc_accum(n, &P->D[1], S->igr_sigma, -1.0, du + 2 * n);
+}
+
 void orc_apply_source(const orc_problem *P, orc_source *S, const double *u, double *du)
 {
     const int64_t n = P->n;
@@ -375,6 +473,9 @@ void orc_apply_source(const orc_problem *P, orc_source *S, const double *u, doub
         orc_update_residual_visc(P, S, du, u, NULL);
         orc_update_visc(P, S);
         apply_eps_dissipation(P, S, u, du);
+        break;
+    case ORC_SRC_IGR: /* IGR.jl:211-239 */
+        igr_apply(P, S, u, du);
         break;
     }
 }

@@ -29,7 +29,7 @@ _LIB = None
 
 EQ_EULER2D, EQ_ADVECTION2D = 0, 1
 BC_DIRICHLET, BC_SLIP_WALL, BC_DO_NOTHING = 0, 1, 2
-SRC_HV_FLYER, SRC_HV_TOMINEC, SRC_UPWIND, SRC_RESIDUAL = 0, 1, 2, 3
+SRC_HV_FLYER, SRC_HV_TOMINEC, SRC_UPWIND, SRC_RESIDUAL, SRC_IGR = 0, 1, 2, 3, 4
 
 
 def build(force: bool = False) -> str:
@@ -264,7 +264,9 @@ class _SRC(C.Structure):
                 ("pad_", C.c_int32), ("hv", _CSC), ("gamma", C.c_double), ("c_rv", C.c_double),
                 ("c_uw", C.c_double), ("dx_avg", C.c_double), ("success_iter", C.c_int64),
                 ("eps_uw", C.c_void_p), ("eps_rv", C.c_void_p), ("eps", C.c_void_p), ("eps_c", C.c_void_p),
-                ("residual", C.c_void_p), ("approx_du", C.c_void_p)]
+                ("residual", C.c_void_p), ("approx_du", C.c_void_p),
+                ("igr_alpha", C.c_double), ("igr_maxiter", C.c_int64), ("igr_sigma", C.c_void_p), ("igr_work", C.c_void_p),
+                ("igr_iters", C.c_int64), ("igr_res", C.c_double)]
 
 
 class _PROBLEM(C.Structure):
@@ -316,6 +318,8 @@ class OracleSource:
     # caches (create_tominec_rv_cache, hyperviscosity.jl:202-244)
     arrays: dict = field(default_factory=dict)
     success_iter: int = 0
+    igr_alpha: float = 1.0
+    igr_maxiter: int = 20
 
 
 class OracleProblem:
@@ -340,6 +344,8 @@ class OracleProblem:
                                 approx_du=np.zeros((V, n)), time_history=np.zeros(s.polydeg + 1),
                                 time_weights=np.zeros(s.polydeg + 1),
                                 sol_history=np.zeros((V, s.polydeg + 1, n)))
+            if s.kind == SRC_IGR and not s.arrays:
+                s.arrays = dict(sigma=np.zeros(n), igr_work=np.zeros(12 * n))
         self._keep = []
 
     # -- struct assembly -------------------------------------------------------------------
@@ -368,7 +374,8 @@ class OracleProblem:
             srcs[i] = _SRC(s.kind, int(s.mean_divisor_vn), int(s.max_lexicographic), 0, hv, s.gamma, s.c_rv,
                            s.c_uw, s.dx_avg, s.success_iter, _ptr(a.get("eps_uw")), _ptr(a.get("eps_rv")),
                            _ptr(a.get("eps")), _ptr(a.get("eps_c")), _ptr(a.get("residual")),
-                           _ptr(a.get("approx_du")))
+                           _ptr(a.get("approx_du")), s.igr_alpha, s.igr_maxiter, _ptr(a.get("sigma")), _ptr(a.get("igr_work")),
+                           0, 0.0)
         P = _PROBLEM()
         P.n, P.nvars, P.eq = self.n, self.nvars, self.eq
         P.eqp[0], P.eqp[1] = self.eqp[0], self.eqp[1]
@@ -387,7 +394,15 @@ class OracleProblem:
         du = np.empty_like(u)
         P = self._cproblem(t)
         lib().orc_rhs(C.byref(P), C.c_void_p(_ptr(u)), C.c_void_p(_ptr(du)))
+        self._collect(P)
         return du
+
+    def _collect(self, P):
+        """scalar outputs the C side leaves in the source structs (IGR: CG iteration count, final residual)"""
+        srcs = C.cast(P.srcs, C.POINTER(_SRC))
+        for i, s in enumerate(self.sources):
+            if s.kind == SRC_IGR:
+                s.arrays["iters"], s.arrays["res"] = int(srcs[i].igr_iters), float(srcs[i].igr_res)
 
     def rhs_repeat(self, u, reps, t=0.0):
         du = np.empty_like(u)
@@ -405,6 +420,7 @@ class OracleProblem:
         P = self._cproblem(t)
         srcs = C.cast(P.srcs, C.POINTER(_SRC))
         lib().orc_apply_source(C.byref(P), C.byref(srcs[i]), C.c_void_p(_ptr(u)), C.c_void_p(_ptr(du)))
+        self._collect(P)
 
     def residual_norms(self, i, u, du, t=0.0):
         """n_inf_norms of update_residual_visc! (hyperviscosity.jl:305-311) for source i; also refreshes eps_rv."""
@@ -596,6 +612,11 @@ def source_hyperviscosity_tominec(points, neighbors, p, N, dx_min, c=1.0):
     lap = sp.csc_matrix(ops[0] + ops[1])
     H = sp.csc_matrix(lap.T @ lap)
     return OracleSource(kind=SRC_HV_TOMINEC, hv=JuliaCSC(H), gamma=c * dx_min ** 4.5)
+
+
+def source_igr(alpha=1.0, maxiter=20):
+    """SourceIGR(solver, equations, domain; alpha, linear_solver = cg!) IGR.jl:32-36; maxiter = 20 is hard-wired (:190)"""
+    return OracleSource(kind=SRC_IGR, igr_alpha=alpha, igr_maxiter=maxiter)
 
 
 def source_upwind(dx_avg, c_uw=1.0, polydeg=4):

@@ -67,3 +67,20 @@ def limiter_zhang_shu(u, neighbors, thresholds, variables, gamma):
     if rc != 0:
         raise EmuError("emu_limiter_zhang_shu failed")
     return u
+
+
+def igr_apply(neighbors, wx, wy, alpha, maxiter, u, du):
+    """emulated launch_igr(): neighbors/wx/wy (n,k) with each row already in ascending-column order; u, du (4,n);
+    du is updated in place.  Returns (sigma, (iterations, |r|, |r0|))"""
+    nb = np.ascontiguousarray(neighbors, dtype=np.int64)
+    n, k = nb.shape
+    wx = np.ascontiguousarray(wx, dtype=np.float64)
+    wy = np.ascontiguousarray(wy, dtype=np.float64)
+    assert u.flags.c_contiguous and du.flags.c_contiguous and u.dtype == np.float64 and du.dtype == np.float64
+    sigma = np.empty(n)
+    st = np.empty(3)
+    rc = lib().emu_igr_apply(C.c_int64(n), C.c_int(k), _p(nb), _p(wx), _p(wy), C.c_double(alpha), C.c_int(maxiter), _p(u), _p(du),
+                             _p(sigma), _p(st))
+    if rc != 0:
+        raise EmuError("emu_igr_apply failed")
+    return sigma, (int(st[0]), float(st[1]), float(st[2]))
