@@ -140,7 +140,7 @@ def run_ours(args):
                                                                 single_sweep_exact=bool(args.single_sweep),
                                                                 exchange=args.exchange, pair_rows=int(args.pair_rows),
                                                                 tile=int(args.tile), tile_rows=int(args.tile_rows),
-                                                                prefetch_distance=args.pf_dist))
+                                                                prefetch_distance=args.pf_dist, setup=args.setup))
     names = dict(left=1, right=2, bottom=3, top=4)
     t_setup = time.time()
     domain = m.ParallelPointCloudDomain(solver, cl, names, comm) if multi else m.PointCloudDomain(solver, cl, names)
@@ -273,7 +273,7 @@ def run_ours(args):
                           "summation": "fma single-sweep" if args.fma else "reference order (bit-exact sums)",
                           "partition": "single GPU" if not multi else f"Hilbert-curve ranges over {world} ranks, halo exchange (u, g) + global norms per stage via {'NVLink peer-memory puts (CUDA IPC), graph-replayed' if args.exchange == 'p2p' else 'NCCL send/recv + all-gather'}",
                           "l2": "inputs larger than L2 (operators 2 x %.0f MB per GPU streamed every stage)" % (n_own * 20 * k / 1e6),
-                          "setup_s": round(t_setup, 1)},
+                          "setup_s": round(t_setup, 1), "setup": args.setup},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(out))
     semi.close()
@@ -416,6 +416,8 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=11, help="rows per thread of the tile kernels: units digit pass A, tens digit pass B")
     ap.add_argument("--pair-rows", type=int, default=1, help="row-pair (union stencil) operator layout (bit0: pass B, bit1: pass A)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo exchange mechanism")
+    ap.add_argument("--setup", default="host", choices=["host", "device"],
+                    help="kNN + RBF-FD weight generation (untimed setup): host numpy/LAPACK, or the GPU pipeline (mft_setup_*)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--cloud-order", default="hilbert", choices=["hilbert", "lattice"],
