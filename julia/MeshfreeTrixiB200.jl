@@ -5,7 +5,8 @@
 # ctypes by meshfreetrixi.jl_b200/api.py and the test-suite.  References are file:line in the MeshfreeTrixi.jl repository.
 
 using MeshfreeTrixi
-using MeshfreeTrixi: RBFSolver, RBFFDEngineCUDA, PointCloudDomain, compute_flux_operator,
+using MeshfreeTrixi: RBFSolver, RBFFDEngineCUDA, PointCloudDomain, PointData, RefPointData, SourceIGR, compute_flux_operator,
+                     PositivityPreservingLimiterZhangShu,
                      SourceResidualViscosityTominec, SourceUpwindViscosityTominec,
                      SourceHyperviscosityTominec, SourceHyperviscosityFlyer,
                      BoundaryConditionDoNothing, boundary_condition_slip_wall, time_deriv_weights!
@@ -120,6 +121,8 @@ function register!(cache, domain, equations, boundary_conditions, source_terms)
                 add_source!(ctx, 1, Float64[c.gamma], c.hv_differentiation_matrix)
             elseif source isa SourceHyperviscosityFlyer
                 add_source!(ctx, 0, Float64[c.gamma], c.hv_differentiation_matrix)
+            elseif source isa MeshfreeTrixi.SourceIGR                           # IGR.jl: maxiter = 20 is hard-wired (:190)
+                add_source!(ctx, 4, Float64[c.alpha, 20.0])
             else
                 error("source $(typeof(source)) has no CUDA implementation")
             end
@@ -213,4 +216,76 @@ function set_halo!(ctx::MftContext, mpi_cache)   # fields of MPICache: send ids 
     recv = Int64.(mpi_cache.halo_recv_length)
     mft_check(ccall((:mft_set_halo, libmft), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
                     ctx.ptr, length(peers), peers, send_off, send_idx, recv))
+end
+
+
+# ---- setup on the device (SURVEY.md section 8 row f1) ------------------------------------------------------------------------
+# PointData constructor with the neighbour search on the GPU (CPU: geometry_primatives.jl:322-339)
+function MeshfreeTrixi.PointData(medusa_data::Vector{SVector{2, Float64}}, basis::RefPointData, ::RBFFDEngineCUDA; device = 0)
+    n, nv = length(medusa_data), basis.nv
+    x = [p[1] for p in medusa_data]
+    y = [p[2] for p in medusa_data]
+    nbr = Matrix{Int64}(undef, nv, n)      # column-major nv x n is the library's n x nv row-major
+    dist = Matrix{Float64}(undef, nv, n)
+    mft_check(ccall((:mft_setup_knn, libmft), Cint,
+                    (Cint, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Int64}, Ptr{Float64}),
+                    device, n, x, y, nv, nbr, dist))
+    return PointData{2, SVector{2, Float64}, Int}(medusa_data, [nbr[:, i] for i in 1:n], n, nv,
+                                                   minimum(@view dist[2, :]), sum(@view dist[2, :]) / n)
+end
+
+phs_power(basis::RefPointData) = basis.approximation_type.Nrbf   # RBF{PolyharmonicSpline}.Nrbf: r^Nrbf (geometry_primatives.jl:97-114)
+
+# compute_flux_operator with the per-point solves on the GPU (CPU: compute_operators.jl:409-453, k-th derivative :549-594)
+function MeshfreeTrixi.compute_flux_operator(solver::RBFSolver{<:Any, RBFFDEngineCUDA}, domain::PointCloudDomain{2},
+                                             k::Int = 1; device = 0)
+    pd = domain.pd
+    n, nv = pd.num_points, pd.num_neighbors
+    x = [p[1] for p in pd.points]
+    y = [p[2] for p in pd.points]
+    nbr = reduce(hcat, pd.neighbors)
+    wx = Matrix{Float64}(undef, nv, n)
+    wy = similar(wx)
+    mft_check(ccall((:mft_setup_rbf_weights, libmft), Cint,
+                    (Cint, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Int64}, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}),
+                    device, n, x, y, nv, nbr, phs_power(solver.basis), solver.basis.N, k, wx, wy))
+    rows = repeat(1:n, inner = nv)
+    return [sparse(rows, vec(nbr), vec(wx), n, n), sparse(rows, vec(nbr), vec(wy), n, n)]
+end
+
+# ---- Zhang-Shu positivity limiter (positivity_zhang_shu.jl:29-72, positivity_zhang_shu_point2d.jl:22-82) ------------------------
+limiter_variable_code(::typeof(Trixi.density)) = Cint(0)    # MFT_VAR_DENSITY
+limiter_variable_code(::typeof(Trixi.pressure)) = Cint(1)   # MFT_VAR_PRESSURE
+
+function set_neighbors!(ctx::MftContext, pd::PointData)
+    nbr = reduce(hcat, pd.neighbors)       # nv x n column-major == n x nv row-major, 1-based
+    mft_check(ccall((:mft_set_neighbors, libmft), Cint, (Ptr{Cvoid}, Ptr{Int64}), ctx.ptr, nbr))
+end
+
+# limiter!(u_ode, integrator, semi, t) on host arrays (one pass per (threshold, variable) pair, in order)
+function limiter_zhang_shu_device!(u, limiter::PositivityPreservingLimiterZhangShu, ctx::MftContext)
+    thr = collect(Float64, limiter.thresholds)
+    var = Cint[limiter_variable_code(v) for v in limiter.variables]
+    up = collect(Ptr{Float64}, pointer.(StructArrays.components(u)))
+    GC.@preserve u begin
+        mft_check(ccall((:mft_limiter_zhang_shu, libmft), Cint,
+                        (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Cint}, Ptr{Ptr{Float64}}, Cint),
+                        ctx.ptr, length(thr), thr, var, up, 0 #= MFT_MEM_HOST =#))
+    end
+end
+
+# SSPRK33(stage_limiter!) for the device-resident loop
+function set_stage_limiter!(ctx::MftContext, limiter::PositivityPreservingLimiterZhangShu)
+    thr = collect(Float64, limiter.thresholds)
+    var = Cint[limiter_variable_code(v) for v in limiter.variables]
+    mft_check(ccall((:mft_set_stage_limiter, libmft), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Cint}),
+                    ctx.ptr, length(thr), thr, var))
+end
+
+# ---- SourceIGR (IGR.jl): registered like the other sources; sigma comes back through mft_get_field -----------------------------
+register_igr!(ctx::MftContext, source::SourceIGR; maxiter = 20) = add_source!(ctx, 4 #= MFT_SRC_IGR =#, [source.cache.alpha, Float64(maxiter)])
+
+function fetch_sigma!(source::SourceIGR, ctx::MftContext)
+    mft_check(ccall((:mft_get_field, libmft), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), ctx.ptr, 7 #= MFT_FIELD_SIGMA =#, source.cache.sigma))
+    return source.cache.sigma
 end

@@ -51,6 +51,8 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "mft_oracle" not in src and "oracle/" not in src, f
+                # nor the tests' host-emulation harness (comments may name the directory; nothing may load or include it)
+                assert "libmft_emu" not in src and "import emu" not in src and "emu_" not in src, f
 
 
 import pytest
