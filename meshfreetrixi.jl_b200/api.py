@@ -371,9 +371,7 @@ class SemidiscretizationHyperbolic:
             L.check(lib.mft_set_permutation(ctx, L.ptr(perm1)))
         else:
             self.perm = None
-        if part is None and self.V == 4:   # domain.pd.neighbors for the Zhang-Shu stage limiter (list order = kNN order)
-            nbr1 = np.ascontiguousarray(pd.neighbors + 1, dtype=np.int64)
-            L.check(lib.mft_set_neighbors(ctx, L.ptr(nbr1)))
+        self._neighbors_set = False        # domain.pd.neighbors go to the device when a Zhang-Shu limiter first needs them
         for slot, A in ((L.OP_DX, ops[0]), (L.OP_DY, ops[1])):
             cp, rv, nz = setup_ops.julia_csc(A)
             L.check(lib.mft_set_operator_csc(ctx, slot, L.ptr(cp), L.ptr(rv), L.ptr(nz)))
@@ -536,14 +534,27 @@ class PositivityPreservingLimiterZhangShu:
     def _arrays(self):
         return (np.asarray(self.thresholds, dtype=np.float64), np.asarray(self.kinds, dtype=np.int32))
 
+    @staticmethod
+    def _neighbors(semi):
+        """hand domain.pd.neighbors (list order = kNN order) to the library once per semidiscretization"""
+        if semi._neighbors_set:
+            return
+        if semi.partition is not None:
+            raise NotImplementedError("the Zhang-Shu limiter is single-GPU (as in the reference: PointCloudDomain{2} only)")
+        nbr1 = np.ascontiguousarray(semi.domain.pd.neighbors + 1, dtype=np.int64)
+        L.check(L.load().mft_set_neighbors(semi.ctx, L.ptr(nbr1)))
+        semi._neighbors_set = True
+
     def __call__(self, u, semi, t=None):
         """limiter!(u_ode, integrator, semi, t) on a host array (in place)"""
         thr, kinds = self._arrays()
+        self._neighbors(semi)
         L.check(L.load().mft_limiter_zhang_shu(semi.ctx, len(kinds), L.ptr(thr), L.ptr(kinds), L.soa_ptrs(u), L.MEM_HOST))
         return u
 
     def install(self, semi):
         thr, kinds = self._arrays()
+        self._neighbors(semi)
         L.check(L.load().mft_set_stage_limiter(semi.ctx, len(kinds), L.ptr(thr), L.ptr(kinds)))
 
 
