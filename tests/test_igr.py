@@ -66,7 +66,7 @@ def test_oracle_igr_matches_numpy_restatement(alpha_scale, maxiter):
 def test_oracle_igr_inside_rhs():
     """calc_sources! order (rbfsolver.jl:388-395): flux divergence, then IGR on the same u"""
     fx, ops = _setup()
-    alpha = 5.0 * fx["dx_avg"] ** 2
+    alpha = 0.01 * fx["dx_avg"] ** 2
     src = orc.source_igr(alpha=alpha)
     ic = cases.ic_smooth_euler
     P = orc.OracleProblem(fx["points"], 4, orc.EQ_EULER2D, [cases.GAMMA], ops[0], ops[1],

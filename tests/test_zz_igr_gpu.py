@@ -54,9 +54,10 @@ def test_igr_source_functor_matches_oracle(alpha_scale, maxiter, reorder):
 
 
 def test_igr_inside_rhs_and_time_loop():
-    """rhs! with SourceIGR (1e-9 against the oracle) and a few graph-replayed SSPRK33 steps (1e-8)"""
+    """rhs! with SourceIGR (1e-9 against the oracle) and a few graph-replayed SSPRK33 steps (1e-8).  alpha = 0.01 dx^2: on
+    the boundary-imposed state larger alpha makes the reference's CG diverge (see tests/golden/make_golden_f.py)"""
     fx0 = cases.fixture_setup(p=3, N=3)
-    alpha = 5.0 * fx0["dx_avg"] ** 2
+    alpha = 0.01 * fx0["dx_avg"] ** 2
     m, fx, ops, semi, bcs, ic = _problem(alpha)
     ode = m.semidiscretize(semi, (0.0, 1.0))
     u = ode.u0.copy()
@@ -78,7 +79,7 @@ def test_igr_inside_rhs_and_time_loop():
 def test_igr_after_upwind_viscosity_and_vtk_field(tmp_path):
     """two sources in NamedTuple order (upwind viscosity fused into the flux sweep, then IGR); sigma reaches the VTK file"""
     fx0 = cases.fixture_setup(p=3, N=3)
-    alpha = 5.0 * fx0["dx_avg"] ** 2
+    alpha = 0.01 * fx0["dx_avg"] ** 2
     import mft_b200 as m0
 
     basis = m0.PointCloudBasis(m0.Point2D(), 3, approximation_type=m0.RBF(m0.PolyharmonicSpline(3)), nv=fx0["nv"])
