@@ -214,6 +214,10 @@ int mft_sfc_order(int64_t n, const double *x, const double *y, int64_t *perm1_ou
  * distance, the point itself first, exact distance ties by ascending index; dist_out (nullable) = the n x k distances
  * (dx_min = minimum, dx_avg = mean of column 2, as the reference forms them from its 2-NN query). */
 int mft_setup_knn(int device, int64_t n, const double *x, const double *y, int k, int64_t *nbr1_out, double *dist_out);
+/* the same search for the nq listed points only (query_idx1: 1-based indices into x, y; outputs nq x k): what one rank of a
+ * partitioned cloud needs for its owned + halo rows (replaces the per-rank knn calls of partition_domain.jl:277-318) */
+int mft_setup_knn_queries(int device, int64_t n, const double *x, const double *y, int k, int64_t nq, const int64_t *query_idx1,
+                          int64_t *nbr1_out, double *dist_out);
 /* mft_setup_rbf_weights replaces the per-point loop of compute_flux_operator
  * (src/solvers/pointcloudsolver/compute_operators.jl:409-453; deriv_order > 1: :549-594) for the polyharmonic spline
  * basis r^phs_power + monomials up to poly_degree: wx_out / wy_out = n x k row-major weights of d^m/dx^m and d^m/dy^m
@@ -221,6 +225,9 @@ int mft_setup_knn(int device, int64_t n, const double *x, const double *y, int k
  * assemble sparse(I, J, V) on the caller's side. */
 int mft_setup_rbf_weights(int device, int64_t n, const double *x, const double *y, int k, const int64_t *nbr1, int phs_power,
                           int poly_degree, int deriv_order, double *wx_out, double *wy_out);
+/* the same for n_rows stencils given as rows of nbr1 (n_rows x k, indices into the n points): a rank's owned + halo rows */
+int mft_setup_rbf_weights_rows(int device, int64_t n, const double *x, const double *y, int64_t n_rows, int k, const int64_t *nbr1,
+                               int phs_power, int poly_degree, int deriv_order, double *wx_out, double *wy_out);
 
 /* ---- Zhang-Shu positivity limiter (stage callback) ------------------------------------------------------
  * replaces Trixi.limiter_zhang_shu!(u, threshold, variable, domain::PointCloudDomain{2}, ...)

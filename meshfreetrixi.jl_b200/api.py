@@ -127,8 +127,14 @@ class ParallelPointCloudDomain(PointCloudDomain):
 
         cl = cloudmod.read_medusa_file(source) if isinstance(source, str) else source
         basis = solver.basis
-        part = partition.build_rank_partition(cl.points, cl.boundary_idxs, cl.boundary_normals, comm.rank, comm.nranks,
-                                              basis.approx_type.rbf_type.Nrbf, basis.N, basis.nv, comm.allgather)
+        eng = solver.engine
+        on_device = getattr(eng, "setup", "host") == "device"
+        part = partition.build_rank_partition(
+            cl.points, cl.boundary_idxs, cl.boundary_normals, comm.rank, comm.nranks, basis.approx_type.rbf_type.Nrbf,
+            basis.N, basis.nv, comm.allgather,
+            knn_queries=(lambda pts, q, nv: setup_ops.knn_queries_device(pts, q, nv, eng.device)) if on_device else None,
+            weights_rows=(lambda pts, rows, p, N: setup_ops.rbf_fd_weights_rows_device(pts, rows, p, N, None, eng.device))
+            if on_device else None)
         self.partition, self.comm, self.cloud = part, comm, cl
         self.pd = PointData(part.points, part.neighbors_owned, part.n_local + part.n_halo, basis.nv, part.dx_min, part.dx_avg)
         self.boundary_tags = {name: BoundaryData(part.boundary_idxs[g - 1], part.boundary_normals[g - 1])

@@ -29,7 +29,7 @@ struct CudaSetupBackend {
     }
     int launch_knn(const mft_setup::KnnArgs &A)
     {
-        mft_setup::k_setup_knn<<<grid_for(A.n, 128), 128>>>(A);
+        mft_setup::k_setup_knn<<<grid_for(A.nq, 128), 128>>>(A);
         const cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? 0 : bad(e, "k_setup_knn launch");
     }
@@ -74,7 +74,20 @@ extern "C" int mft_setup_knn(int device, int64_t n, const double *x, const doubl
     CHECK(setup_select_device("mft_setup_knn", device));
     CudaSetupBackend be;
     std::string err;
-    const int rc = mft_setup::run_knn(be, n, x, y, k, nbr1_out, dist_out, err);
+    const int rc = mft_setup::run_knn(be, n, x, y, k, n, nullptr, nbr1_out, dist_out, err);
+    if (rc) return fail(rc == -1 ? MFT_EINVAL : MFT_ECUDA, "%s", err.c_str());
+    return MFT_OK;
+}
+
+extern "C" int mft_setup_knn_queries(int device, int64_t n, const double *x, const double *y, int k, int64_t nq, const int64_t *query_idx1,
+                                     int64_t *nbr1_out, double *dist_out)
+{
+    CHECK(setup_select_device("mft_setup_knn_queries", device));
+    if (!query_idx1 && nq != 0) return fail(MFT_EINVAL, "mft_setup_knn_queries: query_idx1 is NULL");
+    if (nq == 0) return MFT_OK;
+    CudaSetupBackend be;
+    std::string err;
+    const int rc = mft_setup::run_knn(be, n, x, y, k, nq, query_idx1, nbr1_out, dist_out, err);
     if (rc) return fail(rc == -1 ? MFT_EINVAL : MFT_ECUDA, "%s", err.c_str());
     return MFT_OK;
 }
@@ -85,7 +98,18 @@ extern "C" int mft_setup_rbf_weights(int device, int64_t n, const double *x, con
     CHECK(setup_select_device("mft_setup_rbf_weights", device));
     CudaSetupBackend be;
     std::string err;
-    const int rc = mft_setup::run_weights(be, n, x, y, k, nbr1, phs_power, poly_degree, deriv_order, wx_out, wy_out, err);
+    const int rc = mft_setup::run_weights(be, n, x, y, n, k, nbr1, phs_power, poly_degree, deriv_order, wx_out, wy_out, err);
+    if (rc) return fail(rc == -1 ? MFT_EINVAL : MFT_ECUDA, "%s", err.c_str());
+    return MFT_OK;
+}
+
+extern "C" int mft_setup_rbf_weights_rows(int device, int64_t n, const double *x, const double *y, int64_t n_rows, int k, const int64_t *nbr1,
+                                          int phs_power, int poly_degree, int deriv_order, double *wx_out, double *wy_out)
+{
+    CHECK(setup_select_device("mft_setup_rbf_weights_rows", device));
+    CudaSetupBackend be;
+    std::string err;
+    const int rc = mft_setup::run_weights(be, n, x, y, n_rows, k, nbr1, phs_power, poly_degree, deriv_order, wx_out, wy_out, err);
     if (rc) return fail(rc == -1 ? MFT_EINVAL : MFT_ECUDA, "%s", err.c_str());
     return MFT_OK;
 }

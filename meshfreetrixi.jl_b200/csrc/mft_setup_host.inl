@@ -117,12 +117,17 @@ inline int build_cell_grid(int64_t n, const double *x, const double *y, CellGrid
 }
 
 // PointData(medusa_data, basis) neighbour search (geometry_primatives.jl:322-339).
-// x, y: n coordinates; nbr1_out: n x k row-major, 1-based, self first; dist_out (nullable): n x k distances
-// (column 2 holds what the reference reduces to dx_min / dx_avg).
+// x, y: n coordinates; nbr1_out: nq x k row-major, 1-based, self first; dist_out (nullable): nq x k distances
+// (column 2 holds what the reference reduces to dx_min / dx_avg).  query_idx1 == NULL: every point queries (nq = n, row i =
+// point i); else the nq listed points (1-based) query against all n points -- what a rank of a partitioned cloud needs.
 template <class BE>
-int run_knn(BE &be, int64_t n, const double *x, const double *y, int k, int64_t *nbr1_out, double *dist_out, std::string &err)
+int run_knn(BE &be, int64_t n, const double *x, const double *y, int k, int64_t nq, const int64_t *query_idx1, int64_t *nbr1_out,
+            double *dist_out, std::string &err)
 {
     if (n < 1 || !x || !y || !nbr1_out) return setup_fail(err, "setup_knn: bad arguments (n = %lld)", (long long)n);
+    if (!query_idx1) nq = n;
+    if (nq < 0) return setup_fail(err, "setup_knn: negative query count %lld", (long long)nq);
+    if (nq == 0) return 0;
     if (k < 1 || k > kMaxK) return setup_fail(err, "setup_knn: k = %lld outside 1..%lld", k, kMaxK);
     if (k > n) return setup_fail(err, "setup_knn: k = %lld exceeds the number of points %lld", k, (long long)n);
     if (n > 2000000000LL) return setup_fail(err, "setup_knn: more than 2^31 points per device are not supported");
@@ -133,12 +138,35 @@ int run_knn(BE &be, int64_t n, const double *x, const double *y, int k, int64_t 
         sx[(size_t)q] = x[G.order[(size_t)q]];
         sy[(size_t)q] = y[G.order[(size_t)q]];
     }
-    DevMem<BE> d_sx(be), d_sy(be), d_sid(be), d_cell(be), d_start(be), d_nbr(be), d_dist(be);
+    // queries: threads in cell order of their points (neighbouring threads walk the same cells)
+    std::vector<int> qpos, qrow;
+    if (query_idx1) {
+        std::vector<int> pos_of((size_t)n);
+        for (int64_t q = 0; q < n; ++q) pos_of[(size_t)G.order[(size_t)q]] = (int)q;
+        std::vector<std::pair<int, int>> byp((size_t)nq);
+        for (int64_t s = 0; s < nq; ++s) {
+            const int64_t id = query_idx1[s] - 1;
+            if (id < 0 || id >= n) return setup_fail(err, "setup_knn: query index %lld out of range 1..%lld", (long long)query_idx1[s], (long long)n);
+            byp[(size_t)s] = std::make_pair(pos_of[(size_t)id], (int)s);
+        }
+        std::sort(byp.begin(), byp.end());
+        qpos.resize((size_t)nq);
+        qrow.resize((size_t)nq);
+        for (int64_t t = 0; t < nq; ++t) {
+            qpos[(size_t)t] = byp[(size_t)t].first;
+            qrow[(size_t)t] = byp[(size_t)t].second;
+        }
+    }
+    DevMem<BE> d_sx(be), d_sy(be), d_sid(be), d_cell(be), d_start(be), d_nbr(be), d_dist(be), d_qpos(be), d_qrow(be);
     bool ok = !d_sx.upload(sx) && !d_sy.upload(sy) && !d_sid.upload(G.order) && !d_cell.upload(G.cell_of) && !d_start.upload(G.cell_start) &&
-              !d_nbr.alloc(sizeof(int) * (size_t)n * k) && !d_dist.alloc(sizeof(double) * (size_t)n * k);
+              !d_nbr.alloc(sizeof(int) * (size_t)nq * k) && !d_dist.alloc(sizeof(double) * (size_t)nq * k);
+    if (ok && query_idx1) ok = !d_qpos.upload(qpos) && !d_qrow.upload(qrow);
     if (!ok) return setup_msg(err, be.error());
     KnnArgs A;
     A.n = n;
+    A.nq = nq;
+    A.qpos = query_idx1 ? d_qpos.template as<int>() : nullptr;
+    A.qrow = query_idx1 ? d_qrow.template as<int>() : nullptr;
     A.k = k;
     A.gx = G.gx;
     A.gy = G.gy;
@@ -153,28 +181,31 @@ int run_knn(BE &be, int64_t n, const double *x, const double *y, int k, int64_t 
     A.nbr = d_nbr.template as<int>();
     A.dist = d_dist.template as<double>();
     if (be.launch_knn(A) || be.sync()) return setup_msg(err, be.error());
-    std::vector<int> nbr((size_t)n * k);
+    std::vector<int> nbr((size_t)nq * k);
     if (be.d2h(nbr.data(), d_nbr.p, sizeof(int) * nbr.size())) return setup_msg(err, be.error());
     for (size_t i = 0; i < nbr.size(); ++i) nbr1_out[i] = (int64_t)nbr[i] + 1;
-    if (dist_out && be.d2h(dist_out, d_dist.p, sizeof(double) * (size_t)n * k)) return setup_msg(err, be.error());
+    if (dist_out && be.d2h(dist_out, d_dist.p, sizeof(double) * (size_t)nq * k)) return setup_msg(err, be.error());
     return 0;
 }
 
 // compute_flux_operator (compute_operators.jl:409-453; k-th derivative :549-594) for a polyharmonic-spline basis r^p
 // with monomials up to `degree`: per point the k stencil weights of d^kk/dx^kk and d^kk/dy^kk.
-// nbr1: n x k row-major, 1-based, self first (domain.pd.neighbors); wx_out, wy_out: n x k row-major, aligned with nbr1.
+// nbr1: n_rows x k row-major, 1-based, self first (domain.pd.neighbors); wx_out, wy_out: n_rows x k row-major, aligned with
+// nbr1.  n_rows = n for a whole cloud; a rank of a partitioned cloud passes its own rows only (indices stay global).
 template <class BE>
-int run_weights(BE &be, int64_t n, const double *x, const double *y, int k, const int64_t *nbr1, int p, int degree, int kk, double *wx_out,
-                double *wy_out, std::string &err)
+int run_weights(BE &be, int64_t n, const double *x, const double *y, int64_t n_rows, int k, const int64_t *nbr1, int p, int degree, int kk,
+                double *wx_out, double *wy_out, std::string &err)
 {
     if (n < 1 || !x || !y || !nbr1 || !wx_out || !wy_out) return setup_fail(err, "setup_rbf_weights: bad arguments (n = %lld)", (long long)n);
+    if (n_rows < 0) return setup_fail(err, "setup_rbf_weights: negative row count %lld", (long long)n_rows);
+    if (n_rows == 0) return 0;
     if (k < 1 || k > kMaxK) return setup_fail(err, "setup_rbf_weights: k = %lld outside 1..%lld", k, kMaxK);
     if (degree < 0 || degree > 6) return setup_fail(err, "setup_rbf_weights: polynomial degree %lld outside 0..6", degree);
     if (kk < 1 || kk > 4) return setup_fail(err, "setup_rbf_weights: derivative order %lld outside 1..4", kk);
     if (p < 1 || (p % 2) == 0) return setup_fail(err, "setup_rbf_weights: polyharmonic spline power %lld must be odd and positive", p);
     const int npoly = (degree + 1) * (degree + 2) / 2;
     if (npoly > k) return setup_fail(err, "setup_rbf_weights: %lld monomials need a stencil of at least that many points (k = %lld)", npoly, k);
-    std::vector<int> nbr((size_t)n * k);
+    std::vector<int> nbr((size_t)n_rows * k);
     for (size_t i = 0; i < nbr.size(); ++i) {
         const int64_t j = nbr1[i] - 1;
         if (j < 0 || j >= n) return setup_fail(err, "setup_rbf_weights: neighbour index %lld out of range 1..%lld", (long long)nbr1[i], (long long)n);
@@ -184,11 +215,12 @@ int run_weights(BE &be, int64_t n, const double *x, const double *y, int k, cons
     const size_t per_thread = sizeof(double) * ((size_t)m * m + 2 * (size_t)m);
     int64_t chunk = (int64_t)(be.scratch_budget() / per_thread);
     chunk = std::max<int64_t>(256, chunk / 256 * 256);
-    chunk = std::min<int64_t>(chunk, (n + 255) / 256 * 256);
+    chunk = std::min<int64_t>(chunk, (n_rows + 255) / 256 * 256);
     DevMem<BE> d_x(be), d_y(be), d_nbr(be), d_scr(be), d_wx(be), d_wy(be), d_st(be);
     std::vector<double> hx(x, x + n), hy(y, y + n);
     bool ok = !d_x.upload(hx) && !d_y.upload(hy) && !d_nbr.upload(nbr) && !d_scr.alloc(per_thread * (size_t)chunk) &&
-              !d_wx.alloc(sizeof(double) * (size_t)n * k) && !d_wy.alloc(sizeof(double) * (size_t)n * k) && !d_st.alloc(sizeof(int) * (size_t)n);
+              !d_wx.alloc(sizeof(double) * (size_t)n_rows * k) && !d_wy.alloc(sizeof(double) * (size_t)n_rows * k) &&
+              !d_st.alloc(sizeof(int) * (size_t)n_rows);
     if (!ok) return setup_msg(err, be.error());
     WeightArgs A;
     A.k = k;
@@ -204,18 +236,18 @@ int run_weights(BE &be, int64_t n, const double *x, const double *y, int k, cons
     A.wx = d_wx.template as<double>();
     A.wy = d_wy.template as<double>();
     A.status = d_st.template as<int>();
-    for (int64_t e0 = 0; e0 < n; e0 += chunk) {
+    for (int64_t e0 = 0; e0 < n_rows; e0 += chunk) {
         A.e0 = e0;
-        A.nthreads = std::min<int64_t>(chunk, n - e0);
+        A.nthreads = std::min<int64_t>(chunk, n_rows - e0);
         if (be.launch_weights(A)) return setup_msg(err, be.error());  // same stream: launches serialise on the scratch
     }
     if (be.sync()) return setup_msg(err, be.error());
-    std::vector<int> status((size_t)n);
-    if (be.d2h(status.data(), d_st.p, sizeof(int) * (size_t)n) || be.d2h(wx_out, d_wx.p, sizeof(double) * (size_t)n * k) ||
-        be.d2h(wy_out, d_wy.p, sizeof(double) * (size_t)n * k))
+    std::vector<int> status((size_t)n_rows);
+    if (be.d2h(status.data(), d_st.p, sizeof(int) * (size_t)n_rows) || be.d2h(wx_out, d_wx.p, sizeof(double) * (size_t)n_rows * k) ||
+        be.d2h(wy_out, d_wy.p, sizeof(double) * (size_t)n_rows * k))
         return setup_msg(err, be.error());
-    for (int64_t i = 0; i < n; ++i)
-        if (status[(size_t)i]) return setup_fail(err, "setup_rbf_weights: singular local system at point %lld (degenerate stencil)", (long long)i + 1);
+    for (int64_t i = 0; i < n_rows; ++i)
+        if (status[(size_t)i]) return setup_fail(err, "setup_rbf_weights: singular local system in row %lld (degenerate stencil)", (long long)i + 1);
     return 0;
 }
 

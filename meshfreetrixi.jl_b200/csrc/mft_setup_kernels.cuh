@@ -37,7 +37,10 @@ constexpr double kEps = 2.220446049250313e-16;  // Base.eps()
 // The host sorts the points by cell (stable counting sort: ascending point index inside a cell) and uploads the sorted
 // coordinates.  Thread q serves the q-th point in cell order, so the threads of a warp walk the same few cells.
 struct KnnArgs {
-    int64_t n;
+    int64_t n;        // indexed points
+    int64_t nq;       // queries (= threads): n when every point queries itself
+    const int *qpos;  // nullable: cell-order position of the t-th query's point (queries = a subset of the points, sorted
+    const int *qrow;  //           by cell-order position); qrow[t] = output row of the t-th query
     int k;
     int gx, gy;             // cells per axis
     double x0, y0, h;       // lower-left corner of the grid, cell edge
@@ -45,8 +48,8 @@ struct KnnArgs {
     const int *sid;         // caller index (0-based) of the q-th point in cell order
     const int *scell;       // cell (cy*gx + cx) of the q-th point in cell order
     const int *cell_start;  // gx*gy + 1 offsets into the cell order
-    int *nbr;               // out: n x k row-major, row = CALLER index, entries = caller indices (0-based)
-    double *dist;           // out: n x k row-major distances
+    int *nbr;               // out: nq x k row-major (all points: row = CALLER index), entries = caller indices (0-based)
+    double *dist;           // out: nq x k row-major distances
 };
 
 struct KnnBest {
@@ -75,8 +78,9 @@ MFT_HD void knn_scan(const KnnArgs &A, KnnBest &B, double qx, double qy, int fir
     }
 }
 
-MFT_HD void knn_thread(const KnnArgs &A, int64_t q)
+MFT_HD void knn_thread(const KnnArgs &A, int64_t t)
 {
+    const int64_t q = A.qpos ? A.qpos[t] : t;
     const double qx = A.sx[q], qy = A.sy[q];
     const int cell = A.scell[q];
     const int cx = cell % A.gx, cy = cell / A.gx;
@@ -111,7 +115,7 @@ MFT_HD void knn_thread(const KnnArgs &A, int64_t q)
             if (B.d[k - 1] < gap - 1e-7 * A.h) break;
         }
     }
-    const int64_t out = (int64_t)A.sid[q] * k;
+    const int64_t out = (int64_t)(A.qpos ? A.qrow[t] : A.sid[q]) * k;
     for (int j = 0; j < k; ++j) {
         A.nbr[out + j] = B.i[j];
         A.dist[out + j] = B.d[j];
@@ -293,7 +297,7 @@ MFT_HD void weights_thread(const WeightArgs &A, int64_t t)
 __global__ void __launch_bounds__(128) k_setup_knn(const KnnArgs A)
 {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < A.n) knn_thread(A, q);
+    if (q < A.nq) knn_thread(A, q);
 }
 __global__ void __launch_bounds__(128) k_setup_weights(const WeightArgs A)
 {

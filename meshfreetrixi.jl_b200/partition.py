@@ -61,9 +61,15 @@ def curve_offsets(n: int, nranks: int) -> np.ndarray:
 
 
 def build_rank_partition(points: np.ndarray, boundary_idxs, boundary_normals, rank: int, nranks: int, p: int, N: int,
-                         nv: int, allgather, perm_g: np.ndarray | None = None) -> RankPartition:
+                         nv: int, allgather, perm_g: np.ndarray | None = None, knn_queries=None,
+                         weights_rows=None) -> RankPartition:
     """`allgather(obj) -> list of obj from every rank` is the only communication primitive needed
-    (torch.distributed.all_gather_object in production, a trivial stub for nranks == 1)."""
+    (torch.distributed.all_gather_object in production, a trivial stub for nranks == 1).
+
+    knn_queries(box_points, query_positions, nv) -> (neighbours as positions into box_points, distances) and
+    weights_rows(points, rows_nb, p, N) -> (wx, wy) select who does the two heavy setup steps: None = host (KD-tree +
+    batched LAPACK LU, setup_ops.knn_query / rbf_fd_weights); RBFFDEngineCUDA(setup="device") passes the GPU pipeline
+    (setup_ops.knn_queries_device / rbf_fd_weights_rows_device).  Both produce the same tables (ties by index)."""
     n = points.shape[0]
     if perm_g is None:
         perm_g = L.sfc_order(points)
@@ -81,10 +87,21 @@ def build_rank_partition(points: np.ndarray, boundary_idxs, boundary_normals, ra
     h_est = np.sqrt(area / n)
     pad = 12.0 * h_est * max(1.0, np.sqrt(nv / 20.0))
     box = np.nonzero(np.all((points >= lo - pad) & (points <= hi + pad), axis=1))[0]
-    tree = cKDTree(points[box])
+    if knn_queries is None:
+        tree = cKDTree(points[box])
 
-    def knn(ids):
-        return setup_ops.knn_query(tree, points[ids], nv, index_map=box)
+        def knn(ids):
+            return setup_ops.knn_query(tree, points[ids], nv, index_map=box)
+    else:
+        box_points = np.ascontiguousarray(points[box])
+        pos_in_box = np.full(n, -1, dtype=np.int64)
+        pos_in_box[box] = np.arange(len(box), dtype=np.int64)
+
+        def knn(ids):
+            qp = pos_in_box[ids]
+            assert (qp >= 0).all(), "a query point lies outside the padded partition box"
+            nbp, d = knn_queries(box_points, qp, nv)
+            return box[nbp], d
 
     nb_owned, d_owned = knn(owned)
     F = np.setdiff1d(np.unique(nb_owned), owned)
@@ -115,7 +132,7 @@ def build_rank_partition(points: np.ndarray, boundary_idxs, boundary_normals, ra
 
     # weights: owned rows (full stencils) + halo rows (entries kept only where the column is local)
     rows_nb = np.concatenate([nb_owned, halo_nb]) if n_halo else nb_owned
-    wx, wy = setup_ops.rbf_fd_weights(points, rows_nb, p, N)
+    wx, wy = (weights_rows or setup_ops.rbf_fd_weights)(points, rows_nb, p, N)
     col_local = lut[rows_nb]
     valid = col_local >= 0
     assert valid[:n_local].all(), "an owned row references a point outside owned+halo"

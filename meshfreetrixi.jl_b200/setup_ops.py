@@ -194,6 +194,41 @@ def rbf_fd_weights_device(points: np.ndarray, neighbors: np.ndarray, p: int, N: 
     return wx, wy
 
 
+def knn_queries_device(points: np.ndarray, queries: np.ndarray, nv: int, device: int = 0):
+    """mft_setup_knn_queries: the nv nearest of `points` for the points listed in `queries` (0-based positions);
+    returns (neighbours (nq,nv) 0-based, distances (nq,nv)).  One rank of a partitioned cloud calls this on its padded box."""
+    from . import _lib as L
+
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    n = pts.shape[0]
+    x, y = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1])
+    q1 = np.ascontiguousarray(np.asarray(queries, dtype=np.int64) + 1)
+    nq = len(q1)
+    nbr1 = np.empty((nq, nv), dtype=np.int64)
+    dist = np.empty((nq, nv), dtype=np.float64)
+    if nq:
+        L.check(L.load().mft_setup_knn_queries(device, n, L.ptr(x), L.ptr(y), nv, nq, L.ptr(q1), L.ptr(nbr1), L.ptr(dist)))
+    nbr1 -= 1
+    return nbr1, dist
+
+
+def rbf_fd_weights_rows_device(points: np.ndarray, rows_nb: np.ndarray, p: int, N: int, k: int | None = None, device: int = 0):
+    """mft_setup_rbf_weights_rows: weights for the stencils given as rows of rows_nb (indices into points)"""
+    from . import _lib as L
+
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    n = pts.shape[0]
+    n_rows, nv = rows_nb.shape
+    x, y = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1])
+    nbr1 = np.ascontiguousarray(rows_nb, dtype=np.int64) + 1
+    wx = np.empty((n_rows, nv), dtype=np.float64)
+    wy = np.empty((n_rows, nv), dtype=np.float64)
+    if n_rows:
+        L.check(L.load().mft_setup_rbf_weights_rows(device, n, L.ptr(x), L.ptr(y), n_rows, nv, L.ptr(nbr1), p, N,
+                                                    1 if k is None else k, L.ptr(wx), L.ptr(wy)))
+    return wx, wy
+
+
 def compute_flux_operator_device(points, neighbors, p: int, N: int, k: int | None = None, device: int = 0):
     wx, wy = rbf_fd_weights_device(points, neighbors, p, N, k, device)
     return [assemble_csc(neighbors, wx), assemble_csc(neighbors, wy)]

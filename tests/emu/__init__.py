@@ -32,27 +32,31 @@ def _check(rc):
         raise EmuError(lib().emu_last_error().decode())
 
 
-def setup_knn(points, k):
-    """emulated mft_setup_knn -> (neighbors 0-based (n,k), distances (n,k))"""
+def setup_knn(points, k, queries=None):
+    """emulated mft_setup_knn / mft_setup_knn_queries -> (neighbors 0-based (nq,k), distances (nq,k));
+    queries: 0-based indices of the points that query (None: all)"""
     pts = np.ascontiguousarray(points, dtype=np.float64)
     n = len(pts)
     x, y = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1])
-    nb = np.empty((n, k), np.int64)
-    d = np.empty((n, k))
-    _check(lib().emu_setup_knn(C.c_int64(n), _p(x), _p(y), C.c_int(k), _p(nb), _p(d)))
+    q1 = None if queries is None else np.ascontiguousarray(np.asarray(queries, dtype=np.int64) + 1)
+    nq = n if q1 is None else len(q1)
+    nb = np.empty((nq, k), np.int64)
+    d = np.empty((nq, k))
+    _check(lib().emu_setup_knn(C.c_int64(n), _p(x), _p(y), C.c_int(k), C.c_int64(nq), _p(q1), _p(nb), _p(d)))
     return nb - 1, d
 
 
 def setup_rbf_weights(points, neighbors, p, N, kk=1, scratch_bytes=0):
     """emulated mft_setup_rbf_weights -> (wx, wy) (n,k); scratch_bytes > 0 forces small launches (chunking)"""
     pts = np.ascontiguousarray(points, dtype=np.float64)
-    n, k = neighbors.shape
+    n = len(pts)
+    n_rows, k = neighbors.shape          # rows may be any subset / multiset of the points (their indices stay global)
     x, y = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1])
     nb1 = np.ascontiguousarray(neighbors, dtype=np.int64) + 1
-    wx = np.empty((n, k))
-    wy = np.empty((n, k))
-    _check(lib().emu_setup_rbf_weights(C.c_int64(n), _p(x), _p(y), C.c_int(k), _p(nb1), C.c_int(p), C.c_int(N), C.c_int(kk),
-                                       _p(wx), _p(wy), C.c_int64(scratch_bytes)))
+    wx = np.empty((n_rows, k))
+    wy = np.empty((n_rows, k))
+    _check(lib().emu_setup_rbf_weights(C.c_int64(n), _p(x), _p(y), C.c_int64(n_rows), C.c_int(k), _p(nb1), C.c_int(p), C.c_int(N),
+                                       C.c_int(kk), _p(wx), _p(wy), C.c_int64(scratch_bytes)))
     return wx, wy
 
 

@@ -33,7 +33,7 @@ struct HostEmu {
     int launch_knn(const mft_setup::KnnArgs &A)
     {
 #pragma omp parallel for schedule(dynamic, 256)
-        for (int64_t q = 0; q < A.n; ++q) mft_setup::knn_thread(A, q);
+        for (int64_t q = 0; q < A.nq; ++q) mft_setup::knn_thread(A, q);
         return 0;
     }
     int launch_weights(const mft_setup::WeightArgs &A)
@@ -51,16 +51,17 @@ thread_local std::string g_err;
 
 extern "C" {
 const char *emu_last_error(void) { return g_err.c_str(); }
-int emu_setup_knn(int64_t n, const double *x, const double *y, int k, int64_t *nbr1_out, double *dist_out)
+int emu_setup_knn(int64_t n, const double *x, const double *y, int k, int64_t nq, const int64_t *query_idx1, int64_t *nbr1_out,
+                  double *dist_out)
 {
     HostEmu be;
-    return mft_setup::run_knn(be, n, x, y, k, nbr1_out, dist_out, g_err);
+    return mft_setup::run_knn(be, n, x, y, k, nq, query_idx1, nbr1_out, dist_out, g_err);
 }
-int emu_setup_rbf_weights(int64_t n, const double *x, const double *y, int k, const int64_t *nbr1, int p, int degree, int kk, double *wx,
-                          double *wy, int64_t scratch_bytes)
+int emu_setup_rbf_weights(int64_t n, const double *x, const double *y, int64_t n_rows, int k, const int64_t *nbr1, int p, int degree, int kk,
+                          double *wx, double *wy, int64_t scratch_bytes)
 {
     HostEmu be;
     if (scratch_bytes > 0) be.budget = (size_t)scratch_bytes;
-    return mft_setup::run_weights(be, n, x, y, k, nbr1, p, degree, kk, wx, wy, g_err);
+    return mft_setup::run_weights(be, n, x, y, n_rows, k, nbr1, p, degree, kk, wx, wy, g_err);
 }
 }

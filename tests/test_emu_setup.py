@@ -153,3 +153,77 @@ def test_product_library_refuses_setup_without_a_device():
     nb, _ = emu.setup_knn(pts, 20)
     with pytest.raises(m._lib.MftError, match="no CPU fallback"):
         m.setup_ops.rbf_fd_weights_device(pts, nb, 3, 3)
+
+
+def test_knn_query_subsets_and_weight_row_subsets():
+    """mft_setup_knn_queries / mft_setup_rbf_weights_rows (what a rank of a partitioned cloud calls): the listed points
+    query against all points; any order, duplicates allowed"""
+    rng = np.random.default_rng(11)
+    pts = rng.random((4000, 2)) * [2.0, 1.0]
+    full_nb, full_d = emu.setup_knn(pts, 20)
+    q = rng.integers(0, len(pts), 700)
+    q[5] = q[6]
+    nb, d = emu.setup_knn(pts, 20, queries=q)
+    assert np.array_equal(nb, full_nb[q]) and np.array_equal(d, full_d[q])
+    nb0, _ = emu.setup_knn(pts, 20, queries=np.zeros(0, np.int64))
+    assert nb0.shape == (0, 20)
+    with pytest.raises(emu.EmuError, match="query index"):
+        emu.setup_knn(pts, 20, queries=np.array([4000]))
+    wx, wy = emu.setup_rbf_weights(pts, full_nb, 3, 3, 1)
+    rx, ry = emu.setup_rbf_weights(pts, full_nb[q], 3, 3, 1)
+    assert np.array_equal(rx, wx[q]) and np.array_equal(ry, wy[q])
+
+
+def test_partition_planner_with_device_setup_functions_matches_host_planner():
+    """build_rank_partition with the (emulated) device kNN / weight functions injected gives every rank the same partition,
+    halo plan and neighbour tables as the host KD-tree / LAPACK path; operator values agree to rounding"""
+    import threading
+
+    import mft_b200 as m
+    from mft_b200 import partition
+
+    cl = m.cloud.jittered_lattice(72, 60, 6.0, 5.0, seed=4)
+    R = 3
+
+    class ThreadComm:
+        def __init__(self):
+            self.barrier, self.slots = threading.Barrier(R), [None] * R
+
+        def make(self, rank):
+            def allgather(obj):
+                self.slots[rank] = obj
+                self.barrier.wait()
+                out = list(self.slots)
+                self.barrier.wait()
+                return out
+            return allgather
+
+    def run(device_like):
+        comm, parts, errs = ThreadComm(), [None] * R, []
+
+        def work(r):
+            try:
+                kw = {}
+                if device_like:
+                    kw = dict(knn_queries=lambda pts, q, nv: emu.setup_knn(pts, nv, queries=q),
+                              weights_rows=lambda pts, rows, p, N: emu.setup_rbf_weights(pts, rows, p, N, 1))
+                parts[r] = partition.build_rank_partition(cl.points, [np.asarray(b) for b in cl.boundary_idxs],
+                                                          cl.boundary_normals, r, R, 3, 3, 20, comm.make(r), **kw)
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+                comm.barrier.abort()
+        th = [threading.Thread(target=work, args=(r,)) for r in range(R)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs, errs
+        return parts
+
+    host, dev = run(False), run(True)
+    for a, b in zip(host, dev):
+        assert np.array_equal(a.owned_gid, b.owned_gid) and np.array_equal(a.halo_gid, b.halo_gid)
+        assert np.array_equal(a.neighbors_owned, b.neighbors_owned)
+        assert a.dx_min == b.dx_min and a.dx_avg == b.dx_avg and a.peers == b.peers
+        assert all(np.array_equal(x, y) for x, y in zip(a.send_idx, b.send_idx)) and a.recv_count == b.recv_count
+        for A, B in zip(a.ops, b.ops):
+            assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+            assert np.abs(A.data - B.data).max() <= 1e-8 * np.abs(A.data).max()

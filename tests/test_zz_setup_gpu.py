@@ -121,3 +121,21 @@ def test_device_setup_at_one_million_points():
     # and the host mirror (batched LAPACK LU) agrees on a slice
     hx, hy = m.setup_ops.rbf_fd_weights(cl, nb[:50000], 3, 3)
     assert np.abs(wx[:50000] - hx).max() <= 1e-8 * np.abs(hx).max() and np.abs(wy[:50000] - hy).max() <= 1e-8 * np.abs(hy).max()
+
+
+def test_device_knn_queries_and_weight_rows():
+    """the per-rank entry points (mft_setup_knn_queries / mft_setup_rbf_weights_rows) against the whole-cloud calls"""
+    m = _m()
+    rng = np.random.default_rng(11)
+    pts = rng.random((4000, 2)) * [2.0, 1.0]
+    full_nb, full_d = _knn_dev(pts, 20)
+    q = rng.integers(0, len(pts), 700)
+    nb, d = m.setup_ops.knn_queries_device(pts, q, 20)
+    assert np.array_equal(nb, full_nb[q]) and np.array_equal(d, full_d[q])
+    enb, ed = emu.setup_knn(pts, 20, queries=q)
+    assert np.array_equal(nb, enb) and np.array_equal(d, ed)
+    wx, wy = m.setup_ops.rbf_fd_weights_device(pts, full_nb, 3, 3)
+    rx, ry = m.setup_ops.rbf_fd_weights_rows_device(pts, full_nb[q], 3, 3)
+    assert np.array_equal(rx, wx[q]) and np.array_equal(ry, wy[q])
+    with pytest.raises(m._lib.MftError, match="query index"):
+        m.setup_ops.knn_queries_device(pts, np.array([4000]), 20)
