@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--source", default="upwind")
     ap.add_argument("--exchange", default="p2p")
+    ap.add_argument("--setup", default="host", help="device: every rank builds its kNN tables / weights with the GPU pipeline")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -127,7 +128,7 @@ def main():
         assert err < 1e-12, err
     else:
         solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=int(os.environ.get("LOCAL_RANK", rank)),
-                                                                    diagnostics=True, exchange=args.exchange))
+                                                                    diagnostics=True, exchange=args.exchange, setup=args.setup))
         domain = m.ParallelPointCloudDomain(solver, cl, names, comm)
         part = domain.partition
         eq = m.CompressibleEulerEquations2D(GAMMA)
@@ -155,8 +156,9 @@ def main():
         sol = m.solve(ode, m.SSPRK33(), dt=dt, callback=m.HistoryCallback(3), nsteps=10)
         err2 = max(np.abs(sol.u[v, :nl] - u_ref[v, part.owned_gid]).max() / np.abs(u_ref[v]).max() for v in range(4))
         results = dict(rank=rank, n_local=nl, n_halo=part.n_halo, err=float(err), err_steps=float(err2))
-        assert err < 1e-12, err
-        assert err2 < 1e-9, err2
+        # device-made weights differ from the serial oracle's by rounding (different elimination order): 1e-9 instead of 1e-12
+        assert err < (1e-12 if args.setup == "host" else 1e-9), err
+        assert err2 < (1e-9 if args.setup == "host" else 1e-8), err2
         semi.close()
     allres = comm.allgather(results)
     if rank == 0:

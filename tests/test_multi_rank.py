@@ -20,12 +20,12 @@ def _free_port():
     return p
 
 
-def _launch(nproc, mode, source, tmp_path, timeout=600, exchange="p2p"):
-    out = os.path.join(tmp_path, f"res_{mode}_{source}_{exchange}.json")
+def _launch(nproc, mode, source, tmp_path, timeout=600, exchange="p2p", setup="host"):
+    out = os.path.join(tmp_path, f"res_{mode}_{source}_{exchange}_{setup}.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(cases.ROOT, "tests", "dist_worker.py"), "--mode", mode, "--source", source, "--out", out,
-           "--exchange", exchange]
+           "--exchange", exchange, "--setup", setup]
     env = dict(os.environ, OMP_NUM_THREADS="2")
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
@@ -70,3 +70,13 @@ def test_many_gpus_p2p_match_serial_oracle(tmp_path, nproc):
         pytest.skip(f"needs {nproc} GPUs (run under gpurun --gpus {nproc})")
     res = _launch(nproc, "gpu", "residual", str(tmp_path), timeout=300, exchange="p2p")
     assert len(res) == nproc and all(r["err"] < 1e-12 and r["err_steps"] < 1e-9 for r in res)
+
+
+@pytest.mark.gpu
+def test_two_gpus_device_setup_match_serial_oracle(tmp_path):
+    """RBFFDEngineCUDA(setup="device") on every rank: kNN tables / weights from the GPU pipeline (row f1), then the same
+    multi-GPU rhs! and time loop against the serial oracle (weights agree to rounding, so 1e-9 / 1e-8)"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    res = _launch(2, "gpu", "residual", str(tmp_path), timeout=240, exchange="p2p", setup="device")
+    assert all(r["err"] < 1e-9 and r["err_steps"] < 1e-8 for r in res)
