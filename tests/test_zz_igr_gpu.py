@@ -10,13 +10,13 @@ from cases import orc
 pytestmark = pytest.mark.gpu
 
 
-def _problem(alpha, maxiter=20, reorder="hilbert", extra_sources=(), bcs=None):
+def _problem(alpha, maxiter=20, reorder="hilbert", extra_sources=(), bcs=None, diagnostics=False):
     import mft_b200 as m
 
     fx = cases.fixture_setup(p=3, N=3)
     ops = m.setup_ops.compute_flux_operator(fx["points"], fx["nb"], 3, 3)
     basis = m.PointCloudBasis(m.Point2D(), 3, approximation_type=m.RBF(m.PolyharmonicSpline(3)), nv=fx["nv"])
-    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(reorder=reorder))
+    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(reorder=reorder, diagnostics=diagnostics))
     domain = m.PointCloudDomain(solver, cases.FIXTURE, cases.BOUNDARY_NAMES)
     eq = m.CompressibleEulerEquations2D(cases.GAMMA)
     ic = cases.ic_smooth_euler
@@ -86,7 +86,7 @@ def test_igr_after_upwind_viscosity_and_vtk_field(tmp_path):
     solver0 = m0.PointCloudSolver(basis, engine=m0.RBFFDEngineCUDA())
     domain0 = m0.PointCloudDomain(solver0, cases.FIXTURE, cases.BOUNDARY_NAMES)
     uw = m0.SourceUpwindViscosityTominec(solver0, m0.CompressibleEulerEquations2D(cases.GAMMA), domain0)
-    m, fx, ops, semi, bcs, ic = _problem(alpha, extra_sources=dict(uw=uw))
+    m, fx, ops, semi, bcs, ic = _problem(alpha, extra_sources=dict(uw=uw), diagnostics=True)   # eps fields for the VTK file
     ode = m.semidiscretize(semi, (0.0, 1.0))
     u = ode.u0.copy()
     du = np.empty_like(u)

@@ -1,10 +1,15 @@
 #!/bin/bash
-# round-end GPU pass: parity tests, smoke, the default bench line, ncu launch list + full capture of the two pass kernels
+# GPU pass for the start of the next session (the code of rows f1/f4 has not seen hardware yet):
+# parity tests, smoke, the default bench line, setup-pipeline timing, ncu launch list + full capture of the two pass kernels
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/final_pytest.log 2>&1; tail -2 gpurun_out/final_pytest.log
+python -m pytest tests -m gpu -q > gpurun_out/final_pytest.log 2>&1; tail -5 gpurun_out/final_pytest.log
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/final_smoke.log 2>&1; tail -1 gpurun_out/final_smoke.log
 python bench.py > gpurun_out/final_bench.log 2>gpurun_out/final_bench.err; tail -c 600 gpurun_out/final_bench.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1_tile.csv python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:tiler --launch-skip 8 -c 2 -o gpurun_out/prof_r1_tile_final -f python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-ncu -i gpurun_out/prof_r1_tile_final.ncu-rep --page raw --csv > gpurun_out/raw_r1_tile_final.csv 2>/dev/null
-ls -la gpurun_out/launches_r1_tile.csv gpurun_out/raw_r1_tile_final.csv
+python bench.py --setup device --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_setup_device.log 2>&1; tail -c 300 gpurun_out/bench_setup_device.log
+python tools/setup_bench.py --n-side 1024 > gpurun_out/setup_bench_1m.json 2>gpurun_out/setup_bench.err; cat gpurun_out/setup_bench_1m.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2.csv python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tiler --launch-skip 8 -c 2 -o gpurun_out/prof_r2_tile -f python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+ncu -i gpurun_out/prof_r2_tile.ncu-rep --page raw --csv > gpurun_out/raw_r2_tile.csv 2>/dev/null
+ncu --set full --clock-control none --import-source on -k regex:k_setup --launch-skip 2 -c 2 -o gpurun_out/prof_r2_setup -f python tools/setup_bench.py --n-side 512 --reps 1 > gpurun_out/ncu_setup.log 2>&1
+ncu -i gpurun_out/prof_r2_setup.ncu-rep --page raw --csv > gpurun_out/raw_r2_setup.csv 2>/dev/null
+ls -la gpurun_out/
