@@ -19,6 +19,7 @@ import ctypes as C
 from dataclasses import dataclass, field
 
 import numpy as np
+import scipy.sparse as sp
 
 from . import _lib as L
 from . import cloud as cloudmod
@@ -243,8 +244,29 @@ class SourceHyperviscosityFlyer(_Source):
 
     def __init__(self, solver, equations, domain, k=2, c=1.0):
         p, N = solver.basis.approx_type.rbf_type.Nrbf, solver.basis.N
-        ops = setup_ops.flux_operator_with(solver.engine, domain.pd.points, domain.pd.neighbors, p, N, 2 * k)
-        self.hv_differentiation_matrix = (ops[0] + ops[1]).tocsc()
+        part = getattr(domain, "partition", None)
+        if part is None:
+            ops = setup_ops.flux_operator_with(solver.engine, domain.pd.points, domain.pd.neighbors, p, N, 2 * k)
+            self.hv_differentiation_matrix = (ops[0] + ops[1]).tocsc()
+        else:
+            # one rank of a partitioned cloud: H has the sparsity of D, so the owned rows need exactly the u halo that
+            # rhs! already exchanges.  Weights from the GLOBAL stencils of the owned rows; columns
+            # renumbered to the local [owned ; halo] layout; halo rows stay empty (they are not computed here).
+            eng = solver.engine
+            gpts = np.ascontiguousarray(domain.cloud.points, dtype=np.float64)
+            if getattr(eng, "setup", "host") == "device":
+                wx, wy = setup_ops.rbf_fd_weights_rows_device(gpts, part.neighbors_owned, p, N, 2 * k, eng.device)
+            else:
+                wx, wy = setup_ops.rbf_fd_weights(gpts, part.neighbors_owned, p, N, 2 * k)
+            lut = np.full(part.n_global, -1, dtype=np.int64)
+            lut[part.local_gid] = np.arange(part.n_local + part.n_halo)
+            cols = lut[part.neighbors_owned]
+            assert (cols >= 0).all()
+            n_tot = part.n_local + part.n_halo
+            rows = np.repeat(np.arange(part.n_local, dtype=np.int64), part.neighbors_owned.shape[1])
+            H = sp.coo_matrix(((wx + wy).reshape(-1), (rows, cols.reshape(-1))), shape=(n_tot, n_tot)).tocsc()
+            H.sort_indices()
+            self.hv_differentiation_matrix = H
         self.gamma = c * domain.pd.dx_min ** (2 * k)
         self.c = c
 
@@ -340,9 +362,10 @@ class SemidiscretizationHyperbolic:
         if part is not None:
             ops = part.ops
             for src in self.source_terms.values():
-                if src.kind in (L.SRC_HV_FLYER, L.SRC_HV_TOMINEC):
-                    raise NotImplementedError("hyperviscosity sources are not partitioned yet (multi-GPU supports the "
-                                              "flux divergence and the upwind / residual viscosity sources)")
+                if src.kind == L.SRC_HV_TOMINEC:
+                    raise NotImplementedError("SourceHyperviscosityTominec is not partitioned (L'L reaches two stencil rings: it "
+                                              "needs a wider halo than rhs! exchanges); multi-GPU supports the flux divergence, "
+                                              "Flyer hyperviscosity and the upwind / residual viscosity sources")
         else:
             ops = operators or setup_ops.flux_operator_with(eng, pd.points, pd.neighbors, p, N)
         self.cache = Cache(pd, ops)

@@ -67,14 +67,20 @@ def main():
     cl = m.cloud.jittered_lattice(72, 60, 10.0, 10.0 * 60 / 72, seed=4)
     names = dict(left=1, right=2, bottom=3, top=4)
     ic = lambda x, t, e=None: m.cloud.isentropic_vortex(x, GAMMA, center=(5.0, 4.0))
-    basis = m.PointCloudBasis(m.Point2D(), 3, approximation_type=m.RBF(m.PolyharmonicSpline(3)))
+    PHS = 5 if args.source == "flyer" else 3      # 4th derivatives (Flyer hyperviscosity) want r^5
+    basis = m.PointCloudBasis(m.Point2D(), 3, approximation_type=m.RBF(m.PolyharmonicSpline(PHS)))
 
     # ---- serial oracle on the global cloud (every rank computes it; it is small) -------------------------------
     nb, dx_min, dx_avg = orc.point_data(cl.points, basis.nv)
-    ops = m.setup_ops.compute_flux_operator(cl.points, nb, 3, 3)
+    ops = m.setup_ops.compute_flux_operator(cl.points, nb, PHS, 3)
     obc = [orc.OracleBC(orc.BC_DIRICHLET, cl.boundary_idxs[g], cl.boundary_normals[g], value_fn=lambda x, t: ic(x, t))
            for g in range(4)]
-    src_o = orc.source_upwind(dx_avg) if args.source == "upwind" else orc.source_residual(dx_avg, polydeg=3)
+    if args.source == "flyer":
+        # hyperviscosity.jl:34-50 with the product's (batched-LU) weights, so that serial and partitioned H agree bit for bit
+        hops = m.setup_ops.compute_flux_operator(cl.points, nb, PHS, 3, 4)
+        src_o = orc.OracleSource(kind=orc.SRC_HV_FLYER, hv=orc.JuliaCSC((hops[0] + hops[1]).tocsc()), gamma=1.0 * dx_min ** 4)
+    else:
+        src_o = orc.source_upwind(dx_avg) if args.source == "upwind" else orc.source_residual(dx_avg, polydeg=3)
     P = orc.OracleProblem(cl.points, 4, orc.EQ_EULER2D, [GAMMA], ops[0], ops[1], obc, [src_o])
     u0 = ic(cl.points, 0.0) * (1.0 + 0.01 * np.sin(cl.points[:, 0]))
     u_ser = u0.copy()
@@ -83,7 +89,7 @@ def main():
     results = {}
     if args.mode == "cpu":
         part = partition.build_rank_partition(cl.points, cl.boundary_idxs, cl.boundary_normals, comm.rank, comm.nranks,
-                                              3, 3, basis.nv, comm.allgather)
+                                              PHS, 3, basis.nv, comm.allgather)
         gid = part.local_gid
         nl = part.n_local
         # the local operator rows of owned points are the global rows, bit for bit
@@ -110,6 +116,38 @@ def main():
         F, G, (v1, v2, p) = euler_flux(u)
         Dx, Dy = part.ops[0].tocsr(), part.ops[1].tocsr()
         du = np.stack([-(Dx[:nl] @ F[v]) - (Dy[:nl] @ G[v]) for v in range(4)])
+        if args.source == "flyer":
+            # SourceHyperviscosityFlyer on a partition: du += -gamma H u on owned rows, only the u halo is needed
+            import types
+
+            dom = types.SimpleNamespace(partition=part, cloud=cl, pd=types.SimpleNamespace(dx_min=part.dx_min))
+            solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA())
+            hv = m.SourceHyperviscosityFlyer(solver, None, dom, k=2, c=1.0)
+            H = hv.hv_differentiation_matrix.tocsr()
+            assert H.shape == (len(gid), len(gid)) and H[nl:].nnz == 0
+            Hg = src_o.hv.scipy.tocsr()
+            for i in range(0, nl, 41):        # owned rows of the local H are the global rows, bit for bit
+                gl, ll = Hg[gid[i]], H[i]
+                o1, o2 = np.argsort(gid[ll.indices]), np.argsort(gl.indices)
+                assert np.array_equal(gid[ll.indices][o1], gl.indices[o2]) and np.array_equal(ll.data[o1], gl.data[o2])
+            for v in range(4):
+                du[v] -= hv.gamma * (H[:nl] @ u[v])
+            for g in range(4):
+                du[:, part.boundary_idxs[g]] = 0.0
+            ref = du_ser[:, part.owned_gid]
+            err = max(np.abs(du[v] - ref[v]).max() / np.abs(du_ser[v]).max() for v in range(4))
+            assert err < 1e-12, err
+            results = dict(rank=rank, n_local=nl, n_halo=part.n_halo, err=float(err))
+            allres = comm.allgather(results)
+            if rank == 0:
+                print("MULTI_RANK_OK", allres)
+                if args.out:
+                    import json
+
+                    json.dump(allres, open(args.out, "w"))
+            dist.barrier()
+            dist.destroy_process_group()
+            return
         eps = 0.5 * part.dx_avg * (np.hypot(v1, v2) + np.sqrt(GAMMA * p / u[0]))[:nl]
         g8 = np.zeros((8, len(gid)))
         for v in range(4):
@@ -135,6 +173,8 @@ def main():
         bc = {k: m.BoundaryConditionDirichlet(ic) for k in names}
         if args.source == "upwind":
             srcs = m.SourceTerms(rv=m.SourceUpwindViscosityTominec(solver, eq, domain))
+        elif args.source == "flyer":
+            srcs = m.SourceTerms(hv=m.SourceHyperviscosityFlyer(solver, eq, domain, k=2, c=1.0))
         else:
             srcs = m.SourceTerms(rv=m.SourceResidualViscosityTominec(solver, eq, domain, polydeg=3))
         semi = m.SemidiscretizationHyperbolic(domain, eq, ic, solver, boundary_conditions=bc, source_terms=srcs)
@@ -151,9 +191,10 @@ def main():
         assert (du[:, nl:] == 0).all()                       # reset_halos! parallel_rbfsolver.jl:74-91
         # time integration: 10 SSPRK33 steps with the history callback, against the serial oracle
         dt = 0.1 * dx_min / 8.0
-        u_ref, _ = P.solve_ssprk33(u0, 0.0, dt, 10, approx_order=3)
+        hist = None if args.source == "flyer" else 3
+        u_ref, _ = P.solve_ssprk33(u0, 0.0, dt, 10, approx_order=hist)
         ode = m.ODEProblem(np.ascontiguousarray(u0[:, gid]), (0.0, 10 * dt), semi)
-        sol = m.solve(ode, m.SSPRK33(), dt=dt, callback=m.HistoryCallback(3), nsteps=10)
+        sol = m.solve(ode, m.SSPRK33(), dt=dt, callback=None if hist is None else m.HistoryCallback(3), nsteps=10)
         err2 = max(np.abs(sol.u[v, :nl] - u_ref[v, part.owned_gid]).max() / np.abs(u_ref[v]).max() for v in range(4))
         results = dict(rank=rank, n_local=nl, n_halo=part.n_halo, err=float(err), err_steps=float(err2))
         # device-made weights differ from the serial oracle's by rounding (different elimination order): 1e-9 instead of 1e-12

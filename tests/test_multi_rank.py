@@ -39,6 +39,13 @@ def test_partition_and_algorithm_world2_gloo(tmp_path):
     assert all(r["n_halo"] > 0 and r["err"] < 1e-12 for r in res)
 
 
+def test_flyer_hyperviscosity_on_a_partition_world2_gloo(tmp_path):
+    """Flyer hyperviscosity needs only the u halo; the partition-aware source constructor gives every
+    rank the global rows of H bit for bit, and the partitioned rhs! equals the serial oracle's"""
+    res = _launch(2, "cpu", "flyer", str(tmp_path))
+    assert len(res) == 2 and all(r["n_halo"] > 0 and r["err"] < 1e-12 for r in res)
+
+
 def test_partition_world3_gloo(tmp_path):
     res = _launch(3, "cpu", "upwind", str(tmp_path))
     assert len(res) == 3 and all(r["err"] < 1e-12 for r in res)
@@ -55,7 +62,7 @@ def _ngpu():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
-@pytest.mark.parametrize("source", ["upwind", "residual"])
+@pytest.mark.parametrize("source", ["upwind", "residual", "flyer"])
 def test_two_gpus_match_serial_oracle(tmp_path, source, exchange):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
