@@ -145,15 +145,25 @@ def run_ours(args):
     t_setup = time.time()
     domain = m.ParallelPointCloudDomain(solver, cl, names, comm) if multi else m.PointCloudDomain(solver, cl, names)
     eq = m.CompressibleEulerEquations2D(GAMMA)
-    ic = vortex_ic(m, (5.0, 5.0 * ny / nx))
-    bc = {k: m.BoundaryConditionDirichlet(ic) for k in names}
-    srcs = m.SourceTerms(rv=m.SourceResidualViscosityTominec(solver, eq, domain, c_rv=1.0, c_uw=1.0, polydeg=3))
+    residual = args.source == "residual"
+    if args.workload == "sod":     # configs[3]: Sod shock tube, slip walls top/bottom, Dirichlet left/right
+        ic = lambda x, t, e=None: m.cloud.sod(x, GAMMA, x_mid=5.0)   # noqa: E731
+        bc = dict(left=m.BoundaryConditionDirichlet(ic), right=m.BoundaryConditionDirichlet(ic),
+                  bottom=m.boundary_condition_slip_wall, top=m.boundary_condition_slip_wall)
+    else:                          # configs[1]: isentropic vortex, Dirichlet data on all sides
+        ic = vortex_ic(m, (5.0, 5.0 * ny / nx))
+        bc = {k: m.BoundaryConditionDirichlet(ic) for k in names}
+    if residual:
+        srcs = m.SourceTerms(rv=m.SourceResidualViscosityTominec(solver, eq, domain, c_rv=1.0, c_uw=1.0, polydeg=3))
+    else:                          # configs[2]: upwind (first-order) viscosity, no history callback
+        srcs = m.SourceTerms(uw=m.SourceUpwindViscosityTominec(solver, eq, domain, c_uw=1.0))
     semi = m.SemidiscretizationHyperbolic(domain, eq, ic, solver, boundary_conditions=bc, source_terms=srcs)
     t_setup = time.time() - t_setup
     N = cl.points.shape[0]                                    # global points
     n_own = domain.partition.n_local if multi else N          # rows this rank computes
     pd = domain.pd
-    dt = 0.1 * pd.dx_min / 8.0   # CFL 0.1*dx_min/(|v|+c), |v|+c ~ 7.4 for the vortex base state
+    # CFL 0.1*dx_min/(|v|+c): |v|+c ~ 7.4 for the vortex base state, ~ 2.2 behind the Sod shock
+    dt = 0.1 * pd.dx_min / (8.0 if args.workload == "vortex" else 3.0)
     ode = m.semidiscretize(semi, (0.0, 1.0))
     u0 = ode.u0
     ctx = semi.ctx
@@ -174,12 +184,14 @@ def run_ours(args):
         for i in range(n):
             L.check(lib.mft_ssprk_step(ctx, L.SSPRK33, t, dt))
             t += dt
-            L.check(lib.mft_history_push(ctx, t, it0 + i + 1, 3))
+            if residual:
+                L.check(lib.mft_history_push(ctx, t, it0 + i + 1, 3))
         return t
 
     # ---- device-resident timed region: barrier + sync on both sides, CUDA events on the ctx stream, max over ranks ----
     L.check(lib.mft_upload_state(ctx, L.soa_ptrs(u0)))
-    L.check(lib.mft_history_push(ctx, 0.0, 0, 3))
+    if residual:
+        L.check(lib.mft_history_push(ctx, 0.0, 0, 3))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()   # nvidia-smi needs ~100 ms to deliver its first sample: start before the warm-up steps
@@ -218,13 +230,14 @@ def run_ours(args):
     L.check(lib.mft_set_kernel_timing(ctx, 0))
     peak, peak_src = measured_peak()
     V, k = 4, K_STENCIL
-    bytes_a = n_own * (20 * k + 8 * V + 8 * V + 8 * V + 16 * V)  # idx+wx+wy, u gather, approx_du, du, g
+    src_bytes = 288 if residual else 256                         # 40k + 288 (residual) / 40k + 256 (upwind)
+    bytes_a = n_own * (20 * k + 8 * V + (8 * V if residual else 0) + 8 * V + 16 * V)  # idx+wx+wy, u gather, approx_du, du, g
     bytes_b = n_own * (20 * k + 16 * V + 16 * V)                 # idxT+wxT+wyT, g gather, du read+write
     a_ms, a_n = ktime["pass_a"]
     b_ms, b_n = ktime["pass_b"]
     dom, dom_bytes, dom_ms, dom_n = ("k_pass_a", bytes_a, a_ms, a_n) if a_ms >= b_ms else ("k_pass_b", bytes_b, b_ms, b_n)
     achieved = dom_bytes / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9
-    step_bytes = N * STAGES * (40 * k + 288 + 128)
+    step_bytes = N * STAGES * (40 * k + src_bytes + 128)
     agg_peak = peak * world
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
@@ -232,7 +245,7 @@ def run_ours(args):
                 "avg_launch_ms": round(dom_ms / max(dom_n, 1), 4),
                 "whole_step": {"algorithmic_GBps": round(step_bytes / (ms_per_step * 1e-3) / 1e9, 1),
                                "frac_of_n_gpu_peak": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / agg_peak, 4),
-                               "bytes_per_point_stage": 40 * k + 288 + 128},
+                               "bytes_per_point_stage": 40 * k + src_bytes + 128},
                 "kernel_ms_per_step": {kk: round(v[0] / args.steps, 4) for kk, v in ktime.items()},
                 "note": "per-kernel times: rank 0, CUDA events around every launch (eager replay of the same steps)"}
 
@@ -261,14 +274,18 @@ def run_ours(args):
     # ---- CPU baseline: the oracle's C port of the reference structure, bounded sample, rank 0, N=1 only -----------
     cpu = None
     if not args.no_cpu_baseline and not multi:
-        cpu = cpu_baseline(semi, domain, u_end, m, budget_s=args.cpu_seconds)
+        cpu = cpu_baseline(semi, domain, u_end, m, budget_s=args.cpu_seconds, residual=residual)
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
-               "config": {"workload": f"BASELINE configs[1]: 2D Euler isentropic vortex + residual viscosity, {N}-point "
-                                      f"jittered cloud ({nx}x{ny} + ring), PHS3 deg3 k=20, SSPRK33 + HistoryCallback(3)",
+               "config": {"workload": (f"BASELINE configs[1]: 2D Euler isentropic vortex + residual viscosity, {N}-point "
+                                       f"jittered cloud ({nx}x{ny} + ring), PHS3 deg3 k=20, SSPRK33 + HistoryCallback(3)")
+                          if (args.workload, args.source) == ("vortex", "residual") else
+                          (f"2D Euler {'Sod shock tube (slip walls top/bottom, Dirichlet left/right)' if args.workload == 'sod' else 'isentropic vortex'}"
+                           f" + {'residual viscosity + HistoryCallback(3)' if residual else 'upwind (first-order) viscosity'}, {N}-point "
+                           f"jittered cloud ({nx}x{ny} + ring), PHS3 deg3 k=20, SSPRK33"),
                           "points": N, "points_per_gpu": N // world, "k": k, "stages_per_step": STAGES,
                           "summation": "fma single-sweep" if args.fma else "reference order (bit-exact sums)",
                           "partition": "single GPU" if not multi else f"Hilbert-curve ranges over {world} ranks, halo exchange (u, g) + global norms per stage via {'NVLink peer-memory puts (CUDA IPC), graph-replayed' if args.exchange == 'p2p' else 'NCCL send/recv + all-gather'}",
@@ -290,7 +307,7 @@ except Exception:
     pass
 
 
-def cpu_baseline(semi, domain, u, m, budget_s=15.0):
+def cpu_baseline(semi, domain, u, m, budget_s=15.0, residual=True):
     """Times the reference's CPU execution structure (oracle/mft_oracle.c: CSC/Int64 operators, one SpMV per variable
     per direction, serial loops -- the reference's hot loops are single-threaded) on this box's host cores."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -299,10 +316,15 @@ def cpu_baseline(semi, domain, u, m, budget_s=15.0):
     pd = domain.pd
     ops = semi.cache.rbf_differentiation_matrices
     obc = []
+    all_dirichlet = True
     for name, bc, tag in semi._bc_groups:
-        vals = np.ascontiguousarray(bc.boundary_value_function(pd.points[tag.idx], 0.0, None))
-        obc.append(orc.OracleBC(orc.BC_DIRICHLET, tag.idx, tag.normals, values=vals))
-    src = orc.source_residual(pd.dx_avg, polydeg=3)
+        if hasattr(bc, "boundary_value_function"):
+            vals = np.ascontiguousarray(bc.boundary_value_function(pd.points[tag.idx], 0.0, None))
+            obc.append(orc.OracleBC(orc.BC_DIRICHLET, tag.idx, tag.normals, values=vals))
+        else:
+            all_dirichlet = False
+            obc.append(orc.OracleBC(orc.BC_SLIP_WALL, tag.idx, tag.normals))
+    src = orc.source_residual(pd.dx_avg, polydeg=3) if residual else orc.source_upwind(pd.dx_avg)
     src.success_iter = 5
     P = orc.OracleProblem(pd.points, 4, orc.EQ_EULER2D, [GAMMA], ops[0], ops[1], obc, [src])
     uu = np.ascontiguousarray(u.copy())
@@ -314,10 +336,12 @@ def cpu_baseline(semi, domain, u, m, budget_s=15.0):
     P.rhs_repeat(uu, reps)
     dt = time.perf_counter() - t0
     out = {"value": pd.num_points * reps / dt, "unit": UNIT, "cores": 1, "kind": "port",
-           "sample": f"{reps} rhs! evaluations (Euler + residual viscosity) on the full {pd.num_points}-point cloud, "
+           "sample": f"{reps} rhs! evaluations (Euler + {'residual' if residual else 'upwind'} viscosity) on the full {pd.num_points}-point cloud, "
                      "C port of the reference's serial CSC-SpMV structure (oracle/mft_oracle.c), 1 thread"}
     # variant (ii) of SURVEY.md 8(d): best-effort CPU (fused row-parallel kernel on all host cores, oracle/mft_cpu_fast.c)
     try:
+        if not (all_dirichlet and residual):
+            raise NotImplementedError("the fused CPU kernel covers the configs[1] workload only (Dirichlet data, residual viscosity)")
         bidx = np.concatenate([tag.idx for _, _, tag in semi._bc_groups])
         bvals = np.concatenate([np.asarray(bc.boundary_value_function(pd.points[tag.idx], 0.0, None))
                                 for _, bc, tag in semi._bc_groups], axis=1)
@@ -418,6 +442,10 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo exchange mechanism")
     ap.add_argument("--setup", default="host", choices=["host", "device"],
                     help="kNN + RBF-FD weight generation (untimed setup): host numpy/LAPACK, or the GPU pipeline (mft_setup_*)")
+    ap.add_argument("--workload", default="vortex", choices=["vortex", "sod"],
+                    help="vortex: BASELINE configs[1] (default, the bench line); sod: configs[3] (shock tube, slip/Dirichlet mix)")
+    ap.add_argument("--source", default="residual", choices=["residual", "upwind"],
+                    help="stabilisation source: residual viscosity + history (configs[1], [3]) or upwind viscosity (configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--cloud-order", default="hilbert", choices=["hilbert", "lattice"],

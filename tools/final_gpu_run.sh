@@ -13,3 +13,6 @@ ncu -i gpurun_out/prof_r2_tile.ncu-rep --page raw --csv > gpurun_out/raw_r2_tile
 ncu --set full --clock-control none --import-source on -k regex:k_setup --launch-skip 2 -c 2 -o gpurun_out/prof_r2_setup -f python tools/setup_bench.py --n-side 512 --reps 1 > gpurun_out/ncu_setup.log 2>&1
 ncu -i gpurun_out/prof_r2_setup.ncu-rep --page raw --csv > gpurun_out/raw_r2_setup.csv 2>/dev/null
 ls -la gpurun_out/
+# named configs at bench size (1 GPU): configs[2]-style upwind viscosity, configs[3]-style Sod + residual viscosity
+python bench.py --source upwind --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_vortex_upwind.log 2>&1; tail -c 400 gpurun_out/bench_vortex_upwind.log
+python bench.py --workload sod --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_sod_rv.log 2>&1; tail -c 400 gpurun_out/bench_sod_rv.log
