@@ -270,6 +270,29 @@ def run_ours(args):
            "d2h_bytes_per_step": STAGES * 32 * (N + n_touched * world),
            "call": "mft_rhs(MFT_MEM_HOST): u H2D, rhs!, du D2H + the rows of u that rhs! changes (boundary points, halo), "
                    "pinned host arrays", "calls_timed": e2e_calls}
+    # informational (single GPU): the device-resident stepper driven with host-visible state EVERY STEP instead of every
+    # stage -- u H2D, one SSPRK33 step (3 stages + the f(u_n) evaluation an uploaded state needs), u D2H.  The strict
+    # per-rhs! number above stays the e2e value.
+    if not multi:
+        try:
+            tt = t
+            for _ in range(3):
+                L.check(lib.mft_upload_state(ctx, up))
+                L.check(lib.mft_ssprk_step(ctx, L.SSPRK33, tt, dt))
+                L.check(lib.mft_download_state(ctx, up))
+            calls = max(3, min(args.steps, 20))
+            t0 = time.perf_counter()
+            for _ in range(calls):
+                L.check(lib.mft_upload_state(ctx, up))
+                L.check(lib.mft_ssprk_step(ctx, L.SSPRK33, tt, dt))
+                L.check(lib.mft_download_state(ctx, up))
+                tt += dt
+            el = time.perf_counter() - t0
+            e2e["per_step_host_state"] = {"value": N * STAGES * calls / el, "unit": UNIT, "h2d_bytes_per_step": 32 * N,
+                                          "d2h_bytes_per_step": 32 * N, "calls_timed": calls,
+                                          "call": "mft_upload_state + mft_ssprk_step + mft_download_state per step (pinned)"}
+        except Exception as exc:   # informational only: never lose the bench line over it
+            e2e["per_step_host_state"] = {"unavailable": repr(exc)}
 
     # ---- CPU baseline: the oracle's C port of the reference structure, bounded sample, rank 0, N=1 only -----------
     cpu = None
