@@ -180,6 +180,9 @@ int mft_ssprk43_step(mft_ctx *ctx, double t, double dt, double abstol, double re
 int mft_step_commit(mft_ctx *ctx, int accept);
 int mft_get_field(mft_ctx *ctx, int field, double *out);
 int mft_synchronize(mft_ctx *ctx);
+/* failure detection (the reference has none: Trixi's ode_unstable_check is imported at src/MeshfreeTrixi.jl:33 and unused):
+ * number of NaN / +-Inf entries in the owned rows of the resident state */
+int mft_count_nonfinite(mft_ctx *ctx, int64_t *count_out);
 /* number of kernels launched by this ctx since creation (bench.py `gpu_launches`) */
 int64_t mft_launch_count(mft_ctx *ctx);
 /* CUDA-event time (ms) of kernel class `which` accumulated since the last reset; which<0 resets all. */

@@ -466,6 +466,12 @@ class SemidiscretizationHyperbolic:
             elif eng.exchange != "nccl":
                 raise ValueError("RBFFDEngineCUDA.exchange must be 'p2p' or 'nccl'")
 
+    def count_nonfinite(self):
+        """number of NaN / Inf entries in the owned rows of the device-resident state (mft_count_nonfinite)"""
+        cnt = C.c_int64()
+        L.check(L.load().mft_count_nonfinite(self.ctx, C.byref(cnt)))
+        return int(cnt.value)
+
     def refresh_boundary_values(self, t):
         lib = L.load()
         for g, (name, bc, tag) in enumerate(self._bc_groups):

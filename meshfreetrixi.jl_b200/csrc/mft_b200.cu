@@ -5,7 +5,10 @@
 #include "mft_tile_kernels.cuh"
 #include "mft_limiter_kernels.cuh"
 #include "mft_igr_kernels.cuh"
+#include "mft_aux_kernels.cuh"
 #include "mft_nccl.h"
+
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: a no-op unless a profiler injects itself
 
 #include <algorithm>
 #include <cmath>
@@ -265,6 +268,16 @@ extern "C" int mft_device_count(void)
 }
 
 static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// NVTX ranges carrying the labels of the reference's TimerOutputs sections (`@trixi_timeit timer() "..."`:
+// rbfsolver.jl:392,400-425, parallel_rbfsolver.jl:96-132, history.jl:69), so an nsys / ncu timeline of the GPU path reads
+// like the reference's timer table.  Host-side only: nothing is recorded during CUDA-graph replay (one range per replay).
+struct NvtxRange {
+    explicit NvtxRange(const char *label) { nvtxRangePushA(label); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 struct ScopedTimer {
     mft_ctx *c;
@@ -1170,6 +1183,7 @@ static int build_tiler(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, int R, bool
 extern "C" int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int with_perm, unsigned seed, double *stats4)
 {
     if (n <= 0 || k <= 0 || k > n || (R != 1 && R != 2 && R != 4)) return fail(MFT_EINVAL, "mft_debug_tile_selftest: bad arguments");
+    NvtxRange range("tile layout selftest");
     mft_ctx ctx;
     ctx.n_local = n - n / 7;  // some trailing "halo" columns without rows
     ctx.n_halo = n - ctx.n_local;
@@ -1989,6 +2003,9 @@ static int launch_igr(mft_ctx *c, Source *s)
 // one source functor call on the resident state
 static int apply_source_dev(mft_ctx *c, Source *s)
 {
+    static const char *const kLabels[] = {"calc SourceHyperviscosityFlyer", "calc SourceHyperviscosityTominec",
+                                          "calc SourceUpwindViscosityTominec", "calc SourceResidualViscosityTominec", "calc SourceIGR"};
+    NvtxRange r(s->kind >= 0 && s->kind <= MFT_SRC_IGR ? kLabels[s->kind] : "calc source");
     if (s->kind == MFT_SRC_IGR) return launch_igr(c, s);
     if (s->kind == MFT_SRC_HV_FLYER || s->kind == MFT_SRC_HV_TOMINEC) return launch_spmv(c, s);
     const int visc = s->kind == MFT_SRC_UPWIND ? VISC_UPWIND : VISC_RESIDUAL;
@@ -2005,7 +2022,11 @@ static int rhs_device(mft_ctx *c, double t)
     // update_halos! (parallel_rbfsolver.jl:98-101) happens before the BC pass in the reference; BC points are owned
     // points, and halo copies of boundary points must carry the BC-imposed value the owner computes, so the
     // exchange runs after the owner applied its BCs.
-    CHECK(launch_boundary(c, false));  // pass 1: du is formed from 0 below, only u needs writing
+    NvtxRange rhs_range("rhs!");
+    {
+        NvtxRange r("boundary flux");
+        CHECK(launch_boundary(c, false));  // pass 1: du is formed from 0 below, only u needs writing
+    }
     const bool fused_visc = !c->srcs.empty() && (c->srcs[0]->kind == MFT_SRC_UPWIND || c->srcs[0]->kind == MFT_SRC_RESIDUAL);
     const bool p2p_rv = c->p2p && c->nranks > 1 && fused_visc && c->srcs[0]->kind == MFT_SRC_RESIDUAL;
     if (p2p_rv) {
@@ -2017,21 +2038,29 @@ static int rhs_device(mft_ctx *c, double t)
         CHECK(p2p_wait(c, 0));
         CHECK(p2p_norms_part(c, 2));
     } else {
+        NvtxRange r("update halos");
         CHECK(halo_exchange<4 /*V set below*/>(c, c->u.p));
     }
     size_t first = 0;
     if (fused_visc) {
         Source *s = c->srcs[0];
         const int visc = s->kind == MFT_SRC_UPWIND ? VISC_UPWIND : VISC_RESIDUAL;
+        NvtxRange r(visc == VISC_RESIDUAL ? "calc fluxes + calc SourceResidualViscosityTominec (fused)"
+                                          : "calc fluxes + calc SourceUpwindViscosityTominec (fused)");
         if (visc == VISC_RESIDUAL && !p2p_rv) CHECK(c->nranks > 1 ? launch_norms_multi(c) : launch_norms(c));
         CHECK(launch_pass_a(c, true, visc, s, false));  // flux divergence + D u + eps + g in one sweep
         CHECK(halo_exchange<8>(c, c->g.p));
         CHECK(launch_pass_b(c));
         first = 1;
     } else {
+        NvtxRange r("calc fluxes");
         CHECK(launch_pass_a(c, true, VISC_NONE, nullptr, false));
     }
-    for (size_t i = first; i < c->srcs.size(); ++i) CHECK(apply_source_dev(c, c->srcs[i]));
+    {
+        NvtxRange r("source terms");
+        for (size_t i = first; i < c->srcs.size(); ++i) CHECK(apply_source_dev(c, c->srcs[i]));
+    }
+    NvtxRange r("boundary flux");
     CHECK(launch_boundary(c, true));  // pass 2
     return MFT_OK;
 }
@@ -2164,6 +2193,7 @@ static int history_push_common(mft_ctx *c, double t, int64_t success_iter, bool 
                                const double *weights_or_null, int approx_order)
 {
     if (c->nslots == 0) return MFT_OK;  // modify_cache! fallback: no-op without a residual-viscosity source (history.jl:87-89)
+    NvtxRange range("update history");
     c->success_iter = success_iter;
     // shift_soln_history! history.jl:105-111 as a ring buffer: slot 0 = most recent
     c->hist_head = (c->hist_head + c->nslots - 1) % c->nslots;
@@ -2221,6 +2251,7 @@ static int launch_limiter(mft_ctx *c, int npairs, const double *thresholds, cons
 
 static int launch_stage(mft_ctx *c, int stage, double dt)
 {
+    NvtxRange range("SSPRK stage update");
     ScopedTimer tm(c, MFT_K_STAGE);
     const int64_t len = c->n_local * c->V;
     k_ssprk33_stage<<<c->red_blocks * 2, 256, 0, c->stream>>>(stage, dt, c->uprev.p, c->du.p, c->u.p, len);
@@ -2565,6 +2596,27 @@ extern "C" int mft_get_field(mft_ctx *c, int field, double *out)
         return MFT_OK;
     default: return fail(MFT_EINVAL, "mft_get_field: unknown field %d", field);
     }
+}
+
+// failure detection: number of non-finite entries in the owned rows of the resident state
+extern "C" int mft_count_nonfinite(mft_ctx *c, int64_t *count_out)
+{
+    NEED_CTX(c);
+    CHECK(mft_finalize(c));
+    if (!count_out) return fail(MFT_EINVAL, "mft_count_nonfinite: count_out is NULL");
+    DevBuf<unsigned long long> cnt;
+    CHECK(cnt.alloc(1));
+    CU(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), c->stream));
+    k_count_nonfinite<<<c->red_blocks, 256, 0, c->stream>>>(c->u.p, c->V, c->n_local, cnt.p);
+    c->launches++;
+    const cudaError_t le = cudaGetLastError();
+    unsigned long long h = 0;
+    cudaError_t ce = le == cudaSuccess ? cudaMemcpyAsync(&h, cnt.p, sizeof h, cudaMemcpyDeviceToHost, c->stream) : le;
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+    cnt.release();
+    if (ce != cudaSuccess) return fail(MFT_ECUDA, "mft_count_nonfinite: %s", cudaGetErrorString(ce));
+    *count_out = (int64_t)h;
+    return MFT_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -88,3 +88,11 @@ def igr_apply(neighbors, wx, wy, alpha, maxiter, u, du):
     if rc != 0:
         raise EmuError("emu_igr_apply failed")
     return sigma, (int(st[0]), float(st[1]), float(st[2]))
+
+
+def count_nonfinite(u):
+    """emulated k_count_nonfinite on a (V,N) state (laid out AoS like on the device)"""
+    aos = np.ascontiguousarray(np.asarray(u, dtype=np.float64).T)
+    f = lib().emu_count_nonfinite
+    f.restype = C.c_int64
+    return int(f(C.c_int64(aos.shape[0]), C.c_int(aos.shape[1]), _p(aos)))

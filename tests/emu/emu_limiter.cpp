@@ -31,3 +31,13 @@ extern "C" int emu_limiter_zhang_shu(int64_t n, int k, const int64_t *nbr0 /* n 
     std::free(tbuf);
     return 0;
 }
+
+#include "../../meshfreetrixi.jl_b200/csrc/mft_aux_kernels.cuh"
+
+// k_count_nonfinite's thread body over an AoS state (n x V)
+extern "C" int64_t emu_count_nonfinite(int64_t n, int V, const double *u_aos)
+{
+    int64_t cnt = 0;
+    for (int64_t row = 0; row < n; ++row) cnt += mft::nonfinite_in_row(u_aos, V, row);
+    return cnt;
+}

@@ -16,3 +16,4 @@ ls -la gpurun_out/
 # named configs at bench size (1 GPU): configs[2]-style upwind viscosity, configs[3]-style Sod + residual viscosity
 python bench.py --source upwind --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_vortex_upwind.log 2>&1; tail -c 400 gpurun_out/bench_vortex_upwind.log
 python bench.py --workload sod --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_sod_rv.log 2>&1; tail -c 400 gpurun_out/bench_sod_rv.log
+bash tools/sanitize.sh
