@@ -227,3 +227,44 @@ def test_partition_planner_with_device_setup_functions_matches_host_planner():
         for A, B in zip(a.ops, b.ops):
             assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
             assert np.abs(A.data - B.data).max() <= 1e-8 * np.abs(A.data).max()
+
+
+def test_knn_property_random_clouds():
+    """hypothesis: any finite cloud (random size, anisotropy, clustering, duplicated points, lattice snapping) -> the exact
+    (distance, index)-ordered tables of the all-pairs reference"""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 2 ** 31 - 1), st.integers(1, 260), st.integers(1, 24), st.sampled_from([1.0, 1e-3, 1e3]),
+           st.sampled_from([1.0, 1e-6, 50.0]), st.sampled_from(["uniform", "normal", "snapped", "dups"]))
+    def check(seed, n, k, scale, aspect, kind):
+        rng = np.random.default_rng(seed)
+        k = min(k, n)
+        if kind == "normal":
+            pts = rng.normal(size=(n, 2))
+        else:
+            pts = rng.random((n, 2))
+        if kind == "snapped":
+            pts = np.round(pts * 8) / 8          # many exact ties and coincident points
+        if kind == "dups" and n > 3:
+            pts[rng.integers(0, n, n // 3)] = pts[0]
+        pts = np.ascontiguousarray(pts * [scale, scale * aspect] + [rng.normal() * scale, 0.0])
+        nb, d = emu.setup_knn(pts, k)
+        rb, rd = brute_knn(pts, k)
+        assert np.array_equal(nb, rb) and np.array_equal(d, rd)
+
+    check()
+
+
+def test_weights_scale_exactly_with_a_power_of_two_dilation():
+    """the stencil is normalised per axis before the solve, so doubling the coordinates halves first-derivative weights and
+    quarters second-derivative weights bit for bit; an anisotropic dilation acts per axis"""
+    s = cases.fixture_setup(p=5, N=3)
+    pts, nb = s["points"], s["nb"]
+    wx, wy = emu.setup_rbf_weights(pts, nb, 5, 3, 1)
+    w2x, w2y = emu.setup_rbf_weights(pts * [2.0, 0.25], nb, 5, 3, 1)
+    assert np.array_equal(w2x, wx / 2.0) and np.array_equal(w2y, wy * 4.0)
+    vx, vy = emu.setup_rbf_weights(pts, nb, 5, 3, 2)
+    v2x, v2y = emu.setup_rbf_weights(pts * 2.0, nb, 5, 3, 2)
+    assert np.array_equal(v2x, vx / 4.0) and np.array_equal(v2y, vy / 4.0)
