@@ -231,6 +231,11 @@ int mft_setup_rbf_weights(int device, int64_t n, const double *x, const double *
 /* the same for n_rows stencils given as rows of nbr1 (n_rows x k, indices into the n points): a rank's owned + halo rows */
 int mft_setup_rbf_weights_rows(int device, int64_t n, const double *x, const double *y, int64_t n_rows, int k, const int64_t *nbr1,
                                int phs_power, int poly_degree, int deriv_order, double *wx_out, double *wy_out);
+/* the same for the HybridGaussianPHS basis phi = alpha exp(-(epsilon r)^2) + beta r^phs_power
+ * (RBF(HybridGaussianPHS(; Nrbf, alpha, beta, epsilon)), src/domains/PointCloudDomain/geometry_primatives.jl:117-132, 238-262) */
+int mft_setup_rbf_weights_hybrid(int device, int64_t n, const double *x, const double *y, int64_t n_rows, int k, const int64_t *nbr1,
+                                 int phs_power, double alpha, double beta, double epsilon, int poly_degree, int deriv_order,
+                                 double *wx_out, double *wy_out);
 
 /* ---- Zhang-Shu positivity limiter (stage callback) ------------------------------------------------------
  * replaces Trixi.limiter_zhang_shu!(u, threshold, variable, domain::PointCloudDomain{2}, ...)

@@ -13,7 +13,7 @@ from .api import *  # noqa: F401,F403
 from .vtk import SolutionSavingCallback, trixi2vtk  # noqa: F401
 from .api import (BoundaryConditionDirichlet, BoundaryConditionDoNothing, CompressibleEulerEquations2D,  # noqa: F401
                   HistoryCallback, LinearScalarAdvectionEquation2D, Point2D, PointCloudBasis, PointCloudDomain,
-                  PointCloudSolver, PolyharmonicSpline, RBF, RBFFDEngineCUDA, SemidiscretizationHyperbolic,
+                  PointCloudSolver, PolyharmonicSpline, HybridGaussianPHS, RBF, RBFFDEngineCUDA, SemidiscretizationHyperbolic,
                   SourceHyperviscosityFlyer, SourceHyperviscosityTominec, SourceResidualViscosityTominec,
                   SourceTerms, SourceUpwindViscosityTominec, SourceIGR, cg_, SSPRK33, SSPRK43, PIController, ParallelPointCloudDomain,
                   boundary_condition_slip_wall, solve_adaptive, PositivityPreservingLimiterZhangShu, density, pressure,

@@ -37,8 +37,24 @@ class PolyharmonicSpline:
 
 
 @dataclass
+class HybridGaussianPHS:
+    """blended Gaussian and odd-order polyharmonic spline phi = alpha exp(-(epsilon r)^2) + beta r^Nrbf
+    (geometry_primatives.jl:117-132, 238-262)"""
+    Nrbf: int = 3
+    alpha: float = 1.0
+    beta: float = 1.0
+    epsilon: float = 1.0
+
+
+@dataclass
 class RBF:
-    rbf_type: PolyharmonicSpline = field(default_factory=PolyharmonicSpline)
+    rbf_type: object = field(default_factory=PolyharmonicSpline)   # PolyharmonicSpline | HybridGaussianPHS
+
+
+def _hybrid_of(basis):
+    """(alpha, beta, epsilon) of a HybridGaussianPHS basis, None for a pure polyharmonic spline"""
+    t = basis.approx_type.rbf_type
+    return (t.alpha, t.beta, t.epsilon) if isinstance(t, HybridGaussianPHS) else None
 
 
 @dataclass
@@ -130,12 +146,13 @@ class ParallelPointCloudDomain(PointCloudDomain):
         basis = solver.basis
         eng = solver.engine
         on_device = getattr(eng, "setup", "host") == "device"
+        hyb = _hybrid_of(basis)
         part = partition.build_rank_partition(
             cl.points, cl.boundary_idxs, cl.boundary_normals, comm.rank, comm.nranks, basis.approx_type.rbf_type.Nrbf,
             basis.N, basis.nv, comm.allgather,
             knn_queries=(lambda pts, q, nv: setup_ops.knn_queries_device(pts, q, nv, eng.device)) if on_device else None,
-            weights_rows=(lambda pts, rows, p, N: setup_ops.rbf_fd_weights_rows_device(pts, rows, p, N, None, eng.device))
-            if on_device else None)
+            weights_rows=(lambda pts, rows, p, N: setup_ops.rbf_fd_weights_rows_device(pts, rows, p, N, None, eng.device, hyb))
+            if on_device else ((lambda pts, rows, p, N: setup_ops.rbf_fd_weights(pts, rows, p, N, hybrid=hyb)) if hyb else None))
         self.partition, self.comm, self.cloud = part, comm, cl
         self.pd = PointData(part.points, part.neighbors_owned, part.n_local + part.n_halo, basis.nv, part.dx_min, part.dx_avg)
         self.boundary_tags = {name: BoundaryData(part.boundary_idxs[g - 1], part.boundary_normals[g - 1])
@@ -246,7 +263,7 @@ class SourceHyperviscosityFlyer(_Source):
         p, N = solver.basis.approx_type.rbf_type.Nrbf, solver.basis.N
         part = getattr(domain, "partition", None)
         if part is None:
-            ops = setup_ops.flux_operator_with(solver.engine, domain.pd.points, domain.pd.neighbors, p, N, 2 * k)
+            ops = setup_ops.flux_operator_with(solver.engine, domain.pd.points, domain.pd.neighbors, p, N, 2 * k, _hybrid_of(solver.basis))
             self.hv_differentiation_matrix = (ops[0] + ops[1]).tocsc()
         else:
             # one rank of a partitioned cloud: H has the sparsity of D, so the owned rows need exactly the u halo that
@@ -254,10 +271,11 @@ class SourceHyperviscosityFlyer(_Source):
             # renumbered to the local [owned ; halo] layout; halo rows stay empty (they are not computed here).
             eng = solver.engine
             gpts = np.ascontiguousarray(domain.cloud.points, dtype=np.float64)
+            hyb = _hybrid_of(solver.basis)
             if getattr(eng, "setup", "host") == "device":
-                wx, wy = setup_ops.rbf_fd_weights_rows_device(gpts, part.neighbors_owned, p, N, 2 * k, eng.device)
+                wx, wy = setup_ops.rbf_fd_weights_rows_device(gpts, part.neighbors_owned, p, N, 2 * k, eng.device, hyb)
             else:
-                wx, wy = setup_ops.rbf_fd_weights(gpts, part.neighbors_owned, p, N, 2 * k)
+                wx, wy = setup_ops.rbf_fd_weights(gpts, part.neighbors_owned, p, N, 2 * k, hybrid=hyb)
             lut = np.full(part.n_global, -1, dtype=np.int64)
             lut[part.local_gid] = np.arange(part.n_local + part.n_halo)
             cols = lut[part.neighbors_owned]
@@ -277,7 +295,7 @@ class SourceHyperviscosityTominec(_Source):
 
     def __init__(self, solver, equations, domain, c=1.0):
         p, N = solver.basis.approx_type.rbf_type.Nrbf, solver.basis.N
-        ops = setup_ops.flux_operator_with(solver.engine, domain.pd.points, domain.pd.neighbors, p, N, 2)
+        ops = setup_ops.flux_operator_with(solver.engine, domain.pd.points, domain.pd.neighbors, p, N, 2, _hybrid_of(solver.basis))
         lap = (ops[0] + ops[1]).tocsc()
         self.hv_differentiation_matrix = (lap.T @ lap).tocsc()
         self.gamma = c * domain.pd.dx_min ** 4.5
@@ -367,7 +385,7 @@ class SemidiscretizationHyperbolic:
                                               "needs a wider halo than rhs! exchanges); multi-GPU supports the flux divergence, "
                                               "Flyer hyperviscosity and the upwind / residual viscosity sources")
         else:
-            ops = operators or setup_ops.flux_operator_with(eng, pd.points, pd.neighbors, p, N)
+            ops = operators or setup_ops.flux_operator_with(eng, pd.points, pd.neighbors, p, N, None, _hybrid_of(solver.basis))
         self.cache = Cache(pd, ops)
         lib = L.load()
         ctx = C.c_void_p()

@@ -113,3 +113,17 @@ extern "C" int mft_setup_rbf_weights_rows(int device, int64_t n, const double *x
     if (rc) return fail(rc == -1 ? MFT_EINVAL : MFT_ECUDA, "%s", err.c_str());
     return MFT_OK;
 }
+
+/* HybridGaussianPHS basis (geometry_primatives.jl:117-132, 238-262): phi = alpha exp(-(epsilon r)^2) + beta r^phs_power */
+extern "C" int mft_setup_rbf_weights_hybrid(int device, int64_t n, const double *x, const double *y, int64_t n_rows, int k, const int64_t *nbr1,
+                                            int phs_power, double alpha, double beta, double epsilon, int poly_degree, int deriv_order,
+                                            double *wx_out, double *wy_out)
+{
+    CHECK(setup_select_device("mft_setup_rbf_weights_hybrid", device));
+    CudaSetupBackend be;
+    std::string err;
+    const double hyb[3] = {alpha, beta, epsilon};
+    const int rc = mft_setup::run_weights(be, n, x, y, n_rows, k, nbr1, phs_power, poly_degree, deriv_order, wx_out, wy_out, err, hyb);
+    if (rc) return fail(rc == -1 ? MFT_EINVAL : MFT_ECUDA, "%s", err.c_str());
+    return MFT_OK;
+}

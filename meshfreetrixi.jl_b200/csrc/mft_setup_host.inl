@@ -194,7 +194,7 @@ int run_knn(BE &be, int64_t n, const double *x, const double *y, int k, int64_t 
 // nbr1.  n_rows = n for a whole cloud; a rank of a partitioned cloud passes its own rows only (indices stay global).
 template <class BE>
 int run_weights(BE &be, int64_t n, const double *x, const double *y, int64_t n_rows, int k, const int64_t *nbr1, int p, int degree, int kk,
-                double *wx_out, double *wy_out, std::string &err)
+                double *wx_out, double *wy_out, std::string &err, const double *hybrid3 = nullptr /* alpha, beta, epsilon */)
 {
     if (n < 1 || !x || !y || !nbr1 || !wx_out || !wy_out) return setup_fail(err, "setup_rbf_weights: bad arguments (n = %lld)", (long long)n);
     if (n_rows < 0) return setup_fail(err, "setup_rbf_weights: negative row count %lld", (long long)n_rows);
@@ -203,6 +203,8 @@ int run_weights(BE &be, int64_t n, const double *x, const double *y, int64_t n_r
     if (degree < 0 || degree > 6) return setup_fail(err, "setup_rbf_weights: polynomial degree %lld outside 0..6", degree);
     if (kk < 1 || kk > 4) return setup_fail(err, "setup_rbf_weights: derivative order %lld outside 1..4", kk);
     if (p < 1 || (p % 2) == 0) return setup_fail(err, "setup_rbf_weights: polyharmonic spline power %lld must be odd and positive", p);
+    if (hybrid3 && !(std::isfinite(hybrid3[0]) && std::isfinite(hybrid3[1]) && std::isfinite(hybrid3[2])))
+        return setup_fail(err, "setup_rbf_weights: non-finite HybridGaussianPHS parameter");
     const int npoly = (degree + 1) * (degree + 2) / 2;
     if (npoly > k) return setup_fail(err, "setup_rbf_weights: %lld monomials need a stencil of at least that many points (k = %lld)", npoly, k);
     std::vector<int> nbr((size_t)n_rows * k);
@@ -226,7 +228,11 @@ int run_weights(BE &be, int64_t n, const double *x, const double *y, int64_t n_r
     A.k = k;
     A.degree = degree;
     A.npoly = npoly;
-    A.p = p;
+    A.rbf.p = p;
+    A.rbf.hybrid = hybrid3 ? 1 : 0;
+    A.rbf.alpha = hybrid3 ? hybrid3[0] : 0.0;
+    A.rbf.beta = hybrid3 ? hybrid3[1] : 1.0;
+    A.rbf.eps2 = hybrid3 ? hybrid3[2] * hybrid3[2] : 0.0;
     A.kk = kk;
     A.x = d_x.template as<double>();
     A.y = d_y.template as<double>();

@@ -138,23 +138,35 @@ MFT_HD double half_pow(double s, int h2)
     if (odd) r = r * sqrt(s);
     return r;
 }
-// kk-th derivative along x of phi = (x^2+y^2)^(p/2), written through f(s) = s^q, q = p/2, s = r^2:
-//   f^(m)(s) = q (q-1) ... (q-m+1) s^(q-m)
-MFT_HD double phs_fd(double s, int p, int mm)
+// The radial basis as a function of s = r^2 (geometry_primatives.jl:211-262):
+//   PolyharmonicSpline      phi = r^p                                  f(s) = s^q,  q = p/2
+//   HybridGaussianPHS       phi = alpha exp(-(eps r)^2) + beta r^p     f(s) = alpha exp(-eps^2 s) + beta s^q
+//   f^(m)(s) = [alpha (-eps^2)^m exp(-eps^2 s)] + beta q (q-1) ... (q-m+1) s^(q-m)
+struct RbfKind {
+    int p;          // odd power of the polyharmonic part
+    int hybrid;     // 0: pure PHS (alpha, beta, eps2 unused)
+    double alpha, beta, eps2;
+};
+MFT_HD double rbf_fd(const RbfKind &K, double s, int mm)
 {
-    const double q = 0.5 * (double)p;
+    const double q = 0.5 * (double)K.p;
     double c = 1.0;
     for (int i = 0; i < mm; ++i) c = c * (q - (double)i);
-    return c * half_pow(s, p - 2 * mm);
+    const double phs = c * half_pow(s, K.p - 2 * mm);
+    if (!K.hybrid) return phs;
+    double g = K.alpha * exp(-(K.eps2 * s));
+    for (int i = 0; i < mm; ++i) g = g * -K.eps2;
+    return g + K.beta * phs;
 }
-MFT_HD double phs_axis_derivative(double x, double s, int p, int kk)
+// kk-th derivative along x of phi(x, y) = f(x^2 + y^2)
+MFT_HD double rbf_axis_derivative(const RbfKind &K, double x, double s, int kk)
 {
     switch (kk) {
-    case 0: return half_pow(s, p);
-    case 1: return 2.0 * x * phs_fd(s, p, 1);
-    case 2: return 2.0 * phs_fd(s, p, 1) + 4.0 * x * x * phs_fd(s, p, 2);
-    case 3: return 12.0 * x * phs_fd(s, p, 2) + 8.0 * (x * x * x) * phs_fd(s, p, 3);
-    default: return 12.0 * phs_fd(s, p, 2) + 48.0 * x * x * phs_fd(s, p, 3) + 16.0 * ((x * x) * (x * x)) * phs_fd(s, p, 4);
+    case 0: return rbf_fd(K, s, 0);
+    case 1: return 2.0 * x * rbf_fd(K, s, 1);
+    case 2: return 2.0 * rbf_fd(K, s, 1) + 4.0 * x * x * rbf_fd(K, s, 2);
+    case 3: return 12.0 * x * rbf_fd(K, s, 2) + 8.0 * (x * x * x) * rbf_fd(K, s, 3);
+    default: return 12.0 * rbf_fd(K, s, 2) + 48.0 * x * x * rbf_fd(K, s, 3) + 16.0 * ((x * x) * (x * x)) * rbf_fd(K, s, 4);
     }
 }
 
@@ -164,7 +176,7 @@ struct WeightArgs {
     int k;             // stencil width
     int degree;        // polynomial degree N: monomials x^a y^b, a + b <= N, ordered (d; a = d..0)
     int npoly;         // (N+1)(N+2)/2
-    int p;             // polyharmonic spline r^p
+    RbfKind rbf;       // radial basis (PHS r^p, or the Gaussian + PHS hybrid)
     int kk;            // derivative order 1..4 (1 = compute_flux_operator(solver, domain))
     const double *x, *y;  // caller order
     const int *nbr;       // n x k row-major, 0-based, self first
@@ -203,7 +215,7 @@ MFT_HD void weights_thread(const WeightArgs &A, int64_t t)
     for (int i = 0; i < k; ++i) {
         for (int j = 0; j < k; ++j) {
             const double dx = xs[i] - xs[j], dy = ys[i] - ys[j];
-            MFT_MAT(i, j) = half_pow(dx * dx + dy * dy, A.p);
+            MFT_MAT(i, j) = rbf_fd(A.rbf, dx * dx + dy * dy, 0);
         }
         int c = k;
         for (int d = 0; d <= A.degree; ++d)
@@ -219,8 +231,8 @@ MFT_HD void weights_thread(const WeightArgs &A, int64_t t)
     for (int j = 0; j < k; ++j) {
         const double mx = j == 0 ? kEps : -xs[j], my = j == 0 ? kEps : -ys[j];
         const double s = mx * mx + my * my;
-        MFT_RHS(j, 0) = phs_axis_derivative(mx, s, A.p, A.kk);
-        MFT_RHS(j, 1) = phs_axis_derivative(my, s, A.p, A.kk);
+        MFT_RHS(j, 0) = rbf_axis_derivative(A.rbf, mx, s, A.kk);
+        MFT_RHS(j, 1) = rbf_axis_derivative(A.rbf, my, s, A.kk);
     }
     {
         double fact = 1.0;

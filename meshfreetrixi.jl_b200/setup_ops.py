@@ -61,18 +61,23 @@ def monomial_exponents(N: int):
     return [(a, d - a) for d in range(N + 1) for a in range(d, -1, -1)]
 
 
-def _phs_axis_derivative(x, r2, p: int, k: int):
-    """k-th derivative of (x^2+y^2)^(p/2) with respect to x, written through f(s)=s^q, q=p/2, s=r^2."""
+def _phs_axis_derivative(x, r2, p: int, k: int, hybrid=None):
+    """k-th derivative with respect to x of phi = f(x^2+y^2): f(s) = s^q, q = p/2 (PolyharmonicSpline) or, hybrid =
+    (alpha, beta, epsilon), f(s) = alpha exp(-epsilon^2 s) + beta s^q (HybridGaussianPHS, geometry_primatives.jl:238-262)."""
     q = p / 2.0
 
-    def fd(m):  # m-th derivative of s^q
+    def fd(m):  # m-th derivative of f
         c = 1.0
         for i in range(m):
             c *= q - i
-        return c * np.power(r2, q - m)
+        phs = c * np.power(r2, q - m)
+        if hybrid is None:
+            return phs
+        a, b, e = hybrid
+        return a * (-(e * e)) ** m * np.exp(-(e * e) * r2) + b * phs
 
     if k == 0:
-        return np.power(r2, q)
+        return fd(0)
     if k == 1:
         return 2.0 * x * fd(1)
     if k == 2:
@@ -85,7 +90,7 @@ def _phs_axis_derivative(x, r2, p: int, k: int):
 
 
 def rbf_fd_weights(points: np.ndarray, neighbors: np.ndarray, p: int, N: int, k: int | None = None,
-                   chunk: int = 4096, workers: int | None = None):
+                   chunk: int = 4096, workers: int | None = None, hybrid=None):
     """Per-point weights Dx_loc, Dy_loc (N,nv): shift_stencil / [R P; P' 0] \\ rhs / rescale, batched.
     k=None: first derivatives; k: pure k-th derivatives d^k/dx^k, d^k/dy^k (as the reference builds them)."""
     npts, nv = neighbors.shape
@@ -110,7 +115,7 @@ def rbf_fd_weights(points: np.ndarray, neighbors: np.ndarray, p: int, N: int, k:
         dx = Xs[:, :, None, 0] - Xs[:, None, :, 0]
         dy = Xs[:, :, None, 1] - Xs[:, None, :, 1]
         M = np.zeros((B, m, m))
-        M[:, :nv, :nv] = np.power(dx * dx + dy * dy, p / 2.0)
+        M[:, :nv, :nv] = _phs_axis_derivative(None, dx * dx + dy * dy, p, 0, hybrid)
         P = np.power(Xs[:, :, None, 0], ea[None, None, :]) * np.power(Xs[:, :, None, 1], eb[None, None, :])
         M[:, :nv, nv:] = P
         M[:, nv:, :nv] = np.transpose(P, (0, 2, 1))
@@ -121,8 +126,8 @@ def rbf_fd_weights(points: np.ndarray, neighbors: np.ndarray, p: int, N: int, k:
         my[:, 0] = eps
         r2 = mx * mx + my * my
         rhs = np.zeros((B, m, 2))
-        rhs[:, :nv, 0] = _phs_axis_derivative(mx, r2, p, kk)
-        rhs[:, :nv, 1] = _phs_axis_derivative(my, r2, p, kk)
+        rhs[:, :nv, 0] = _phs_axis_derivative(mx, r2, p, kk, hybrid)
+        rhs[:, :nv, 1] = _phs_axis_derivative(my, r2, p, kk, hybrid)
         rhs[:, nv:, 0] = pr_x
         rhs[:, nv:, 1] = pr_y
         W = np.linalg.solve(M, rhs)
@@ -149,8 +154,8 @@ def assemble_csc(neighbors: np.ndarray, w: np.ndarray, ncols: int | None = None)
     return A
 
 
-def compute_flux_operator(points, neighbors, p: int, N: int, k: int | None = None):
-    wx, wy = rbf_fd_weights(points, neighbors, p, N, k)
+def compute_flux_operator(points, neighbors, p: int, N: int, k: int | None = None, hybrid=None):
+    wx, wy = rbf_fd_weights(points, neighbors, p, N, k, hybrid=hybrid)
     return [assemble_csc(neighbors, wx), assemble_csc(neighbors, wy)]
 
 
@@ -212,8 +217,9 @@ def knn_queries_device(points: np.ndarray, queries: np.ndarray, nv: int, device:
     return nbr1, dist
 
 
-def rbf_fd_weights_rows_device(points: np.ndarray, rows_nb: np.ndarray, p: int, N: int, k: int | None = None, device: int = 0):
-    """mft_setup_rbf_weights_rows: weights for the stencils given as rows of rows_nb (indices into points)"""
+def rbf_fd_weights_rows_device(points: np.ndarray, rows_nb: np.ndarray, p: int, N: int, k: int | None = None, device: int = 0,
+                               hybrid=None):
+    """mft_setup_rbf_weights_rows / _hybrid: weights for the stencils given as rows of rows_nb (indices into points)"""
     from . import _lib as L
 
     pts = np.ascontiguousarray(points, dtype=np.float64)
@@ -223,14 +229,21 @@ def rbf_fd_weights_rows_device(points: np.ndarray, rows_nb: np.ndarray, p: int, 
     nbr1 = np.ascontiguousarray(rows_nb, dtype=np.int64) + 1
     wx = np.empty((n_rows, nv), dtype=np.float64)
     wy = np.empty((n_rows, nv), dtype=np.float64)
-    if n_rows:
+    if n_rows and hybrid is not None:
+        a, b, e = (float(v) for v in hybrid)
+        L.check(L.load().mft_setup_rbf_weights_hybrid(device, n, L.ptr(x), L.ptr(y), n_rows, nv, L.ptr(nbr1), p, a, b, e, N,
+                                                      1 if k is None else k, L.ptr(wx), L.ptr(wy)))
+    elif n_rows:
         L.check(L.load().mft_setup_rbf_weights_rows(device, n, L.ptr(x), L.ptr(y), n_rows, nv, L.ptr(nbr1), p, N,
                                                     1 if k is None else k, L.ptr(wx), L.ptr(wy)))
     return wx, wy
 
 
-def compute_flux_operator_device(points, neighbors, p: int, N: int, k: int | None = None, device: int = 0):
-    wx, wy = rbf_fd_weights_device(points, neighbors, p, N, k, device)
+def compute_flux_operator_device(points, neighbors, p: int, N: int, k: int | None = None, device: int = 0, hybrid=None):
+    if hybrid is not None:
+        wx, wy = rbf_fd_weights_rows_device(points, neighbors, p, N, k, device, hybrid)
+    else:
+        wx, wy = rbf_fd_weights_device(points, neighbors, p, N, k, device)
     return [assemble_csc(neighbors, wx), assemble_csc(neighbors, wy)]
 
 
@@ -241,7 +254,7 @@ def knn_with(engine, points, nv):
     return knn(points, nv)
 
 
-def flux_operator_with(engine, points, neighbors, p, N, k=None):
+def flux_operator_with(engine, points, neighbors, p, N, k=None, hybrid=None):
     if getattr(engine, "setup", "host") == "device":
-        return compute_flux_operator_device(points, neighbors, p, N, k, engine.device)
-    return compute_flux_operator(points, neighbors, p, N, k)
+        return compute_flux_operator_device(points, neighbors, p, N, k, engine.device, hybrid)
+    return compute_flux_operator(points, neighbors, p, N, k, hybrid)

@@ -164,15 +164,21 @@ def _monomial_exponents(N: int):
 _RBF_CACHE = {}
 
 
-def _phs_functions(p: int, k: int | None):
-    """phi = sqrt(x^2+y^2)^p and its (k-th) x/y derivatives, built symbolically like
+def _phs_functions(p: int, k: int | None, hybrid=None):
+    """phi = sqrt(x^2+y^2)^p -- or, hybrid = (alpha, beta, epsilon), alpha*exp(-(epsilon*r)^2) + beta*r^p
+    (rbf_basis, geometry_primatives.jl:211-262) -- and its (k-th) x/y derivatives, built symbolically like
     concrete_rbf_flux_basis (compute_operators.jl:9-82 with Symbolics)."""
-    key = (p, k)
+    key = (p, k, None if hybrid is None else tuple(float(v) for v in hybrid))
     if key not in _RBF_CACHE:
         import sympy
 
         x, y = sympy.symbols("x y", real=True)
-        phi = sympy.sqrt(x**2 + y**2) ** p
+        r = sympy.sqrt(x**2 + y**2)
+        if hybrid is None:
+            phi = r ** p
+        else:
+            a, b, e = (sympy.Float(float(v)) for v in hybrid)
+            phi = a * sympy.exp(-(e * r) ** 2) + b * r ** p
         kk = 1 if k is None else k
         fx = sympy.simplify(sympy.diff(phi, x, kk))
         fy = sympy.simplify(sympy.diff(phi, y, kk))
@@ -194,7 +200,7 @@ def _poly_deriv_at_origin(exps, axis: int, k: int):
     return out
 
 
-def compute_flux_operator(points, neighbors, p: int, N: int, k: int | None = None):
+def compute_flux_operator(points, neighbors, p: int, N: int, k: int | None = None, hybrid=None):
     """compute_flux_operator, compute_operators.jl:409-453 (k=None) and :549-594 (k-th derivative).
     Per point: shift_stencil (:225-246), rbf_block/poly_block (:191-223), Symmetric [R P; P' 0] (:265-267),
     rhs from mirror_stencil (:248-263) with the centre at (eps,eps), `M \\ rhs` (Bunch-Kaufman; scipy
@@ -203,7 +209,7 @@ def compute_flux_operator(points, neighbors, p: int, N: int, k: int | None = Non
     npts, nv = neighbors.shape
     exps = _monomial_exponents(N)
     npoly = len(exps)
-    phi, phi_x, phi_y = _phs_functions(p, k)
+    phi, phi_x, phi_y = _phs_functions(p, k, hybrid)
     kk = 1 if k is None else k
     Dx_loc = np.zeros((npts, nv))
     Dy_loc = np.zeros((npts, nv))

@@ -46,8 +46,9 @@ def setup_knn(points, k, queries=None):
     return nb - 1, d
 
 
-def setup_rbf_weights(points, neighbors, p, N, kk=1, scratch_bytes=0):
-    """emulated mft_setup_rbf_weights -> (wx, wy) (n,k); scratch_bytes > 0 forces small launches (chunking)"""
+def setup_rbf_weights(points, neighbors, p, N, kk=1, scratch_bytes=0, hybrid=None):
+    """emulated mft_setup_rbf_weights[_rows|_hybrid] -> (wx, wy) (n,k); scratch_bytes > 0 forces small launches (chunking);
+    hybrid = (alpha, beta, epsilon) selects the HybridGaussianPHS basis"""
     pts = np.ascontiguousarray(points, dtype=np.float64)
     n = len(pts)
     n_rows, k = neighbors.shape          # rows may be any subset / multiset of the points (their indices stay global)
@@ -55,6 +56,11 @@ def setup_rbf_weights(points, neighbors, p, N, kk=1, scratch_bytes=0):
     nb1 = np.ascontiguousarray(neighbors, dtype=np.int64) + 1
     wx = np.empty((n_rows, k))
     wy = np.empty((n_rows, k))
+    if hybrid is not None:
+        a, b, e = (float(v) for v in hybrid)
+        _check(lib().emu_setup_rbf_weights_hybrid(C.c_int64(n), _p(x), _p(y), C.c_int64(n_rows), C.c_int(k), _p(nb1), C.c_int(p),
+                                                  C.c_double(a), C.c_double(b), C.c_double(e), C.c_int(N), C.c_int(kk), _p(wx), _p(wy)))
+        return wx, wy
     _check(lib().emu_setup_rbf_weights(C.c_int64(n), _p(x), _p(y), C.c_int64(n_rows), C.c_int(k), _p(nb1), C.c_int(p), C.c_int(N),
                                        C.c_int(kk), _p(wx), _p(wy), C.c_int64(scratch_bytes)))
     return wx, wy

@@ -64,4 +64,11 @@ int emu_setup_rbf_weights(int64_t n, const double *x, const double *y, int64_t n
     if (scratch_bytes > 0) be.budget = (size_t)scratch_bytes;
     return mft_setup::run_weights(be, n, x, y, n_rows, k, nbr1, p, degree, kk, wx, wy, g_err);
 }
+int emu_setup_rbf_weights_hybrid(int64_t n, const double *x, const double *y, int64_t n_rows, int k, const int64_t *nbr1, int p, double alpha,
+                                 double beta, double epsilon, int degree, int kk, double *wx, double *wy)
+{
+    HostEmu be;
+    const double hyb[3] = {alpha, beta, epsilon};
+    return mft_setup::run_weights(be, n, x, y, n_rows, k, nbr1, p, degree, kk, wx, wy, g_err, hyb);
+}
 }

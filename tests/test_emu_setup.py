@@ -268,3 +268,28 @@ def test_weights_scale_exactly_with_a_power_of_two_dilation():
     vx, vy = emu.setup_rbf_weights(pts, nb, 5, 3, 2)
     v2x, v2y = emu.setup_rbf_weights(pts * 2.0, nb, 5, 3, 2)
     assert np.array_equal(v2x, vx / 4.0) and np.array_equal(v2y, vy / 4.0)
+
+
+@pytest.mark.parametrize("hyb,p,N,k", [((1.0, 1.0, 1.0), 3, 3, None), ((0.5, 2.0, 0.7), 5, 3, 2), ((2.0, 1.0, 1.5), 3, 2, None)])
+def test_hybrid_gaussian_phs_weights(hyb, p, N, k):
+    """RBF(HybridGaussianPHS(Nrbf, alpha, beta, epsilon)) (geometry_primatives.jl:117-132, 238-262): the emulated device
+    kernel and the host mirror against the oracle's symbolic restatement; polynomial reproduction still holds"""
+    import mft_b200 as m
+
+    s = cases.fixture_setup(p=p, N=N)
+    ref = orc.compute_flux_operator(s["points"], s["nb"], p, N, k, hybrid=hyb)
+    wx, wy = emu.setup_rbf_weights(s["points"], s["nb"], p, N, k or 1, hybrid=hyb)
+    hx, hy = m.setup_ops.rbf_fd_weights(s["points"], s["nb"], p, N, k, hybrid=hyb)
+    for w, h, B in zip((wx, wy), (hx, hy), ref):
+        A = m.setup_ops.assemble_csc(s["nb"], w)
+        H = m.setup_ops.assemble_csc(s["nb"], h)
+        assert np.array_equal(A.indices, B.indices)
+        assert np.abs(A.data - B.data).max() <= 1e-8 * np.abs(B.data).max()
+        assert np.abs(H.data - B.data).max() <= 1e-8 * np.abs(B.data).max()
+    phs = orc.compute_flux_operator(s["points"], s["nb"], p, N, k)
+    assert np.abs(phs[0].data - ref[0].data).max() > 1e-6 * np.abs(ref[0].data).max()      # really a different basis
+    if k is None:
+        X = s["points"][s["nb"], 0]
+        assert np.abs(wx.sum(axis=1)).max() <= 1e-9 * np.abs(wx).sum(axis=1).max() and np.abs((wx * X).sum(axis=1) - 1).max() <= 1e-8
+    basis = m.PointCloudBasis(m.Point2D(), N, approximation_type=m.RBF(m.HybridGaussianPHS(p, *hyb)))
+    assert m.api._hybrid_of(basis) == hyb and basis.approx_type.rbf_type.Nrbf == p

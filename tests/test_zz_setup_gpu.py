@@ -139,3 +139,18 @@ def test_device_knn_queries_and_weight_rows():
     assert np.array_equal(rx, wx[q]) and np.array_equal(ry, wy[q])
     with pytest.raises(m._lib.MftError, match="query index"):
         m.setup_ops.knn_queries_device(pts, np.array([4000]), 20)
+
+
+def test_device_hybrid_gaussian_phs_weights():
+    """mft_setup_rbf_weights_hybrid against the oracle and the host emulation (exp differs by an ulp between libm and CUDA:
+    1e-10 of the row scale instead of 1e-12)"""
+    m = _m()
+    hyb = (0.5, 2.0, 0.7)
+    s = cases.fixture_setup(p=5, N=3)
+    wx, wy = m.setup_ops.rbf_fd_weights_rows_device(s["points"], s["nb"], 5, 3, None, 0, hyb)
+    ref = orc.compute_flux_operator(s["points"], s["nb"], 5, 3, None, hybrid=hyb)
+    ex, ey = emu.setup_rbf_weights(s["points"], s["nb"], 5, 3, 1, hybrid=hyb)
+    for w, e, B in zip((wx, wy), (ex, ey), ref):
+        A = m.setup_ops.assemble_csc(s["nb"], w)
+        assert np.abs(A.data - B.data).max() <= 1e-8 * np.abs(B.data).max()
+        assert np.abs(w - e).max() <= 1e-10 * np.abs(e).max()
