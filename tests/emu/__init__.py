@@ -79,7 +79,7 @@ def limiter_zhang_shu(u, neighbors, thresholds, variables, gamma):
     return u
 
 
-def igr_apply(neighbors, wx, wy, alpha, maxiter, u, du):
+def igr_apply(neighbors, wx, wy, alpha, maxiter, u, du, b_out=None):
     """emulated launch_igr(): neighbors/wx/wy (n,k) with each row already in ascending-column order; u, du (4,n);
     du is updated in place.  Returns (sigma, (iterations, |r|, |r0|))"""
     nb = np.ascontiguousarray(neighbors, dtype=np.int64)
@@ -90,7 +90,7 @@ def igr_apply(neighbors, wx, wy, alpha, maxiter, u, du):
     sigma = np.empty(n)
     st = np.empty(3)
     rc = lib().emu_igr_apply(C.c_int64(n), C.c_int(k), _p(nb), _p(wx), _p(wy), C.c_double(alpha), C.c_int(maxiter), _p(u), _p(du),
-                             _p(sigma), _p(st))
+                             _p(sigma), _p(st), _p(b_out))
     if rc != 0:
         raise EmuError("emu_igr_apply failed")
     return sigma, (int(st[0]), float(st[1]), float(st[2]))

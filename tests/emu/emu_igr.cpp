@@ -60,7 +60,7 @@ void launch_plain(const IgrArgs &A, Body body)
 // reference's summation order (ascending column).  Builds the sliced-ELL blobs like build_ell() (padding -> dummy
 // record n with weight 0), runs the product's launch sequence, returns sigma, the updated du and the CG status.
 extern "C" int emu_igr_apply(int64_t n, int k, const int64_t *nbr0, const double *wx, const double *wy, double alpha, int maxiter,
-                             const double *u_soa, double *du_soa, double *sigma_out, double *status3)
+                             const double *u_soa, double *du_soa, double *sigma_out, double *status3, double *b_out /* nullable */)
 {
     const int64_t nsl = (n + 31) / 32;
     std::vector<int> off((size_t)nsl + 1);
@@ -126,6 +126,7 @@ extern "C" int emu_igr_apply(int64_t n, int k, const int64_t *nbr0, const double
     for (int64_t i = 0; i < n; ++i) {
         for (int q = 0; q < 4; ++q) du_soa[q * n + i] = du[i].a[q];
         sigma_out[i] = A.x[i];
+        if (b_out) b_out[i] = A.b[i];
     }
     status3[0] = S.iter;
     status3[1] = S.res;

@@ -106,12 +106,15 @@ def test_emulated_device_kernels_match_oracle(alpha_scale, maxiter):
     u = cases.ic_smooth_euler(fx["points"], 0.0)
     du0 = 0.01 * np.sin(3 * u)
     du = du0.copy()
-    sigma, (it, res, res0) = emu.igr_apply(nbs, wx, wy, alpha, maxiter, u, du)
+    b = np.empty(len(fx["points"]))
+    sigma, (it, res, res0) = emu.igr_apply(nbs, wx, wy, alpha, maxiter, u, du, b_out=b)
     src = orc.source_igr(alpha=alpha, maxiter=maxiter)
     P = orc.OracleProblem(fx["points"], 4, orc.EQ_EULER2D, [cases.GAMMA], ops[0], ops[1], [], [src])
     du_ref = du0.copy()
     P.apply_source(0, u, du_ref)
     sref = src.arrays["sigma"]
+    n = len(b)
+    assert np.array_equal(b, src.arrays["igr_work"][n:2 * n])      # update_igr_rhs!: same summation order -> bit-identical
     assert it == src.arrays["iters"]
     if maxiter == 0:
         assert np.array_equal(sigma, np.zeros_like(sigma)) and np.array_equal(du, du0)
