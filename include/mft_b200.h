@@ -240,7 +240,8 @@ int mft_setup_rbf_weights_hybrid(int device, int64_t n, const double *x, const d
 /* ---- Zhang-Shu positivity limiter (stage callback) ------------------------------------------------------
  * replaces Trixi.limiter_zhang_shu!(u, threshold, variable, domain::PointCloudDomain{2}, ...)
  * (src/callbacks_stage/positivity_zhang_shu_point2d.jl:22-82) and the (thresholds, variables) recursion of
- * PositivityPreservingLimiterZhangShu (src/callbacks_stage/positivity_zhang_shu.jl:29-72).  Euler 2-D, single GPU. */
+ * PositivityPreservingLimiterZhangShu (src/callbacks_stage/positivity_zhang_shu.jl:29-72).  Euler 2-D.  Multi-rank: every rank
+ * passes the stencils of its owned rows in local numbering and calls the limiter collectively (one u halo refresh per pass). */
 #define MFT_VAR_DENSITY 0   /* Trixi.density  */
 #define MFT_VAR_PRESSURE 1  /* Trixi.pressure */
 /* domain.pd.neighbors flattened: n_local x k row-major, 1-based, in the kNN list order (distance-sorted, self first) */

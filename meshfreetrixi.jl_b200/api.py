@@ -592,9 +592,15 @@ class PositivityPreservingLimiterZhangShu:
         """hand domain.pd.neighbors (list order = kNN order) to the library once per semidiscretization"""
         if semi._neighbors_set:
             return
-        if semi.partition is not None:
-            raise NotImplementedError("the Zhang-Shu limiter is single-GPU (as in the reference: PointCloudDomain{2} only)")
-        nbr1 = np.ascontiguousarray(semi.domain.pd.neighbors + 1, dtype=np.int64)
+        part = semi.partition
+        if part is None:
+            nbr = semi.domain.pd.neighbors
+        else:   # one rank of a partitioned cloud: stencils of the owned rows (global ids) in local [owned ; halo] numbering
+            lut = np.full(part.n_global, -1, dtype=np.int64)
+            lut[part.local_gid] = np.arange(part.n_local + part.n_halo)
+            nbr = lut[part.neighbors_owned]
+            assert (nbr >= 0).all()
+        nbr1 = np.ascontiguousarray(nbr + 1, dtype=np.int64)
         L.check(L.load().mft_set_neighbors(semi.ctx, L.ptr(nbr1)))
         semi._neighbors_set = True
 

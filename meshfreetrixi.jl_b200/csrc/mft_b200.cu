@@ -2342,7 +2342,6 @@ extern "C" int mft_set_neighbors(mft_ctx *c, const int64_t *nbr1)
 static int zs_prepare(mft_ctx *c)
 {
     if (c->V != 4 || c->eq != MFT_EQ_EULER2D) return fail(MFT_ENOTSUP, "Zhang-Shu limiter: Euler 2-D only");
-    if (c->nranks > 1) return fail(MFT_ENOTSUP, "Zhang-Shu limiter: multi-rank runs need a halo refresh per pass (not implemented)");
     if (c->host_nbr.empty()) return fail(MFT_EINVAL, "Zhang-Shu limiter: mft_set_neighbors was not called");
     if (c->zs_nbr.p) return MFT_OK;
     const int64_t n = c->n_local, k = c->k;
@@ -2368,6 +2367,10 @@ static int launch_limiter(mft_ctx *c, int npairs, const double *thresholds, cons
     const int64_t n = c->n_local;
     for (int i = 0; i < npairs; ++i) {
         if (variables[i] != ZS_VAR_DENSITY && variables[i] != ZS_VAR_PRESSURE) return fail(MFT_EINVAL, "Zhang-Shu limiter: unknown variable %d", variables[i]);
+        // multi-rank: the pass reads u at every stencil point of the owned rows -> refresh the halo copies first (the stage
+        // update / the previous pass changed the owners' values).  Same exchange as at the start of rhs!; the credit protocol
+        // of the peer-memory path allows any stream-ordered sequence of exchanges as long as all ranks issue the same one.
+        CHECK(halo_exchange<4>(c, c->u.p));
         ZsArgs a{c->zs_nbr.p, c->k, n, c->u.p, c->zs_tmp.p, c->zs_flag.p, thresholds[i], c->eqp[0], variables[i]};
         k_zs_detect<<<grid_for(n, 128), 128, 0, c->stream>>>(a);
         k_zs_apply<<<grid_for(n, 256), 256, 0, c->stream>>>(n, c->zs_flag.p, c->zs_tmp.p, c->u.p);

@@ -80,11 +80,18 @@ def main():
         hops = m.setup_ops.compute_flux_operator(cl.points, nb, PHS, 3, 4)
         src_o = orc.OracleSource(kind=orc.SRC_HV_FLYER, hv=orc.JuliaCSC((hops[0] + hops[1]).tocsc()), gamma=1.0 * dx_min ** 4)
     else:
-        src_o = orc.source_upwind(dx_avg) if args.source == "upwind" else orc.source_residual(dx_avg, polydeg=3)
+        src_o = orc.source_residual(dx_avg, polydeg=3) if args.source == "residual" else orc.source_upwind(dx_avg)
     P = orc.OracleProblem(cl.points, 4, orc.EQ_EULER2D, [GAMMA], ops[0], ops[1], obc, [src_o])
     u0 = ic(cl.points, 0.0) * (1.0 + 0.01 * np.sin(cl.points[:, 0]))
     u_ser = u0.copy()
     du_ser = P.rhs(u_ser, 0.0)
+
+    # Zhang-Shu limiter case: a state with low-density / low-pressure pockets, limited serially on the global cloud
+    LIM_THR, LIM_VAR = (0.6, 5.0), (orc.VAR_DENSITY, orc.VAR_PRESSURE)
+    u_lim0 = u0.copy()
+    u_lim0[0, 100:160] *= 0.3
+    u_lim0[3, 900:960] *= 0.1
+    u_lim_ser = orc.limiter_zhang_shu(u_lim0.copy(), nb, LIM_THR, LIM_VAR, GAMMA)
 
     results = {}
     if args.mode == "cpu":
@@ -113,6 +120,45 @@ def main():
             u[:, bi] = ic(part.points[bi], 0.0)
         exchange(dist, part, u)
         assert np.array_equal(u, u_ser[:, gid])             # halo copies carry the owner's BC-imposed values
+        if args.source == "limiter":
+            # multi-rank limiter ALGORITHM: per (threshold, variable) pass one u halo refresh, then the owned rows are limited
+            # from their global stencils in local numbering (what mft_limiter_zhang_shu does on every rank)
+            lut = np.full(len(cl.points), -1, dtype=np.int64)
+            lut[gid] = np.arange(len(gid))
+            nbl = lut[part.neighbors_owned]
+            assert (nbl >= 0).all()
+            w = np.ascontiguousarray(u_lim0[:, gid])
+            w[:, nl:] = np.nan
+            for thr, var in zip(LIM_THR, LIM_VAR):
+                exchange(dist, part, w)
+                val = (lambda q: q[0]) if var == orc.VAR_DENSITY else (lambda q: (GAMMA - 1) * (q[3] - 0.5 * (q[1] * q[1] + q[2] * q[2]) / q[0]))
+                vmin = np.min(np.stack([val(w[:, nbl[:, q]]) for q in range(nbl.shape[1])]), axis=0)
+                mean = np.zeros((4, nl))
+                for q in range(nbl.shape[1]):
+                    mean = mean + w[:, nbl[:, q]]
+                mean = mean / nbl.shape[1]
+                lim = vmin < thr
+                vm = val(mean)
+                with np.errstate(all="ignore"):
+                    theta = (vm - thr) / (vm - vmin)
+                    new = theta * w[:, :nl] + (1 - theta) * mean
+                w[:, :nl] = np.where(lim & (new != 0).any(axis=0), new, w[:, :nl])
+            ref = u_lim_ser[:, part.owned_gid]
+            err = float(np.abs(w[:, :nl] - ref).max() / np.abs(ref).max())
+            changed = int((ref != u_lim0[:, part.owned_gid]).any(axis=0).sum())
+            assert err < 1e-14, err                      # fma vs separate rounding in the blend only
+            results = dict(rank=rank, n_local=nl, n_halo=part.n_halo, err=err, changed=changed)
+            allres = comm.allgather(results)
+            assert sum(r["changed"] for r in allres) > 50
+            if rank == 0:
+                print("MULTI_RANK_OK", allres)
+                if args.out:
+                    import json
+
+                    json.dump(allres, open(args.out, "w"))
+            dist.barrier()
+            dist.destroy_process_group()
+            return
         F, G, (v1, v2, p) = euler_flux(u)
         Dx, Dy = part.ops[0].tocsr(), part.ops[1].tocsr()
         du = np.stack([-(Dx[:nl] @ F[v]) - (Dy[:nl] @ G[v]) for v in range(4)])
@@ -171,7 +217,7 @@ def main():
         part = domain.partition
         eq = m.CompressibleEulerEquations2D(GAMMA)
         bc = {k: m.BoundaryConditionDirichlet(ic) for k in names}
-        if args.source == "upwind":
+        if args.source in ("upwind", "limiter"):
             srcs = m.SourceTerms(rv=m.SourceUpwindViscosityTominec(solver, eq, domain))
         elif args.source == "flyer":
             srcs = m.SourceTerms(hv=m.SourceHyperviscosityFlyer(solver, eq, domain, k=2, c=1.0))
@@ -180,6 +226,45 @@ def main():
         semi = m.SemidiscretizationHyperbolic(domain, eq, ic, solver, boundary_conditions=bc, source_terms=srcs)
         gid = part.local_gid
         nl = part.n_local
+        if args.source == "limiter":
+            # collective limiter call on every rank, owned rows bit-identical to the serial oracle (same fma blend)
+            lim = m.PositivityPreservingLimiterZhangShu(thresholds=LIM_THR, variables=(m.density, m.pressure))
+            w = np.ascontiguousarray(u_lim0[:, gid])
+            w[:, nl:] = 0.0
+            lim(w, semi)
+            assert np.array_equal(w[:, :nl], u_lim_ser[:, part.owned_gid])
+            # and as SSPRK33 stage limiter inside the (graph-replayed) multi-GPU step, against the serial loop
+            import ctypes as C
+
+            thr1, var1 = (0.9,), (orc.VAR_DENSITY,)
+            lim1 = m.PositivityPreservingLimiterZhangShu(thresholds=thr1, variables=(m.density,))
+            dt = 0.1 * dx_min / 8.0
+            ode = m.ODEProblem(np.ascontiguousarray(u0[:, gid]), (0.0, 4 * dt), semi)
+            sol = m.solve(ode, m.SSPRK33(stage_limiter=lim1), dt=dt, nsteps=4)
+            lib = orc.lib()
+            us = u0.copy()
+            k = P.rhs(us, 0.0)
+            for _ in range(4):
+                uprev = us.copy()
+                for st in (1, 2, 3):
+                    lib.orc_ssprk33_stage(C.c_int64(us.size), st, C.c_double(dt), C.c_void_p(uprev.ctypes.data),
+                                          C.c_void_p(k.ctypes.data), C.c_void_p(us.ctypes.data))
+                    orc.limiter_zhang_shu(us, nb, thr1, var1, GAMMA)
+                    k = P.rhs(us, 0.0)
+            err2 = max(np.abs(sol.u[v, :nl] - us[v, part.owned_gid]).max() / np.abs(us[v]).max() for v in range(4))
+            assert err2 < 1e-9, err2
+            results = dict(rank=rank, n_local=nl, n_halo=part.n_halo, err=0.0, err_steps=float(err2))
+            semi.close()
+            allres = comm.allgather(results)
+            if rank == 0:
+                print("MULTI_RANK_OK", allres)
+                if args.out:
+                    import json
+
+                    json.dump(allres, open(args.out, "w"))
+            dist.barrier()
+            dist.destroy_process_group()
+            return
         u = np.ascontiguousarray(u0[:, gid])
         u[:, nl:] = 0.0
         du = np.zeros_like(u)

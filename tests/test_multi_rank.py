@@ -46,6 +46,13 @@ def test_flyer_hyperviscosity_on_a_partition_world2_gloo(tmp_path):
     assert len(res) == 2 and all(r["n_halo"] > 0 and r["err"] < 1e-12 for r in res)
 
 
+def test_limiter_on_a_partition_world2_gloo(tmp_path):
+    """Zhang-Shu limiter on a partitioned cloud: one u halo refresh per (threshold, variable) pass, owned rows limited from
+    their global stencils -- equals the serial limiter on the global cloud"""
+    res = _launch(2, "cpu", "limiter", str(tmp_path))
+    assert len(res) == 2 and all(r["err"] < 1e-14 for r in res)
+
+
 def test_partition_world3_gloo(tmp_path):
     res = _launch(3, "cpu", "upwind", str(tmp_path))
     assert len(res) == 3 and all(r["err"] < 1e-12 for r in res)
@@ -77,6 +84,16 @@ def test_many_gpus_p2p_match_serial_oracle(tmp_path, nproc):
         pytest.skip(f"needs {nproc} GPUs (run under gpurun --gpus {nproc})")
     res = _launch(nproc, "gpu", "residual", str(tmp_path), timeout=300, exchange="p2p")
     assert len(res) == nproc and all(r["err"] < 1e-12 and r["err_steps"] < 1e-9 for r in res)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_two_gpus_limiter_matches_serial_oracle(tmp_path, exchange):
+    """collective mft_limiter_zhang_shu (bit-identical owned rows) and the stage limiter inside the multi-GPU SSPRK33 step"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    res = _launch(2, "gpu", "limiter", str(tmp_path), timeout=240, exchange=exchange)
+    assert all(r["err"] == 0.0 and r["err_steps"] < 1e-9 for r in res)
 
 
 @pytest.mark.gpu
