@@ -293,3 +293,32 @@ def test_hybrid_gaussian_phs_weights(hyb, p, N, k):
         assert np.abs(wx.sum(axis=1)).max() <= 1e-9 * np.abs(wx).sum(axis=1).max() and np.abs((wx * X).sum(axis=1) - 1).max() <= 1e-8
     basis = m.PointCloudBasis(m.Point2D(), N, approximation_type=m.RBF(m.HybridGaussianPHS(p, *hyb)))
     assert m.api._hybrid_of(basis) == hyb and basis.approx_type.rbf_type.Nrbf == p
+
+
+def test_weights_differentiate_a_smooth_function_with_the_expected_order():
+    """independent of the oracle: Dx, Dy from the emulated device kernel applied to sin(x) cos(y) converge like h^N (interior
+    points of jittered clouds, PHS r^5 + polynomials of degree N = 3: halving h cuts the error by ~2^3 or better)"""
+    import mft_b200 as m
+
+    errs = []
+    for n_side in (24, 48, 96):
+        cl = m.cloud.jittered_lattice(n_side, n_side, 2.0, 2.0, seed=7).points
+        nb, _ = emu.setup_knn(cl, 20)
+        wx, wy = emu.setup_rbf_weights(cl, nb, 5, 3, 1)
+        f = np.sin(cl[:, 0]) * np.cos(cl[:, 1])
+        fx = (wx * f[nb]).sum(axis=1)
+        fy = (wy * f[nb]).sum(axis=1)
+        inner = np.all((cl > 0.3) & (cl < 1.7), axis=1)          # one-sided boundary stencils converge a bit slower
+        ex = np.abs(fx - np.cos(cl[:, 0]) * np.cos(cl[:, 1]))[inner].max()
+        ey = np.abs(fy + np.sin(cl[:, 0]) * np.sin(cl[:, 1]))[inner].max()
+        errs.append(max(ex, ey))
+    assert errs[0] < 1e-3 and errs[2] < errs[1] < errs[0]
+    assert errs[0] / errs[1] > 6.0 and errs[1] / errs[2] > 6.0, errs
+    # second derivatives (k = 2): Laplacian of the same function, order N - 1
+    cl = m.cloud.jittered_lattice(96, 96, 2.0, 2.0, seed=7).points
+    nb, _ = emu.setup_knn(cl, 20)
+    wxx, wyy = emu.setup_rbf_weights(cl, nb, 5, 3, 2)
+    f = np.sin(cl[:, 0]) * np.cos(cl[:, 1])
+    lap = ((wxx + wyy) * f[nb]).sum(axis=1)
+    inner = np.all((cl > 0.3) & (cl < 1.7), axis=1)
+    assert np.abs(lap + 2 * f)[inner].max() < 5e-3
