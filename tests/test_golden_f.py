@@ -59,3 +59,28 @@ def test_emulated_limiter_and_igr_kernels_reproduce_golden():
     sigma, (it, _, _) = emu.igr_apply(nbs, wx, wy, float(GF["igr_alpha"]), mg.IGR_MAXITER, u0, np.zeros_like(u0))
     assert it == int(GF["igr_iters"])
     assert np.abs(sigma - GF["igr_sigma"]).max() <= 1e-9 * np.abs(GF["igr_sigma"]).max()
+
+
+def test_oracle_reproduces_advection_config_golden():
+    """BASELINE configs[0] (advection + both hyperviscosity sources on the fixture cloud, 100 SSPRK33 steps) from the stored
+    r^5 weight tables"""
+    fx5 = cases.fixture_setup(p=5, N=3)
+    nb = G["neighbors"].astype(np.int64)
+    P, gam = mg.advection_problem(fx5, nb, GF)
+    assert gam == (float(GF["adv_gamma_flyer"]), float(GF["adv_gamma_tominec"]))
+    u = cases.ic_bump_advection(fx5["points"], 0.0)
+    du = P.rhs(u, 0.0)
+    assert np.array_equal(u, GF["adv_rhs_u"]) and cases.relerr(du, GF["adv_rhs_du"]) < 1e-13
+    u_end, _ = P.solve_ssprk33(cases.ic_bump_advection(fx5["points"], 0.0), 0.0, float(GF["adv_dt"]), 100)
+    assert cases.relerr(u_end, GF["adv_steps100_u"]) < 1e-12
+
+
+def test_emulated_weight_kernel_reproduces_the_stored_r5_tables():
+    pts = cases.orc.read_medusa_file(cases.FIXTURE)[0]
+    nb = G["neighbors"].astype(np.int64)
+    wx, wy = emu.setup_rbf_weights(pts, nb, 5, 3, 1)
+    assert np.abs(wx - GF["wx5"]).max() <= 1e-8 * np.abs(GF["wx5"]).max() and np.abs(wy - GF["wy5"]).max() <= 1e-8 * np.abs(GF["wy5"]).max()
+    lx, ly = emu.setup_rbf_weights(pts, nb, 5, 3, 2)
+    assert np.abs(lx + ly - GF["lap"]).max() <= 1e-8 * np.abs(GF["lap"]).max()
+    hx, hy = emu.setup_rbf_weights(pts, nb, 5, 3, 4)
+    assert np.abs(hx + hy - GF["h4"]).max() <= 1e-5 * np.abs(GF["h4"]).max()     # 4th derivatives of r^5 at (eps,eps): SURVEY appendix A.8

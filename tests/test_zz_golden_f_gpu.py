@@ -67,3 +67,30 @@ def test_device_igr_rhs_reproduces_golden():
     assert np.abs(sigma - GF["igr_sigma"]).max() <= 1e-9 * np.abs(GF["igr_sigma"]).max()
     assert semi.source_terms.igr.cache.igr_status[0] == int(GF["igr_iters"])
     semi.close()
+
+
+def test_device_advection_config_reproduces_golden():
+    """BASELINE configs[0] on the CUDA path from the stored r^5 tables: rhs! bit-identical, 100 SSPRK33 steps to 1e-9"""
+    import mft_b200 as m
+
+    nb = G["neighbors"].astype(np.int64)
+    D, Hf, Ht = mg.advection_matrices(nb, GF)
+    basis = m.PointCloudBasis(m.Point2D(), 3, approximation_type=m.RBF(m.PolyharmonicSpline(5)))
+    solver = m.PointCloudSolver(basis)
+    domain = m.PointCloudDomain(solver, cases.FIXTURE, cases.BOUNDARY_NAMES)
+    eq = m.LinearScalarAdvectionEquation2D(1.0, 0.5)
+    ic = cases.ic_bump_advection
+    bc = dict(inlet=m.BoundaryConditionDirichlet(ic), outlet=m.BoundaryConditionDoNothing(),
+              top=m.BoundaryConditionDoNothing(), bottom=m.BoundaryConditionDoNothing(), cyl=m.BoundaryConditionDoNothing())
+    hv, hv2 = object.__new__(m.SourceHyperviscosityFlyer), object.__new__(m.SourceHyperviscosityTominec)
+    hv.hv_differentiation_matrix, hv.gamma, hv.c = Hf, float(GF["adv_gamma_flyer"]), 1.0      # matrices from the golden tables,
+    hv2.hv_differentiation_matrix, hv2.gamma, hv2.c = Ht, float(GF["adv_gamma_tominec"]), 1.0  # not regenerated here
+    semi = m.SemidiscretizationHyperbolic(domain, eq, ic, solver, boundary_conditions=bc,
+                                          source_terms=m.SourceTerms(hv=hv, hv2=hv2), operators=D)
+    u = ic(domain.pd.points, 0.0)
+    du = np.empty_like(u)
+    m.rhs_(du, u, semi, 0.0)
+    assert np.array_equal(u, GF["adv_rhs_u"]) and np.array_equal(du, GF["adv_rhs_du"])
+    sol = m.solve(m.semidiscretize(semi, (0.0, 100 * float(GF["adv_dt"]))), m.SSPRK33(), dt=float(GF["adv_dt"]), nsteps=100)
+    assert cases.relerr(sol.u, GF["adv_steps100_u"]) <= 1e-9
+    semi.close()
