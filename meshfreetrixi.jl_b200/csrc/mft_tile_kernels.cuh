@@ -18,6 +18,15 @@ namespace mft {
 
 constexpr int kTileWarps = 4;
 
+// minimum resident blocks per SM the compiler must allow for the R = 1 tile kernels (register cap = 65536 / (128 x blocks)).
+// Experiment knobs: MFT_NVCC_EXTRA="-DMFT_TILE_OCC_A=6 -DMFT_TILE_OCC_B=5" python meshfreetrixi.jl_b200/build.py --force
+#ifndef MFT_TILE_OCC_A
+#define MFT_TILE_OCC_A 4
+#endif
+#ifndef MFT_TILE_OCC_B
+#define MFT_TILE_OCC_B 4
+#endif
+
 __device__ __forceinline__ double2 lds2(const unsigned char *arr, uint32_t off)
 {
     return *reinterpret_cast<const double2 *>(arr + off);
@@ -111,7 +120,7 @@ __device__ __forceinline__ void tile_pf_issue(const TileROp &T, const TilePf &p,
 }
 
 template <int R, bool EXACT, bool DO_FLUX, int VISC, bool STAGE_W>
-__global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)) k_pass_a_tiler(const PassAArgs A, const TileROp T)
+__global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R == 2 ? 3 : 2)) k_pass_a_tiler(const PassAArgs A, const TileROp T)
 {
     static_assert(EXACT || !STAGE_W, "staged weights: exact-order (two sweep) mode only");
     constexpr int V = 4;
@@ -355,7 +364,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)
 // STAGE_W: two sweeps (the x chain with wx_* over arrays A,B, then the y chain with wy_* over C,D -- the chains are
 // independent, so splitting them changes no sum), each with its weight blocks staged like pass A.
 template <int R, bool EXACT, bool STAGE_W>
-__global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? 4 : R == 2 ? 3 : 2)) k_pass_b_tiler(const PassBTileArgs A, const TileROp T)
+__global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_B : R == 2 ? 3 : 2)) k_pass_b_tiler(const PassBTileArgs A, const TileROp T)
 {
     constexpr int V = 4;
     extern __shared__ __align__(128) unsigned char smem_dyn[];
