@@ -17,3 +17,11 @@ ls -la gpurun_out/
 python bench.py --source upwind --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_vortex_upwind.log 2>&1; tail -c 400 gpurun_out/bench_vortex_upwind.log
 python bench.py --workload sod --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_sod_rv.log 2>&1; tail -c 400 gpurun_out/bench_sod_rv.log
 bash tools/sanitize.sh
+# occupancy experiment: 6 / 5 resident CTAs per SM for the tile kernels (no spills per ptxas)
+for occ in "6 5" "6 4" "5 5"; do
+  set -- $occ
+  MFT_NVCC_EXTRA="-DMFT_TILE_OCC_A=$1 -DMFT_TILE_OCC_B=$2" python meshfreetrixi.jl_b200/build.py --force > /dev/null 2>&1
+  python bench.py --no-cpu-baseline > gpurun_out/bench_occ_$1_$2.log 2>&1
+  python -c "import json,sys; d=json.loads(open('gpurun_out/bench_occ_$1_$2.log').read().strip().splitlines()[-1]); print('occ $1 $2', d['value'], d['roofline']['kernel_ms_per_step'])"
+done
+python meshfreetrixi.jl_b200/build.py --force > /dev/null 2>&1   # back to the default build
