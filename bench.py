@@ -314,7 +314,10 @@ def run_ours(args):
                           "partition": "single GPU" if not multi else f"Hilbert-curve ranges over {world} ranks, halo exchange (u, g) + global norms per stage via {'NVLink peer-memory puts (CUDA IPC), graph-replayed' if args.exchange == 'p2p' else 'NCCL send/recv + all-gather'}",
                           "l2": "inputs larger than L2 (operators 2 x %.0f MB per GPU streamed every stage)" % (n_own * 20 * k / 1e6),
                           "setup_s": round(t_setup, 1), "setup": args.setup},
-               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+               # the reference's own (printed, never recorded) metric: PerformanceCallback's performance index
+               # PID = runtime * nranks / (ndofsglobal * ncalls_rhs), src/callbacks_step/performance.jl:229-235 (one DOF = one point)
+               "reference_native_metric": {"name": "PID [s per DOF per rhs! per rank]", "value": world / value}}
         print(json.dumps(out))
     semi.close()
     if multi:
