@@ -104,3 +104,65 @@ def test_two_gpus_device_setup_match_serial_oracle(tmp_path):
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     res = _launch(2, "gpu", "residual", str(tmp_path), timeout=240, exchange="p2p", setup="device")
     assert all(r["err"] < 1e-9 and r["err_steps"] < 1e-8 for r in res)
+
+
+@pytest.mark.parametrize("nranks,shape", [(1, (40, 30)), (4, (64, 48)), (5, (50, 70)), (8, (96, 64))])
+def test_partition_planner_invariants(nranks, shape):
+    """host planner on 1/4/5/8 ranks (threads stand in for the ranks; the planner only needs an allgather): ownership is a
+    partition of the cloud, every stencil column of an owned row is local, halo blocks are grouped by owner, and the send
+    lists of one rank are exactly what its peers expect to receive, in the receivers' halo order"""
+    import threading
+
+    import numpy as np
+
+    import mft_b200 as m
+    from mft_b200 import partition
+
+    cl = m.cloud.jittered_lattice(shape[0], shape[1], 10.0, 10.0 * shape[1] / shape[0], seed=3)
+    nb_g, dx_min, dx_avg = cases.orc.point_data(cl.points, 20)
+    barrier, slots, parts, errs = threading.Barrier(nranks), [None] * nranks, [None] * nranks, []
+
+    def work(r):
+        def allgather(obj):
+            slots[r] = obj
+            barrier.wait()
+            out = list(slots)
+            barrier.wait()
+            return out
+        try:
+            parts[r] = partition.build_rank_partition(cl.points, [np.asarray(b) for b in cl.boundary_idxs], cl.boundary_normals,
+                                                      r, nranks, 3, 3, 20, allgather)
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+            barrier.abort()
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    owned = np.concatenate([p.owned_gid for p in parts])
+    assert len(owned) == len(cl.points) == len(np.unique(owned))
+    sizes = [p.n_local for p in parts]
+    assert max(sizes) - min(sizes) <= 1                                   # contiguous equal ranges of the curve
+    owner_of = np.empty(len(cl.points), dtype=np.int64)
+    for p in parts:
+        owner_of[p.owned_gid] = p.rank
+    for p in parts:
+        assert p.dx_min == dx_min and abs(p.dx_avg - dx_avg) <= 1e-15
+        assert np.array_equal(p.neighbors_owned, nb_g[p.owned_gid])      # global stencils, bit-identical tables
+        local = set(p.local_gid.tolist())
+        assert set(np.unique(p.neighbors_owned).tolist()) <= local       # every column of an owned row is local
+        assert np.array_equal(owner_of[p.halo_gid], p.halo_owner) and (np.diff(p.halo_owner) >= 0).all()
+        assert (p.halo_owner != p.rank).all()
+        off = 0
+        for q, cnt in zip(p.peers, p.recv_count):
+            want = p.halo_gid[off:off + cnt]
+            assert (p.halo_owner[off:off + cnt] == q).all()
+            sender = parts[q]
+            i = sender.peers.index(p.rank)
+            assert np.array_equal(sender.owned_gid[sender.send_idx[i]], want)   # what q sends is what p expects, in order
+            off += cnt
+        assert off == p.n_halo
+        # boundary points: each global boundary point belongs to exactly one rank's list
+    for g in range(4):
+        got = np.concatenate([p.owned_gid[p.boundary_idxs[g]] for p in parts])
+        assert np.array_equal(np.sort(got), np.sort(cl.boundary_idxs[g]))
