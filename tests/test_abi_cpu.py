@@ -78,3 +78,18 @@ def test_union_tile_format_replays_bit_exact(R, layout, with_perm):
             assert st[0] <= plain[0] + 1e-12
             if layout and not (R == 4 and layout == 2):   # R = 4 has no copy-select bit
                 assert st[0] < 0.95 * plain[0]
+
+
+def test_union_tile_format_at_the_edge_sizes_of_the_gpu_tests():
+    """the host layout builder at the cloud sizes tests/test_zzz_edge_sizes_gpu.py runs on hardware (below one slice, below
+    one tile, straddling the 32-row and 128-row boundaries) and the stencil widths of the sweep"""
+    m = _mft()
+    lib = m._lib.load()
+    st = (C.c_double * 4)()
+    for n in (21, 26, 33, 45, 96, 128, 129, 140, 165, 220, 257, 285, 302):
+        for k in (13, 15, 20, 30, 42):
+            if k > n:
+                continue
+            for layout in (0, 3):
+                for perm in (0, 1):
+                    assert lib.mft_debug_tile_selftest(n, k, 1, layout, perm, 7 + n, st) == 0, (n, k, layout, perm, lib.mft_last_error())
