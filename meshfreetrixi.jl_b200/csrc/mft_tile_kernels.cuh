@@ -16,7 +16,12 @@
 
 namespace mft {
 
-constexpr int kTileWarps = 4;
+// warps (= 32-row slices) per tile.  Experiment knob: MFT_NVCC_EXTRA="-DMFT_TILE_WARPS=8" -> 256-row tiles (smaller union per
+// row, twice the shared memory per block); the host layout builder and its selftest follow the constant.
+#ifndef MFT_TILE_WARPS
+#define MFT_TILE_WARPS 4
+#endif
+constexpr int kTileWarps = MFT_TILE_WARPS;
 
 // minimum resident blocks per SM the compiler must allow for the R = 1 tile kernels (register cap = 65536 / (128 x blocks)).
 // Experiment knobs: MFT_NVCC_EXTRA="-DMFT_TILE_OCC_A=6 -DMFT_TILE_OCC_B=5" python meshfreetrixi.jl_b200/build.py --force

@@ -24,4 +24,9 @@ for occ in "6 5" "6 4" "5 5"; do
   python bench.py --no-cpu-baseline > gpurun_out/bench_occ_$1_$2.log 2>&1
   python -c "import json,sys; d=json.loads(open('gpurun_out/bench_occ_$1_$2.log').read().strip().splitlines()[-1]); print('occ $1 $2', d['value'], d['roofline']['kernel_ms_per_step'])"
 done
+# 256-row tiles
+MFT_NVCC_EXTRA="-DMFT_TILE_WARPS=8 -DMFT_TILE_OCC_A=3 -DMFT_TILE_OCC_B=2" python meshfreetrixi.jl_b200/build.py --force > /dev/null 2>&1
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/tile8_pytest.log 2>&1; tail -1 gpurun_out/tile8_pytest.log
+python bench.py --no-cpu-baseline > gpurun_out/bench_tile8.log 2>&1
+python -c "import json; d=json.loads(open('gpurun_out/bench_tile8.log').read().strip().splitlines()[-1]); print('tile8', d['value'], d['roofline']['kernel_ms_per_step'])"
 python meshfreetrixi.jl_b200/build.py --force > /dev/null 2>&1   # back to the default build
