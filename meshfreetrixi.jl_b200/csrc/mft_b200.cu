@@ -256,7 +256,7 @@ struct mft_ctx {
 // misc
 // ------------------------------------------------------------------------------------------------------
 extern "C" const char *mft_last_error(void) { return g_err.c_str(); }
-extern "C" int mft_version(void) { return 100; }
+extern "C" int mft_version(void) { return 110; }  // 1.1: setup pipeline, limiter, IGR source, non-finite check
 extern "C" int mft_device_count(void)
 {
     int n = 0;
