@@ -14,7 +14,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",              # FMAs only where the source says fma() (mirrors the reference's @muladd scope)
-    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-pthread",   # host threads: layout builders
     "-cudart", "static",
 ]
 

@@ -11,12 +11,16 @@
 #include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: a no-op unless a profiler injects itself
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace mft;
@@ -882,11 +886,45 @@ struct HostTileR {
     std::vector<unsigned short> uslot;
 };
 
+// Run fn(worker) on `nthreads` host threads (the caller's thread is worker 0) and wait for all of them.
+template <class F>
+static void host_parallel(int nthreads, F fn)
+{
+    std::vector<std::thread> pool;
+    for (int w = 1; w < nthreads; ++w) pool.emplace_back([&fn, w]() { fn(w); });
+    fn(0);
+    for (auto &th : pool) th.join();
+}
+
+// host threads for the layout builders: MFT_HOST_THREADS, else the hardware concurrency (at most 64)
+static int host_threads(int64_t work_items)
+{
+    int n = 0;
+    if (const char *e = getenv("MFT_HOST_THREADS")) n = atoi(e);
+    if (n <= 0) n = (int)std::thread::hardware_concurrency();
+    n = std::max(1, std::min(n, 64));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(n, work_items));
+}
+
+// state of x -> a x + c (mod 2^64) after `k` more steps (jump-ahead by repeated squaring of the affine map)
+static inline uint64_t lcg_jump(uint64_t x, uint64_t k)
+{
+    uint64_t cur_a = 6364136223846793005ULL, cur_c = 1442695040888963407ULL, acc_a = 1, acc_c = 0;
+    for (; k; k >>= 1) {
+        if (k & 1) {
+            acc_a *= cur_a;
+            acc_c = acc_c * cur_a + cur_c;
+        }
+        cur_c = (cur_a + 1) * cur_c;
+        cur_a *= cur_a;
+    }
+    return acc_a * x + acc_c;
+}
+
 static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, int R, bool colour, bool two_copies, HostTileR &out)
 {
     if (R > 2) two_copies = false;  // the copy-select bit (14) is a row-mask bit for R = 4
-    uint64_t lcg = 0x9e3779b97f4a7c15ULL;
-    std::vector<int> slot1;
+    const uint64_t lcg0 = 0x9e3779b97f4a7c15ULL;
     const int64_t rows_per_slice = (int64_t)kSlice * R, rows_per_tile = rows_per_slice * kTileWarps;
     const int64_t nsl = (nrows_dev + rows_per_slice - 1) / rows_per_slice;
     const int64_t ntl = (nrows_dev + rows_per_tile - 1) / rows_per_tile;
@@ -901,40 +939,34 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
     boff.assign(nsl, 0);
     wl.assign(2 * nsl, 0);
     uoff.assign(ntl + 1, 0);
-    ulist.clear();
-    uslot.clear();
-    blob.clear();
-    std::vector<int> cols;
-    std::vector<int> node_of((size_t)c->n_tot + 1, -1);
-    blob.reserve((size_t)nrows_dev * 20 * 18);
     struct Step { int node; unsigned mask; };
-    std::vector<std::vector<Step>> lanes((size_t)kTileWarps * kSlice);
-    std::vector<unsigned short> adj;   // nu x nu co-request counts
-    std::vector<int> slot, order, bank, deg, grp, nb_ptr, nb_idx, nb_w;
-    int max_slot = 0, maxW = 0, maxL = 0;
-    int64_t nnz = 0, nsteps = 0;
-    for (int64_t t = 0; t < ntl; ++t) {
+    // per-thread scratch of one tile
+    struct Scratch {
+        std::vector<int> cols;                   // the tile's union: sorted device columns (node q = cols[q])
+        std::vector<std::vector<Step>> lanes;    // step lists of the tile's lanes
+        std::vector<unsigned short> adj;         // nu x nu co-request counts
+        std::vector<int> slot, slot1, order, bank, deg, grp, nb_ptr, nb_idx, nb_w;
+    };
+    // union of the tile's stencils (sorted) + the lane step lists of its slices (R-way merge by summation key);
+    // returns the number of stored entries of the tile's rows
+    auto tile_lanes = [&](int64_t t, Scratch &S) -> int64_t {
         const int64_t d0 = t * rows_per_tile, d1 = std::min(nrows_dev, d0 + rows_per_tile);
+        std::vector<int> &cols = S.cols;
         cols.clear();
         for (int64_t d = d0; d < d1; ++d) {
             const int64_t r = caller_row(d);
-            for (int64_t p = A.ptr[r]; p < A.ptr[r + 1]; ++p) {
-                const int j = dev_col(A.col[p]);
-                if (node_of[j] < 0) {
-                    node_of[j] = 0;
-                    cols.push_back(j);
-                }
-            }
+            for (int64_t p = A.ptr[r]; p < A.ptr[r + 1]; ++p) cols.push_back(dev_col(A.col[p]));
         }
         std::sort(cols.begin(), cols.end());
-        const int nu = (int)cols.size();
-        for (int q = 0; q < nu; ++q) node_of[cols[q]] = q;
-        // lane step lists of the tile's slices: R-way merge by summation key
+        cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+        auto node_of = [&](int j) -> int { return (int)(std::lower_bound(cols.begin(), cols.end(), j) - cols.begin()); };
         const int64_t s0 = d0 / rows_per_slice;
         const int ns_tile = (int)((d1 - d0 + rows_per_slice - 1) / rows_per_slice);
+        S.lanes.resize((size_t)kTileWarps * kSlice);
+        int64_t nnz = 0;
         for (int si = 0; si < ns_tile; ++si)
             for (int l = 0; l < kSlice; ++l) {
-                std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
+                std::vector<Step> &U = S.lanes[(size_t)si * kSlice + l];
                 U.clear();
                 int64_t pp[4], ee[4];
                 for (int r = 0; r < R; ++r) {
@@ -953,7 +985,7 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
                         if (pp[r] < ee[r] && (best < 0 || key(A.col[pp[r]]) < key(A.col[pp[best]]))) best = r;
                     if (best < 0) break;
                     const int32_t col = A.col[pp[best]];
-                    Step st{node_of[dev_col(col)], 0u};
+                    Step st{node_of(dev_col(col)), 0u};
                     for (int r = 0; r < R; ++r)
                         if (pp[r] < ee[r] && A.col[pp[r]] == col) {
                             st.mask |= 1u << r;
@@ -962,181 +994,265 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
                     U.push_back(st);
                 }
             }
-        // slots
-        slot.assign(nu, 0);
-        int nslots = nu;
-        if (!colour || nu <= NB) {
-            for (int q = 0; q < nu; ++q) slot[q] = q;
-        } else {
-            adj.assign((size_t)nu * nu, 0);
-            for (int si = 0; si < ns_tile; ++si) {
-                size_t W = 0;
-                for (int l = 0; l < kSlice; ++l) W = std::max(W, lanes[(size_t)si * kSlice + l].size());
-                for (size_t cpos = 0; cpos < W; ++cpos)
-                    for (int ph = 0; ph < kSlice / NB; ++ph) {
-                        grp.clear();
-                        for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
-                            const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
-                            if (cpos < U.size() && std::find(grp.begin(), grp.end(), U[cpos].node) == grp.end()) grp.push_back(U[cpos].node);
-                        }
-                        for (size_t x = 0; x < grp.size(); ++x)
-                            for (size_t y = 0; y < grp.size(); ++y)
-                                if (x != y) {
-                                    unsigned short &e = adj[(size_t)grp[x] * nu + grp[y]];
-                                    if (e < 0xffff) ++e;
+        return nnz;
+    };
+    // W (steps) and L (longest row) of slice si of the tile whose lanes are in S
+    auto slice_wl = [&](int64_t s, int si, const Scratch &S, int &W, int &L) {
+        W = 0;
+        L = 0;
+        for (int l = 0; l < kSlice; ++l) {
+            W = std::max(W, (int)S.lanes[(size_t)si * kSlice + l].size());
+            for (int r = 0; r < R; ++r) {
+                const int64_t d = (s * kSlice + l) * R + r;
+                if (d < nrows_dev) {
+                    const int64_t cr = caller_row(d);
+                    L = std::max(L, (int)(A.ptr[cr + 1] - A.ptr[cr]));
+                }
+            }
+        }
+    };
+    const int nthreads = host_threads(ntl);
+    constexpr int64_t kChunk = 16;  // tiles a worker claims at a time
+    // ---- pass 1: sizes.  Per tile the union size, per slice (W, L): every offset of the layout follows from them ----
+    std::vector<int> nu_of((size_t)ntl, 0);
+    {
+        std::atomic<int64_t> next{0};
+        host_parallel(nthreads, [&](int) {
+            Scratch S;
+            for (;;) {
+                const int64_t t0 = next.fetch_add(kChunk);
+                if (t0 >= ntl) break;
+                for (int64_t t = t0; t < std::min(ntl, t0 + kChunk); ++t) {
+                    tile_lanes(t, S);
+                    nu_of[(size_t)t] = (int)S.cols.size();
+                    const int64_t d0 = t * rows_per_tile, d1 = std::min(nrows_dev, d0 + rows_per_tile);
+                    const int64_t s0 = d0 / rows_per_slice;
+                    const int ns_tile = (int)((d1 - d0 + rows_per_slice - 1) / rows_per_slice);
+                    for (int si = 0; si < ns_tile; ++si) slice_wl(s0 + si, si, S, wl[2 * (s0 + si)], wl[2 * (s0 + si) + 1]);
+                }
+            }
+        });
+    }
+    std::vector<uint64_t> lcg_skip((size_t)ntl + 1, 0);  // steps of the copy-1 generator consumed before tile t
+    {
+        int64_t usum = 0;
+        for (int64_t t = 0; t < ntl; ++t) {
+            usum += nu_of[(size_t)t] + 1;  // + the dummy record
+            if (usum > 0x7fffffffLL) return fail(MFT_EINVAL, "union lists exceed 32-bit offsets");
+            uoff[t + 1] = (int)usum;
+            lcg_skip[(size_t)t + 1] = lcg_skip[(size_t)t] + (two_copies ? (uint64_t)std::max(nu_of[(size_t)t] - 1, 0) : 0);
+        }
+        long long at = 0;
+        for (int64_t s = 0; s < nsl; ++s) {
+            boff[s] = at;
+            at += (long long)wl[2 * s] * kSlice * 2 + 2LL * R * wl[2 * s + 1] * kSlice * 8;
+        }
+        blob.assign((size_t)at + 128, 0);
+        ulist.assign((size_t)usum, 0);
+        uslot.assign((size_t)usum * 2, 0);
+    }
+    // ---- pass 2: slots (bank colouring, second copy) and the slices, written in place ----
+    struct Totals {
+        int max_slot = 0, maxW = 0, maxL = 0, err_slots = 0;
+        int64_t nnz = 0, nsteps = 0;
+    };
+    std::vector<Totals> totals((size_t)nthreads);
+    std::atomic<int64_t> next{0};
+    std::atomic<bool> failed{false};
+    host_parallel(nthreads, [&](int worker) {
+        Scratch S;
+        Totals &T = totals[(size_t)worker];
+        std::vector<int> &slot = S.slot, &slot1 = S.slot1, &order = S.order, &bank = S.bank, &deg = S.deg, &grp = S.grp, &nb_ptr = S.nb_ptr,
+                         &nb_idx = S.nb_idx, &nb_w = S.nb_w;
+        std::vector<unsigned short> &adj = S.adj;
+        for (;;) {
+            const int64_t tc = next.fetch_add(kChunk);
+            if (tc >= ntl || failed.load()) break;
+            for (int64_t t = tc; t < std::min(ntl, tc + kChunk); ++t) {
+                const int64_t d0 = t * rows_per_tile, d1 = std::min(nrows_dev, d0 + rows_per_tile);
+                T.nnz += tile_lanes(t, S);
+                const std::vector<int> &cols = S.cols;
+                const std::vector<std::vector<Step>> &lanes = S.lanes;
+                const int nu = (int)cols.size();
+                const int64_t s0 = d0 / rows_per_slice;
+                const int ns_tile = (int)((d1 - d0 + rows_per_slice - 1) / rows_per_slice);
+                // slots
+                slot.assign(nu, 0);
+                int nslots = nu;
+                if (!colour || nu <= NB) {
+                    for (int q = 0; q < nu; ++q) slot[q] = q;
+                } else {
+                    adj.assign((size_t)nu * nu, 0);
+                    for (int si = 0; si < ns_tile; ++si) {
+                        size_t W = 0;
+                        for (int l = 0; l < kSlice; ++l) W = std::max(W, lanes[(size_t)si * kSlice + l].size());
+                        for (size_t cpos = 0; cpos < W; ++cpos)
+                            for (int ph = 0; ph < kSlice / NB; ++ph) {
+                                grp.clear();
+                                for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
+                                    const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
+                                    if (cpos < U.size() && std::find(grp.begin(), grp.end(), U[cpos].node) == grp.end()) grp.push_back(U[cpos].node);
                                 }
+                                for (size_t x = 0; x < grp.size(); ++x)
+                                    for (size_t y = 0; y < grp.size(); ++y)
+                                        if (x != y) {
+                                            unsigned short &e = adj[(size_t)grp[x] * nu + grp[y]];
+                                            if (e < 0xffff) ++e;
+                                        }
+                            }
                     }
-            }
-            // adjacency lists (node, weight) from the dense counts
-            deg.assign(nu, 0);
-            nb_ptr.assign(nu + 1, 0);
-            nb_idx.clear();
-            nb_w.clear();
-            for (int a = 0; a < nu; ++a) {
-                const unsigned short *row = &adj[(size_t)a * nu];
-                int sum = 0;
-                for (int b = 0; b < nu; ++b)
-                    if (row[b]) {
-                        sum += row[b];
-                        nb_idx.push_back(b);
-                        nb_w.push_back(row[b]);
+                    // adjacency lists (node, weight) from the dense counts
+                    deg.assign(nu, 0);
+                    nb_ptr.assign(nu + 1, 0);
+                    nb_idx.clear();
+                    nb_w.clear();
+                    for (int a = 0; a < nu; ++a) {
+                        const unsigned short *row = &adj[(size_t)a * nu];
+                        int sum = 0;
+                        for (int b = 0; b < nu; ++b)
+                            if (row[b]) {
+                                sum += row[b];
+                                nb_idx.push_back(b);
+                                nb_w.push_back(row[b]);
+                            }
+                        deg[a] = sum;
+                        nb_ptr[a + 1] = (int)nb_idx.size();
                     }
-                deg[a] = sum;
-                nb_ptr[a + 1] = (int)nb_idx.size();
-            }
-            order.resize(nu);
-            std::iota(order.begin(), order.end(), 0);
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return deg[a] > deg[b]; });
-            bank.assign(nu, -1);
-            int fill[NB] = {0};
-            auto choose = [&](int a) {
-                long long cost[NB] = {0};
-                for (int q = nb_ptr[a]; q < nb_ptr[a + 1]; ++q)
-                    if (bank[nb_idx[q]] >= 0) cost[bank[nb_idx[q]]] += nb_w[q];
-                int bestb = 0;
-                for (int k = 1; k < NB; ++k)   // ties -> emptiest bank group (keeps the slot count low)
-                    if (cost[k] < cost[bestb] || (cost[k] == cost[bestb] && fill[k] < fill[bestb])) bestb = k;
-                return bestb;
-            };
-            for (int a : order) {
-                bank[a] = choose(a);
-                ++fill[bank[a]];
-            }
-            for (int pass = 0; pass < 2; ++pass)
-                for (int a : order) {
-                    --fill[bank[a]];
-                    bank[a] = -1;
-                    bank[a] = choose(a);
-                    ++fill[bank[a]];
-                }
-            int level[NB] = {0};
-            nslots = 0;
-            for (int q = 0; q < nu; ++q) {
-                slot[q] = level[bank[q]]++ * NB + bank[q];
-                nslots = std::max(nslots, slot[q] + 1);
-            }
-        }
-        // second copy of the tile's records under an independent (pseudo-random) bank assignment: each distinct point a
-        // phase requests may then be read from either copy ("two choices"), which the emit loop below exploits
-        if (two_copies) {
-            slot1.resize(nu);   // a random permutation of 0..nu-1: balanced bank groups, independent of copy 0
-            std::iota(slot1.begin(), slot1.end(), 0);
-            for (int q = nu - 1; q > 0; --q) {
-                lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
-                std::swap(slot1[q], slot1[(int)((lcg >> 33) % (uint64_t)(q + 1))]);
-            }
-            nslots = std::max(nslots, nu);
-        }
-        if (nslots + 1 > 4095) return fail(MFT_ENOTSUP, "union tile: %d slots in one block exceed the 12-bit slot field", nslots);
-        max_slot = std::max(max_slot, nslots);  // the dummy record takes slot `nslots`
-        // emit the slices
-        for (int si = 0; si < ns_tile; ++si) {
-            const int64_t s = s0 + si;
-            int W = 0, L = 0;
-            for (int l = 0; l < kSlice; ++l) {
-                W = std::max(W, (int)lanes[(size_t)si * kSlice + l].size());
-                for (int r = 0; r < R; ++r) {
-                    const int64_t d = (s * kSlice + l) * R + r;
-                    if (d < nrows_dev) {
-                        const int64_t cr = caller_row(d);
-                        L = std::max(L, (int)(A.ptr[cr + 1] - A.ptr[cr]));
+                    order.resize(nu);
+                    std::iota(order.begin(), order.end(), 0);
+                    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return deg[a] > deg[b]; });
+                    bank.assign(nu, -1);
+                    int fill[NB] = {0};
+                    auto choose = [&](int a) {
+                        long long cost[NB] = {0};
+                        for (int q = nb_ptr[a]; q < nb_ptr[a + 1]; ++q)
+                            if (bank[nb_idx[q]] >= 0) cost[bank[nb_idx[q]]] += nb_w[q];
+                        int bestb = 0;
+                        for (int k = 1; k < NB; ++k)   // ties -> emptiest bank group (keeps the slot count low)
+                            if (cost[k] < cost[bestb] || (cost[k] == cost[bestb] && fill[k] < fill[bestb])) bestb = k;
+                        return bestb;
+                    };
+                    for (int a : order) {
+                        bank[a] = choose(a);
+                        ++fill[bank[a]];
                     }
-                }
-            }
-            maxW = std::max(maxW, W);
-            maxL = std::max(maxL, L);
-            nsteps += W;
-            const size_t word_bytes = (size_t)W * kSlice * 2, wblk = (size_t)L * kSlice * 8;
-            const size_t at0 = blob.size();
-            boff[s] = (long long)at0;
-            wl[2 * s] = W;
-            wl[2 * s + 1] = L;
-            blob.resize(at0 + word_bytes + 2 * R * wblk, 0);
-            unsigned short *word = reinterpret_cast<unsigned short *>(blob.data() + at0);
-            for (int q = 0; q < W * kSlice; ++q) word[q] = (unsigned short)nslots;  // dummy slot, empty mask
-            for (int l = 0; l < kSlice; ++l) {
-                const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
-                for (size_t cpos = 0; cpos < U.size(); ++cpos)
-                    word[cpos * kSlice + l] = (unsigned short)(slot[U[cpos].node] | (U[cpos].mask << 12));
-            }
-            if (two_copies) {
-                // per step and LDS.128 phase (8 lanes): the copy of each distinct point that minimises the largest number of
-                // distinct addresses in one bank group (exhaustive over <= 2^8 choices)
-                for (int cpos = 0; cpos < W; ++cpos)
-                    for (int ph = 0; ph < kSlice / NB; ++ph) {
-                        grp.clear();
-                        for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
-                            const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
-                            if ((size_t)cpos < U.size() && std::find(grp.begin(), grp.end(), U[cpos].node) == grp.end()) grp.push_back(U[cpos].node);
+                    for (int pass = 0; pass < 2; ++pass)
+                        for (int a : order) {
+                            --fill[bank[a]];
+                            bank[a] = -1;
+                            bank[a] = choose(a);
+                            ++fill[bank[a]];
                         }
-                        const int kk = (int)grp.size();
-                        if (kk < 2) continue;
-                        int best_bits = 0, best_max = 99;
-                        for (int bits = 0; bits < (1 << kk) && best_max > 1; ++bits) {
-                            int cnt[NB] = {0}, mx = 0;
-                            for (int q = 0; q < kk; ++q) mx = std::max(mx, ++cnt[((bits >> q) & 1 ? slot1[grp[q]] : slot[grp[q]]) % NB]);
-                            if (mx < best_max) {
-                                best_max = mx;
-                                best_bits = bits;
+                    int level[NB] = {0};
+                    nslots = 0;
+                    for (int q = 0; q < nu; ++q) {
+                        slot[q] = level[bank[q]]++ * NB + bank[q];
+                        nslots = std::max(nslots, slot[q] + 1);
+                    }
+                }
+                // second copy of the tile's records under an independent (pseudo-random) bank assignment: each distinct point a
+                // phase requests may then be read from either copy ("two choices"), which the emit loop below exploits.
+                // One generator runs through the tiles in order; a worker jumps it to its tile's position.
+                if (two_copies) {
+                    uint64_t lcg = lcg_jump(lcg0, lcg_skip[(size_t)t]);
+                    slot1.resize(nu);   // a random permutation of 0..nu-1: balanced bank groups, independent of copy 0
+                    std::iota(slot1.begin(), slot1.end(), 0);
+                    for (int q = nu - 1; q > 0; --q) {
+                        lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+                        std::swap(slot1[q], slot1[(int)((lcg >> 33) % (uint64_t)(q + 1))]);
+                    }
+                    nslots = std::max(nslots, nu);
+                }
+                if (nslots + 1 > 4095) {
+                    T.err_slots = nslots;
+                    failed.store(true);
+                    break;
+                }
+                T.max_slot = std::max(T.max_slot, nslots);  // the dummy record takes slot `nslots`
+                // emit the slices
+                for (int si = 0; si < ns_tile; ++si) {
+                    const int64_t s = s0 + si;
+                    const int W = wl[2 * s], L = wl[2 * s + 1];
+                    T.maxW = std::max(T.maxW, W);
+                    T.maxL = std::max(T.maxL, L);
+                    T.nsteps += W;
+                    const size_t word_bytes = (size_t)W * kSlice * 2, wblk = (size_t)L * kSlice * 8;
+                    const size_t at0 = (size_t)boff[s];
+                    unsigned short *word = reinterpret_cast<unsigned short *>(blob.data() + at0);
+                    for (int q = 0; q < W * kSlice; ++q) word[q] = (unsigned short)nslots;  // dummy slot, empty mask
+                    for (int l = 0; l < kSlice; ++l) {
+                        const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
+                        for (size_t cpos = 0; cpos < U.size(); ++cpos)
+                            word[cpos * kSlice + l] = (unsigned short)(slot[U[cpos].node] | (U[cpos].mask << 12));
+                    }
+                    if (two_copies) {
+                        // per step and LDS.128 phase (8 lanes): the copy of each distinct point that minimises the largest number
+                        // of distinct addresses in one bank group (exhaustive over <= 2^8 choices)
+                        for (int cpos = 0; cpos < W; ++cpos)
+                            for (int ph = 0; ph < kSlice / NB; ++ph) {
+                                grp.clear();
+                                for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
+                                    const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
+                                    if ((size_t)cpos < U.size() && std::find(grp.begin(), grp.end(), U[cpos].node) == grp.end()) grp.push_back(U[cpos].node);
+                                }
+                                const int kk = (int)grp.size();
+                                if (kk < 2) continue;
+                                int best_bits = 0, best_max = 99;
+                                for (int bits = 0; bits < (1 << kk) && best_max > 1; ++bits) {
+                                    int cnt[NB] = {0}, mx = 0;
+                                    for (int q = 0; q < kk; ++q) mx = std::max(mx, ++cnt[((bits >> q) & 1 ? slot1[grp[q]] : slot[grp[q]]) % NB]);
+                                    if (mx < best_max) {
+                                        best_max = mx;
+                                        best_bits = bits;
+                                    }
+                                }
+                                for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
+                                    const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
+                                    if ((size_t)cpos >= U.size()) continue;
+                                    const int q = (int)(std::find(grp.begin(), grp.end(), U[cpos].node) - grp.begin());
+                                    if ((best_bits >> q) & 1)
+                                        word[(size_t)cpos * kSlice + l] = (unsigned short)(slot1[U[cpos].node] | (U[cpos].mask << 12) | 0x4000u);
+                                }
+                            }
+                    }
+                    for (int l = 0; l < kSlice; ++l) {
+                        for (int r = 0; r < R; ++r) {
+                            const int64_t d = (s * kSlice + l) * R + r;
+                            if (d >= nrows_dev) continue;
+                            const int64_t cr = caller_row(d);
+                            double *wx = reinterpret_cast<double *>(blob.data() + at0 + word_bytes + (size_t)r * wblk);
+                            double *wy = reinterpret_cast<double *>(blob.data() + at0 + word_bytes + (size_t)(R + r) * wblk);
+                            int pos = 0;
+                            for (int64_t p = A.ptr[cr]; p < A.ptr[cr + 1]; ++p, ++pos) {
+                                wx[(size_t)pos * kSlice + l] = A.wx[p];
+                                wy[(size_t)pos * kSlice + l] = A.wy[p];
                             }
                         }
-                        for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
-                            const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
-                            if ((size_t)cpos >= U.size()) continue;
-                            const int q = (int)(std::find(grp.begin(), grp.end(), U[cpos].node) - grp.begin());
-                            if ((best_bits >> q) & 1)
-                                word[(size_t)cpos * kSlice + l] = (unsigned short)(slot1[U[cpos].node] | (U[cpos].mask << 12) | 0x4000u);
-                        }
-                    }
-            }
-            for (int l = 0; l < kSlice; ++l) {
-                for (int r = 0; r < R; ++r) {
-                    const int64_t d = (s * kSlice + l) * R + r;
-                    if (d >= nrows_dev) continue;
-                    const int64_t cr = caller_row(d);
-                    double *wx = reinterpret_cast<double *>(blob.data() + at0 + word_bytes + (size_t)r * wblk);
-                    double *wy = reinterpret_cast<double *>(blob.data() + at0 + word_bytes + (size_t)(R + r) * wblk);
-                    int pos = 0;
-                    for (int64_t p = A.ptr[cr]; p < A.ptr[cr + 1]; ++p, ++pos) {
-                        wx[(size_t)pos * kSlice + l] = A.wx[p];
-                        wy[(size_t)pos * kSlice + l] = A.wy[p];
                     }
                 }
+                // the tile's union list and slot table; last entry = the dummy record (a finite state in u, zeros in g)
+                const size_t u0 = (size_t)uoff[t];
+                for (int q = 0; q < nu; ++q) {
+                    ulist[u0 + q] = cols[q];
+                    uslot[2 * (u0 + q)] = (unsigned short)slot[q];
+                    uslot[2 * (u0 + q) + 1] = (unsigned short)(two_copies ? slot1[q] : slot[q]);
+                }
+                ulist[u0 + nu] = (int)c->n_tot;
+                uslot[2 * (u0 + nu)] = (unsigned short)nslots;
+                uslot[2 * (u0 + nu) + 1] = (unsigned short)nslots;
             }
         }
-        for (int q = 0; q < nu; ++q) node_of[cols[q]] = -1;
-        ulist.insert(ulist.end(), cols.begin(), cols.end());
-        for (int q = 0; q < nu; ++q) {
-            uslot.push_back((unsigned short)slot[q]);
-            uslot.push_back((unsigned short)(two_copies ? slot1[q] : slot[q]));
-        }
-        ulist.push_back((int)c->n_tot);  // the dummy record (a finite state in u, zeros in g)
-        uslot.push_back((unsigned short)nslots);
-        uslot.push_back((unsigned short)nslots);
-        if (ulist.size() > 0x7fffffffULL) return fail(MFT_EINVAL, "union lists exceed 32-bit offsets");
-        uoff[t + 1] = (int)ulist.size();
+    });
+    int max_slot = 0, maxW = 0, maxL = 0;
+    int64_t nnz = 0, nsteps = 0;
+    for (const Totals &T : totals) {
+        if (T.err_slots) return fail(MFT_ENOTSUP, "union tile: %d slots in one block exceed the 12-bit slot field", T.err_slots);
+        max_slot = std::max(max_slot, T.max_slot);
+        maxW = std::max(maxW, T.maxW);
+        maxL = std::max(maxL, T.maxL);
+        nnz += T.nnz;
+        nsteps += T.nsteps;
     }
-    blob.resize(blob.size() + 128, 0);
     out.R = R;
     out.nslices = (int)nsl;
     out.ntiles = (int)ntl;
@@ -1223,7 +1339,25 @@ extern "C" int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int 
         A.ptr[r + 1] = (int64_t)A.col.size();
     }
     HostTileR h;
+    const auto t_build0 = std::chrono::steady_clock::now();
     CHECK(build_tiler_host(&ctx, A, ctx.n_local, R, (layout & 1) != 0, (layout & 2) != 0, h));
+    if (getenv("MFT_TRACE")) {   // build time + a checksum of the whole layout (compare builds / thread counts)
+        uint64_t fnv = 1469598103934665603ULL;
+        auto mix = [&](const void *p, size_t bytes) {
+            const unsigned char *b = static_cast<const unsigned char *>(p);
+            for (size_t i = 0; i < bytes; ++i) fnv = (fnv ^ b[i]) * 1099511628211ULL;
+        };
+        mix(h.blob.data(), h.blob.size());
+        mix(h.boff.data(), h.boff.size() * sizeof(long long));
+        mix(h.wl.data(), h.wl.size() * sizeof(int));
+        mix(h.uoff.data(), h.uoff.size() * sizeof(int));
+        mix(h.ulist.data(), h.ulist.size() * sizeof(int));
+        mix(h.uslot.data(), h.uslot.size() * sizeof(unsigned short));
+        const int meta[7] = {h.R, h.nslices, h.ntiles, h.maxW, h.maxL, h.sstride, h.ncopy};
+        mix(meta, sizeof meta);
+        fprintf(stderr, "[mft] tile layout: n=%lld k=%d R=%d layout=%d perm=%d  build %.3f s  fnv %016llx\n", (long long)n, k, R, layout, with_perm,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_build0).count(), (unsigned long long)fnv);
+    }
     std::vector<double> x((size_t)n + 1);
     for (auto &v : x) v = (double)(int)(rnd() % 4001 - 2000) / 128.0;   // indexed by DEVICE column; x[n] = dummy record
     auto caller_row = [&](int64_t d) -> int64_t { return ctx.have_perm ? ctx.perm[d] : d; };

@@ -93,3 +93,24 @@ def test_union_tile_format_at_the_edge_sizes_of_the_gpu_tests():
             for layout in (0, 3):
                 for perm in (0, 1):
                     assert lib.mft_debug_tile_selftest(n, k, 1, layout, perm, 7 + n, st) == 0, (n, k, layout, perm, lib.mft_last_error())
+
+
+def test_union_tile_layout_does_not_depend_on_the_host_thread_count():
+    """the layout builder runs on all host cores (MFT_HOST_THREADS); offsets come from a sizing pass and the generator of
+    the second-copy permutations is jumped to each tile's position, so the bytes are the same for any thread count"""
+    import re
+    import subprocess
+    import sys
+
+    code = ("import sys, ctypes as C; sys.path.insert(0, %r); import mft_b200 as m; lib = m._lib.load(); st = (C.c_double * 4)()\n"
+            "for n, k, R, layout, perm in ((20000, 20, 1, 3, 1), (9000, 13, 2, 3, 0), (7000, 30, 4, 1, 1), (300, 20, 1, 3, 0)):\n"
+            "    assert lib.mft_debug_tile_selftest(n, k, R, layout, perm, 11, st) == 0\n") % cases.ROOT
+    seen = []
+    for threads in ("1", "3", "8"):
+        env = dict(os.environ, MFT_TRACE="1", MFT_HOST_THREADS=threads)
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr
+        sums = re.findall(r"fnv ([0-9a-f]{16})", res.stderr)
+        assert len(sums) == 4, res.stderr
+        seen.append(sums)
+    assert seen[0] == seen[1] == seen[2]
