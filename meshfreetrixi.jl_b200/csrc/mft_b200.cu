@@ -678,761 +678,7 @@ extern "C" int mft_add_source(mft_ctx *c, int kind, const double *params, int np
     return MFT_OK;
 }
 
-// ------------------------------------------------------------------------------------------------------
-// finalize: build device layouts
-// ------------------------------------------------------------------------------------------------------
-static void sort_rows_by_key(Csr2 &A, const std::vector<int64_t> &keys, bool paired)
-{
-    if (keys.empty()) return;
-    std::vector<int64_t> ord;
-    std::vector<int32_t> tc;
-    std::vector<double> tx, ty;
-    for (int64_t r = 0; r < A.nrows; ++r) {
-        const int64_t b = A.ptr[r], e = A.ptr[r + 1], len = e - b;
-        bool sorted = true;
-        for (int64_t p = b + 1; p < e; ++p)
-            if (keys[A.col[p - 1]] > keys[A.col[p]]) {
-                sorted = false;
-                break;
-            }
-        if (sorted) continue;
-        ord.resize(len);
-        std::iota(ord.begin(), ord.end(), (int64_t)0);
-        std::stable_sort(ord.begin(), ord.end(), [&](int64_t a, int64_t c2) { return keys[A.col[b + a]] < keys[A.col[b + c2]]; });
-        tc.resize(len);
-        tx.resize(len);
-        if (paired) ty.resize(len);
-        for (int64_t q = 0; q < len; ++q) {
-            tc[q] = A.col[b + ord[q]];
-            tx[q] = A.wx[b + ord[q]];
-            if (paired) ty[q] = A.wy[b + ord[q]];
-        }
-        for (int64_t q = 0; q < len; ++q) {
-            A.col[b + q] = tc[q];
-            A.wx[b + q] = tx[q];
-            if (paired) A.wy[b + q] = ty[q];
-        }
-    }
-}
-
-// rows of A^T from rows of A (entries of each output row in ascending source-row order)
-static void transpose_rows(const Csr2 &A, int64_t ncols, bool paired, Csr2 &T)
-{
-    T.nrows = ncols;
-    T.ptr.assign(ncols + 1, 0);
-    for (int64_t p = 0; p < (int64_t)A.col.size(); ++p) T.ptr[A.col[p] + 1]++;
-    for (int64_t i = 0; i < ncols; ++i) T.ptr[i + 1] += T.ptr[i];
-    T.col.resize(A.col.size());
-    T.wx.resize(A.col.size());
-    if (paired) T.wy.resize(A.col.size());
-    std::vector<int64_t> fill(T.ptr.begin(), T.ptr.end() - 1);
-    for (int64_t r = 0; r < A.nrows; ++r)
-        for (int64_t p = A.ptr[r]; p < A.ptr[r + 1]; ++p) {
-            const int64_t q = fill[A.col[p]]++;
-            T.col[q] = (int32_t)r;
-            T.wx[q] = A.wx[p];
-            if (paired) T.wy[q] = A.wy[p];
-        }
-}
-
-// CSC columns -> "rows of the transpose" directly (column i of D = row i of D'), ascending row index
-static void csc_to_colrows(const HostCsc &X, const HostCsc *Y, int64_t n, Csr2 &T)
-{
-    T.nrows = n;
-    T.ptr.assign(X.colptr.begin(), X.colptr.end());
-    T.col.resize(X.rowval.size());
-    for (size_t p = 0; p < X.rowval.size(); ++p) T.col[p] = (int32_t)X.rowval[p];
-    T.wx = X.nz;
-    if (Y) T.wy = Y->nz;
-}
-
-// build sliced ELL for device rows [0, nrows_dev): device row d <- caller row perm[d]; columns remapped by iperm
-static int build_ell(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, bool paired, DevEll &out)
-{
-    const int64_t nsl = (nrows_dev + kSlice - 1) / kSlice;
-    std::vector<int> off(nsl + 1, 0);
-    auto caller_row = [&](int64_t d) -> int64_t { return c->have_perm ? c->perm[d] : d; };
-    int64_t nnz = 0;
-    for (int64_t s = 0; s < nsl; ++s) {
-        int64_t w = 0;
-        for (int64_t d = s * kSlice; d < std::min(nrows_dev, (s + 1) * kSlice); ++d) {
-            const int64_t r = caller_row(d);
-            const int64_t len = A.ptr[r + 1] - A.ptr[r];
-            w = std::max(w, len);
-            nnz += len;
-        }
-        const int64_t tot = (int64_t)off[s] + w;
-        if (tot > 0x7fffffffLL / kSlice * 16) return fail(MFT_EINVAL, "operator too large for 32-bit slice offsets");
-        off[s + 1] = (int)tot;
-    }
-    const int64_t ncols = off[nsl];
-    const int colb = paired ? kColBytes2 : kColBytes1;
-    std::vector<unsigned char> blob((size_t)ncols * colb + 128, 0);
-    int maxw = 0;
-    for (int64_t s = 0; s < nsl; ++s) {
-        const int w = off[s + 1] - off[s];
-        maxw = std::max(maxw, w);
-        unsigned char *b = blob.data() + (size_t)off[s] * colb;
-        int *idx = reinterpret_cast<int *>(b);
-        double *wx = reinterpret_cast<double *>(b + (size_t)w * kSlice * 4);
-        double *wy = reinterpret_cast<double *>(b + (size_t)w * kSlice * 12);
-        // padding: the dummy record (index n_tot) with weight 0 -> adds an exact zero, one shared sector per request
-        for (int q = 0; q < w * kSlice; ++q) idx[q] = (int)c->n_tot;
-        for (int64_t d = s * kSlice; d < std::min(nrows_dev, (s + 1) * kSlice); ++d) {
-            const int64_t r = caller_row(d);
-            const int lane = (int)(d - s * kSlice);
-            int cpos = 0;
-            for (int64_t p = A.ptr[r]; p < A.ptr[r + 1]; ++p, ++cpos) {
-                const int64_t j = A.col[p];
-                const size_t at = (size_t)cpos * kSlice + lane;
-                idx[at] = c->have_perm ? c->iperm[j] : (int)j;
-                wx[at] = A.wx[p];
-                if (paired) wy[at] = A.wy[p];
-            }
-        }
-    }
-    out.nslices = (int)nsl;
-    out.colb = colb;
-    out.maxw = maxw;
-    out.ncols_total = ncols;
-    out.nnz = nnz;
-    CHECK(out.blob.upload(blob));
-    CHECK(out.off.upload(off));
-    return MFT_OK;
-}
-
-// pair-slice blobs: device rows (2l, 2l+1) share one lane; the lane walks the union of the two rows' entries in the
-// reference order (ascending key), with a zero weight where a row lacks the entry
-static int build_ell_pairs(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, DevEll &out)
-{
-    const int64_t rows_per_slice = 2 * kSlice;
-    const int64_t nsl = (nrows_dev + rows_per_slice - 1) / rows_per_slice;
-    auto caller_row = [&](int64_t d) -> int64_t { return c->have_perm ? c->perm[d] : d; };
-    auto key = [&](int32_t col) -> int64_t { return c->keys.empty() ? (int64_t)col : c->keys[col]; };
-    struct Ent { int32_t col; double w[4]; };
-    std::vector<std::vector<Ent>> lists((size_t)nsl * kSlice);
-    std::vector<int> off(nsl + 1, 0);
-    int maxw = 0;
-    int64_t nnz = 0;
-    for (int64_t s = 0; s < nsl; ++s) {
-        int w = 0;
-        for (int l = 0; l < kSlice; ++l) {
-            const int64_t dA = s * rows_per_slice + 2 * l, dB = dA + 1;
-            std::vector<Ent> &U = lists[s * kSlice + l];
-            int64_t pa = 0, ea = 0, pb = 0, eb = 0;
-            if (dA < nrows_dev) { const int64_t r = caller_row(dA); pa = A.ptr[r]; ea = A.ptr[r + 1]; }
-            if (dB < nrows_dev) { const int64_t r = caller_row(dB); pb = A.ptr[r]; eb = A.ptr[r + 1]; }
-            nnz += (ea - pa) + (eb - pb);
-            while (pa < ea || pb < eb) {
-                Ent e{};
-                const bool takeA = pa < ea && (pb >= eb || key(A.col[pa]) <= key(A.col[pb]));
-                const bool takeB = pb < eb && (pa >= ea || key(A.col[pb]) <= key(A.col[pa]));
-                if (takeA && takeB && A.col[pa] != A.col[pb]) {
-                    // equal keys on different columns cannot happen for a permutation of keys; fall back to A first
-                    e.col = A.col[pa]; e.w[0] = A.wx[pa]; e.w[1] = A.wy[pa]; ++pa;
-                } else if (takeA && takeB) {
-                    e.col = A.col[pa]; e.w[0] = A.wx[pa]; e.w[1] = A.wy[pa]; e.w[2] = A.wx[pb]; e.w[3] = A.wy[pb]; ++pa; ++pb;
-                } else if (takeA) {
-                    e.col = A.col[pa]; e.w[0] = A.wx[pa]; e.w[1] = A.wy[pa]; ++pa;
-                } else {
-                    e.col = A.col[pb]; e.w[2] = A.wx[pb]; e.w[3] = A.wy[pb]; ++pb;
-                }
-                U.push_back(e);
-            }
-            w = std::max(w, (int)U.size());
-        }
-        maxw = std::max(maxw, w);
-        off[s + 1] = off[s] + w;
-    }
-    const int64_t ncols = off[nsl];
-    std::vector<unsigned char> blob((size_t)ncols * kColBytesPair + 128, 0);
-    for (int64_t s = 0; s < nsl; ++s) {
-        const int w = off[s + 1] - off[s];
-        unsigned char *b = blob.data() + (size_t)off[s] * kColBytesPair;
-        int *idx = reinterpret_cast<int *>(b);
-        double *wq = reinterpret_cast<double *>(b + (size_t)w * kSlice * 4);
-        for (int q = 0; q < w * kSlice; ++q) idx[q] = (int)c->n_tot;
-        for (int l = 0; l < kSlice; ++l) {
-            const std::vector<Ent> &U = lists[s * kSlice + l];
-            for (size_t cpos = 0; cpos < U.size(); ++cpos) {
-                const size_t at = cpos * kSlice + l;
-                idx[at] = c->have_perm ? c->iperm[U[cpos].col] : (int)U[cpos].col;
-                for (int q = 0; q < 4; ++q) wq[(size_t)q * w * kSlice + at] = U[cpos].w[q];
-            }
-        }
-    }
-    out.nslices = (int)nsl;
-    out.colb = kColBytesPair;
-    out.maxw = maxw;
-    out.ncols_total = ncols;
-    out.nnz = nnz;
-    CHECK(out.blob.upload(blob));
-    CHECK(out.off.upload(off));
-    return MFT_OK;
-}
-
-// Union tiles (mft_tile_kernels.cuh).  Tile = kTileWarps slices; slice = 32 lanes x R rows: lane l of slice s owns device
-// rows (s*32 + l)*R + r and walks the union of their entries in summation order; step word = slot | row mask << 12; the
-// weights stay compact per row.  The tile's union list is sorted by device index (coalesced loads) and ends with the dummy
-// record; uslot[] gives each entry its shared-memory slot.  With `colour` the slots are chosen so that points requested
-// together by the 8 lanes of an LDS.128 phase fall into different 16-byte bank groups (slot mod 8) where possible:
-// greedy weighted colouring of the co-request graph + two refinement sweeps.
-struct HostTileR {
-    int R = 0, nslices = 0, ntiles = 0, maxW = 0, maxL = 0, sstride = 0, ncopy = 1;
-    int64_t nnz = 0, nsteps = 0;
-    std::vector<unsigned char> blob;
-    std::vector<long long> boff;
-    std::vector<int> wl, uoff, ulist;
-    std::vector<unsigned short> uslot;
-};
-
-// Run fn(worker) on `nthreads` host threads (the caller's thread is worker 0) and wait for all of them.
-template <class F>
-static void host_parallel(int nthreads, F fn)
-{
-    std::vector<std::thread> pool;
-    for (int w = 1; w < nthreads; ++w) pool.emplace_back([&fn, w]() { fn(w); });
-    fn(0);
-    for (auto &th : pool) th.join();
-}
-
-// host threads for the layout builders: MFT_HOST_THREADS, else the hardware concurrency (at most 64)
-static int host_threads(int64_t work_items)
-{
-    int n = 0;
-    if (const char *e = getenv("MFT_HOST_THREADS")) n = atoi(e);
-    if (n <= 0) n = (int)std::thread::hardware_concurrency();
-    n = std::max(1, std::min(n, 64));
-    return (int)std::max<int64_t>(1, std::min<int64_t>(n, work_items));
-}
-
-// state of x -> a x + c (mod 2^64) after `k` more steps (jump-ahead by repeated squaring of the affine map)
-static inline uint64_t lcg_jump(uint64_t x, uint64_t k)
-{
-    uint64_t cur_a = 6364136223846793005ULL, cur_c = 1442695040888963407ULL, acc_a = 1, acc_c = 0;
-    for (; k; k >>= 1) {
-        if (k & 1) {
-            acc_a *= cur_a;
-            acc_c = acc_c * cur_a + cur_c;
-        }
-        cur_c = (cur_a + 1) * cur_c;
-        cur_a *= cur_a;
-    }
-    return acc_a * x + acc_c;
-}
-
-static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, int R, bool colour, bool two_copies, HostTileR &out)
-{
-    if (R > 2) two_copies = false;  // the copy-select bit (14) is a row-mask bit for R = 4
-    const uint64_t lcg0 = 0x9e3779b97f4a7c15ULL;
-    const int64_t rows_per_slice = (int64_t)kSlice * R, rows_per_tile = rows_per_slice * kTileWarps;
-    const int64_t nsl = (nrows_dev + rows_per_slice - 1) / rows_per_slice;
-    const int64_t ntl = (nrows_dev + rows_per_tile - 1) / rows_per_tile;
-    auto caller_row = [&](int64_t d) -> int64_t { return c->have_perm ? c->perm[d] : d; };
-    auto dev_col = [&](int64_t j) -> int { return c->have_perm ? c->iperm[j] : (int)j; };
-    auto key = [&](int32_t col) -> int64_t { return c->keys.empty() ? (int64_t)col : c->keys[col]; };
-    constexpr int NB = 8;  // 16-byte bank groups seen by one LDS.128 phase (8 lanes)
-    std::vector<long long> &boff = out.boff;
-    std::vector<int> &wl = out.wl, &uoff = out.uoff, &ulist = out.ulist;
-    std::vector<unsigned short> &uslot = out.uslot;
-    std::vector<unsigned char> &blob = out.blob;
-    boff.assign(nsl, 0);
-    wl.assign(2 * nsl, 0);
-    uoff.assign(ntl + 1, 0);
-    struct Step { int node; unsigned mask; };
-    // per-thread scratch of one tile
-    struct Scratch {
-        std::vector<int> cols;                   // the tile's union: sorted device columns (node q = cols[q])
-        std::vector<std::vector<Step>> lanes;    // step lists of the tile's lanes
-        std::vector<unsigned short> adj;         // nu x nu co-request counts
-        std::vector<int> slot, slot1, order, bank, deg, grp, nb_ptr, nb_idx, nb_w;
-    };
-    // union of the tile's stencils (sorted) + the lane step lists of its slices (R-way merge by summation key);
-    // returns the number of stored entries of the tile's rows
-    auto tile_lanes = [&](int64_t t, Scratch &S) -> int64_t {
-        const int64_t d0 = t * rows_per_tile, d1 = std::min(nrows_dev, d0 + rows_per_tile);
-        std::vector<int> &cols = S.cols;
-        cols.clear();
-        for (int64_t d = d0; d < d1; ++d) {
-            const int64_t r = caller_row(d);
-            for (int64_t p = A.ptr[r]; p < A.ptr[r + 1]; ++p) cols.push_back(dev_col(A.col[p]));
-        }
-        std::sort(cols.begin(), cols.end());
-        cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
-        auto node_of = [&](int j) -> int { return (int)(std::lower_bound(cols.begin(), cols.end(), j) - cols.begin()); };
-        const int64_t s0 = d0 / rows_per_slice;
-        const int ns_tile = (int)((d1 - d0 + rows_per_slice - 1) / rows_per_slice);
-        S.lanes.resize((size_t)kTileWarps * kSlice);
-        int64_t nnz = 0;
-        for (int si = 0; si < ns_tile; ++si)
-            for (int l = 0; l < kSlice; ++l) {
-                std::vector<Step> &U = S.lanes[(size_t)si * kSlice + l];
-                U.clear();
-                int64_t pp[4], ee[4];
-                for (int r = 0; r < R; ++r) {
-                    const int64_t d = ((s0 + si) * kSlice + l) * R + r;
-                    pp[r] = ee[r] = 0;
-                    if (d < nrows_dev) {
-                        const int64_t cr = caller_row(d);
-                        pp[r] = A.ptr[cr];
-                        ee[r] = A.ptr[cr + 1];
-                        nnz += ee[r] - pp[r];
-                    }
-                }
-                for (;;) {
-                    int best = -1;
-                    for (int r = 0; r < R; ++r)
-                        if (pp[r] < ee[r] && (best < 0 || key(A.col[pp[r]]) < key(A.col[pp[best]]))) best = r;
-                    if (best < 0) break;
-                    const int32_t col = A.col[pp[best]];
-                    Step st{node_of(dev_col(col)), 0u};
-                    for (int r = 0; r < R; ++r)
-                        if (pp[r] < ee[r] && A.col[pp[r]] == col) {
-                            st.mask |= 1u << r;
-                            ++pp[r];
-                        }
-                    U.push_back(st);
-                }
-            }
-        return nnz;
-    };
-    // W (steps) and L (longest row) of slice si of the tile whose lanes are in S
-    auto slice_wl = [&](int64_t s, int si, const Scratch &S, int &W, int &L) {
-        W = 0;
-        L = 0;
-        for (int l = 0; l < kSlice; ++l) {
-            W = std::max(W, (int)S.lanes[(size_t)si * kSlice + l].size());
-            for (int r = 0; r < R; ++r) {
-                const int64_t d = (s * kSlice + l) * R + r;
-                if (d < nrows_dev) {
-                    const int64_t cr = caller_row(d);
-                    L = std::max(L, (int)(A.ptr[cr + 1] - A.ptr[cr]));
-                }
-            }
-        }
-    };
-    const int nthreads = host_threads(ntl);
-    constexpr int64_t kChunk = 16;  // tiles a worker claims at a time
-    // ---- pass 1: sizes.  Per tile the union size, per slice (W, L): every offset of the layout follows from them ----
-    std::vector<int> nu_of((size_t)ntl, 0);
-    {
-        std::atomic<int64_t> next{0};
-        host_parallel(nthreads, [&](int) {
-            Scratch S;
-            for (;;) {
-                const int64_t t0 = next.fetch_add(kChunk);
-                if (t0 >= ntl) break;
-                for (int64_t t = t0; t < std::min(ntl, t0 + kChunk); ++t) {
-                    tile_lanes(t, S);
-                    nu_of[(size_t)t] = (int)S.cols.size();
-                    const int64_t d0 = t * rows_per_tile, d1 = std::min(nrows_dev, d0 + rows_per_tile);
-                    const int64_t s0 = d0 / rows_per_slice;
-                    const int ns_tile = (int)((d1 - d0 + rows_per_slice - 1) / rows_per_slice);
-                    for (int si = 0; si < ns_tile; ++si) slice_wl(s0 + si, si, S, wl[2 * (s0 + si)], wl[2 * (s0 + si) + 1]);
-                }
-            }
-        });
-    }
-    std::vector<uint64_t> lcg_skip((size_t)ntl + 1, 0);  // steps of the copy-1 generator consumed before tile t
-    {
-        int64_t usum = 0;
-        for (int64_t t = 0; t < ntl; ++t) {
-            usum += nu_of[(size_t)t] + 1;  // + the dummy record
-            if (usum > 0x7fffffffLL) return fail(MFT_EINVAL, "union lists exceed 32-bit offsets");
-            uoff[t + 1] = (int)usum;
-            lcg_skip[(size_t)t + 1] = lcg_skip[(size_t)t] + (two_copies ? (uint64_t)std::max(nu_of[(size_t)t] - 1, 0) : 0);
-        }
-        long long at = 0;
-        for (int64_t s = 0; s < nsl; ++s) {
-            boff[s] = at;
-            at += (long long)wl[2 * s] * kSlice * 2 + 2LL * R * wl[2 * s + 1] * kSlice * 8;
-        }
-        blob.assign((size_t)at + 128, 0);
-        ulist.assign((size_t)usum, 0);
-        uslot.assign((size_t)usum * 2, 0);
-    }
-    // ---- pass 2: slots (bank colouring, second copy) and the slices, written in place ----
-    struct Totals {
-        int max_slot = 0, maxW = 0, maxL = 0, err_slots = 0;
-        int64_t nnz = 0, nsteps = 0;
-    };
-    std::vector<Totals> totals((size_t)nthreads);
-    std::atomic<int64_t> next{0};
-    std::atomic<bool> failed{false};
-    host_parallel(nthreads, [&](int worker) {
-        Scratch S;
-        Totals &T = totals[(size_t)worker];
-        std::vector<int> &slot = S.slot, &slot1 = S.slot1, &order = S.order, &bank = S.bank, &deg = S.deg, &grp = S.grp, &nb_ptr = S.nb_ptr,
-                         &nb_idx = S.nb_idx, &nb_w = S.nb_w;
-        std::vector<unsigned short> &adj = S.adj;
-        for (;;) {
-            const int64_t tc = next.fetch_add(kChunk);
-            if (tc >= ntl || failed.load()) break;
-            for (int64_t t = tc; t < std::min(ntl, tc + kChunk); ++t) {
-                const int64_t d0 = t * rows_per_tile, d1 = std::min(nrows_dev, d0 + rows_per_tile);
-                T.nnz += tile_lanes(t, S);
-                const std::vector<int> &cols = S.cols;
-                const std::vector<std::vector<Step>> &lanes = S.lanes;
-                const int nu = (int)cols.size();
-                const int64_t s0 = d0 / rows_per_slice;
-                const int ns_tile = (int)((d1 - d0 + rows_per_slice - 1) / rows_per_slice);
-                // slots
-                slot.assign(nu, 0);
-                int nslots = nu;
-                if (!colour || nu <= NB) {
-                    for (int q = 0; q < nu; ++q) slot[q] = q;
-                } else {
-                    adj.assign((size_t)nu * nu, 0);
-                    for (int si = 0; si < ns_tile; ++si) {
-                        size_t W = 0;
-                        for (int l = 0; l < kSlice; ++l) W = std::max(W, lanes[(size_t)si * kSlice + l].size());
-                        for (size_t cpos = 0; cpos < W; ++cpos)
-                            for (int ph = 0; ph < kSlice / NB; ++ph) {
-                                grp.clear();
-                                for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
-                                    const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
-                                    if (cpos < U.size() && std::find(grp.begin(), grp.end(), U[cpos].node) == grp.end()) grp.push_back(U[cpos].node);
-                                }
-                                for (size_t x = 0; x < grp.size(); ++x)
-                                    for (size_t y = 0; y < grp.size(); ++y)
-                                        if (x != y) {
-                                            unsigned short &e = adj[(size_t)grp[x] * nu + grp[y]];
-                                            if (e < 0xffff) ++e;
-                                        }
-                            }
-                    }
-                    // adjacency lists (node, weight) from the dense counts
-                    deg.assign(nu, 0);
-                    nb_ptr.assign(nu + 1, 0);
-                    nb_idx.clear();
-                    nb_w.clear();
-                    for (int a = 0; a < nu; ++a) {
-                        const unsigned short *row = &adj[(size_t)a * nu];
-                        int sum = 0;
-                        for (int b = 0; b < nu; ++b)
-                            if (row[b]) {
-                                sum += row[b];
-                                nb_idx.push_back(b);
-                                nb_w.push_back(row[b]);
-                            }
-                        deg[a] = sum;
-                        nb_ptr[a + 1] = (int)nb_idx.size();
-                    }
-                    order.resize(nu);
-                    std::iota(order.begin(), order.end(), 0);
-                    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return deg[a] > deg[b]; });
-                    bank.assign(nu, -1);
-                    int fill[NB] = {0};
-                    auto choose = [&](int a) {
-                        long long cost[NB] = {0};
-                        for (int q = nb_ptr[a]; q < nb_ptr[a + 1]; ++q)
-                            if (bank[nb_idx[q]] >= 0) cost[bank[nb_idx[q]]] += nb_w[q];
-                        int bestb = 0;
-                        for (int k = 1; k < NB; ++k)   // ties -> emptiest bank group (keeps the slot count low)
-                            if (cost[k] < cost[bestb] || (cost[k] == cost[bestb] && fill[k] < fill[bestb])) bestb = k;
-                        return bestb;
-                    };
-                    for (int a : order) {
-                        bank[a] = choose(a);
-                        ++fill[bank[a]];
-                    }
-                    for (int pass = 0; pass < 2; ++pass)
-                        for (int a : order) {
-                            --fill[bank[a]];
-                            bank[a] = -1;
-                            bank[a] = choose(a);
-                            ++fill[bank[a]];
-                        }
-                    int level[NB] = {0};
-                    nslots = 0;
-                    for (int q = 0; q < nu; ++q) {
-                        slot[q] = level[bank[q]]++ * NB + bank[q];
-                        nslots = std::max(nslots, slot[q] + 1);
-                    }
-                }
-                // second copy of the tile's records under an independent (pseudo-random) bank assignment: each distinct point a
-                // phase requests may then be read from either copy ("two choices"), which the emit loop below exploits.
-                // One generator runs through the tiles in order; a worker jumps it to its tile's position.
-                if (two_copies) {
-                    uint64_t lcg = lcg_jump(lcg0, lcg_skip[(size_t)t]);
-                    slot1.resize(nu);   // a random permutation of 0..nu-1: balanced bank groups, independent of copy 0
-                    std::iota(slot1.begin(), slot1.end(), 0);
-                    for (int q = nu - 1; q > 0; --q) {
-                        lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
-                        std::swap(slot1[q], slot1[(int)((lcg >> 33) % (uint64_t)(q + 1))]);
-                    }
-                    nslots = std::max(nslots, nu);
-                }
-                if (nslots + 1 > 4095) {
-                    T.err_slots = nslots;
-                    failed.store(true);
-                    break;
-                }
-                T.max_slot = std::max(T.max_slot, nslots);  // the dummy record takes slot `nslots`
-                // emit the slices
-                for (int si = 0; si < ns_tile; ++si) {
-                    const int64_t s = s0 + si;
-                    const int W = wl[2 * s], L = wl[2 * s + 1];
-                    T.maxW = std::max(T.maxW, W);
-                    T.maxL = std::max(T.maxL, L);
-                    T.nsteps += W;
-                    const size_t word_bytes = (size_t)W * kSlice * 2, wblk = (size_t)L * kSlice * 8;
-                    const size_t at0 = (size_t)boff[s];
-                    unsigned short *word = reinterpret_cast<unsigned short *>(blob.data() + at0);
-                    for (int q = 0; q < W * kSlice; ++q) word[q] = (unsigned short)nslots;  // dummy slot, empty mask
-                    for (int l = 0; l < kSlice; ++l) {
-                        const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
-                        for (size_t cpos = 0; cpos < U.size(); ++cpos)
-                            word[cpos * kSlice + l] = (unsigned short)(slot[U[cpos].node] | (U[cpos].mask << 12));
-                    }
-                    if (two_copies) {
-                        // per step and LDS.128 phase (8 lanes): the copy of each distinct point that minimises the largest number
-                        // of distinct addresses in one bank group (exhaustive over <= 2^8 choices)
-                        for (int cpos = 0; cpos < W; ++cpos)
-                            for (int ph = 0; ph < kSlice / NB; ++ph) {
-                                grp.clear();
-                                for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
-                                    const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
-                                    if ((size_t)cpos < U.size() && std::find(grp.begin(), grp.end(), U[cpos].node) == grp.end()) grp.push_back(U[cpos].node);
-                                }
-                                const int kk = (int)grp.size();
-                                if (kk < 2) continue;
-                                int best_bits = 0, best_max = 99;
-                                for (int bits = 0; bits < (1 << kk) && best_max > 1; ++bits) {
-                                    int cnt[NB] = {0}, mx = 0;
-                                    for (int q = 0; q < kk; ++q) mx = std::max(mx, ++cnt[((bits >> q) & 1 ? slot1[grp[q]] : slot[grp[q]]) % NB]);
-                                    if (mx < best_max) {
-                                        best_max = mx;
-                                        best_bits = bits;
-                                    }
-                                }
-                                for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
-                                    const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
-                                    if ((size_t)cpos >= U.size()) continue;
-                                    const int q = (int)(std::find(grp.begin(), grp.end(), U[cpos].node) - grp.begin());
-                                    if ((best_bits >> q) & 1)
-                                        word[(size_t)cpos * kSlice + l] = (unsigned short)(slot1[U[cpos].node] | (U[cpos].mask << 12) | 0x4000u);
-                                }
-                            }
-                    }
-                    for (int l = 0; l < kSlice; ++l) {
-                        for (int r = 0; r < R; ++r) {
-                            const int64_t d = (s * kSlice + l) * R + r;
-                            if (d >= nrows_dev) continue;
-                            const int64_t cr = caller_row(d);
-                            double *wx = reinterpret_cast<double *>(blob.data() + at0 + word_bytes + (size_t)r * wblk);
-                            double *wy = reinterpret_cast<double *>(blob.data() + at0 + word_bytes + (size_t)(R + r) * wblk);
-                            int pos = 0;
-                            for (int64_t p = A.ptr[cr]; p < A.ptr[cr + 1]; ++p, ++pos) {
-                                wx[(size_t)pos * kSlice + l] = A.wx[p];
-                                wy[(size_t)pos * kSlice + l] = A.wy[p];
-                            }
-                        }
-                    }
-                }
-                // the tile's union list and slot table; last entry = the dummy record (a finite state in u, zeros in g)
-                const size_t u0 = (size_t)uoff[t];
-                for (int q = 0; q < nu; ++q) {
-                    ulist[u0 + q] = cols[q];
-                    uslot[2 * (u0 + q)] = (unsigned short)slot[q];
-                    uslot[2 * (u0 + q) + 1] = (unsigned short)(two_copies ? slot1[q] : slot[q]);
-                }
-                ulist[u0 + nu] = (int)c->n_tot;
-                uslot[2 * (u0 + nu)] = (unsigned short)nslots;
-                uslot[2 * (u0 + nu) + 1] = (unsigned short)nslots;
-            }
-        }
-    });
-    int max_slot = 0, maxW = 0, maxL = 0;
-    int64_t nnz = 0, nsteps = 0;
-    for (const Totals &T : totals) {
-        if (T.err_slots) return fail(MFT_ENOTSUP, "union tile: %d slots in one block exceed the 12-bit slot field", T.err_slots);
-        max_slot = std::max(max_slot, T.max_slot);
-        maxW = std::max(maxW, T.maxW);
-        maxL = std::max(maxL, T.maxL);
-        nnz += T.nnz;
-        nsteps += T.nsteps;
-    }
-    out.R = R;
-    out.nslices = (int)nsl;
-    out.ntiles = (int)ntl;
-    out.maxW = maxW;
-    out.maxL = maxL;
-    out.sstride = ((max_slot + 1 + 7) / 8) * 8;
-    out.nnz = nnz;
-    out.nsteps = nsteps;
-    out.ncopy = two_copies ? 2 : 1;
-    if (ulist.empty()) {
-        ulist.push_back(0);
-        uslot.push_back(0);
-        uslot.push_back(0);
-    }
-    return MFT_OK;
-}
-
-static int build_tiler(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, int R, bool colour, bool two_copies, DevTileR &out)
-{
-    HostTileR h;
-    CHECK(build_tiler_host(c, A, nrows_dev, R, colour, two_copies, h));
-    out.ncopy = h.ncopy;
-    out.R = h.R;
-    out.nslices = h.nslices;
-    out.ntiles = h.ntiles;
-    out.maxW = h.maxW;
-    out.maxL = h.maxL;
-    out.sstride = h.sstride;
-    out.nnz = h.nnz;
-    out.nunion = (int64_t)h.ulist.size();
-    out.nsteps = h.nsteps;
-    CHECK(out.blob.upload(h.blob));
-    CHECK(out.boff.upload(h.boff));
-    CHECK(out.wl.upload(h.wl));
-    CHECK(out.uoff.upload(h.uoff));
-    CHECK(out.ulist.upload(h.ulist));
-    CHECK(out.uslot.upload(h.uslot));
-    return MFT_OK;
-}
-
-// Host-only self test of the union-tile format (no CUDA calls): a random banded operator is laid out by
-// build_tiler_host, then the kernels' walk (step words, row masks, per-row weight cursors, slot table) is replayed on
-// the CPU and compared bit for bit with the plain row sums in summation order.  Returns 0 when identical.
-extern "C" int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int with_perm, unsigned seed, double *stats4)
-{
-    if (n <= 0 || k <= 0 || k > n || (R != 1 && R != 2 && R != 4)) return fail(MFT_EINVAL, "mft_debug_tile_selftest: bad arguments");
-    NvtxRange range("tile layout selftest");
-    mft_ctx ctx;
-    ctx.n_local = n - n / 7;  // some trailing "halo" columns without rows
-    ctx.n_halo = n - ctx.n_local;
-    ctx.n_tot = n;
-    ctx.V = 4;
-    uint64_t st = seed * 6364136223846793005ULL + 1442695040888963407ULL;
-    auto rnd = [&]() { st = st * 6364136223846793005ULL + 1442695040888963407ULL; return (uint32_t)(st >> 33); };
-    if (with_perm) {
-        ctx.have_perm = true;
-        ctx.perm.resize(n);
-        std::iota(ctx.perm.begin(), ctx.perm.end(), 0);
-        // shuffle inside windows so that locality survives (device rows near each other stay near)
-        for (int64_t b = 0; b < ctx.n_local; b += 64)
-            for (int64_t i = std::min(ctx.n_local, b + 64) - 1; i > b; --i) std::swap(ctx.perm[i], ctx.perm[b + rnd() % (i - b + 1)]);
-        ctx.iperm.resize(n);
-        for (int64_t d = 0; d < n; ++d) ctx.iperm[ctx.perm[d]] = (int32_t)d;
-        ctx.keys.resize(n);
-        for (int64_t i = 0; i < n; ++i) ctx.keys[i] = (int64_t)(n - 1 - i) * 3;  // descending keys: order != column order
-    }
-    Csr2 A;
-    A.nrows = n;
-    A.ptr.assign(n + 1, 0);
-    for (int64_t r = 0; r < n; ++r) {
-        const int len = r < ctx.n_local ? std::max(1, k - (int)(rnd() % 4)) : 0;   // ragged rows
-        std::vector<int32_t> cs;
-        while ((int)cs.size() < len) {
-            const int64_t j = std::min<int64_t>(n - 1, std::max<int64_t>(0, r + (int64_t)(rnd() % (6 * k)) - 3 * k));
-            if (std::find(cs.begin(), cs.end(), (int32_t)j) == cs.end()) cs.push_back((int32_t)j);
-        }
-        auto keyf = [&](int32_t col) { return ctx.keys.empty() ? (int64_t)col : ctx.keys[col]; };
-        std::sort(cs.begin(), cs.end(), [&](int32_t a, int32_t b) { return keyf(a) < keyf(b); });
-        for (int32_t j : cs) {
-            A.col.push_back(j);
-            A.wx.push_back((double)(int)(rnd() % 2001 - 1000) / 64.0);
-            A.wy.push_back((double)(int)(rnd() % 2001 - 1000) / 32.0);
-        }
-        A.ptr[r + 1] = (int64_t)A.col.size();
-    }
-    HostTileR h;
-    const auto t_build0 = std::chrono::steady_clock::now();
-    CHECK(build_tiler_host(&ctx, A, ctx.n_local, R, (layout & 1) != 0, (layout & 2) != 0, h));
-    if (getenv("MFT_TRACE")) {   // build time + a checksum of the whole layout (compare builds / thread counts)
-        uint64_t fnv = 1469598103934665603ULL;
-        auto mix = [&](const void *p, size_t bytes) {
-            const unsigned char *b = static_cast<const unsigned char *>(p);
-            for (size_t i = 0; i < bytes; ++i) fnv = (fnv ^ b[i]) * 1099511628211ULL;
-        };
-        mix(h.blob.data(), h.blob.size());
-        mix(h.boff.data(), h.boff.size() * sizeof(long long));
-        mix(h.wl.data(), h.wl.size() * sizeof(int));
-        mix(h.uoff.data(), h.uoff.size() * sizeof(int));
-        mix(h.ulist.data(), h.ulist.size() * sizeof(int));
-        mix(h.uslot.data(), h.uslot.size() * sizeof(unsigned short));
-        const int meta[7] = {h.R, h.nslices, h.ntiles, h.maxW, h.maxL, h.sstride, h.ncopy};
-        mix(meta, sizeof meta);
-        fprintf(stderr, "[mft] tile layout: n=%lld k=%d R=%d layout=%d perm=%d  build %.3f s  fnv %016llx\n", (long long)n, k, R, layout, with_perm,
-                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_build0).count(), (unsigned long long)fnv);
-    }
-    std::vector<double> x((size_t)n + 1);
-    for (auto &v : x) v = (double)(int)(rnd() % 4001 - 2000) / 128.0;   // indexed by DEVICE column; x[n] = dummy record
-    auto caller_row = [&](int64_t d) -> int64_t { return ctx.have_perm ? ctx.perm[d] : d; };
-    auto dev_col = [&](int64_t j) -> int64_t { return ctx.have_perm ? ctx.iperm[j] : j; };
-    int64_t bad = 0, conflicts = 0, phases = 0;
-    std::vector<double> smem((size_t)h.sstride * 2);
-    for (int t = 0; t < h.ntiles; ++t) {
-        std::fill(smem.begin(), smem.end(), std::nan(""));
-        const int u0 = h.uoff[t], nu = h.uoff[t + 1] - u0;
-        for (int q = 0; q < nu; ++q) {
-            if (h.uslot[2 * (u0 + q)] >= h.sstride || h.uslot[2 * (u0 + q) + 1] >= h.sstride) return fail(MFT_EINVAL, "selftest: slot beyond sstride");
-            if (q > 0 && q < nu - 1 && h.ulist[u0 + q] <= h.ulist[u0 + q - 1]) return fail(MFT_EINVAL, "selftest: union list not ascending");
-            smem[h.uslot[2 * (u0 + q)]] = x[h.ulist[u0 + q]];
-            if (h.ncopy == 2) smem[h.sstride + h.uslot[2 * (u0 + q) + 1]] = x[h.ulist[u0 + q]];
-        }
-        if (h.ulist[u0 + nu - 1] != n) return fail(MFT_EINVAL, "selftest: tile list does not end with the dummy record");
-        const uint32_t dword = h.uslot[2 * (u0 + nu - 1)];
-        for (int w = 0; w < kTileWarps; ++w) {
-            const int64_t s = (int64_t)t * kTileWarps + w;
-            if (s >= h.nslices) break;
-            const int W = h.wl[2 * s], L = h.wl[2 * s + 1];
-            const unsigned char *src = h.blob.data() + h.boff[s];
-            const unsigned short *word = reinterpret_cast<const unsigned short *>(src);
-            const double *wx = reinterpret_cast<const double *>(src + (size_t)W * kSlice * 2);
-            const double *wy = wx + (size_t)R * L * kSlice;
-            for (int c0 = 0; c0 < W; ++c0)
-                for (int ph = 0; ph < 4; ++ph) {   // bank-conflict degree of this LDS.128 phase
-                    int cnt[8] = {0}, seen[8], ns = 0;
-                    for (int l = ph * 8; l < ph * 8 + 8; ++l) {
-                        const int sl = word[c0 * kSlice + l] & 0x4fff;   // slot + copy bit: distinct addresses
-                        bool dup = false;
-                        for (int q = 0; q < ns; ++q) dup |= seen[q] == sl;
-                        if (!dup) { seen[ns++] = sl; ++cnt[(sl & 0xfff) % 8]; }
-                    }
-                    conflicts += *std::max_element(cnt, cnt + 8);
-                    ++phases;
-                }
-            for (int l = 0; l < kSlice; ++l) {
-                double ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0};
-                int pos[4] = {0, 0, 0, 0};
-                for (int c0 = 0; c0 < W + 3; ++c0) {   // + batch tail steps
-                    const uint32_t wd = c0 < W ? word[c0 * kSlice + l] : dword;
-                    const double xv = smem[(wd & 0xfff) + ((R <= 2 && (wd & 0x4000u)) ? (size_t)h.sstride : 0)];
-                    for (int r = 0; r < R; ++r) {
-                        const bool m = (wd >> (12 + r)) & 1u;
-                        const double w1 = m ? wx[((size_t)r * L + pos[r]) * kSlice + l] : 0.0;
-                        const double w2 = m ? wy[((size_t)r * L + pos[r]) * kSlice + l] : 0.0;
-                        pos[r] += m;
-                        ax[r] = ax[r] + w1 * xv;
-                        ay[r] = ay[r] + w2 * xv;
-                    }
-                }
-                for (int r = 0; r < R; ++r) {
-                    const int64_t d = (s * kSlice + l) * R + r;
-                    if (d >= ctx.n_local) continue;
-                    const int64_t cr = caller_row(d);
-                    double rx = 0.0, ry = 0.0;
-                    for (int64_t p = A.ptr[cr]; p < A.ptr[cr + 1]; ++p) {
-                        rx = rx + A.wx[p] * x[dev_col(A.col[p])];
-                        ry = ry + A.wy[p] * x[dev_col(A.col[p])];
-                    }
-                    if (!(rx == ax[r] && ry == ay[r]) || pos[r] != (int)(A.ptr[cr + 1] - A.ptr[cr])) ++bad;
-                }
-            }
-        }
-    }
-    if (stats4) {
-        stats4[0] = phases ? (double)conflicts / (double)phases : 0.0;   // mean LDS.128 conflict degree
-        stats4[1] = (double)h.nsteps * kSlice / (double)std::max<int64_t>(1, ctx.n_local);  // union steps per row
-        stats4[2] = (double)h.ulist.size() / (double)std::max<int64_t>(1, ctx.n_local);    // union entries per row
-        stats4[3] = (double)h.sstride;
-    }
-    if (bad) return fail(MFT_EINVAL, "mft_debug_tile_selftest: %lld rows differ", (long long)bad);
-    return MFT_OK;
-}
+#include "mft_layout_host.inl"
 
 static bool has_visc(const mft_ctx *c)
 {
@@ -2281,341 +1527,7 @@ extern "C" int mft_boundary_pass(mft_ctx *c, double t, double *const *u_soa, dou
     return MFT_OK;
 }
 
-// ------------------------------------------------------------------------------------------------------
-// history + time stepping
-// ------------------------------------------------------------------------------------------------------
-// time_deriv_weights! history.jl:131-152: w = scale * (A' \ b'), LU with partial pivoting
-static void time_deriv_weights(int m, const double *t, double *w)
-{
-    double maxabs = 0.0;
-    for (int i = 0; i < m; ++i) maxabs = std::fmax(maxabs, std::fabs(t[i]));
-    const double scale = 1.0 / maxabs;
-    double ts[8], M[64], b[8];
-    for (int i = 0; i < m; ++i) ts[i] = t[i] * scale;
-    for (int k = 0; k < m; ++k) {
-        for (int i = 0; i < m; ++i) M[k * m + i] = std::pow(ts[i], (double)k);
-        b[k] = (double)k * std::pow(ts[0], (double)(k - 1));
-    }
-    for (int col = 0; col < m; ++col) {
-        int piv = col;
-        double best = std::fabs(M[col * m + col]);
-        for (int r = col + 1; r < m; ++r)
-            if (std::fabs(M[r * m + col]) > best) {
-                best = std::fabs(M[r * m + col]);
-                piv = r;
-            }
-        if (piv != col) {
-            for (int j = 0; j < m; ++j) std::swap(M[col * m + j], M[piv * m + j]);
-            std::swap(b[col], b[piv]);
-        }
-        for (int r = col + 1; r < m; ++r) {
-            const double l = M[r * m + col] / M[col * m + col];
-            M[r * m + col] = l;
-            for (int j = col + 1; j < m; ++j) M[r * m + j] = M[r * m + j] - l * M[col * m + j];
-            b[r] = b[r] - l * b[col];
-        }
-    }
-    for (int r = m - 1; r >= 0; --r) {
-        double s = b[r];
-        for (int j = r + 1; j < m; ++j) s = s - M[r * m + j] * b[j];
-        b[r] = s / M[r * m + r];
-    }
-    for (int i = 0; i < m; ++i) w[i] = scale * b[i];
-}
-
-static int history_push_common(mft_ctx *c, double t, int64_t success_iter, bool given, int nterms,
-                               const double *weights_or_null, int approx_order)
-{
-    if (c->nslots == 0) return MFT_OK;  // modify_cache! fallback: no-op without a residual-viscosity source (history.jl:87-89)
-    NvtxRange range("update history");
-    c->success_iter = success_iter;
-    // shift_soln_history! history.jl:105-111 as a ring buffer: slot 0 = most recent
-    c->hist_head = (c->hist_head + c->nslots - 1) % c->nslots;
-    for (int s = c->nslots - 1; s >= 1; --s) c->time_history[s] = c->time_history[s - 1];
-    c->time_history[0] = t;
-    const int64_t len = c->n_tot * c->V;
-    CU(cudaMemcpyAsync(c->hist[c->hist_head].p, c->u.p, sizeof(double) * len, cudaMemcpyDeviceToDevice, c->stream));
-    // update_approx_du! history.jl:113-129
-    ApproxDuArgs a{};
-    a.out = c->approx_du.p;
-    a.len = len;
-    a.nterms = 0;
-    if (success_iter > 0) {
-        int ntp = nterms;
-        if (!given) {
-            ntp = (int)std::min<int64_t>(success_iter + 1, (int64_t)approx_order + 1);
-            if (ntp > c->nslots) return fail(MFT_EINVAL, "mft_history_push: approx_order+1 = %d exceeds polydeg+1 = %d history slots", approx_order + 1, c->nslots);
-            time_deriv_weights(ntp, c->time_history.data(), c->time_weights.data());
-        } else {
-            if (ntp > c->nslots || ntp > 8) return fail(MFT_EINVAL, "mft_history_push_weights: %d weights exceed %d history slots", ntp, c->nslots);
-            for (int i = 0; i < ntp; ++i) c->time_weights[i] = weights_or_null[i];
-        }
-        a.nterms = ntp;
-        for (int s = 0; s < ntp; ++s) {
-            a.hist[s] = c->hist[(c->hist_head + s) % c->nslots].p;
-            a.w[s] = c->time_weights[s];
-        }
-    }
-    {
-        ScopedTimer tm(c, MFT_K_OTHER);
-        k_approx_du<<<c->red_blocks * 2, 256, 0, c->stream>>>(a);
-        c->launches++;
-        LAUNCH_CHECK();
-    }
-    return MFT_OK;  // asynchronous (stream order); downloads / mft_synchronize wait
-}
-
-extern "C" int mft_history_push(mft_ctx *c, double t, int64_t success_iter, int approx_order)
-{
-    NEED_CTX(c);
-    CHECK(mft_finalize(c));
-    if (approx_order < 0 || approx_order > 7) return fail(MFT_EINVAL, "mft_history_push: approx_order must be in [0,7]");
-    return history_push_common(c, t, success_iter, false, 0, nullptr, approx_order);
-}
-
-extern "C" int mft_history_push_weights(mft_ctx *c, double t, int64_t success_iter, int n, const double *weights)
-{
-    NEED_CTX(c);
-    CHECK(mft_finalize(c));
-    if (n < 0 || (n > 0 && !weights)) return fail(MFT_EINVAL, "mft_history_push_weights: bad weights");
-    return history_push_common(c, t, success_iter, true, n, weights, 0);
-}
-
-static int launch_limiter(mft_ctx *c, int npairs, const double *thresholds, const int *variables);
-
-static int launch_stage(mft_ctx *c, int stage, double dt)
-{
-    NvtxRange range("SSPRK stage update");
-    ScopedTimer tm(c, MFT_K_STAGE);
-    const int64_t len = c->n_local * c->V;
-    k_ssprk33_stage<<<c->red_blocks * 2, 256, 0, c->stream>>>(stage, dt, c->uprev.p, c->du.p, c->u.p, len);
-    c->launches++;
-    LAUNCH_CHECK();
-    // stage_limiter!(u, integrator, p, t) after every stage update (OrdinaryDiffEq SSPRK33(stage_limiter!))
-    if (!c->stage_lim_variables.empty())
-        CHECK(launch_limiter(c, (int)c->stage_lim_variables.size(), c->stage_lim_thresholds.data(), c->stage_lim_variables.data()));
-    return MFT_OK;
-}
-
-static int ssprk33_step_launches(mft_ctx *c, double t, double dt, bool first_rhs)
-{
-    if (first_rhs) CHECK(rhs_device(c, t));  // k = f(u_n): first step only (FSAL afterwards)
-    CHECK(launch_stage(c, 1, dt));
-    CHECK(rhs_device(c, t + dt));
-    CHECK(launch_stage(c, 2, dt));
-    CHECK(rhs_device(c, t + dt / 2));
-    CHECK(launch_stage(c, 3, dt));
-    CHECK(rhs_device(c, t + dt));
-    return MFT_OK;
-}
-
-extern "C" int mft_ssprk_step(mft_ctx *c, int scheme, double t, double dt)
-{
-    NEED_CTX(c);
-    CHECK(mft_finalize(c));
-    if (scheme != MFT_SSPRK33) return fail(MFT_ENOTSUP, "mft_ssprk_step: only MFT_SSPRK33 is implemented");
-    const bool first = !c->have_fsal;
-    c->have_fsal = true;
-    // The step is a fixed sequence of ~35 launches: replay it as one CUDA graph (the kernel arguments that vary
-    // between steps -- dt and the success_iter==0 flag -- are part of the cache key; t only selects Dirichlet tables,
-    // which the caller refreshes).  Eager path: per-kernel timing on, multi-rank (NCCL calls), or first use of a key.
-    const bool graph_ok = c->use_graphs && !c->timing && (c->nranks == 1 || c->p2p || c->use_graphs >= 2);
-    if (!graph_ok) return ssprk33_step_launches(c, t, dt, first);
-    const int si_zero = c->success_iter == 0;
-    mft_ctx::StepGraph *g = nullptr;
-    for (auto &e : c->graphs)
-        if (e.dt == dt && e.si_zero == si_zero && e.with_first_rhs == (int)first) g = &e;
-    if (!g) {
-        c->graphs.push_back(mft_ctx::StepGraph{dt, si_zero, (int)first, 0, 0, nullptr});
-        g = &c->graphs.back();
-    }
-    g->uses++;
-    if (g->uses == 1) return ssprk33_step_launches(c, t, dt, first);  // warm (also sets per-kernel smem attributes)
-    if (!g->exec) {
-        const int64_t l0 = c->launches;
-        cudaGraph_t graph = nullptr;
-        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = ssprk33_step_launches(c, t, dt, first);
-        const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
-        if (rc != MFT_OK) {
-            if (graph) cudaGraphDestroy(graph);
-            return rc;
-        }
-        if (ce != cudaSuccess) return fail(MFT_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
-        g->nlaunch = c->launches - l0;
-        c->launches = l0;
-        CU(cudaGraphInstantiate(&g->exec, graph, 0));
-        CU(cudaGraphDestroy(graph));
-    }
-    CU(cudaGraphLaunch(g->exec, c->stream));
-    c->launches += g->nlaunch;
-    return MFT_OK;  // asynchronous: mft_synchronize / downloads wait
-}
-
-// ---- Zhang-Shu positivity limiter (row f4; positivity_zhang_shu_point2d.jl:22-82, positivity_zhang_shu.jl:50-72) --------
-extern "C" int mft_set_neighbors(mft_ctx *c, const int64_t *nbr1)
-{
-    NEED_CTX(c);
-    if (!nbr1) return fail(MFT_EINVAL, "mft_set_neighbors: NULL array");
-    if (c->k <= 0) return fail(MFT_EINVAL, "mft_set_neighbors: ctx was created with k=%d", c->k);
-    const int64_t n = c->n_local, k = c->k;
-    c->host_nbr.resize((size_t)(n * k));
-    for (int64_t p = 0; p < n * k; ++p) {
-        const int64_t j = nbr1[p] - 1;
-        if (j < 0 || j >= c->n_tot) return fail(MFT_EINVAL, "mft_set_neighbors: neighbour %lld out of range", (long long)nbr1[p]);
-        c->host_nbr[(size_t)p] = (int32_t)j;
-    }
-    // captured steps may hold the old table's address: start over
-    for (auto &g : c->graphs)
-        if (g.exec) cudaGraphExecDestroy(g.exec);
-    c->graphs.clear();
-    c->zs_nbr.release();  // rebuilt (device numbering) at the next limiter call
-    return MFT_OK;
-}
-
-static int zs_prepare(mft_ctx *c)
-{
-    if (c->V != 4 || c->eq != MFT_EQ_EULER2D) return fail(MFT_ENOTSUP, "Zhang-Shu limiter: Euler 2-D only");
-    if (c->host_nbr.empty()) return fail(MFT_EINVAL, "Zhang-Shu limiter: mft_set_neighbors was not called");
-    if (c->zs_nbr.p) return MFT_OK;
-    const int64_t n = c->n_local, k = c->k;
-    std::vector<int> tab((size_t)(n * k));
-    for (int64_t d = 0; d < n; ++d) {
-        const int64_t r = c->have_perm ? c->perm[d] : d;  // device row d holds caller point r
-        for (int64_t q = 0; q < k; ++q) {
-            const int32_t j = c->host_nbr[(size_t)(r * k + q)];
-            tab[(size_t)(q * n + d)] = c->have_perm ? c->iperm[j] : j;
-        }
-    }
-    CHECK(c->zs_nbr.upload(tab));
-    CHECK(c->zs_tmp.alloc(n * c->V));
-    CHECK(c->zs_flag.alloc(n));
-    return MFT_OK;
-}
-
-// one limiter call = one pass per (threshold, variable) pair, in order, each pass on the state the previous one left
-static int launch_limiter(mft_ctx *c, int npairs, const double *thresholds, const int *variables)
-{
-    CHECK(zs_prepare(c));
-    ScopedTimer tm(c, MFT_K_OTHER);
-    const int64_t n = c->n_local;
-    for (int i = 0; i < npairs; ++i) {
-        if (variables[i] != ZS_VAR_DENSITY && variables[i] != ZS_VAR_PRESSURE) return fail(MFT_EINVAL, "Zhang-Shu limiter: unknown variable %d", variables[i]);
-        // multi-rank: the pass reads u at every stencil point of the owned rows -> refresh the halo copies first (the stage
-        // update / the previous pass changed the owners' values).  Same exchange as at the start of rhs!; the credit protocol
-        // of the peer-memory path allows any stream-ordered sequence of exchanges as long as all ranks issue the same one.
-        CHECK(halo_exchange<4>(c, c->u.p));
-        ZsArgs a{c->zs_nbr.p, c->k, n, c->u.p, c->zs_tmp.p, c->zs_flag.p, thresholds[i], c->eqp[0], variables[i]};
-        k_zs_detect<<<grid_for(n, 128), 128, 0, c->stream>>>(a);
-        k_zs_apply<<<grid_for(n, 256), 256, 0, c->stream>>>(n, c->zs_flag.p, c->zs_tmp.p, c->u.p);
-        c->launches += 2;
-        LAUNCH_CHECK();
-    }
-    return MFT_OK;
-}
-
-extern "C" int mft_limiter_zhang_shu(mft_ctx *c, int npairs, const double *thresholds, const int *variables,
-                                     double *const *u_soa, int mem)
-{
-    NEED_CTX(c);
-    CHECK(mft_finalize(c));
-    if (npairs < 0 || (npairs > 0 && (!thresholds || !variables))) return fail(MFT_EINVAL, "mft_limiter_zhang_shu: bad arguments");
-    if (mem == MFT_MEM_HOST) {
-        CHECK(upload_soa(c, u_soa, c->u.p));
-    } else if (mem != MFT_MEM_DEVICE) {
-        return fail(MFT_EINVAL, "mft_limiter_zhang_shu: mem must be MFT_MEM_HOST or MFT_MEM_DEVICE");
-    }
-    c->have_fsal = false;  // u changed: f(u) has to be recomputed
-    CHECK(launch_limiter(c, npairs, thresholds, variables));
-    if (mem == MFT_MEM_HOST) {
-        CHECK(download_soa(c, c->u.p, u_soa));
-        CU(cudaStreamSynchronize(c->stream));
-    }
-    return MFT_OK;
-}
-
-extern "C" int mft_set_stage_limiter(mft_ctx *c, int npairs, const double *thresholds, const int *variables)
-{
-    NEED_CTX(c);
-    if (npairs < 0 || (npairs > 0 && (!thresholds || !variables))) return fail(MFT_EINVAL, "mft_set_stage_limiter: bad arguments");
-    c->stage_lim_thresholds.assign(thresholds, thresholds + npairs);
-    c->stage_lim_variables.assign(variables, variables + npairs);
-    // captured steps bake the launch sequence in: start over
-    for (auto &g : c->graphs)
-        if (g.exec) cudaGraphExecDestroy(g.exec);
-    c->graphs.clear();
-    return MFT_OK;
-}
-
-// ---- SSPRK43 with embedded error estimate (the integrator the reference names: rbfsolver_test.jl:104-107) ------------
-// The library does the four stages and returns the LOCAL sum of squared scaled errors and the local entry count; the
-// caller combines ranks (sum both), forms EEst = sqrt(sumsq/count) (ode_norm, src/auxiliary/mpi.jl:15-19) and runs its
-// own step-size controller (OrdinaryDiffEq's stays in charge in the Julia deployment), then commits or rolls back
-// with mft_step_commit.
-extern "C" int mft_ssprk43_step(mft_ctx *c, double t, double dt, double abstol, double reltol, double *sumsq_out,
-                                int64_t *count_out)
-{
-    NEED_CTX(c);
-    CHECK(mft_finalize(c));
-    if (c->step_pending) return fail(MFT_EINVAL, "mft_ssprk43_step: previous step was neither committed nor rejected (mft_step_commit)");
-    if (!c->stage_lim_variables.empty()) return fail(MFT_ENOTSUP, "mft_ssprk43_step: the stage limiter is wired into mft_ssprk_step (SSPRK33) only");
-    const int64_t len = c->n_local * c->V, len_tot = c->n_tot * c->V;
-    if (!c->utilde.p) {
-        CHECK(c->utilde.alloc(len_tot));
-        CHECK(c->kfsal.alloc(len_tot));
-        CHECK(c->u_save.alloc(len_tot + c->V));
-        CU(cudaMemsetAsync(c->utilde.p, 0, sizeof(double) * len_tot, c->stream));
-    }
-    if (!c->have_fsal) CHECK(rhs_device(c, t));  // k = f(u_n, t)
-    c->have_fsal = true;
-    // keep f(u_n) and u_n (rhs! also rewrites boundary / halo entries of u) for a possible rejection
-    CU(cudaMemcpyAsync(c->kfsal.p, c->du.p, sizeof(double) * len_tot, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->u_save.p, c->u.p, sizeof(double) * len_tot, cudaMemcpyDeviceToDevice, c->stream));
-    const int grid = c->red_blocks * 2;
-    auto stage = [&](int st) -> int {
-        ScopedTimer tm(c, MFT_K_STAGE);
-        k_ssprk43_stage<<<grid, 256, 0, c->stream>>>(st, dt, c->uprev.p, c->du.p, c->u.p, c->utilde.p, len);
-        c->launches++;
-        LAUNCH_CHECK();
-        return MFT_OK;
-    };
-    CHECK(stage(1));
-    CHECK(rhs_device(c, t + dt / 2));
-    CHECK(stage(2));
-    CHECK(rhs_device(c, t + dt));
-    CHECK(stage(3));
-    CHECK(rhs_device(c, t + dt / 2));
-    CHECK(stage(4));
-    {
-        ScopedTimer tm(c, MFT_K_REDUCE);
-        k_error_sumsq<<<c->red_blocks, 256, 0, c->stream>>>(c->utilde.p, c->uprev.p, c->u.p, len, abstol, reltol, c->partial.p,
-                                                         c->ticket.p + 2, c->stats.p + 3 * c->V);
-        c->launches++;
-        LAUNCH_CHECK();
-    }
-    CHECK(rhs_device(c, t + dt));  // FSAL: k = f(u_{n+1}, t+dt)
-    double ss = 0.0;
-    CU(cudaMemcpyAsync(&ss, c->stats.p + 3 * c->V, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (sumsq_out) *sumsq_out = ss;
-    if (count_out) *count_out = len;
-    c->step_pending = true;
-    return MFT_OK;
-}
-
-// accept != 0: keep u_{n+1} and its f; accept == 0: restore u_n and f(u_n) (a rejected step leaves no trace)
-extern "C" int mft_step_commit(mft_ctx *c, int accept)
-{
-    NEED_CTX(c);
-    if (!c->step_pending) return fail(MFT_EINVAL, "mft_step_commit: no step pending");
-    if (!accept) {
-        const int64_t len_tot = c->n_tot * c->V;
-        CU(cudaMemcpyAsync(c->u.p, c->u_save.p, sizeof(double) * len_tot, cudaMemcpyDeviceToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->du.p, c->kfsal.p, sizeof(double) * len_tot, cudaMemcpyDeviceToDevice, c->stream));
-    }
-    c->step_pending = false;
-    return MFT_OK;
-}
+#include "mft_time_loop.inl"
 
 extern "C" int mft_synchronize(mft_ctx *c)
 {
@@ -2829,204 +1741,4 @@ extern "C" int mft_sfc_order(int64_t n, const double *x, const double *y, int64_
     return MFT_OK;
 }
 
-// ------------------------------------------------------------------------------------------------------
-// multi-GPU: NCCL (loaded at run time so single-GPU users do not need libnccl)
-// ------------------------------------------------------------------------------------------------------
-extern "C" int mft_nccl_unique_id(void *id128)
-{
-    if (!id128) return fail(MFT_EINVAL, "mft_nccl_unique_id: NULL");
-    NcclApi *N = nccl_api();
-    if (!N) return fail(MFT_ENCCL, "NCCL could not be loaded: %s", nccl_load_error());
-    if (N->getUniqueId(id128) != 0) return fail(MFT_ENCCL, "ncclGetUniqueId failed");
-    return MFT_OK;
-}
-
-extern "C" int mft_comm_init(mft_ctx *c, int nranks, int rank, const void *id128)
-{
-    NEED_CTX(c);
-    if (nranks < 1 || rank < 0 || rank >= nranks || !id128) return fail(MFT_EINVAL, "mft_comm_init: bad arguments");
-    NcclApi *N = nccl_api();
-    if (!N) return fail(MFT_ENCCL, "NCCL could not be loaded: %s", nccl_load_error());
-    c->nccl = N;
-    if (N->commInitRank(&c->comm, nranks, id128, rank) != 0) return fail(MFT_ENCCL, "ncclCommInitRank failed");
-    c->nranks = nranks;
-    c->rank = rank;
-    CHECK(c->gather_buf.alloc((int64_t)2 * nranks * c->V + 4 * c->V));
-    // global point count (ndofs of the parallel domain, parallel_rbfsolver.jl:10-13) = sum of the owned counts
-    double nl = (double)c->n_local, ng = 0.0;
-    CU(cudaMemcpy(c->gather_buf.p, &nl, sizeof(double), cudaMemcpyHostToDevice));
-    if (N->allReduce(c->gather_buf.p, c->gather_buf.p + 1, 1, NCCL_DOUBLE, NCCL_SUM, c->comm, c->stream) != 0)
-        return fail(MFT_ENCCL, "ncclAllReduce failed: %s", N->lastError(c->comm));
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaMemcpy(&ng, c->gather_buf.p + 1, sizeof(double), cudaMemcpyDeviceToHost));
-    c->n_global = (int64_t)(ng + 0.5);
-    return MFT_OK;
-}
-
-extern "C" int mft_set_halo(mft_ctx *c, int npeers, const int *peers, const int64_t *send_off, const int64_t *send_idx1,
-                            const int64_t *recv_count)
-{
-    NEED_CTX(c);
-    if (npeers < 0 || (npeers > 0 && (!peers || !send_off || !recv_count))) return fail(MFT_EINVAL, "mft_set_halo: bad arguments");
-    c->peers.assign(peers, peers + npeers);
-    c->send_off.assign(send_off, send_off + npeers + 1);
-    c->recv_off.assign(npeers + 1, 0);
-    for (int p = 0; p < npeers; ++p) c->recv_off[p + 1] = c->recv_off[p] + recv_count[p];
-    if (c->recv_off[npeers] != c->n_halo) return fail(MFT_EINVAL, "mft_set_halo: receive counts sum to %lld, n_halo is %lld", (long long)c->recv_off[npeers], (long long)c->n_halo);
-    c->n_send = npeers > 0 ? c->send_off[npeers] : 0;
-    std::vector<int> rows((size_t)c->n_send);
-    for (int64_t i = 0; i < c->n_send; ++i) {
-        const int64_t p = send_idx1[i] - 1;
-        if (p < 0 || p >= c->n_local) return fail(MFT_EINVAL, "mft_set_halo: send index %lld is not an owned point", (long long)send_idx1[i]);
-        rows[i] = c->have_perm ? c->iperm[p] : (int)p;
-    }
-    CHECK(c->send_rows.upload(rows));
-    CHECK(c->send_buf.alloc(std::max<int64_t>(1, c->n_send) * 2 * c->V));
-    return MFT_OK;
-}
-
-// peer-memory norms in three separately launchable parts: 0 = local sum + publish, 1 = wait sums, max deviation from the
-// global mean + publish, 2 = wait candidates and stage them for pass A
-static int p2p_norms_part(mft_ctx *c, int part)
-{
-    ScopedTimer t(c, MFT_K_REDUCE);
-    const int V = 4;
-    const int64_t n = c->n_local;
-    const Vec<4> *u = reinterpret_cast<const Vec<4> *>(c->u.p);
-    P2PLocal *L = reinterpret_cast<P2PLocal *>(c->p2p_local.p);
-    if (part == 0) {
-        k_p2p_sum<<<c->red_blocks, 256, 0, c->stream>>>(u, n, c->partial.p, c->peers_dev, L);
-    } else if (part == 1) {
-        k_p2p_wait_norms<<<1, 32, 0, c->stream>>>(c->peers_dev, L, 0, nullptr);
-        c->launches++;
-        const double ng = (double)c->n_global;
-        const double divisor = c->mean_div_vn ? (double)V * ng : ng;
-        if (c->max_lex) k_p2p_maxdev<true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, divisor, c->partial.p, c->peers_dev, L, c->stats.p + V);
-        else k_p2p_maxdev<false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, divisor, c->partial.p, c->peers_dev, L, c->stats.p + V);
-    } else {
-        k_p2p_wait_norms<<<1, 32, 0, c->stream>>>(c->peers_dev, L, 1, c->gather_buf.p + (int64_t)c->nranks * V);
-    }
-    c->launches++;
-    LAUNCH_CHECK();
-    return MFT_OK;
-}
-
-// global ode_mean / ode_maximum across ranks (MPI.Allreduce in src/auxiliary/mpi.jl:45-46,76): every rank reduces its
-// owned points, the per-rank results are all-gathered, and the CONSUMER kernel combines them in rank order
-// (k_maxdev_norms forms the mean from the gathered sums, pass A forms the norms from the gathered candidates):
-// two kernels + two tiny all-gathers per stage.
-static int launch_norms_multi(mft_ctx *c)
-{
-    ScopedTimer t(c, MFT_K_REDUCE);
-    const int V = 4;
-    NcclApi *N = c->nccl;
-    if (c->p2p) {
-        CHECK(p2p_norms_part(c, 0));
-        CHECK(p2p_norms_part(c, 1));
-        return p2p_norms_part(c, 2);
-    }
-    if (!c->comm) return fail(MFT_EINVAL, "multi-rank norms need mft_comm_init");
-    const int64_t n = c->n_local;
-    const Vec<4> *u = reinterpret_cast<const Vec<4> *>(c->u.p);
-    double *gsum = c->gather_buf.p;                              // nranks x V
-    double *gmax = c->gather_buf.p + (int64_t)c->nranks * V;     // nranks x V
-    double *mine = c->gather_buf.p + (int64_t)2 * c->nranks * V; // 2V scratch (sum | mean, unused)
-    double *mine2 = mine + 2 * V;                                // V scratch
-    k_sum_mean<4><<<c->red_blocks, 256, 0, c->stream>>>(u, n, c->partial.p, c->ticket.p, 1.0, mine);
-    c->launches++;
-    LAUNCH_CHECK();
-    if (N->allGather(mine, gsum, V, NCCL_DOUBLE, c->comm, c->stream) != 0)
-        return fail(MFT_ENCCL, "ncclAllGather failed: %s", N->lastError(c->comm));
-    const double ng = (double)c->n_global;
-    const double divisor = c->mean_div_vn ? (double)V * ng : ng;
-    if (c->max_lex)
-        k_maxdev_norms<4, true><<<c->red_blocks, 256, 0, c->stream>>>(u, n, gsum, c->nranks, divisor, c->partial.p, c->ticket.p + 1, mine2, 0, c->stats.p + V);
-    else
-        k_maxdev_norms<4, false><<<c->red_blocks, 256, 0, c->stream>>>(u, n, gsum, c->nranks, divisor, c->partial.p, c->ticket.p + 1, mine2, 0, c->stats.p + V);
-    c->launches++;
-    LAUNCH_CHECK();
-    if (N->allGather(mine2, gmax, V, NCCL_DOUBLE, c->comm, c->stream) != 0)
-        return fail(MFT_ENCCL, "ncclAllGather failed: %s", N->lastError(c->comm));
-    return MFT_OK;
-}
-
-// ------------------------------------------------------------------------------------------------------
-// peer-memory exchange setup: CUDA IPC handles of {u, g, window} travel through the host program (all-gather)
-// ------------------------------------------------------------------------------------------------------
-extern "C" int mft_p2p_handles(mft_ctx *c, void *out3x64)
-{
-    NEED_CTX(c);
-    CHECK(mft_finalize(c));
-    if (!out3x64) return fail(MFT_EINVAL, "mft_p2p_handles: NULL");
-    if (c->V != 4) return fail(MFT_ENOTSUP, "peer-memory exchange is implemented for Euler 2-D");
-    if (!c->p2p_window.p) {
-        CHECK(c->p2p_window.alloc((int64_t)sizeof(P2PWindow)));
-        CHECK(c->p2p_local.alloc((int64_t)sizeof(P2PLocal)));
-        CU(cudaMemset(c->p2p_window.p, 0, sizeof(P2PWindow)));
-        CU(cudaMemset(c->p2p_local.p, 0, sizeof(P2PLocal)));
-        if (!c->g.p) {  // no viscosity source: still give peers something valid to map
-            CHECK(c->g.alloc((c->n_tot + 1) * 2 * c->V));
-            CU(cudaMemset(c->g.p, 0, sizeof(double) * (c->n_tot + 1) * 2 * c->V));
-        }
-    }
-    cudaIpcMemHandle_t h[3];
-    CU(cudaIpcGetMemHandle(&h[0], c->u.p));
-    CU(cudaIpcGetMemHandle(&h[1], c->g.p));
-    CU(cudaIpcGetMemHandle(&h[2], c->p2p_window.p));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    memcpy(out3x64, h, sizeof h);
-    return MFT_OK;
-}
-
-extern "C" int mft_p2p_connect(mft_ctx *c, int nranks, int rank, const void *all_handles, const int64_t *peer_dst_row,
-                               int64_t n_global)
-{
-    NEED_CTX(c);
-    if (nranks < 2 || nranks > kMaxRanks || rank < 0 || rank >= nranks || !all_handles)
-        return fail(MFT_EINVAL, "mft_p2p_connect: bad arguments (2..%d ranks)", kMaxRanks);
-    if (!c->p2p_window.p) return fail(MFT_EINVAL, "mft_p2p_connect: call mft_p2p_handles first");
-    if (c->peers.empty() && c->n_halo > 0) return fail(MFT_EINVAL, "mft_p2p_connect: call mft_set_halo first");
-    const cudaIpcMemHandle_t *H = reinterpret_cast<const cudaIpcMemHandle_t *>(all_handles);
-    P2PPeers &P = c->peers_dev;
-    memset(&P, 0, sizeof P);
-    P.nranks = nranks;
-    P.rank = rank;
-    for (int r = 0; r < nranks; ++r) {
-        if (r == rank) {
-            P.field[0][r] = c->u.p;
-            P.field[1][r] = c->g.p;
-            P.win[r] = reinterpret_cast<P2PWindow *>(c->p2p_window.p);
-            continue;
-        }
-        void *q[3];
-        for (int k = 0; k < 3; ++k) {
-            cudaError_t e = cudaIpcOpenMemHandle(&q[k], H[r * 3 + k], cudaIpcMemLazyEnablePeerAccess);
-            if (e != cudaSuccess) return fail(MFT_ECUDA, "cudaIpcOpenMemHandle(rank %d): %s (peer access over NVLink/PCIe is required)", r, cudaGetErrorString(e));
-            c->ipc_opened.push_back(q[k]);
-        }
-        P.field[0][r] = q[0];
-        P.field[1][r] = q[1];
-        P.win[r] = reinterpret_cast<P2PWindow *>(q[2]);
-    }
-    // destinations / sources and the per-entry routing table
-    std::vector<int> speer((size_t)c->n_send);
-    std::vector<long long> sdst((size_t)c->n_send);
-    for (size_t p = 0; p < c->peers.size(); ++p) {
-        const int64_t ns = c->send_off[p + 1] - c->send_off[p];
-        const int64_t nr = c->recv_off[p + 1] - c->recv_off[p];
-        if (ns > 0) P.dst[P.ndst++] = c->peers[p];
-        if (nr > 0) P.src[P.nsrc++] = c->peers[p];
-        for (int64_t i = 0; i < ns; ++i) {
-            speer[c->send_off[p] + i] = c->peers[p];
-            sdst[c->send_off[p] + i] = (long long)(peer_dst_row[p] + i);
-        }
-    }
-    CHECK(c->send_peer.upload(speer));
-    CHECK(c->send_dst.upload(sdst));
-    c->nranks = nranks;
-    c->rank = rank;
-    c->n_global = n_global;
-    if (!c->gather_buf.p) CHECK(c->gather_buf.alloc((int64_t)2 * nranks * c->V + 4 * c->V));
-    c->p2p = true;
-    return MFT_OK;
-}
+#include "mft_multi_gpu.inl"
