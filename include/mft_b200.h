@@ -140,6 +140,13 @@ int mft_set_operator_ell(mft_ctx *ctx, const int64_t *nbr1, const double *wx, co
  * idx1: 1-based point indices (BoundaryData.idx), normals: nb x 2 row-major, values: Dirichlet table SoA values[v*nb+j] or NULL */
 int mft_add_boundary(mft_ctx *ctx, int kind, int64_t nb, const int64_t *idx1, const double *normals, const double *values);
 int mft_update_boundary_values(mft_ctx *ctx, int group, const double *values);
+/* Time-dependent Dirichlet data inside a device-resident step (mft_ssprk_step / mft_ssprk43_step).  The reference's BC
+ * closures receive the stage time (calc_single_boundary_flux!, rbfsolver.jl:311-316) and one step
+ * evaluates rhs! at t + dt and t + dt/2: hand the tables for both times to the library before the step (slot 0 = values at
+ * t + dt, slot 1 = values at t + dt/2; same layout as mft_update_boundary_values); it makes each the current table in front
+ * of the rhs! evaluated at that time.  The table current at the start of a run (time t0) is set with
+ * mft_update_boundary_values.  Groups without stage tables keep their table for the whole step. */
+int mft_set_stage_boundary_values(mft_ctx *ctx, int group, int slot, const double *values);
 
 /* sources, call order = order of SourceTerms(...) (calc_sources!, rbfsolver.jl:388-395).  HV kinds take their
  * matrix (CSC as above); others pass NULLs. */

@@ -179,17 +179,32 @@ function MeshfreeTrixi.modify_cache!(source::SourceResidualViscosityTominec, u, 
                     ctx.ptr, t, integrator.success_iter, n, time_weights))
 end
 
+# Dirichlet tables for the two stage times of the next device-resident step (slot 0: t + dt, slot 1: t + dt/2); the
+# reference's closures receive the stage time (rbfsolver.jl:311-316)
+function stage_dirichlet!(cache, domain, equations, boundary_conditions, t, dt)
+    for (g, (key, bc)) in enumerate(zip(keys(boundary_conditions), boundary_conditions))
+        bc isa BoundaryConditionDirichlet || continue
+        for (slot, ts) in ((0, t + dt), (1, t + dt / 2))
+            vals = dirichlet_table(bc, domain, domain.boundary_tags[key], ts, equations)
+            mft_check(ccall((:mft_set_stage_boundary_values, libmft), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}),
+                            cache.ctx.ptr, g - 1, slot, vals))
+        end
+    end
+end
+
 # ---- device-resident SSPRK33 loop (same shape as Trixi's SimpleSSPRK33: init / step! / solve!) ------------------------------
-function solve_ssprk33_resident!(u, semi, tspan, dt; approx_order = nothing)
+function solve_ssprk33_resident!(u, semi, tspan, dt; approx_order = nothing, time_dependent_bcs = false)
     cache = semi.cache
     ctx = cache.ctx
     cache.registered[] || register!(cache, semi.mesh, semi.equations, semi.boundary_conditions, semi.source_terms)
+    time_dependent_bcs && refresh_dirichlet!(cache, semi.mesh, semi.equations, semi.boundary_conditions, first(tspan))
     up = collect(Ptr{Float64}, pointer.(StructArrays.components(u)))
     GC.@preserve u up mft_check(ccall((:mft_upload_state, libmft), Cint, (Ptr{Cvoid}, Ptr{Ptr{Float64}}), ctx.ptr, up))
     t, iter = first(tspan), 0
     approx_order === nothing || mft_check(ccall((:mft_history_push, libmft), Cint, (Ptr{Cvoid}, Float64, Int64, Cint),
                                                 ctx.ptr, t, 0, approx_order))
     while t < last(tspan) - 0.5dt
+        time_dependent_bcs && stage_dirichlet!(cache, semi.mesh, semi.equations, semi.boundary_conditions, t, dt)
         mft_check(ccall((:mft_ssprk_step, libmft), Cint, (Ptr{Cvoid}, Cint, Float64, Float64), ctx.ptr, 0, t, dt))
         t += dt
         iter += 1

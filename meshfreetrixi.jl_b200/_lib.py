@@ -32,7 +32,7 @@ K_PASS_A, K_PASS_B, K_REDUCE, K_STAGE, K_BC, K_OTHER = range(6)
 EXPORTS = [
     "mft_last_error", "mft_version", "mft_device_count", "mft_ctx_create", "mft_ctx_destroy", "mft_set_equation",
     "mft_set_option", "mft_set_permutation", "mft_set_order_keys", "mft_set_operator_csc", "mft_set_operator_ell",
-    "mft_add_boundary", "mft_update_boundary_values", "mft_add_source", "mft_finalize", "mft_rhs", "mft_calc_fluxes",
+    "mft_add_boundary", "mft_update_boundary_values", "mft_set_stage_boundary_values", "mft_add_source", "mft_finalize", "mft_rhs", "mft_calc_fluxes",
     "mft_apply_source", "mft_boundary_pass", "mft_upload_state", "mft_download_state", "mft_download_du",
     "mft_history_push", "mft_history_push_weights", "mft_ssprk_step", "mft_ssprk43_step", "mft_step_commit", "mft_get_field", "mft_synchronize", "mft_count_nonfinite",
     "mft_launch_count", "mft_timer_start", "mft_timer_stop", "mft_kernel_time_ms", "mft_set_kernel_timing", "mft_host_alloc", "mft_host_free",
@@ -80,6 +80,7 @@ def load():
         "mft_set_operator_ell": [vp, vp, vp, vp],
         "mft_add_boundary": [vp, i32, i64, vp, vp, vp],
         "mft_update_boundary_values": [vp, i32, vp],
+        "mft_set_stage_boundary_values": [vp, i32, i32, vp],
         "mft_add_source": [vp, i32, vp, i32, vp, vp, vp],
         "mft_finalize": [vp],
         "mft_rhs": [vp, dbl, vp, vp, i32],

@@ -497,6 +497,20 @@ class SemidiscretizationHyperbolic:
                 vals = np.ascontiguousarray(bc.boundary_value_function(self.domain.pd.points[tag.idx], t, self.equations))
                 L.check(lib.mft_update_boundary_values(self.ctx, g, L.ptr(vals)))
 
+    def has_time_dependent_bcs(self):
+        return any(bc.kind == L.BC_DIRICHLET and bc.time_dependent for _, bc, _ in self._bc_groups)
+
+    def set_stage_boundary_values(self, t, dt):
+        """Dirichlet tables for the stage times of the next device-resident step: the reference's BC closures receive the
+        stage time (rbfsolver.jl:311-316) and a step evaluates rhs! at t + dt and t + dt/2 (mft_set_stage_boundary_values)."""
+        lib = L.load()
+        for g, (name, bc, tag) in enumerate(self._bc_groups):
+            if bc.kind == L.BC_DIRICHLET and bc.time_dependent:
+                for slot, ts in ((0, t + dt), (1, t + dt / 2)):
+                    vals = np.ascontiguousarray(bc.boundary_value_function(self.domain.pd.points[tag.idx], ts, self.equations),
+                                                dtype=np.float64)
+                    L.check(lib.mft_set_stage_boundary_values(self.ctx, g, slot, L.ptr(vals)))
+
     def close(self):
         if getattr(self, "ctx", None):
             L.load().mft_ctx_destroy(self.ctx)
@@ -678,6 +692,8 @@ def solve_adaptive(ode, alg, dt, abstol=1e-8, reltol=1e-8, callback=None, max_st
     u0 = np.ascontiguousarray(ode.u0, dtype=np.float64)
     L.check(lib.mft_upload_state(semi.ctx, L.soa_ptrs(u0)))
     t, dt = float(t0), float(dt)
+    tdep = semi.has_time_dependent_bcs()
+    semi.refresh_boundary_values(t)
     for h in hist:
         L.check(lib.mft_history_push(semi.ctx, t, 0, h.approx_order))
     _run_savers(savers, semi, t, 0, False, u0)
@@ -688,6 +704,8 @@ def solve_adaptive(ode, alg, dt, abstol=1e-8, reltol=1e-8, callback=None, max_st
         if t >= t1 - 1e-14 * max(1.0, abs(t1)):
             break
         dt = min(dt, t1 - t)
+        if tdep:
+            semi.set_stage_boundary_values(t, dt)
         L.check(lib.mft_ssprk43_step(semi.ctx, t, dt, abstol, reltol, C.byref(ss), C.byref(cnt)))
         sumsq, count = (ss.value, cnt.value) if allreduce is None else allreduce(ss.value, cnt.value)
         eest = float(np.sqrt(sumsq / count))
@@ -732,11 +750,15 @@ def solve(ode, alg, dt, callback=None, nsteps=None, **kw):
     u0 = np.ascontiguousarray(ode.u0, dtype=np.float64)
     L.check(lib.mft_upload_state(semi.ctx, L.soa_ptrs(u0)))
     t = float(t0)
+    tdep = semi.has_time_dependent_bcs()
+    semi.refresh_boundary_values(t)      # Dirichlet data at the start time (no-op for time-independent tables)
     for h in hist:   # initialize! (history.jl:51-54)
         L.check(lib.mft_history_push(semi.ctx, t, 0, h.approx_order))
     _run_savers(savers, semi, t, 0, False, u0)   # initialize_save_cb! (save_solution_vtk.jl:123-134)
     nrhs = 1 if nsteps > 0 else 0
     for it in range(nsteps):
+        if tdep:
+            semi.set_stage_boundary_values(t, float(dt))
         L.check(lib.mft_ssprk_step(semi.ctx, alg.scheme, t, float(dt)))
         t = t + dt
         nrhs += alg.stages

@@ -133,6 +133,10 @@ struct BcGroup {
     int64_t nb;
     DevBuf<int> idx;
     DevBuf<double> normals, values;
+    // time-dependent Dirichlet data inside a device-resident step: tables for the two stage times of the step
+    // (slot 0: t + dt, slot 1: t + dt/2), copied over `values` in front of the rhs! evaluated at that time
+    DevBuf<double> stage_values[2];
+    bool stage_set[2] = {false, false};
 };
 
 struct Source {
@@ -260,7 +264,7 @@ struct mft_ctx {
 // misc
 // ------------------------------------------------------------------------------------------------------
 extern "C" const char *mft_last_error(void) { return g_err.c_str(); }
-extern "C" int mft_version(void) { return 110; }  // 1.1: setup pipeline, limiter, IGR source, non-finite check
+extern "C" int mft_version(void) { return 120; }  // 1.1: setup pipeline, limiter, IGR source, non-finite check; 1.2: stage-time Dirichlet tables
 extern "C" int mft_device_count(void)
 {
     int n = 0;
@@ -378,6 +382,8 @@ extern "C" int mft_ctx_destroy(mft_ctx *c)
         b->idx.release();
         b->normals.release();
         b->values.release();
+        b->stage_values[0].release();
+        b->stage_values[1].release();
         delete b;
     }
     for (auto *s : c->srcs) {
@@ -623,6 +629,50 @@ extern "C" int mft_update_boundary_values(mft_ctx *c, int group, const double *v
         CU(cudaMemcpyAsync(c->bc_values.p + c->bc_group_off[group] * c->V, aos.data(), sizeof(double) * aos.size(),
                            cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return MFT_OK;
+}
+
+// Dirichlet tables for the stage times of the NEXT device-resident step (mft_ssprk_step / mft_ssprk43_step): the reference's
+// BC closures receive the stage time (calc_single_boundary_flux!, rbfsolver.jl:311-316: boundary_condition(..., t, ...)), and
+// one step evaluates rhs! at t + dt and t + dt/2.  slot 0 = values at t + dt, slot 1 = values at t + dt/2.  The step copies the
+// slot's table over the group's current table (device to device, stream-ordered, part of the captured graph) in front of the
+// rhs! evaluated at that time; after the step the current table is the t + dt one, i.e. the start time of the next step.
+extern "C" int mft_set_stage_boundary_values(mft_ctx *c, int group, int slot, const double *values)
+{
+    NEED_CTX(c);
+    if (group < 0 || group >= (int)c->bcs.size()) return fail(MFT_EINVAL, "mft_set_stage_boundary_values: group %d out of range", group);
+    if (slot < 0 || slot > 1) return fail(MFT_EINVAL, "mft_set_stage_boundary_values: slot must be 0 (t + dt) or 1 (t + dt/2)");
+    BcGroup *g = c->bcs[group];
+    if (g->kind != MFT_BC_DIRICHLET) return fail(MFT_EINVAL, "mft_set_stage_boundary_values: group %d is not Dirichlet", group);
+    if (!values) return fail(MFT_EINVAL, "mft_set_stage_boundary_values: values is NULL");
+    if (g->nb == 0) return MFT_OK;
+    if (!g->stage_values[slot].p) {
+        CHECK(g->stage_values[slot].alloc(g->nb * c->V));
+        // captured steps were recorded without the table copies: start over
+        for (auto &e : c->graphs)
+            if (e.exec) cudaGraphExecDestroy(e.exec);
+        c->graphs.clear();
+    }
+    std::vector<double> aos((size_t)g->nb * c->V);
+    for (int64_t j = 0; j < g->nb; ++j)
+        for (int v = 0; v < c->V; ++v) aos[j * c->V + v] = values[(int64_t)v * g->nb + j];
+    CU(cudaMemcpyAsync(g->stage_values[slot].p, aos.data(), sizeof(double) * aos.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    g->stage_set[slot] = true;
+    return MFT_OK;
+}
+
+// in front of a stage's rhs!: make the slot's Dirichlet tables the current ones (no-op unless stage tables were supplied)
+static int select_stage_boundary_values(mft_ctx *c, int slot)
+{
+    for (size_t gi = 0; gi < c->bcs.size(); ++gi) {
+        BcGroup *g = c->bcs[gi];
+        if (g->kind != MFT_BC_DIRICHLET || g->nb == 0 || !g->stage_set[slot]) continue;
+        const size_t bytes = sizeof(double) * (size_t)g->nb * c->V;
+        CU(cudaMemcpyAsync(g->values.p, g->stage_values[slot].p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        if (c->bc_merged && c->bc_group_off[gi] >= 0)
+            CU(cudaMemcpyAsync(c->bc_values.p + c->bc_group_off[gi] * c->V, g->stage_values[slot].p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
     return MFT_OK;
 }
 

@@ -118,12 +118,15 @@ static int launch_stage(mft_ctx *c, int stage, double dt)
 
 static int ssprk33_step_launches(mft_ctx *c, double t, double dt, bool first_rhs)
 {
-    if (first_rhs) CHECK(rhs_device(c, t));  // k = f(u_n): first step only (FSAL afterwards)
+    if (first_rhs) CHECK(rhs_device(c, t));  // k = f(u_n): first step only (FSAL afterwards); current Dirichlet tables = time t
     CHECK(launch_stage(c, 1, dt));
+    CHECK(select_stage_boundary_values(c, 0));
     CHECK(rhs_device(c, t + dt));
     CHECK(launch_stage(c, 2, dt));
+    CHECK(select_stage_boundary_values(c, 1));
     CHECK(rhs_device(c, t + dt / 2));
     CHECK(launch_stage(c, 3, dt));
+    CHECK(select_stage_boundary_values(c, 0));
     CHECK(rhs_device(c, t + dt));
     return MFT_OK;
 }
@@ -299,10 +302,13 @@ extern "C" int mft_ssprk43_step(mft_ctx *c, double t, double dt, double abstol, 
         return MFT_OK;
     };
     CHECK(stage(1));
+    CHECK(select_stage_boundary_values(c, 1));
     CHECK(rhs_device(c, t + dt / 2));
     CHECK(stage(2));
+    CHECK(select_stage_boundary_values(c, 0));
     CHECK(rhs_device(c, t + dt));
     CHECK(stage(3));
+    CHECK(select_stage_boundary_values(c, 1));
     CHECK(rhs_device(c, t + dt / 2));
     CHECK(stage(4));
     {
@@ -312,6 +318,7 @@ extern "C" int mft_ssprk43_step(mft_ctx *c, double t, double dt, double abstol, 
         c->launches++;
         LAUNCH_CHECK();
     }
+    CHECK(select_stage_boundary_values(c, 0));
     CHECK(rhs_device(c, t + dt));  // FSAL: k = f(u_{n+1}, t+dt)
     double ss = 0.0;
     CU(cudaMemcpyAsync(&ss, c->stats.p + 3 * c->V, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
