@@ -139,7 +139,9 @@ class ParallelPointCloudDomain(PointCloudDomain):
     ParallelPointCloudDomain, src/domains/PointCloudDomain/ParallelPointCloud.jl:85-162), but cut along a
     space-filling curve and with full global stencils for the owned rows (see partition.py)."""
 
-    def __init__(self, solver, source, boundary_names, comm):
+    def __init__(self, solver, source, boundary_names, comm, wide_halo=False):
+        """wide_halo=True keeps a second stencil ring of column-only halo points: needed by sources whose operator is a
+        product of two stencil operators (SourceHyperviscosityTominec: L'L)"""
         from . import partition
 
         cl = cloudmod.read_medusa_file(source) if isinstance(source, str) else source
@@ -152,7 +154,8 @@ class ParallelPointCloudDomain(PointCloudDomain):
             basis.N, basis.nv, comm.allgather,
             knn_queries=(lambda pts, q, nv: setup_ops.knn_queries_device(pts, q, nv, eng.device)) if on_device else None,
             weights_rows=(lambda pts, rows, p, N: setup_ops.rbf_fd_weights_rows_device(pts, rows, p, N, None, eng.device, hyb))
-            if on_device else ((lambda pts, rows, p, N: setup_ops.rbf_fd_weights(pts, rows, p, N, hybrid=hyb)) if hyb else None))
+            if on_device else ((lambda pts, rows, p, N: setup_ops.rbf_fd_weights(pts, rows, p, N, hybrid=hyb)) if hyb else None),
+            wide_halo=wide_halo)
         self.partition, self.comm, self.cloud = part, comm, cl
         self.pd = PointData(part.points, part.neighbors_owned, part.n_local + part.n_halo, basis.nv, part.dx_min, part.dx_avg)
         self.boundary_tags = {name: BoundaryData(part.boundary_idxs[g - 1], part.boundary_normals[g - 1])
@@ -295,9 +298,47 @@ class SourceHyperviscosityTominec(_Source):
 
     def __init__(self, solver, equations, domain, c=1.0):
         p, N = solver.basis.approx_type.rbf_type.Nrbf, solver.basis.N
-        ops = setup_ops.flux_operator_with(solver.engine, domain.pd.points, domain.pd.neighbors, p, N, 2, _hybrid_of(solver.basis))
-        lap = (ops[0] + ops[1]).tocsc()
-        self.hv_differentiation_matrix = (lap.T @ lap).tocsc()
+        part = getattr(domain, "partition", None)
+        if part is None:
+            ops = setup_ops.flux_operator_with(solver.engine, domain.pd.points, domain.pd.neighbors, p, N, 2, _hybrid_of(solver.basis))
+            lap = (ops[0] + ops[1]).tocsc()
+            self.hv_differentiation_matrix = (lap.T @ lap).tocsc()
+        else:
+            # one rank of a partitioned cloud.  Row i of L'L is sum_k L[k,i] L[k,:] over the rows k whose stencils contain i:
+            # for an owned i these are owned rows and the foreign rows R_r of the halo, and the columns are their stencils --
+            # local thanks to the wide halo.  L rows from the GLOBAL stencils; halo rows of the result are dropped.
+            if not part.wide_halo:
+                raise ValueError("SourceHyperviscosityTominec on a partitioned cloud needs ParallelPointCloudDomain(..., "
+                                 "wide_halo=True): L'L reaches two stencil rings")
+            eng = solver.engine
+            gpts = np.ascontiguousarray(domain.cloud.points, dtype=np.float64)
+            hyb = _hybrid_of(solver.basis)
+            n_loc, n_tot = part.n_local, part.n_local + part.n_halo
+            is_owned_g = np.zeros(part.n_global, dtype=bool)
+            is_owned_g[part.owned_gid] = True
+            hnb = part.neighbors_halo
+            in_R = np.zeros(part.n_halo, dtype=bool)
+            if part.n_halo:
+                has = hnb[:, 0] >= 0
+                in_R[has] = is_owned_g[hnb[has]].any(axis=1)
+            rows_local = np.concatenate([np.arange(n_loc, dtype=np.int64), n_loc + np.nonzero(in_R)[0]])
+            rows_nb = np.concatenate([part.neighbors_owned, hnb[in_R]]) if in_R.any() else part.neighbors_owned
+            if getattr(eng, "setup", "host") == "device":
+                wx, wy = setup_ops.rbf_fd_weights_rows_device(gpts, rows_nb, p, N, 2, eng.device, hyb)
+            else:
+                wx, wy = setup_ops.rbf_fd_weights(gpts, rows_nb, p, N, 2, hybrid=hyb)
+            lut = np.full(part.n_global, -1, dtype=np.int64)
+            lut[part.local_gid] = np.arange(n_tot)
+            cols = lut[rows_nb]
+            assert (cols >= 0).all(), "a stencil column of an owned / R row is not local (wide halo incomplete)"
+            rr = np.repeat(rows_local, rows_nb.shape[1])
+            lap = sp.coo_matrix(((wx + wy).reshape(-1), (rr, cols.reshape(-1))), shape=(n_tot, n_tot)).tocsc()
+            H = (lap.T @ lap).tocsr()
+            keep = sp.diags(np.concatenate([np.ones(n_loc), np.zeros(part.n_halo)]))
+            H = (keep @ H).tocsc()
+            H.eliminate_zeros()
+            H.sort_indices()
+            self.hv_differentiation_matrix = H
         self.gamma = c * domain.pd.dx_min ** 4.5
         self.c = c
 
@@ -380,10 +421,9 @@ class SemidiscretizationHyperbolic:
         if part is not None:
             ops = part.ops
             for src in self.source_terms.values():
-                if src.kind == L.SRC_HV_TOMINEC:
-                    raise NotImplementedError("SourceHyperviscosityTominec is not partitioned (L'L reaches two stencil rings: it "
-                                              "needs a wider halo than rhs! exchanges); multi-GPU supports the flux divergence, "
-                                              "Flyer hyperviscosity and the upwind / residual viscosity sources")
+                if src.kind == L.SRC_HV_TOMINEC and not part.wide_halo:
+                    raise ValueError("SourceHyperviscosityTominec on a partitioned cloud needs "
+                                     "ParallelPointCloudDomain(..., wide_halo=True): L'L reaches two stencil rings")
         else:
             ops = operators or setup_ops.flux_operator_with(eng, pd.points, pd.neighbors, p, N, None, _hybrid_of(solver.basis))
         self.cache = Cache(pd, ops)

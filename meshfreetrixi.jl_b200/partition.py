@@ -41,6 +41,8 @@ class RankPartition:
     recv_count: list = field(default_factory=list)
     boundary_idxs: list = field(default_factory=list)    # per group: LOCAL owned indices
     boundary_normals: list = field(default_factory=list)
+    neighbors_halo: np.ndarray | None = None   # (n_halo, k) GLOBAL stencils of the halo rows; -1 rows: column-only halo points
+    wide_halo: bool = False                    # halo also holds every stencil column of the foreign rows R_r (second ring)
 
     @property
     def n_local(self):
@@ -62,14 +64,19 @@ def curve_offsets(n: int, nranks: int) -> np.ndarray:
 
 def build_rank_partition(points: np.ndarray, boundary_idxs, boundary_normals, rank: int, nranks: int, p: int, N: int,
                          nv: int, allgather, perm_g: np.ndarray | None = None, knn_queries=None,
-                         weights_rows=None) -> RankPartition:
+                         weights_rows=None, wide_halo: bool = False) -> RankPartition:
     """`allgather(obj) -> list of obj from every rank` is the only communication primitive needed
     (torch.distributed.all_gather_object in production, a trivial stub for nranks == 1).
 
     knn_queries(box_points, query_positions, nv) -> (neighbours as positions into box_points, distances) and
     weights_rows(points, rows_nb, p, N) -> (wx, wy) select who does the two heavy setup steps: None = host (KD-tree +
     batched LAPACK LU, setup_ops.knn_query / rbf_fd_weights); RBFFDEngineCUDA(setup="device") passes the GPU pipeline
-    (setup_ops.knn_queries_device / rbf_fd_weights_rows_device).  Both produce the same tables (ties by index)."""
+    (setup_ops.knn_queries_device / rbf_fd_weights_rows_device).  Both produce the same tables (ties by index).
+
+    wide_halo: also keep every stencil column of the foreign rows R_r as (column-only) halo points.  Operators of the form
+    L'L (SourceHyperviscosityTominec, hyperviscosity.jl:101-119) reach two stencil rings: row i of L'L is
+    sum_k L[k,i] L[k,:] over the rows k whose stencils contain i (owned rows and R_r), so its columns are exactly those
+    stencils.  The extra points take part in the u exchange only; they have no operator rows."""
     n = points.shape[0]
     if perm_g is None:
         perm_g = L.sfc_order(points)
@@ -119,6 +126,11 @@ def build_rank_partition(points: np.ndarray, boundary_idxs, boundary_normals, ra
     keep = in_F | touches
     halo = cand[keep]
     halo_nb = cand_nb[keep]
+    if wide_halo and len(halo):
+        rows_R = halo_nb[is_owned[halo_nb].any(axis=1)]
+        extra = np.setdiff1d(np.setdiff1d(np.unique(rows_R), owned), halo)
+        halo = np.concatenate([halo, extra])
+        halo_nb = np.concatenate([halo_nb, np.full((len(extra), nv), -1, dtype=np.int64)])
     owner = np.searchsorted(offs, pos[halo], side="right") - 1
     order = np.lexsort((pos[halo], owner))
     halo, halo_nb, owner = halo[order], halo_nb[order], owner[order]
@@ -132,8 +144,10 @@ def build_rank_partition(points: np.ndarray, boundary_idxs, boundary_normals, ra
 
     # weights: owned rows (full stencils) + halo rows (entries kept only where the column is local)
     rows_nb = np.concatenate([nb_owned, halo_nb]) if n_halo else nb_owned
-    wx, wy = (weights_rows or setup_ops.rbf_fd_weights)(points, rows_nb, p, N)
-    col_local = lut[rows_nb]
+    has_row = rows_nb[:, 0] >= 0                      # column-only halo points (wide_halo) carry no stencil
+    wx, wy = np.zeros(rows_nb.shape), np.zeros(rows_nb.shape)
+    wx[has_row], wy[has_row] = (weights_rows or setup_ops.rbf_fd_weights)(points, rows_nb[has_row], p, N)
+    col_local = np.where(rows_nb >= 0, lut[np.maximum(rows_nb, 0)], -1)
     valid = col_local >= 0
     assert valid[:n_local].all(), "an owned row references a point outside owned+halo"
     r_idx = np.repeat(np.arange(n_tot, dtype=np.int64), nv).reshape(n_tot, nv)
@@ -167,7 +181,7 @@ def build_rank_partition(points: np.ndarray, boundary_idxs, boundary_normals, ra
         bnrm.append(np.asarray(gn)[sel])
 
     return RankPartition(rank, nranks, n, owned, halo, owner, np.ascontiguousarray(points[local_gid]), nb_owned, ops,
-                         dx_min, dx_avg, peers, send_idx, recv_count, bidx, bnrm)
+                         dx_min, dx_avg, peers, send_idx, recv_count, bidx, bnrm, neighbors_halo=halo_nb, wide_halo=wide_halo)
 
 
 # ---- communicators used at setup time (and to bootstrap NCCL) ------------------------------------------------------

@@ -79,6 +79,11 @@ def main():
         # hyperviscosity.jl:34-50 with the product's (batched-LU) weights, so that serial and partitioned H agree bit for bit
         hops = m.setup_ops.compute_flux_operator(cl.points, nb, PHS, 3, 4)
         src_o = orc.OracleSource(kind=orc.SRC_HV_FLYER, hv=orc.JuliaCSC((hops[0] + hops[1]).tocsc()), gamma=1.0 * dx_min ** 4)
+    elif args.source == "tominec":
+        # hyperviscosity.jl:101-119: H = lap' * lap with the product's (batched-LU) weights, gamma = dx_min^4.5
+        lops = m.setup_ops.compute_flux_operator(cl.points, nb, PHS, 3, 2)
+        lap = (lops[0] + lops[1]).tocsc()
+        src_o = orc.OracleSource(kind=orc.SRC_HV_TOMINEC, hv=orc.JuliaCSC((lap.T @ lap).tocsc()), gamma=1.0 * dx_min ** 4.5)
     else:
         src_o = orc.source_residual(dx_avg, polydeg=3) if args.source == "residual" else orc.source_upwind(dx_avg)
     P = orc.OracleProblem(cl.points, 4, orc.EQ_EULER2D, [GAMMA], ops[0], ops[1], obc, [src_o])
@@ -96,7 +101,7 @@ def main():
     results = {}
     if args.mode == "cpu":
         part = partition.build_rank_partition(cl.points, cl.boundary_idxs, cl.boundary_normals, comm.rank, comm.nranks,
-                                              PHS, 3, basis.nv, comm.allgather)
+                                              PHS, 3, basis.nv, comm.allgather, wide_halo=args.source == "tominec")
         gid = part.local_gid
         nl = part.n_local
         # the local operator rows of owned points are the global rows, bit for bit
@@ -162,20 +167,40 @@ def main():
         F, G, (v1, v2, p) = euler_flux(u)
         Dx, Dy = part.ops[0].tocsr(), part.ops[1].tocsr()
         du = np.stack([-(Dx[:nl] @ F[v]) - (Dy[:nl] @ G[v]) for v in range(4)])
-        if args.source == "flyer":
-            # SourceHyperviscosityFlyer on a partition: du += -gamma H u on owned rows, only the u halo is needed
+        if args.source in ("flyer", "tominec"):
+            # SourceHyperviscosityFlyer on a partition: du += -gamma H u on owned rows, only the u halo is needed.
+            # SourceHyperviscosityTominec: H = L'L reaches a second stencil ring -> wide halo (column-only halo points)
             import types
 
             dom = types.SimpleNamespace(partition=part, cloud=cl, pd=types.SimpleNamespace(dx_min=part.dx_min))
             solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA())
-            hv = m.SourceHyperviscosityFlyer(solver, None, dom, k=2, c=1.0)
+            if args.source == "flyer":
+                hv = m.SourceHyperviscosityFlyer(solver, None, dom, k=2, c=1.0)
+            else:
+                hv = m.SourceHyperviscosityTominec(solver, None, dom, c=1.0)
+                assert (part.neighbors_halo[:, 0] < 0).any(), "the wide halo added no column-only points"
+                narrow = partition.build_rank_partition(cl.points, cl.boundary_idxs, cl.boundary_normals, comm.rank, comm.nranks,
+                                                        PHS, 3, basis.nv, comm.allgather)
+                assert narrow.n_halo < part.n_halo and np.array_equal(narrow.owned_gid, part.owned_gid)
+                try:
+                    m.SourceHyperviscosityTominec(solver, None, types.SimpleNamespace(partition=narrow, cloud=cl, pd=dom.pd))
+                    raise AssertionError("the narrow halo must be refused")
+                except ValueError:
+                    pass
             H = hv.hv_differentiation_matrix.tocsr()
             assert H.shape == (len(gid), len(gid)) and H[nl:].nnz == 0
             Hg = src_o.hv.scipy.tocsr()
-            for i in range(0, nl, 41):        # owned rows of the local H are the global rows, bit for bit
+            for i in range(0, nl, 41):        # owned rows of the local H are the global rows (Flyer: bit for bit)
                 gl, ll = Hg[gid[i]], H[i]
-                o1, o2 = np.argsort(gid[ll.indices]), np.argsort(gl.indices)
-                assert np.array_equal(gid[ll.indices][o1], gl.indices[o2]) and np.array_equal(ll.data[o1], gl.data[o2])
+                if args.source == "flyer":
+                    o1, o2 = np.argsort(gid[ll.indices]), np.argsort(gl.indices)
+                    assert np.array_equal(gid[ll.indices][o1], gl.indices[o2]) and np.array_equal(ll.data[o1], gl.data[o2])
+                else:                         # L'L: same entries up to the summation order inside the sparse product
+                    dl = np.zeros(len(cl.points))
+                    dl[gid[ll.indices]] = ll.data
+                    dg = np.zeros(len(cl.points))
+                    dg[gl.indices] = gl.data
+                    assert np.abs(dl - dg).max() <= 1e-13 * np.abs(dg).max()
             for v in range(4):
                 du[v] -= hv.gamma * (H[:nl] @ u[v])
             for g in range(4):
@@ -213,7 +238,7 @@ def main():
     else:
         solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=int(os.environ.get("LOCAL_RANK", rank)),
                                                                     diagnostics=True, exchange=args.exchange, setup=args.setup))
-        domain = m.ParallelPointCloudDomain(solver, cl, names, comm)
+        domain = m.ParallelPointCloudDomain(solver, cl, names, comm, wide_halo=args.source == "tominec")
         part = domain.partition
         eq = m.CompressibleEulerEquations2D(GAMMA)
         bc = {k: m.BoundaryConditionDirichlet(ic) for k in names}
@@ -221,6 +246,8 @@ def main():
             srcs = m.SourceTerms(rv=m.SourceUpwindViscosityTominec(solver, eq, domain))
         elif args.source == "flyer":
             srcs = m.SourceTerms(hv=m.SourceHyperviscosityFlyer(solver, eq, domain, k=2, c=1.0))
+        elif args.source == "tominec":
+            srcs = m.SourceTerms(hv=m.SourceHyperviscosityTominec(solver, eq, domain, c=1.0))
         else:
             srcs = m.SourceTerms(rv=m.SourceResidualViscosityTominec(solver, eq, domain, polydeg=3))
         semi = m.SemidiscretizationHyperbolic(domain, eq, ic, solver, boundary_conditions=bc, source_terms=srcs)
@@ -276,7 +303,7 @@ def main():
         assert (du[:, nl:] == 0).all()                       # reset_halos! parallel_rbfsolver.jl:74-91
         # time integration: 10 SSPRK33 steps with the history callback, against the serial oracle
         dt = 0.1 * dx_min / 8.0
-        hist = None if args.source == "flyer" else 3
+        hist = None if args.source in ("flyer", "tominec") else 3
         u_ref, _ = P.solve_ssprk33(u0, 0.0, dt, 10, approx_order=hist)
         ode = m.ODEProblem(np.ascontiguousarray(u0[:, gid]), (0.0, 10 * dt), semi)
         sol = m.solve(ode, m.SSPRK33(), dt=dt, callback=None if hist is None else m.HistoryCallback(3), nsteps=10)

@@ -46,6 +46,14 @@ def test_flyer_hyperviscosity_on_a_partition_world2_gloo(tmp_path):
     assert len(res) == 2 and all(r["n_halo"] > 0 and r["err"] < 1e-12 for r in res)
 
 
+def test_tominec_hyperviscosity_on_a_partition_world2_gloo(tmp_path):
+    """SourceHyperviscosityTominec (H = L'L, two stencil rings) on a partitioned cloud: ParallelPointCloudDomain(wide_halo=True)
+    keeps the stencil columns of the foreign rows R_r as column-only halo points; the owned rows of the local L'L equal the
+    global ones and the partitioned rhs! equals the serial oracle's.  The narrow halo is refused."""
+    res = _launch(2, "cpu", "tominec", str(tmp_path))
+    assert len(res) == 2 and all(r["n_halo"] > 0 and r["err"] < 1e-12 for r in res)
+
+
 def test_limiter_on_a_partition_world2_gloo(tmp_path):
     """Zhang-Shu limiter on a partitioned cloud: one u halo refresh per (threshold, variable) pass, owned rows limited from
     their global stencils -- equals the serial limiter on the global cloud"""
@@ -69,7 +77,7 @@ def _ngpu():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
-@pytest.mark.parametrize("source", ["upwind", "residual", "flyer"])
+@pytest.mark.parametrize("source", ["upwind", "residual", "flyer", "tominec"])
 def test_two_gpus_match_serial_oracle(tmp_path, source, exchange):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
