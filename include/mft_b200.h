@@ -89,7 +89,9 @@ typedef struct mft_ctx mft_ctx;
                                       union of its stencils into shared memory once and rows read it with 16-bit local offsets
                                       (mft_tile_kernels.cuh); bit 2: the slots of a tile are bank-coloured (fewer LDS conflicts);
                                       bit 3: every record is kept twice under different bank assignments and each read picks the
-                                      copy that avoids a conflict.  Same sums bit for bit.  Default 15.                     */
+                                      copy that avoids a conflict; bit 4 (opt-in): the bank groups of the second copy are tuned by
+                                      a local search so that the points of an LDS.128 phase can be matched to distinct groups
+                                      (simulated conflict degree 1.20 -> 1.02, layout only).  Same sums bit for bit.  Default 15. */
 #define MFT_OPT_TILE_ROWS 11       /* rows per thread of the union-tile kernels, decimal digits: units = pass A, tens = pass B, each 1, 2
                                       or 4 (e.g. 42 = pass B 4 rows, pass A 2 rows).  A thread walks the union of its rows' stencils
                                       (16-bit word = slot | row mask << 12, weights compact per row).  Same sums bit for bit.   */
@@ -266,6 +268,11 @@ int mft_set_stage_limiter(mft_ctx *ctx, int npairs, const double *thresholds, co
  * replays the kernels' walk on the CPU and compares it bit for bit with plain row sums.  Returns 0 when identical.
  * stats4 (nullable): mean LDS.128 bank-conflict degree, union steps per row, union entries per row, slots per tile. */
 int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int with_perm, unsigned seed, double *stats4);
+/* The same self test on a caller-supplied sparsity (the kNN table of a real cloud, or its transpose): n_rows stencils over n
+ * columns, 0-based CSR, the columns of a row in summation order; pseudo-random dyadic weights.  layout bits as MFT_OPT_TILE >> 2
+ * (1: bank-coloured slots, 2: two record copies, 4: tuned second copy). */
+int mft_debug_tile_selftest_csr(int64_t n, int64_t n_rows, const int64_t *rowptr, const int32_t *col, int R, int layout,
+                                unsigned seed, double *stats4);
 
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------------------------------------
  * replaces MPICache + perform_halo_update! (src/domains/PointCloudDomain/ParallelPointCloud.jl:6-71,

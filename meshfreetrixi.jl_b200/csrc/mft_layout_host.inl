@@ -244,7 +244,38 @@ static inline uint64_t lcg_jump(uint64_t x, uint64_t k)
     return acc_a * x + acc_c;
 }
 
-static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, int R, bool colour, bool two_copies, HostTileR &out)
+// <= 8 points, each offering two bank groups (its slot in copy 0 / copy 1): is there an assignment with all groups distinct?
+// (Kuhn's augmenting paths on an 8 x 8 bipartite graph)
+struct BankMatcher {
+    int opt[8][2];
+    int owner[8];
+    int kk = 0;
+    bool augment(int i, unsigned &seen)
+    {
+        for (int o = 0; o < 2; ++o) {
+            const int b = opt[i][o];
+            if (seen & (1u << b)) continue;
+            seen |= 1u << b;
+            if (owner[b] < 0 || augment(owner[b], seen)) {
+                owner[b] = i;
+                return true;
+            }
+        }
+        return false;
+    }
+    bool perfect()
+    {
+        for (int b = 0; b < 8; ++b) owner[b] = -1;
+        for (int i = 0; i < kk; ++i) {
+            unsigned seen = 0;
+            if (!augment(i, seen)) return false;
+        }
+        return true;
+    }
+};
+
+static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, int R, bool colour, bool two_copies, HostTileR &out,
+                            bool tune_copy1 = false)
 {
     if (R > 2) two_copies = false;  // the copy-select bit (14) is a row-mask bit for R = 4
     const uint64_t lcg0 = 0x9e3779b97f4a7c15ULL;
@@ -269,6 +300,8 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
         std::vector<std::vector<Step>> lanes;    // step lists of the tile's lanes
         std::vector<unsigned short> adj;         // nu x nu co-request counts
         std::vector<int> slot, slot1, order, bank, deg, grp, nb_ptr, nb_idx, nb_w;
+        std::vector<int> rq_ptr, rq_node, nr_ptr, nr_idx, bank1;  // tune_copy1: the tile's requests and node -> requests
+        std::vector<char> rq_ok;
     };
     // union of the tile's stencils (sorted) + the lane step lists of its slices (R-way merge by summation key);
     // returns the number of stored entries of the tile's rows
@@ -485,6 +518,91 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
                         std::swap(slot1[q], slot1[(int)((lcg >> 33) % (uint64_t)(q + 1))]);
                     }
                     nslots = std::max(nslots, nu);
+                    if (tune_copy1 && nu > NB) {
+                        // Local search on the bank groups of copy 1 (tools/tile_sim.py model: LDS.128 conflict degree 1.25 -> 1.01).
+                        // A request = the distinct points the 8 lanes of one LDS.128 phase ask for; it is conflict-free iff its
+                        // points can be matched to distinct bank groups, each point offering the group of its copy-0 slot and of
+                        // its copy-1 slot (bipartite matching, <= 8 x 8).  Two sweeps over the points: move a point of copy 1 to
+                        // the group that leaves the fewest of its requests unmatched; groups stay balanced (cap per group).
+                        std::vector<int> &rq_ptr = S.rq_ptr, &rq_node = S.rq_node, &nr_ptr = S.nr_ptr, &nr_idx = S.nr_idx, &bank1 = S.bank1;
+                        std::vector<char> &rq_ok = S.rq_ok;
+                        rq_ptr.assign(1, 0);
+                        rq_node.clear();
+                        for (int si = 0; si < ns_tile; ++si) {
+                            size_t W = 0;
+                            for (int l = 0; l < kSlice; ++l) W = std::max(W, lanes[(size_t)si * kSlice + l].size());
+                            for (size_t cpos = 0; cpos < W; ++cpos)
+                                for (int ph = 0; ph < kSlice / NB; ++ph) {
+                                    grp.clear();
+                                    for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
+                                        const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
+                                        if (cpos < U.size() && std::find(grp.begin(), grp.end(), U[cpos].node) == grp.end()) grp.push_back(U[cpos].node);
+                                    }
+                                    if (grp.size() < 2) continue;
+                                    rq_node.insert(rq_node.end(), grp.begin(), grp.end());
+                                    rq_ptr.push_back((int)rq_node.size());
+                                }
+                        }
+                        const int nreq = (int)rq_ptr.size() - 1;
+                        nr_ptr.assign(nu + 1, 0);
+                        for (int x : rq_node) nr_ptr[x + 1]++;
+                        for (int q = 0; q < nu; ++q) nr_ptr[q + 1] += nr_ptr[q];
+                        nr_idx.assign(rq_node.size(), 0);
+                        {
+                            std::vector<int> cur(nr_ptr.begin(), nr_ptr.end() - 1);
+                            for (int r = 0; r < nreq; ++r)
+                                for (int e = rq_ptr[r]; e < rq_ptr[r + 1]; ++e) nr_idx[cur[rq_node[e]]++] = r;
+                        }
+                        bank1.resize(nu);
+                        int fill1[NB] = {0};
+                        for (int q = 0; q < nu; ++q) {
+                            bank1[q] = slot1[q] % NB;
+                            ++fill1[bank1[q]];
+                        }
+                        constexpr int kSweeps = 2;   // more sweeps / a looser cap do not lower the conflict degree further (measured)
+                        const int cap = (nu + NB - 1) / NB + 1;
+                        auto matched = [&](int r) -> bool {   // can the request's points take distinct bank groups?
+                            BankMatcher M;
+                            const int e0 = rq_ptr[r];
+                            M.kk = rq_ptr[r + 1] - e0;
+                            for (int i = 0; i < M.kk; ++i) {
+                                M.opt[i][0] = slot[rq_node[e0 + i]] % NB;
+                                M.opt[i][1] = bank1[rq_node[e0 + i]];
+                            }
+                            return M.perfect();
+                        };
+                        rq_ok.assign(nreq, 0);
+                        for (int r = 0; r < nreq; ++r) rq_ok[r] = matched(r) ? 1 : 0;
+                        for (int sweep = 0; sweep < kSweeps; ++sweep)
+                            for (int q = 0; q < nu; ++q) {
+                                int bad0 = 0;
+                                for (int e = nr_ptr[q]; e < nr_ptr[q + 1]; ++e) bad0 += rq_ok[nr_idx[e]] ? 0 : 1;
+                                if (bad0 == 0) continue;
+                                const int oldb = bank1[q];
+                                int bestb = oldb, bestbad = bad0;
+                                for (int b = 0; b < NB && bestbad > 0; ++b) {
+                                    if (b == oldb || fill1[b] >= cap) continue;
+                                    bank1[q] = b;
+                                    int bad = 0;
+                                    for (int e = nr_ptr[q]; e < nr_ptr[q + 1] && bad < bestbad; ++e) bad += matched(nr_idx[e]) ? 0 : 1;
+                                    if (bad < bestbad) {
+                                        bestbad = bad;
+                                        bestb = b;
+                                    }
+                                }
+                                bank1[q] = bestb;
+                                if (bestb != oldb) {
+                                    --fill1[oldb];
+                                    ++fill1[bestb];
+                                    for (int e = nr_ptr[q]; e < nr_ptr[q + 1]; ++e) rq_ok[nr_idx[e]] = matched(nr_idx[e]) ? 1 : 0;
+                                }
+                            }
+                        int level1[NB] = {0};
+                        for (int q = 0; q < nu; ++q) {
+                            slot1[q] = level1[bank1[q]]++ * NB + bank1[q];
+                            nslots = std::max(nslots, slot1[q] + 1);
+                        }
+                    }
                 }
                 if (nslots + 1 > 4095) {
                     T.err_slots = nslots;
@@ -596,7 +714,7 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
 static int build_tiler(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, int R, bool colour, bool two_copies, DevTileR &out)
 {
     HostTileR h;
-    CHECK(build_tiler_host(c, A, nrows_dev, R, colour, two_copies, h));
+    CHECK(build_tiler_host(c, A, nrows_dev, R, colour, two_copies, h, (c->tile & 16) != 0));
     out.ncopy = h.ncopy;
     out.R = h.R;
     out.nslices = h.nslices;
@@ -619,51 +737,13 @@ static int build_tiler(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, int R, bool
 // Host-only self test of the union-tile format (no CUDA calls): a random banded operator is laid out by
 // build_tiler_host, then the kernels' walk (step words, row masks, per-row weight cursors, slot table) is replayed on
 // the CPU and compared bit for bit with the plain row sums in summation order.  Returns 0 when identical.
-extern "C" int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int with_perm, unsigned seed, double *stats4)
+// build the union-tile layout of A for the (stack) ctx, replay the kernels' walk on the CPU and compare with the plain row sums
+static int tile_selftest_run(mft_ctx &ctx, const Csr2 &A, int64_t n, int k, int R, int layout, int with_perm, uint64_t st, double *stats4)
 {
-    if (n <= 0 || k <= 0 || k > n || (R != 1 && R != 2 && R != 4)) return fail(MFT_EINVAL, "mft_debug_tile_selftest: bad arguments");
-    NvtxRange range("tile layout selftest");
-    mft_ctx ctx;
-    ctx.n_local = n - n / 7;  // some trailing "halo" columns without rows
-    ctx.n_halo = n - ctx.n_local;
-    ctx.n_tot = n;
-    ctx.V = 4;
-    uint64_t st = seed * 6364136223846793005ULL + 1442695040888963407ULL;
     auto rnd = [&]() { st = st * 6364136223846793005ULL + 1442695040888963407ULL; return (uint32_t)(st >> 33); };
-    if (with_perm) {
-        ctx.have_perm = true;
-        ctx.perm.resize(n);
-        std::iota(ctx.perm.begin(), ctx.perm.end(), 0);
-        // shuffle inside windows so that locality survives (device rows near each other stay near)
-        for (int64_t b = 0; b < ctx.n_local; b += 64)
-            for (int64_t i = std::min(ctx.n_local, b + 64) - 1; i > b; --i) std::swap(ctx.perm[i], ctx.perm[b + rnd() % (i - b + 1)]);
-        ctx.iperm.resize(n);
-        for (int64_t d = 0; d < n; ++d) ctx.iperm[ctx.perm[d]] = (int32_t)d;
-        ctx.keys.resize(n);
-        for (int64_t i = 0; i < n; ++i) ctx.keys[i] = (int64_t)(n - 1 - i) * 3;  // descending keys: order != column order
-    }
-    Csr2 A;
-    A.nrows = n;
-    A.ptr.assign(n + 1, 0);
-    for (int64_t r = 0; r < n; ++r) {
-        const int len = r < ctx.n_local ? std::max(1, k - (int)(rnd() % 4)) : 0;   // ragged rows
-        std::vector<int32_t> cs;
-        while ((int)cs.size() < len) {
-            const int64_t j = std::min<int64_t>(n - 1, std::max<int64_t>(0, r + (int64_t)(rnd() % (6 * k)) - 3 * k));
-            if (std::find(cs.begin(), cs.end(), (int32_t)j) == cs.end()) cs.push_back((int32_t)j);
-        }
-        auto keyf = [&](int32_t col) { return ctx.keys.empty() ? (int64_t)col : ctx.keys[col]; };
-        std::sort(cs.begin(), cs.end(), [&](int32_t a, int32_t b) { return keyf(a) < keyf(b); });
-        for (int32_t j : cs) {
-            A.col.push_back(j);
-            A.wx.push_back((double)(int)(rnd() % 2001 - 1000) / 64.0);
-            A.wy.push_back((double)(int)(rnd() % 2001 - 1000) / 32.0);
-        }
-        A.ptr[r + 1] = (int64_t)A.col.size();
-    }
     HostTileR h;
     const auto t_build0 = std::chrono::steady_clock::now();
-    CHECK(build_tiler_host(&ctx, A, ctx.n_local, R, (layout & 1) != 0, (layout & 2) != 0, h));
+    CHECK(build_tiler_host(&ctx, A, ctx.n_local, R, (layout & 1) != 0, (layout & 2) != 0, h, (layout & 4) != 0));
     if (getenv("MFT_TRACE")) {   // build time + a checksum of the whole layout (compare builds / thread counts)
         uint64_t fnv = 1469598103934665603ULL;
         auto mix = [&](const void *p, size_t bytes) {
@@ -755,4 +835,82 @@ extern "C" int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int 
     }
     if (bad) return fail(MFT_EINVAL, "mft_debug_tile_selftest: %lld rows differ", (long long)bad);
     return MFT_OK;
+}
+
+extern "C" int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int with_perm, unsigned seed, double *stats4)
+{
+    if (n <= 0 || k <= 0 || k > n || (R != 1 && R != 2 && R != 4)) return fail(MFT_EINVAL, "mft_debug_tile_selftest: bad arguments");
+    NvtxRange range("tile layout selftest");
+    mft_ctx ctx;
+    ctx.n_local = n - n / 7;  // some trailing "halo" columns without rows
+    ctx.n_halo = n - ctx.n_local;
+    ctx.n_tot = n;
+    ctx.V = 4;
+    uint64_t st = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+    auto rnd = [&]() { st = st * 6364136223846793005ULL + 1442695040888963407ULL; return (uint32_t)(st >> 33); };
+    if (with_perm) {
+        ctx.have_perm = true;
+        ctx.perm.resize(n);
+        std::iota(ctx.perm.begin(), ctx.perm.end(), 0);
+        // shuffle inside windows so that locality survives (device rows near each other stay near)
+        for (int64_t b = 0; b < ctx.n_local; b += 64)
+            for (int64_t i = std::min(ctx.n_local, b + 64) - 1; i > b; --i) std::swap(ctx.perm[i], ctx.perm[b + rnd() % (i - b + 1)]);
+        ctx.iperm.resize(n);
+        for (int64_t d = 0; d < n; ++d) ctx.iperm[ctx.perm[d]] = (int32_t)d;
+        ctx.keys.resize(n);
+        for (int64_t i = 0; i < n; ++i) ctx.keys[i] = (int64_t)(n - 1 - i) * 3;  // descending keys: order != column order
+    }
+    Csr2 A;
+    A.nrows = n;
+    A.ptr.assign(n + 1, 0);
+    for (int64_t r = 0; r < n; ++r) {
+        const int len = r < ctx.n_local ? std::max(1, k - (int)(rnd() % 4)) : 0;   // ragged rows
+        std::vector<int32_t> cs;
+        while ((int)cs.size() < len) {
+            const int64_t j = std::min<int64_t>(n - 1, std::max<int64_t>(0, r + (int64_t)(rnd() % (6 * k)) - 3 * k));
+            if (std::find(cs.begin(), cs.end(), (int32_t)j) == cs.end()) cs.push_back((int32_t)j);
+        }
+        auto keyf = [&](int32_t col) { return ctx.keys.empty() ? (int64_t)col : ctx.keys[col]; };
+        std::sort(cs.begin(), cs.end(), [&](int32_t a, int32_t b) { return keyf(a) < keyf(b); });
+        for (int32_t j : cs) {
+            A.col.push_back(j);
+            A.wx.push_back((double)(int)(rnd() % 2001 - 1000) / 64.0);
+            A.wy.push_back((double)(int)(rnd() % 2001 - 1000) / 32.0);
+        }
+        A.ptr[r + 1] = (int64_t)A.col.size();
+    }
+    return tile_selftest_run(ctx, A, n, k, R, layout, with_perm, st, stats4);
+}
+
+// the same self test on a caller-supplied sparsity (e.g. the kNN table of a real cloud or its transpose): rows = n_rows stencils
+// over n columns (0-based CSR, columns of a row in summation order = as given); weights are pseudo-random dyadic numbers
+extern "C" int mft_debug_tile_selftest_csr(int64_t n, int64_t n_rows, const int64_t *rowptr, const int32_t *col, int R, int layout,
+                                           unsigned seed, double *stats4)
+{
+    if (n <= 0 || n_rows < 0 || n_rows > n || !rowptr || !col || (R != 1 && R != 2 && R != 4))
+        return fail(MFT_EINVAL, "mft_debug_tile_selftest_csr: bad arguments");
+    mft_ctx ctx;
+    ctx.n_local = n_rows;
+    ctx.n_halo = n - n_rows;
+    ctx.n_tot = n;
+    ctx.V = 4;
+    uint64_t st = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+    auto rnd = [&]() { st = st * 6364136223846793005ULL + 1442695040888963407ULL; return (uint32_t)(st >> 33); };
+    Csr2 A;
+    A.nrows = n;
+    A.ptr.assign(n + 1, rowptr[n_rows]);
+    int kmax = 1;
+    for (int64_t r = 0; r <= n_rows; ++r) A.ptr[r] = rowptr[r];
+    const int64_t nnz = rowptr[n_rows];
+    A.col.resize(nnz);
+    A.wx.resize(nnz);
+    A.wy.resize(nnz);
+    for (int64_t r = 0; r < n_rows; ++r) kmax = std::max<int>(kmax, (int)(rowptr[r + 1] - rowptr[r]));
+    for (int64_t p = 0; p < nnz; ++p) {
+        if (col[p] < 0 || col[p] >= n) return fail(MFT_EINVAL, "mft_debug_tile_selftest_csr: column out of range");
+        A.col[p] = col[p];
+        A.wx[p] = (double)(int)(rnd() % 2001 - 1000) / 64.0;
+        A.wy[p] = (double)(int)(rnd() % 2001 - 1000) / 32.0;
+    }
+    return tile_selftest_run(ctx, A, n, kmax, R, layout, 0, st, stats4);
 }

@@ -59,7 +59,7 @@ import pytest
 
 
 @pytest.mark.parametrize("R", [1, 2, 4])
-@pytest.mark.parametrize("layout", [0, 1, 2, 3])   # bit 0: bank-coloured slots, bit 1: two copies of the records
+@pytest.mark.parametrize("layout", [0, 1, 2, 3, 7])   # bit 0: bank-coloured slots, bit 1: two copies of the records, bit 2: tuned copy
 @pytest.mark.parametrize("with_perm", [0, 1])
 def test_union_tile_format_replays_bit_exact(R, layout, with_perm):
     """Host logic of the union-tile operator layout (mft_tile_kernels.cuh): the builder's step words, row masks,
@@ -90,7 +90,7 @@ def test_union_tile_format_at_the_edge_sizes_of_the_gpu_tests():
         for k in (13, 15, 20, 30, 42):
             if k > n:
                 continue
-            for layout in (0, 3):
+            for layout in (0, 3, 7):
                 for perm in (0, 1):
                     assert lib.mft_debug_tile_selftest(n, k, 1, layout, perm, 7 + n, st) == 0, (n, k, layout, perm, lib.mft_last_error())
 
@@ -103,7 +103,7 @@ def test_union_tile_layout_does_not_depend_on_the_host_thread_count():
     import sys
 
     code = ("import sys, ctypes as C; sys.path.insert(0, %r); import mft_b200 as m; lib = m._lib.load(); st = (C.c_double * 4)()\n"
-            "for n, k, R, layout, perm in ((20000, 20, 1, 3, 1), (9000, 13, 2, 3, 0), (7000, 30, 4, 1, 1), (300, 20, 1, 3, 0)):\n"
+            "for n, k, R, layout, perm in ((20000, 20, 1, 3, 1), (9000, 13, 2, 7, 0), (7000, 30, 4, 1, 1), (300, 20, 1, 7, 0)):\n"
             "    assert lib.mft_debug_tile_selftest(n, k, R, layout, perm, 11, st) == 0\n") % cases.ROOT
     seen = []
     for threads in ("1", "3", "8"):
@@ -114,3 +114,43 @@ def test_union_tile_layout_does_not_depend_on_the_host_thread_count():
         assert len(sums) == 4, res.stderr
         seen.append(sums)
     assert seen[0] == seen[1] == seen[2]
+
+
+def test_tuned_second_copy_lowers_the_conflict_degree_on_a_real_stencil_structure():
+    """MFT_OPT_TILE bit 4 (layout only): on the kNN structure of the fixture cloud (forward operator and its transpose, ragged
+    rows) the builder's local search brings the simulated LDS.128 conflict degree of the two-copy layout close to 1, and the
+    replayed row sums stay bit-identical."""
+    import numpy as np
+    import scipy.sparse as sp
+
+    m = _mft()
+    L = m._lib
+    lib = L.load()
+    fx = cases.fixture_setup()
+    pts = fx["points"]
+    order = L.sfc_order(pts)
+    rank = np.empty(len(pts), dtype=np.int64)
+    rank[order] = np.arange(len(pts))
+    nb = rank[fx["nb"][order]]                      # the cloud renumbered along the curve, as the device sees it
+    n, k = nb.shape
+    A = sp.csr_matrix((np.ones(n * k), (np.repeat(np.arange(n), k), nb.reshape(-1))), shape=(n, n))
+    A.sort_indices()
+    AT = A.T.tocsr()
+    AT.sort_indices()
+    for M in (A, AT):
+        rp = np.ascontiguousarray(M.indptr, dtype=np.int64)
+        ci = np.ascontiguousarray(M.indices, dtype=np.int32)
+        deg = {}
+        for R in (1, 2):
+            for layout in (0, 3, 7):
+                st = (C.c_double * 4)()
+                assert lib.mft_debug_tile_selftest_csr(n, n, L.ptr(rp), L.ptr(ci), R, layout, 9, st) == 0, lib.mft_last_error()
+                deg[R, layout] = st[0]
+                assert st[3] < 4095
+        assert deg[1, 7] < deg[1, 3] < deg[1, 0] and deg[1, 7] < 1.12
+        assert deg[2, 7] < deg[2, 3] < deg[2, 0]
+    # argument checks
+    assert lib.mft_debug_tile_selftest_csr(n, n + 1, L.ptr(rp), L.ptr(ci), 1, 3, 9, None) != 0
+    bad = ci.copy()
+    bad[5] = n
+    assert lib.mft_debug_tile_selftest_csr(n, n, L.ptr(rp), L.ptr(bad), 1, 3, 9, None) != 0

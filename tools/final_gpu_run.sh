@@ -17,6 +17,11 @@ ls -la gpurun_out/
 python bench.py --source upwind --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_vortex_upwind.log 2>&1; tail -c 400 gpurun_out/bench_vortex_upwind.log
 python bench.py --workload sod --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_sod_rv.log 2>&1; tail -c 400 gpurun_out/bench_sod_rv.log
 bash tools/sanitize.sh
+# tuned second copy (layout only, MFT_OPT_TILE bit 4): simulated LDS.128 conflict degree 1.20 -> 1.02
+python bench.py --tile 31 --no-cpu-baseline > gpurun_out/bench_tile31.log 2>&1
+python -c "import json; d=json.loads(open('gpurun_out/bench_tile31.log').read().strip().splitlines()[-1]); print('tile31', d['value'], d['roofline']['kernel_ms_per_step'])"
+ncu --set full --clock-control none --import-source on -k regex:tiler --launch-skip 8 -c 2 -o gpurun_out/prof_r2_tile31 -f python bench.py --tile 31 --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncu_full31.log 2>&1
+ncu -i gpurun_out/prof_r2_tile31.ncu-rep --page raw --csv > gpurun_out/raw_r2_tile31.csv 2>/dev/null
 # occupancy experiment: 6 / 5 resident CTAs per SM for the tile kernels (no spills per ptxas)
 for occ in "6 5" "6 4" "5 5"; do
   set -- $occ
