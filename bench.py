@@ -140,7 +140,8 @@ def run_ours(args):
                                                                 single_sweep_exact=bool(args.single_sweep),
                                                                 exchange=args.exchange, pair_rows=int(args.pair_rows),
                                                                 tile=int(args.tile), tile_rows=int(args.tile_rows),
-                                                                prefetch_distance=args.pf_dist, setup=args.setup))
+                                                                prefetch_distance=args.pf_dist, setup=args.setup,
+                                                                refine_order=bool(args.refine_order)))
     names = dict(left=1, right=2, bottom=3, top=4)
     t_setup = time.time()
     domain = m.ParallelPointCloudDomain(solver, cl, names, comm) if multi else m.PointCloudDomain(solver, cl, names)
@@ -472,6 +473,7 @@ def main():
                     help="vortex: BASELINE configs[1] (default, the bench line); sod: configs[3] (shock tube, slip/Dirichlet mix)")
     ap.add_argument("--source", default="residual", choices=["residual", "upwind"],
                     help="stabilisation source: residual viscosity + history (configs[1], [3]) or upwind viscosity (configs[2])")
+    ap.add_argument("--refine-order", type=int, default=0, help="1: order the rows inside a tile by D' row length (fewer padding steps in pass B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--cloud-order", default="hilbert", choices=["hilbert", "lattice"],

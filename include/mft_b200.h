@@ -76,8 +76,9 @@ typedef struct mft_ctx mft_ctx;
                                       after the x sweep (smaller footprint -> larger L1).  Union-tile kernels stream their weights (measured faster) unless bit 3 is set:
                                       then bit 0 / bit 1 stage the compact weight blocks of one direction (two sweeps).
                                       Default 5 (measured best). */
-#define MFT_OPT_REFINE_ORDER 7     /* 1 (default 0): within blocks of 256 device rows, order rows by D' row length
-                                      (near-uniform transposed-ELL slices); the caller-visible numbering is unaffected */
+#define MFT_OPT_REFINE_ORDER 7     /* 1 (default 0): within blocks of device rows (one union tile; 256 rows for the sliced-ELL kernels),
+                                      order rows by D' row length: near-uniform slices of the transposed operator (fewer padding
+                                      steps in pass B); tiles keep their rows and unions; the caller-visible numbering is unaffected */
 #define MFT_OPT_SINGLE_SWEEP_EXACT 8/* 1: for the default 20-wide stencil use the single-sweep exact kernel (y-products parked in registers:
                                       one gather + one flux per neighbour, but 255 registers -> 8 warps/SM; measured 20 % slower);
                                       0 (default): the two-sweep exact kernel.  Same results bit for bit.                       */

@@ -90,7 +90,7 @@ class RBFFDEngineCUDA:
     tile_rows: int = 11                # rows per thread of the union-tile kernels: units digit pass A, tens digit pass B (1, 2, 4)
     prefetch_distance: int | None = None  # slices ahead for the L2 prefetch of operator data (None: library default, 0: off)
     single_sweep_exact: bool = False   # k=20: exact-order pass A in one sweep (y-products parked in registers)
-    refine_order: bool = False         # order rows inside 256-row blocks by D' row length (less padding, worse gather locality)
+    refine_order: bool = False         # order the rows inside a tile by D' row length (fewer padding steps in pass B; opt-in)
     setup: str = "host"                # "device": kNN + RBF-FD weight solves on the GPU (mft_setup_knn / mft_setup_rbf_weights)
 
 

@@ -766,8 +766,12 @@ extern "C" int mft_finalize(mft_ctx *c)
         sort_rows_by_key(F, c->keys, true);
         sort_rows_by_key(T, c->keys, true);
     }
-    // Within blocks of 256 device rows, order the rows by the length of their D' row: slices of the transposed
-    // sliced-ELL operator then have near-uniform width (little padding).  Locality is untouched (same block).
+    // Within blocks of device rows, order the rows by the length of their D' row: slices of the transposed operator then
+    // have near-uniform width (little padding).  Sliced-ELL kernels: blocks of 256 rows (locality is untouched inside a block,
+    // measured no gain: the gathers of a warp spread).  Union-tile kernels: block = one tile, so every tile keeps exactly its
+    // rows and its stencil union and only the order inside the tile changes -- simulated on the bench cloud (host replay):
+    // 22.2 -> 20.7 steps per row of D' and conflict degree 1.08 -> 1.04.
+    const bool tiles_on = (c->tile & 3) && c->V == 4 && c->eq == MFT_EQ_EULER2D;
     if (has_visc(c) && c->refine_order) {
         const int64_t nl = c->n_local;
         if (!c->have_perm) {
@@ -777,8 +781,14 @@ extern "C" int mft_finalize(mft_ctx *c)
             c->have_perm = true;
         }
         auto len = [&](int32_t pt) { return T.ptr[pt + 1] - T.ptr[pt]; };
-        for (int64_t b0 = 0; b0 < nl; b0 += 256) {
-            const int64_t b1 = std::min(nl, b0 + 256);
+        int64_t blk = 256;
+        if (tiles_on) {
+            const int64_t ta = (c->tile & 1) ? (int64_t)kSlice * kTileWarps * c->tile_rows_a : (int64_t)1 << 40;
+            const int64_t tb = (c->tile & 2) ? (int64_t)kSlice * kTileWarps * c->tile_rows_b : (int64_t)1 << 40;
+            blk = std::min(ta, tb);   // tile sizes are 128 * {1, 2, 4}: the smaller one divides the larger
+        }
+        for (int64_t b0 = 0; b0 < nl; b0 += blk) {
+            const int64_t b1 = std::min(nl, b0 + blk);
             std::stable_sort(c->perm.begin() + b0, c->perm.begin() + b1, [&](int32_t x, int32_t y) { return len(x) > len(y); });
         }
         for (int64_t d = 0; d < n; ++d) c->iperm[c->perm[d]] = (int32_t)d;

@@ -13,14 +13,14 @@ pytestmark = pytest.mark.gpu
 NAMES = dict(left=1, right=2, bottom=3, top=4)
 
 
-def _case(m, nx, ny, nv, tile, source, empty_group=False):
+def _case(m, nx, ny, nv, tile, source, empty_group=False, refine_order=False):
     cl = m.cloud.jittered_lattice(nx, ny, 2.0, 2.0 * ny / nx, seed=5)
     if empty_group:      # BoundaryData with no points (a group that exists in the file but is empty on this cloud)
         cl.boundary_idxs[3] = np.zeros(0, dtype=np.int64)
         cl.boundary_normals[3] = np.zeros((0, 2))
     deg = 3 if nv >= 20 else 2
     basis = m.PointCloudBasis(m.Point2D(), deg, approximation_type=m.RBF(m.PolyharmonicSpline(3)), nv=nv)
-    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(tile=tile))
+    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(tile=tile, refine_order=refine_order))
     domain = m.PointCloudDomain(solver, cl, NAMES)
     eq = m.CompressibleEulerEquations2D(cases.GAMMA)
     ic = lambda x, t, e=None: cases.ic_smooth_euler(x, t)   # noqa: E731
@@ -88,3 +88,11 @@ def test_tuned_second_copy_layout(source):
     import mft_b200 as m
 
     _case(m, 40, 36, 20, 31, source)
+
+
+@pytest.mark.parametrize("tile", [15, 31, 0])
+def test_rows_of_a_tile_ordered_by_transposed_row_length(tile):
+    """MFT_OPT_REFINE_ORDER: a permutation inside every tile (256-row blocks for the sliced-ELL kernels) -- same results"""
+    import mft_b200 as m
+
+    _case(m, 40, 36, 20, tile, "residual", refine_order=True)

@@ -22,6 +22,12 @@ python bench.py --tile 31 --no-cpu-baseline > gpurun_out/bench_tile31.log 2>&1
 python -c "import json; d=json.loads(open('gpurun_out/bench_tile31.log').read().strip().splitlines()[-1]); print('tile31', d['value'], d['roofline']['kernel_ms_per_step'])"
 ncu --set full --clock-control none --import-source on -k regex:tiler --launch-skip 8 -c 2 -o gpurun_out/prof_r2_tile31 -f python bench.py --tile 31 --steps 2 --warmup 3 --graph 0 --no-cpu-baseline > gpurun_out/ncu_full31.log 2>&1
 ncu -i gpurun_out/prof_r2_tile31.ncu-rep --page raw --csv > gpurun_out/raw_r2_tile31.csv 2>/dev/null
+# rows of a tile ordered by D' row length (pass B: 22.2 -> 20.7 steps per row in the host replay), alone and with the tuned copy
+for cfg in "15 1" "31 1"; do
+  set -- $cfg
+  python bench.py --tile $1 --refine-order $2 --no-cpu-baseline > gpurun_out/bench_tile$1_refine$2.log 2>&1
+  python -c "import json; d=json.loads(open('gpurun_out/bench_tile$1_refine$2.log').read().strip().splitlines()[-1]); print('tile $1 refine $2', d['value'], d['roofline']['kernel_ms_per_step'])"
+done
 # occupancy experiment: 6 / 5 resident CTAs per SM for the tile kernels (no spills per ptxas)
 for occ in "6 5" "6 4" "5 5"; do
   set -- $occ
