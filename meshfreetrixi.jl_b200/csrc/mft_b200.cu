@@ -20,6 +20,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 

@@ -214,7 +214,14 @@ template <class F>
 static void host_parallel(int nthreads, F fn)
 {
     std::vector<std::thread> pool;
-    for (int w = 1; w < nthreads; ++w) pool.emplace_back([&fn, w]() { fn(w); });
+    pool.reserve(nthreads > 1 ? nthreads - 1 : 0);
+    for (int w = 1; w < nthreads; ++w) {
+        try {
+            pool.emplace_back([&fn, w]() { fn(w); });
+        } catch (const std::system_error &) {
+            break;  // thread limit reached: the workers that did start (and this thread) share the work through the atomic cursor
+        }
+    }
     fn(0);
     for (auto &th : pool) th.join();
 }
