@@ -114,8 +114,9 @@ def test_two_gpus_device_setup_match_serial_oracle(tmp_path):
     assert all(r["err"] < 1e-9 and r["err_steps"] < 1e-8 for r in res)
 
 
-@pytest.mark.parametrize("nranks,shape", [(1, (40, 30)), (4, (64, 48)), (5, (50, 70)), (8, (96, 64))])
-def test_partition_planner_invariants(nranks, shape):
+@pytest.mark.parametrize("nranks,shape,wide", [(1, (40, 30), False), (4, (64, 48), False), (5, (50, 70), False), (8, (96, 64), False),
+                                               (4, (64, 48), True), (7, (60, 50), True)])
+def test_partition_planner_invariants(nranks, shape, wide):
     """host planner on 1/4/5/8 ranks (threads stand in for the ranks; the planner only needs an allgather): ownership is a
     partition of the cloud, every stencil column of an owned row is local, halo blocks are grouped by owner, and the send
     lists of one rank are exactly what its peers expect to receive, in the receivers' halo order"""
@@ -139,7 +140,7 @@ def test_partition_planner_invariants(nranks, shape):
             return out
         try:
             parts[r] = partition.build_rank_partition(cl.points, [np.asarray(b) for b in cl.boundary_idxs], cl.boundary_normals,
-                                                      r, nranks, 3, 3, 20, allgather)
+                                                      r, nranks, 3, 3, 20, allgather, wide_halo=wide)
         except Exception as e:   # noqa: BLE001
             errs.append(e)
             barrier.abort()
@@ -170,6 +171,18 @@ def test_partition_planner_invariants(nranks, shape):
             assert np.array_equal(sender.owned_gid[sender.send_idx[i]], want)   # what q sends is what p expects, in order
             off += cnt
         assert off == p.n_halo
+        if wide:
+            # wide halo: the foreign rows whose stencils contain an owned point (R_r) are halo rows, every one of their stencil
+            # columns is local, the column-only points carry no operator row, and the narrow plan is a subset
+            touches = np.isin(nb_g, p.owned_gid).any(axis=1)
+            R = np.setdiff1d(np.nonzero(touches)[0], p.owned_gid)
+            assert set(R.tolist()) <= set(p.halo_gid.tolist())
+            assert set(np.unique(nb_g[R]).tolist()) <= local
+            col_only = p.neighbors_halo[:, 0] < 0
+            assert col_only.any() and not np.isin(p.halo_gid[col_only], R).any()
+            assert np.array_equal(p.neighbors_halo[~col_only], nb_g[p.halo_gid[~col_only]])
+            for A in p.ops:
+                assert A.tocsr()[p.n_local + np.nonzero(col_only)[0]].nnz == 0
         # boundary points: each global boundary point belongs to exactly one rank's list
     for g in range(4):
         got = np.concatenate([p.owned_gid[p.boundary_idxs[g]] for p in parts])
