@@ -1,6 +1,6 @@
 """Row f1 (device setup pipeline), CPU tier: the product's kernel thread bodies and host orchestration
 (csrc/mft_setup_kernels.cuh, csrc/mft_setup_host.inl), compiled for the host by tests/emu and checked against the oracle
-and brute force.  The GPU tier (tests/test_zz_setup_gpu.py) runs the same source as CUDA kernels through the C ABI."""
+and brute force.  The GPU tier (tests/test_zz_g_setup_gpu.py) runs the same source as CUDA kernels through the C ABI."""
 import ctypes as C
 
 import numpy as np
@@ -146,7 +146,7 @@ def test_product_library_refuses_setup_without_a_device():
 
     lib = m._lib.load()
     if lib.mft_device_count() > 0:
-        pytest.skip("GPU box: covered by tests/test_zz_setup_gpu.py")
+        pytest.skip("GPU box: covered by tests/test_zz_g_setup_gpu.py")
     pts = np.random.default_rng(0).random((50, 2))
     with pytest.raises(m._lib.MftError, match="no CPU fallback"):
         m.setup_ops.knn_device(pts, 5)

@@ -1,6 +1,6 @@
 """Committed golden vectors of the "next" rows (tests/golden/fixture_golden_f.npz + the kNN table / weights stored in
 fixture_golden.npz).  CPU: the oracle reproduces them, and so do the product's kernel bodies under host emulation, without
-the oracle in the loop.  GPU (tests/test_zz_golden_f_gpu.py): the CUDA path reproduces them."""
+the oracle in the loop.  GPU (tests/test_zz_h_golden_f_gpu.py): the CUDA path reproduces them."""
 import os
 import sys
 

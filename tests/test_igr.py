@@ -2,7 +2,7 @@
  * the oracle's C restatement against an independent numpy/scipy restatement of the same formulas and of
    IterativeSolvers.cg! (parity unpinned: no reference test uses the source, the solver is third party);
  * the product's kernel thread bodies + launch sequence + reduction tree, run on the host by tests/emu, against the oracle.
-The GPU tier is tests/test_zz_igr_gpu.py."""
+The GPU tier is tests/test_zz_i_igr_gpu.py."""
 import numpy as np
 import pytest
 import scipy.sparse as sp

@@ -1,6 +1,6 @@
 """The CUDA path reproduces the committed golden vectors of the "next" rows WITHOUT the oracle in the loop
 (tests/golden/fixture_golden_f.npz, made by tests/golden/make_golden_f.py; kNN table / weights of fixture_golden.npz).
-First hardware run is the round-end test pass (see tests/test_zz_setup_gpu.py)."""
+First hardware run is the round-end test pass (see tests/test_zz_g_setup_gpu.py)."""
 import os
 import sys
 

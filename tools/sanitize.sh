@@ -8,6 +8,6 @@ for tool in memcheck racecheck; do
   $SAN --tool $tool --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitize_${tool}_smoke.log 2>&1
   echo "$tool smoke: exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/sanitize_${tool}_smoke.log
 done
-$SAN --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_setup_gpu.py tests/test_zz_limiter.py tests/test_zz_igr_gpu.py tests/test_zz_aux_gpu.py \
+$SAN --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_g_setup_gpu.py tests/test_zz_f_limiter.py tests/test_zz_i_igr_gpu.py tests/test_zz_b_aux_gpu.py \
   -m gpu -q -k "not million" > gpurun_out/sanitize_memcheck_next_rows.log 2>&1
 echo "memcheck next rows: exit $?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitize_memcheck_next_rows.log
