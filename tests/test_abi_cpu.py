@@ -81,7 +81,7 @@ def test_union_tile_format_replays_bit_exact(R, layout, with_perm):
 
 
 def test_union_tile_format_at_the_edge_sizes_of_the_gpu_tests():
-    """the host layout builder at the cloud sizes tests/test_zzz_edge_sizes_gpu.py runs on hardware (below one slice, below
+    """the host layout builder at the cloud sizes tests/test_zz_ee_edge_sizes_gpu.py runs on hardware (below one slice, below
     one tile, straddling the 32-row and 128-row boundaries) and the stencil widths of the sweep"""
     m = _mft()
     lib = m._lib.load()

@@ -79,20 +79,3 @@ def test_empty_boundary_group_and_no_sources():
 
     _case(m, 9, 7, 20, 15, None, empty_group=True)
     _case(m, 9, 7, 20, 0, "upwind", empty_group=True)
-
-
-@pytest.mark.parametrize("source", ["upwind", "residual"])
-def test_tuned_second_copy_layout(source):
-    """MFT_OPT_TILE = 31: the second record copy's bank groups come from the builder's local search (layout only; the kernels
-    follow the step words) -- same results as every other layout"""
-    import mft_b200 as m
-
-    _case(m, 40, 36, 20, 31, source)
-
-
-@pytest.mark.parametrize("tile", [15, 31, 0])
-def test_rows_of_a_tile_ordered_by_transposed_row_length(tile):
-    """MFT_OPT_REFINE_ORDER: a permutation inside every tile (256-row blocks for the sliced-ELL kernels) -- same results"""
-    import mft_b200 as m
-
-    _case(m, 40, 36, 20, tile, "residual", refine_order=True)
