@@ -271,9 +271,9 @@ int mft_set_stage_limiter(mft_ctx *ctx, int npairs, const double *thresholds, co
 int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int with_perm, unsigned seed, double *stats4);
 /* The same self test on a caller-supplied sparsity (the kNN table of a real cloud, or its transpose): n_rows stencils over n
  * columns, 0-based CSR, the columns of a row in summation order; pseudo-random dyadic weights.  layout bits as MFT_OPT_TILE >> 2
- * (1: bank-coloured slots, 2: two record copies, 4: tuned second copy). */
+ * (1: bank-coloured slots, 2: two record copies, 4: tuned copies). */
 int mft_debug_tile_selftest_csr(int64_t n, int64_t n_rows, const int64_t *rowptr, const int32_t *col, int R, int layout,
-                                unsigned seed, double *stats4);
+                                unsigned seed, double *stats6);  /* stats4 + STS.128 conflict degree of the phase-1 stores, copy 0 / copy 1 */
 
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------------------------------------
  * replaces MPICache + perform_halo_update! (src/domains/PointCloudDomain/ParallelPointCloud.jl:6-71,

@@ -506,11 +506,37 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
                             bank[a] = choose(a);
                             ++fill[bank[a]];
                         }
-                    int level[NB] = {0};
-                    nslots = 0;
-                    for (int q = 0; q < nu; ++q) {
-                        slot[q] = level[bank[q]]++ * NB + bank[q];
-                        nslots = std::max(nslots, slot[q] + 1);
+                    if (tune_copy1) {
+                        // phase 1 stores entry q of the union list from thread q: the 8 lanes of an STS.128 phase hold an aligned
+                        // octet of the list.  Keep the colouring where it already gives the octet 8 different bank groups and move
+                        // the duplicates to the free groups: conflict-free stores, slot = octet * 8 + group (compact).
+                        for (int o = 0; o < nu; o += NB) {
+                            const int oe = std::min(nu, o + NB);
+                            unsigned used = 0;
+                            int dup[NB], nd = 0;
+                            for (int q = o; q < oe; ++q) {
+                                if (used & (1u << bank[q])) dup[nd++] = q;
+                                else used |= 1u << bank[q];
+                            }
+                            int b = 0;
+                            for (int i = 0; i < nd; ++i) {
+                                while (used & (1u << b)) ++b;
+                                bank[dup[i]] = b;
+                                used |= 1u << b;
+                            }
+                        }
+                        nslots = 0;
+                        for (int q = 0; q < nu; ++q) {
+                            slot[q] = (q / NB) * NB + bank[q];
+                            nslots = std::max(nslots, slot[q] + 1);
+                        }
+                    } else {
+                        int level[NB] = {0};
+                        nslots = 0;
+                        for (int q = 0; q < nu; ++q) {
+                            slot[q] = level[bank[q]]++ * NB + bank[q];
+                            nslots = std::max(nslots, slot[q] + 1);
+                        }
                     }
                 }
                 // second copy of the tile's records under an independent (pseudo-random) bank assignment: each distinct point a
@@ -560,14 +586,18 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
                             for (int r = 0; r < nreq; ++r)
                                 for (int e = rq_ptr[r]; e < rq_ptr[r + 1]; ++e) nr_idx[cur[rq_node[e]]++] = r;
                         }
+                        // copy 1 starts from a random permutation of the bank groups inside every octet of the union list (octets
+                        // stay permutations: conflict-free phase-1 stores, compact slots) ...
                         bank1.resize(nu);
-                        int fill1[NB] = {0};
-                        for (int q = 0; q < nu; ++q) {
-                            bank1[q] = slot1[q] % NB;
-                            ++fill1[bank1[q]];
+                        for (int o = 0; o < nu; o += NB) {
+                            const int oe = std::min(nu, o + NB);
+                            for (int q = o; q < oe; ++q) {
+                                int rank = 0;
+                                for (int q2 = o; q2 < oe; ++q2) rank += slot1[q2] < slot1[q] ? 1 : 0;   // slot1: random permutation
+                                bank1[q] = rank;
+                            }
                         }
-                        constexpr int kSweeps = 2;   // more sweeps / a looser cap do not lower the conflict degree further (measured)
-                        const int cap = (nu + NB - 1) / NB + 1;
+                        constexpr int kSweeps = 2;   // more sweeps do not lower the conflict degree further (measured)
                         auto matched = [&](int r) -> bool {   // can the request's points take distinct bank groups?
                             BankMatcher M;
                             const int e0 = rq_ptr[r];
@@ -580,33 +610,42 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
                         };
                         rq_ok.assign(nreq, 0);
                         for (int r = 0; r < nreq; ++r) rq_ok[r] = matched(r) ? 1 : 0;
+                        std::vector<int> &stamp = S.order;   // request -> last point that counted it (scratch)
+                        stamp.assign(nreq, -1);
+                        // ... and is improved by swaps inside an octet: the swap that leaves the fewest requests of the two points
+                        // unmatched
                         for (int sweep = 0; sweep < kSweeps; ++sweep)
                             for (int q = 0; q < nu; ++q) {
-                                int bad0 = 0;
-                                for (int e = nr_ptr[q]; e < nr_ptr[q + 1]; ++e) bad0 += rq_ok[nr_idx[e]] ? 0 : 1;
-                                if (bad0 == 0) continue;
-                                const int oldb = bank1[q];
-                                int bestb = oldb, bestbad = bad0;
-                                for (int b = 0; b < NB && bestbad > 0; ++b) {
-                                    if (b == oldb || fill1[b] >= cap) continue;
-                                    bank1[q] = b;
-                                    int bad = 0;
-                                    for (int e = nr_ptr[q]; e < nr_ptr[q + 1] && bad < bestbad; ++e) bad += matched(nr_idx[e]) ? 0 : 1;
-                                    if (bad < bestbad) {
-                                        bestbad = bad;
-                                        bestb = b;
+                                int bad_q = 0;
+                                for (int e = nr_ptr[q]; e < nr_ptr[q + 1]; ++e) bad_q += rq_ok[nr_idx[e]] ? 0 : 1;
+                                if (bad_q == 0) continue;
+                                const int o = (q / NB) * NB, oe = std::min(nu, o + NB);
+                                int best2 = -1, best_gain = 0;
+                                for (int q2 = o; q2 < oe; ++q2) {
+                                    if (q2 == q) continue;
+                                    const int mark = q * NB + (q2 - o);
+                                    int before = bad_q, after = 0;
+                                    for (int e = nr_ptr[q]; e < nr_ptr[q + 1]; ++e) stamp[nr_idx[e]] = mark;
+                                    for (int e = nr_ptr[q2]; e < nr_ptr[q2 + 1]; ++e)
+                                        if (stamp[nr_idx[e]] != mark) before += rq_ok[nr_idx[e]] ? 0 : 1;
+                                    std::swap(bank1[q], bank1[q2]);
+                                    for (int e = nr_ptr[q]; e < nr_ptr[q + 1] && before - after > best_gain; ++e) after += matched(nr_idx[e]) ? 0 : 1;
+                                    for (int e = nr_ptr[q2]; e < nr_ptr[q2 + 1] && before - after > best_gain; ++e)
+                                        if (stamp[nr_idx[e]] != mark) after += matched(nr_idx[e]) ? 0 : 1;
+                                    std::swap(bank1[q], bank1[q2]);
+                                    if (before - after > best_gain) {
+                                        best_gain = before - after;
+                                        best2 = q2;
                                     }
                                 }
-                                bank1[q] = bestb;
-                                if (bestb != oldb) {
-                                    --fill1[oldb];
-                                    ++fill1[bestb];
+                                if (best2 >= 0) {
+                                    std::swap(bank1[q], bank1[best2]);
                                     for (int e = nr_ptr[q]; e < nr_ptr[q + 1]; ++e) rq_ok[nr_idx[e]] = matched(nr_idx[e]) ? 1 : 0;
+                                    for (int e = nr_ptr[best2]; e < nr_ptr[best2 + 1]; ++e) rq_ok[nr_idx[e]] = matched(nr_idx[e]) ? 1 : 0;
                                 }
                             }
-                        int level1[NB] = {0};
                         for (int q = 0; q < nu; ++q) {
-                            slot1[q] = level1[bank1[q]]++ * NB + bank1[q];
+                            slot1[q] = (q / NB) * NB + bank1[q];
                             nslots = std::max(nslots, slot1[q] + 1);
                         }
                     }
@@ -745,7 +784,8 @@ static int build_tiler(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, int R, bool
 // build_tiler_host, then the kernels' walk (step words, row masks, per-row weight cursors, slot table) is replayed on
 // the CPU and compared bit for bit with the plain row sums in summation order.  Returns 0 when identical.
 // build the union-tile layout of A for the (stack) ctx, replay the kernels' walk on the CPU and compare with the plain row sums
-static int tile_selftest_run(mft_ctx &ctx, const Csr2 &A, int64_t n, int k, int R, int layout, int with_perm, uint64_t st, double *stats4)
+static int tile_selftest_run(mft_ctx &ctx, const Csr2 &A, int64_t n, int k, int R, int layout, int with_perm, uint64_t st, double *stats4,
+                             int nstats = 4)
 {
     auto rnd = [&]() { st = st * 6364136223846793005ULL + 1442695040888963407ULL; return (uint32_t)(st >> 33); };
     HostTileR h;
@@ -839,6 +879,23 @@ static int tile_selftest_run(mft_ctx &ctx, const Csr2 &A, int64_t n, int k, int 
         stats4[1] = (double)h.nsteps * kSlice / (double)std::max<int64_t>(1, ctx.n_local);  // union steps per row
         stats4[2] = (double)h.ulist.size() / (double)std::max<int64_t>(1, ctx.n_local);    // union entries per row
         stats4[3] = (double)h.sstride;
+        if (nstats >= 6) {
+            // phase-1 stores: thread q writes entry q of the tile's union list; the 8 lanes of an STS.128 phase hold an aligned
+            // octet of the list -> conflict degree = largest number of entries of the octet in one bank group, per copy
+            double sum[2] = {0.0, 0.0};
+            int64_t noct = 0;
+            for (int t = 0; t < h.ntiles; ++t) {
+                const int u0 = h.uoff[t], nu = h.uoff[t + 1] - u0;
+                for (int o = 0; o < nu; o += 8, ++noct)
+                    for (int cpy = 0; cpy < 2; ++cpy) {
+                        int cnt[8] = {0}, mx = 0;
+                        for (int q = o; q < std::min(nu, o + 8); ++q) mx = std::max(mx, ++cnt[h.uslot[2 * (u0 + q) + cpy] % 8]);
+                        sum[cpy] += mx;
+                    }
+            }
+            stats4[4] = noct ? sum[0] / (double)noct : 0.0;
+            stats4[5] = noct ? sum[1] / (double)noct : 0.0;
+        }
     }
     if (bad) return fail(MFT_EINVAL, "mft_debug_tile_selftest: %lld rows differ", (long long)bad);
     return MFT_OK;
@@ -892,7 +949,7 @@ extern "C" int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int 
 // the same self test on a caller-supplied sparsity (e.g. the kNN table of a real cloud or its transpose): rows = n_rows stencils
 // over n columns (0-based CSR, columns of a row in summation order = as given); weights are pseudo-random dyadic numbers
 extern "C" int mft_debug_tile_selftest_csr(int64_t n, int64_t n_rows, const int64_t *rowptr, const int32_t *col, int R, int layout,
-                                           unsigned seed, double *stats4)
+                                           unsigned seed, double *stats6)
 {
     if (n <= 0 || n_rows < 0 || n_rows > n || !rowptr || !col || (R != 1 && R != 2 && R != 4))
         return fail(MFT_EINVAL, "mft_debug_tile_selftest_csr: bad arguments");
@@ -919,5 +976,5 @@ extern "C" int mft_debug_tile_selftest_csr(int64_t n, int64_t n_rows, const int6
         A.wx[p] = (double)(int)(rnd() % 2001 - 1000) / 64.0;
         A.wy[p] = (double)(int)(rnd() % 2001 - 1000) / 32.0;
     }
-    return tile_selftest_run(ctx, A, n, kmax, R, layout, 0, st, stats4);
+    return tile_selftest_run(ctx, A, n, kmax, R, layout, 0, st, stats6, 6);
 }

@@ -118,8 +118,8 @@ def test_union_tile_layout_does_not_depend_on_the_host_thread_count():
 
 def test_tuned_second_copy_lowers_the_conflict_degree_on_a_real_stencil_structure():
     """MFT_OPT_TILE bit 4 (layout only): on the kNN structure of the fixture cloud (forward operator and its transpose, ragged
-    rows) the builder's local search brings the simulated LDS.128 conflict degree of the two-copy layout close to 1, and the
-    replayed row sums stay bit-identical."""
+    rows) the builder's local search brings the simulated LDS.128 conflict degree of the two-copy layout close to 1, the
+    phase-1 stores become conflict-free, and the replayed row sums stay bit-identical."""
     import numpy as np
     import scipy.sparse as sp
 
@@ -143,10 +143,14 @@ def test_tuned_second_copy_lowers_the_conflict_degree_on_a_real_stencil_structur
         deg = {}
         for R in (1, 2):
             for layout in (0, 3, 7):
-                st = (C.c_double * 4)()
+                st = (C.c_double * 6)()
                 assert lib.mft_debug_tile_selftest_csr(n, n, L.ptr(rp), L.ptr(ci), R, layout, 9, st) == 0, lib.mft_last_error()
                 deg[R, layout] = st[0]
                 assert st[3] < 4095
+                if layout == 7:      # octets of the union list are permutations of the bank groups: conflict-free phase-1 stores
+                    assert st[4] <= 1.06 and st[5] <= 1.06
+                elif layout == 3:
+                    assert st[4] > 1.5 and st[5] > 1.5
         assert deg[1, 7] < deg[1, 3] < deg[1, 0] and deg[1, 7] < 1.12
         assert deg[2, 7] < deg[2, 3] < deg[2, 0]
     # argument checks
