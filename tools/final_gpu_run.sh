@@ -28,6 +28,12 @@ for cfg in "15 1" "31 1"; do
   python bench.py --tile $1 --refine-order $2 --no-cpu-baseline > gpurun_out/bench_tile$1_refine$2.log 2>&1
   python -c "import json; d=json.loads(open('gpurun_out/bench_tile$1_refine$2.log').read().strip().splitlines()[-1]); print('tile $1 refine $2', d['value'], d['roofline']['kernel_ms_per_step'])"
 done
+# pass B with two rows per thread (same register count as one row per thread: 120 vs 118; 14.3 instead of 22.3 union steps per row in
+# the host replay, but 256-row tiles: 60 KB of shared memory per block), default and tuned layout
+for t in 15 31; do
+  python bench.py --tile $t --tile-rows 21 --no-cpu-baseline > gpurun_out/bench_tile${t}_rowsB2.log 2>&1
+  python -c "import json; d=json.loads(open('gpurun_out/bench_tile${t}_rowsB2.log').read().strip().splitlines()[-1]); print('tile $t rows 21', d['value'], d['roofline']['kernel_ms_per_step'])"
+done
 # occupancy experiment: 6 / 5 resident CTAs per SM for the tile kernels (no spills per ptxas)
 for occ in "6 5" "6 4" "5 5"; do
   set -- $occ
