@@ -13,14 +13,14 @@ pytestmark = pytest.mark.gpu
 NAMES = dict(left=1, right=2, bottom=3, top=4)
 
 
-def _case(m, nx, ny, nv, tile, source, empty_group=False, refine_order=False):
+def _case(m, nx, ny, nv, tile, source, empty_group=False, refine_order=False, tile_rows=11):
     cl = m.cloud.jittered_lattice(nx, ny, 2.0, 2.0 * ny / nx, seed=5)
     if empty_group:      # BoundaryData with no points (a group that exists in the file but is empty on this cloud)
         cl.boundary_idxs[3] = np.zeros(0, dtype=np.int64)
         cl.boundary_normals[3] = np.zeros((0, 2))
     deg = 3 if nv >= 20 else 2
     basis = m.PointCloudBasis(m.Point2D(), deg, approximation_type=m.RBF(m.PolyharmonicSpline(3)), nv=nv)
-    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(tile=tile, refine_order=refine_order))
+    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(tile=tile, refine_order=refine_order, tile_rows=tile_rows))
     domain = m.PointCloudDomain(solver, cl, NAMES)
     eq = m.CompressibleEulerEquations2D(cases.GAMMA)
     ic = lambda x, t, e=None: cases.ic_smooth_euler(x, t)   # noqa: E731

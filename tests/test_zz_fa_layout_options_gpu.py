@@ -23,3 +23,11 @@ def test_rows_of_a_tile_ordered_by_transposed_row_length(tile):
     import mft_b200 as m
 
     _case(m, 40, 36, 20, tile, "residual", refine_order=True)
+
+
+@pytest.mark.parametrize("tile,tile_rows", [(15, 21), (31, 21), (31, 22), (31, 42)])
+def test_rows_per_thread_with_the_tuned_layout(tile, tile_rows):
+    """two / four rows per thread over the union of their stencils (pass B digit first), default and tuned record copies"""
+    import mft_b200 as m
+
+    _case(m, 40, 36, 20, tile, "residual", tile_rows=tile_rows)
