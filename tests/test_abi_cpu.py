@@ -158,3 +158,33 @@ def test_tuned_second_copy_lowers_the_conflict_degree_on_a_real_stencil_structur
     bad = ci.copy()
     bad[5] = n
     assert lib.mft_debug_tile_selftest_csr(n, n, L.ptr(rp), L.ptr(bad), 1, 3, 9, None) != 0
+
+
+def test_union_tile_layout_property_random_structures():
+    """hypothesis: for random ragged sparsity patterns (empty rows, rows longer than a slice is wide, duplicate-free columns in
+    arbitrary summation order, rows < columns), every layout variant replays to bit-identical row sums"""
+    import numpy as np
+    from hypothesis import given, settings, strategies as st_
+
+    m = _mft()
+    L = m._lib
+    lib = L.load()
+
+    @settings(max_examples=40, deadline=None)
+    @given(st_.integers(1, 400), st_.integers(0, 60), st_.integers(0, 2 ** 31 - 1), st_.sampled_from([1, 2, 4]),
+           st_.sampled_from([0, 1, 3, 7]), st_.floats(0.0, 1.0))
+    def run(n, kmax, seed, R, layout, frac_rows):
+        rng = np.random.default_rng(seed)
+        n_rows = max(0, min(n, int(round(frac_rows * n))))
+        lens = rng.integers(0, min(kmax, n) + 1, size=n_rows)
+        rowptr = np.zeros(n_rows + 1, dtype=np.int64)
+        rowptr[1:] = np.cumsum(lens)
+        cols = np.concatenate([rng.choice(n, size=int(k), replace=False) for k in lens]) if n_rows and lens.sum() else np.zeros(0)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        if len(cols) == 0:
+            cols = np.zeros(1, dtype=np.int32)
+        stats = (C.c_double * 6)()
+        rc = lib.mft_debug_tile_selftest_csr(n, n_rows, L.ptr(rowptr), L.ptr(cols), R, layout, seed % 1000, stats)
+        assert rc == 0, (n, n_rows, kmax, R, layout, lib.mft_last_error())
+
+    run()
