@@ -113,7 +113,8 @@ typedef struct mft_ctx mft_ctx;
 #define MFT_SSPRK33 0
 
 const char *mft_last_error(void);
-int mft_version(void);
+int mft_version(void);  /* 100 * major + 10 * minor: 120 = 1.2 (1.1: setup pipeline, limiter, IGR, non-finite check; 1.2: stage-time
+                           Dirichlet tables, tuned tile layout, CSR self test) */
 int mft_device_count(void);
 
 /* ---- lifetime -------------------------------------------------------------------------------------
