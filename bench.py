@@ -314,7 +314,9 @@ def run_ours(args):
                           "summation": "fma single-sweep" if args.fma else "reference order (bit-exact sums)",
                           "partition": "single GPU" if not multi else f"Hilbert-curve ranges over {world} ranks, halo exchange (u, g) + global norms per stage via {'NVLink peer-memory puts (CUDA IPC), graph-replayed' if args.exchange == 'p2p' else 'NCCL send/recv + all-gather'}",
                           "l2": "inputs larger than L2 (operators 2 x %.0f MB per GPU streamed every stage)" % (n_own * 20 * k / 1e6),
-                          "setup_s": round(t_setup, 1), "setup": args.setup},
+                          "setup_s": round(t_setup, 1), "setup": args.setup,
+                          "layout": {"tile": int(args.tile), "tile_rows": int(args.tile_rows), "refine_order": int(args.refine_order),
+                                     "exchange": args.exchange if multi else None}},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                # the reference's own (printed, never recorded) metric: PerformanceCallback's performance index
                # PID = runtime * nranks / (ndofsglobal * ncalls_rhs), src/callbacks_step/performance.jl:229-235 (one DOF = one point)
