@@ -506,7 +506,7 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
                             bank[a] = choose(a);
                             ++fill[bank[a]];
                         }
-                    if (tune_copy1) {
+                    if (tune_copy1 && two_copies) {   // (alone, the octet constraint would undo the colouring: 1.68 -> 1.95 read conflicts)
                         // phase 1 stores entry q of the union list from thread q: the 8 lanes of an STS.128 phase hold an aligned
                         // octet of the list.  Keep the colouring where it already gives the octet 8 different bank groups and move
                         // the duplicates to the free groups: conflict-free stores, slot = octet * 8 + group (compact).
