@@ -257,11 +257,12 @@ struct BankMatcher {
     int opt[8][2];
     int owner[8];
     int kk = 0;
+    unsigned blocked = 0;   // bank groups that are taken already (the dummy record read by the padding lanes of the phase)
     bool augment(int i, unsigned &seen)
     {
         for (int o = 0; o < 2; ++o) {
             const int b = opt[i][o];
-            if (seen & (1u << b)) continue;
+            if ((seen | blocked) & (1u << b)) continue;
             seen |= 1u << b;
             if (owner[b] < 0 || augment(owner[b], seen)) {
                 owner[b] = i;
@@ -308,7 +309,7 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
         std::vector<unsigned short> adj;         // nu x nu co-request counts
         std::vector<int> slot, slot1, order, bank, deg, grp, nb_ptr, nb_idx, nb_w;
         std::vector<int> rq_ptr, rq_node, nr_ptr, nr_idx, bank1;  // tune_copy1: the tile's requests and node -> requests
-        std::vector<char> rq_ok;
+        std::vector<char> rq_ok, rq_pad;
     };
     // union of the tile's stencils (sorted) + the lane step lists of its slices (R-way merge by summation key);
     // returns the number of stored entries of the tile's rows
@@ -559,21 +560,28 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
                         // the group that leaves the fewest of its requests unmatched; groups stay balanced (cap per group).
                         std::vector<int> &rq_ptr = S.rq_ptr, &rq_node = S.rq_node, &nr_ptr = S.nr_ptr, &nr_idx = S.nr_idx, &bank1 = S.bank1;
                         std::vector<char> &rq_ok = S.rq_ok;
+                        // In this mode the dummy record (read by the padding lanes of a step) sits in slot roundup8(nu) of both copies,
+                        // i.e. in bank group 0: a phase with padding lanes has that group taken.
+                        std::vector<char> &rq_pad = S.rq_pad;
                         rq_ptr.assign(1, 0);
                         rq_node.clear();
+                        rq_pad.clear();
                         for (int si = 0; si < ns_tile; ++si) {
                             size_t W = 0;
                             for (int l = 0; l < kSlice; ++l) W = std::max(W, lanes[(size_t)si * kSlice + l].size());
                             for (size_t cpos = 0; cpos < W; ++cpos)
                                 for (int ph = 0; ph < kSlice / NB; ++ph) {
                                     grp.clear();
+                                    bool pad = false;
                                     for (int l = ph * NB; l < (ph + 1) * NB; ++l) {
                                         const std::vector<Step> &U = lanes[(size_t)si * kSlice + l];
-                                        if (cpos < U.size() && std::find(grp.begin(), grp.end(), U[cpos].node) == grp.end()) grp.push_back(U[cpos].node);
+                                        if (cpos >= U.size()) pad = true;
+                                        else if (std::find(grp.begin(), grp.end(), U[cpos].node) == grp.end()) grp.push_back(U[cpos].node);
                                     }
-                                    if (grp.size() < 2) continue;
+                                    if (grp.size() + (pad ? 1 : 0) < 2) continue;
                                     rq_node.insert(rq_node.end(), grp.begin(), grp.end());
                                     rq_ptr.push_back((int)rq_node.size());
+                                    rq_pad.push_back(pad ? 1 : 0);
                                 }
                         }
                         const int nreq = (int)rq_ptr.size() - 1;
@@ -602,6 +610,7 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
                             BankMatcher M;
                             const int e0 = rq_ptr[r];
                             M.kk = rq_ptr[r + 1] - e0;
+                            M.blocked = rq_pad[r] ? 1u : 0u;
                             for (int i = 0; i < M.kk; ++i) {
                                 M.opt[i][0] = slot[rq_node[e0 + i]] % NB;
                                 M.opt[i][1] = bank1[rq_node[e0 + i]];
@@ -644,10 +653,8 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
                                     for (int e = nr_ptr[best2]; e < nr_ptr[best2 + 1]; ++e) rq_ok[nr_idx[e]] = matched(nr_idx[e]) ? 1 : 0;
                                 }
                             }
-                        for (int q = 0; q < nu; ++q) {
-                            slot1[q] = (q / NB) * NB + bank1[q];
-                            nslots = std::max(nslots, slot1[q] + 1);
-                        }
+                        for (int q = 0; q < nu; ++q) slot1[q] = (q / NB) * NB + bank1[q];
+                        nslots = (nu + NB - 1) / NB * NB;   // dummy slot: bank group 0 in both copies
                     }
                 }
                 if (nslots + 1 > 4095) {
@@ -683,10 +690,13 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
                                     if ((size_t)cpos < U.size() && std::find(grp.begin(), grp.end(), U[cpos].node) == grp.end()) grp.push_back(U[cpos].node);
                                 }
                                 const int kk = (int)grp.size();
-                                if (kk < 2) continue;
+                                bool pad = false;   // tuned layout: padding lanes of this phase read the dummy record in bank group 0
+                                if (tune_copy1 && nu > NB)
+                                    for (int l = ph * NB; l < (ph + 1) * NB; ++l) pad |= (size_t)cpos >= lanes[(size_t)si * kSlice + l].size();
+                                if (kk + (pad ? 1 : 0) < 2) continue;
                                 int best_bits = 0, best_max = 99;
                                 for (int bits = 0; bits < (1 << kk) && best_max > 1; ++bits) {
-                                    int cnt[NB] = {0}, mx = 0;
+                                    int cnt[NB] = {pad ? 1 : 0}, mx = 0;
                                     for (int q = 0; q < kk; ++q) mx = std::max(mx, ++cnt[((bits >> q) & 1 ? slot1[grp[q]] : slot[grp[q]]) % NB]);
                                     if (mx < best_max) {
                                         best_max = mx;
