@@ -788,9 +788,20 @@ extern "C" int mft_finalize(mft_ctx *c)
             const int64_t tb = (c->tile & 2) ? (int64_t)kSlice * kTileWarps * c->tile_rows_b : (int64_t)1 << 40;
             blk = std::min(ta, tb);   // tile sizes are 128 * {1, 2, 4}: the smaller one divides the larger
         }
+        std::vector<int64_t> pos_before;   // tiles: position of a point in the order before the refinement (= along the curve)
+        if (tiles_on) {
+            pos_before.resize(n);
+            for (int64_t d = 0; d < n; ++d) pos_before[c->perm[d]] = d;
+        }
         for (int64_t b0 = 0; b0 < nl; b0 += blk) {
             const int64_t b1 = std::min(nl, b0 + blk);
             std::stable_sort(c->perm.begin() + b0, c->perm.begin() + b1, [&](int32_t x, int32_t y) { return len(x) > len(y); });
+            // the length of a slice's walk depends on WHICH rows it holds, not on their order: inside every slice go back to the
+            // order along the curve, so that the rows of an LDS.128 phase stay neighbours (replay: conflict degree 1.06 -> 1.05)
+            if (tiles_on)
+                for (int64_t s0 = b0; s0 < b1; s0 += kSlice)
+                    std::sort(c->perm.begin() + s0, c->perm.begin() + std::min(b1, s0 + kSlice),
+                              [&](int32_t x, int32_t y) { return pos_before[x] < pos_before[y]; });
         }
         for (int64_t d = 0; d < n; ++d) c->iperm[c->perm[d]] = (int32_t)d;
     }
