@@ -479,7 +479,7 @@ def main():
     ap.add_argument("--stage-weights", type=int, default=5, help="bit0: pass A slices staged in smem, bit1: pass B, bit2: one weight buffer refilled between the x and y sweeps")
     ap.add_argument("--graph", type=int, default=1, help="0 eager, 1 CUDA-graph replay on one GPU, 2 also multi-rank")
     ap.add_argument("--single-sweep", type=int, default=0, help="k=20 single-sweep exact pass A (register-parked y-products)")
-    ap.add_argument("--tile", type=int, default=15, help="union-tile kernels (bit0: pass A, bit1: pass B, bit2: bank-coloured slots, bit3: two record copies, bit4 (31): tuned second copy)")
+    ap.add_argument("--tile", type=int, default=31, help="union-tile kernels (bit0: pass A, bit1: pass B, bit2: bank-coloured slots, bit3: two record copies, bit4 (31): tuned second copy)")
     ap.add_argument("--pf-dist", type=int, default=None, help="slices ahead for the L2 prefetch of operator data (0: off; default: 16 per SM)")
     ap.add_argument("--tile-rows", type=int, default=11, help="rows per thread of the tile kernels: units digit pass A, tens digit pass B")
     ap.add_argument("--pair-rows", type=int, default=1, help="row-pair (union stencil) operator layout (bit0: pass B, bit1: pass A)")

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmft_b200.so")
+# MFT_LIB_PATH: a prebuilt variant of the same library (kernel-tuning experiments: other launch bounds / tile sizes)
+LIB_PATH = os.environ.get("MFT_LIB_PATH") or os.path.join(HERE, "libmft_b200.so")
 
 # constants of include/mft_b200.h
 EQ_EULER2D, EQ_ADVECTION2D = 0, 1

@@ -85,8 +85,8 @@ class RBFFDEngineCUDA:
     cuda_graph: int = 1                # 1: graph replay of SSPRK steps on one GPU; 2: also multi-rank; 0: eager
     exchange: str = "p2p"              # multi-GPU halo exchange: "p2p" (CUDA-IPC peer memory over NVLink) or "nccl"
     pair_rows: int = 1                 # row-pair (union stencil) layout: bit0 transposed operator (pass B), bit1 forward (pass A)
-    tile: int = 15                     # union-tile kernels: bit0 pass A, bit1 pass B, bit2 bank-coloured slots, bit3 two record copies,
-                                       # bit4 (31): second copy's bank groups tuned by local search (layout only, opt-in)
+    tile: int = 31                     # union-tile kernels: bit0 pass A, bit1 pass B, bit2 bank-coloured slots, bit3 two record copies,
+                                       # bit4 (31, default since r2: -13 % shared wavefronts measured): second copy tuned by local search
     tile_rows: int = 11                # rows per thread of the union-tile kernels: units digit pass A, tens digit pass B (1, 2, 4)
     prefetch_distance: int | None = None  # slices ahead for the L2 prefetch of operator data (None: library default, 0: off)
     single_sweep_exact: bool = False   # k=20: exact-order pass A in one sweep (y-products parked in registers)

@@ -194,8 +194,8 @@ struct mft_ctx {
     std::vector<int> stage_lim_variables;
     int tile_rows_a = 1, tile_rows_b = 1;  // MFT_OPT_TILE_ROWS: rows per thread of the union-tile kernels (1, 2 or 4)
     int stage_force = 0;
-    int tile = 15;  // MFT_OPT_TILE: bit 0 pass A, bit 1 pass B (Euler 2-D only), bit 2 bank-coloured slots, bit 3 two copies,
-                    // bit 4 tuned second copy (opt-in)
+    int tile = 31;  // MFT_OPT_TILE: bit 0 pass A, bit 1 pass B (Euler 2-D only), bit 2 bank-coloured slots, bit 3 two copies,
+                    // bit 4 tuned second copy (default: profiles/README.md r2)
     int pair_rows = 1;
     int two_phase = 1;
     // bcs, sources

@@ -26,10 +26,10 @@ constexpr int kTileWarps = MFT_TILE_WARPS;
 // minimum resident blocks per SM the compiler must allow for the R = 1 tile kernels (register cap = 65536 / (128 x blocks)).
 // Experiment knobs: MFT_NVCC_EXTRA="-DMFT_TILE_OCC_A=6 -DMFT_TILE_OCC_B=5" python meshfreetrixi.jl_b200/build.py --force
 #ifndef MFT_TILE_OCC_A
-#define MFT_TILE_OCC_A 4
+#define MFT_TILE_OCC_A 6
 #endif
 #ifndef MFT_TILE_OCC_B
-#define MFT_TILE_OCC_B 4
+#define MFT_TILE_OCC_B 5
 #endif
 
 __device__ __forceinline__ double2 lds2(const unsigned char *arr, uint32_t off)

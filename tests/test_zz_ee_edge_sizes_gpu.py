@@ -57,7 +57,7 @@ def _case(m, nx, ny, nv, tile, source, empty_group=False, refine_order=False, ti
     semi.close()
 
 
-@pytest.mark.parametrize("tile", [15, 0])
+@pytest.mark.parametrize("tile", [31, 15, 0])
 @pytest.mark.parametrize("nx,ny", [(4, 3), (5, 5), (8, 8), (10, 10), (11, 11), (15, 15), (16, 15)])
 def test_odd_cloud_sizes(nx, ny, tile):
     """26, 45, 96, 140, 165, 285, 302 points with the default 20-wide stencil"""
@@ -66,7 +66,7 @@ def test_odd_cloud_sizes(nx, ny, tile):
     _case(m, nx, ny, 20, tile, "upwind")
 
 
-@pytest.mark.parametrize("tile", [15, 0])
+@pytest.mark.parametrize("tile", [31, 15, 0])
 @pytest.mark.parametrize("nv", [13, 15, 30, 42])
 def test_stencil_widths(nv, tile):
     import mft_b200 as m
