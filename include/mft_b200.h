@@ -96,6 +96,11 @@ typedef struct mft_ctx mft_ctx;
 #define MFT_OPT_TILE_ROWS 11       /* rows per thread of the union-tile kernels, decimal digits: units = pass A, tens = pass B, each 1, 2
                                       or 4 (e.g. 42 = pass B 4 rows, pass A 2 rows).  A thread walks the union of its rows' stencils
                                       (16-bit word = slot | row mask << 12, weights compact per row).  Same sums bit for bit.   */
+#define MFT_OPT_FUSED_STEP 12      /* 1 (default): mft_ssprk_step runs the fused device-resident step for Euler 2-D + one upwind / residual
+                                    * viscosity source over union tiles: ONE kernel per stage does BC pass 2, the SSPRK33 stage update, BC
+                                    * pass 1, ode_mean / ode_maximum (one-pass statistic) and -- on several GPUs -- the u halo puts; pass A
+                                    * puts its g halo rows itself and tiles that touch the halo wait for it while the interior runs.
+                                    * 0: separate stage / boundary / norm / put / wait kernels (the round-1 sequence). */
 #define MFT_OPT_PREFETCH_DISTANCE 6/* slices ahead for the L2 prefetch of operator data (weight blocks; union tiles: step words, weights, union
                                       list of the tile that many slices ahead).  Default 8 per SM; 0: off.               */
 
@@ -109,6 +114,8 @@ typedef struct mft_ctx mft_ctx;
 #define MFT_FIELD_NORMS 6      /* V doubles: n_inf_norms of update_residual_visc! */
 #define MFT_FIELD_SIGMA 7      /* N doubles: cache.sigma of SourceIGR (IGR.jl:169-191) */
 #define MFT_FIELD_IGR_STATUS 8 /* 3 doubles: CG iterations of the last solve, final |r|, initial |r| */
+#define MFT_FIELD_NORM_MISSES 9/* 1 double: rows (summed over all rhs! so far) whose |u - mean| exceeded the norms of the fused step's one-pass
+                                * statistic (csrc/mft_fused_kernels.cuh); 0 unless a rounding tie decided ode_maximum's lexicographic order */
 
 #define MFT_SSPRK33 0
 

@@ -25,8 +25,9 @@ OPT_STAGE_WEIGHTS, OPT_PREFETCH_DISTANCE, OPT_REFINE_ORDER, OPT_SINGLE_SWEEP_EXA
 OPT_PAIR_ROWS = 9
 OPT_TILE = 10
 OPT_TILE_ROWS = 11
+OPT_FUSED_STEP = 12
 VAR_DENSITY, VAR_PRESSURE = 0, 1
-FIELD_EPS, FIELD_EPS_UW, FIELD_EPS_RV, FIELD_EPS_C, FIELD_RESIDUAL, FIELD_APPROX_DU, FIELD_NORMS, FIELD_SIGMA, FIELD_IGR_STATUS = range(9)
+FIELD_EPS, FIELD_EPS_UW, FIELD_EPS_RV, FIELD_EPS_C, FIELD_RESIDUAL, FIELD_APPROX_DU, FIELD_NORMS, FIELD_SIGMA, FIELD_IGR_STATUS, FIELD_NORM_MISSES = range(10)
 SSPRK33 = 0
 K_PASS_A, K_PASS_B, K_REDUCE, K_STAGE, K_BC, K_OTHER = range(6)
 

@@ -2,6 +2,7 @@
 // There is no CPU fallback anywhere in this file: every compute entry point needs a CUDA device.
 #include "../../include/mft_b200.h"
 #include "mft_kernels.cuh"
+#include "mft_fused_kernels.cuh"
 #include "mft_tile_kernels.cuh"
 #include "mft_limiter_kernels.cuh"
 #include "mft_igr_kernels.cuh"
@@ -117,9 +118,13 @@ struct DevTileR {
     DevBuf<unsigned short> uslot;
     int R = 0, nslices = 0, ntiles = 0, maxW = 0, maxL = 0, sstride = 0, ncopy = 1;
     int64_t nnz = 0, nunion = 0, nsteps = 0;
+    // several GPUs, fused step: block -> tile, interior tiles first; the last ntiles - n_free blocks are band tiles
+    DevBuf<int> order;
+    int n_free = 0;
     bool ready() const { return blob.p != nullptr; }
     void release()
     {
+        order.release();
         blob.release();
         boff.release();
         wl.release();
@@ -192,6 +197,18 @@ struct mft_ctx {
     DevBuf<unsigned char> zs_flag;
     std::vector<double> stage_lim_thresholds;
     std::vector<int> stage_lim_variables;
+    // fused step (mft_fused_kernels.cuh): per-row side table (boundary entry, halo routes), miss counter of the one-pass norms
+    int fused_step = 1;
+    bool fused_active = false;             // the launches being issued belong to the fused step
+    DevBuf<int> row_aux;
+    DevBuf<RowAux> row_aux_tab;
+    DevBuf<int> route_peer;
+    DevBuf<long long> route_dst;
+    DevBuf<unsigned long long> norm_miss;
+    DevBuf<P2PPeers> peers_dev_buf;        // device copy of peers_dev for kernels that take a pointer
+    std::vector<int> bc_idx_host;          // merged boundary table: device rows
+    std::vector<int> send_rows_host, send_peer_host;
+    std::vector<long long> send_dst_host;
     int tile_rows_a = 1, tile_rows_b = 1;  // MFT_OPT_TILE_ROWS: rows per thread of the union-tile kernels (1, 2 or 4)
     int stage_force = 0;
     int tile = 31;  // MFT_OPT_TILE: bit 0 pass A, bit 1 pass B (Euler 2-D only), bit 2 bank-coloured slots, bit 3 two copies,
@@ -364,12 +381,14 @@ extern "C" int mft_ctx_create(mft_ctx **out, int device, int64_t n_local, int64_
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->red_blocks = prop.multiProcessorCount * 4;
-    CHECK(c->partial.alloc((int64_t)c->red_blocks * nvars));
-    CHECK(c->stats.alloc(3 * nvars + 4));  // sum | mean | norms | SSPRK43 error sum
-    CHECK(c->ticket.alloc(4));
-    CU(cudaMemset(c->ticket.p, 0, 4 * sizeof(unsigned int)));
+    CHECK(c->partial.alloc((int64_t)c->red_blocks * kRecDoubles));  // per-block partials: V sums, or one norm record (fused step)
+    CHECK(c->stats.alloc(24));  // sum | mean | norms | SSPRK43 error sum | [16..19] raw norms of the fused step
+    CHECK(c->ticket.alloc(8));
+    CU(cudaMemset(c->ticket.p, 0, 8 * sizeof(unsigned int)));
+    CHECK(c->norm_miss.alloc(1));
+    CU(cudaMemset(c->norm_miss.p, 0, sizeof(unsigned long long)));
     c->pf_dist = prop.multiProcessorCount * 8;
-    CU(cudaMemset(c->stats.p, 0, sizeof(double) * (3 * nvars + 4)));
+    CU(cudaMemset(c->stats.p, 0, sizeof(double) * 24));
     *out = c;
     return MFT_OK;
 }
@@ -418,6 +437,12 @@ extern "C" int mft_ctx_destroy(mft_ctx *c)
     c->p2p_local.release();
     c->send_peer.release();
     c->send_dst.release();
+    c->row_aux.release();
+    c->row_aux_tab.release();
+    c->route_peer.release();
+    c->route_dst.release();
+    c->norm_miss.release();
+    c->peers_dev_buf.release();
     c->d_perm.release();
     c->send_rows.release();
     c->ticket.release();
@@ -479,6 +504,12 @@ extern "C" int mft_set_option(mft_ctx *c, int option, double value)
     case MFT_OPT_SINGLE_SWEEP_EXACT: c->kfix_ok = value != 0; break;
     case MFT_OPT_PAIR_ROWS: c->pair_rows = (int)value; break;
     case MFT_OPT_TILE: c->tile = (int)value; break;
+    case MFT_OPT_FUSED_STEP:
+        c->fused_step = value != 0;
+        for (auto &g : c->graphs)   // captured steps bake the launch sequence in: start over
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        c->graphs.clear();
+        break;
     case MFT_OPT_TILE_ROWS: {
         const int a = (int)value % 10, b = ((int)value / 10) % 10;
         if ((a != 1 && a != 2 && a != 4) || (b != 1 && b != 2 && b != 4)) return fail(MFT_EINVAL, "MFT_OPT_TILE_ROWS: digits must be 1, 2 or 4");
@@ -732,6 +763,51 @@ extern "C" int mft_add_source(mft_ctx *c, int kind, const double *params, int np
 
 #include "mft_layout_host.inl"
 
+// per-row side table of the fused stage kernel: boundary entry (merged table) and halo routes of a row
+static int build_row_aux(mft_ctx *c)
+{
+    const int64_t nl = c->n_local;
+    std::vector<int> aux((size_t)nl, -1);
+    std::vector<RowAux> tab;
+    auto entry = [&](int row) -> RowAux & {
+        if (aux[(size_t)row] < 0) {
+            aux[(size_t)row] = (int)tab.size();
+            tab.push_back(RowAux{-1, 0, 0});
+        }
+        return tab[(size_t)aux[(size_t)row]];
+    };
+    if (c->bc_merged)
+        for (size_t j = 0; j < c->bc_idx_host.size(); ++j) {
+            const int row = c->bc_idx_host[j];
+            if (row >= 0 && row < nl) entry(row).bc = (int)j;
+        }
+    // routes sorted by row: a row that several peers hold in their halo owns a contiguous slice
+    const size_t ns = c->send_rows_host.size();
+    std::vector<int> ord(ns), rpeer(ns);
+    std::vector<long long> rdst(ns);
+    std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return c->send_rows_host[(size_t)a] < c->send_rows_host[(size_t)b]; });
+    for (size_t q = 0; q < ns; ++q) {
+        const int i = ord[q];
+        const int row = c->send_rows_host[(size_t)i];
+        rpeer[q] = c->send_peer_host[(size_t)i];
+        rdst[q] = c->send_dst_host[(size_t)i];
+        RowAux &e = entry(row);
+        if (e.send == e.sbeg) e.sbeg = (int)q;
+        e.send = (int)q + 1;
+    }
+    if (tab.empty()) tab.push_back(RowAux{-1, 0, 0});
+    if (rpeer.empty()) {
+        rpeer.push_back(0);
+        rdst.push_back(0);
+    }
+    CHECK(c->row_aux.upload(aux));
+    CHECK(c->row_aux_tab.upload(tab));
+    CHECK(c->route_peer.upload(rpeer));
+    CHECK(c->route_dst.upload(rdst));
+    return MFT_OK;
+}
+
 static bool has_visc(const mft_ctx *c)
 {
     for (auto *s : c->srcs)
@@ -922,6 +998,7 @@ extern "C" int mft_finalize(mft_ctx *c)
         c->bc_merged = std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end();
         if (c->bc_merged) {
             c->bc_total = (int64_t)idx.size();
+            c->bc_idx_host = idx;
             CHECK(c->bc_kind.upload(kind));
             CHECK(c->bc_idx.upload(idx));
             CHECK(c->bc_normals.upload(nrm));
@@ -942,6 +1019,7 @@ extern "C" int mft_finalize(mft_ctx *c)
         CU(cudaHostAlloc((void **)&c->touched_host, sizeof(double) * std::max<size_t>(1, rows.size()) * c->V, cudaHostAllocDefault));
     }
     CHECK(c->uprev.alloc(n * c->V));
+    CHECK(build_row_aux(c));
     // free host staging
     c->host_ops[0] = HostCsc();
     c->host_ops[1] = HostCsc();
@@ -1188,7 +1266,16 @@ static int launch_pass_a_t(mft_ctx *c, const PassAArgs &a, bool do_flux, int vis
 static TileROp tiler_view(const DevTileR &e, bool stage_w, int pf_slices = 0)
 {
     const int bytes = std::max(e.maxW, 1) * kSlice * 2 + (stage_w ? e.R * std::max(e.maxL, 1) * kSlice * 8 : 0);
-    return TileROp{e.blob.p, e.boff.p, e.wl.p, e.uoff.p, e.ulist.p, e.uslot.p, e.sstride, e.ncopy, ((bytes + 127) / 128) * 128, pf_slices / kTileWarps};
+    return TileROp{e.blob.p, e.boff.p, e.wl.p, e.uoff.p, e.ulist.p, e.uslot.p, e.sstride, e.ncopy, ((bytes + 127) / 128) * 128, pf_slices / kTileWarps,
+                   nullptr, 0};
+}
+// fused step on several GPUs: interior tiles first, band tiles wait for the halo inside the kernel
+static void tiler_band_order(const mft_ctx *c, const DevTileR &e, TileROp &t)
+{
+    if (c->fused_active && c->p2p && c->nranks > 1 && e.order.p) {
+        t.order = e.order.p;
+        t.n_free = e.n_free;
+    }
 }
 
 // staged weights keep at least `min_blocks` blocks per SM resident; otherwise stream them
@@ -1209,7 +1296,8 @@ static int launch_pass_a_tiler(mft_ctx *c, const PassAArgs &a0, bool do_flux, in
     PassAArgs a = a0;
     const DevTileR &e = c->fwd_tiler;
     const bool stage = tiler_stage(c, e, 3, c->stage_w, R == 1 ? 4 : R == 2 ? 3 : 2);
-    const TileROp t = tiler_view(e, stage, c->pf_dist);
+    TileROp t = tiler_view(e, stage, c->pf_dist);
+    tiler_band_order(c, e, t);
     a.n_slices = e.nslices;
     const int grid = e.ntiles;
     const int smem = 3 * e.ncopy * t.sstride * 16 + kTileWarps * t.buf_bytes;
@@ -1243,8 +1331,10 @@ static int launch_pass_b_tiler(mft_ctx *c)
 {
     const DevTileR &e = c->tra_tiler;
     const bool stage = tiler_stage(c, e, 4, c->stage_w_b, R == 1 ? 4 : R == 2 ? 3 : 2);
-    const TileROp t = tiler_view(e, stage, c->pf_dist);
-    PassBTileArgs a{c->g.p, c->du.p, c->n_local, e.nslices};
+    TileROp t = tiler_view(e, stage, c->pf_dist);
+    tiler_band_order(c, e, t);
+    PassBTileArgs a{c->g.p, c->du.p, c->n_local, e.nslices, t.order ? c->peers_dev_buf.p : nullptr,
+                    reinterpret_cast<P2PLocal *>(c->p2p_local.p)};
     const int smem = 4 * e.ncopy * t.sstride * 16 + kTileWarps * t.buf_bytes;
     if (smem > 200 * 1024) return fail(MFT_ENOTSUP, "union tile: %d bytes of shared memory per block", smem);
 #define PBR(EX, ST)                                                                                  \
@@ -1298,6 +1388,27 @@ static int launch_pass_a(mft_ctx *c, bool do_flux, int visc, const Source *s, bo
     a.dx_avg = s ? s->dx_avg : 0.0;
     a.success_iter_zero = c->success_iter == 0;
     a.accumulate = accumulate ? 1 : 0;
+    if (c->fused_active && use_tiler) {
+        // fused step: the stage kernel left the norms (one GPU) or the ranks' records (several GPUs: block 0 merges them)
+        if (visc == VISC_RESIDUAL) {
+            a.norms = c->stats.p + 2 * c->V;
+            a.norm_parts = 0;
+            a.norms_out = nullptr;
+            a.stats = c->stats.p;
+            a.norm_miss = c->norm_miss.p;
+        }
+        if (c->p2p && c->nranks > 1) {
+            a.P = c->peers_dev_buf.p;
+            a.L = reinterpret_cast<P2PLocal *>(c->p2p_local.p);
+            a.aux = c->row_aux.p;
+            a.rows = c->row_aux_tab.p;
+            a.route_peer = c->route_peer.p;
+            a.route_dst = c->route_dst.p;
+            const double ng = (double)c->n_global;
+            a.divisor = c->mean_div_vn ? (double)c->V * ng : ng;
+            a.norm_merge = visc == VISC_RESIDUAL ? 1 : 0;
+        }
+    }
     if (c->diagnostics && visc != VISC_NONE) {
         a.eps = c->eps.p;
         a.eps_uw = c->eps_uw.p;
@@ -1712,6 +1823,12 @@ extern "C" int mft_get_field(mft_ctx *c, int field, double *out)
                 return MFT_OK;
             }
         return fail(MFT_EINVAL, "mft_get_field: no IGR source");
+    }
+    case MFT_FIELD_NORM_MISSES: {
+        unsigned long long m = 0;
+        CU(cudaMemcpy(&m, c->norm_miss.p, sizeof m, cudaMemcpyDeviceToHost));
+        out[0] = (double)m;
+        return MFT_OK;
     }
     case MFT_FIELD_NORMS:
         CU(cudaMemcpy(out, c->stats.p + 2 * c->V, sizeof(double) * c->V, cudaMemcpyDeviceToHost));

@@ -1,0 +1,516 @@
+// mft_fused_kernels.cuh -- the fused SSPRK33 stage kernel of the device-resident step (round 2).
+//
+// One launch replaces, per Runge-Kutta stage, what used to be five (six on several GPUs):
+//     BC pass 2 of the previous rhs!  (calc_boundary_flux!, rbfsolver.jl:288-318: du and u at boundary points)
+//     the SSPRK33 stage update         (OrdinaryDiffEq stage formulas)
+//     BC pass 1 of the next rhs!       (strong BCs written into u)
+//     ode_mean(u)                      (src/auxiliary/mpi.jl:40-52)
+//     ode_maximum(|u - mean|)          (src/auxiliary/mpi.jl:71-81; hyperviscosity.jl:305-311)
+//     the halo put of u                (perform_halo_update!, src/auxiliary/mpi.jl:217-265)
+// so u, uprev and du are read once and u is written once per stage, and on several GPUs the norms need ONE exchange of a
+// small record per stage instead of two dependent ones.
+//
+// The norms in one pass.  ode_maximum compares SVectors with isless, i.e. LEXICOGRAPHICALLY: the result is the deviation
+// vector |u_p - mean| of the point p that maximises (|rho - m0|, |m1 - m_1|, |m2 - m_2|, |E - m_3|) in lexicographic order.
+// The mean is only known after the pass -- but x -> fl|x - m| is monotone on either side of m, so whatever m turns out to
+// be, the maximiser of the first key has rho = max rho or rho = min rho; among the points that tie there, the maximiser of
+// the second key has the largest or the smallest m1; and so on.  Hence the 16 "leaves"
+//     leaf(s0,s1,s2,s3) = lexicographic maximum of (s0 rho, s1 m1, s2 m2, s3 E),   s in {+,-}^4
+// are a sufficient statistic: the answer is the lexicographic maximum of the 16 leaf deviation vectors, evaluated once
+// the mean is known.  Leaves merge associatively and commutatively (they are maxima), so blocks and ranks combine them in
+// any order with a bit-identical result; only the sums keep a fixed order.  Exact value ties (a far field at rho = 1.0
+// exactly with different momenta: 8 % of the points of the vortex workload, 1808 of them pinned by Dirichlet data) are
+// what the nested leaves are for.  What they cannot see is a ROUNDING tie (two different values whose deviations round to
+// the same double, deciding the order on a later key); pass A checks every row against the norms it was given and counts
+// misses (MFT_FIELD_NORM_MISSES), and MFT_OPT_FUSED_STEP = 0 selects the two-pass kernels.
+#pragma once
+#include "mft_kernels.cuh"
+
+namespace mft {
+
+// ---- the record ----------------------------------------------------------------------------------------------------
+constexpr int kRecSum = 0;     // 4: sum of the states
+constexpr int kRecExt = 4;     // 2: max rho, min rho
+constexpr int kRecLeaf = 6;    // 2 sides x 8 leaves x (m1, m2, E); leaf index bit c set = component c+1 is minimised
+constexpr int kRecCmax = 54;   // per-component mode (MFT_OPT_MAX_LEXICOGRAPHIC = 0): max and min of every component
+constexpr int kRecCmin = 58;
+// kRecDoubles = 64 (mft_kernels.cuh): padded to 512 bytes
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ double pos_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
+
+// is a = (a1,a2,a3) lexicographically better than b under the leaf's sign bits (bit c set: smaller is better)?
+__device__ __forceinline__ bool leaf_better(double a1, double a2, double a3, double b1, double b2, double b3, int bits)
+{
+    const double a[3] = {a1, a2, a3}, b[3] = {b1, b2, b3};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const bool mn = (bits >> c) & 1;
+        if (mn ? a[c] < b[c] : a[c] > b[c]) return true;
+        if (mn ? a[c] > b[c] : a[c] < b[c]) return false;
+    }
+    return false;
+}
+
+template <bool MIN>
+__device__ __forceinline__ double warp_extreme(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double y = __shfl_xor_sync(kFull, x, o);
+        x = MIN ? fmin(x, y) : fmax(x, y);
+    }
+    return x;
+}
+
+// One chunk of 32 points (one per lane) against the warp's running record `wr` (shared memory), side 0 = max rho,
+// side 1 = min rho.  run_ext is the warp-uniform register copy of wr[kRecExt + SIDE].  Warp-uniform control flow.
+template <int SIDE>
+__device__ __forceinline__ void lex_side_update(double *wr, bool valid, double rho, double m1, double m2, double E, double &run_ext, int lane)
+{
+    const bool hot = valid && (SIDE == 0 ? !(rho < run_ext) : !(rho > run_ext));
+    if (__ballot_sync(kFull, hot) == 0) return;   // the common case: nobody reaches the running extreme
+    const double cm = SIDE == 0 ? warp_extreme<false>(hot ? rho : neg_inf()) : warp_extreme<true>(hot ? rho : pos_inf());
+    unsigned tied = __ballot_sync(kFull, hot && rho == cm);
+    if (tied == 0) return;   // only NaNs were "hot"
+    const bool reset = SIDE == 0 ? cm > run_ext : cm < run_ext;
+    if (!reset && !(cm == run_ext)) return;
+    double *leaf = wr + kRecLeaf + SIDE * 24;
+    if (!reset) {
+        // same extreme as before: a point only matters if its m1 reaches the running extremes of m1 over the tie set
+        const double m1max = leaf[0], m1min = leaf[3];   // leaf 0: maximise m1; leaf 1: minimise m1
+        tied = __ballot_sync(kFull, ((tied >> lane) & 1u) && (!(m1 < m1max) || !(m1 > m1min)));
+        if (tied == 0) return;
+    }
+    const bool in = (tied >> lane) & 1u;
+    const int first = __ffs(tied) - 1;
+    const double r1 = __shfl_sync(kFull, m1, first), r2 = __shfl_sync(kFull, m2, first), r3 = __shfl_sync(kFull, E, first);
+    double l1 = r1, l2 = r2, l3 = r3;   // leaf `lane` of the tie set (lanes 0..7)
+    if (__ballot_sync(kFull, in && (m1 != r1 || m2 != r2 || E != r3)) != 0) {
+        // several different states tie on rho: nested extremes per sign pattern
+#pragma unroll 1
+        for (int lf = 0; lf < 8; ++lf) {
+            unsigned set = tied;
+            double c[3];
+            const double val[3] = {m1, m2, E};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const bool mn = (lf >> k) & 1;
+                const bool ins = (set >> lane) & 1u;
+                c[k] = mn ? warp_extreme<true>(ins ? val[k] : pos_inf()) : warp_extreme<false>(ins ? val[k] : neg_inf());
+                set = __ballot_sync(kFull, ins && val[k] == c[k]);
+            }
+            if (lane == lf) {
+                l1 = c[0];
+                l2 = c[1];
+                l3 = c[2];
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < 8) {
+        double *lf = leaf + lane * 3;
+        if (reset || leaf_better(l1, l2, l3, lf[0], lf[1], lf[2], lane)) {
+            lf[0] = l1;
+            lf[1] = l2;
+            lf[2] = l3;
+        }
+    }
+    if (lane == 0 && reset) wr[kRecExt + SIDE] = cm;
+    __syncwarp();
+    run_ext = cm;
+}
+
+// slot = side * 8 + leaf: merge candidate (ext, l1..l3) into the running best (bext, b1..b3)
+__device__ __forceinline__ void slot_merge(int slot, double ext, double l1, double l2, double l3, double &bext, double &b1, double &b2, double &b3)
+{
+    const int side = slot >> 3, lf = slot & 7;
+    const bool better_ext = side == 0 ? ext > bext : ext < bext;
+    if (better_ext || (ext == bext && leaf_better(l1, l2, l3, b1, b2, b3, lf))) {
+        bext = ext;
+        b1 = l1;
+        b2 = l2;
+        b3 = l3;
+    }
+}
+
+// ode_mean + ode_maximum(|u - mean|) from `nrec` records (one per rank, combined in rank order for the sums).
+// Executed by ONE thread.  Writes mean[4], norms[4] (zero -> eps) and raw[4] (before the zero replacement: what pass A
+// verifies rows against).  VOL: the records were written by other GPUs -- read them past L1.
+template <bool VOL>
+__device__ inline void norms_from_records(const double *recs, int stride, int nrec, double divisor, int lex, double *mean_out, double *norms_out, double *raw_out)
+{
+    auto ld = [](const double *p) -> double { return VOL ? __ldcv(p) : *p; };
+    double m[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        double t = ld(recs + kRecSum + v);
+        for (int r = 1; r < nrec; ++r) t += ld(recs + (size_t)r * stride + kRecSum + v);
+        m[v] = t / divisor;
+        if (mean_out) mean_out[v] = m[v];
+    }
+    double best[4] = {-1.0, -1.0, -1.0, -1.0};
+    if (lex) {
+        for (int r = 0; r < nrec; ++r) {
+            const double *R = recs + (size_t)r * stride;
+            for (int side = 0; side < 2; ++side) {
+                const double ext = ld(R + kRecExt + side);
+                if (!(ext > neg_inf() && ext < pos_inf())) continue;   // empty record (no owned rows) or non-finite
+                for (int lf = 0; lf < 8; ++lf) {
+                    const double *q = R + kRecLeaf + side * 24 + lf * 3;
+                    const double c[4] = {fabs(ext - m[0]), fabs(ld(q) - m[1]), fabs(ld(q + 1) - m[2]), fabs(ld(q + 2) - m[3])};
+                    if (lex_less<4>(best, c)) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) best[v] = c[v];
+                    }
+                }
+            }
+        }
+    } else {
+        for (int r = 0; r < nrec; ++r) {
+            const double *R = recs + (size_t)r * stride;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                best[v] = jl_max(best[v], fabs(ld(R + kRecCmax + v) - m[v]));
+                best[v] = jl_max(best[v], fabs(ld(R + kRecCmin + v) - m[v]));
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        if (raw_out) raw_out[v] = best[v];
+        norms_out[v] = best[v] == 0.0 ? kEps : best[v];
+    }
+}
+
+// ---- per-row side table ---------------------------------------------------------------------------------------------
+// aux[row] = -1 for a plain row, else an index into RowAux: the row's entry in the merged boundary table and its slice
+// of the halo routing table (a row can be in the halo of several peers)
+struct RowAux {
+    int bc;            // index into the merged BC table, or -1
+    int sbeg, send;    // [sbeg, send) into route_peer / route_dst
+};
+
+struct StageArgs {
+    int stage;         // 1, 2, 3
+    int apply_bc2;     // BC pass 2 of the previous rhs! has not been applied yet (stages fused behind pass B)
+    double dt;
+    double *u, *uprev, *du;
+    int64_t n;         // owned rows
+    const int *aux;    // nullable
+    const RowAux *rows;
+    // merged boundary table (k_boundary_merged)
+    const int *bc_kind;
+    const double *bc_normals, *bc_values;
+    // reductions
+    double *partial;   // gridDim.x records
+    unsigned int *ticket;
+    double divisor;
+    int lex;
+    double *stats;     // sum[4] | mean[4] | norms[4] | ... | raw norms at [kStatsRaw]
+    // peer-memory exchange (nranks > 1)
+    P2PPeers P;
+    P2PLocal *L;
+    const int *route_peer;
+    const long long *route_dst;
+};
+constexpr int kStatsRaw = 16;   // stats[16..19]: norms before the zero replacement
+
+template <bool NORMS, bool MULTI>
+__global__ void __launch_bounds__(256, 3) k_stage_fused(const StageArgs A)
+{
+    constexpr int V = 4;
+    __shared__ double wrec[8][kRecDoubles];
+    __shared__ double sh[8][V];
+    __shared__ bool is_last;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Vec<V> *u = reinterpret_cast<Vec<V> *>(A.u);
+    Vec<V> *uprev = reinterpret_cast<Vec<V> *>(A.uprev);
+    Vec<V> *du = reinterpret_cast<Vec<V> *>(A.du);
+    unsigned long long e_u = 0;
+    if constexpr (MULTI) {
+        e_u = A.L->epoch[0] + 1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            // credits for the two-kernel exchange protocol (k_p2p_put): everything stream-ordered before this kernel has
+            // consumed the halos of both fields' last epochs
+            for (int f = 0; f < 2; ++f) {
+                const unsigned long long ef = A.L->epoch[f];
+                for (int i = 0; i < A.P.nsrc; ++i) st_release_sys(&A.P.win[A.P.src[i]]->credit[f][A.P.rank], ef);
+            }
+        }
+    }
+    double s[V] = {0.0, 0.0, 0.0, 0.0};
+    double cmx[V], cmn[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        cmx[v] = neg_inf();
+        cmn[v] = pos_inf();
+    }
+    double run_max = neg_inf(), run_min = pos_inf();
+    if (NORMS && lane < 2) wrec[w][kRecExt + lane] = lane == 0 ? neg_inf() : pos_inf();
+    __syncwarp();
+    const double dt = A.dt, dt2 = 2.0 * A.dt;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nround = (A.n + 31) & ~(int64_t)31;   // whole warps stay in the loop (warp-wide reductions inside)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        const bool valid = i < A.n;
+        Vec<V> un;
+#pragma unroll
+        for (int v = 0; v < V; ++v) un.a[v] = 0.0;
+        if (valid) {
+            const int ax = A.aux ? __ldg(A.aux + i) : -1;
+            Vec<V> k = du[i];
+            Vec<V> uo = u[i];
+            int bcj = -1, kind = -1;
+            RowAux ra{-1, 0, 0};
+            if (ax >= 0) {
+                ra = A.rows[ax];
+                bcj = ra.bc;
+                if (bcj >= 0) kind = A.bc_kind[bcj];
+            }
+            double nx = 0.0, ny = 0.0;
+            if (kind == 1) {   // slip wall: unit normal as k_boundary_merged forms it
+                const double nx0 = A.bc_normals[2 * bcj], ny0 = A.bc_normals[2 * bcj + 1];
+                const double nrm = sqrt(nx0 * nx0 + ny0 * ny0);
+                nx = nx0 / nrm;
+                ny = ny0 / nrm;
+            }
+            if (A.apply_bc2 && kind >= 0) {
+                // BC pass 2 of the rhs! that produced k (rbfsolver.jl:424-427): u and du at the boundary point
+                if (kind == 0) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) k.a[v] = 0.0;   // u already holds the Dirichlet values of that rhs!
+                } else {
+                    const double vdotn = uo.a[1] * nx + uo.a[2] * ny;
+                    uo.a[1] = uo.a[1] - vdotn * nx;
+                    uo.a[2] = uo.a[2] - vdotn * ny;
+                    k.a[1] = 0.0;
+                    k.a[2] = 0.0;
+                }
+                st_vec(du + i, k);
+            }
+            if (A.stage == 1) {
+                st_vec(uprev + i, uo);
+#pragma unroll
+                for (int v = 0; v < V; ++v) un.a[v] = fma(dt, k.a[v], uo.a[v]);
+            } else {
+                const Vec<V> up = uprev[i];
+                if (A.stage == 2) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) un.a[v] = fma(dt, k.a[v], fma(3.0, up.a[v], uo.a[v])) / 4.0;
+                } else {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) un.a[v] = fma(dt2, k.a[v], fma(2.0, uo.a[v], up.a[v])) / 3.0;
+                }
+            }
+            if (kind == 0) {   // BC pass 1 of the next rhs!: Dirichlet values of the new stage time
+#pragma unroll
+                for (int v = 0; v < V; ++v) un.a[v] = A.bc_values[(int64_t)bcj * V + v];
+            } else if (kind == 1) {
+                const double vdotn = un.a[1] * nx + un.a[2] * ny;
+                un.a[1] = un.a[1] - vdotn * nx;
+                un.a[2] = un.a[2] - vdotn * ny;
+            }
+            st_vec(u + i, un);
+            if constexpr (MULTI) {
+                for (int q = ra.sbeg; q < ra.send; ++q)
+                    st_vec(reinterpret_cast<Vec<V> *>(A.P.field[0][A.route_peer[q]]) + A.route_dst[q], un);
+            }
+        }
+        if constexpr (NORMS) {
+            if (valid) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) s[v] += un.a[v];
+            }
+            if (A.lex) {
+                lex_side_update<0>(wrec[w], valid, un.a[0], un.a[1], un.a[2], un.a[3], run_max, lane);
+                lex_side_update<1>(wrec[w], valid, un.a[0], un.a[1], un.a[2], un.a[3], run_min, lane);
+            } else if (valid) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    cmx[v] = fmax(cmx[v], un.a[v]);
+                    cmn[v] = fmin(cmn[v], un.a[v]);
+                }
+            }
+        }
+    }
+    if constexpr (!NORMS && !MULTI) return;
+
+    // ---- block record -> partial[blockIdx.x] -----------------------------------------------------------------------
+    if constexpr (NORMS) {
+        // the sums: the reduction tree of k_sum_mean (same grid, same order => the same bits)
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            for (int o = 16; o > 0; o >>= 1) s[v] += __shfl_down_sync(kFull, s[v], o);
+        if (lane == 0)
+            for (int v = 0; v < V; ++v) sh[w][v] = s[v];
+        if (!A.lex) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                cmx[v] = warp_extreme<false>(cmx[v]);
+                cmn[v] = warp_extreme<true>(cmn[v]);
+            }
+            if (lane == 0)
+                for (int v = 0; v < V; ++v) {
+                    wrec[w][kRecCmax + v] = cmx[v];
+                    wrec[w][kRecCmin + v] = cmn[v];
+                }
+        }
+    }
+    __syncthreads();
+    double *prec = A.partial + (size_t)blockIdx.x * kRecDoubles;
+    if constexpr (NORMS) {
+        if (threadIdx.x == 0) {
+            for (int v = 0; v < V; ++v) {
+                double t = 0.0;
+                for (int k = 0; k < 8; ++k) t += sh[k][v];
+                prec[kRecSum + v] = t;
+            }
+        }
+        if (A.lex) {
+            if (threadIdx.x < 16) {
+                const int slot = threadIdx.x, side = slot >> 3, lf = slot & 7;
+                double bext = side == 0 ? neg_inf() : pos_inf(), b1 = 0.0, b2 = 0.0, b3 = 0.0;
+                for (int k = 0; k < 8; ++k) {
+                    const double *q = &wrec[k][kRecLeaf + side * 24 + lf * 3];
+                    slot_merge(slot, wrec[k][kRecExt + side], q[0], q[1], q[2], bext, b1, b2, b3);
+                }
+                if (lf == 0) prec[kRecExt + side] = bext;
+                double *q = prec + kRecLeaf + side * 24 + lf * 3;
+                q[0] = b1;
+                q[1] = b2;
+                q[2] = b3;
+            }
+        } else if (threadIdx.x < 8) {
+            const int v = threadIdx.x & 3;
+            const bool mn = threadIdx.x >= 4;
+            double b = mn ? pos_inf() : neg_inf();
+            for (int k = 0; k < 8; ++k) b = mn ? fmin(b, wrec[k][kRecCmin + v]) : fmax(b, wrec[k][kRecCmax + v]);
+            prec[(mn ? kRecCmin : kRecCmax) + v] = b;
+        }
+    }
+    // fences are cumulative: the block barrier makes every thread's stores (incl. the remote halo rows) visible to
+    // thread 0, whose fence then orders them before the ticket (and, in the last block, before the flags)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if constexpr (MULTI) __threadfence_system();
+        else __threadfence();
+        is_last = atomicAdd(A.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    // ---- last block: this rank's record ----------------------------------------------------------------------------
+    __shared__ double fin[kRecDoubles];
+    __shared__ double xw[8][16][4];
+    const int nb = (int)gridDim.x;
+    if constexpr (NORMS) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) s[v] = 0.0;
+        for (int b = threadIdx.x; b < nb; b += blockDim.x)
+            for (int v = 0; v < V; ++v) s[v] += __ldcg(&A.partial[(size_t)b * kRecDoubles + kRecSum + v]);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            for (int o = 16; o > 0; o >>= 1) s[v] += __shfl_down_sync(kFull, s[v], o);
+        __syncthreads();
+        if (lane == 0)
+            for (int v = 0; v < V; ++v) sh[w][v] = s[v];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int v = 0; v < V; ++v) {
+                double t = 0.0;
+                for (int k = 0; k < 8; ++k) t += sh[k][v];
+                fin[kRecSum + v] = t;
+            }
+        }
+        if (A.lex) {
+            // thread = (j, slot): slot = side*8 + leaf scans the block records j, j+16, ...; then the 16 scanners of a slot merge
+            const int slot = threadIdx.x & 15, j = threadIdx.x >> 4, side = slot >> 3, lf = slot & 7;
+            double bext = side == 0 ? neg_inf() : pos_inf(), b1 = 0.0, b2 = 0.0, b3 = 0.0;
+            for (int b = j; b < nb; b += 16) {
+                const double *R = A.partial + (size_t)b * kRecDoubles;
+                const double *q = R + kRecLeaf + side * 24 + lf * 3;
+                slot_merge(slot, __ldcg(R + kRecExt + side), __ldcg(q), __ldcg(q + 1), __ldcg(q + 2), bext, b1, b2, b3);
+            }
+            {   // lanes slot and slot + 16 hold the same slot
+                const double oe = __shfl_xor_sync(kFull, bext, 16), o1 = __shfl_xor_sync(kFull, b1, 16);
+                const double o2 = __shfl_xor_sync(kFull, b2, 16), o3 = __shfl_xor_sync(kFull, b3, 16);
+                slot_merge(slot, oe, o1, o2, o3, bext, b1, b2, b3);
+            }
+            if (lane < 16) {
+                xw[w][slot][0] = bext;
+                xw[w][slot][1] = b1;
+                xw[w][slot][2] = b2;
+                xw[w][slot][3] = b3;
+            }
+            __syncthreads();
+            if (threadIdx.x < 16) {
+                for (int k = 0; k < 8; ++k)
+                    if (k != w) slot_merge(slot, xw[k][slot][0], xw[k][slot][1], xw[k][slot][2], xw[k][slot][3], bext, b1, b2, b3);
+                if (lf == 0) fin[kRecExt + side] = bext;
+                double *q = fin + kRecLeaf + side * 24 + lf * 3;
+                q[0] = b1;
+                q[1] = b2;
+                q[2] = b3;
+            }
+        } else if (threadIdx.x < 8) {
+            const int v = threadIdx.x & 3;
+            const bool mn = threadIdx.x >= 4;
+            double b = mn ? pos_inf() : neg_inf();
+            for (int k = 0; k < nb; ++k) {
+                const double x = __ldcg(&A.partial[(size_t)k * kRecDoubles + (mn ? kRecCmin : kRecCmax) + v]);
+                b = mn ? fmin(b, x) : fmax(b, x);
+            }
+            fin[(mn ? kRecCmin : kRecCmax) + v] = b;
+        }
+        __syncthreads();
+    }
+    if constexpr (MULTI) {
+        const unsigned long long en = A.L->epoch_n + 1;
+        const int par = (int)(en & 1);
+        if constexpr (NORMS) {
+            // this rank's record into every rank's window (own included)
+            for (int t = threadIdx.x; t < A.P.nranks * kRecDoubles; t += blockDim.x) {
+                const int r = t / kRecDoubles, d = t % kRecDoubles;
+                A.P.win[r]->rec[par][A.P.rank][d] = fin[d];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if constexpr (NORMS)
+                for (int r = 0; r < A.P.nranks; ++r) st_release_sys(&A.P.win[r]->rec_flag[par][A.P.rank], en);
+            for (int i = 0; i < A.P.ndst; ++i) st_release_sys(&A.P.win[A.P.dst[i]]->data_flag[0][A.P.rank], e_u);
+            A.L->epoch[0] = e_u;
+            if constexpr (NORMS) A.L->epoch_n = en;
+            *A.ticket = 0;
+        }
+    } else {
+        if (threadIdx.x == 0) {
+            for (int v = 0; v < V; ++v) A.stats[v] = fin[kRecSum + v];
+            norms_from_records<false>(fin, kRecDoubles, 1, A.divisor, A.lex, A.stats + V, A.stats + 2 * V, A.stats + kStatsRaw);
+            *A.ticket = 0;
+        }
+    }
+}
+
+// Several GPUs: block 0 of pass A turns the ranks' records into the norms while the other blocks run their main loops;
+// epilogues wait for norm_ready.  Executed by the threads of one warp (lane 0 does the arithmetic).
+__device__ inline void p2p_norms_merge(const P2PPeers &P, P2PLocal *L, double divisor, int lex, double *stats, int lane)
+{
+    const unsigned long long en = L->epoch_n;
+    const int par = (int)(en & 1);
+    P2PWindow *win = P.win[P.rank];
+    if (lane < P.nranks) spin_until(&win->rec_flag[par][lane], en, &L->error);
+    __syncwarp();
+    if (lane == 0) {
+        norms_from_records<true>(&win->rec[par][0][0], kRecDoubles, P.nranks, divisor, lex, stats + 4, stats + 8, stats + kStatsRaw);
+        __threadfence();
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&L->norm_ready), "l"(en) : "memory");
+    }
+}
+
+}  // namespace mft

@@ -19,6 +19,10 @@
 
 namespace mft {
 
+struct P2PPeers;
+struct P2PLocal;
+struct RowAux;
+
 constexpr int kSlice = 32;
 constexpr double kEps = 2.220446049250313e-16;  // Base.eps()
 
@@ -274,6 +278,20 @@ struct PassAArgs {
     // diagnostics (nullable)
     double *eps_uw, *eps_rv, *eps, *eps_c;
     void *residual;
+    // fused step (mft_fused_kernels.cuh).  stats = sum[4] | mean[4] | norms[4] | .. | raw norms at [16]; norm_miss counts the
+    // rows whose deviation from the mean exceeds the norms pass A was given (the leaf statistic missed a rounding tie)
+    const double *stats;          // nullable: no check
+    unsigned long long *norm_miss;
+    // several GPUs, fused step: g rows on the send list go straight into the peers' halo tails (band tiles only), block 0
+    // merges the ranks' norm records, epilogues wait for norm_ready
+    const struct P2PPeers *P;     // nullable
+    struct P2PLocal *L;
+    const int *aux;
+    const struct RowAux *rows;
+    const int *route_peer;
+    const long long *route_dst;
+    double divisor;
+    int norm_merge;
 };
 
 constexpr int VISC_NONE = 0;
@@ -284,7 +302,7 @@ constexpr int VISC_RESIDUAL = 2;
 // update_visc!, hyperviscosity.jl:246-349) and store g = eps .* (Dx u, Dy u)
 template <int V, int EQ, bool DO_FLUX, int VISC>
 __device__ __forceinline__ void pass_a_epilogue(const PassAArgs &A, int64_t row, const Vec<V> &acc, const Vec<V> &gx,
-                                                const Vec<V> &gy, const Vec<V> &ui, const Vec<V> &ad)
+                                                const Vec<V> &gy, const Vec<V> &ui, const Vec<V> &ad, Vec<2 * V> *g_ret = nullptr)
 {
     if constexpr (DO_FLUX) st_vec(reinterpret_cast<Vec<V> *>(A.du) + row, acc);
 
@@ -339,8 +357,9 @@ __device__ __forceinline__ void pass_a_epilogue(const PassAArgs &A, int64_t row,
                     for (int v = 0; v < V; ++v) A.norms_out[v] = nrm[v];
                 }
             } else {
+                // norm_merge: block 0 of this very launch wrote the norms (the caller waited for norm_ready): read them at L2
 #pragma unroll
-                for (int v = 0; v < V; ++v) nrm[v] = A.norms[v];
+                for (int v = 0; v < V; ++v) nrm[v] = A.norm_merge ? __ldcg(A.norms + v) : A.norms[v];
             }
             double mx = res.a[0] / nrm[0];
 #pragma unroll
@@ -373,6 +392,7 @@ __device__ __forceinline__ void pass_a_epilogue(const PassAArgs &A, int64_t row,
             gout.a[V + v] = e * gy.a[v];
         }
         st_vec(reinterpret_cast<Vec<2 * V> *>(A.g) + row, gout);
+        if (g_ret) *g_ret = gout;
     }
 }
 
@@ -1338,6 +1358,7 @@ __global__ void k_halo_pack(const Vec<W> *__restrict__ src, const int *__restric
 // after that peer has signalled (credit flag) that it consumed the previous epoch.
 // =====================================================================================================================
 constexpr int kMaxRanks = 16;
+constexpr int kRecDoubles = 64;  // one norm record (mft_fused_kernels.cuh): sums + lexicographic leaves, 512 bytes
 constexpr unsigned long long kSpinLimit = 1ull << 31;  // ~ seconds: then give up and raise the error flag
 
 struct P2PWindow {                                 // lives in every rank's memory; peers write into it
@@ -1347,6 +1368,9 @@ struct P2PWindow {                                 // lives in every rank's memo
     unsigned long long max_flag[2][kMaxRanks];
     double sums[2][kMaxRanks][4];
     double maxs[2][kMaxRanks][4];
+    // fused step (mft_fused_kernels.cuh): one norm record per rank and parity, and its epoch flag
+    unsigned long long rec_flag[2][kMaxRanks];
+    double rec[2][kMaxRanks][kRecDoubles];
 };
 
 struct P2PLocal {                                  // local counters (never written remotely)
@@ -1354,6 +1378,8 @@ struct P2PLocal {                                  // local counters (never writ
     unsigned long long epoch_n;                    // norms epoch
     unsigned int ticket[4];
     int error;
+    unsigned long long norm_ready;                 // fused step: norms epoch whose merged norms are in stats[] (set by block 0 of pass A)
+    unsigned int ticket_g;                         // fused step: band blocks of pass A that have finished their g puts
 };
 
 struct P2PPeers {

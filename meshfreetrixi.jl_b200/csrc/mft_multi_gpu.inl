@@ -52,7 +52,46 @@ extern "C" int mft_set_halo(mft_ctx *c, int npeers, const int *peers, const int6
         rows[i] = c->have_perm ? c->iperm[p] : (int)p;
     }
     CHECK(c->send_rows.upload(rows));
+    c->send_rows_host = rows;
     CHECK(c->send_buf.alloc(std::max<int64_t>(1, c->n_send) * 2 * c->V));
+    return MFT_OK;
+}
+
+// Fused step on several GPUs: block -> tile map of a union-tile operator.  A tile is a BAND tile if its stencil union holds a
+// halo column (it must wait for the peers' rows) or -- forward operator -- if one of its rows is in a peer's halo (its pass A
+// epilogue writes g into the peer's memory, which must not happen before the peer is done with the previous epoch: the same
+// wait orders that).  Interior tiles come first and start at once; band tiles are scheduled last.  At least one band tile
+// exists per kernel, so a finished kernel has always seen every source rank's flag of the epoch (the ordering argument in
+// DESIGN.md section 7 rests on that).
+static int build_tile_order(mft_ctx *c, DevTileR &e, bool with_send_rows)
+{
+    if (!e.ready()) return MFT_OK;
+    std::vector<int> uoff((size_t)e.ntiles + 1), ulist((size_t)e.uoff.n > 0 ? (size_t)e.ulist.n : 0);
+    CU(cudaMemcpy(uoff.data(), e.uoff.p, sizeof(int) * uoff.size(), cudaMemcpyDeviceToHost));
+    if (!ulist.empty()) CU(cudaMemcpy(ulist.data(), e.ulist.p, sizeof(int) * ulist.size(), cudaMemcpyDeviceToHost));
+    std::vector<char> band((size_t)e.ntiles, 0);
+    const int64_t rows_per_tile = (int64_t)kSlice * kTileWarps * e.R;
+    for (int t = 0; t < e.ntiles; ++t)
+        for (int q = uoff[(size_t)t]; q < uoff[(size_t)t + 1]; ++q) {
+            const int j = ulist[(size_t)q];
+            if (j >= c->n_local && j < c->n_tot) {   // n_tot itself is the dummy record
+                band[(size_t)t] = 1;
+                break;
+            }
+        }
+    if (with_send_rows)
+        for (int row : c->send_rows_host) band[(size_t)(row / rows_per_tile)] = 1;
+    int nband = 0;
+    for (char b : band) nband += b;
+    if (nband == 0 && e.ntiles > 0) band[(size_t)e.ntiles - 1] = 1;
+    std::vector<int> order;
+    order.reserve((size_t)e.ntiles);
+    for (int t = 0; t < e.ntiles; ++t)
+        if (!band[(size_t)t]) order.push_back(t);
+    e.n_free = (int)order.size();
+    for (int t = 0; t < e.ntiles; ++t)
+        if (band[(size_t)t]) order.push_back(t);
+    CHECK(e.order.upload(order));
     return MFT_OK;
 }
 
@@ -194,6 +233,15 @@ extern "C" int mft_p2p_connect(mft_ctx *c, int nranks, int rank, const void *all
     }
     CHECK(c->send_peer.upload(speer));
     CHECK(c->send_dst.upload(sdst));
+    c->send_peer_host = speer;
+    c->send_dst_host = sdst;
+    CHECK(c->peers_dev_buf.upload(std::vector<P2PPeers>(1, P)));
+    CHECK(build_row_aux(c));                        // now with the halo routes
+    CHECK(build_tile_order(c, c->fwd_tiler, true));
+    CHECK(build_tile_order(c, c->tra_tiler, false));
+    for (auto &g : c->graphs)                       // captured steps hold the old tables
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
     c->nranks = nranks;
     c->rank = rank;
     c->n_global = n_global;

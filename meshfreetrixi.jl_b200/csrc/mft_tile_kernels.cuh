@@ -13,6 +13,7 @@
 // Indices cost 2 bytes per entry instead of 4; the union lists add ~6 bytes per row and union point.
 #pragma once
 #include "mft_kernels.cuh"
+#include "mft_fused_kernels.cuh"
 
 namespace mft {
 
@@ -42,7 +43,41 @@ struct PassBTileArgs {
     void *du;
     int64_t n_rows;
     int64_t n_slices;
+    // several GPUs, fused step: band tiles (T.order, T.n_free) wait for the peers' g halo rows themselves
+    const P2PPeers *P;   // nullable
+    P2PLocal *L;
 };
+
+// 256-bit loads that go to L2 (rows another GPU writes while this kernel is running: never through the read-only path)
+__device__ __forceinline__ Vec<4> ld_cg(const Vec<4> *p)
+{
+    Vec<4> v;
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v.a[0]), "=d"(v.a[1]), "=d"(v.a[2]), "=d"(v.a[3])
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ Vec<8> ld_cg(const Vec<8> *p)
+{
+    Vec<8> v;
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v.a[0]), "=d"(v.a[1]), "=d"(v.a[2]), "=d"(v.a[3])
+                 : "l"(p)
+                 : "memory");
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4+32];"
+                 : "=d"(v.a[4]), "=d"(v.a[5]), "=d"(v.a[6]), "=d"(v.a[7])
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+
+// band tile: wait until the halo rows of field F (0: u, 1: g) of the current epoch have arrived from every source rank
+__device__ __forceinline__ void band_wait(const P2PPeers *P, P2PLocal *L, int F)
+{
+    if ((int)threadIdx.x < P->nsrc) spin_until(&P->win[P->rank]->data_flag[F][P->src[threadIdx.x]], L->epoch[F], &L->error);
+    __syncthreads();
+}
 
 // =====================================================================================================================
 // R rows per thread over union tiles.
@@ -77,6 +112,10 @@ struct TileROp {
     int buf_bytes;          // per-warp staging buffer (word block)
     int pf_tiles;           // > 0: pull the operator data of tile blockIdx.x + pf_tiles into L2 (it is first touched about one
                             // block lifetime later, by then an L2 hit instead of a DRAM round trip on the critical path)
+    // several GPUs, fused step: block b works on tile order[b]; the first n_free blocks touch neither halo columns nor send rows
+    // and start at once, the others ("band" tiles, scheduled last) wait for the peers' halo rows while the interior runs
+    const int *order;       // nullable: identity
+    int n_free;
 };
 
 // STAGE_W (exact order only): the warp also stages its compact weight blocks in shared memory -- wx_0..wx_{R-1} with the
@@ -93,9 +132,10 @@ __device__ __forceinline__ TilePf tile_pf_begin(const TileROp &T, int64_t n_slic
 {
     TilePf p{0, 0, 0, 0, 0, false, false};
     if (T.pf_tiles <= 0) return p;
-    const int64_t tn = (int64_t)blockIdx.x + T.pf_tiles;
-    p.tile_ok = tn < (int64_t)gridDim.x;
+    const int64_t bn = (int64_t)blockIdx.x + T.pf_tiles;
+    p.tile_ok = bn < (int64_t)gridDim.x;
     if (p.tile_ok) {
+        const int64_t tn = T.order ? (int64_t)__ldg(T.order + bn) : bn;
         p.u0 = __ldg(T.uoff + tn);
         p.u1 = __ldg(T.uoff + tn + 1);
         const int64_t sn = tn * kTileWarps + warp;
@@ -132,12 +172,19 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ uint64_t bars[kTileWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t slice = (int64_t)blockIdx.x * kTileWarps + warp;
+    const int tile = T.order ? __ldg(T.order + blockIdx.x) : (int)blockIdx.x;
+    const bool band = T.order != nullptr && (int)blockIdx.x >= T.n_free;   // several GPUs: this tile reads halo rows / feeds peers
+    const int64_t slice = (int64_t)tile * kTileWarps + warp;
     const bool has_slice = slice < A.n_slices;
     const int64_t row0 = (slice * kSlice + lane) * R;
     const uint32_t arr_bytes = (uint32_t)T.sstride * 16u, nc = (uint32_t)T.ncopy;
     unsigned char *sA = smem_dyn, *sB = smem_dyn + nc * arr_bytes, *sC = smem_dyn + 2 * nc * arr_bytes;
     unsigned char *buf = smem_dyn + 3 * nc * arr_bytes + (size_t)warp * T.buf_bytes;
+    if constexpr (VISC == VISC_RESIDUAL) {
+        // fused step on several GPUs: the first block turns the ranks' norm records into the norms (they are needed in the
+        // epilogues only, by then the records have long arrived)
+        if (A.norm_merge && blockIdx.x == 0 && warp == 0) p2p_norms_merge(*A.P, A.L, A.divisor, A.norm_lex, const_cast<double *>(A.stats), lane);
+    }
 
     int W = 0, L = 0;
     const unsigned char *src = nullptr;
@@ -161,13 +208,14 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
     const size_t rstride = (size_t)L * kSlice;                                                    // doubles per weight block
     const Vec<V> *__restrict__ u = reinterpret_cast<const Vec<V> *>(A.u);
 
-    const int u0 = T.uoff[blockIdx.x];
-    const int nu = T.uoff[blockIdx.x + 1] - u0;
+    const int u0 = T.uoff[tile];
+    const int nu = T.uoff[tile + 1] - u0;
+    if (band) band_wait(A.P, A.L, 0);   // the peers' u rows of this stage are in the halo tail from here on
     for (int t = threadIdx.x; t < nu; t += kTileWarps * 32) {
         const int j = __ldg(T.ulist + u0 + t);
         const unsigned int sl2 = __ldg(reinterpret_cast<const unsigned int *>(T.uslot) + u0 + t);
         const int sl = (int)(sl2 & 0xffffu);
-        const Vec<V> x = ld_ro(u + j);
+        const Vec<V> x = band ? ld_cg(u + j) : ld_ro(u + j);
         const double v1 = x.a[1] / x.a[0];
         const double v2 = x.a[2] / x.a[0];
         reinterpret_cast<double2 *>(sA)[sl] = make_double2(x.a[0], x.a[1]);
@@ -201,7 +249,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
     }
     __syncthreads();
     tile_pf_issue<R>(T, pf, warp, lane);
-    if (!has_slice) return;
+    if (has_slice) {
     if (W > 0) mbar_wait(&bars[warp], 0);
 
     const double gm1 = A.eqp0 - 1.0;
@@ -361,7 +409,58 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
                 ui = ld_ro(u + row);
                 if constexpr (VISC == VISC_RESIDUAL) ad = ld_ro(reinterpret_cast<const Vec<V> *>(A.approx_du) + row);
             }
-            pass_a_epilogue<V, EQ_EULER2D, DO_FLUX, VISC>(A, row, acc[r], gx[r], gy[r], ui, ad);
+            if constexpr (VISC == VISC_RESIDUAL) {
+                if (A.norm_merge) {   // block 0 publishes the merged norms: wait for this stage's
+                    if (lane == 0) spin_until(&A.L->norm_ready, A.L->epoch_n, &A.L->error);
+                    __syncwarp();
+                }
+                if (A.stats && A.norm_miss) {
+                    // the norms are the lexicographic (or per-component) maximum of |u - mean| over ALL points: check this row
+                    double dv[V], raw[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        dv[v] = fabs(ui.a[v] - __ldcg(A.stats + V + v));
+                        raw[v] = __ldcg(A.stats + kStatsRaw + v);
+                    }
+                    bool miss = false;
+                    if (A.norm_lex) miss = lex_less<V>(raw, dv);
+                    else {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) miss |= dv[v] > raw[v];
+                    }
+                    if (miss) atomicAdd(A.norm_miss, 1ull);
+                }
+            }
+            Vec<2 * V> gout;
+            pass_a_epilogue<V, EQ_EULER2D, DO_FLUX, VISC>(A, row, acc[r], gx[r], gy[r], ui, ad, &gout);
+            if constexpr (VISC != VISC_NONE) {
+                if (band && A.aux) {   // rows in a peer's halo: g goes straight into the peer's halo tail
+                    const int ax = __ldg(A.aux + row);
+                    if (ax >= 0) {
+                        const RowAux ra = A.rows[ax];
+                        for (int q = ra.sbeg; q < ra.send; ++q)
+                            st_vec(reinterpret_cast<Vec<2 * V> *>(A.P->field[1][A.route_peer[q]]) + A.route_dst[q], gout);
+                    }
+                }
+            }
+        }
+    }
+    }  // has_slice
+    if constexpr (VISC != VISC_NONE) {
+        if (band) {
+            // the last band block to finish raises the g flags of this epoch at every destination (cumulative fences as in k_p2p_put)
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence_system();
+                const unsigned int nband = gridDim.x - (unsigned int)T.n_free;
+                if (atomicAdd(&A.L->ticket_g, 1u) == nband - 1) {
+                    __threadfence_system();
+                    const unsigned long long e = A.L->epoch[1] + 1;
+                    for (int i = 0; i < A.P->ndst; ++i) st_release_sys(&A.P->win[A.P->dst[i]]->data_flag[1][A.P->rank], e);
+                    A.L->epoch[1] = e;
+                    A.L->ticket_g = 0;
+                }
+            }
         }
     }
 }
@@ -375,7 +474,9 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_B : R 
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ uint64_t bars[kTileWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t slice = (int64_t)blockIdx.x * kTileWarps + warp;
+    const int tile = T.order ? __ldg(T.order + blockIdx.x) : (int)blockIdx.x;
+    const bool band = T.order != nullptr && (int)blockIdx.x >= T.n_free;   // several GPUs: this tile reads g rows of the halo
+    const int64_t slice = (int64_t)tile * kTileWarps + warp;
     const bool has_slice = slice < A.n_slices;
     const int64_t row0 = (slice * kSlice + lane) * R;
     const uint32_t arr_bytes = (uint32_t)T.sstride * 16u, nc = (uint32_t)T.ncopy;
@@ -408,13 +509,14 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_B : R 
     const double *wdy = wdx + (STAGE_W ? (size_t)0 : (size_t)R * rstride);
     const Vec<2 * V> *__restrict__ g = reinterpret_cast<const Vec<2 * V> *>(A.g);
 
-    const int u0 = T.uoff[blockIdx.x];
-    const int nu = T.uoff[blockIdx.x + 1] - u0;
+    const int u0 = T.uoff[tile];
+    const int nu = T.uoff[tile + 1] - u0;
+    if (band) band_wait(A.P, A.L, 1);   // the peers' g rows of this stage are in the halo tail from here on
     for (int t = threadIdx.x; t < nu; t += kTileWarps * 32) {
         const int j = __ldg(T.ulist + u0 + t);
         const unsigned int sl2 = __ldg(reinterpret_cast<const unsigned int *>(T.uslot) + u0 + t);
         const int sl = (int)(sl2 & 0xffffu);
-        const Vec<2 * V> x = ld_ro(g + j);
+        const Vec<2 * V> x = band ? ld_cg(g + j) : ld_ro(g + j);
         reinterpret_cast<double2 *>(sA)[sl] = make_double2(x.a[0], x.a[1]);
         reinterpret_cast<double2 *>(sB)[sl] = make_double2(x.a[2], x.a[3]);
         reinterpret_cast<double2 *>(sC)[sl] = make_double2(x.a[4], x.a[5]);

@@ -116,8 +116,94 @@ static int launch_stage(mft_ctx *c, int stage, double dt)
     return MFT_OK;
 }
 
+// ---- fused device-resident step (MFT_OPT_FUSED_STEP; kernels: mft_fused_kernels.cuh, band logic: mft_tile_kernels.cuh) ----
+// Per stage three launches: k_stage_fused (BC pass 2 of the previous rhs!, stage update, BC pass 1, norm statistic, u halo
+// puts + flags), pass A (band tiles wait for the u halo; g halo puts + flags), pass B (band tiles wait for the g halo).
+static bool fused_step_ok(const mft_ctx *c)
+{
+    if (!c->fused_step || c->V != 4 || c->eq != MFT_EQ_EULER2D || c->srcs.size() != 1) return false;
+    const int kind = c->srcs[0]->kind;
+    if (kind != MFT_SRC_UPWIND && kind != MFT_SRC_RESIDUAL) return false;
+    if (!c->fwd_tiler.ready() || !c->tra_tiler.ready()) return false;
+    if (!c->bc_merged && !c->bcs.empty()) {
+        bool any = false;
+        for (auto *g : c->bcs) any |= g->nb > 0 && g->kind != MFT_BC_DO_NOTHING;
+        if (any) return false;   // a point in two boundary groups: the group order matters, keep the per-group launches
+    }
+    if (!c->stage_lim_variables.empty()) return false;
+    if (c->nranks > 1 && (!c->p2p || !c->fwd_tiler.order.p || !c->tra_tiler.order.p)) return false;
+    return true;
+}
+
+static int launch_stage_fused(mft_ctx *c, int stage, double dt, bool apply_bc2)
+{
+    NvtxRange range("SSPRK stage update + boundary flux + norms (fused)");
+    ScopedTimer tm(c, MFT_K_STAGE);
+    const bool residual = c->srcs[0]->kind == MFT_SRC_RESIDUAL;
+    const bool multi = c->nranks > 1;
+    StageArgs a{};
+    a.stage = stage;
+    a.apply_bc2 = apply_bc2 ? 1 : 0;
+    a.dt = dt;
+    a.u = c->u.p;
+    a.uprev = c->uprev.p;
+    a.du = c->du.p;
+    a.n = c->n_local;
+    a.aux = c->row_aux.p;
+    a.rows = c->row_aux_tab.p;
+    a.bc_kind = c->bc_kind.p;
+    a.bc_normals = c->bc_normals.p;
+    a.bc_values = c->bc_values.p;
+    a.partial = c->partial.p;
+    a.ticket = c->ticket.p + 4;
+    const double ng = multi ? (double)c->n_global : (double)c->n_local;
+    a.divisor = c->mean_div_vn ? (double)c->V * ng : ng;
+    a.lex = c->max_lex;
+    a.stats = c->stats.p;
+    a.L = reinterpret_cast<P2PLocal *>(c->p2p_local.p);
+    a.route_peer = c->route_peer.p;
+    a.route_dst = c->route_dst.p;
+    if (multi) a.P = c->peers_dev;
+    const int grid = c->red_blocks;
+    if (multi) {
+        if (residual) k_stage_fused<true, true><<<grid, 256, 0, c->stream>>>(a);
+        else k_stage_fused<false, true><<<grid, 256, 0, c->stream>>>(a);
+    } else {
+        if (residual) k_stage_fused<true, false><<<grid, 256, 0, c->stream>>>(a);
+        else k_stage_fused<false, false><<<grid, 256, 0, c->stream>>>(a);
+    }
+    c->launches++;
+    LAUNCH_CHECK();
+    return MFT_OK;
+}
+
+static int ssprk33_step_fused(mft_ctx *c, double t, double dt, bool first_rhs)
+{
+    if (first_rhs) CHECK(rhs_device(c, t));   // k = f(u_n): the separate kernels (complete rhs! incl. BC pass 2)
+    Source *s = c->srcs[0];
+    const int visc = s->kind == MFT_SRC_UPWIND ? VISC_UPWIND : VISC_RESIDUAL;
+    struct Guard {
+        mft_ctx *c;
+        ~Guard() { c->fused_active = false; }
+    } guard{c};
+    c->fused_active = true;
+    for (int stage = 1; stage <= 3; ++stage) {
+        CHECK(select_stage_boundary_values(c, stage == 2 ? 1 : 0));   // rhs! of stage 1 and 3 is evaluated at t + dt, of stage 2 at t + dt/2
+        CHECK(launch_stage_fused(c, stage, dt, stage > 1));
+        NvtxRange r(visc == VISC_RESIDUAL ? "calc fluxes + calc SourceResidualViscosityTominec (fused)"
+                                          : "calc fluxes + calc SourceUpwindViscosityTominec (fused)");
+        CHECK(launch_pass_a(c, true, visc, s, false));
+        CHECK(launch_pass_b(c));
+    }
+    c->fused_active = false;
+    NvtxRange r("boundary flux");
+    CHECK(launch_boundary(c, true));   // BC pass 2 of the last rhs!: u and du are complete when the step returns
+    return MFT_OK;
+}
+
 static int ssprk33_step_launches(mft_ctx *c, double t, double dt, bool first_rhs)
 {
+    if (fused_step_ok(c)) return ssprk33_step_fused(c, t, dt, first_rhs);
     if (first_rhs) CHECK(rhs_device(c, t));  // k = f(u_n): first step only (FSAL afterwards); current Dirichlet tables = time t
     CHECK(launch_stage(c, 1, dt));
     CHECK(select_stage_boundary_values(c, 0));

@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--source", default="upwind")
     ap.add_argument("--exchange", default="p2p")
     ap.add_argument("--setup", default="host", help="device: every rank builds its kNN tables / weights with the GPU pipeline")
+    ap.add_argument("--fused", type=int, default=1, help="0: the separate stage / boundary / norm / put / wait kernels (MFT_OPT_FUSED_STEP = 0)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -237,7 +238,8 @@ def main():
         assert err < 1e-12, err
     else:
         solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=int(os.environ.get("LOCAL_RANK", rank)),
-                                                                    diagnostics=True, exchange=args.exchange, setup=args.setup))
+                                                                    diagnostics=True, exchange=args.exchange, setup=args.setup,
+                                                                    fused_step=bool(args.fused)))
         domain = m.ParallelPointCloudDomain(solver, cl, names, comm, wide_halo=args.source == "tominec")
         part = domain.partition
         eq = m.CompressibleEulerEquations2D(GAMMA)
@@ -308,7 +310,10 @@ def main():
         ode = m.ODEProblem(np.ascontiguousarray(u0[:, gid]), (0.0, 10 * dt), semi)
         sol = m.solve(ode, m.SSPRK33(), dt=dt, callback=None if hist is None else m.HistoryCallback(3), nsteps=10)
         err2 = max(np.abs(sol.u[v, :nl] - u_ref[v, part.owned_gid]).max() / np.abs(u_ref[v]).max() for v in range(4))
-        results = dict(rank=rank, n_local=nl, n_halo=part.n_halo, err=float(err), err_steps=float(err2))
+        miss = np.zeros(1)
+        m._lib.check(m.load().mft_get_field(semi.ctx, m._lib.FIELD_NORM_MISSES, m._lib.ptr(miss)))
+        results = dict(rank=rank, n_local=nl, n_halo=part.n_halo, err=float(err), err_steps=float(err2), norm_misses=int(miss[0]))
+        assert miss[0] == 0, miss
         # device-made weights differ from the serial oracle's by rounding (different elimination order): 1e-9 instead of 1e-12
         assert err < (1e-12 if args.setup == "host" else 1e-9), err
         assert err2 < (1e-9 if args.setup == "host" else 1e-8), err2

@@ -20,12 +20,12 @@ def _free_port():
     return p
 
 
-def _launch(nproc, mode, source, tmp_path, timeout=600, exchange="p2p", setup="host"):
-    out = os.path.join(tmp_path, f"res_{mode}_{source}_{exchange}_{setup}.json")
+def _launch(nproc, mode, source, tmp_path, timeout=600, exchange="p2p", setup="host", fused=1):
+    out = os.path.join(tmp_path, f"res_{mode}_{source}_{exchange}_{setup}_{fused}.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(cases.ROOT, "tests", "dist_worker.py"), "--mode", mode, "--source", source, "--out", out,
-           "--exchange", exchange, "--setup", setup]
+           "--exchange", exchange, "--setup", setup, "--fused", str(fused)]
     env = dict(os.environ, OMP_NUM_THREADS="2")
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
@@ -82,6 +82,16 @@ def test_two_gpus_match_serial_oracle(tmp_path, source, exchange):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     res = _launch(2, "gpu", source, str(tmp_path), timeout=240, exchange=exchange)
+    assert all(r["err"] < 1e-12 and r["err_steps"] < 1e-9 for r in res)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("source", ["upwind", "residual"])
+def test_two_gpus_separate_kernels_match_serial_oracle(tmp_path, source):
+    """MFT_OPT_FUSED_STEP = 0: the round-1 sequence (put / wait kernels, two norm round trips) stays covered"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    res = _launch(2, "gpu", source, str(tmp_path), timeout=240, exchange="p2p", fused=0)
     assert all(r["err"] < 1e-12 and r["err_steps"] < 1e-9 for r in res)
 
 
