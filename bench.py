@@ -111,6 +111,67 @@ def vortex_ic(m, center):
 GRID_FOR_GPUS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}   # lattice multiples: fixed points per GPU (weak scaling)
 
 
+def multi_gpu_parity(m, comm, dist, args, local_rank):
+    """N > 1 only, OUTSIDE the timed region: a small jittered cloud partitioned over the same ranks, through the same engine /
+    exchange settings as the timed run (fused step, peer-memory puts), against the SERIAL oracle on the global cloud (the
+    checker; every rank evaluates it, the cloud is small): one rhs! (tolerance 1e-12) and 10 SSPRK33 steps with the history
+    callback (1e-9).  Returns the max over ranks; the bench refuses to print a line above the tolerances."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mft_oracle as orc
+
+    nx, ny = 40 * max(1, GRID_FOR_GPUS.get(comm.nranks, (comm.nranks, 1))[0]), 36 * max(1, GRID_FOR_GPUS.get(comm.nranks, (comm.nranks, 1))[1])
+    cl = m.cloud.jittered_lattice(nx, ny, 10.0, 10.0 * ny / nx, seed=4)
+    names = dict(left=1, right=2, bottom=3, top=4)
+    ic = lambda x, t, e=None: m.cloud.isentropic_vortex(x, GAMMA, center=(5.0, 5.0 * ny / nx))   # noqa: E731
+    basis = m.PointCloudBasis(m.Point2D(), 3, approximation_type=m.RBF(m.PolyharmonicSpline(3)))
+    nb, dx_min, dx_avg = orc.point_data(cl.points, basis.nv)
+    ops = m.setup_ops.compute_flux_operator(cl.points, nb, 3, 3)
+    obc = [orc.OracleBC(orc.BC_DIRICHLET, cl.boundary_idxs[g], cl.boundary_normals[g], value_fn=lambda x, t: ic(x, t)) for g in range(4)]
+    residual = args.source == "residual"
+    src_o = orc.source_residual(dx_avg, polydeg=3) if residual else orc.source_upwind(dx_avg)
+    P = orc.OracleProblem(cl.points, 4, orc.EQ_EULER2D, [GAMMA], ops[0], ops[1], obc, [src_o])
+    u0 = ic(cl.points, 0.0) * (1.0 + 0.01 * np.sin(cl.points[:, 0]))
+    u_ser = u0.copy()
+    du_ser = P.rhs(u_ser, 0.0)
+    dt = 0.1 * dx_min / 8.0
+    u_ref, _ = P.solve_ssprk33(u0, 0.0, dt, 10, approx_order=3 if residual else None)
+
+    solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=local_rank, exact_order=not args.fma, cuda_graph=int(args.graph),
+                                                                exchange=args.exchange, tile=int(args.tile), tile_rows=int(args.tile_rows),
+                                                                fused_step=bool(args.fused_step)))
+    domain = m.ParallelPointCloudDomain(solver, cl, names, comm)
+    part = domain.partition
+    eq = m.CompressibleEulerEquations2D(GAMMA)
+    bc = {k: m.BoundaryConditionDirichlet(ic) for k in names}
+    srcs = (m.SourceTerms(rv=m.SourceResidualViscosityTominec(solver, eq, domain, polydeg=3)) if residual
+            else m.SourceTerms(uw=m.SourceUpwindViscosityTominec(solver, eq, domain)))
+    semi = m.SemidiscretizationHyperbolic(domain, eq, ic, solver, boundary_conditions=bc, source_terms=srcs)
+    gid, nl = part.local_gid, part.n_local
+    u = np.ascontiguousarray(u0[:, gid])
+    u[:, nl:] = 0.0
+    du = np.zeros_like(u)
+    m.rhs_(du, u, semi, 0.0)
+    ref = du_ser[:, part.owned_gid]
+    e_rhs = max(np.abs(du[v, :nl] - ref[v]).max() / np.abs(du_ser[v]).max() for v in range(4))
+    ode = m.ODEProblem(np.ascontiguousarray(u0[:, gid]), (0.0, 10 * dt), semi)
+    sol = m.solve(ode, m.SSPRK33(), dt=dt, callback=m.HistoryCallback(3) if residual else None, nsteps=10)
+    e_steps = max(np.abs(sol.u[v, :nl] - u_ref[v, part.owned_gid]).max() / np.abs(u_ref[v]).max() for v in range(4))
+    miss = np.zeros(1)
+    m._lib.check(m.load().mft_get_field(semi.ctx, m._lib.FIELD_NORM_MISSES, m._lib.ptr(miss)))
+    semi.close()
+    t = torch.tensor([e_rhs, e_steps, miss[0]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e_rhs, e_steps, misses = (float(x) for x in t.tolist())
+    out = {"ranks": comm.nranks, "points": int(len(cl.points)), "rhs_relerr": e_rhs, "steps_relerr": e_steps, "steps": 10,
+           "norm_misses": int(misses), "against": "serial oracle (oracle/mft_oracle.c) on the global cloud",
+           "tolerances": {"rhs": 1e-12, "steps": 1e-9}, "ok": bool(e_rhs <= 1e-12 and e_steps <= 1e-9 and misses == 0)}
+    if not out["ok"]:
+        raise SystemExit(f"bench: multi-GPU parity check failed: {out}")
+    return out
+
+
 def run_ours(args):
     import mft_b200 as m
 
@@ -131,6 +192,7 @@ def run_ours(args):
         dist.init_process_group("nccl")
         from mft_b200 import partition
         comm = partition.TorchComm()
+    parity = multi_gpu_parity(m, comm, dist, args, local_rank) if multi and not args.no_parity else None
     gx, gy = GRID_FOR_GPUS.get(world, (world, 1))
     nx, ny = args.n_side * gx, args.n_side * gy
     cl, basis, _ = build_workload(nx, ny, 0, m)
@@ -141,7 +203,8 @@ def run_ours(args):
                                                                 exchange=args.exchange, pair_rows=int(args.pair_rows),
                                                                 tile=int(args.tile), tile_rows=int(args.tile_rows),
                                                                 prefetch_distance=args.pf_dist, setup=args.setup,
-                                                                refine_order=bool(args.refine_order)))
+                                                                refine_order=bool(args.refine_order),
+                                                                fused_step=bool(args.fused_step)))
     names = dict(left=1, right=2, bottom=3, top=4)
     t_setup = time.time()
     domain = m.ParallelPointCloudDomain(solver, cl, names, comm) if multi else m.PointCloudDomain(solver, cl, names)
@@ -218,6 +281,8 @@ def run_ours(args):
     L.check(lib.mft_download_state(ctx, L.soa_ptrs(u_end)))
     if not np.isfinite(u_end[:, :n_own]).all():
         raise SystemExit("bench: non-finite state after the timed region")
+    miss = np.zeros(1)
+    L.check(lib.mft_get_field(ctx, L.FIELD_NORM_MISSES, L.ptr(miss)))
 
     # ---- per-kernel CUDA-event pass (same steps, events around every launch on the ctx stream) -----------
     L.check(lib.mft_set_kernel_timing(ctx, 1))
@@ -316,8 +381,9 @@ def run_ours(args):
                           "l2": "inputs larger than L2 (operators 2 x %.0f MB per GPU streamed every stage)" % (n_own * 20 * k / 1e6),
                           "setup_s": round(t_setup, 1), "setup": args.setup,
                           "layout": {"tile": int(args.tile), "tile_rows": int(args.tile_rows), "refine_order": int(args.refine_order),
-                                     "exchange": args.exchange if multi else None}},
+                                     "exchange": args.exchange if multi else None, "fused_step": int(args.fused_step)}},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+               "parity": parity, "norm_misses": int(miss[0]),
                # the reference's own (printed, never recorded) metric: PerformanceCallback's performance index
                # PID = runtime * nranks / (ndofsglobal * ncalls_rhs), src/callbacks_step/performance.jl:229-235 (one DOF = one point)
                "reference_native_metric": {"name": "PID [s per DOF per rhs! per rank]", "value": world / value}}
@@ -491,6 +557,8 @@ def main():
     ap.add_argument("--source", default="residual", choices=["residual", "upwind"],
                     help="stabilisation source: residual viscosity + history (configs[1], [3]) or upwind viscosity (configs[2])")
     ap.add_argument("--refine-order", type=int, default=0, help="1: order the rows inside a tile by D' row length (fewer padding steps in pass B)")
+    ap.add_argument("--fused-step", type=int, default=1, help="0: separate stage / boundary / norm / halo put / wait kernels (round-1 sequence)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the untimed parity check against the serial oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--cloud-order", default="hilbert", choices=["hilbert", "lattice"],

@@ -782,7 +782,8 @@ static int build_row_aux(mft_ctx *c)
             if (row >= 0 && row < nl) entry(row).bc = (int)j;
         }
     // routes sorted by row: a row that several peers hold in their halo owns a contiguous slice
-    const size_t ns = c->send_rows_host.size();
+    // (mft_set_halo may precede mft_finalize; the routes only exist once mft_p2p_connect has run)
+    const size_t ns = c->send_peer_host.size() == c->send_rows_host.size() ? c->send_rows_host.size() : 0;
     std::vector<int> ord(ns), rpeer(ns);
     std::vector<long long> rdst(ns);
     std::iota(ord.begin(), ord.end(), 0);

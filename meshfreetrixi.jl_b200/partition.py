@@ -8,7 +8,8 @@ so every owned row keeps its full global stencil (weights are computed from the 
 sets are exchanged per `rhs!`: the state `u` before the forward pass and `g = eps .* D u` before the transposed
 pass.  One halo set H_r = F_r + R_r serves both:
     F_r  columns of owned rows outside the rank            (needed for u)
-    R_r  foreign rows whose stencils contain owned points   (their g enters D' rows of owned points)
+    R_r  foreign rows whose stencils contain owned points   (their g enters D' rows of owned points); kNN is not symmetric,
+         so R_r is built from what the OTHER ranks report about their own rows (one allgather), not by a local search
 Each rank builds only its own part: kNN / weights for its owned + halo rows, in parallel on all ranks.
 """
 from __future__ import annotations
@@ -87,45 +88,77 @@ def build_rank_partition(points: np.ndarray, boundary_idxs, boundary_normals, ra
     is_owned = np.zeros(n, dtype=bool)
     is_owned[owned] = True
 
-    # kNN against the cloud restricted to a padded bounding box of the partition (exact as long as the padding
-    # exceeds the stencil radius; the padding is 12 mean spacings)
+    # kNN against the cloud restricted to a padded bounding box of the partition.  The result is exact iff no stencil reaches
+    # further than its query point's distance to a box side that cuts the cloud; that is CHECKED for every query and the box is
+    # doubled until it holds (graded clouds: the stencil radius of a coarse region can exceed any fixed multiple of the mean
+    # spacing).
     lo, hi = points[owned].min(axis=0), points[owned].max(axis=0)
-    area = np.prod(np.maximum(points.max(axis=0) - points.min(axis=0), 1e-300))
+    glo, ghi = points.min(axis=0), points.max(axis=0)
+    area = np.prod(np.maximum(ghi - glo, 1e-300))
     h_est = np.sqrt(area / n)
     pad = 12.0 * h_est * max(1.0, np.sqrt(nv / 20.0))
-    box = np.nonzero(np.all((points >= lo - pad) & (points <= hi + pad), axis=1))[0]
-    if knn_queries is None:
-        tree = cKDTree(points[box])
+    state = {}
 
-        def knn(ids):
-            return setup_ops.knn_query(tree, points[ids], nv, index_map=box)
-    else:
-        box_points = np.ascontiguousarray(points[box])
-        pos_in_box = np.full(n, -1, dtype=np.int64)
-        pos_in_box[box] = np.arange(len(box), dtype=np.int64)
+    def make_box(pad):
+        blo, bhi = lo - pad, hi + pad
+        box = np.nonzero(np.all((points >= blo) & (points <= bhi), axis=1))[0]
+        state.update(box=box, blo=blo, bhi=bhi)
+        if knn_queries is None:
+            state["tree"] = cKDTree(points[box])
+        else:
+            state["box_points"] = np.ascontiguousarray(points[box])
+            pib = np.full(n, -1, dtype=np.int64)
+            pib[box] = np.arange(len(box), dtype=np.int64)
+            state["pos_in_box"] = pib
 
-        def knn(ids):
-            qp = pos_in_box[ids]
-            assert (qp >= 0).all(), "a query point lies outside the padded partition box"
-            nbp, d = knn_queries(box_points, qp, nv)
-            return box[nbp], d
+    def knn_once(ids):
+        box = state["box"]
+        if knn_queries is None:
+            return setup_ops.knn_query(state["tree"], points[ids], nv, index_map=box)
+        qp = state["pos_in_box"][ids]
+        if (qp < 0).any():
+            return None, None
+        nbp, d = knn_queries(state["box_points"], qp, nv)
+        return box[nbp], d
 
+    def knn(ids):
+        nonlocal pad
+        ids = np.asarray(ids, dtype=np.int64)
+        if len(ids) == 0:
+            return np.zeros((0, nv), dtype=np.int64), np.zeros((0, nv))
+        while True:
+            nb, d = knn_once(ids)
+            if nb is not None:
+                q = points[ids]
+                # distance to the nearest box side that actually cuts the cloud (a side beyond the global extent cuts nothing)
+                room = np.full(len(ids), np.inf)
+                for ax in range(points.shape[1]):
+                    if state["blo"][ax] > glo[ax]:
+                        room = np.minimum(room, q[:, ax] - state["blo"][ax])
+                    if state["bhi"][ax] < ghi[ax]:
+                        room = np.minimum(room, state["bhi"][ax] - q[:, ax])
+                if (d[:, -1] <= room).all():
+                    return nb, d
+            pad *= 2.0
+            make_box(pad)
+
+    make_box(pad)
     nb_owned, d_owned = knn(owned)
     F = np.setdiff1d(np.unique(nb_owned), owned)
-    ring1_nb, _ = knn(F) if len(F) else (np.zeros((0, nv), dtype=np.int64), None)
-    ring2 = np.setdiff1d(np.setdiff1d(np.unique(ring1_nb), owned), F)
-    cand = np.concatenate([F, ring2])
-    if len(cand):
-        cand_nb = np.concatenate([ring1_nb, knn(ring2)[0]]) if len(ring2) else ring1_nb
-        touches = is_owned[cand_nb].any(axis=1)
-    else:
-        cand_nb = np.zeros((0, nv), dtype=np.int64)
-        touches = np.zeros(0, dtype=bool)
-    in_F = np.zeros(len(cand), dtype=bool)
-    in_F[:len(F)] = True
-    keep = in_F | touches
-    halo = cand[keep]
-    halo_nb = cand_nb[keep]
+    # R_r exactly: kNN is not symmetric, so the foreign rows whose stencils contain one of MY points cannot be found by
+    # searching around my own stencils.  Every rank knows its own rows' stencils: it tells each other rank which of its rows
+    # reference that rank's points.
+    col_owner = np.searchsorted(offs, pos[nb_owned], side="right") - 1
+    touching = {}
+    for q in np.unique(col_owner):
+        if int(q) != rank:
+            touching[int(q)] = owned[(col_owner == q).any(axis=1)]
+    all_touching = allgather(touching)
+    R_parts = [all_touching[q][rank] for q in range(nranks) if q != rank and rank in all_touching[q]]
+    R = np.unique(np.concatenate(R_parts)) if R_parts else np.zeros(0, dtype=np.int64)
+    assert not is_owned[R].any()
+    halo = np.union1d(F, R)
+    halo_nb, _ = knn(halo)
     if wide_halo and len(halo):
         rows_R = halo_nb[is_owned[halo_nb].any(axis=1)]
         extra = np.setdiff1d(np.setdiff1d(np.unique(rows_R), owned), halo)

@@ -197,3 +197,55 @@ def test_partition_planner_invariants(nranks, shape, wide):
     for g in range(4):
         got = np.concatenate([p.owned_gid[p.boundary_idxs[g]] for p in parts])
         assert np.array_equal(np.sort(got), np.sort(cl.boundary_idxs[g]))
+
+
+def _plan_all(points, boundary_idxs, boundary_normals, nranks, nv=20, wide=False):
+    """the production planner on `nranks` ranks, threads standing in for the ranks"""
+    import threading
+
+    from mft_b200 import partition
+
+    barrier, slots, parts, errs = threading.Barrier(nranks), [None] * nranks, [None] * nranks, []
+
+    def work(r):
+        def allgather(obj):
+            slots[r] = obj
+            barrier.wait()
+            out = list(slots)
+            barrier.wait()
+            return out
+        try:
+            parts[r] = partition.build_rank_partition(points, boundary_idxs, boundary_normals, r, nranks, 3, 3, nv, allgather, wide_halo=wide)
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+            barrier.abort()
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    return parts
+
+
+def test_reverse_halo_is_exact_on_a_graded_cloud():
+    """kNN is not symmetric: on a graded cloud a foreign row can hold an owned point in its stencil without being anywhere near
+    the owned rows' own stencils (3 such rows were missed on this kind of cloud).  R_r comes from the other ranks'
+    reports now: every foreign row that references an owned point must be a halo row, on every rank; and the padded kNN box
+    must have grown where the coarse region's stencil radius exceeds the default padding (tables equal the global ones)."""
+    import numpy as np
+
+    rng = np.random.default_rng(11)
+    pts = np.concatenate([rng.random((2000, 2)) * 10.0, 5.0 + 0.05 * rng.standard_normal((18000, 2))])
+    pts = np.unique(pts, axis=0)
+    nb_g, dx_min, dx_avg = cases.orc.point_data(pts, 20)
+    parts = _plan_all(pts, [np.zeros(0, dtype=np.int64)], [np.zeros((0, 2))], 8)
+    missed = 0
+    for p in parts:
+        assert np.array_equal(p.neighbors_owned, nb_g[p.owned_gid])          # exact kNN despite the partition box
+        touches = np.isin(nb_g, p.owned_gid).any(axis=1)
+        R = np.setdiff1d(np.nonzero(touches)[0], p.owned_gid)
+        missed += len(np.setdiff1d(R, p.halo_gid))
+        F = np.setdiff1d(np.unique(nb_g[p.owned_gid]), p.owned_gid)
+        assert len(np.setdiff1d(F, p.halo_gid)) == 0
+        has_row = p.neighbors_halo[:, 0] >= 0
+        assert np.array_equal(p.neighbors_halo[has_row], nb_g[p.halo_gid[has_row]])
+    assert missed == 0
