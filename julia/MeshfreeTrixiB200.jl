@@ -96,14 +96,20 @@ function Trixi.create_cache(domain::PointCloudDomain{2}, equations,
     return (; pd, rbf_differentiation_matrices, ctx, registered = Ref(false))
 end
 
-# boundary conditions / sources are only known to rhs!; register them on first use, in NamedTuple order
-function register!(cache, domain, equations, boundary_conditions, source_terms)
+# Dirichlet closures get the stage time on every call in the reference (calc_single_boundary_flux!, rbfsolver.jl:311-316).
+# Host-mode rhs! therefore re-evaluates every Dirichlet table at the actual `t` of the call (O(sqrt(N)) closure calls, small
+# next to the state transfer).  Set STATIC_DIRICHLET[] = true to skip that when the data do not depend on time.
+const STATIC_DIRICHLET = Ref(false)
+
+# boundary conditions / sources are only known to rhs! (and to the history callback, whichever runs first); register them on
+# first use, in NamedTuple order, with the Dirichlet data of the time of that first call
+function register!(cache, domain, equations, boundary_conditions, source_terms, t0 = 0.0)
     ctx = cache.ctx
     for (key, bc) in zip(keys(boundary_conditions), boundary_conditions)     # rbfsolver.jl:280-285
         tag = domain.boundary_tags[key]
         nrm = collect(reinterpret(Float64, tag.normals))
         if bc isa BoundaryConditionDirichlet
-            add_boundary!(ctx, 0, tag.idx, nrm, dirichlet_table(bc, domain, tag, 0.0, equations))
+            add_boundary!(ctx, 0, tag.idx, nrm, dirichlet_table(bc, domain, tag, t0, equations))
         elseif bc === boundary_condition_slip_wall
             add_boundary!(ctx, 1, tag.idx, nrm, nothing)
         else
@@ -143,11 +149,14 @@ function refresh_dirichlet!(cache, domain, equations, boundary_conditions, t)
 end
 
 # ---- Trixi.rhs! (CPU engine: rbfsolver.jl:397-428) ---------------------------------------------------------------------
+# Trixi's rhs!(du_ode, u_ode, semi, t) calls this 10-argument method positionally, so nothing here may depend on a keyword.
 function Trixi.rhs!(du, u, t, domain, equations, initial_condition, boundary_conditions::BC,
-                    source_terms::Source, solver::RBFSolver{<:Any, RBFFDEngineCUDA}, cache;
-                    time_dependent_bcs = false) where {BC, Source}
-    cache.registered[] || register!(cache, domain, equations, boundary_conditions, source_terms)
-    time_dependent_bcs && refresh_dirichlet!(cache, domain, equations, boundary_conditions, t)
+                    source_terms::Source, solver::RBFSolver{<:Any, RBFFDEngineCUDA}, cache) where {BC, Source}
+    if !cache.registered[]
+        register!(cache, domain, equations, boundary_conditions, source_terms, t)   # tables of the first call's t
+    elseif !STATIC_DIRICHLET[]
+        refresh_dirichlet!(cache, domain, equations, boundary_conditions, t)
+    end
     up = collect(Ptr{Float64}, pointer.(StructArrays.components(u)))
     dup = collect(Ptr{Float64}, pointer.(StructArrays.components(du)))
     GC.@preserve u du up dup begin
@@ -166,15 +175,40 @@ function MeshfreeTrixi.calc_fluxes!(du, u, domain::PointCloudDomain, have_noncon
                                              (Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}), cache.ctx.ptr, up, dup))
 end
 
-# ---- HistoryCallback (history.jl:91-103): the (polydeg+1)^2 weight solve stays in Julia ------------------------------------
-function MeshfreeTrixi.modify_cache!(source::SourceResidualViscosityTominec, u, t, approx_order, integrator,
-                                     ctx::MftContext)
+# ---- HistoryCallback (history.jl:53-103) for the CUDA engine -----------------------------------------------------------------
+# The stock callback runs update_history!(semi, u, t, approx_order, integrator) (history.jl:80-88), which calls the
+# FIVE-argument modify_cache!(source, u, t, approx_order, integrator) of every source.  The stock method for
+# SourceResidualViscosityTominec would update the HOST cache only, the device would never see a history push, success_iter
+# would stay 0 there and every point would take the first-order branch of update_visc!.  So for a semidiscretization whose
+# solver carries the CUDA engine, update_history! itself is routed here: the callback and the OrdinaryDiffEq driver stay as
+# they are, the (polydeg+1)^2 weight solve stays in Julia (time_deriv_weights!, history.jl:131-152), the shift of the
+# solution history and update_approx_du! happen on the device.
+function MeshfreeTrixi.update_history!(semi::Trixi.SemidiscretizationHyperbolic, u, t, approx_order, integrator)
+    if !(semi.solver isa RBFSolver{<:Any, RBFFDEngineCUDA})
+        return invoke(MeshfreeTrixi.update_history!, Tuple{Any, Any, Any, Any, Any}, semi, u, t, approx_order, integrator)
+    end
+    cache = semi.cache
+    # initialize! of the callback runs before the first rhs!: boundary conditions and sources must be registered (and the
+    # layouts built) before the first push
+    cache.registered[] || register!(cache, semi.mesh, semi.equations, semi.boundary_conditions, semi.source_terms, t)
+    semi.source_terms === nothing && return nothing
+    for source in values(semi.source_terms)
+        source isa SourceResidualViscosityTominec && push_history!(source, u, t, approx_order, integrator, cache.ctx)
+    end
+    return nothing
+end
+
+function push_history!(source::SourceResidualViscosityTominec, u, t, approx_order, integrator, ctx::MftContext)
     @unpack time_history, time_weights = source.cache
     source.cache.success_iter .= integrator.success_iter
     time_history[2:end] .= time_history[1:(end - 1)]
     time_history[1] = t
     n = min(integrator.success_iter + 1, approx_order + 1)
     integrator.success_iter > 0 && time_deriv_weights!(@view(time_weights[1:n]), @view(time_history[1:n]))
+    # the snapshot must be the u the callback received (integrator.u), not whatever the last rhs! left on the device: in
+    # host mode the resident state is the last STAGE value, post-BC
+    up = collect(Ptr{Float64}, pointer.(StructArrays.components(u)))
+    GC.@preserve u up mft_check(ccall((:mft_upload_state, libmft), Cint, (Ptr{Cvoid}, Ptr{Ptr{Float64}}), ctx.ptr, up))
     mft_check(ccall((:mft_history_push_weights, libmft), Cint, (Ptr{Cvoid}, Float64, Int64, Cint, Ptr{Float64}),
                     ctx.ptr, t, integrator.success_iter, n, time_weights))
 end
@@ -196,7 +230,7 @@ end
 function solve_ssprk33_resident!(u, semi, tspan, dt; approx_order = nothing, time_dependent_bcs = false)
     cache = semi.cache
     ctx = cache.ctx
-    cache.registered[] || register!(cache, semi.mesh, semi.equations, semi.boundary_conditions, semi.source_terms)
+    cache.registered[] || register!(cache, semi.mesh, semi.equations, semi.boundary_conditions, semi.source_terms, first(tspan))
     time_dependent_bcs && refresh_dirichlet!(cache, semi.mesh, semi.equations, semi.boundary_conditions, first(tspan))
     up = collect(Ptr{Float64}, pointer.(StructArrays.components(u)))
     GC.@preserve u up mft_check(ccall((:mft_upload_state, libmft), Cint, (Ptr{Cvoid}, Ptr{Ptr{Float64}}), ctx.ptr, up))
