@@ -460,42 +460,60 @@ def cpu_baseline(semi, domain, u, m, budget_s=15.0, residual=True):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU path.  The reference is pure Julia and Julia is not in this image,
-    so the oracle's C port of its execution structure is timed (kind = "port"), single-threaded like the reference."""
+    """--impl reference: the reference's own CPU path on this box's host cores.  The reference is pure Julia and Julia is not
+    in this image, so the oracle's C port of its execution structure is timed (kind = "port"),
+    single-threaded like the reference's hot loops (serial CSC SpMVs).  Same config as the GPU arm at N = 1: the full
+    1,052,672-point cloud in the same numbering, Euler + residual viscosity, SSPRK33 with the HistoryCallback.  Nothing of the
+    product's shared library is used: cloud numbering, kNN and weights come from oracle/ (bench_setup.py, mft_oracle.py)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import mft_b200 as m
-
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bench_setup as bs
     import mft_oracle as orc
 
+    cm = bs.cloud_module()
     nx = ny = args.ref_n_side
-    cl, basis, _ = build_workload(nx, ny, 0, m)
-    nb, dx_min, dx_avg = m.setup_ops.knn(cl.points, K_STENCIL)
-    ops = m.setup_ops.compute_flux_operator(cl.points, nb, 3, 3)
-    ic = vortex_ic(m, (5.0, 5.0 * ny / nx))
-    obc = [orc.OracleBC(orc.BC_DIRICHLET, cl.boundary_idxs[g], cl.boundary_normals[g],
-                        values=np.ascontiguousarray(ic(cl.points[cl.boundary_idxs[g]], 0.0))) for g in range(4)]
-    src = orc.source_residual(dx_avg, polydeg=3)
-    src.success_iter = 5
+    t_setup = time.time()
+    cl = cm.jittered_lattice(nx, ny, 10.0, 10.0 * ny / nx, seed=0)
+    if CLOUD_ORDER == "hilbert":
+        cl = cm.reorder(cl, bs.hilbert_order(cl.points))
+    nb, dx_min, dx_avg = orc.point_data(cl.points, K_STENCIL)
+    ops = bs.flux_operator_batched(cl.points, nb, 3, 3)
+    residual = args.source == "residual"
+    if args.workload == "sod":
+        ic = lambda x, t: cm.sod(x, GAMMA, x_mid=5.0)   # noqa: E731
+        kinds = [orc.BC_DIRICHLET, orc.BC_DIRICHLET, orc.BC_SLIP_WALL, orc.BC_SLIP_WALL]
+    else:
+        ic = lambda x, t: cm.isentropic_vortex(x, GAMMA, center=(5.0, 5.0 * ny / nx))   # noqa: E731
+        kinds = [orc.BC_DIRICHLET] * 4
+    obc = [orc.OracleBC(kinds[g], cl.boundary_idxs[g], cl.boundary_normals[g],
+                        values=np.ascontiguousarray(ic(cl.points[cl.boundary_idxs[g]], 0.0)) if kinds[g] == orc.BC_DIRICHLET else None)
+           for g in range(4)]
+    src = orc.source_residual(dx_avg, polydeg=3) if residual else orc.source_upwind(dx_avg)
     P = orc.OracleProblem(cl.points, 4, orc.EQ_EULER2D, [GAMMA], ops[0], ops[1], obc, [src])
     N = cl.points.shape[0]
     u = np.ascontiguousarray(ic(cl.points, 0.0))
     lib = orc.lib()
-    dt = 0.1 * dx_min / 8.0
+    dt = 0.1 * dx_min / (8.0 if args.workload == "vortex" else 3.0)
     n_el = u.size
+    t_setup = time.time() - t_setup
+    state = {"t": 0.0, "it": 0, "k": None}
+    if residual:
+        P.history_callback(u, 0.0, 0, 3)          # initialize!  history.jl:51-54
+    state["k"] = P.rhs(u, 0.0)                    # FSAL: k = f(u_0)
 
     def step():
-        # one SSPRK33 step of the CPU path: 3 rhs! + 3 stage updates
-        nonlocal u
+        # one SSPRK33 step of the CPU path, OrdinaryDiffEq's FSAL structure: 3 rhs! + 3 stage updates + the history callback
+        t, k = state["t"], state["k"]
         uprev = u.copy()
-        k = P.rhs(u, 0.0)
-        for s in (1, 2, 3):
-            lib.orc_ssprk33_stage(C.c_int64(n_el), s, C.c_double(dt), C.c_void_p(uprev.ctypes.data),
+        for s_, ts in ((1, t + dt), (2, t + dt / 2), (3, t + dt)):
+            lib.orc_ssprk33_stage(C.c_int64(n_el), s_, C.c_double(dt), C.c_void_p(uprev.ctypes.data),
                                   C.c_void_p(k.ctypes.data), C.c_void_p(u.ctypes.data))
-            if s < 3:
-                k = P.rhs(u, 0.0)
+            k = P.rhs(u, ts)
+        state["t"], state["it"], state["k"] = t + dt, state["it"] + 1, k
+        if residual:
+            P.history_callback(u, state["t"], state["it"], 3)
 
     for _ in range(args.warmup):
         step()
@@ -503,33 +521,30 @@ def run_reference(args):
     for _ in range(args.steps):
         step()
     el = time.perf_counter() - t0
+    if not np.isfinite(u).all():
+        raise SystemExit("bench --impl reference: non-finite state")
     value = N * STAGES * args.steps / el
-    # informational: what a restructured CPU implementation reaches on all host cores (SURVEY.md 8(d) variant ii); the line's
-    # value stays the reference's own single-threaded structure
-    try:
-        bidx = np.concatenate([cl.boundary_idxs[g] for g in range(4)])
-        bvals = np.concatenate([np.asarray(ic(cl.points[cl.boundary_idxs[g]], 0.0)) for g in range(4)], axis=1)
-        F = orc.FastCpuProblem(ops[0], ops[1], GAMMA, dx_avg, bidx, bvals, success_iter=5)
-        uu = np.ascontiguousarray(ic(cl.points, 0.0))
-        F.rhs(uu, reps=2)
-        t0 = time.perf_counter()
-        reps = 30
-        F.rhs(uu, reps=reps)
-        best = {"value": N * reps / (time.perf_counter() - t0), "unit": UNIT, "cores": int(orc.fast_lib().fast_max_threads()),
-                "kind": "port", "sample": f"{reps} rhs! evaluations, fused row-parallel CPU kernel (oracle/mft_cpu_fast.c), all host cores"}
-    except Exception as exc:   # a report, never a gate
-        best = {"unavailable": repr(exc)}
+    same = (nx == args.n_side) and args.gpus == 1
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "BASELINE configs[1]: 2D Euler isentropic vortex + residual viscosity, jittered cloud, "
-                                  f"PHS3 deg3 k=20, SSPRK33; CPU arm runs a bounded {N}-point sample ({nx}x{ny} + ring) "
-                                  "of the same generator", "points": N, "k": K_STENCIL, "stages_per_step": STAGES},
+           "config": {"workload": (f"BASELINE configs[1]: 2D Euler isentropic vortex + residual viscosity, {N}-point "
+                                   f"jittered cloud ({nx}x{ny} + ring), PHS3 deg3 k=20, SSPRK33 + HistoryCallback(3)")
+                      if (args.workload, args.source) == ("vortex", "residual") else
+                      f"2D Euler {args.workload} + {args.source} viscosity, {N}-point jittered cloud ({nx}x{ny} + ring), PHS3 deg3 k=20, SSPRK33",
+                      "points": N, "k": K_STENCIL, "stages_per_step": STAGES, "setup_s": round(t_setup, 1),
+                      "same_config_as_gpu_arm": bool(same),
+                      "note": None if same else "CPU arm runs the N = 1 cloud (throughput metric; the N-GPU arm's cloud is N times larger)"},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                            "sample": f"{args.steps} SSPRK33 steps (3 rhs! each) on a {N}-point cloud; C port of "
-                                      "the reference's serial structure (Julia is not installed; the reference's hot "
-                                      "loops are single-threaded)", "best_effort": best},
+                            "sample": f"{args.steps} SSPRK33 steps (3 rhs! + history callback each) on the full {N}-point cloud; C port of "
+                                      "the reference's serial structure (oracle/mft_oracle.c; Julia is not installed; the reference's hot "
+                                      "loops are single-threaded)"},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    try:   # the repo's own shared objects this process has mapped: oracle/ only (the product library is not on this path)
+        libs = sorted({ln.split()[-1] for ln in open("/proc/self/maps") if ROOT in ln and ".so" in ln})
+        out["repo_native_libs"] = [os.path.relpath(p_, ROOT) for p_ in libs]
+    except Exception:
+        pass
     print(json.dumps(out))
 
 
@@ -540,7 +555,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-side", type=int, default=1024, help="lattice side; 1024 -> the 1M-point cloud of configs[1]")
-    ap.add_argument("--ref-n-side", type=int, default=512, help="lattice side of the bounded sample the CPU arm runs")
+    ap.add_argument("--ref-n-side", type=int, default=1024, help="lattice side of the cloud the CPU arm runs (1024: the full configs[1] cloud)")
     ap.add_argument("--fma", action="store_true", help="single-sweep FMA summation instead of the reference order")
     ap.add_argument("--stage-weights", type=int, default=5, help="bit0: pass A slices staged in smem, bit1: pass B, bit2: one weight buffer refilled between the x and y sweeps")
     ap.add_argument("--graph", type=int, default=1, help="0 eager, 1 CUDA-graph replay on one GPU, 2 also multi-rank")

@@ -84,28 +84,37 @@ __device__ __forceinline__ void lex_side_update(double *wr, bool valid, double r
         tied = __ballot_sync(kFull, ((tied >> lane) & 1u) && (!(m1 < m1max) || !(m1 > m1min)));
         if (tied == 0) return;
     }
+    // Level 1 first: only the lanes that hold the largest or the smallest m1 of the tie set can be a leaf (leaves with bit 0
+    // clear maximise m1, the others minimise it).  On noisy plateaus (rho ties exactly, the momenta carry rounding noise) each
+    // of the two groups is a single lane and no deeper reduction is needed.
     const bool in = (tied >> lane) & 1u;
-    const int first = __ffs(tied) - 1;
-    const double r1 = __shfl_sync(kFull, m1, first), r2 = __shfl_sync(kFull, m2, first), r3 = __shfl_sync(kFull, E, first);
-    double l1 = r1, l2 = r2, l3 = r3;   // leaf `lane` of the tie set (lanes 0..7)
-    if (__ballot_sync(kFull, in && (m1 != r1 || m2 != r2 || E != r3)) != 0) {
-        // several different states tie on rho: nested extremes per sign pattern
-#pragma unroll 1
-        for (int lf = 0; lf < 8; ++lf) {
-            unsigned set = tied;
-            double c[3];
-            const double val[3] = {m1, m2, E};
+    const double g1max = warp_extreme<false>(in ? m1 : neg_inf()), g1min = warp_extreme<true>(in ? m1 : pos_inf());
+    double l1 = 0.0, l2 = 0.0, l3 = 0.0;   // leaf `lane` of the tie set (lanes 0..7)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const bool mn = (lf >> k) & 1;
-                const bool ins = (set >> lane) & 1u;
-                c[k] = mn ? warp_extreme<true>(ins ? val[k] : pos_inf()) : warp_extreme<false>(ins ? val[k] : neg_inf());
-                set = __ballot_sync(kFull, ins && val[k] == c[k]);
-            }
-            if (lane == lf) {
-                l1 = c[0];
-                l2 = c[1];
-                l3 = c[2];
+    for (int half = 0; half < 2; ++half) {   // half 0: leaves 0,2,4,6 (max m1); half 1: leaves 1,3,5,7 (min m1)
+        const double g1 = half == 0 ? g1max : g1min;
+        const unsigned grp = __ballot_sync(kFull, in && m1 == g1);
+        const bool ing = (grp >> lane) & 1u;
+        const int first = __ffs(grp) - 1;
+        const double r2 = __shfl_sync(kFull, m2, first), r3 = __shfl_sync(kFull, E, first);
+        const bool mine = lane < 8 && (lane & 1) == half;
+        if (mine) {
+            l1 = g1;
+            l2 = r2;
+            l3 = r3;
+        }
+        if (__ballot_sync(kFull, ing && (m2 != r2 || E != r3)) != 0) {
+            // several different states share rho and m1: nested extremes of (m2, E) per sign pattern
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {   // leaf = half | q << 1: bit 1 = minimise m2, bit 2 = minimise E
+                const bool mn2 = q & 1, mn3 = (q >> 1) & 1;
+                const double c2 = mn2 ? warp_extreme<true>(ing ? m2 : pos_inf()) : warp_extreme<false>(ing ? m2 : neg_inf());
+                const bool in2 = ing && m2 == c2;
+                const double c3 = mn3 ? warp_extreme<true>(in2 ? E : pos_inf()) : warp_extreme<false>(in2 ? E : neg_inf());
+                if (lane == (half | (q << 1))) {
+                    l2 = c2;
+                    l3 = c3;
+                }
             }
         }
     }
@@ -218,10 +227,28 @@ struct StageArgs {
 };
 constexpr int kStatsRaw = 16;   // stats[16..19]: norms before the zero replacement
 
-template <bool NORMS, bool MULTI>
-__global__ void __launch_bounds__(256, 3) k_stage_fused(const StageArgs A)
+// 256-bit row loads / in-place row stores as volatile asm: their program order is kept, which is what lets the loop below
+// issue the loads of the NEXT row before the stores of the current one (the compiler cannot prove u[i + stride] != u[i])
+__device__ __forceinline__ Vec<4> ld_row(const Vec<4> *p)
+{
+    Vec<4> v;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a[0]), "=d"(v.a[1]), "=d"(v.a[2]), "=d"(v.a[3]) : "l"(p));
+    return v;
+}
+
+constexpr int NORMS_NONE = 0, NORMS_LEX = 1, NORMS_COMP = 2;
+
+// resident blocks per SM the compiler must allow (2: 128 registers, no spills with two rows in flight per thread)
+#ifndef MFT_STAGE_OCC
+#define MFT_STAGE_OCC 2
+#endif
+
+// grid = ctx red_blocks x 256 threads, the grid of k_sum_mean: same rows per thread and same reduction tree => same sums
+template <int NMODE, bool MULTI>
+__global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageArgs A)
 {
     constexpr int V = 4;
+    constexpr bool NORMS = NMODE != NORMS_NONE;
     __shared__ double wrec[8][kRecDoubles];
     __shared__ double sh[8][V];
     __shared__ bool is_last;
@@ -242,27 +269,48 @@ __global__ void __launch_bounds__(256, 3) k_stage_fused(const StageArgs A)
         }
     }
     double s[V] = {0.0, 0.0, 0.0, 0.0};
-    double cmx[V], cmn[V];
+    double cmx[NMODE == NORMS_COMP ? V : 1], cmn[NMODE == NORMS_COMP ? V : 1];
+    if constexpr (NMODE == NORMS_COMP) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        cmx[v] = neg_inf();
-        cmn[v] = pos_inf();
+        for (int v = 0; v < V; ++v) {
+            cmx[v] = neg_inf();
+            cmn[v] = pos_inf();
+        }
     }
     double run_max = neg_inf(), run_min = pos_inf();
-    if (NORMS && lane < 2) wrec[w][kRecExt + lane] = lane == 0 ? neg_inf() : pos_inf();
+    if (NMODE == NORMS_LEX && lane < 2) wrec[w][kRecExt + lane] = lane == 0 ? neg_inf() : pos_inf();
     __syncwarp();
     const double dt = A.dt, dt2 = 2.0 * A.dt;
+    const int stage = A.stage;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t nround = (A.n + 31) & ~(int64_t)31;   // whole warps stay in the loop (warp-wide reductions inside)
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    // software pipeline: the operands of the next row are in flight while the current row is processed
+    struct RowIn {
+        Vec<V> k, uo, up;
+        int ax;
+    };
+    auto fetch = [&](int64_t i, RowIn &r) {
+        r.ax = -1;
+        if (i < A.n) {
+            if (A.aux) r.ax = __ldg(A.aux + i);
+            r.k = ld_row(du + i);
+            r.uo = ld_row(u + i);
+            if (stage != 1) r.up = ld_row(uprev + i);
+        }
+    };
+    RowIn cur, nxt;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nround) fetch(i, cur);
+    for (; i < nround; i += stride) {
+        if (i + stride < nround) fetch(i + stride, nxt);
         const bool valid = i < A.n;
         Vec<V> un;
 #pragma unroll
         for (int v = 0; v < V; ++v) un.a[v] = 0.0;
         if (valid) {
-            const int ax = A.aux ? __ldg(A.aux + i) : -1;
-            Vec<V> k = du[i];
-            Vec<V> uo = u[i];
+            const int ax = cur.ax;
+            Vec<V> k = cur.k;
+            Vec<V> uo = cur.uo;
             int bcj = -1, kind = -1;
             RowAux ra{-1, 0, 0};
             if (ax >= 0) {
@@ -291,13 +339,13 @@ __global__ void __launch_bounds__(256, 3) k_stage_fused(const StageArgs A)
                 }
                 st_vec(du + i, k);
             }
-            if (A.stage == 1) {
+            if (stage == 1) {
                 st_vec(uprev + i, uo);
 #pragma unroll
                 for (int v = 0; v < V; ++v) un.a[v] = fma(dt, k.a[v], uo.a[v]);
             } else {
-                const Vec<V> up = uprev[i];
-                if (A.stage == 2) {
+                const Vec<V> up = cur.up;
+                if (stage == 2) {
 #pragma unroll
                     for (int v = 0; v < V; ++v) un.a[v] = fma(dt, k.a[v], fma(3.0, up.a[v], uo.a[v])) / 4.0;
                 } else {
@@ -324,7 +372,7 @@ __global__ void __launch_bounds__(256, 3) k_stage_fused(const StageArgs A)
 #pragma unroll
                 for (int v = 0; v < V; ++v) s[v] += un.a[v];
             }
-            if (A.lex) {
+            if constexpr (NMODE == NORMS_LEX) {
                 lex_side_update<0>(wrec[w], valid, un.a[0], un.a[1], un.a[2], un.a[3], run_max, lane);
                 lex_side_update<1>(wrec[w], valid, un.a[0], un.a[1], un.a[2], un.a[3], run_min, lane);
             } else if (valid) {
@@ -335,6 +383,7 @@ __global__ void __launch_bounds__(256, 3) k_stage_fused(const StageArgs A)
                 }
             }
         }
+        cur = nxt;
     }
     if constexpr (!NORMS && !MULTI) return;
 
@@ -346,7 +395,7 @@ __global__ void __launch_bounds__(256, 3) k_stage_fused(const StageArgs A)
             for (int o = 16; o > 0; o >>= 1) s[v] += __shfl_down_sync(kFull, s[v], o);
         if (lane == 0)
             for (int v = 0; v < V; ++v) sh[w][v] = s[v];
-        if (!A.lex) {
+        if constexpr (NMODE == NORMS_COMP) {
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 cmx[v] = warp_extreme<false>(cmx[v]);
@@ -369,7 +418,7 @@ __global__ void __launch_bounds__(256, 3) k_stage_fused(const StageArgs A)
                 prec[kRecSum + v] = t;
             }
         }
-        if (A.lex) {
+        if constexpr (NMODE == NORMS_LEX) {
             if (threadIdx.x < 16) {
                 const int slot = threadIdx.x, side = slot >> 3, lf = slot & 7;
                 double bext = side == 0 ? neg_inf() : pos_inf(), b1 = 0.0, b2 = 0.0, b3 = 0.0;
@@ -426,14 +475,25 @@ __global__ void __launch_bounds__(256, 3) k_stage_fused(const StageArgs A)
                 fin[kRecSum + v] = t;
             }
         }
-        if (A.lex) {
+        if constexpr (NMODE == NORMS_LEX) {
             // thread = (j, slot): slot = side*8 + leaf scans the block records j, j+16, ...; then the 16 scanners of a slot merge
             const int slot = threadIdx.x & 15, j = threadIdx.x >> 4, side = slot >> 3, lf = slot & 7;
             double bext = side == 0 ? neg_inf() : pos_inf(), b1 = 0.0, b2 = 0.0, b3 = 0.0;
-            for (int b = j; b < nb; b += 16) {
-                const double *R = A.partial + (size_t)b * kRecDoubles;
-                const double *q = R + kRecLeaf + side * 24 + lf * 3;
-                slot_merge(slot, __ldcg(R + kRecExt + side), __ldcg(q), __ldcg(q + 1), __ldcg(q + 2), bext, b1, b2, b3);
+            // (four records' loads in flight per scanner: the chain of merges is short, the L2 round trips are not)
+            for (int b0 = j; b0 < nb; b0 += 64) {
+                double xe[4], x1[4], x2[4], x3[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int b = b0 + 16 * r;
+                    const double *R = A.partial + (size_t)(b < nb ? b : j) * kRecDoubles;
+                    const double *q = R + kRecLeaf + side * 24 + lf * 3;
+                    xe[r] = __ldcg(R + kRecExt + side);
+                    x1[r] = __ldcg(q);
+                    x2[r] = __ldcg(q + 1);
+                    x3[r] = __ldcg(q + 2);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) slot_merge(slot, xe[r], x1[r], x2[r], x3[r], bext, b1, b2, b3);   // (a re-read of record j merges nothing new)
             }
             {   // lanes slot and slot + 16 hold the same slot
                 const double oe = __shfl_xor_sync(kFull, bext, 16), o1 = __shfl_xor_sync(kFull, b1, 16);

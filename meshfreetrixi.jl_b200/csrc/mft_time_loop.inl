@@ -165,13 +165,18 @@ static int launch_stage_fused(mft_ctx *c, int stage, double dt, bool apply_bc2)
     a.route_dst = c->route_dst.p;
     if (multi) a.P = c->peers_dev;
     const int grid = c->red_blocks;
+    const int nmode = !residual ? NORMS_NONE : c->max_lex ? NORMS_LEX : NORMS_COMP;
+#define STAGE_K(NM, MU) k_stage_fused<NM, MU><<<grid, 256, 0, c->stream>>>(a)
     if (multi) {
-        if (residual) k_stage_fused<true, true><<<grid, 256, 0, c->stream>>>(a);
-        else k_stage_fused<false, true><<<grid, 256, 0, c->stream>>>(a);
+        if (nmode == NORMS_LEX) STAGE_K(NORMS_LEX, true);
+        else if (nmode == NORMS_COMP) STAGE_K(NORMS_COMP, true);
+        else STAGE_K(NORMS_NONE, true);
     } else {
-        if (residual) k_stage_fused<true, false><<<grid, 256, 0, c->stream>>>(a);
-        else k_stage_fused<false, false><<<grid, 256, 0, c->stream>>>(a);
+        if (nmode == NORMS_LEX) STAGE_K(NORMS_LEX, false);
+        else if (nmode == NORMS_COMP) STAGE_K(NORMS_COMP, false);
+        else STAGE_K(NORMS_NONE, false);
     }
+#undef STAGE_K
     c->launches++;
     LAUNCH_CHECK();
     return MFT_OK;

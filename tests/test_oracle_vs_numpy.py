@@ -144,3 +144,28 @@ def test_advection_with_flyer_hyperviscosity():
     ua, _ = P.solve_ssprk33(u0, 0.0, dt, 20)
     ub, _ = R.solve_ssprk33(u0, 0.0, dt, 20)
     assert cases.relerr(ua, ub) <= 1e-11
+
+
+def test_batched_setup_of_the_cpu_bench_arm():
+    """oracle/bench_setup.py (setup of `bench.py --impl reference`): the numpy Hilbert numbering equals the product's
+    mft_sfc_order, and the batched weights agree with the oracle's point-by-point compute_flux_operator to rounding"""
+    import bench_setup as bs
+    import mft_oracle as orc
+
+    cm = bs.cloud_module()
+    cl = cm.jittered_lattice(40, 32, 10.0, 8.0, seed=0)
+    perm = bs.hilbert_order(cl.points)
+    assert sorted(perm.tolist()) == list(range(len(cl.points)))
+    try:
+        import mft_b200 as m
+
+        assert np.array_equal(perm, m._lib.sfc_order(cl.points))
+    except OSError:
+        pass   # (the product library is not needed for this test)
+    cl = cm.reorder(cl, perm)
+    nb, dx_min, dx_avg = orc.point_data(cl.points, 20)
+    fast = bs.flux_operator_batched(cl.points, nb, 3, 3)
+    ref = orc.compute_flux_operator(cl.points, nb, 3, 3)
+    for a, b in zip(fast, ref):
+        assert a.nnz == b.nnz and np.array_equal(a.indices, b.indices) and np.array_equal(a.indptr, b.indptr)
+        assert np.abs(a.data - b.data).max() <= 1e-11 * np.abs(b.data).max()
