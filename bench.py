@@ -193,6 +193,13 @@ def run_ours(args):
         from mft_b200 import partition
         comm = partition.TorchComm()
     parity = multi_gpu_parity(m, comm, dist, args, local_rank) if multi and not args.no_parity else None
+    topo = None
+    if multi and rank == 0:   # how the GPUs of this box reach each other (NV# = NVLink lanes; PIX/PXB/NODE/SYS = PCIe only)
+        try:
+            rows = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout.splitlines()
+            topo = [" ".join(r.split()[:world + 1]) for r in rows if r.startswith("GPU")][:world]
+        except Exception:
+            topo = None
     gx, gy = GRID_FOR_GPUS.get(world, (world, 1))
     nx, ny = args.n_side * gx, args.n_side * gy
     cl, basis, _ = build_workload(nx, ny, 0, m)
@@ -381,7 +388,8 @@ def run_ours(args):
                           "l2": "inputs larger than L2 (operators 2 x %.0f MB per GPU streamed every stage)" % (n_own * 20 * k / 1e6),
                           "setup_s": round(t_setup, 1), "setup": args.setup,
                           "layout": {"tile": int(args.tile), "tile_rows": int(args.tile_rows), "refine_order": int(args.refine_order),
-                                     "exchange": args.exchange if multi else None, "fused_step": int(args.fused_step)}},
+                                     "exchange": args.exchange if multi else None, "fused_step": int(args.fused_step)},
+                          "gpu_topology": topo},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "parity": parity, "norm_misses": int(miss[0]),
                # the reference's own (printed, never recorded) metric: PerformanceCallback's performance index
@@ -565,7 +573,7 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=11, help="rows per thread of the tile kernels: units digit pass A, tens digit pass B")
     ap.add_argument("--pair-rows", type=int, default=1, help="row-pair (union stencil) operator layout (bit0: pass B, bit1: pass A)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo exchange mechanism")
-    ap.add_argument("--setup", default="host", choices=["host", "device"],
+    ap.add_argument("--setup", default="device", choices=["host", "device"],
                     help="kNN + RBF-FD weight generation (untimed setup): host numpy/LAPACK, or the GPU pipeline (mft_setup_*)")
     ap.add_argument("--workload", default="vortex", choices=["vortex", "sod"],
                     help="vortex: BASELINE configs[1] (default, the bench line); sod: configs[3] (shock tube, slip/Dirichlet mix)")

@@ -380,7 +380,9 @@ extern "C" int mft_ctx_create(mft_ctx **out, int device, int64_t n_local, int64_
     }
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    c->red_blocks = prop.multiProcessorCount * 4;
+    // one wave of the fused stage kernel (MFT_STAGE_OCC blocks of 256 threads per SM); the separate reduction kernels use the
+    // same grid, so both paths sum in the same order
+    c->red_blocks = prop.multiProcessorCount * MFT_STAGE_OCC;
     CHECK(c->partial.alloc((int64_t)c->red_blocks * kRecDoubles));  // per-block partials: V sums, or one norm record (fused step)
     CHECK(c->stats.alloc(24));  // sum | mean | norms | SSPRK43 error sum | [16..19] raw norms of the fused step
     CHECK(c->ticket.alloc(8));
@@ -767,7 +769,7 @@ extern "C" int mft_add_source(mft_ctx *c, int kind, const double *params, int np
 static int build_row_aux(mft_ctx *c)
 {
     const int64_t nl = c->n_local;
-    std::vector<int> aux((size_t)nl, -1);
+    std::vector<int> aux((size_t)nl + 4, -1);   // (+ padding: the stage kernel copies it in 16-byte multiples)
     std::vector<RowAux> tab;
     auto entry = [&](int row) -> RowAux & {
         if (aux[(size_t)row] < 0) {

@@ -54,15 +54,30 @@ __device__ __forceinline__ bool leaf_better(double a1, double a2, double a3, dou
     return false;
 }
 
-template <bool MIN>
-__device__ __forceinline__ double warp_extreme(double x)
+// order-preserving map double -> uint64 (NaNs excluded by the callers): unsigned order of the keys = numeric order
+__device__ __forceinline__ unsigned long long f64_key(double x)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double y = __shfl_xor_sync(kFull, x, o);
-        x = MIN ? fmin(x, y) : fmax(x, y);
-    }
-    return x;
+    const long long b = __double_as_longlong(x);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000LL));
+}
+__device__ __forceinline__ double key_f64(unsigned long long k)
+{
+    const long long b = (long long)k;
+    return __longlong_as_double(b ^ (((~b) >> 63) | (long long)0x8000000000000000LL));
+}
+// maximum (MIN: minimum) of x over the lanes with `active` set, through two 32-bit REDUX operations on the keys instead of
+// five rounds of 64-bit shuffles + FP64 compares; inactive lanes contribute the neutral key.  All 32 lanes must call it.
+template <bool MIN>
+__device__ __forceinline__ double warp_extreme(double x, bool active)
+{
+    unsigned long long k = f64_key(x);
+    if (MIN) k = ~k;
+    if (!active) k = 0ull;
+    const unsigned hi = __reduce_max_sync(kFull, (unsigned)(k >> 32));
+    const unsigned lo = __reduce_max_sync(kFull, (unsigned)(k >> 32) == hi ? (unsigned)k : 0u);
+    unsigned long long r = ((unsigned long long)hi << 32) | lo;
+    if (MIN) r = ~r;
+    return key_f64(r);
 }
 
 // One chunk of 32 points (one per lane) against the warp's running record `wr` (shared memory), side 0 = max rho,
@@ -70,50 +85,64 @@ __device__ __forceinline__ double warp_extreme(double x)
 template <int SIDE>
 __device__ __forceinline__ void lex_side_update(double *wr, bool valid, double rho, double m1, double m2, double E, double &run_ext, int lane)
 {
-    const bool hot = valid && (SIDE == 0 ? !(rho < run_ext) : !(rho > run_ext));
-    if (__ballot_sync(kFull, hot) == 0) return;   // the common case: nobody reaches the running extreme
-    const double cm = SIDE == 0 ? warp_extreme<false>(hot ? rho : neg_inf()) : warp_extreme<true>(hot ? rho : pos_inf());
-    unsigned tied = __ballot_sync(kFull, hot && rho == cm);
-    if (tied == 0) return;   // only NaNs were "hot"
+    const bool hot = valid && (SIDE == 0 ? rho >= run_ext : rho <= run_ext);   // (a NaN is never hot)
+    const unsigned hm = __ballot_sync(kFull, hot);
+    if (hm == 0) return;   // the common case: nobody reaches the running extreme
+    double cm;
+    unsigned tied;
+    if (__popc(hm) == 1) {   // one candidate: no reduction
+        cm = __shfl_sync(kFull, rho, __ffs(hm) - 1);
+        tied = hm;
+    } else {
+        cm = warp_extreme<SIDE == 1>(rho, hot);
+        tied = __ballot_sync(kFull, hot && rho == cm);
+    }
     const bool reset = SIDE == 0 ? cm > run_ext : cm < run_ext;
-    if (!reset && !(cm == run_ext)) return;
     double *leaf = wr + kRecLeaf + SIDE * 24;
     if (!reset) {
         // same extreme as before: a point only matters if its m1 reaches the running extremes of m1 over the tie set
         const double m1max = leaf[0], m1min = leaf[3];   // leaf 0: maximise m1; leaf 1: minimise m1
-        tied = __ballot_sync(kFull, ((tied >> lane) & 1u) && (!(m1 < m1max) || !(m1 > m1min)));
+        tied = __ballot_sync(kFull, ((tied >> lane) & 1u) && (m1 >= m1max || m1 <= m1min));
         if (tied == 0) return;
     }
-    // Level 1 first: only the lanes that hold the largest or the smallest m1 of the tie set can be a leaf (leaves with bit 0
-    // clear maximise m1, the others minimise it).  On noisy plateaus (rho ties exactly, the momenta carry rounding noise) each
-    // of the two groups is a single lane and no deeper reduction is needed.
-    const bool in = (tied >> lane) & 1u;
-    const double g1max = warp_extreme<false>(in ? m1 : neg_inf()), g1min = warp_extreme<true>(in ? m1 : pos_inf());
-    double l1 = 0.0, l2 = 0.0, l3 = 0.0;   // leaf `lane` of the tie set (lanes 0..7)
+    double l1, l2, l3;   // leaf `lane` of the tie set (lanes 0..7)
+    if (__popc(tied) == 1) {
+        // one point: it is every leaf of the set
+        const int src = __ffs(tied) - 1;
+        l1 = __shfl_sync(kFull, m1, src);
+        l2 = __shfl_sync(kFull, m2, src);
+        l3 = __shfl_sync(kFull, E, src);
+    } else {
+        // Level 1 first: only the lanes that hold the largest or the smallest m1 of the tie set can be a leaf (leaves with bit
+        // 0 clear maximise m1, the others minimise it).  On noisy plateaus (rho ties exactly, the momenta carry rounding noise)
+        // each of the two groups is a single lane and no deeper reduction is needed.
+        const bool in = (tied >> lane) & 1u;
+        const double g1max = warp_extreme<false>(m1, in), g1min = warp_extreme<true>(m1, in);
+        l1 = l2 = l3 = 0.0;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {   // half 0: leaves 0,2,4,6 (max m1); half 1: leaves 1,3,5,7 (min m1)
-        const double g1 = half == 0 ? g1max : g1min;
-        const unsigned grp = __ballot_sync(kFull, in && m1 == g1);
-        const bool ing = (grp >> lane) & 1u;
-        const int first = __ffs(grp) - 1;
-        const double r2 = __shfl_sync(kFull, m2, first), r3 = __shfl_sync(kFull, E, first);
-        const bool mine = lane < 8 && (lane & 1) == half;
-        if (mine) {
-            l1 = g1;
-            l2 = r2;
-            l3 = r3;
-        }
-        if (__ballot_sync(kFull, ing && (m2 != r2 || E != r3)) != 0) {
-            // several different states share rho and m1: nested extremes of (m2, E) per sign pattern
+        for (int half = 0; half < 2; ++half) {   // half 0: leaves 0,2,4,6 (max m1); half 1: leaves 1,3,5,7 (min m1)
+            const double g1 = half == 0 ? g1max : g1min;
+            const unsigned grp = __ballot_sync(kFull, in && m1 == g1);
+            const bool ing = (grp >> lane) & 1u;
+            const int first = __ffs(grp) - 1;
+            const double r2 = __shfl_sync(kFull, m2, first), r3 = __shfl_sync(kFull, E, first);
+            if (lane < 8 && (lane & 1) == half) {
+                l1 = g1;
+                l2 = r2;
+                l3 = r3;
+            }
+            if (__ballot_sync(kFull, ing && (m2 != r2 || E != r3)) != 0) {
+                // several different states share rho and m1: nested extremes of (m2, E) per sign pattern
 #pragma unroll 1
-            for (int q = 0; q < 4; ++q) {   // leaf = half | q << 1: bit 1 = minimise m2, bit 2 = minimise E
-                const bool mn2 = q & 1, mn3 = (q >> 1) & 1;
-                const double c2 = mn2 ? warp_extreme<true>(ing ? m2 : pos_inf()) : warp_extreme<false>(ing ? m2 : neg_inf());
-                const bool in2 = ing && m2 == c2;
-                const double c3 = mn3 ? warp_extreme<true>(in2 ? E : pos_inf()) : warp_extreme<false>(in2 ? E : neg_inf());
-                if (lane == (half | (q << 1))) {
-                    l2 = c2;
-                    l3 = c3;
+                for (int q = 0; q < 4; ++q) {   // leaf = half | q << 1: bit 1 = minimise m2, bit 2 = minimise E
+                    const bool mn2 = q & 1, mn3 = (q >> 1) & 1;
+                    const double c2 = mn2 ? warp_extreme<true>(m2, ing) : warp_extreme<false>(m2, ing);
+                    const bool in2 = ing && m2 == c2;
+                    const double c3 = mn3 ? warp_extreme<true>(E, in2) : warp_extreme<false>(E, in2);
+                    if (lane == (half | (q << 1))) {
+                        l2 = c2;
+                        l3 = c3;
+                    }
                 }
             }
         }
@@ -227,21 +256,18 @@ struct StageArgs {
 };
 constexpr int kStatsRaw = 16;   // stats[16..19]: norms before the zero replacement
 
-// 256-bit row loads / in-place row stores as volatile asm: their program order is kept, which is what lets the loop below
-// issue the loads of the NEXT row before the stores of the current one (the compiler cannot prove u[i + stride] != u[i])
-__device__ __forceinline__ Vec<4> ld_row(const Vec<4> *p)
-{
-    Vec<4> v;
-    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a[0]), "=d"(v.a[1]), "=d"(v.a[2]), "=d"(v.a[3]) : "l"(p));
-    return v;
-}
-
 constexpr int NORMS_NONE = 0, NORMS_LEX = 1, NORMS_COMP = 2;
 
-// resident blocks per SM the compiler must allow (2: 128 registers, no spills with two rows in flight per thread)
+// resident blocks per SM (the grid is one wave of them) and depth of the operand ring in shared memory
 #ifndef MFT_STAGE_OCC
 #define MFT_STAGE_OCC 2
 #endif
+#ifndef MFT_STAGE_DEPTH
+#define MFT_STAGE_DEPTH 4
+#endif
+constexpr int kStageDepth = MFT_STAGE_DEPTH;
+constexpr int kStageSlotBytes = 256 * (3 * 32 + 4);   // du, u, uprev rows + aux of 256 rows
+constexpr int kStageSmemBytes = kStageDepth * kStageSlotBytes;
 
 // grid = ctx red_blocks x 256 threads, the grid of k_sum_mean: same rows per thread and same reduction tree => same sums
 template <int NMODE, bool MULTI>
@@ -283,26 +309,55 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
     const double dt = A.dt, dt2 = 2.0 * A.dt;
     const int stage = A.stage;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t nround = (A.n + 31) & ~(int64_t)31;   // whole warps stay in the loop (warp-wide reductions inside)
-    // software pipeline: the operands of the next row are in flight while the current row is processed
+    // Operand ring: one elected thread streams the block's next row batches (du, u, uprev, aux: 256 consecutive rows each) into
+    // shared memory with bulk-async copies (cp.async.bulk = the 1-D TMA path) kStageDepth batches ahead, completion on an
+    // mbarrier per slot.  The kernel is a pure stream (128 B per row): what bounds it is bytes in flight, and a ring of
+    // 4 x 25 KB per block keeps ~200 KB per SM in flight without a single register.
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    __shared__ uint64_t full[kStageDepth];
+    struct Slot {
+        Vec<V> k[256], uo[256], up[256];
+        int ax[256];
+    };
+    Slot *ring = reinterpret_cast<Slot *>(ring_raw);
+    const int64_t base0 = (int64_t)blockIdx.x * blockDim.x;
+    auto issue = [&](int it) {   // thread 0 only
+        const int64_t base = base0 + (int64_t)it * stride;
+        if (base >= A.n) return;
+        const int slot = it % kStageDepth;
+        const uint32_t nrows = (uint32_t)(A.n - base < 256 ? A.n - base : 256);
+        const uint32_t rb = nrows * 32u, ab = ((nrows * 4u + 15u) / 16u) * 16u;   // (aux is padded to a multiple of 16 bytes)
+        mbar_expect_tx(&full[slot], rb * (stage != 1 ? 3u : 2u) + ab);
+        bulk_g2s(ring[slot].k, du + base, rb, &full[slot]);
+        bulk_g2s(ring[slot].uo, u + base, rb, &full[slot]);
+        if (stage != 1) bulk_g2s(ring[slot].up, uprev + base, rb, &full[slot]);
+        bulk_g2s(ring[slot].ax, A.aux + base, ab, &full[slot]);
+    };
+    if (threadIdx.x == 0) {
+        for (int d = 0; d < kStageDepth; ++d) mbar_init(&full[d], 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int d = 0; d < kStageDepth; ++d) issue(d);
     struct RowIn {
         Vec<V> k, uo, up;
         int ax;
     };
-    auto fetch = [&](int64_t i, RowIn &r) {
-        r.ax = -1;
+    RowIn cur;
+    int it = 0;
+    for (int64_t i = base0 + threadIdx.x; i - threadIdx.x < A.n; i += stride, ++it) {
+        const int slot = it % kStageDepth;
+        mbar_wait(&full[slot], (uint32_t)(it / kStageDepth) & 1u);
+        cur.ax = -1;
         if (i < A.n) {
-            if (A.aux) r.ax = __ldg(A.aux + i);
-            r.k = ld_row(du + i);
-            r.uo = ld_row(u + i);
-            if (stage != 1) r.up = ld_row(uprev + i);
+            cur.k = ring[slot].k[threadIdx.x];
+            cur.uo = ring[slot].uo[threadIdx.x];
+            if (stage != 1) cur.up = ring[slot].up[threadIdx.x];
+            cur.ax = ring[slot].ax[threadIdx.x];
         }
-    };
-    RowIn cur, nxt;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nround) fetch(i, cur);
-    for (; i < nround; i += stride) {
-        if (i + stride < nround) fetch(i + stride, nxt);
+        __syncthreads();   // every thread holds its row in registers: the slot can be refilled
+        if (threadIdx.x == 0) issue(it + kStageDepth);
         const bool valid = i < A.n;
         Vec<V> un;
 #pragma unroll
@@ -383,7 +438,6 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
                 }
             }
         }
-        cur = nxt;
     }
     if constexpr (!NORMS && !MULTI) return;
 
@@ -398,8 +452,8 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
         if constexpr (NMODE == NORMS_COMP) {
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                cmx[v] = warp_extreme<false>(cmx[v]);
-                cmn[v] = warp_extreme<true>(cmn[v]);
+                cmx[v] = warp_extreme<false>(cmx[v], true);
+                cmn[v] = warp_extreme<true>(cmn[v], true);
             }
             if (lane == 0)
                 for (int v = 0; v < V; ++v) {

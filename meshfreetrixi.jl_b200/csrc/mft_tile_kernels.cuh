@@ -398,6 +398,14 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
             }
         }
     }
+    if constexpr (VISC == VISC_RESIDUAL) {
+        // several GPUs: block 0 publishes the merged norms of this stage; the whole warp waits here, converged (the last slice
+        // of a cloud may hold fewer than 32 rows: no warp-level barrier inside the per-row branch below)
+        if (A.norm_merge) {
+            if (lane == 0) spin_until(&A.L->norm_ready, A.L->epoch_n, &A.L->error);
+            __syncwarp();
+        }
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int64_t row = row0 + r;
@@ -410,10 +418,6 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
                 if constexpr (VISC == VISC_RESIDUAL) ad = ld_ro(reinterpret_cast<const Vec<V> *>(A.approx_du) + row);
             }
             if constexpr (VISC == VISC_RESIDUAL) {
-                if (A.norm_merge) {   // block 0 publishes the merged norms: wait for this stage's
-                    if (lane == 0) spin_until(&A.L->norm_ready, A.L->epoch_n, &A.L->error);
-                    __syncwarp();
-                }
                 if (A.stats && A.norm_miss) {
                     // the norms are the lexicographic (or per-component) maximum of |u - mean| over ALL points: check this row
                     double dv[V], raw[V];

@@ -77,7 +77,7 @@ static int history_push_common(mft_ctx *c, double t, int64_t success_iter, bool 
     }
     {
         ScopedTimer tm(c, MFT_K_OTHER);
-        k_approx_du<<<c->red_blocks * 2, 256, 0, c->stream>>>(a);
+        k_approx_du<<<c->red_blocks * 4, 256, 0, c->stream>>>(a);
         c->launches++;
         LAUNCH_CHECK();
     }
@@ -107,7 +107,7 @@ static int launch_stage(mft_ctx *c, int stage, double dt)
     NvtxRange range("SSPRK stage update");
     ScopedTimer tm(c, MFT_K_STAGE);
     const int64_t len = c->n_local * c->V;
-    k_ssprk33_stage<<<c->red_blocks * 2, 256, 0, c->stream>>>(stage, dt, c->uprev.p, c->du.p, c->u.p, len);
+    k_ssprk33_stage<<<c->red_blocks * 4, 256, 0, c->stream>>>(stage, dt, c->uprev.p, c->du.p, c->u.p, len);
     c->launches++;
     LAUNCH_CHECK();
     // stage_limiter!(u, integrator, p, t) after every stage update (OrdinaryDiffEq SSPRK33(stage_limiter!))
@@ -166,7 +166,11 @@ static int launch_stage_fused(mft_ctx *c, int stage, double dt, bool apply_bc2)
     if (multi) a.P = c->peers_dev;
     const int grid = c->red_blocks;
     const int nmode = !residual ? NORMS_NONE : c->max_lex ? NORMS_LEX : NORMS_COMP;
-#define STAGE_K(NM, MU) k_stage_fused<NM, MU><<<grid, 256, 0, c->stream>>>(a)
+#define STAGE_K(NM, MU)                                                            \
+    do {                                                                           \
+        CHECK(ensure_smem(c, k_stage_fused<NM, MU>, kStageSmemBytes));             \
+        k_stage_fused<NM, MU><<<grid, 256, kStageSmemBytes, c->stream>>>(a);       \
+    } while (0)
     if (multi) {
         if (nmode == NORMS_LEX) STAGE_K(NORMS_LEX, true);
         else if (nmode == NORMS_COMP) STAGE_K(NORMS_COMP, true);
@@ -384,7 +388,7 @@ extern "C" int mft_ssprk43_step(mft_ctx *c, double t, double dt, double abstol, 
     // keep f(u_n) and u_n (rhs! also rewrites boundary / halo entries of u) for a possible rejection
     CU(cudaMemcpyAsync(c->kfsal.p, c->du.p, sizeof(double) * len_tot, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemcpyAsync(c->u_save.p, c->u.p, sizeof(double) * len_tot, cudaMemcpyDeviceToDevice, c->stream));
-    const int grid = c->red_blocks * 2;
+    const int grid = c->red_blocks * 4;
     auto stage = [&](int st) -> int {
         ScopedTimer tm(c, MFT_K_STAGE);
         k_ssprk43_stage<<<grid, 256, 0, c->stream>>>(st, dt, c->uprev.p, c->du.p, c->u.p, c->utilde.p, len);

@@ -49,6 +49,9 @@ def main():
     ap.add_argument("--exchange", default="p2p")
     ap.add_argument("--setup", default="host", help="device: every rank builds its kNN tables / weights with the GPU pipeline")
     ap.add_argument("--fused", type=int, default=1, help="0: the separate stage / boundary / norm / put / wait kernels (MFT_OPT_FUSED_STEP = 0)")
+    ap.add_argument("--same-device", type=int, default=0,
+                    help="1: every rank uses cuda:0 (CUDA IPC between processes on ONE GPU; the ranks' kernels are time-sliced): the "
+                         "multi-rank code path on a single-GPU box.  Process group: gloo (NCCL refuses two ranks on one device)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -58,7 +61,9 @@ def main():
     from mft_b200 import partition
 
     rank = int(os.environ["RANK"])
-    if args.mode == "gpu":
+    if args.mode == "gpu" and args.same_device:
+        dist.init_process_group("gloo")
+    elif args.mode == "gpu":
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
         dist.init_process_group("nccl")
     else:
@@ -237,7 +242,7 @@ def main():
         assert args.source == "upwind"
         assert err < 1e-12, err
     else:
-        solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=int(os.environ.get("LOCAL_RANK", rank)),
+        solver = m.PointCloudSolver(basis, engine=m.RBFFDEngineCUDA(device=0 if args.same_device else int(os.environ.get("LOCAL_RANK", rank)),
                                                                     diagnostics=True, exchange=args.exchange, setup=args.setup,
                                                                     fused_step=bool(args.fused)))
         domain = m.ParallelPointCloudDomain(solver, cl, names, comm, wide_halo=args.source == "tominec")

@@ -20,12 +20,12 @@ def _free_port():
     return p
 
 
-def _launch(nproc, mode, source, tmp_path, timeout=600, exchange="p2p", setup="host", fused=1):
-    out = os.path.join(tmp_path, f"res_{mode}_{source}_{exchange}_{setup}_{fused}.json")
+def _launch(nproc, mode, source, tmp_path, timeout=600, exchange="p2p", setup="host", fused=1, same_device=0):
+    out = os.path.join(tmp_path, f"res_{mode}_{source}_{exchange}_{setup}_{fused}_{same_device}.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(cases.ROOT, "tests", "dist_worker.py"), "--mode", mode, "--source", source, "--out", out,
-           "--exchange", exchange, "--setup", setup, "--fused", str(fused)]
+           "--exchange", exchange, "--setup", setup, "--fused", str(fused), "--same-device", str(same_device)]
     env = dict(os.environ, OMP_NUM_THREADS="2")
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
@@ -73,6 +73,20 @@ def _ngpu():
         return mft_b200._lib.load().mft_device_count()
     except Exception:
         return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nproc,source,fused", [(2, "residual", 1), (2, "upwind", 1), (3, "residual", 1), (2, "residual", 0)])
+def test_ranks_sharing_one_gpu_match_serial_oracle(tmp_path, nproc, source, fused):
+    """The multi-rank path on a SINGLE-GPU box: every rank is its own process with its own ctx on cuda:0, the ranks map each
+    other's u / g / flag windows with CUDA IPC exactly as on several GPUs, and the device time-slices their kernels (a kernel
+    that waits for a peer's flag spins until the peer's process gets the GPU).  Same checks as on several GPUs: one rhs! against
+    the serial oracle to 1e-12, 10 SSPRK33 steps with the history callback to 1e-9, halo copies equal the owners' values, no
+    norm misses.  fused = 1: fused stage kernel, band-tile waits and g puts inside pass A / pass B; 0: the separate kernels."""
+    if _ngpu() < 1:
+        pytest.skip("needs a GPU")
+    res = _launch(nproc, "gpu", source, str(tmp_path), timeout=420, exchange="p2p", fused=fused, same_device=1)
+    assert len(res) == nproc and all(r["err"] < 1e-12 and r["err_steps"] < 1e-9 for r in res)
 
 
 @pytest.mark.gpu

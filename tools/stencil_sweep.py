@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--n-side", type=int, default=1024)
     ap.add_argument("--reps", type=int, default=30)
     ap.add_argument("--out", default="")
+    ap.add_argument("--tiles", default="31,0", help="MFT_OPT_TILE values to compare per width: 31 = union-tile kernels (default), 0 = thread-per-row sliced ELL")
     args = ap.parse_args()
     import mft_b200 as m
 
@@ -47,12 +48,13 @@ def main():
         w -= w.mean(axis=2, keepdims=True)               # row sums zero: constants are annihilated
         nbr1 = np.ascontiguousarray(nb + 1)
         res = {"k": k, "points": n}
-        for mode in ("flux_only", "residual_viscosity"):
+        for tile, mode in [(int(t), md) for t in args.tiles.split(",") for md in ("flux_only", "residual_viscosity")]:
             ctx = C.c_void_p()
             L.check(lib.mft_ctx_create(C.byref(ctx), 0, n, 0, 4, 2, k))
             g = np.array([1.4])
             L.check(lib.mft_set_equation(ctx, L.EQ_EULER2D, L.ptr(g), 1))
             L.check(lib.mft_set_permutation(ctx, L.ptr(perm1)))
+            L.check(lib.mft_set_option(ctx, L.OPT_TILE, float(tile)))
             wx, wy = np.ascontiguousarray(w[0]), np.ascontiguousarray(w[1])
             L.check(lib.mft_set_operator_ell(ctx, L.ptr(nbr1), L.ptr(wx), L.ptr(wy)))
             if mode == "residual_viscosity":
@@ -73,9 +75,12 @@ def main():
             per = ms.value / args.reps
             bytes_pt = (20 * k + 64) if mode == "flux_only" else (40 * k + 288)
             gbs = n * bytes_pt / (per * 1e-3) / 1e9
-            res[mode] = {"ms_per_rhs": round(per, 4), "alg_bytes_per_point": bytes_pt, "GBps": round(gbs, 1),
+            res[f"{mode}_tile{tile}"] = {"ms_per_rhs": round(per, 4), "alg_bytes_per_point": bytes_pt, "GBps": round(gbs, 1),
                          "frac_of_measured_peak": round(gbs / peak, 4), "Gpoint_rhs_per_s": round(n / (per * 1e-3) / 1e9, 3)}
             L.check(lib.mft_ctx_destroy(ctx))
+        for md in ("flux_only", "residual_viscosity"):   # which kernel family wins at this width (the selection rule's evidence)
+            best = max((int(t) for t in args.tiles.split(",")), key=lambda t: res[f"{md}_tile{t}"]["GBps"])
+            res[f"{md}_best_tile"] = best
         print(json.dumps(res), flush=True)
         rows.append(res)
     if args.out:
