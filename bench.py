@@ -374,7 +374,7 @@ def run_ours(args):
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
                "config": {"workload": (f"BASELINE configs[1]: 2D Euler isentropic vortex + residual viscosity, {N}-point "
                                        f"jittered cloud ({nx}x{ny} + ring), PHS3 deg3 k=20, SSPRK33 + HistoryCallback(3)")
@@ -581,6 +581,8 @@ def main():
                     help="stabilisation source: residual viscosity + history (configs[1], [3]) or upwind viscosity (configs[2])")
     ap.add_argument("--refine-order", type=int, default=0, help="1: order the rows inside a tile by D' row length (fewer padding steps in pass B)")
     ap.add_argument("--fused-step", type=int, default=1, help="0: separate stage / boundary / norm / halo put / wait kernels (round-1 sequence)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="label of the JSON line: weak (default: --n-side is the per-GPU lattice side) or strong (the caller chose --n-side so that the TOTAL cloud is fixed)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the untimed parity check against the serial oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

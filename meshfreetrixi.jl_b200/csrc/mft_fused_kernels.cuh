@@ -174,52 +174,68 @@ __device__ __forceinline__ void slot_merge(int slot, double ext, double l1, doub
     }
 }
 
-// ode_mean + ode_maximum(|u - mean|) from `nrec` records (one per rank, combined in rank order for the sums).
-// Executed by ONE thread.  Writes mean[4], norms[4] (zero -> eps) and raw[4] (before the zero replacement: what pass A
-// verifies rows against).  VOL: the records were written by other GPUs -- read them past L1.
+// ode_mean + ode_maximum(|u - mean|) from `nrec` records (one per rank; the sums are combined in rank order), by ONE WARP:
+// lanes 0..3 form the means, lanes 0..15 each merge one (side, leaf) slot over the ranks and evaluate its deviation vector,
+// a shuffle tree takes the lexicographic maximum.  Writes mean[4], norms[4] (zero -> eps) and raw[4] (before the zero
+// replacement: what pass A verifies rows against).  VOL: the records were written by other GPUs -- read them past L1.
 template <bool VOL>
-__device__ inline void norms_from_records(const double *recs, int stride, int nrec, double divisor, int lex, double *mean_out, double *norms_out, double *raw_out)
+__device__ inline void norms_from_records(const double *recs, int stride, int nrec, double divisor, int lex, double *mean_out, double *norms_out, double *raw_out, int lane)
 {
     auto ld = [](const double *p) -> double { return VOL ? __ldcv(p) : *p; };
+    double mv = 0.0;
+    if (lane < 4) {
+        double t = ld(recs + kRecSum + lane);
+        for (int r = 1; r < nrec; ++r) t += ld(recs + (size_t)r * stride + kRecSum + lane);
+        mv = t / divisor;
+        if (mean_out) mean_out[lane] = mv;
+    }
     double m[4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        double t = ld(recs + kRecSum + v);
-        for (int r = 1; r < nrec; ++r) t += ld(recs + (size_t)r * stride + kRecSum + v);
-        m[v] = t / divisor;
-        if (mean_out) mean_out[v] = m[v];
-    }
-    double best[4] = {-1.0, -1.0, -1.0, -1.0};
+    for (int v = 0; v < 4; ++v) m[v] = __shfl_sync(kFull, mv, v);
+    double c[4] = {-1.0, -1.0, -1.0, -1.0};
     if (lex) {
-        for (int r = 0; r < nrec; ++r) {
-            const double *R = recs + (size_t)r * stride;
-            for (int side = 0; side < 2; ++side) {
-                const double ext = ld(R + kRecExt + side);
-                if (!(ext > neg_inf() && ext < pos_inf())) continue;   // empty record (no owned rows) or non-finite
-                for (int lf = 0; lf < 8; ++lf) {
-                    const double *q = R + kRecLeaf + side * 24 + lf * 3;
-                    const double c[4] = {fabs(ext - m[0]), fabs(ld(q) - m[1]), fabs(ld(q + 1) - m[2]), fabs(ld(q + 2) - m[3])};
-                    if (lex_less<4>(best, c)) {
+        if (lane < 16) {
+            const int side = lane >> 3, lf = lane & 7;
+            double bext = side == 0 ? neg_inf() : pos_inf(), b1 = 0.0, b2 = 0.0, b3 = 0.0;
+            for (int r = 0; r < nrec; ++r) {
+                const double *R = recs + (size_t)r * stride;
+                const double *q = R + kRecLeaf + side * 24 + lf * 3;
+                slot_merge(lane, ld(R + kRecExt + side), ld(q), ld(q + 1), ld(q + 2), bext, b1, b2, b3);
+            }
+            if (bext > neg_inf() && bext < pos_inf()) {   // (no owned rows anywhere, or a non-finite state: no candidate)
+                c[0] = fabs(bext - m[0]);
+                c[1] = fabs(b1 - m[1]);
+                c[2] = fabs(b2 - m[2]);
+                c[3] = fabs(b3 - m[3]);
+            }
+        }
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) best[v] = c[v];
-                    }
-                }
+        for (int o = 16; o > 0; o >>= 1) {
+            double d[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) d[v] = __shfl_xor_sync(kFull, c[v], o);
+            if (lex_less<4>(c, d)) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) c[v] = d[v];
             }
         }
     } else {
-        for (int r = 0; r < nrec; ++r) {
-            const double *R = recs + (size_t)r * stride;
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                best[v] = jl_max(best[v], fabs(ld(R + kRecCmax + v) - m[v]));
-                best[v] = jl_max(best[v], fabs(ld(R + kRecCmin + v) - m[v]));
+        double b = -1.0;
+        if (lane < 4)
+            for (int r = 0; r < nrec; ++r) {
+                const double *R = recs + (size_t)r * stride;
+                b = jl_max(b, fabs(ld(R + kRecCmax + lane) - mv));
+                b = jl_max(b, fabs(ld(R + kRecCmin + lane) - mv));
             }
-        }
-    }
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        if (raw_out) raw_out[v] = best[v];
-        norms_out[v] = best[v] == 0.0 ? kEps : best[v];
+        for (int v = 0; v < 4; ++v) c[v] = __shfl_sync(kFull, b, v);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            if (raw_out) raw_out[v] = c[v];
+            norms_out[v] = c[v] == 0.0 ? kEps : c[v];
+        }
     }
 }
 
@@ -266,7 +282,7 @@ constexpr int NORMS_NONE = 0, NORMS_LEX = 1, NORMS_COMP = 2;
 #define MFT_STAGE_DEPTH 4
 #endif
 constexpr int kStageDepth = MFT_STAGE_DEPTH;
-constexpr int kStageSlotBytes = 256 * (3 * 32 + 4);   // du, u, uprev rows + aux of 256 rows
+constexpr int kStageSlotBytes = 256 * (3 * 32 + 4);   // per ring stage and block: du, u, uprev rows + aux of 8 warps x 32 rows
 constexpr int kStageSmemBytes = kStageDepth * kStageSlotBytes;
 
 // grid = ctx red_blocks x 256 threads, the grid of k_sum_mean: same rows per thread and same reduction tree => same sums
@@ -309,36 +325,37 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
     const double dt = A.dt, dt2 = 2.0 * A.dt;
     const int stage = A.stage;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    // Operand ring: one elected thread streams the block's next row batches (du, u, uprev, aux: 256 consecutive rows each) into
-    // shared memory with bulk-async copies (cp.async.bulk = the 1-D TMA path) kStageDepth batches ahead, completion on an
-    // mbarrier per slot.  The kernel is a pure stream (128 B per row): what bounds it is bytes in flight, and a ring of
-    // 4 x 25 KB per block keeps ~200 KB per SM in flight without a single register.
+    // Operand rings: every warp streams ITS next row batches (du, u, uprev, aux of 32 consecutive rows) into shared memory with
+    // bulk-async copies (cp.async.bulk = the 1-D TMA path) kStageDepth batches ahead, completion on an mbarrier per (warp,
+    // slot); no block-level barrier in the loop.  The kernel is a pure stream (128 B per row): what bounds it is bytes in
+    // flight, and 8 warps x 4 slots x 3.2 KB per block keep ~200 KB per SM in flight without a single register.
     extern __shared__ __align__(128) unsigned char ring_raw[];
-    __shared__ uint64_t full[kStageDepth];
+    __shared__ uint64_t full[8][kStageDepth];
     struct Slot {
-        Vec<V> k[256], uo[256], up[256];
-        int ax[256];
+        Vec<V> k[32], uo[32], up[32];
+        int ax[32];
     };
-    Slot *ring = reinterpret_cast<Slot *>(ring_raw);
-    const int64_t base0 = (int64_t)blockIdx.x * blockDim.x;
-    auto issue = [&](int it) {   // thread 0 only
+    static_assert(sizeof(Slot) * 8 * kStageDepth == kStageSmemBytes, "ring size");
+    Slot *ring = reinterpret_cast<Slot *>(ring_raw) + (size_t)w * kStageDepth;
+    const int64_t base0 = (int64_t)blockIdx.x * blockDim.x + (int64_t)w * 32;
+    auto issue = [&](int it) {   // lane 0 only
         const int64_t base = base0 + (int64_t)it * stride;
         if (base >= A.n) return;
         const int slot = it % kStageDepth;
-        const uint32_t nrows = (uint32_t)(A.n - base < 256 ? A.n - base : 256);
+        const uint32_t nrows = (uint32_t)(A.n - base < 32 ? A.n - base : 32);
         const uint32_t rb = nrows * 32u, ab = ((nrows * 4u + 15u) / 16u) * 16u;   // (aux is padded to a multiple of 16 bytes)
-        mbar_expect_tx(&full[slot], rb * (stage != 1 ? 3u : 2u) + ab);
-        bulk_g2s(ring[slot].k, du + base, rb, &full[slot]);
-        bulk_g2s(ring[slot].uo, u + base, rb, &full[slot]);
-        if (stage != 1) bulk_g2s(ring[slot].up, uprev + base, rb, &full[slot]);
-        bulk_g2s(ring[slot].ax, A.aux + base, ab, &full[slot]);
+        mbar_expect_tx(&full[w][slot], rb * (stage != 1 ? 3u : 2u) + ab);
+        bulk_g2s(ring[slot].k, du + base, rb, &full[w][slot]);
+        bulk_g2s(ring[slot].uo, u + base, rb, &full[w][slot]);
+        if (stage != 1) bulk_g2s(ring[slot].up, uprev + base, rb, &full[w][slot]);
+        bulk_g2s(ring[slot].ax, A.aux + base, ab, &full[w][slot]);
     };
-    if (threadIdx.x == 0) {
-        for (int d = 0; d < kStageDepth; ++d) mbar_init(&full[d], 1);
+    if (lane == 0) {
+        for (int d = 0; d < kStageDepth; ++d) mbar_init(&full[w][d], 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads();
-    if (threadIdx.x == 0)
+    __syncwarp();
+    if (lane == 0)
         for (int d = 0; d < kStageDepth; ++d) issue(d);
     struct RowIn {
         Vec<V> k, uo, up;
@@ -346,18 +363,18 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
     };
     RowIn cur;
     int it = 0;
-    for (int64_t i = base0 + threadIdx.x; i - threadIdx.x < A.n; i += stride, ++it) {
+    for (int64_t i = base0 + lane; i - lane < A.n; i += stride, ++it) {
         const int slot = it % kStageDepth;
-        mbar_wait(&full[slot], (uint32_t)(it / kStageDepth) & 1u);
+        mbar_wait(&full[w][slot], (uint32_t)(it / kStageDepth) & 1u);
         cur.ax = -1;
         if (i < A.n) {
-            cur.k = ring[slot].k[threadIdx.x];
-            cur.uo = ring[slot].uo[threadIdx.x];
-            if (stage != 1) cur.up = ring[slot].up[threadIdx.x];
-            cur.ax = ring[slot].ax[threadIdx.x];
+            cur.k = ring[slot].k[lane];
+            cur.uo = ring[slot].uo[lane];
+            if (stage != 1) cur.up = ring[slot].up[lane];
+            cur.ax = ring[slot].ax[lane];
         }
-        __syncthreads();   // every thread holds its row in registers: the slot can be refilled
-        if (threadIdx.x == 0) issue(it + kStageDepth);
+        __syncwarp();   // every lane holds its row in registers: the slot can be refilled
+        if (lane == 0) issue(it + kStageDepth);
         const bool valid = i < A.n;
         Vec<V> un;
 #pragma unroll
@@ -533,11 +550,11 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
             // thread = (j, slot): slot = side*8 + leaf scans the block records j, j+16, ...; then the 16 scanners of a slot merge
             const int slot = threadIdx.x & 15, j = threadIdx.x >> 4, side = slot >> 3, lf = slot & 7;
             double bext = side == 0 ? neg_inf() : pos_inf(), b1 = 0.0, b2 = 0.0, b3 = 0.0;
-            // (four records' loads in flight per scanner: the chain of merges is short, the L2 round trips are not)
-            for (int b0 = j; b0 < nb; b0 += 64) {
-                double xe[4], x1[4], x2[4], x3[4];
+            // (eight records' loads in flight per scanner: the chain of merges is short, the L2 round trips are not)
+            for (int b0 = j; b0 < nb; b0 += 128) {
+                double xe[8], x1[8], x2[8], x3[8];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                for (int r = 0; r < 8; ++r) {
                     const int b = b0 + 16 * r;
                     const double *R = A.partial + (size_t)(b < nb ? b : j) * kRecDoubles;
                     const double *q = R + kRecLeaf + side * 24 + lf * 3;
@@ -547,7 +564,7 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
                     x3[r] = __ldcg(q + 2);
                 }
 #pragma unroll
-                for (int r = 0; r < 4; ++r) slot_merge(slot, xe[r], x1[r], x2[r], x3[r], bext, b1, b2, b3);   // (a re-read of record j merges nothing new)
+                for (int r = 0; r < 8; ++r) slot_merge(slot, xe[r], x1[r], x2[r], x3[r], bext, b1, b2, b3);   // (a re-read of record j merges nothing new)
             }
             {   // lanes slot and slot + 16 hold the same slot
                 const double oe = __shfl_xor_sync(kFull, bext, 16), o1 = __shfl_xor_sync(kFull, b1, 16);
@@ -603,10 +620,10 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
             *A.ticket = 0;
         }
     } else {
-        if (threadIdx.x == 0) {
-            for (int v = 0; v < V; ++v) A.stats[v] = fin[kRecSum + v];
-            norms_from_records<false>(fin, kRecDoubles, 1, A.divisor, A.lex, A.stats + V, A.stats + 2 * V, A.stats + kStatsRaw);
-            *A.ticket = 0;
+        if (w == 0) {
+            if (lane < V) A.stats[lane] = fin[kRecSum + lane];
+            norms_from_records<false>(fin, kRecDoubles, 1, A.divisor, A.lex, A.stats + V, A.stats + 2 * V, A.stats + kStatsRaw, lane);
+            if (lane == 0) *A.ticket = 0;
         }
     }
 }
@@ -620,8 +637,9 @@ __device__ inline void p2p_norms_merge(const P2PPeers &P, P2PLocal *L, double di
     P2PWindow *win = P.win[P.rank];
     if (lane < P.nranks) spin_until(&win->rec_flag[par][lane], en, &L->error);
     __syncwarp();
+    norms_from_records<true>(&win->rec[par][0][0], kRecDoubles, P.nranks, divisor, lex, stats + 4, stats + 8, stats + kStatsRaw, lane);
+    __syncwarp();
     if (lane == 0) {
-        norms_from_records<true>(&win->rec[par][0][0], kRecDoubles, P.nranks, divisor, lex, stats + 4, stats + 8, stats + kStatsRaw);
         __threadfence();
         asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&L->norm_ready), "l"(en) : "memory");
     }

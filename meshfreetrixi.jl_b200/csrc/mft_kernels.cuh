@@ -357,9 +357,9 @@ __device__ __forceinline__ void pass_a_epilogue(const PassAArgs &A, int64_t row,
                     for (int v = 0; v < V; ++v) A.norms_out[v] = nrm[v];
                 }
             } else {
-                // norm_merge: block 0 of this very launch wrote the norms (the caller waited for norm_ready): read them at L2
+                // (norm_merge: block 0 of this very launch wrote the norms; the caller acquired norm_ready before any read)
 #pragma unroll
-                for (int v = 0; v < V; ++v) nrm[v] = A.norm_merge ? __ldcg(A.norms + v) : A.norms[v];
+                for (int v = 0; v < V; ++v) nrm[v] = A.norms[v];
             }
             double mx = res.a[0] / nrm[0];
 #pragma unroll

@@ -402,8 +402,31 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
         // several GPUs: block 0 publishes the merged norms of this stage; the whole warp waits here, converged (the last slice
         // of a cloud may hold fewer than 32 rows: no warp-level barrier inside the per-row branch below)
         if (A.norm_merge) {
-            if (lane == 0) spin_until(&A.L->norm_ready, A.L->epoch_n, &A.L->error);
+            if (lane == 0) {   // (a flag of this GPU: device-scope acquire, not the system-scope poll of the peer flags)
+                const unsigned long long want = A.L->epoch_n;
+                unsigned long long have, n = 0;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(have) : "l"(&A.L->norm_ready) : "memory");
+                    if (have < want) {
+                        if (++n > kSpinLimit) {
+                            A.L->error = 1;
+                            break;
+                        }
+                        __nanosleep(40);
+                    }
+                } while (have < want);
+            }
             __syncwarp();
+        }
+    }
+    double nmean[4] = {0.0, 0.0, 0.0, 0.0}, nraw[4] = {0.0, 0.0, 0.0, 0.0};
+    if constexpr (VISC == VISC_RESIDUAL) {
+        if (A.stats && A.norm_miss) {   // (written by the previous kernel, or by block 0 before norm_ready: plain loads are safe)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                nmean[v] = A.stats[4 + v];
+                nraw[v] = A.stats[kStatsRaw + v];
+            }
         }
     }
 #pragma unroll
@@ -420,17 +443,14 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
             if constexpr (VISC == VISC_RESIDUAL) {
                 if (A.stats && A.norm_miss) {
                     // the norms are the lexicographic (or per-component) maximum of |u - mean| over ALL points: check this row
-                    double dv[V], raw[V];
+                    double dv[V];
 #pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        dv[v] = fabs(ui.a[v] - __ldcg(A.stats + V + v));
-                        raw[v] = __ldcg(A.stats + kStatsRaw + v);
-                    }
+                    for (int v = 0; v < V; ++v) dv[v] = fabs(ui.a[v] - nmean[v]);
                     bool miss = false;
-                    if (A.norm_lex) miss = lex_less<V>(raw, dv);
+                    if (A.norm_lex) miss = lex_less<V>(nraw, dv);
                     else {
 #pragma unroll
-                        for (int v = 0; v < V; ++v) miss |= dv[v] > raw[v];
+                        for (int v = 0; v < V; ++v) miss |= dv[v] > nraw[v];
                     }
                     if (miss) atomicAdd(A.norm_miss, 1ull);
                 }
