@@ -211,7 +211,7 @@ def run_ours(args):
                                                                 tile=int(args.tile), tile_rows=int(args.tile_rows),
                                                                 prefetch_distance=args.pf_dist, setup=args.setup,
                                                                 refine_order=bool(args.refine_order),
-                                                                fused_step=bool(args.fused_step)))
+                                                                fused_step=bool(args.fused_step), pdl=bool(args.pdl)))
     names = dict(left=1, right=2, bottom=3, top=4)
     t_setup = time.time()
     domain = m.ParallelPointCloudDomain(solver, cl, names, comm) if multi else m.PointCloudDomain(solver, cl, names)
@@ -583,6 +583,7 @@ def main():
     ap.add_argument("--fused-step", type=int, default=1, help="0: separate stage / boundary / norm / halo put / wait kernels (round-1 sequence)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="label of the JSON line: weak (default: --n-side is the per-GPU lattice side) or strong (the caller chose --n-side so that the TOTAL cloud is fixed)")
+    ap.add_argument("--pdl", type=int, default=1, help="0: no programmatic dependent launch between the kernels of a fused stage")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the untimed parity check against the serial oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

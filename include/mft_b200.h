@@ -101,6 +101,9 @@ typedef struct mft_ctx mft_ctx;
                                     * pass 1, ode_mean / ode_maximum (one-pass statistic) and -- on several GPUs -- the u halo puts; pass A
                                     * puts its g halo rows itself and tiles that touch the halo wait for it while the interior runs.
                                     * 0: separate stage / boundary / norm / put / wait kernels (the round-1 sequence). */
+#define MFT_OPT_PDL 13             /* 1 (default): the kernels of a fused stage are launched as programmatic dependents of each other
+                                    * (cudaLaunchAttributeProgrammaticStreamSerialization): a kernel starts its operator-only prologue
+                                    * while its predecessor drains and waits (griddepcontrol.wait) before reading the predecessor's output */
 #define MFT_OPT_PREFETCH_DISTANCE 6/* slices ahead for the L2 prefetch of operator data (weight blocks; union tiles: step words, weights, union
                                       list of the tile that many slices ahead).  Default 8 per SM; 0: off.               */
 

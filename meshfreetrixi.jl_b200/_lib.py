@@ -26,6 +26,7 @@ OPT_PAIR_ROWS = 9
 OPT_TILE = 10
 OPT_TILE_ROWS = 11
 OPT_FUSED_STEP = 12
+OPT_PDL = 13
 VAR_DENSITY, VAR_PRESSURE = 0, 1
 FIELD_EPS, FIELD_EPS_UW, FIELD_EPS_RV, FIELD_EPS_C, FIELD_RESIDUAL, FIELD_APPROX_DU, FIELD_NORMS, FIELD_SIGMA, FIELD_IGR_STATUS, FIELD_NORM_MISSES = range(10)
 SSPRK33 = 0

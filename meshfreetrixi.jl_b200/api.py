@@ -88,6 +88,7 @@ class RBFFDEngineCUDA:
     tile: int = 31                     # union-tile kernels: bit0 pass A, bit1 pass B, bit2 bank-coloured slots, bit3 two record copies,
                                        # bit4 (31, default since r2: -13 % shared wavefronts measured): second copy tuned by local search
     tile_rows: int = 11                # rows per thread of the union-tile kernels: units digit pass A, tens digit pass B (1, 2, 4)
+    pdl: bool = True                   # programmatic dependent launch between the kernels of a fused stage
     fused_step: bool = True            # mft_ssprk_step: one fused stage kernel (stage update + BCs + norms + u halo puts), halo waits inside the pass kernels
     prefetch_distance: int | None = None  # slices ahead for the L2 prefetch of operator data (None: library default, 0: off)
     single_sweep_exact: bool = False   # k=20: exact-order pass A in one sweep (y-products parked in registers)
@@ -448,6 +449,7 @@ class SemidiscretizationHyperbolic:
         L.check(lib.mft_set_option(ctx, L.OPT_TILE, float(eng.tile)))
         L.check(lib.mft_set_option(ctx, L.OPT_TILE_ROWS, float(eng.tile_rows)))
         L.check(lib.mft_set_option(ctx, L.OPT_FUSED_STEP, 1.0 if eng.fused_step else 0.0))
+        L.check(lib.mft_set_option(ctx, L.OPT_PDL, 1.0 if eng.pdl else 0.0))
         if eng.prefetch_distance is not None:
             L.check(lib.mft_set_option(ctx, L.OPT_PREFETCH_DISTANCE, float(eng.prefetch_distance)))
         if part is not None:

@@ -199,7 +199,9 @@ struct mft_ctx {
     std::vector<int> stage_lim_variables;
     // fused step (mft_fused_kernels.cuh): per-row side table (boundary entry, halo routes), miss counter of the one-pass norms
     int fused_step = 1;
+    int pdl = 1;                           // MFT_OPT_PDL: programmatic dependent launch between the kernels of a fused stage
     bool fused_active = false;             // the launches being issued belong to the fused step
+    bool pdl_next = false;                 // the next fused kernel follows another kernel of the fused step directly
     DevBuf<int> row_aux;
     DevBuf<RowAux> row_aux_tab;
     DevBuf<int> route_peer;
@@ -333,6 +335,25 @@ struct ScopedTimer {
         if (e_ != cudaSuccess) return fail(MFT_ECUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
     } while (0)
 
+// Kernel launch, optionally as a programmatic dependent of the previous kernel on the stream (PDL): the kernel may begin while
+// its predecessor drains; it calls pdl_wait() before it reads the predecessor's output.  Captured into CUDA graphs as a
+// programmatic edge.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // lifetime
 // ------------------------------------------------------------------------------------------------------
@@ -383,10 +404,14 @@ extern "C" int mft_ctx_create(mft_ctx **out, int device, int64_t n_local, int64_
     // one wave of the fused stage kernel (MFT_STAGE_OCC blocks of 256 threads per SM); the separate reduction kernels use the
     // same grid, so both paths sum in the same order
     c->red_blocks = prop.multiProcessorCount * MFT_STAGE_OCC;
-    CHECK(c->partial.alloc((int64_t)c->red_blocks * kRecDoubles));  // per-block partials: V sums, or one norm record (fused step)
+    // per-block partials: V sums, or one norm record (fused step) + one record per group of kStageGroup blocks
+    const int ngroups = (c->red_blocks + kStageGroup - 1) / kStageGroup;
+    CHECK(c->partial.alloc((int64_t)(c->red_blocks + ngroups) * kRecDoubles));
     CHECK(c->stats.alloc(24));  // sum | mean | norms | SSPRK43 error sum | [16..19] raw norms of the fused step
-    CHECK(c->ticket.alloc(8));
-    CU(cudaMemset(c->ticket.p, 0, 8 * sizeof(unsigned int)));
+    CHECK(c->ticket.alloc(8 + ngroups));   // [8..]: group tickets of the fused stage kernel
+    CU(cudaMemset(c->ticket.p, 0, (8 + ngroups) * sizeof(unsigned int)));
+    CHECK(c->p2p_local.alloc((int64_t)sizeof(P2PLocal)));   // norms epoch / norm_ready of the fused step (also on one GPU)
+    CU(cudaMemset(c->p2p_local.p, 0, sizeof(P2PLocal)));
     CHECK(c->norm_miss.alloc(1));
     CU(cudaMemset(c->norm_miss.p, 0, sizeof(unsigned long long)));
     c->pf_dist = prop.multiProcessorCount * 8;
@@ -506,6 +531,12 @@ extern "C" int mft_set_option(mft_ctx *c, int option, double value)
     case MFT_OPT_SINGLE_SWEEP_EXACT: c->kfix_ok = value != 0; break;
     case MFT_OPT_PAIR_ROWS: c->pair_rows = (int)value; break;
     case MFT_OPT_TILE: c->tile = (int)value; break;
+    case MFT_OPT_PDL:
+        c->pdl = value != 0;
+        for (auto &g : c->graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        c->graphs.clear();
+        break;
     case MFT_OPT_FUSED_STEP:
         c->fused_step = value != 0;
         for (auto &g : c->graphs)   // captured steps bake the launch sequence in: start over
@@ -1304,11 +1335,12 @@ static int launch_pass_a_tiler(mft_ctx *c, const PassAArgs &a0, bool do_flux, in
     a.n_slices = e.nslices;
     const int grid = e.ntiles;
     const int smem = 3 * e.ncopy * t.sstride * 16 + kTileWarps * t.buf_bytes;
+    const bool use_pdl = c->fused_active && c->pdl && c->pdl_next;
     if (smem > 200 * 1024) return fail(MFT_ENOTSUP, "union tile: %d bytes of shared memory per block", smem);
 #define PAR(EX, DF, VI, ST)                                                                         \
     do {                                                                                            \
         CHECK(ensure_smem(c, k_pass_a_tiler<R, EX, DF, VI, ST>, smem));                             \
-        k_pass_a_tiler<R, EX, DF, VI, ST><<<grid, kTileWarps * 32, smem, c->stream>>>(a, t);       \
+        CU(launch_k(k_pass_a_tiler<R, EX, DF, VI, ST>, grid, kTileWarps * 32, smem, c->stream, use_pdl, a, t)); \
     } while (0)
 #define PAR2(DF, VI)                                        \
     do {                                                    \
@@ -1340,10 +1372,11 @@ static int launch_pass_b_tiler(mft_ctx *c)
                     reinterpret_cast<P2PLocal *>(c->p2p_local.p)};
     const int smem = 4 * e.ncopy * t.sstride * 16 + kTileWarps * t.buf_bytes;
     if (smem > 200 * 1024) return fail(MFT_ENOTSUP, "union tile: %d bytes of shared memory per block", smem);
+    const bool use_pdl = c->fused_active && c->pdl && c->pdl_next;
 #define PBR(EX, ST)                                                                                  \
     do {                                                                                             \
         CHECK(ensure_smem(c, k_pass_b_tiler<R, EX, ST>, smem));                                      \
-        k_pass_b_tiler<R, EX, ST><<<e.ntiles, kTileWarps * 32, smem, c->stream>>>(a, t);            \
+        CU(launch_k(k_pass_b_tiler<R, EX, ST>, e.ntiles, kTileWarps * 32, smem, c->stream, use_pdl, a, t)); \
     } while (0)
     if (!c->exact) PBR(false, false);
     else if (stage) PBR(true, true);

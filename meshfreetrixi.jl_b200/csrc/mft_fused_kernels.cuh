@@ -259,7 +259,9 @@ struct StageArgs {
     const int *bc_kind;
     const double *bc_normals, *bc_values;
     // reductions
-    double *partial;   // gridDim.x records
+    double *partial;   // gridDim.x block records
+    double *grec;      // one record per group of kStageGroup blocks (leaves / component extremes only)
+    unsigned int *gticket;   // one ticket per group, zero between launches
     unsigned int *ticket;
     double divisor;
     int lex;
@@ -279,9 +281,10 @@ constexpr int NORMS_NONE = 0, NORMS_LEX = 1, NORMS_COMP = 2;
 #define MFT_STAGE_OCC 2
 #endif
 #ifndef MFT_STAGE_DEPTH
-#define MFT_STAGE_DEPTH 4
+#define MFT_STAGE_DEPTH 3
 #endif
 constexpr int kStageDepth = MFT_STAGE_DEPTH;
+constexpr int kStageGroup = 16;   // blocks whose records the last of them to finish merges into one group record
 constexpr int kStageSlotBytes = 256 * (3 * 32 + 4);   // per ring stage and block: du, u, uprev rows + aux of 8 warps x 32 rows
 constexpr int kStageSmemBytes = kStageDepth * kStageSlotBytes;
 
@@ -298,6 +301,8 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
     Vec<V> *u = reinterpret_cast<Vec<V> *>(A.u);
     Vec<V> *uprev = reinterpret_cast<Vec<V> *>(A.uprev);
     Vec<V> *du = reinterpret_cast<Vec<V> *>(A.du);
+    pdl_launch_dependents();
+    pdl_wait();   // every operand of this kernel is the predecessor's output (du from pass B)
     unsigned long long e_u = 0;
     if constexpr (MULTI) {
         e_u = A.L->epoch[0] + 1;
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
     // Operand rings: every warp streams ITS next row batches (du, u, uprev, aux of 32 consecutive rows) into shared memory with
     // bulk-async copies (cp.async.bulk = the 1-D TMA path) kStageDepth batches ahead, completion on an mbarrier per (warp,
     // slot); no block-level barrier in the loop.  The kernel is a pure stream (128 B per row): what bounds it is bytes in
-    // flight, and 8 warps x 4 slots x 3.2 KB per block keep ~200 KB per SM in flight without a single register.
+    // flight, and 8 warps x 3 slots x 3.2 KB per block keep ~150 KB per SM in flight without a single register.
     extern __shared__ __align__(128) unsigned char ring_raw[];
     __shared__ uint64_t full[8][kStageDepth];
     struct Slot {
@@ -511,8 +516,68 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
             prec[(mn ? kRecCmin : kRecCmax) + v] = b;
         }
     }
-    // fences are cumulative: the block barrier makes every thread's stores (incl. the remote halo rows) visible to
-    // thread 0, whose fence then orders them before the ticket (and, in the last block, before the flags)
+    // ---- group records: the last block of every group of kStageGroup blocks merges the group's leaves (parallel over the
+    // groups: no single serial tail; whoever combines the whole grid afterwards reads gridDim.x / 16 records, one round trip)
+    __shared__ double fin[kRecDoubles];
+    __shared__ double xw[8][16][4];
+    __shared__ bool glast;
+    const int nb = (int)gridDim.x;
+    if constexpr (NORMS) {
+        const int g = (int)blockIdx.x / kStageGroup;
+        const int gsize = nb - g * kStageGroup < kStageGroup ? nb - g * kStageGroup : kStageGroup;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            glast = atomicAdd(&A.gticket[g], 1u) == (unsigned)gsize - 1u;
+        }
+        __syncthreads();
+        if (glast) {
+            __threadfence();
+            double *G = A.grec + (size_t)g * kRecDoubles;
+            if constexpr (NMODE == NORMS_LEX) {
+                const int slot = threadIdx.x & 15, j = threadIdx.x >> 4, side = slot >> 3, lf = slot & 7;
+                double bext = side == 0 ? neg_inf() : pos_inf(), b1 = 0.0, b2 = 0.0, b3 = 0.0;
+                if (j < gsize) {
+                    const double *R = A.partial + (size_t)(g * kStageGroup + j) * kRecDoubles;
+                    const double *q = R + kRecLeaf + side * 24 + lf * 3;
+                    bext = __ldcg(R + kRecExt + side);
+                    b1 = __ldcg(q);
+                    b2 = __ldcg(q + 1);
+                    b3 = __ldcg(q + 2);
+                }
+                const double oe = __shfl_xor_sync(kFull, bext, 16), o1 = __shfl_xor_sync(kFull, b1, 16);
+                const double o2 = __shfl_xor_sync(kFull, b2, 16), o3 = __shfl_xor_sync(kFull, b3, 16);
+                slot_merge(slot, oe, o1, o2, o3, bext, b1, b2, b3);
+                if (lane < 16) {
+                    xw[w][slot][0] = bext;
+                    xw[w][slot][1] = b1;
+                    xw[w][slot][2] = b2;
+                    xw[w][slot][3] = b3;
+                }
+                __syncthreads();
+                if (threadIdx.x < 16) {
+                    for (int k = 1; k < 8; ++k) slot_merge(slot, xw[k][slot][0], xw[k][slot][1], xw[k][slot][2], xw[k][slot][3], bext, b1, b2, b3);
+                    if (lf == 0) G[kRecExt + side] = bext;
+                    double *q = G + kRecLeaf + side * 24 + lf * 3;
+                    q[0] = b1;
+                    q[1] = b2;
+                    q[2] = b3;
+                }
+            } else if (threadIdx.x < 8) {
+                const int v = threadIdx.x & 3;
+                const bool mn = threadIdx.x >= 4;
+                double b = mn ? pos_inf() : neg_inf();
+                for (int k = 0; k < gsize; ++k) {
+                    const double x = __ldcg(&A.partial[(size_t)(g * kStageGroup + k) * kRecDoubles + (mn ? kRecCmin : kRecCmax) + v]);
+                    b = mn ? fmin(b, x) : fmax(b, x);
+                }
+                G[(mn ? kRecCmin : kRecCmax) + v] = b;
+            }
+            if (threadIdx.x == 0) A.gticket[g] = 0;
+        }
+    }
+    // fences are cumulative: the block barrier makes every thread's stores (incl. the remote halo rows and a group record) visible
+    // to thread 0, whose fence then orders them before the ticket (and, in the last block, before the flags)
     __syncthreads();
     if (threadIdx.x == 0) {
         if constexpr (MULTI) __threadfence_system();
@@ -523,10 +588,8 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
     if (!is_last) return;
     __threadfence();
 
-    // ---- last block: this rank's record ----------------------------------------------------------------------------
-    __shared__ double fin[kRecDoubles];
-    __shared__ double xw[8][16][4];
-    const int nb = (int)gridDim.x;
+    // ---- last block: this rank's record = block sums (tree of k_sum_mean) + merged group records (one L2 round trip) --------
+    const int ng = (nb + kStageGroup - 1) / kStageGroup;
     if constexpr (NORMS) {
 #pragma unroll
         for (int v = 0; v < V; ++v) s[v] = 0.0;
@@ -547,24 +610,13 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
             }
         }
         if constexpr (NMODE == NORMS_LEX) {
-            // thread = (j, slot): slot = side*8 + leaf scans the block records j, j+16, ...; then the 16 scanners of a slot merge
+            // thread = (j, slot): 16 scanners per (side, leaf) slot over the group records, then the scanners of a slot merge
             const int slot = threadIdx.x & 15, j = threadIdx.x >> 4, side = slot >> 3, lf = slot & 7;
             double bext = side == 0 ? neg_inf() : pos_inf(), b1 = 0.0, b2 = 0.0, b3 = 0.0;
-            // (eight records' loads in flight per scanner: the chain of merges is short, the L2 round trips are not)
-            for (int b0 = j; b0 < nb; b0 += 128) {
-                double xe[8], x1[8], x2[8], x3[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int b = b0 + 16 * r;
-                    const double *R = A.partial + (size_t)(b < nb ? b : j) * kRecDoubles;
-                    const double *q = R + kRecLeaf + side * 24 + lf * 3;
-                    xe[r] = __ldcg(R + kRecExt + side);
-                    x1[r] = __ldcg(q);
-                    x2[r] = __ldcg(q + 1);
-                    x3[r] = __ldcg(q + 2);
-                }
-#pragma unroll
-                for (int r = 0; r < 8; ++r) slot_merge(slot, xe[r], x1[r], x2[r], x3[r], bext, b1, b2, b3);   // (a re-read of record j merges nothing new)
+            for (int b = j; b < ng; b += 16) {
+                const double *R = A.grec + (size_t)b * kRecDoubles;
+                const double *q = R + kRecLeaf + side * 24 + lf * 3;
+                slot_merge(slot, __ldcg(R + kRecExt + side), __ldcg(q), __ldcg(q + 1), __ldcg(q + 2), bext, b1, b2, b3);
             }
             {   // lanes slot and slot + 16 hold the same slot
                 const double oe = __shfl_xor_sync(kFull, bext, 16), o1 = __shfl_xor_sync(kFull, b1, 16);
@@ -591,8 +643,8 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
             const int v = threadIdx.x & 3;
             const bool mn = threadIdx.x >= 4;
             double b = mn ? pos_inf() : neg_inf();
-            for (int k = 0; k < nb; ++k) {
-                const double x = __ldcg(&A.partial[(size_t)k * kRecDoubles + (mn ? kRecCmin : kRecCmax) + v]);
+            for (int k = 0; k < ng; ++k) {
+                const double x = __ldcg(&A.grec[(size_t)k * kRecDoubles + (mn ? kRecCmin : kRecCmax) + v]);
                 b = mn ? fmin(b, x) : fmax(b, x);
             }
             fin[(mn ? kRecCmin : kRecCmax) + v] = b;
@@ -611,15 +663,16 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence_system();
+            __threadfence_system();   // ONE fence orders the halo rows and the record before all the flags below
             if constexpr (NORMS)
-                for (int r = 0; r < A.P.nranks; ++r) st_release_sys(&A.P.win[r]->rec_flag[par][A.P.rank], en);
-            for (int i = 0; i < A.P.ndst; ++i) st_release_sys(&A.P.win[A.P.dst[i]]->data_flag[0][A.P.rank], e_u);
+                for (int r = 0; r < A.P.nranks; ++r) st_relaxed_sys(&A.P.win[r]->rec_flag[par][A.P.rank], en);
+            for (int i = 0; i < A.P.ndst; ++i) st_relaxed_sys(&A.P.win[A.P.dst[i]]->data_flag[0][A.P.rank], e_u);
             A.L->epoch[0] = e_u;
             if constexpr (NORMS) A.L->epoch_n = en;
             *A.ticket = 0;
         }
     } else {
+        // one GPU: the norms are final here; pass A reads them from stats[] (stream order)
         if (w == 0) {
             if (lane < V) A.stats[lane] = fin[kRecSum + lane];
             norms_from_records<false>(fin, kRecDoubles, 1, A.divisor, A.lex, A.stats + V, A.stats + 2 * V, A.stats + kStatsRaw, lane);

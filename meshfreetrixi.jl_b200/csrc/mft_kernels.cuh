@@ -121,6 +121,14 @@ __device__ __forceinline__ SliceView stage_slice(const EllBlob &op, int64_t slic
     return v;
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// The three kernels of a fused stage are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel may start
+// (and run the part of its prologue that only touches operator data) while the tail of its predecessor is still running;
+// pdl_wait() returns once the predecessor grid has completed and its memory operations are visible.  Both instructions are
+// no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- 256-bit / 64-bit read-only loads and stores ------------------------------------------------------
 __device__ __forceinline__ Vec<4> ld_ro(const Vec<4> *p)
 {
@@ -291,7 +299,7 @@ struct PassAArgs {
     const int *route_peer;
     const long long *route_dst;
     double divisor;
-    int norm_merge;
+    int norm_merge;               // 0: norms[] is final (one GPU: the stage kernel's last block wrote it); 1: block 0 merges the ranks' records
 };
 
 constexpr int VISC_NONE = 0;
@@ -302,7 +310,8 @@ constexpr int VISC_RESIDUAL = 2;
 // update_visc!, hyperviscosity.jl:246-349) and store g = eps .* (Dx u, Dy u)
 template <int V, int EQ, bool DO_FLUX, int VISC>
 __device__ __forceinline__ void pass_a_epilogue(const PassAArgs &A, int64_t row, const Vec<V> &acc, const Vec<V> &gx,
-                                                const Vec<V> &gy, const Vec<V> &ui, const Vec<V> &ad, Vec<2 * V> *g_ret = nullptr)
+                                                const Vec<V> &gy, const Vec<V> &ui, const Vec<V> &ad, Vec<2 * V> *g_ret = nullptr,
+                                                const double *norms_reg = nullptr)
 {
     if constexpr (DO_FLUX) st_vec(reinterpret_cast<Vec<V> *>(A.du) + row, acc);
 
@@ -357,9 +366,9 @@ __device__ __forceinline__ void pass_a_epilogue(const PassAArgs &A, int64_t row,
                     for (int v = 0; v < V; ++v) A.norms_out[v] = nrm[v];
                 }
             } else {
-                // (norm_merge: block 0 of this very launch wrote the norms; the caller acquired norm_ready before any read)
+                // (norms_reg: block 0 of this very launch wrote the norms; the caller fetched them after seeing norm_ready)
 #pragma unroll
-                for (int v = 0; v < V; ++v) nrm[v] = A.norms[v];
+                for (int v = 0; v < V; ++v) nrm[v] = norms_reg ? norms_reg[v] : A.norms[v];
             }
             double mx = res.a[0] / nrm[0];
 #pragma unroll
@@ -1399,6 +1408,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// flag store AFTER one __threadfence_system(): a release store per flag would run a system-scope fence each (one NVLink round
+// trip per flag, serialised: measured as a ~30 us tail on 8 GPUs); one fence orders the data before all the flags
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long want, int *error)
 {

@@ -171,7 +171,7 @@ extern "C" int mft_p2p_handles(mft_ctx *c, void *out3x64)
     if (c->V != 4) return fail(MFT_ENOTSUP, "peer-memory exchange is implemented for Euler 2-D");
     if (!c->p2p_window.p) {
         CHECK(c->p2p_window.alloc((int64_t)sizeof(P2PWindow)));
-        CHECK(c->p2p_local.alloc((int64_t)sizeof(P2PLocal)));
+        if (!c->p2p_local.p) CHECK(c->p2p_local.alloc((int64_t)sizeof(P2PLocal)));
         CU(cudaMemset(c->p2p_window.p, 0, sizeof(P2PWindow)));
         CU(cudaMemset(c->p2p_local.p, 0, sizeof(P2PLocal)));
         if (!c->g.p) {  // no viscosity source: still give peers something valid to map

@@ -75,7 +75,23 @@ __device__ __forceinline__ Vec<8> ld_cg(const Vec<8> *p)
 // band tile: wait until the halo rows of field F (0: u, 1: g) of the current epoch have arrived from every source rank
 __device__ __forceinline__ void band_wait(const P2PPeers *P, P2PLocal *L, int F)
 {
-    if ((int)threadIdx.x < P->nsrc) spin_until(&P->win[P->rank]->data_flag[F][P->src[threadIdx.x]], L->epoch[F], &L->error);
+    if ((int)threadIdx.x < P->nsrc) {
+        // relaxed polls (no L1 invalidation per poll); the halo rows are then read with ld.global.cg, i.e. at L2, where the
+        // peer's rows arrived before its flag did
+        const unsigned long long *flag = &P->win[P->rank]->data_flag[F][P->src[threadIdx.x]];
+        const unsigned long long want = L->epoch[F];
+        unsigned long long have, n = 0;
+        do {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(have) : "l"(flag) : "memory");
+            if (have < want) {
+                if (++n > kSpinLimit) {
+                    L->error = 1;
+                    break;
+                }
+                __nanosleep(100);
+            }
+        } while (have < want);
+    }
     __syncthreads();
 }
 
@@ -180,11 +196,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
     const uint32_t arr_bytes = (uint32_t)T.sstride * 16u, nc = (uint32_t)T.ncopy;
     unsigned char *sA = smem_dyn, *sB = smem_dyn + nc * arr_bytes, *sC = smem_dyn + 2 * nc * arr_bytes;
     unsigned char *buf = smem_dyn + 3 * nc * arr_bytes + (size_t)warp * T.buf_bytes;
-    if constexpr (VISC == VISC_RESIDUAL) {
-        // fused step on several GPUs: the first block turns the ranks' norm records into the norms (they are needed in the
-        // epilogues only, by then the records have long arrived)
-        if (A.norm_merge && blockIdx.x == 0 && warp == 0) p2p_norms_merge(*A.P, A.L, A.divisor, A.norm_lex, const_cast<double *>(A.stats), lane);
-    }
+    pdl_launch_dependents();   // (the successor's blocks only take SM slots this grid no longer needs)
 
     int W = 0, L = 0;
     const unsigned char *src = nullptr;
@@ -210,6 +222,30 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
 
     const int u0 = T.uoff[tile];
     const int nu = T.uoff[tile + 1] - u0;
+    // everything above touched operator data only (staged step words, prefetches, tile tables); from here on the kernel reads
+    // what its predecessor wrote (u, the norm records)
+    pdl_wait();
+    if constexpr (VISC == VISC_RESIDUAL) {
+        // fused step on several GPUs: the first block turns the ranks' norm records into the norms (they are needed in the
+        // epilogues only, by then the records have long arrived)
+        if (A.norm_merge == 1 && blockIdx.x == 0 && warp == 0) p2p_norms_merge(*A.P, A.L, A.divisor, A.norm_lex, const_cast<double *>(A.stats), lane);
+    }
+
+    // Several GPUs: the norms of this stage (mean | raw maximum | norms, 12 doubles) come from block 0 of this very launch.  A
+    // warp must not pay L2 round trips for them in its epilogue (three dependent ones there cost +34 us per launch, measured):
+    // the readiness flag is loaded HERE, looked at after phase 1 (long since returned), and if block 0 was done by then the 12
+    // values are fetched, one per lane, behind the main loop; the epilogue only shuffles.  Only warps of the first wave can find
+    // the flag unset; they poll in the epilogue.
+    double nval = 0.0;
+    bool nhave = false;
+    unsigned long long nflag = 0, nwant = 0;
+    if constexpr (VISC == VISC_RESIDUAL) {
+        if (A.norm_merge) {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(nflag) : "l"(&A.L->norm_ready) : "memory");
+            nwant = A.L->epoch_n;
+        }
+    }
+
     if (band) band_wait(A.P, A.L, 0);   // the peers' u rows of this stage are in the halo tail from here on
     for (int t = threadIdx.x; t < nu; t += kTileWarps * 32) {
         const int j = __ldg(T.ulist + u0 + t);
@@ -249,6 +285,12 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
     }
     __syncthreads();
     tile_pf_issue<R>(T, pf, warp, lane);
+    if constexpr (VISC == VISC_RESIDUAL) {
+        if (A.norm_merge) {
+            nhave = nflag >= nwant;   // (the flag was read before phase 1: the values below were written before it was set)
+            if (nhave && lane < 12) nval = __ldcg(A.stats + (lane < 4 ? 4 + lane : lane < 8 ? kStatsRaw + lane - 4 : lane));
+        }
+    }
     if (has_slice) {
     if (W > 0) mbar_wait(&bars[warp], 0);
 
@@ -398,30 +440,37 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
             }
         }
     }
+    double nmean[4] = {0.0, 0.0, 0.0, 0.0}, nraw[4] = {0.0, 0.0, 0.0, 0.0}, nnorm[4] = {0.0, 0.0, 0.0, 0.0};
     if constexpr (VISC == VISC_RESIDUAL) {
-        // several GPUs: block 0 publishes the merged norms of this stage; the whole warp waits here, converged (the last slice
-        // of a cloud may hold fewer than 32 rows: no warp-level barrier inside the per-row branch below)
         if (A.norm_merge) {
-            if (lane == 0) {   // (a flag of this GPU: device-scope acquire, not the system-scope poll of the peer flags)
-                const unsigned long long want = A.L->epoch_n;
-                unsigned long long have, n = 0;
-                do {
-                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(have) : "l"(&A.L->norm_ready) : "memory");
-                    if (have < want) {
-                        if (++n > kSpinLimit) {
-                            A.L->error = 1;
-                            break;
+            // first-wave blocks only: block 0 was not done when this warp started.  The whole warp waits here, converged (the
+            // last slice of a cloud may hold fewer than 32 rows: no warp-level barrier inside the per-row branch below).
+            // RELAXED polls (an acquire load would invalidate the SM's L1 on every poll); the values are then read at L2.
+            if (!nhave) {
+                if (lane == 0) {
+                    const unsigned long long want = A.L->epoch_n;
+                    unsigned long long have, n = 0;
+                    do {
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(have) : "l"(&A.L->norm_ready) : "memory");
+                        if (have < want) {
+                            if (++n > kSpinLimit) {
+                                A.L->error = 1;
+                                break;
+                            }
+                            __nanosleep(200);
                         }
-                        __nanosleep(40);
-                    }
-                } while (have < want);
+                    } while (have < want);
+                }
+                __syncwarp();
+                if (lane < 12) nval = __ldcg(A.stats + (lane < 4 ? 4 + lane : lane < 8 ? kStatsRaw + lane - 4 : lane));
             }
-            __syncwarp();
-        }
-    }
-    double nmean[4] = {0.0, 0.0, 0.0, 0.0}, nraw[4] = {0.0, 0.0, 0.0, 0.0};
-    if constexpr (VISC == VISC_RESIDUAL) {
-        if (A.stats && A.norm_miss) {   // (written by the previous kernel, or by block 0 before norm_ready: plain loads are safe)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                nmean[v] = __shfl_sync(0xffffffffu, nval, v);
+                nraw[v] = __shfl_sync(0xffffffffu, nval, 4 + v);
+                nnorm[v] = __shfl_sync(0xffffffffu, nval, 8 + v);
+            }
+        } else if (A.stats && A.norm_miss) {   // (written by the previous kernel: plain loads)
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
                 nmean[v] = A.stats[4 + v];
@@ -456,7 +505,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
                 }
             }
             Vec<2 * V> gout;
-            pass_a_epilogue<V, EQ_EULER2D, DO_FLUX, VISC>(A, row, acc[r], gx[r], gy[r], ui, ad, &gout);
+            pass_a_epilogue<V, EQ_EULER2D, DO_FLUX, VISC>(A, row, acc[r], gx[r], gy[r], ui, ad, &gout, A.norm_merge ? nnorm : nullptr);
             if constexpr (VISC != VISC_NONE) {
                 if (band && A.aux) {   // rows in a peer's halo: g goes straight into the peer's halo tail
                     const int ax = __ldg(A.aux + row);
@@ -480,7 +529,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
                 if (atomicAdd(&A.L->ticket_g, 1u) == nband - 1) {
                     __threadfence_system();
                     const unsigned long long e = A.L->epoch[1] + 1;
-                    for (int i = 0; i < A.P->ndst; ++i) st_release_sys(&A.P->win[A.P->dst[i]]->data_flag[1][A.P->rank], e);
+                    for (int i = 0; i < A.P->ndst; ++i) st_relaxed_sys(&A.P->win[A.P->dst[i]]->data_flag[1][A.P->rank], e);
                     A.L->epoch[1] = e;
                     A.L->ticket_g = 0;
                 }
@@ -506,6 +555,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_B : R 
     const uint32_t arr_bytes = (uint32_t)T.sstride * 16u, nc = (uint32_t)T.ncopy;
     unsigned char *sA = smem_dyn, *sB = smem_dyn + nc * arr_bytes, *sC = smem_dyn + 2 * nc * arr_bytes, *sD = smem_dyn + 3 * nc * arr_bytes;
     unsigned char *buf = smem_dyn + 4 * nc * arr_bytes + (size_t)warp * T.buf_bytes;
+    pdl_launch_dependents();
 
     int W = 0, L = 0;
     const unsigned char *src = nullptr;
@@ -535,6 +585,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_B : R 
 
     const int u0 = T.uoff[tile];
     const int nu = T.uoff[tile + 1] - u0;
+    pdl_wait();                         // operator prologue done; g and du are the predecessor's output
     if (band) band_wait(A.P, A.L, 1);   // the peers' g rows of this stage are in the halo tail from here on
     for (int t = threadIdx.x; t < nu; t += kTileWarps * 32) {
         const int j = __ldg(T.ulist + u0 + t);

@@ -155,6 +155,8 @@ static int launch_stage_fused(mft_ctx *c, int stage, double dt, bool apply_bc2)
     a.bc_normals = c->bc_normals.p;
     a.bc_values = c->bc_values.p;
     a.partial = c->partial.p;
+    a.grec = c->partial.p + (size_t)c->red_blocks * kRecDoubles;
+    a.gticket = c->ticket.p + 8;
     a.ticket = c->ticket.p + 4;
     const double ng = multi ? (double)c->n_global : (double)c->n_local;
     a.divisor = c->mean_div_vn ? (double)c->V * ng : ng;
@@ -169,7 +171,7 @@ static int launch_stage_fused(mft_ctx *c, int stage, double dt, bool apply_bc2)
 #define STAGE_K(NM, MU)                                                            \
     do {                                                                           \
         CHECK(ensure_smem(c, k_stage_fused<NM, MU>, kStageSmemBytes));             \
-        k_stage_fused<NM, MU><<<grid, 256, kStageSmemBytes, c->stream>>>(a);       \
+        CU(launch_k(k_stage_fused<NM, MU>, grid, 256, kStageSmemBytes, c->stream, c->pdl && c->pdl_next, a)); \
     } while (0)
     if (multi) {
         if (nmode == NORMS_LEX) STAGE_K(NORMS_LEX, true);
@@ -193,18 +195,23 @@ static int ssprk33_step_fused(mft_ctx *c, double t, double dt, bool first_rhs)
     const int visc = s->kind == MFT_SRC_UPWIND ? VISC_UPWIND : VISC_RESIDUAL;
     struct Guard {
         mft_ctx *c;
-        ~Guard() { c->fused_active = false; }
+        ~Guard() { c->fused_active = c->pdl_next = false; }
     } guard{c};
     c->fused_active = true;
+    bool tables = false;   // stage-time Dirichlet tables put memcpy nodes between the kernels: no programmatic edge across them
+    for (auto *g : c->bcs) tables |= g->stage_set[0] || g->stage_set[1];
     for (int stage = 1; stage <= 3; ++stage) {
         CHECK(select_stage_boundary_values(c, stage == 2 ? 1 : 0));   // rhs! of stage 1 and 3 is evaluated at t + dt, of stage 2 at t + dt/2
+        c->pdl_next = stage > 1 && !tables && !c->timing;   // (the first stage kernel follows whatever ran before the step)
         CHECK(launch_stage_fused(c, stage, dt, stage > 1));
+        c->pdl_next = !c->timing;
         NvtxRange r(visc == VISC_RESIDUAL ? "calc fluxes + calc SourceResidualViscosityTominec (fused)"
                                           : "calc fluxes + calc SourceUpwindViscosityTominec (fused)");
         CHECK(launch_pass_a(c, true, visc, s, false));
         CHECK(launch_pass_b(c));
     }
     c->fused_active = false;
+    c->pdl_next = false;
     NvtxRange r("boundary flux");
     CHECK(launch_boundary(c, true));   // BC pass 2 of the last rhs!: u and du are complete when the step returns
     return MFT_OK;
