@@ -186,7 +186,10 @@ int mft_boundary_pass(mft_ctx *ctx, double t, double *const *u_soa, double *cons
 int mft_upload_state(mft_ctx *ctx, const double *const *u_soa);
 int mft_download_state(mft_ctx *ctx, double *const *u_soa);
 int mft_download_du(mft_ctx *ctx, double *const *du_soa);
-/* HistoryCallback affect: modify_cache!(::SourceResidualViscosityTominec) history.jl:91-129 on the resident u.
+/* HistoryCallback affect: modify_cache!(::SourceResidualViscosityTominec) history.jl:91-129 on the RESIDENT u.
+ * The snapshot that enters the solution history is the device-resident state: after mft_ssprk_step / mft_upload_state that is
+ * the state the callback means.  A host-driven integrator (mft_rhs with MFT_MEM_HOST) leaves the last STAGE value (post-BC)
+ * resident, so such a caller uploads the callback's u first (mft_upload_state; julia/MeshfreeTrixiB200.jl does).
  * Weights from time_deriv_weights! (:131-152) are computed by the library ... */
 int mft_history_push(mft_ctx *ctx, double t, int64_t success_iter, int approx_order);
 /* ... or supplied by the caller (n weights, most recent first), so the Julia side can keep its own solve */
