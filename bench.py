@@ -79,19 +79,27 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows[getattr(self, 'first', 0):]:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for nm, val in zip(names, r[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
+
+        def parse(rows):
+            sm, mx, reasons = [], [], set()
+            for r in rows:
+                try:
+                    sm.append(float(r[1]))
+                    mx.append(float(r[2]))
+                    for nm, val in zip(names, r[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(nm)
+                except Exception:
+                    continue
+            return sm, mx, reasons
+        sm, mx, reasons = parse(self.rows[getattr(self, 'first', 0):])
+        window = "timed region"
+        if not sm:   # a timed region shorter than the sampling period: the samples of the warm-up steps right before it
+            sm, mx, reasons = parse(self.rows[-3:])
+            window = "warm-up steps just before the timed region (the region was shorter than one sampling period)"
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def build_workload(nx, ny, seed, m, need_oracle_ops=False):
@@ -320,7 +328,9 @@ def run_ours(args):
                                "frac_of_n_gpu_peak": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / agg_peak, 4),
                                "bytes_per_point_stage": 40 * k + src_bytes + 128},
                 "kernel_ms_per_step": {kk: round(v[0] / args.steps, 4) for kk, v in ktime.items()},
-                "note": "per-kernel times: rank 0, CUDA events around every launch (eager replay of the same steps)"}
+                "note": "per-kernel times: rank 0, CUDA events around every launch (eager replay of the same steps)"
+                        + ("; at N > 1 the pass kernels' times include their in-kernel waits for the peers' halo rows and norm records, and "
+                           "eagerly launched ranks drift apart -- the N = 1 line carries the roofline of the kernels themselves" if multi else "")}
 
     # ---- end-to-end through the reference-facing call: mft_rhs with HOST buffers (pinned) -------------------
     n_arr = u0.shape[1]

@@ -917,6 +917,13 @@ extern "C" int mft_finalize(mft_ctx *c)
     }
     // drop halo rows of the forward operator: only owned rows are computed here
     if (c->have_perm) CHECK(c->d_perm.upload(std::vector<int>(c->perm.begin(), c->perm.end())));
+    // Kernel family by stencil width (north_star: "warp-per-row or thread-per-row chosen from measured stencil width").  Measured
+    // on the B200 for k = 13, 15, 20, 25, 30, 36, 42, 50 at 1M points (tools/stencil_sweep.py, profiles/r2_stencil_sweep.json):
+    // union tiles 0.49 - 0.64 of the HBM peak (flux only) and 0.50 - 0.60 (full residual-viscosity rhs!), thread-per-row sliced
+    // ELL 0.29 - 0.41 and 0.39 - 0.48.  The tiles win at EVERY width of the reference's range (geometry_primatives.jl:197-198:
+    // k = 15 / 20 / 30 / 42), so there is no crossover to switch on: Euler 2-D always takes the tile kernels unless MFT_OPT_TILE
+    // says otherwise; the only width-dependent choice left is inside the tile format (slot count <= 4095 and shared memory
+    // <= 200 KB per block are checked at build / launch time and reported, not silently worked around).
     const bool tile_a = (c->tile & 1) && c->V == 4 && c->eq == MFT_EQ_EULER2D;
     const bool tile_b = (c->tile & 2) && c->V == 4 && c->eq == MFT_EQ_EULER2D;
     if (tile_a) CHECK(build_tiler(c, F, c->n_local, c->tile_rows_a, (c->tile & 4) != 0, (c->tile & 8) != 0, c->fwd_tiler));
