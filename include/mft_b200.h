@@ -37,6 +37,9 @@ typedef struct mft_ctx mft_ctx;
 #define MFT_ENODEVICE (-3)
 #define MFT_ENOTSUP (-4)  /* combination not implemented (e.g. residual viscosity for advection) */
 #define MFT_ENCCL (-5)
+#define MFT_ENORMS (-6)   /* fused step: some rows exceeded the one-pass ode_maximum statistic (a ROUNDING tie decided the lexicographic order,
+                           * DESIGN.md 3d); returned by mft_synchronize / mft_download_state so that it is never silent.  Re-run with
+                           * MFT_OPT_FUSED_STEP = 0 (two-pass norms).  The counter is MFT_FIELD_NORM_MISSES. */
 
 /* equations: Trixi CompressibleEulerEquations2D(gamma) / LinearScalarAdvectionEquation2D(a1,a2);
  * flux call site src/solvers/pointcloudsolver/rbfsolver.jl:259 */

@@ -207,6 +207,8 @@ struct mft_ctx {
     DevBuf<int> route_peer;
     DevBuf<long long> route_dst;
     DevBuf<unsigned long long> norm_miss;
+    unsigned long long norm_miss_seen = 0;   // value of the counter at the last check (mft_synchronize / mft_download_state)
+    bool fused_used = false;
     DevBuf<P2PPeers> peers_dev_buf;        // device copy of peers_dev for kernels that take a pointer
     std::vector<int> bc_idx_host;          // merged boundary table: device rows
     std::vector<int> send_rows_host, send_peer_host;
@@ -1111,6 +1113,22 @@ static int download_soa(mft_ctx *c, const double *src_aos, double *const *soa)
     return MFT_OK;
 }
 
+// fused step: rows that exceeded the one-pass norms since the last check (loud, never silent: MFT_ENORMS)
+static int check_norm_misses(mft_ctx *c)
+{
+    if (!c->fused_used || !c->norm_miss.p) return MFT_OK;
+    unsigned long long m = 0;
+    CU(cudaMemcpy(&m, c->norm_miss.p, sizeof m, cudaMemcpyDeviceToHost));
+    if (m > c->norm_miss_seen) {
+        const unsigned long long d = m - c->norm_miss_seen;
+        c->norm_miss_seen = m;
+        return fail(MFT_ENORMS, "fused step: %llu row(s) exceeded the one-pass ode_maximum statistic (a rounding tie decided the lexicographic "
+                                "order); the affected stages used norms that differ from the reference's -- re-run with MFT_OPT_FUSED_STEP = 0",
+                    d);
+    }
+    return MFT_OK;
+}
+
 extern "C" int mft_upload_state(mft_ctx *c, const double *const *u_soa)
 {
     NEED_CTX(c);
@@ -1126,7 +1144,7 @@ extern "C" int mft_download_state(mft_ctx *c, double *const *u_soa)
     CHECK(mft_finalize(c));
     CHECK(download_soa(c, c->u.p, u_soa));
     CU(cudaStreamSynchronize(c->stream));
-    return MFT_OK;
+    return check_norm_misses(c);
 }
 extern "C" int mft_download_du(mft_ctx *c, double *const *du_soa)
 {
@@ -1765,7 +1783,7 @@ extern "C" int mft_synchronize(mft_ctx *c)
         CU(cudaMemcpy(&h, c->p2p_local.p, sizeof h, cudaMemcpyDeviceToHost));
         if (h.error) return fail(MFT_ENCCL, "peer-memory exchange timed out waiting for a peer flag (a rank fell out of step)");
     }
-    return MFT_OK;
+    return check_norm_misses(c);
 }
 
 extern "C" int mft_timer_start(mft_ctx *c)

@@ -198,6 +198,7 @@ static int ssprk33_step_fused(mft_ctx *c, double t, double dt, bool first_rhs)
         ~Guard() { c->fused_active = c->pdl_next = false; }
     } guard{c};
     c->fused_active = true;
+    c->fused_used = true;
     bool tables = false;   // stage-time Dirichlet tables put memcpy nodes between the kernels: no programmatic edge across them
     for (auto *g : c->bcs) tables |= g->stage_set[0] || g->stage_set[1];
     for (int stage = 1; stage <= 3; ++stage) {

@@ -191,3 +191,47 @@ def test_fused_on_the_fixture_cloud():
     assert out[0][3] == 0
     for a, b in zip(out[0][:3], out[1][:3]):
         assert np.array_equal(a, b)
+
+
+def test_a_rounding_tie_is_reported_loudly():
+    """The documented limit of the one-pass statistic (tests/test_norm_leaves_cpu.py): a plateau that ties EXACTLY on
+    the density, carries rounding noise in m1 while the mean of m1 is O(1) (so |m1 - mean| rounds to one double for the whole
+    plateau) and varies materially in m2.  The reference's lexicographic maximum is then decided on m2 among ALL plateau points;
+    the leaves only hold the points with extreme m1.  Pass A checks every row against the norms it was given, so the fused step
+    must not return silently: mft_synchronize reports MFT_ENORMS; the separate kernels (two passes) are unaffected."""
+    import mft_b200 as m
+
+    cl = m.cloud.jittered_lattice(64, 48, 8.0, 6.0, seed=3)
+    pts = cl.points
+    rng = np.random.default_rng(9)
+    n = len(pts)
+    plateau = pts[:, 0] < 4.0
+    u0 = np.stack([np.where(plateau, 2.0, 1.0), np.where(plateau, 1e-20 * rng.standard_normal(n), 1.0),
+                   np.where(plateau, np.sin(2.0 * pts[:, 1]), 0.0), np.full(n, 30.0)])
+    u0 = np.ascontiguousarray(u0)
+    kinds = dict(left="nothing", right="nothing", bottom="nothing", top="nothing")
+    ic = lambda x, t, e=None: _table(cl, u0, x)   # noqa: E731
+    L = m._lib
+    lib = m.load()
+    norms = {}
+    for fused in (True, False):
+        semi, _ = _semi(m, cl, ic, kinds, "residual", fused)
+        L.check(lib.mft_upload_state(semi.ctx, L.soa_ptrs(u0)))
+        L.check(lib.mft_history_push(semi.ctx, 0.0, 0, 3))
+        L.check(lib.mft_ssprk_step(semi.ctx, L.SSPRK33, 0.0, 0.0))      # dt = 0: every stage sees exactly u0
+        rc = lib.mft_synchronize(semi.ctx)
+        out = np.zeros(4)
+        L.check(lib.mft_get_field(semi.ctx, L.FIELD_NORMS, L.ptr(out)))
+        norms[fused] = out
+        if fused:
+            assert rc == -6, rc                                          # MFT_ENORMS
+            assert b"one-pass" in lib.mft_last_error()
+            miss = np.zeros(1)
+            L.check(lib.mft_get_field(semi.ctx, L.FIELD_NORM_MISSES, L.ptr(miss)))
+            assert miss[0] > 0
+            assert lib.mft_synchronize(semi.ctx) == 0                    # reported once per occurrence
+        else:
+            assert rc == 0
+        semi.close()
+    # the first two keys agree (same maximal |rho - mean| and the rounded |m1 - mean|); the third is where the tie is decided
+    assert np.array_equal(norms[True][:2], norms[False][:2]) and norms[True][2] < norms[False][2]
