@@ -33,6 +33,21 @@ constexpr int kTileWarps = MFT_TILE_WARPS;
 #define MFT_TILE_OCC_B 5
 #endif
 
+// steps per batch of the R <= 2 main loops (loads of a batch are issued together, then consumed in order) and software pipelining
+// of the operator fetch (1: the step words + weights of batch i+1 are requested before batch i is consumed)
+#ifndef MFT_TILE_BATCH_A
+#define MFT_TILE_BATCH_A 4
+#endif
+#ifndef MFT_TILE_BATCH_B
+#define MFT_TILE_BATCH_B 6
+#endif
+#ifndef MFT_TILE_PIPE_A
+#define MFT_TILE_PIPE_A 0
+#endif
+#ifndef MFT_TILE_PIPE_B
+#define MFT_TILE_PIPE_B 0
+#endif
+
 __device__ __forceinline__ double2 lds2(const unsigned char *arr, uint32_t off)
 {
     return *reinterpret_cast<const double2 *>(arr + off);
@@ -229,6 +244,10 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
         // fused step on several GPUs: the first block turns the ranks' norm records into the norms (they are needed in the
         // epilogues only, by then the records have long arrived)
         if (A.norm_merge == 1 && blockIdx.x == 0 && warp == 0) p2p_norms_merge(*A.P, A.L, A.divisor, A.norm_lex, const_cast<double *>(A.stats), lane);
+        // (One GPU: the stage kernel's last block finishes the norms itself.  Moving that combine here -- block 0, while the other
+        // blocks run their main loops -- was measured three ways in round 2 and lost every time: block 0 shares L2 with 887 block
+        // prologues, its round trips take microseconds, and the whole first wave then waits in its epilogue: pass A +11 ... +29 us
+        // per launch against 9 us saved in the stage kernel; profiles/README.md.)
     }
 
     // Several GPUs: the norms of this stage (mean | raw maximum | norms, 12 doubles) come from block 0 of this very launch.  A
@@ -295,7 +314,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
     if (W > 0) mbar_wait(&bars[warp], 0);
 
     const double gm1 = A.eqp0 - 1.0;
-    constexpr int kBatch = R <= 2 ? 4 : 2;
+    constexpr int kBatch = R <= 2 ? MFT_TILE_BATCH_A : 2;
     auto pressure = [&](const double2 &qa, const double2 &qb, const double2 &qc) {
         const double s = fma(qa.y, qc.x, qb.x * qc.y);
         const double e = fma(-0.5, s, qb.y);
@@ -336,11 +355,24 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
                     }
                 }
             };
+            [[maybe_unused]] uint32_t wordn[kBatch];
+            [[maybe_unused]] double wn[kBatch][R];
+            if constexpr (MFT_TILE_PIPE_A != 0) fetch(0, wordn, wn);
             for (int c0 = 0; c0 < W; c0 += kBatch) {
                 double2 qa[kBatch], qb[kBatch], qc[kBatch];
                 uint32_t wordc[kBatch];
                 double w[kBatch][R];
-                fetch(c0, wordc, w);
+                if constexpr (MFT_TILE_PIPE_A != 0) {
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b) {
+                        wordc[b] = wordn[b];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) w[b][r] = wn[b][r];
+                    }
+                    if (c0 + kBatch < W) fetch(c0 + kBatch, wordn, wn);
+                } else {
+                    fetch(c0, wordc, w);
+                }
 #pragma unroll
                 for (int b = 0; b < kBatch; ++b) {
                     const uint32_t o = ((wordc[b] & 0xfffu) << 4) + (R <= 2 ? ((wordc[b] >> 14) & 1u) * arr_bytes : 0u);
@@ -492,16 +524,22 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_A : R 
             if constexpr (VISC == VISC_RESIDUAL) {
                 if (A.stats && A.norm_miss) {
                     // the norms are the lexicographic (or per-component) maximum of |u - mean| over ALL points: check this row
-                    double dv[V];
+                    // (lexicographic order: a row can only exceed the norms if its FIRST key reaches theirs -- one subtraction and
+                    // one compare for all but the handful of rows at the density extremes)
+                    const double d0 = fabs(ui.a[0] - nmean[0]);
+                    if (!A.norm_lex || d0 >= nraw[0]) {
+                        double dv[V];
+                        dv[0] = d0;
 #pragma unroll
-                    for (int v = 0; v < V; ++v) dv[v] = fabs(ui.a[v] - nmean[v]);
-                    bool miss = false;
-                    if (A.norm_lex) miss = lex_less<V>(nraw, dv);
-                    else {
+                        for (int v = 1; v < V; ++v) dv[v] = fabs(ui.a[v] - nmean[v]);
+                        bool miss = false;
+                        if (A.norm_lex) miss = lex_less<V>(nraw, dv);
+                        else {
 #pragma unroll
-                        for (int v = 0; v < V; ++v) miss |= dv[v] > nraw[v];
+                            for (int v = 0; v < V; ++v) miss |= dv[v] > nraw[v];
+                        }
+                        if (miss) atomicAdd(A.norm_miss, 1ull);
                     }
-                    if (miss) atomicAdd(A.norm_miss, 1ull);
                 }
             }
             Vec<2 * V> gout;
@@ -620,7 +658,7 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_B : R 
     if (!has_slice) return;
     if (W > 0) mbar_wait(&bars[warp], 0);
 
-    constexpr int kBatch = R <= 2 ? 4 : 2;
+    constexpr int kBatch = R <= 2 ? MFT_TILE_BATCH_B : 2;
     if constexpr (STAGE_W) {
         auto sweep = [&](auto dir_tag) {
             constexpr int DIR = decltype(dir_tag)::value;
@@ -701,11 +739,27 @@ __global__ void __launch_bounds__(kTileWarps * 32, (R == 1 ? MFT_TILE_OCC_B : R 
                 }
             }
         };
+        [[maybe_unused]] uint32_t wordn[kBatch];
+        [[maybe_unused]] double wan[kBatch][R], wbn[kBatch][R];
+        if constexpr (MFT_TILE_PIPE_B != 0) fetch(0, wordn, wan, wbn);
         for (int c0 = 0; c0 < W; c0 += kBatch) {
             double2 qa[kBatch], qb[kBatch], qc[kBatch], qd[kBatch];
             uint32_t wordc[kBatch];
             double wa[kBatch][R], wb[kBatch][R];
-            fetch(c0, wordc, wa, wb);
+            if constexpr (MFT_TILE_PIPE_B != 0) {
+#pragma unroll
+                for (int b = 0; b < kBatch; ++b) {
+                    wordc[b] = wordn[b];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        wa[b][r] = wan[b][r];
+                        wb[b][r] = wbn[b][r];
+                    }
+                }
+                if (c0 + kBatch < W) fetch(c0 + kBatch, wordn, wan, wbn);
+            } else {
+                fetch(c0, wordc, wa, wb);
+            }
 #pragma unroll
             for (int b = 0; b < kBatch; ++b) {
                 const uint32_t o = ((wordc[b] & 0xfffu) << 4) + (R <= 2 ? ((wordc[b] >> 14) & 1u) * arr_bytes : 0u);
