@@ -219,7 +219,8 @@ def run_ours(args):
                                                                 tile=int(args.tile), tile_rows=int(args.tile_rows),
                                                                 prefetch_distance=args.pf_dist, setup=args.setup,
                                                                 refine_order=bool(args.refine_order),
-                                                                fused_step=bool(args.fused_step), pdl=bool(args.pdl)))
+                                                                fused_step=bool(args.fused_step), pdl=bool(args.pdl),
+                                                                layout_device=bool(args.layout_device)))
     names = dict(left=1, right=2, bottom=3, top=4)
     t_setup = time.time()
     domain = m.ParallelPointCloudDomain(solver, cl, names, comm) if multi else m.PointCloudDomain(solver, cl, names)
@@ -398,7 +399,8 @@ def run_ours(args):
                           "l2": "inputs larger than L2 (operators 2 x %.0f MB per GPU streamed every stage)" % (n_own * 20 * k / 1e6),
                           "setup_s": round(t_setup, 1), "setup": args.setup,
                           "layout": {"tile": int(args.tile), "tile_rows": int(args.tile_rows), "refine_order": int(args.refine_order),
-                                     "exchange": args.exchange if multi else None, "fused_step": int(args.fused_step)},
+                                     "exchange": args.exchange if multi else None, "fused_step": int(args.fused_step),
+                                     "built_on": "device" if args.layout_device else "host threads"},
                           "gpu_topology": topo},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "parity": parity, "norm_misses": int(miss[0]),
@@ -593,6 +595,7 @@ def main():
     ap.add_argument("--fused-step", type=int, default=1, help="0: separate stage / boundary / norm / halo put / wait kernels (round-1 sequence)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="label of the JSON line: weak (default: --n-side is the per-GPU lattice side) or strong (the caller chose --n-side so that the TOTAL cloud is fixed)")
+    ap.add_argument("--layout-device", type=int, default=1, help="0: union-tile layouts on host threads instead of the device builder (same bytes)")
     ap.add_argument("--pdl", type=int, default=1, help="0: no programmatic dependent launch between the kernels of a fused stage")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the untimed parity check against the serial oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")

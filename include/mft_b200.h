@@ -107,6 +107,9 @@ typedef struct mft_ctx mft_ctx;
 #define MFT_OPT_PDL 13             /* 1 (default): the kernels of a fused stage are launched as programmatic dependents of each other
                                     * (cudaLaunchAttributeProgrammaticStreamSerialization): a kernel starts its operator-only prologue
                                     * while its predecessor drains and waits (griddepcontrol.wait) before reading the predecessor's output */
+#define MFT_OPT_LAYOUT_DEVICE 14   /* 1 (default): the union-tile layouts (one row per thread, the default) are built on the GPU at
+                                    * mft_finalize -- one tile per warp, the per-tile code of csrc/mft_tile_build.cuh, byte-identical to
+                                    * the host builder; 0: host threads (also used for the 2 / 4 rows-per-thread variants) */
 #define MFT_OPT_PREFETCH_DISTANCE 6/* slices ahead for the L2 prefetch of operator data (weight blocks; union tiles: step words, weights, union
                                       list of the tile that many slices ahead).  Default 8 per SM; 0: off.               */
 
@@ -291,6 +294,17 @@ int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int with_perm, 
  * (1: bank-coloured slots, 2: two record copies, 4: tuned copies). */
 int mft_debug_tile_selftest_csr(int64_t n, int64_t n_rows, const int64_t *rowptr, const int32_t *col, int R, int layout,
                                 unsigned seed, double *stats6);  /* stats4 + STS.128 conflict degree of the phase-1 stores, copy 0 / copy 1 */
+
+/* Host-only: the portable per-tile builder (the code the device runs, csrc/mft_tile_build.cuh) against the host builder on the
+ * operator of mft_debug_tile_selftest / mft_debug_tile_selftest_csr: 0 when every array of the layout is identical. */
+int mft_debug_tile_build_compare(int64_t n, int k, int layout, int with_perm, unsigned seed);
+int mft_debug_tile_build_compare_csr(int64_t n, int64_t n_rows, const int64_t *rowptr, const int32_t *col, int layout, unsigned seed);
+/* Host-only: the recursion-free bank-group feasibility test of the portable builder against the augmenting-path matcher of the
+ * host builder (all instances with <= 3 points, then `trials` random ones with <= 8); *mismatches must come back 0. */
+int mft_debug_matcher_compare(unsigned seed, int trials, long long *mismatches);
+/* FNV-1a checksum (and size in bytes) of the union-tile layout a finalized context holds for the forward (0) or transposed (1)
+ * operator: lets a test compare the device-built layout with the host-built one. */
+int mft_debug_tiler_checksum(mft_ctx *ctx, int which, unsigned long long *fnv_out, long long *bytes_out);
 
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------------------------------------
  * replaces MPICache + perform_halo_update! (src/domains/PointCloudDomain/ParallelPointCloud.jl:6-71,

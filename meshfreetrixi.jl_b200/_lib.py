@@ -27,6 +27,7 @@ OPT_TILE = 10
 OPT_TILE_ROWS = 11
 OPT_FUSED_STEP = 12
 OPT_PDL = 13
+OPT_LAYOUT_DEVICE = 14
 VAR_DENSITY, VAR_PRESSURE = 0, 1
 FIELD_EPS, FIELD_EPS_UW, FIELD_EPS_RV, FIELD_EPS_C, FIELD_RESIDUAL, FIELD_APPROX_DU, FIELD_NORMS, FIELD_SIGMA, FIELD_IGR_STATUS, FIELD_NORM_MISSES = range(10)
 SSPRK33 = 0
@@ -39,7 +40,7 @@ EXPORTS = [
     "mft_apply_source", "mft_boundary_pass", "mft_upload_state", "mft_download_state", "mft_download_du",
     "mft_history_push", "mft_history_push_weights", "mft_ssprk_step", "mft_ssprk43_step", "mft_step_commit", "mft_get_field", "mft_synchronize", "mft_count_nonfinite",
     "mft_launch_count", "mft_timer_start", "mft_timer_stop", "mft_kernel_time_ms", "mft_set_kernel_timing", "mft_host_alloc", "mft_host_free",
-    "mft_host_register", "mft_host_unregister", "mft_sfc_order", "mft_debug_tile_selftest", "mft_debug_tile_selftest_csr", "mft_setup_knn", "mft_setup_knn_queries", "mft_setup_rbf_weights", "mft_setup_rbf_weights_rows", "mft_setup_rbf_weights_hybrid", "mft_set_neighbors", "mft_limiter_zhang_shu", "mft_set_stage_limiter", "mft_nccl_unique_id", "mft_comm_init", "mft_set_halo", "mft_p2p_handles", "mft_p2p_connect",
+    "mft_host_register", "mft_host_unregister", "mft_sfc_order", "mft_debug_tile_selftest", "mft_debug_tile_selftest_csr", "mft_debug_tile_build_compare", "mft_debug_tile_build_compare_csr", "mft_debug_matcher_compare", "mft_debug_tiler_checksum", "mft_setup_knn", "mft_setup_knn_queries", "mft_setup_rbf_weights", "mft_setup_rbf_weights_rows", "mft_setup_rbf_weights_hybrid", "mft_set_neighbors", "mft_limiter_zhang_shu", "mft_set_stage_limiter", "mft_nccl_unique_id", "mft_comm_init", "mft_set_halo", "mft_p2p_handles", "mft_p2p_connect",
 ]
 
 _lib = None
@@ -76,6 +77,10 @@ def load():
         "mft_set_stage_limiter": [vp, i32, vp, vp],
         "mft_debug_tile_selftest": [i64, i32, i32, i32, i32, C.c_uint, vp],
         "mft_debug_tile_selftest_csr": [i64, i64, vp, vp, i32, i32, C.c_uint, vp],
+        "mft_debug_tile_build_compare": [i64, i32, i32, i32, C.c_uint],
+        "mft_debug_tile_build_compare_csr": [i64, i64, vp, vp, i32, C.c_uint],
+        "mft_debug_matcher_compare": [C.c_uint, i32, C.POINTER(C.c_longlong)],
+        "mft_debug_tiler_checksum": [vp, i32, C.POINTER(C.c_ulonglong), C.POINTER(C.c_longlong)],
         "mft_set_equation": [vp, i32, vp, i32],
         "mft_set_option": [vp, i32, dbl],
         "mft_set_permutation": [vp, vp],

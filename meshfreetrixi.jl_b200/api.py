@@ -94,6 +94,7 @@ class RBFFDEngineCUDA:
     single_sweep_exact: bool = False   # k=20: exact-order pass A in one sweep (y-products parked in registers)
     refine_order: bool = False         # order the rows inside a tile by D' row length (fewer padding steps in pass B; opt-in)
     setup: str = "host"                # "device": kNN + RBF-FD weight solves on the GPU (mft_setup_knn / mft_setup_rbf_weights)
+    layout_device: bool = True         # union-tile layouts built on the GPU at finalize (False: host threads; same bytes)
 
 
 @dataclass
@@ -450,6 +451,7 @@ class SemidiscretizationHyperbolic:
         L.check(lib.mft_set_option(ctx, L.OPT_TILE_ROWS, float(eng.tile_rows)))
         L.check(lib.mft_set_option(ctx, L.OPT_FUSED_STEP, 1.0 if eng.fused_step else 0.0))
         L.check(lib.mft_set_option(ctx, L.OPT_PDL, 1.0 if eng.pdl else 0.0))
+        L.check(lib.mft_set_option(ctx, L.OPT_LAYOUT_DEVICE, 1.0 if eng.layout_device else 0.0))
         if eng.prefetch_distance is not None:
             L.check(lib.mft_set_option(ctx, L.OPT_PREFETCH_DISTANCE, float(eng.prefetch_distance)))
         if part is not None:

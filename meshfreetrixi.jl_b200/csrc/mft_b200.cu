@@ -200,6 +200,7 @@ struct mft_ctx {
     // fused step (mft_fused_kernels.cuh): per-row side table (boundary entry, halo routes), miss counter of the one-pass norms
     int fused_step = 1;
     int pdl = 1;                           // MFT_OPT_PDL: programmatic dependent launch between the kernels of a fused stage
+    int layout_device = 1;                 // MFT_OPT_LAYOUT_DEVICE: R = 1 union tiles are laid out by the device builder
     bool fused_active = false;             // the launches being issued belong to the fused step
     bool pdl_next = false;                 // the next fused kernel follows another kernel of the fused step directly
     DevBuf<int> row_aux;
@@ -533,6 +534,7 @@ extern "C" int mft_set_option(mft_ctx *c, int option, double value)
     case MFT_OPT_SINGLE_SWEEP_EXACT: c->kfix_ok = value != 0; break;
     case MFT_OPT_PAIR_ROWS: c->pair_rows = (int)value; break;
     case MFT_OPT_TILE: c->tile = (int)value; break;
+    case MFT_OPT_LAYOUT_DEVICE: c->layout_device = value != 0; break;
     case MFT_OPT_PDL:
         c->pdl = value != 0;
         for (auto &g : c->graphs)
@@ -797,6 +799,7 @@ extern "C" int mft_add_source(mft_ctx *c, int kind, const double *params, int np
 }
 
 #include "mft_layout_host.inl"
+#include "mft_layout_device.inl"
 
 // per-row side table of the fused stage kernel: boundary entry (merged table) and halo routes of a row
 static int build_row_aux(mft_ctx *c)
@@ -856,6 +859,15 @@ extern "C" int mft_finalize(mft_ctx *c)
     if (c->finalized) return MFT_OK;
     if (c->eq < 0) return fail(MFT_EINVAL, "mft_finalize: mft_set_equation was not called");
     const int64_t n = c->n_tot;
+    const bool trace = getenv("MFT_TRACE") != nullptr;
+    auto t_phase = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {   // MFT_TRACE: wall time of the setup phases of mft_finalize
+        if (!trace) return;
+        cudaDeviceSynchronize();
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mft] finalize: %-44s %.3f s\n", what, std::chrono::duration<double>(now - t_phase).count());
+        t_phase = now;
+    };
     Csr2 F, T;
     if (c->have_ell_input) {
         F = c->host_ell;
@@ -879,6 +891,7 @@ extern "C" int mft_finalize(mft_ctx *c)
         sort_rows_by_key(F, c->keys, true);
         sort_rows_by_key(T, c->keys, true);
     }
+    lap("operator rows (transpose, summation-key sort)");
     // Within blocks of device rows, order the rows by the length of their D' row: slices of the transposed operator then
     // have near-uniform width (little padding).  Sliced-ELL kernels: blocks of 256 rows (locality is untouched inside a block,
     // measured no gain: the gathers of a warp spread).  Union-tile kernels: block = one tile, so every tile keeps exactly its
@@ -931,10 +944,12 @@ extern "C" int mft_finalize(mft_ctx *c)
     if (tile_a) CHECK(build_tiler(c, F, c->n_local, c->tile_rows_a, (c->tile & 4) != 0, (c->tile & 8) != 0, c->fwd_tiler));
     else CHECK(build_ell(c, F, c->n_local, true, c->fwd));
     if (!tile_a && (c->pair_rows & 2) && c->V == 4) CHECK(build_ell_pairs(c, F, c->n_local, c->fwd_pair));
+    lap("forward operator layout");
     if (has_visc(c)) {
         if (tile_b) CHECK(build_tiler(c, T, c->n_local, c->tile_rows_b, (c->tile & 4) != 0, (c->tile & 8) != 0, c->tra_tiler));
         else if ((c->pair_rows & 1) && c->V == 4) CHECK(build_ell_pairs(c, T, c->n_local, c->tra_pair));
         else CHECK(build_ell(c, T, c->n_local, true, c->tra));
+        lap("transposed operator layout");
         CHECK(c->g.alloc((n + 1) * 2 * c->V));  // + zero dummy record
         CU(cudaMemset(c->g.p, 0, sizeof(double) * (n + 1) * 2 * c->V));
     }

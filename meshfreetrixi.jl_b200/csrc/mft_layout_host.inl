@@ -767,8 +767,13 @@ static int build_tiler_host(const mft_ctx *c, const Csr2 &A, int64_t nrows_dev, 
     return MFT_OK;
 }
 
+static int build_tiler_device(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, bool colour, bool two_copies, bool tune, DevTileR &out);
+
 static int build_tiler(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, int R, bool colour, bool two_copies, DevTileR &out)
 {
+    // default tiles (one row per thread): laid out on the device (mft_layout_device.inl; same bytes as the host builder below)
+    if (c->layout_device && R == 1 && nrows_dev > 0) return build_tiler_device(c, A, nrows_dev, colour, two_copies, (c->tile & 16) != 0, out);
+    const auto t_host0 = std::chrono::steady_clock::now();
     HostTileR h;
     CHECK(build_tiler_host(c, A, nrows_dev, R, colour, two_copies, h, (c->tile & 16) != 0));
     out.ncopy = h.ncopy;
@@ -787,6 +792,9 @@ static int build_tiler(mft_ctx *c, const Csr2 &A, int64_t nrows_dev, int R, bool
     CHECK(out.uoff.upload(h.uoff));
     CHECK(out.ulist.upload(h.ulist));
     CHECK(out.uslot.upload(h.uslot));
+    if (getenv("MFT_TRACE"))
+        fprintf(stderr, "[mft] union-tile layout on %d host threads: %d tiles, R = %d: %.3f s\n", host_threads(h.ntiles), h.ntiles, R,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count());
     return MFT_OK;
 }
 
@@ -911,11 +919,10 @@ static int tile_selftest_run(mft_ctx &ctx, const Csr2 &A, int64_t n, int k, int 
     return MFT_OK;
 }
 
-extern "C" int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int with_perm, unsigned seed, double *stats4)
+// the random ragged banded operator of the self tests (rows = the first n - n/7 points; optional window-shuffled permutation with
+// descending summation keys); returns the generator state for the caller's own draws
+static uint64_t selftest_operator(mft_ctx &ctx, Csr2 &A, int64_t n, int k, int with_perm, unsigned seed)
 {
-    if (n <= 0 || k <= 0 || k > n || (R != 1 && R != 2 && R != 4)) return fail(MFT_EINVAL, "mft_debug_tile_selftest: bad arguments");
-    NvtxRange range("tile layout selftest");
-    mft_ctx ctx;
     ctx.n_local = n - n / 7;  // some trailing "halo" columns without rows
     ctx.n_halo = n - ctx.n_local;
     ctx.n_tot = n;
@@ -934,7 +941,6 @@ extern "C" int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int 
         ctx.keys.resize(n);
         for (int64_t i = 0; i < n; ++i) ctx.keys[i] = (int64_t)(n - 1 - i) * 3;  // descending keys: order != column order
     }
-    Csr2 A;
     A.nrows = n;
     A.ptr.assign(n + 1, 0);
     for (int64_t r = 0; r < n; ++r) {
@@ -953,24 +959,30 @@ extern "C" int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int 
         }
         A.ptr[r + 1] = (int64_t)A.col.size();
     }
+    return st;
+}
+
+extern "C" int mft_debug_tile_selftest(int64_t n, int k, int R, int layout, int with_perm, unsigned seed, double *stats4)
+{
+    if (n <= 0 || k <= 0 || k > n || (R != 1 && R != 2 && R != 4)) return fail(MFT_EINVAL, "mft_debug_tile_selftest: bad arguments");
+    NvtxRange range("tile layout selftest");
+    mft_ctx ctx;
+    Csr2 A;
+    const uint64_t st = selftest_operator(ctx, A, n, k, with_perm, seed);
     return tile_selftest_run(ctx, A, n, k, R, layout, with_perm, st, stats4);
 }
 
 // the same self test on a caller-supplied sparsity (e.g. the kNN table of a real cloud or its transpose): rows = n_rows stencils
 // over n columns (0-based CSR, columns of a row in summation order = as given); weights are pseudo-random dyadic numbers
-extern "C" int mft_debug_tile_selftest_csr(int64_t n, int64_t n_rows, const int64_t *rowptr, const int32_t *col, int R, int layout,
-                                           unsigned seed, double *stats6)
+static int selftest_operator_csr(mft_ctx &ctx, Csr2 &A, int64_t n, int64_t n_rows, const int64_t *rowptr, const int32_t *col, unsigned seed,
+                                 uint64_t &st_out, int &kmax_out)
 {
-    if (n <= 0 || n_rows < 0 || n_rows > n || !rowptr || !col || (R != 1 && R != 2 && R != 4))
-        return fail(MFT_EINVAL, "mft_debug_tile_selftest_csr: bad arguments");
-    mft_ctx ctx;
     ctx.n_local = n_rows;
     ctx.n_halo = n - n_rows;
     ctx.n_tot = n;
     ctx.V = 4;
     uint64_t st = seed * 6364136223846793005ULL + 1442695040888963407ULL;
     auto rnd = [&]() { st = st * 6364136223846793005ULL + 1442695040888963407ULL; return (uint32_t)(st >> 33); };
-    Csr2 A;
     A.nrows = n;
     A.ptr.assign(n + 1, rowptr[n_rows]);
     int kmax = 1;
@@ -986,5 +998,20 @@ extern "C" int mft_debug_tile_selftest_csr(int64_t n, int64_t n_rows, const int6
         A.wx[p] = (double)(int)(rnd() % 2001 - 1000) / 64.0;
         A.wy[p] = (double)(int)(rnd() % 2001 - 1000) / 32.0;
     }
+    st_out = st;
+    kmax_out = kmax;
+    return MFT_OK;
+}
+
+extern "C" int mft_debug_tile_selftest_csr(int64_t n, int64_t n_rows, const int64_t *rowptr, const int32_t *col, int R, int layout,
+                                           unsigned seed, double *stats6)
+{
+    if (n <= 0 || n_rows < 0 || n_rows > n || !rowptr || !col || (R != 1 && R != 2 && R != 4))
+        return fail(MFT_EINVAL, "mft_debug_tile_selftest_csr: bad arguments");
+    mft_ctx ctx;
+    Csr2 A;
+    uint64_t st = 0;
+    int kmax = 1;
+    CHECK(selftest_operator_csr(ctx, A, n, n_rows, rowptr, col, seed, st, kmax));
     return tile_selftest_run(ctx, A, n, kmax, R, layout, 0, st, stats6, 6);
 }

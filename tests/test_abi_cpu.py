@@ -188,3 +188,83 @@ def test_union_tile_layout_property_random_structures():
         assert rc == 0, (n, n_rows, kmax, R, layout, lib.mft_last_error())
 
     run()
+
+
+# ---- the portable per-tile builder (csrc/mft_tile_build.cuh: the code the device layout kernels run) ----------------------------
+
+def test_bank_group_feasibility_equals_the_augmenting_path_matcher():
+    """The recursion-free two-choice test (union-find over the 8 bank groups: no component with more points than groups) gives
+    the answer of the host builder's bipartite matcher on every instance with <= 3 points and on 2M random ones with <= 8."""
+    m = _mft()
+    lib = m._lib.load()
+    bad = C.c_longlong(-1)
+    assert lib.mft_debug_matcher_compare(7, 2_000_000, C.byref(bad)) == 0, lib.mft_last_error()
+    assert bad.value == 0
+
+
+def test_portable_tile_builder_is_byte_identical_to_the_host_builder():
+    """Every array of the layout (step words, weights, slot tables of both copies, union lists, offsets, meta data) for random
+    ragged banded operators: all layout variants, with and without a device permutation, k = 5 ... 50, a partial last tile."""
+    m = _mft()
+    lib = m._lib.load()
+    for n, k, layout, perm in ((5000, 20, 7, 0), (5000, 20, 7, 1), (3000, 13, 3, 1), (3000, 30, 1, 0), (2000, 20, 0, 1), (700, 50, 7, 1),
+                               (100, 5, 7, 0), (129, 20, 7, 1), (5000, 42, 7, 1), (4000, 15, 6, 1), (1, 1, 7, 0)):
+        assert lib.mft_debug_tile_build_compare(n, k, layout, perm, 11) == 0, (n, k, layout, perm, lib.mft_last_error())
+    assert lib.mft_debug_tile_build_compare(0, 20, 7, 0, 1) != 0   # argument checks
+    assert lib.mft_debug_tile_build_compare(10, 20, 7, 0, 1) != 0
+
+
+def test_portable_tile_builder_on_a_real_stencil_structure():
+    """the kNN structure of the fixture cloud along the curve (forward operator: k entries per row; its transpose: ragged rows)"""
+    import numpy as np
+    import scipy.sparse as sp
+
+    m = _mft()
+    L = m._lib
+    lib = L.load()
+    fx = cases.fixture_setup()
+    pts = fx["points"]
+    order = L.sfc_order(pts)
+    rank = np.empty(len(pts), dtype=np.int64)
+    rank[order] = np.arange(len(pts))
+    nb = rank[fx["nb"][order]]
+    n, k = nb.shape
+    A = sp.csr_matrix((np.ones(n * k), (np.repeat(np.arange(n), k), nb.reshape(-1))), shape=(n, n))
+    A.sort_indices()
+    AT = A.T.tocsr()
+    AT.sort_indices()
+    for M in (A, AT):
+        rp = np.ascontiguousarray(M.indptr, dtype=np.int64)
+        ci = np.ascontiguousarray(M.indices, dtype=np.int32)
+        for layout in (0, 1, 3, 7):
+            assert lib.mft_debug_tile_build_compare_csr(n, n, L.ptr(rp), L.ptr(ci), layout, 9) == 0, (layout, lib.mft_last_error())
+        # fewer rows than columns (a partition's owned rows over owned + halo columns)
+        nr = n - n // 5
+        assert lib.mft_debug_tile_build_compare_csr(n, nr, L.ptr(rp[:nr + 1].copy()), L.ptr(ci), 7, 9) == 0, lib.mft_last_error()
+
+
+def test_portable_tile_builder_property_random_structures():
+    """hypothesis: random ragged sparsity patterns (empty rows, rows longer than a slice is wide, arbitrary summation order)"""
+    import numpy as np
+    from hypothesis import given, settings, strategies as st_
+
+    m = _mft()
+    L = m._lib
+    lib = L.load()
+
+    @settings(max_examples=40, deadline=None)
+    @given(st_.integers(1, 400), st_.integers(0, 60), st_.integers(0, 2 ** 31 - 1), st_.sampled_from([0, 1, 3, 7, 6]), st_.floats(0.0, 1.0))
+    def run(n, kmax, seed, layout, frac_rows):
+        rng = np.random.default_rng(seed)
+        n_rows = max(0, min(n, int(round(frac_rows * n))))
+        lens = rng.integers(0, min(kmax, n) + 1, size=n_rows)
+        rowptr = np.zeros(n_rows + 1, dtype=np.int64)
+        rowptr[1:] = np.cumsum(lens)
+        cols = np.concatenate([rng.choice(n, size=int(k), replace=False) for k in lens]) if n_rows and lens.sum() else np.zeros(0)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        if len(cols) == 0:
+            cols = np.zeros(1, dtype=np.int32)
+        rc = lib.mft_debug_tile_build_compare_csr(n, n_rows, L.ptr(rowptr), L.ptr(cols), layout, seed % 1000)
+        assert rc == 0, (n, n_rows, kmax, layout, lib.mft_last_error())
+
+    run()
