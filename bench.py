@@ -269,28 +269,64 @@ def run_ours(args):
         return t
 
     # ---- device-resident timed region: barrier + sync on both sides, CUDA events on the ctx stream, max over ranks ----
-    L.check(lib.mft_upload_state(ctx, L.soa_ptrs(u0)))
-    if residual:
-        L.check(lib.mft_history_push(ctx, 0.0, 0, 3))
+    # The fused step's one-pass ode_maximum statistic is verified row by row inside pass A; rows it missed (a rounding tie decided
+    # the reference's lexicographic order: DESIGN.md 3d) make mft_synchronize fail with MFT_ENORMS.  The bench reports them and
+    # NEVER times a region that had any: misses during warm-up are noted (norm_misses.warmup), misses inside the timed region send
+    # every rank to the two-pass kernels (MFT_OPT_FUSED_STEP = 0) and the region is run again.
+    MFT_ENORMS = -6
+
+    def sync_soft():
+        rc = lib.mft_synchronize(ctx)
+        if rc not in (0, MFT_ENORMS):
+            L.check(rc)
+
+    def norm_misses():
+        x = np.zeros(1)
+        L.check(lib.mft_get_field(ctx, L.FIELD_NORM_MISSES, L.ptr(x)))
+        return int(x[0])
+
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()   # nvidia-smi needs ~100 ms to deliver its first sample: start before the warm-up steps
-    t = steps(args.warmup, 0.0, 0)
-    L.check(lib.mft_synchronize(ctx))
-    barrier()
-    if rank == 0:
-        sampler.mark()
-    launches0 = lib.mft_launch_count(ctx)
-    L.check(lib.mft_timer_start(ctx))
-    t = steps(args.steps, t, args.warmup)
-    ms = C.c_double()
-    L.check(lib.mft_timer_stop(ctx, C.byref(ms)))
-    barrier()
-    launches = lib.mft_launch_count(ctx) - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = max_over_ranks(ms.value)
+
+    def timed_region():
+        L.check(lib.mft_upload_state(ctx, L.soa_ptrs(u0)))
+        if residual:
+            L.check(lib.mft_history_push(ctx, 0.0, 0, 3))
+        if rank == 0:
+            sampler.start()   # nvidia-smi needs ~100 ms to deliver its first sample: start before the warm-up steps
+        m0 = norm_misses()
+        t_ = steps(args.warmup, 0.0, 0)
+        sync_soft()
+        m1 = norm_misses()
+        barrier()
+        if rank == 0:
+            sampler.mark()
+        l0 = lib.mft_launch_count(ctx)
+        L.check(lib.mft_timer_start(ctx))
+        t_ = steps(args.steps, t_, args.warmup)
+        ms_ = C.c_double()
+        L.check(lib.mft_timer_stop(ctx, C.byref(ms_)))
+        barrier()
+        sync_soft()
+        m2 = norm_misses()
+        return t_, ms_.value, lib.mft_launch_count(ctx) - l0, (sampler.stop() if rank == 0 else None), m1 - m0, m2 - m1
+
+    t, ms_value, launches, clocks, miss_warm, miss_timed = timed_region()
+    fallback = None
+    if max_over_ranks(float(miss_timed)) > 0:
+        if rank == 0:
+            sys.stderr.write("bench: the one-pass norms missed rows inside the timed region; re-running with the two-pass kernels\n")
+        L.check(lib.mft_set_option(ctx, L.OPT_FUSED_STEP, 0.0))
+        sampler = ClockSampler(local_rank)
+        t, ms_value, launches, clocks, _, miss_again = timed_region()
+        fallback = "MFT_OPT_FUSED_STEP = 0 (two-pass norm kernels): the one-pass statistic missed rows inside the first timed region"
+        args.fused_step = 0
+        if max_over_ranks(float(miss_again)) > 0:
+            raise SystemExit("bench: norm misses with the two-pass kernels (cannot happen: they do not use the statistic)")
+    total_ms = max_over_ranks(ms_value)
     ms_per_step = total_ms / args.steps
     value = N * STAGES * args.steps / (total_ms * 1e-3)
+    miss_detail = {"warmup": int(max_over_ranks(float(miss_warm))), "timed": 0, "fallback": fallback,
+                   "note": "rows per rank (max over ranks) that exceeded the fused step's one-pass ode_maximum statistic; the timed region never has any"}
 
     # sanity: the state is still finite after the timed steps
     u_end = np.empty_like(u0)
@@ -403,7 +439,7 @@ def run_ours(args):
                                      "built_on": "device" if args.layout_device else "host threads"},
                           "gpu_topology": topo},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-               "parity": parity, "norm_misses": int(miss[0]),
+               "parity": parity, "norm_misses": int(miss[0]), "norm_misses_detail": miss_detail,
                # the reference's own (printed, never recorded) metric: PerformanceCallback's performance index
                # PID = runtime * nranks / (ndofsglobal * ncalls_rhs), src/callbacks_step/performance.jl:229-235 (one DOF = one point)
                "reference_native_metric": {"name": "PID [s per DOF per rhs! per rank]", "value": world / value}}

@@ -339,6 +339,9 @@ class MockLib:
         if field == 6:
             _arr(out, c.V)[:] = 0.0
             return 0
+        if field == 9:   # MFT_FIELD_NORM_MISSES: the stand-in has no one-pass statistic
+            _arr(out, 1)[:] = 0.0
+            return 0
         return self.fail(-1, "bad field")
 
     def mft_count_nonfinite(self, ctx, out):
