@@ -20,9 +20,20 @@
 // the mean is known.  Leaves merge associatively and commutatively (they are maxima), so blocks and ranks combine them in
 // any order with a bit-identical result; only the sums keep a fixed order.  Exact value ties (a far field at rho = 1.0
 // exactly with different momenta: 8 % of the points of the vortex workload, 1808 of them pinned by Dirichlet data) are
-// what the nested leaves are for.  What they cannot see is a ROUNDING tie (two different values whose deviations round to
-// the same double, deciding the order on a later key); pass A checks every row against the norms it was given and counts
-// misses (MFT_FIELD_NORM_MISSES), and MFT_OPT_FUSED_STEP = 0 selects the two-pass kernels.
+// what the nested leaves are for.
+//
+// Rounding ties on the first key.  fl|rho - m0| is monotone but not injective: with ode_mean's divisor V*N the mean sits on a
+// finer binary grid than the densities, rho - m0 falls between two doubles, and two ADJACENT densities (one ulp apart) can round
+// to the same deviation (ties-to-even at an exact half).  The 2-GPU bench cloud does it in its very first stage: 17 far-field
+// points share the largest density, the stage update moves five of them by one ulp, and the lexicographic order between the
+// two groups is then decided on |m1 - mean| (profiles/r2y_norm_miss_diagnostic_2ranks.log).  A single rounding can only merge
+// neighbours, so every record keeps the leaves of the extreme density AND of the next distinct density on either side
+// ("second level"); the finalize evaluates all 32 deviation vectors and takes their lexicographic maximum -- candidates whose
+// rounded first key is smaller simply lose.  What still cannot be seen is a rounding tie on a LATER key (a plateau that ties
+// exactly on rho and carries rounding noise in m1 around an O(1) mean: any number of values collapse) or a first key whose
+// deviation is coarser than the densities (|rho - m0| > 2 rho: never for positive densities and 0 <= m0 <= max rho); pass A
+// checks every row against the norms it was given and counts misses (MFT_FIELD_NORM_MISSES -> MFT_ENORMS), and
+// MFT_OPT_FUSED_STEP = 0 selects the two-pass kernels.
 #pragma once
 #include "mft_kernels.cuh"
 
@@ -34,7 +45,10 @@ constexpr int kRecExt = 4;     // 2: max rho, min rho
 constexpr int kRecLeaf = 6;    // 2 sides x 8 leaves x (m1, m2, E); leaf index bit c set = component c+1 is minimised
 constexpr int kRecCmax = 54;   // per-component mode (MFT_OPT_MAX_LEXICOGRAPHIC = 0): max and min of every component
 constexpr int kRecCmin = 58;
-// kRecDoubles = 64 (mft_kernels.cuh): padded to 512 bytes
+constexpr int kRecExt2 = 62;   // 2: the largest density below max rho, the smallest above min rho (-inf / +inf: none)
+constexpr int kRecLeaf2 = 64;  // their leaves, laid out like kRecLeaf
+// kRecDoubles = 128 (mft_kernels.cuh): 112 used, padded to 1 KB
+static_assert(kRecLeaf2 + 48 <= kRecDoubles, "norm record layout");
 
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -80,104 +94,230 @@ __device__ __forceinline__ double warp_extreme(double x, bool active)
     return key_f64(r);
 }
 
-// One chunk of 32 points (one per lane) against the warp's running record `wr` (shared memory), side 0 = max rho,
-// side 1 = min rho.  run_ext is the warp-uniform register copy of wr[kRecExt + SIDE].  Warp-uniform control flow.
-template <int SIDE>
-__device__ __forceinline__ void lex_side_update(double *wr, bool valid, double rho, double m1, double m2, double E, double &run_ext, int lane)
+// The 8 leaves of a tie set: `tied` = the lanes of this chunk that hold one density value.  Lanes 0..7 return leaf `lane`
+// (l1, l2, l3) = (m1, m2, E) of the point that is lexicographically extreme under the leaf's sign pattern.  Warp-uniform.
+__device__ __forceinline__ void tie_set_leaves(unsigned tied, double m1, double m2, double E, int lane, double &l1, double &l2, double &l3)
 {
-    const bool hot = valid && (SIDE == 0 ? rho >= run_ext : rho <= run_ext);   // (a NaN is never hot)
-    const unsigned hm = __ballot_sync(kFull, hot);
-    if (hm == 0) return;   // the common case: nobody reaches the running extreme
-    double cm;
-    unsigned tied;
-    if (__popc(hm) == 1) {   // one candidate: no reduction
-        cm = __shfl_sync(kFull, rho, __ffs(hm) - 1);
-        tied = hm;
-    } else {
-        cm = warp_extreme<SIDE == 1>(rho, hot);
-        tied = __ballot_sync(kFull, hot && rho == cm);
-    }
-    const bool reset = SIDE == 0 ? cm > run_ext : cm < run_ext;
-    double *leaf = wr + kRecLeaf + SIDE * 24;
-    if (!reset) {
-        // same extreme as before: a point only matters if its m1 reaches the running extremes of m1 over the tie set
-        const double m1max = leaf[0], m1min = leaf[3];   // leaf 0: maximise m1; leaf 1: minimise m1
-        tied = __ballot_sync(kFull, ((tied >> lane) & 1u) && (m1 >= m1max || m1 <= m1min));
-        if (tied == 0) return;
-    }
-    double l1, l2, l3;   // leaf `lane` of the tie set (lanes 0..7)
     if (__popc(tied) == 1) {
         // one point: it is every leaf of the set
         const int src = __ffs(tied) - 1;
         l1 = __shfl_sync(kFull, m1, src);
         l2 = __shfl_sync(kFull, m2, src);
         l3 = __shfl_sync(kFull, E, src);
-    } else {
-        // Level 1 first: only the lanes that hold the largest or the smallest m1 of the tie set can be a leaf (leaves with bit
-        // 0 clear maximise m1, the others minimise it).  On noisy plateaus (rho ties exactly, the momenta carry rounding noise)
-        // each of the two groups is a single lane and no deeper reduction is needed.
-        const bool in = (tied >> lane) & 1u;
-        const double g1max = warp_extreme<false>(m1, in), g1min = warp_extreme<true>(m1, in);
-        l1 = l2 = l3 = 0.0;
+        return;
+    }
+    // Level 1 first: only the lanes that hold the largest or the smallest m1 of the tie set can be a leaf (leaves with bit
+    // 0 clear maximise m1, the others minimise it).  On noisy plateaus (rho ties exactly, the momenta carry rounding noise)
+    // each of the two groups is a single lane and no deeper reduction is needed.
+    const bool in = (tied >> lane) & 1u;
+    const double g1max = warp_extreme<false>(m1, in), g1min = warp_extreme<true>(m1, in);
+    l1 = l2 = l3 = 0.0;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {   // half 0: leaves 0,2,4,6 (max m1); half 1: leaves 1,3,5,7 (min m1)
-            const double g1 = half == 0 ? g1max : g1min;
-            const unsigned grp = __ballot_sync(kFull, in && m1 == g1);
-            const bool ing = (grp >> lane) & 1u;
-            const int first = __ffs(grp) - 1;
-            const double r2 = __shfl_sync(kFull, m2, first), r3 = __shfl_sync(kFull, E, first);
-            if (lane < 8 && (lane & 1) == half) {
-                l1 = g1;
-                l2 = r2;
-                l3 = r3;
-            }
-            if (__ballot_sync(kFull, ing && (m2 != r2 || E != r3)) != 0) {
-                // several different states share rho and m1: nested extremes of (m2, E) per sign pattern
+    for (int half = 0; half < 2; ++half) {   // half 0: leaves 0,2,4,6 (max m1); half 1: leaves 1,3,5,7 (min m1)
+        const double g1 = half == 0 ? g1max : g1min;
+        const unsigned grp = __ballot_sync(kFull, in && m1 == g1);
+        const bool ing = (grp >> lane) & 1u;
+        const int first = __ffs(grp) - 1;
+        const double r2 = __shfl_sync(kFull, m2, first), r3 = __shfl_sync(kFull, E, first);
+        if (lane < 8 && (lane & 1) == half) {
+            l1 = g1;
+            l2 = r2;
+            l3 = r3;
+        }
+        if (__ballot_sync(kFull, ing && (m2 != r2 || E != r3)) != 0) {
+            // several different states share rho and m1: nested extremes of (m2, E) per sign pattern
 #pragma unroll 1
-                for (int q = 0; q < 4; ++q) {   // leaf = half | q << 1: bit 1 = minimise m2, bit 2 = minimise E
-                    const bool mn2 = q & 1, mn3 = (q >> 1) & 1;
-                    const double c2 = mn2 ? warp_extreme<true>(m2, ing) : warp_extreme<false>(m2, ing);
-                    const bool in2 = ing && m2 == c2;
-                    const double c3 = mn3 ? warp_extreme<true>(E, in2) : warp_extreme<false>(E, in2);
-                    if (lane == (half | (q << 1))) {
-                        l2 = c2;
-                        l3 = c3;
-                    }
+            for (int q = 0; q < 4; ++q) {   // leaf = half | q << 1: bit 1 = minimise m2, bit 2 = minimise E
+                const bool mn2 = q & 1, mn3 = (q >> 1) & 1;
+                const double c2 = mn2 ? warp_extreme<true>(m2, ing) : warp_extreme<false>(m2, ing);
+                const bool in2 = ing && m2 == c2;
+                const double c3 = mn3 ? warp_extreme<true>(E, in2) : warp_extreme<false>(E, in2);
+                if (lane == (half | (q << 1))) {
+                    l2 = c2;
+                    l3 = c3;
                 }
             }
         }
     }
-    __syncwarp();
-    if (lane < 8) {
-        double *lf = leaf + lane * 3;
-        if (reset || leaf_better(l1, l2, l3, lf[0], lf[1], lf[2], lane)) {
-            lf[0] = l1;
-            lf[1] = l2;
-            lf[2] = l3;
-        }
-    }
-    if (lane == 0 && reset) wr[kRecExt + SIDE] = cm;
-    __syncwarp();
-    run_ext = cm;
 }
 
-// slot = side * 8 + leaf: merge candidate (ext, l1..l3) into the running best (bext, b1..b3)
-__device__ __forceinline__ void slot_merge(int slot, double ext, double l1, double l2, double l3, double &bext, double &b1, double &b2, double &b3)
+// One chunk of 32 points (one per lane) against the warp's running record `wr` (shared memory), side 0 = max rho,
+// side 1 = min rho.  run_ext / run_ext2 are the warp-uniform register copies of wr[kRecExt + SIDE] / wr[kRecExt2 + SIDE]: the
+// extreme density so far and the next distinct one.  A chunk can contribute its two most extreme distinct values; anything
+// else in it is third at best.  Warp-uniform control flow.
+template <int SIDE>
+__device__ __forceinline__ void lex_side_update(double *wr, bool valid, double rho, double m1, double m2, double E, double &run_ext,
+                                                double &run_ext2, int lane)
+{
+    auto reaches = [](double x, double y) { return SIDE == 0 ? x >= y : x <= y; };
+    auto beyond = [](double x, double y) { return SIDE == 0 ? x > y : x < y; };
+    unsigned hm = __ballot_sync(kFull, valid && reaches(rho, run_ext2));   // (a NaN is never hot)
+    if (hm == 0) return;   // the common case: nobody reaches the second running value
+#pragma unroll 1
+    for (int level = 0; level < 2; ++level) {
+        double cm;
+        unsigned tied;
+        if (__popc(hm) == 1) {   // one candidate: no reduction
+            cm = __shfl_sync(kFull, rho, __ffs(hm) - 1);
+            tied = hm;
+        } else {
+            const bool in = (hm >> lane) & 1u;
+            cm = warp_extreme<SIDE == 1>(rho, in);
+            tied = __ballot_sync(kFull, in && rho == cm);
+        }
+        hm &= ~tied;
+        // where the value goes: 0 beyond the running extreme (which becomes the second value), 1 equal to it, 2 a new second
+        // value, 3 equal to the second value (it reaches run_ext2, or it would not be hot)
+        const int where = beyond(cm, run_ext) ? 0 : cm == run_ext ? 1 : beyond(cm, run_ext2) ? 2 : 3;
+        double *leaf = wr + (where <= 1 ? kRecLeaf : kRecLeaf2) + SIDE * 24;
+        if (where == 1 || where == 3) {
+            // a value seen before: a point only matters if its m1 reaches the running extremes of m1 over that tie set
+            const double m1max = leaf[0], m1min = leaf[3];   // leaf 0: maximise m1; leaf 1: minimise m1
+            tied = __ballot_sync(kFull, ((tied >> lane) & 1u) && (m1 >= m1max || m1 <= m1min));
+        }
+        if (tied != 0) {
+            double l1, l2, l3;   // leaf `lane` of the tie set (lanes 0..7)
+            tie_set_leaves(tied, m1, m2, E, lane, l1, l2, l3);
+            __syncwarp();
+            double *lf = leaf + (lane & 7) * 3;
+            if (where == 0) {
+                if (lane < 8) {   // the old extreme and its leaves move to the second level
+                    double *l2nd = wr + kRecLeaf2 + SIDE * 24 + lane * 3;
+                    l2nd[0] = lf[0];
+                    l2nd[1] = lf[1];
+                    l2nd[2] = lf[2];
+                    lf[0] = l1;
+                    lf[1] = l2;
+                    lf[2] = l3;
+                }
+                if (lane == 0) {
+                    wr[kRecExt2 + SIDE] = run_ext;
+                    wr[kRecExt + SIDE] = cm;
+                }
+                run_ext2 = run_ext;
+                run_ext = cm;
+            } else if (where == 2) {
+                if (lane < 8) {
+                    lf[0] = l1;
+                    lf[1] = l2;
+                    lf[2] = l3;
+                }
+                if (lane == 0) wr[kRecExt2 + SIDE] = cm;
+                run_ext2 = cm;
+            } else if (lane < 8 && leaf_better(l1, l2, l3, lf[0], lf[1], lf[2], lane)) {
+                lf[0] = l1;
+                lf[1] = l2;
+                lf[2] = l3;
+            }
+            __syncwarp();
+        }
+        // the rest of the chunk only matters where it still reaches the (possibly new) second value
+        hm = __ballot_sync(kFull, ((hm >> lane) & 1u) && reaches(rho, run_ext2));
+        if (hm == 0) break;
+    }
+}
+
+// ---- slots ------------------------------------------------------------------------------------------------------------
+// slot = side * 8 + leaf.  A thread that owns a slot carries the leaf of the extreme density (e; a1..a3) and of the next distinct
+// density (e2; c1..c3); records are folded in with slot_insert: leaves are maxima, so any order gives the same bits.
+struct Slot2 {
+    double e, a1, a2, a3, e2, c1, c2, c3;
+};
+__device__ __forceinline__ void slot_init(int slot, Slot2 &S)
+{
+    S.e = S.e2 = (slot >> 3) == 0 ? neg_inf() : pos_inf();
+    S.a1 = S.a2 = S.a3 = S.c1 = S.c2 = S.c3 = 0.0;
+}
+// one density value `ext` with its leaf (l1, l2, l3) into the two-level state of the slot
+__device__ __forceinline__ void slot_insert(int slot, double ext, double l1, double l2, double l3, Slot2 &S)
 {
     const int side = slot >> 3, lf = slot & 7;
-    const bool better_ext = side == 0 ? ext > bext : ext < bext;
-    if (better_ext || (ext == bext && leaf_better(l1, l2, l3, b1, b2, b3, lf))) {
-        bext = ext;
-        b1 = l1;
-        b2 = l2;
-        b3 = l3;
+    const bool beyond1 = side == 0 ? ext > S.e : ext < S.e;
+    if (beyond1) {
+        S.e2 = S.e;
+        S.c1 = S.a1;
+        S.c2 = S.a2;
+        S.c3 = S.a3;
+        S.e = ext;
+        S.a1 = l1;
+        S.a2 = l2;
+        S.a3 = l3;
+    } else if (ext == S.e) {
+        if (leaf_better(l1, l2, l3, S.a1, S.a2, S.a3, lf)) {
+            S.a1 = l1;
+            S.a2 = l2;
+            S.a3 = l3;
+        }
+    } else if (side == 0 ? ext > S.e2 : ext < S.e2) {
+        S.e2 = ext;
+        S.c1 = l1;
+        S.c2 = l2;
+        S.c3 = l3;
+    } else if (ext == S.e2) {
+        if (leaf_better(l1, l2, l3, S.c1, S.c2, S.c3, lf)) {
+            S.c1 = l1;
+            S.c2 = l2;
+            S.c3 = l3;
+        }
     }
+}
+__device__ __forceinline__ void slot_merge(int slot, const Slot2 &X, Slot2 &S)
+{
+    slot_insert(slot, X.e, X.a1, X.a2, X.a3, S);
+    slot_insert(slot, X.e2, X.c1, X.c2, X.c3, S);   // (X.e2 is below X.e: the order of the two inserts does not matter)
+}
+// LD: 0 plain (shared memory / this block's data), 1 __ldcg (another block's record, at L2), 2 __ldcv (another GPU's record)
+template <int LD>
+__device__ __forceinline__ Slot2 slot_load(const double *R, int slot)
+{
+    auto ld = [](const double *p) -> double { return LD == 0 ? *p : LD == 1 ? __ldcg(p) : __ldcv(p); };
+    const int side = slot >> 3, lf = slot & 7;
+    const double *q = R + kRecLeaf + side * 24 + lf * 3, *q2 = R + kRecLeaf2 + side * 24 + lf * 3;
+    Slot2 X;
+    X.e = ld(R + kRecExt + side);
+    X.a1 = ld(q);
+    X.a2 = ld(q + 1);
+    X.a3 = ld(q + 2);
+    X.e2 = ld(R + kRecExt2 + side);
+    X.c1 = ld(q2);
+    X.c2 = ld(q2 + 1);
+    X.c3 = ld(q2 + 2);
+    return X;
+}
+__device__ __forceinline__ void slot_store(double *R, int slot, const Slot2 &S)
+{
+    const int side = slot >> 3, lf = slot & 7;
+    if (lf == 0) {
+        R[kRecExt + side] = S.e;
+        R[kRecExt2 + side] = S.e2;
+    }
+    double *q = R + kRecLeaf + side * 24 + lf * 3, *q2 = R + kRecLeaf2 + side * 24 + lf * 3;
+    q[0] = S.a1;
+    q[1] = S.a2;
+    q[2] = S.a3;
+    q2[0] = S.c1;
+    q2[1] = S.c2;
+    q2[2] = S.c3;
+}
+__device__ __forceinline__ Slot2 slot_shfl_xor(const Slot2 &S, int mask)
+{
+    Slot2 X;
+    X.e = __shfl_xor_sync(kFull, S.e, mask);
+    X.a1 = __shfl_xor_sync(kFull, S.a1, mask);
+    X.a2 = __shfl_xor_sync(kFull, S.a2, mask);
+    X.a3 = __shfl_xor_sync(kFull, S.a3, mask);
+    X.e2 = __shfl_xor_sync(kFull, S.e2, mask);
+    X.c1 = __shfl_xor_sync(kFull, S.c1, mask);
+    X.c2 = __shfl_xor_sync(kFull, S.c2, mask);
+    X.c3 = __shfl_xor_sync(kFull, S.c3, mask);
+    return X;
 }
 
 // ode_mean + ode_maximum(|u - mean|) from `nrec` records (one per rank; the sums are combined in rank order), by ONE WARP:
-// lanes 0..3 form the means, lanes 0..15 each merge one (side, leaf) slot over the ranks and evaluate its deviation vector,
-// a shuffle tree takes the lexicographic maximum.  Writes mean[4], norms[4] (zero -> eps) and raw[4] (before the zero
-// replacement: what pass A verifies rows against).  VOL: the records were written by other GPUs -- read them past L1.
+// lanes 0..3 form the means; lane = level * 16 + slot folds its (side, leaf) slot over the ranks and evaluates the deviation vector
+// of the slot's first (lanes 0..15) or second (lanes 16..31) density level; a shuffle tree takes the lexicographic maximum of
+// the 32 vectors.  Writes mean[4], norms[4] (zero -> eps) and raw[4] (before the zero replacement: what pass A verifies rows
+// against).  VOL: the records were written by other GPUs -- read them past L1.
 template <bool VOL>
 __device__ inline void norms_from_records(const double *recs, int stride, int nrec, double divisor, int lex, double *mean_out, double *norms_out, double *raw_out, int lane)
 {
@@ -194,20 +334,17 @@ __device__ inline void norms_from_records(const double *recs, int stride, int nr
     for (int v = 0; v < 4; ++v) m[v] = __shfl_sync(kFull, mv, v);
     double c[4] = {-1.0, -1.0, -1.0, -1.0};
     if (lex) {
-        if (lane < 16) {
-            const int side = lane >> 3, lf = lane & 7;
-            double bext = side == 0 ? neg_inf() : pos_inf(), b1 = 0.0, b2 = 0.0, b3 = 0.0;
-            for (int r = 0; r < nrec; ++r) {
-                const double *R = recs + (size_t)r * stride;
-                const double *q = R + kRecLeaf + side * 24 + lf * 3;
-                slot_merge(lane, ld(R + kRecExt + side), ld(q), ld(q + 1), ld(q + 2), bext, b1, b2, b3);
-            }
-            if (bext > neg_inf() && bext < pos_inf()) {   // (no owned rows anywhere, or a non-finite state: no candidate)
-                c[0] = fabs(bext - m[0]);
-                c[1] = fabs(b1 - m[1]);
-                c[2] = fabs(b2 - m[2]);
-                c[3] = fabs(b3 - m[3]);
-            }
+        const int slot = lane & 15;
+        Slot2 S;
+        slot_init(slot, S);
+        for (int r = 0; r < nrec; ++r) slot_merge(slot, slot_load<VOL ? 2 : 0>(recs + (size_t)r * stride, slot), S);
+        const bool second = lane >= 16;
+        const double ext = second ? S.e2 : S.e, b1 = second ? S.c1 : S.a1, b2 = second ? S.c2 : S.a2, b3 = second ? S.c3 : S.a3;
+        if (ext > neg_inf() && ext < pos_inf()) {   // (no such density level anywhere, or a non-finite state: no candidate)
+            c[0] = fabs(ext - m[0]);
+            c[1] = fabs(b1 - m[1]);
+            c[2] = fabs(b2 - m[2]);
+            c[3] = fabs(b3 - m[3]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -324,8 +461,8 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
             cmn[v] = pos_inf();
         }
     }
-    double run_max = neg_inf(), run_min = pos_inf();
-    if (NMODE == NORMS_LEX && lane < 2) wrec[w][kRecExt + lane] = lane == 0 ? neg_inf() : pos_inf();
+    double run_max = neg_inf(), run_min = pos_inf(), run_max2 = neg_inf(), run_min2 = pos_inf();
+    if (NMODE == NORMS_LEX && lane < 2) wrec[w][kRecExt + lane] = wrec[w][kRecExt2 + lane] = lane == 0 ? neg_inf() : pos_inf();
     __syncwarp();
     const double dt = A.dt, dt2 = 2.0 * A.dt;
     const int stage = A.stage;
@@ -450,8 +587,8 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
                 for (int v = 0; v < V; ++v) s[v] += un.a[v];
             }
             if constexpr (NMODE == NORMS_LEX) {
-                lex_side_update<0>(wrec[w], valid, un.a[0], un.a[1], un.a[2], un.a[3], run_max, lane);
-                lex_side_update<1>(wrec[w], valid, un.a[0], un.a[1], un.a[2], un.a[3], run_min, lane);
+                lex_side_update<0>(wrec[w], valid, un.a[0], un.a[1], un.a[2], un.a[3], run_max, run_max2, lane);
+                lex_side_update<1>(wrec[w], valid, un.a[0], un.a[1], un.a[2], un.a[3], run_min, run_min2, lane);
             } else if (valid) {
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
@@ -496,17 +633,11 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
         }
         if constexpr (NMODE == NORMS_LEX) {
             if (threadIdx.x < 16) {
-                const int slot = threadIdx.x, side = slot >> 3, lf = slot & 7;
-                double bext = side == 0 ? neg_inf() : pos_inf(), b1 = 0.0, b2 = 0.0, b3 = 0.0;
-                for (int k = 0; k < 8; ++k) {
-                    const double *q = &wrec[k][kRecLeaf + side * 24 + lf * 3];
-                    slot_merge(slot, wrec[k][kRecExt + side], q[0], q[1], q[2], bext, b1, b2, b3);
-                }
-                if (lf == 0) prec[kRecExt + side] = bext;
-                double *q = prec + kRecLeaf + side * 24 + lf * 3;
-                q[0] = b1;
-                q[1] = b2;
-                q[2] = b3;
+                const int slot = threadIdx.x;
+                Slot2 S;
+                slot_init(slot, S);
+                for (int k = 0; k < 8; ++k) slot_merge(slot, slot_load<0>(wrec[k], slot), S);
+                slot_store(prec, slot, S);
             }
         } else if (threadIdx.x < 8) {
             const int v = threadIdx.x & 3;
@@ -519,7 +650,7 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
     // ---- group records: the last block of every group of kStageGroup blocks merges the group's leaves (parallel over the
     // groups: no single serial tail; whoever combines the whole grid afterwards reads gridDim.x / 16 records, one round trip)
     __shared__ double fin[kRecDoubles];
-    __shared__ double xw[8][16][4];
+    __shared__ Slot2 xw[8][16];
     __shared__ bool glast;
     const int nb = (int)gridDim.x;
     if constexpr (NORMS) {
@@ -535,33 +666,16 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
             __threadfence();
             double *G = A.grec + (size_t)g * kRecDoubles;
             if constexpr (NMODE == NORMS_LEX) {
-                const int slot = threadIdx.x & 15, j = threadIdx.x >> 4, side = slot >> 3, lf = slot & 7;
-                double bext = side == 0 ? neg_inf() : pos_inf(), b1 = 0.0, b2 = 0.0, b3 = 0.0;
-                if (j < gsize) {
-                    const double *R = A.partial + (size_t)(g * kStageGroup + j) * kRecDoubles;
-                    const double *q = R + kRecLeaf + side * 24 + lf * 3;
-                    bext = __ldcg(R + kRecExt + side);
-                    b1 = __ldcg(q);
-                    b2 = __ldcg(q + 1);
-                    b3 = __ldcg(q + 2);
-                }
-                const double oe = __shfl_xor_sync(kFull, bext, 16), o1 = __shfl_xor_sync(kFull, b1, 16);
-                const double o2 = __shfl_xor_sync(kFull, b2, 16), o3 = __shfl_xor_sync(kFull, b3, 16);
-                slot_merge(slot, oe, o1, o2, o3, bext, b1, b2, b3);
-                if (lane < 16) {
-                    xw[w][slot][0] = bext;
-                    xw[w][slot][1] = b1;
-                    xw[w][slot][2] = b2;
-                    xw[w][slot][3] = b3;
-                }
+                const int slot = threadIdx.x & 15, j = threadIdx.x >> 4;
+                Slot2 S;
+                slot_init(slot, S);
+                if (j < gsize) S = slot_load<1>(A.partial + (size_t)(g * kStageGroup + j) * kRecDoubles, slot);
+                slot_merge(slot, slot_shfl_xor(S, 16), S);   // lanes slot and slot + 16 hold the same slot
+                if (lane < 16) xw[w][slot] = S;
                 __syncthreads();
                 if (threadIdx.x < 16) {
-                    for (int k = 1; k < 8; ++k) slot_merge(slot, xw[k][slot][0], xw[k][slot][1], xw[k][slot][2], xw[k][slot][3], bext, b1, b2, b3);
-                    if (lf == 0) G[kRecExt + side] = bext;
-                    double *q = G + kRecLeaf + side * 24 + lf * 3;
-                    q[0] = b1;
-                    q[1] = b2;
-                    q[2] = b3;
+                    for (int k = 1; k < 8; ++k) slot_merge(slot, xw[k][slot], S);
+                    slot_store(G, slot, S);
                 }
             } else if (threadIdx.x < 8) {
                 const int v = threadIdx.x & 3;
@@ -611,33 +725,16 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
         }
         if constexpr (NMODE == NORMS_LEX) {
             // thread = (j, slot): 16 scanners per (side, leaf) slot over the group records, then the scanners of a slot merge
-            const int slot = threadIdx.x & 15, j = threadIdx.x >> 4, side = slot >> 3, lf = slot & 7;
-            double bext = side == 0 ? neg_inf() : pos_inf(), b1 = 0.0, b2 = 0.0, b3 = 0.0;
-            for (int b = j; b < ng; b += 16) {
-                const double *R = A.grec + (size_t)b * kRecDoubles;
-                const double *q = R + kRecLeaf + side * 24 + lf * 3;
-                slot_merge(slot, __ldcg(R + kRecExt + side), __ldcg(q), __ldcg(q + 1), __ldcg(q + 2), bext, b1, b2, b3);
-            }
-            {   // lanes slot and slot + 16 hold the same slot
-                const double oe = __shfl_xor_sync(kFull, bext, 16), o1 = __shfl_xor_sync(kFull, b1, 16);
-                const double o2 = __shfl_xor_sync(kFull, b2, 16), o3 = __shfl_xor_sync(kFull, b3, 16);
-                slot_merge(slot, oe, o1, o2, o3, bext, b1, b2, b3);
-            }
-            if (lane < 16) {
-                xw[w][slot][0] = bext;
-                xw[w][slot][1] = b1;
-                xw[w][slot][2] = b2;
-                xw[w][slot][3] = b3;
-            }
+            const int slot = threadIdx.x & 15, j = threadIdx.x >> 4;
+            Slot2 S;
+            slot_init(slot, S);
+            for (int b = j; b < ng; b += 16) slot_merge(slot, slot_load<1>(A.grec + (size_t)b * kRecDoubles, slot), S);
+            slot_merge(slot, slot_shfl_xor(S, 16), S);   // lanes slot and slot + 16 hold the same slot
+            if (lane < 16) xw[w][slot] = S;
             __syncthreads();
             if (threadIdx.x < 16) {
-                for (int k = 0; k < 8; ++k)
-                    if (k != w) slot_merge(slot, xw[k][slot][0], xw[k][slot][1], xw[k][slot][2], xw[k][slot][3], bext, b1, b2, b3);
-                if (lf == 0) fin[kRecExt + side] = bext;
-                double *q = fin + kRecLeaf + side * 24 + lf * 3;
-                q[0] = b1;
-                q[1] = b2;
-                q[2] = b3;
+                for (int k = 1; k < 8; ++k) slot_merge(slot, xw[k][slot], S);
+                slot_store(fin, slot, S);
             }
         } else if (threadIdx.x < 8) {
             const int v = threadIdx.x & 3;

@@ -1367,7 +1367,7 @@ __global__ void k_halo_pack(const Vec<W> *__restrict__ src, const int *__restric
 // after that peer has signalled (credit flag) that it consumed the previous epoch.
 // =====================================================================================================================
 constexpr int kMaxRanks = 16;
-constexpr int kRecDoubles = 64;  // one norm record (mft_fused_kernels.cuh): sums + lexicographic leaves, 512 bytes
+constexpr int kRecDoubles = 128; // one norm record (mft_fused_kernels.cuh): sums + two levels of lexicographic leaves, 1 KB
 constexpr unsigned long long kSpinLimit = 1ull << 31;  // ~ seconds: then give up and raise the error flag
 
 struct P2PWindow {                                 // lives in every rank's memory; peers write into it

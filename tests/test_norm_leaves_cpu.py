@@ -119,3 +119,55 @@ def test_a_rounding_tie_is_what_leaves_cannot_see():
     assert len(np.unique(np.abs(u[: n // 2, 1] - mean[1]))) == 1          # the rounding tie
     got, want = norms_from_leaves(leaves(u), mean), brute(u, mean)
     assert np.array_equal(got[:2], want[:2]) and got[2] < want[2]
+
+
+# ---- the second density level (round 2): rounding ties on the FIRST key ---------------------------------------------------------
+
+def leaves2(u):
+    """the record of the device statistic: per side the leaves of the extreme density and of the next distinct density"""
+    out = []
+    vals = np.unique(u[:, 0])
+    for level_vals in (vals[::-1][:2], vals[:2]):      # max side: two largest distinct densities; min side: two smallest
+        for v in level_vals:
+            out.append(leaves(u[u[:, 0] == v]))
+    return np.concatenate(out)
+
+
+def test_adjacent_densities_can_tie_after_rounding_and_the_second_level_sees_it():
+    """17 far-field points share the largest density T (the 2-GPU bench cloud, profiles/r2y_norm_miss_diagnostic_2ranks.log); a stage
+    update moves some of them to T + ulp.  With the mean on a finer grid (ode_mean divides by V*N) |T - m| and |T + ulp - m| round
+    to the same double for half of the means: the lexicographic maximum is then decided on |m1 - mean| among BOTH groups.  One
+    level of leaves (the exact maximum only) misses that; two levels do not -- for every mean."""
+    rng = np.random.default_rng(5)
+    T = 1.0 - 5 * 2.0 ** -53
+    n = 4000
+    u = np.stack([0.4 + 0.5 * rng.random(n), 1.0 + 1e-3 * rng.standard_normal(n), 1e-3 * rng.standard_normal(n), 30 + rng.random(n)], axis=1)
+    tie = np.arange(17)
+    u[tie, 0] = T
+    u[tie, 1] = 1.0 + 5e-7 * np.linspace(-1.0, 1.0, 17)
+    moved = tie[[2, 9]]                                    # two rows, not the ones with the extreme momenta
+    one_level_fails = two_level_fails = collisions = 0
+    for up in (np.nextafter(T, 2.0), np.nextafter(T, 0.0)):
+        w = u.copy()
+        w[moved, 0] = up
+        base = w.sum(axis=0) / (4.0 * n)
+        for k in range(-16, 17):                           # the last bits of the mean decide whether the two densities collide
+            mean = base.copy()
+            mean[0] = base[0] + k * 2.0 ** -56
+            want = brute(w, mean)
+            d0 = np.abs(w[:, 0] - mean[0])
+            if len(np.unique(w[d0 == d0.max(), 0])) > 1:
+                collisions += 1
+            one_level_fails += not np.array_equal(norms_from_leaves(leaves(w), mean), want)
+            two_level_fails += not np.array_equal(norms_from_leaves(leaves2(w), mean), want)
+    assert collisions > 0 and one_level_fails > 0          # the failure mode is real ...
+    assert two_level_fails == 0                            # ... and the second level removes it
+
+
+def test_two_levels_on_tie_heavy_and_generic_states():
+    rng = np.random.default_rng(13)
+    for trial in range(80):
+        u = _tie_heavy(rng, int(rng.integers(1, 300)), int(rng.integers(1, 6))) if trial % 2 else rng.standard_normal((int(rng.integers(1, 300)), 4))
+        for div in (4.0 * len(u), float(len(u))):
+            mean = u.sum(axis=0) / div
+            assert np.array_equal(norms_from_leaves(leaves2(u), mean), brute(u, mean))

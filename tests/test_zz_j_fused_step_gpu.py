@@ -160,6 +160,49 @@ def test_one_pass_norms_on_tied_states(lex, vn):
             _both(m, cl, ic, kinds, "residual", u0, dt, 2, max_lexicographic=lex, mean_divisor_vn=vn)
 
 
+def test_adjacent_densities_that_tie_after_rounding():
+    """The 2-GPU bench cloud's first stage (profiles/r2y_norm_miss_diagnostic_2ranks.log): 17 points share the largest density T,
+    a few of them sit one ulp above / below it, and with the V*N divisor of ode_mean the deviations |T - m0| and |T +- ulp - m0|
+    round to the same double for half of the means -- the order is then decided on |m1 - mean| among BOTH density groups.  The
+    statistic keeps a second density level for exactly this; the means' last bits are swept by nudging one far-away row."""
+    import mft_b200 as m
+
+    cl = m.cloud.jittered_lattice(80, 72, 10.0, 9.0, seed=7)
+    n = len(cl.points)
+    X, Y = cl.points[:, 0], cl.points[:, 1]
+    rng = np.random.default_rng(11)
+    kinds = dict(left="nothing", right="nothing", bottom="nothing", top="nothing")
+    T = 1.0 - 5 * 2.0 ** -53
+    base = np.stack([0.5 + 0.3 * np.sin(X) * np.cos(Y), 1.0 + 0.01 * np.cos(X), 0.01 * np.sin(Y), 30.0 + np.sin(3.1 * X)])
+    tie = rng.choice(n, 17, replace=False)
+    base[0, tie] = T
+    base[1, tie] = 1.0 + 5e-7 * np.linspace(-1.0, 1.0, 17)
+    far = int(np.argsort(base[0])[n // 2])                        # a row in the middle of the density range: only moves the mean
+    ic = lambda x, t, e=None: _table(cl, base, x)                 # noqa: E731  (no Dirichlet boundary: never evaluated on the device)
+    semi_f, _ = _semi(m, cl, ic, kinds, "residual", True)
+    semi_c, _ = _semi(m, cl, ic, kinds, "residual", False)
+    decided_on_m1 = 0
+    for up in (np.nextafter(T, 2.0), np.nextafter(T, 0.0)):
+        for k in range(64):
+            u0 = base.copy()
+            u0[0, tie[[2, 9]]] = up                               # not the rows with the extreme momenta
+            u0[0, far] += k * 4.0 * n * 2.0 ** -56                # shifts ode_mean(rho) = sum / (4 n) by about k * 2^-56
+            u0 = np.ascontiguousarray(u0)
+            uf, duf, nf, mf = _run(m, semi_f, u0, 0.0, 1, True)
+            uc, duc, nc, _ = _run(m, semi_c, u0, 0.0, 1, True)
+            assert mf == 0, f"{mf} rows exceeded the one-pass norms (k = {k})"
+            assert np.array_equal(nf, nc), (k, nf, nc)
+            assert np.array_equal(uf, uc) and np.array_equal(duf, duc)
+            # did the two density groups tie after rounding?  then |m1 - mean| of the norms belongs to a row of the OTHER group
+            dev1 = np.abs(u0[1, tie] - u0[1].sum() / (4.0 * n))
+            j = int(np.argmin(np.abs(dev1 - nc[1])))
+            top = up if up > T else T
+            decided_on_m1 += int(u0[0, tie[j]] != top)
+    semi_f.close()
+    semi_c.close()
+    assert decided_on_m1 > 0, "none of the swept means made the two densities tie: the sweep does not exercise the second level"
+
+
 def _table(cl, u0, x):
     """Dirichlet data = the state itself at the queried boundary points (nearest point of the cloud)"""
     from scipy.spatial import cKDTree
