@@ -79,6 +79,26 @@ __device__ __forceinline__ double key_f64(unsigned long long k)
     const long long b = (long long)k;
     return __longlong_as_double(b ^ (((~b) >> 63) | (long long)0x8000000000000000LL));
 }
+// The second density level only has to cover values that can share a rounded deviation with the extreme: its neighbours on the
+// grid of doubles.  kNearUlps bounds the distance (in representable steps) at which a value is still kept as "second level"; 1
+// would do while the deviation is no coarser than the densities (0 <= mean <= max rho, comparable minimum), a few more cover
+// a minimum that is several times smaller than the mean.  near_enough(a, b): b lies at most kNearUlps steps inside of a.
+constexpr unsigned long long kNearUlps = 4;
+template <int SIDE>
+__device__ __forceinline__ bool near_enough(double a, double b)
+{
+    const unsigned long long ka = f64_key(a), kb = f64_key(b);
+    return SIDE == 0 ? (kb <= ka && ka - kb <= kNearUlps) : (kb >= ka && kb - ka <= kNearUlps);
+}
+// the value kNearUlps steps inside of a (a finite; -inf / +inf map to themselves: nothing has been seen yet)
+template <int SIDE>
+__device__ __forceinline__ double window_bound(double a)
+{
+    if (!(a > neg_inf() && a < pos_inf())) return a;
+    const unsigned long long ka = f64_key(a);
+    return key_f64(SIDE == 0 ? ka - kNearUlps : ka + kNearUlps);
+}
+
 // maximum (MIN: minimum) of x over the lanes with `active` set, through two 32-bit REDUX operations on the keys instead of
 // five rounds of 64-bit shuffles + FP64 compares; inactive lanes contribute the neutral key.  All 32 lanes must call it.
 template <bool MIN>
@@ -142,17 +162,18 @@ __device__ __forceinline__ void tie_set_leaves(unsigned tied, double m1, double 
 }
 
 // One chunk of 32 points (one per lane) against the warp's running record `wr` (shared memory), side 0 = max rho,
-// side 1 = min rho.  run_ext / run_ext2 are the warp-uniform register copies of wr[kRecExt + SIDE] / wr[kRecExt2 + SIDE]: the
-// extreme density so far and the next distinct one.  A chunk can contribute its two most extreme distinct values; anything
-// else in it is third at best.  Warp-uniform control flow.
+// side 1 = min rho.  Warp-uniform register state: run_ext = wr[kRecExt + SIDE], the extreme density so far; has2 / run_thr: is
+// there a second level (the next distinct density, at most kNearUlps steps inside the extreme), and the value a row has to reach
+// to matter at all -- that second density, or the window bound while there is none.  A chunk can contribute its two most
+// extreme distinct values; anything else in it is third at best.  Warp-uniform control flow.
 template <int SIDE>
 __device__ __forceinline__ void lex_side_update(double *wr, bool valid, double rho, double m1, double m2, double E, double &run_ext,
-                                                double &run_ext2, int lane)
+                                                double &run_thr, bool &has2, int lane)
 {
     auto reaches = [](double x, double y) { return SIDE == 0 ? x >= y : x <= y; };
     auto beyond = [](double x, double y) { return SIDE == 0 ? x > y : x < y; };
-    unsigned hm = __ballot_sync(kFull, valid && reaches(rho, run_ext2));   // (a NaN is never hot)
-    if (hm == 0) return;   // the common case: nobody reaches the second running value
+    unsigned hm = __ballot_sync(kFull, valid && reaches(rho, run_thr));   // (a NaN is never hot)
+    if (hm == 0) return;   // the common case: nobody comes near the running extreme
 #pragma unroll 1
     for (int level = 0; level < 2; ++level) {
         double cm;
@@ -166,9 +187,9 @@ __device__ __forceinline__ void lex_side_update(double *wr, bool valid, double r
             tied = __ballot_sync(kFull, in && rho == cm);
         }
         hm &= ~tied;
-        // where the value goes: 0 beyond the running extreme (which becomes the second value), 1 equal to it, 2 a new second
-        // value, 3 equal to the second value (it reaches run_ext2, or it would not be hot)
-        const int where = beyond(cm, run_ext) ? 0 : cm == run_ext ? 1 : beyond(cm, run_ext2) ? 2 : 3;
+        // where the value goes: 0 beyond the running extreme, 1 equal to it, 3 equal to the second density, 2 a new second density
+        // (between the two, or the first one inside the window)
+        const int where = beyond(cm, run_ext) ? 0 : cm == run_ext ? 1 : (has2 && cm == run_thr) ? 3 : 2;
         double *leaf = wr + (where <= 1 ? kRecLeaf : kRecLeaf2) + SIDE * 24;
         if (where == 1 || where == 3) {
             // a value seen before: a point only matters if its m1 reaches the running extremes of m1 over that tie set
@@ -181,20 +202,25 @@ __device__ __forceinline__ void lex_side_update(double *wr, bool valid, double r
             __syncwarp();
             double *lf = leaf + (lane & 7) * 3;
             if (where == 0) {
-                if (lane < 8) {   // the old extreme and its leaves move to the second level
-                    double *l2nd = wr + kRecLeaf2 + SIDE * 24 + lane * 3;
-                    l2nd[0] = lf[0];
-                    l2nd[1] = lf[1];
-                    l2nd[2] = lf[2];
+                // the old extreme and its leaves become the second level if they are near enough, else there is none any more
+                const bool keep = near_enough<SIDE>(cm, run_ext);
+                if (lane < 8) {
+                    if (keep) {
+                        double *l2nd = wr + kRecLeaf2 + SIDE * 24 + lane * 3;
+                        l2nd[0] = lf[0];
+                        l2nd[1] = lf[1];
+                        l2nd[2] = lf[2];
+                    }
                     lf[0] = l1;
                     lf[1] = l2;
                     lf[2] = l3;
                 }
                 if (lane == 0) {
-                    wr[kRecExt2 + SIDE] = run_ext;
+                    wr[kRecExt2 + SIDE] = keep ? run_ext : (SIDE == 0 ? neg_inf() : pos_inf());
                     wr[kRecExt + SIDE] = cm;
                 }
-                run_ext2 = run_ext;
+                has2 = keep;
+                run_thr = keep ? run_ext : window_bound<SIDE>(cm);
                 run_ext = cm;
             } else if (where == 2) {
                 if (lane < 8) {
@@ -203,7 +229,8 @@ __device__ __forceinline__ void lex_side_update(double *wr, bool valid, double r
                     lf[2] = l3;
                 }
                 if (lane == 0) wr[kRecExt2 + SIDE] = cm;
-                run_ext2 = cm;
+                has2 = true;
+                run_thr = cm;
             } else if (lane < 8 && leaf_better(l1, l2, l3, lf[0], lf[1], lf[2], lane)) {
                 lf[0] = l1;
                 lf[1] = l2;
@@ -211,8 +238,8 @@ __device__ __forceinline__ void lex_side_update(double *wr, bool valid, double r
             }
             __syncwarp();
         }
-        // the rest of the chunk only matters where it still reaches the (possibly new) second value
-        hm = __ballot_sync(kFull, ((hm >> lane) & 1u) && reaches(rho, run_ext2));
+        // the rest of the chunk only matters where it still reaches the (possibly new) threshold
+        hm = __ballot_sync(kFull, ((hm >> lane) & 1u) && reaches(rho, run_thr));
         if (hm == 0) break;
     }
 }
@@ -228,16 +255,22 @@ __device__ __forceinline__ void slot_init(int slot, Slot2 &S)
     S.e = S.e2 = (slot >> 3) == 0 ? neg_inf() : pos_inf();
     S.a1 = S.a2 = S.a3 = S.c1 = S.c2 = S.c3 = 0.0;
 }
-// one density value `ext` with its leaf (l1, l2, l3) into the two-level state of the slot
+// one density value `ext` with its leaf (l1, l2, l3) into the two-level state of the slot (second level: the next distinct density,
+// kept only while it lies within kNearUlps steps of the extreme -- the same rule as in lex_side_update)
 __device__ __forceinline__ void slot_insert(int slot, double ext, double l1, double l2, double l3, Slot2 &S)
 {
     const int side = slot >> 3, lf = slot & 7;
+    auto near = [&](double a, double b) { return side == 0 ? near_enough<0>(a, b) : near_enough<1>(a, b); };
     const bool beyond1 = side == 0 ? ext > S.e : ext < S.e;
     if (beyond1) {
-        S.e2 = S.e;
-        S.c1 = S.a1;
-        S.c2 = S.a2;
-        S.c3 = S.a3;
+        if (near(ext, S.e)) {
+            S.e2 = S.e;
+            S.c1 = S.a1;
+            S.c2 = S.a2;
+            S.c3 = S.a3;
+        } else {
+            S.e2 = side == 0 ? neg_inf() : pos_inf();
+        }
         S.e = ext;
         S.a1 = l1;
         S.a2 = l2;
@@ -248,13 +281,13 @@ __device__ __forceinline__ void slot_insert(int slot, double ext, double l1, dou
             S.a2 = l2;
             S.a3 = l3;
         }
-    } else if (side == 0 ? ext > S.e2 : ext < S.e2) {
-        S.e2 = ext;
-        S.c1 = l1;
-        S.c2 = l2;
-        S.c3 = l3;
-    } else if (ext == S.e2) {
-        if (leaf_better(l1, l2, l3, S.c1, S.c2, S.c3, lf)) {
+    } else if (near(S.e, ext)) {
+        if (side == 0 ? ext > S.e2 : ext < S.e2) {
+            S.e2 = ext;
+            S.c1 = l1;
+            S.c2 = l2;
+            S.c3 = l3;
+        } else if (ext == S.e2 && leaf_better(l1, l2, l3, S.c1, S.c2, S.c3, lf)) {
             S.c1 = l1;
             S.c2 = l2;
             S.c3 = l3;
@@ -264,7 +297,7 @@ __device__ __forceinline__ void slot_insert(int slot, double ext, double l1, dou
 __device__ __forceinline__ void slot_merge(int slot, const Slot2 &X, Slot2 &S)
 {
     slot_insert(slot, X.e, X.a1, X.a2, X.a3, S);
-    slot_insert(slot, X.e2, X.c1, X.c2, X.c3, S);   // (X.e2 is below X.e: the order of the two inserts does not matter)
+    if (X.e2 > neg_inf() && X.e2 < pos_inf()) slot_insert(slot, X.e2, X.c1, X.c2, X.c3, S);   // (absent in almost every record)
 }
 // LD: 0 plain (shared memory / this block's data), 1 __ldcg (another block's record, at L2), 2 __ldcv (another GPU's record)
 template <int LD>
@@ -279,9 +312,12 @@ __device__ __forceinline__ Slot2 slot_load(const double *R, int slot)
     X.a2 = ld(q + 1);
     X.a3 = ld(q + 2);
     X.e2 = ld(R + kRecExt2 + side);
-    X.c1 = ld(q2);
-    X.c2 = ld(q2 + 1);
-    X.c3 = ld(q2 + 2);
+    X.c1 = X.c2 = X.c3 = 0.0;
+    if (X.e2 > neg_inf() && X.e2 < pos_inf()) {
+        X.c1 = ld(q2);
+        X.c2 = ld(q2 + 1);
+        X.c3 = ld(q2 + 2);
+    }
     return X;
 }
 __device__ __forceinline__ void slot_store(double *R, int slot, const Slot2 &S)
@@ -461,7 +497,8 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
             cmn[v] = pos_inf();
         }
     }
-    double run_max = neg_inf(), run_min = pos_inf(), run_max2 = neg_inf(), run_min2 = pos_inf();
+    double run_max = neg_inf(), run_min = pos_inf(), thr_max = neg_inf(), thr_min = pos_inf();
+    bool has2_max = false, has2_min = false;
     if (NMODE == NORMS_LEX && lane < 2) wrec[w][kRecExt + lane] = wrec[w][kRecExt2 + lane] = lane == 0 ? neg_inf() : pos_inf();
     __syncwarp();
     const double dt = A.dt, dt2 = 2.0 * A.dt;
@@ -587,8 +624,8 @@ __global__ void __launch_bounds__(256, MFT_STAGE_OCC) k_stage_fused(const StageA
                 for (int v = 0; v < V; ++v) s[v] += un.a[v];
             }
             if constexpr (NMODE == NORMS_LEX) {
-                lex_side_update<0>(wrec[w], valid, un.a[0], un.a[1], un.a[2], un.a[3], run_max, run_max2, lane);
-                lex_side_update<1>(wrec[w], valid, un.a[0], un.a[1], un.a[2], un.a[3], run_min, run_min2, lane);
+                lex_side_update<0>(wrec[w], valid, un.a[0], un.a[1], un.a[2], un.a[3], run_max, thr_max, has2_max, lane);
+                lex_side_update<1>(wrec[w], valid, un.a[0], un.a[1], un.a[2], un.a[3], run_min, thr_min, has2_min, lane);
             } else if (valid) {
 #pragma unroll
                 for (int v = 0; v < V; ++v) {

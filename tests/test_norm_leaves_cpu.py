@@ -123,12 +123,21 @@ def test_a_rounding_tie_is_what_leaves_cannot_see():
 
 # ---- the second density level (round 2): rounding ties on the FIRST key ---------------------------------------------------------
 
-def leaves2(u):
-    """the record of the device statistic: per side the leaves of the extreme density and of the next distinct density"""
+def _steps_inside(x, k, direction):
+    for _ in range(k):
+        x = np.nextafter(x, direction)
+    return x
+
+
+def leaves2(u, near_ulps=4):
+    """the record of the device statistic: per side the leaves of the extreme density and of the next distinct density, the latter
+    only if it lies within `near_ulps` representable steps of the extreme (kNearUlps in csrc/mft_fused_kernels.cuh)"""
     out = []
     vals = np.unique(u[:, 0])
-    for level_vals in (vals[::-1][:2], vals[:2]):      # max side: two largest distinct densities; min side: two smallest
-        for v in level_vals:
+    for level_vals, inside in ((vals[::-1][:2], -np.inf), (vals[:2], np.inf)):   # max side: two largest distinct; min side: two smallest
+        for i, v in enumerate(level_vals):
+            if i == 1 and abs(v - level_vals[0]) > abs(_steps_inside(level_vals[0], near_ulps, inside) - level_vals[0]):
+                continue
             out.append(leaves(u[u[:, 0] == v]))
     return np.concatenate(out)
 
