@@ -79,6 +79,10 @@ class MockLib:
         return 42
 
     def mft_synchronize(self, ctx):
+        c = self._c(ctx)
+        if getattr(c, "norm_misses", 0) > getattr(c, "norm_misses_seen", 0):   # loud once, like check_norm_misses
+            c.norm_misses_seen = c.norm_misses
+            return self.fail(-6, "fused step: rows exceeded the one-pass ode_maximum statistic (mock)")
         return 0
 
     # --- ctx
@@ -249,6 +253,7 @@ class MockLib:
         self.mft_finalize(ctx)
         c.u = self._get(soa, c)
         c.have_fsal = False
+        c.nsteps_since_upload = 0
         return 0
 
     def mft_download_state(self, ctx, soa):
@@ -270,6 +275,15 @@ class MockLib:
     def mft_ssprk_step(self, ctx, scheme, t, dt):
         c = self._c(ctx)
         self.mft_finalize(ctx)
+        # MFT_MOCK_NORM_MISSES="step,count": pretend that the fused step's one-pass norms missed `count` rows in the step-th
+        # mft_ssprk_step call since the last mft_upload_state (the two-pass kernels, MFT_OPT_FUSED_STEP = 0, never miss): lets a
+        # CPU test drive the miss handling of bench.py
+        c.nsteps_since_upload = getattr(c, "nsteps_since_upload", 0) + 1
+        spec = os.environ.get("MFT_MOCK_NORM_MISSES")
+        if spec and c.opts.get(12, 1.0) != 0.0:
+            step, count = (int(x) for x in spec.split(","))
+            if c.nsteps_since_upload == step:
+                c.norm_misses = getattr(c, "norm_misses", 0) + count
         L = orc.lib()
         t, dt = float(t), float(dt)
         u = c.u
@@ -339,8 +353,8 @@ class MockLib:
         if field == 6:
             _arr(out, c.V)[:] = 0.0
             return 0
-        if field == 9:   # MFT_FIELD_NORM_MISSES: the stand-in has no one-pass statistic
-            _arr(out, 1)[:] = 0.0
+        if field == 9:   # MFT_FIELD_NORM_MISSES: the stand-in has no one-pass statistic (see MFT_MOCK_NORM_MISSES)
+            _arr(out, 1)[:] = float(getattr(c, "norm_misses", 0))
             return 0
         return self.fail(-1, "bad field")
 
