@@ -34,7 +34,8 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "mft_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inl", ".h"))]
+    deps.append(os.path.join(HERE, "..", "include", "mft_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
