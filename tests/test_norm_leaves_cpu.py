@@ -180,3 +180,190 @@ def test_two_levels_on_tie_heavy_and_generic_states():
         for div in (4.0 * len(u), float(len(u))):
             mean = u.sum(axis=0) / div
             assert np.array_equal(norms_from_leaves(leaves2(u), mean), brute(u, mean))
+
+
+# ---- a model of the DEVICE bookkeeping (csrc/mft_fused_kernels.cuh: lex_side_update, slot_insert, norms_from_records) ------------
+# The functions below restate, value for value, what a warp does with a chunk of 32 rows and how records are folded into each other
+# (same branches, same window rule), so that the sufficiency and the order independence of the windowed two-level records can be
+# checked on adversarial data without a GPU: densities on a few-ulp grid around the extremes, exact ties at every level, random
+# splits into chunks / warps / ranks, random merge orders.  (The CUDA code itself is compared with the two-pass kernels on the
+# device: tests/test_zz_j_fused_step_gpu.py.)
+
+K_NEAR = 4
+SIGNS = [tuple(1.0 if not (k >> c) & 1 else -1.0 for c in range(3)) for k in range(8)]   # leaf bit c set: component c+1 minimised
+
+
+def _key(x):
+    b = np.float64(x).view(np.int64)
+    return int(b) ^ (0x7FFFFFFFFFFFFFFF if b < 0 else 0) if b < 0 else int(b)   # monotone in x (signed integer order)
+
+
+def _near(side, a, b):
+    """b lies at most K_NEAR representable steps inside of a (side 0: below, side 1: above)"""
+    if not (np.isfinite(a) and np.isfinite(b)):
+        return False
+    ka, kb = _key(a), _key(b)
+    return 0 <= (ka - kb if side == 0 else kb - ka) <= K_NEAR
+
+
+def _leaf_better(a, b, k):
+    for c in range(3):
+        if SIGNS[k][c] * a[c] > SIGNS[k][c] * b[c]:
+            return True
+        if SIGNS[k][c] * a[c] < SIGNS[k][c] * b[c]:
+            return False
+    return False
+
+
+def _tie_leaves(rows):
+    """8 leaves of a tie set: rows (n, 3) = (m1, m2, E)"""
+    out = []
+    for k in range(8):
+        best = rows[0]
+        for r in rows[1:]:
+            if _leaf_better(r, best, k):
+                best = r
+        out.append(tuple(best))
+    return out
+
+
+class SideRec:
+    def __init__(self, side):
+        self.side, self.e, self.e2, self.L, self.L2 = side, (-np.inf if side == 0 else np.inf), (-np.inf if side == 0 else np.inf), None, None
+
+    def beyond(self, x, y):
+        return x > y if self.side == 0 else x < y
+
+    def insert(self, ext, leaves):
+        """slot_insert for the 8 leaf slots of this side at once (their (e, e2) evolve identically)"""
+        if leaves is None or not np.isfinite(ext):
+            return
+        if self.beyond(ext, self.e):
+            if _near(self.side, ext, self.e):
+                self.e2, self.L2 = self.e, self.L
+            else:
+                self.e2, self.L2 = (-np.inf if self.side == 0 else np.inf), None
+            self.e, self.L = ext, list(leaves)
+        elif ext == self.e:
+            self.L = [leaves[k] if _leaf_better(leaves[k], self.L[k], k) else self.L[k] for k in range(8)]
+        elif _near(self.side, self.e, ext):
+            if self.beyond(ext, self.e2):
+                self.e2, self.L2 = ext, list(leaves)
+            elif ext == self.e2:
+                self.L2 = [leaves[k] if _leaf_better(leaves[k], self.L2[k], k) else self.L2[k] for k in range(8)]
+
+    def merge(self, other):
+        self.insert(other.e, other.L)
+        self.insert(other.e2, other.L2)
+
+    def chunk(self, u):
+        """lex_side_update: one chunk of <= 32 rows (n, 4) against the running record"""
+        side = self.side
+        has2 = self.L2 is not None
+
+        def window_bound(a):
+            if not np.isfinite(a):
+                return a
+            x = np.float64(a)
+            for _ in range(K_NEAR):
+                x = np.nextafter(x, -np.inf if side == 0 else np.inf)
+            return float(x)
+
+        thr = self.e2 if has2 else window_bound(self.e)
+        reaches = (lambda x, y: x >= y) if side == 0 else (lambda x, y: x <= y)
+        hot = [i for i in range(len(u)) if reaches(u[i, 0], thr)]
+        for _level in range(2):
+            if not hot:
+                return
+            cm = max(u[i, 0] for i in hot) if side == 0 else min(u[i, 0] for i in hot)
+            tied = [i for i in hot if u[i, 0] == cm]
+            hot = [i for i in hot if u[i, 0] != cm]
+            leaves = _tie_leaves(u[tied][:, 1:])
+            if self.beyond(cm, self.e):
+                keep = _near(side, cm, self.e)
+                self.e2, self.L2 = (self.e, self.L) if keep else ((-np.inf if side == 0 else np.inf), None)
+                self.e, self.L = cm, leaves
+                has2 = keep
+                thr = self.e2 if keep else window_bound(cm)
+            elif cm == self.e:
+                self.L = [leaves[k] if _leaf_better(leaves[k], self.L[k], k) else self.L[k] for k in range(8)]
+            elif has2 and cm == thr:
+                self.L2 = [leaves[k] if _leaf_better(leaves[k], self.L2[k], k) else self.L2[k] for k in range(8)]
+            else:
+                self.e2, self.L2, has2, thr = cm, leaves, True, cm
+            hot = [i for i in hot if reaches(u[i, 0], thr)]
+
+    def state(self):
+        return (self.e, tuple(self.L) if self.L else None, self.e2 if self.L2 else None, tuple(self.L2) if self.L2 else None)
+
+
+def device_record(u, rng, chunk=32):
+    """rows -> chunks -> 'warps' (random runs of chunks) -> random merge tree, as blocks / groups / ranks would"""
+    chunks = [u[i:i + chunk] for i in range(0, len(u), chunk)]
+    warps = []
+    i = 0
+    while i < len(chunks):
+        n = int(rng.integers(1, 6))
+        recs = [SideRec(0), SideRec(1)]
+        for ch in chunks[i:i + n]:
+            for r in recs:
+                r.chunk(ch)
+        warps.append(recs)
+        i += n
+    order = rng.permutation(len(warps))
+    acc = [SideRec(0), SideRec(1)]
+    pending = [warps[k] for k in order]
+    while len(pending) > 1:                       # random pairwise merges (any tree, any order)
+        a = pending.pop(int(rng.integers(len(pending))))
+        b = pending.pop(int(rng.integers(len(pending))))
+        for s in range(2):
+            a[s].merge(b[s])
+        pending.append(a)
+    for s in range(2):
+        acc[s].merge(pending[0][s])
+    return acc
+
+
+def norms_from_device_record(rec, mean):
+    cands = []
+    for r in rec:
+        for ext, L in ((r.e, r.L), (r.e2, r.L2)):
+            if L is not None and np.isfinite(ext):
+                cands += [(ext,) + tuple(l) for l in L]
+    return lexmax_rows(np.abs(np.asarray(cands) - mean))
+
+
+def _adversarial_states(rng, n):
+    """densities on a one-ulp grid around both extremes (exact ties AND neighbours), momenta / energy on a few exact levels"""
+    hi, lo = 1.0 - 5 * 2.0 ** -53, 0.5 + 3 * 2.0 ** -53
+    u = np.stack([0.6 + 0.3 * rng.random(n), rng.integers(-3, 4, n) / 4.0, rng.integers(-2, 3, n) / 4.0, 30.0 + rng.integers(0, 3, n) / 2.0], axis=1)
+    for base, sgn in ((hi, -1.0), (lo, 1.0)):
+        idx = rng.choice(n, int(rng.integers(2, 40)), replace=False)
+        steps = rng.integers(0, 7, len(idx))       # 0 .. 6 ulps inside the extreme: inside and outside the window
+        vals = np.full(len(idx), base)
+        for k in range(6):
+            vals = np.where(steps > k, np.nextafter(vals, -np.inf if sgn < 0 else np.inf), vals)
+        u[idx, 0] = vals
+        u[idx, 1] = 1.0 + 1e-6 * rng.standard_normal(len(idx)) * (rng.random(len(idx)) < 0.7)   # some exact ties on m1 too
+    return u
+
+
+def test_device_bookkeeping_is_sufficient_and_order_independent():
+    rng = np.random.default_rng(21)
+    decided_by_second_level = 0
+    for trial in range(120):
+        n = int(rng.integers(40, 700))
+        u = _adversarial_states(rng, n)
+        rec = device_record(u, rng)
+        again = device_record(u[rng.permutation(n)], rng)      # other chunks, other warps, another merge tree
+        assert [r.state() for r in rec] == [r.state() for r in again], trial
+        base = u.sum(axis=0) / (4.0 * n)
+        for k in range(-6, 7):                                 # sweep the last bits of the mean: collisions come and go
+            mean = base.copy()
+            mean[0] = base[0] + k * 2.0 ** -56
+            want = brute(u, mean)
+            got = norms_from_device_record(rec, mean)
+            assert np.array_equal(got, want), (trial, k, got, want)
+            one = norms_from_leaves(leaves(u), mean)
+            decided_by_second_level += not np.array_equal(one, want)
+    assert decided_by_second_level > 0      # the sweep really contains cases that one density level gets wrong
